@@ -1,0 +1,3 @@
+class VelocityVerlet:
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError('MD is outside the hot path (shim)')
