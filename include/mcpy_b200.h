@@ -1,0 +1,152 @@
+/* mcpy_b200.h -- C ABI of the B200-native energy-and-move engine for mcpy.
+ *
+ * This header is the drop-in boundary.  Every entry point
+ * takes plain pointers and sizes; there are no torch / numpy / ASE types.  The
+ * reference (farrisric/mcpy v1.4.0) is pure Python, so the binding a maintainer
+ * adds on the reference side is a ctypes stub -- shown in INTEGRATION.md and
+ * shipped as mcpy_b200/_lib.py.
+ *
+ * Conventions
+ *   - All functions return 0 on success or a negative mcpyb_status; the message is
+ *     available from mcpyb_last_error(engine).  Nothing falls back to the CPU.
+ *   - "_host" entry points take host buffers and include the host<->device
+ *     copies (this is the end-to-end path).  "_dev" entry points take device
+ *     pointers, enqueue on the engine's stream and do not synchronise.
+ *   - positions are fp64, row-major [n][3], Angstrom (ase.Atoms.positions);
+ *     numbers are int32 atomic numbers; cell is the row-major 3x3 lattice
+ *     (np.asarray(atoms.cell)); pbc is 3 bytes.
+ *   - A "batch" is R configurations (replicas) concatenated; atom_off[R+1]
+ *     delimits them.  R = 1 is the single-GCMC case.
+ */
+#ifndef MCPY_B200_H
+#define MCPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcpyb_engine mcpyb_engine;
+
+typedef enum {
+    MCPYB_OK = 0,
+    MCPYB_ERR_CUDA = -1,        /* a CUDA runtime call failed                      */
+    MCPYB_ERR_ARG = -2,         /* invalid argument (ValueError on the Python side) */
+    MCPYB_ERR_STATE = -3,       /* call sequence error (no potential / no batch)   */
+    MCPYB_ERR_SPECIES = -4,     /* atomic number without parameters                */
+    MCPYB_ERR_GEOMETRY = -5,    /* atom more than 511 boxes away / singular cell   */
+    MCPYB_ERR_CAPACITY = -6     /* internal capacity exceeded                      */
+} mcpyb_status;
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* Create an engine on CUDA device `device` (fails if there is no such GPU).  */
+int mcpyb_create(int device, mcpyb_engine** out);
+void mcpyb_destroy(mcpyb_engine* e);
+const char* mcpyb_last_error(const mcpyb_engine* e);
+const char* mcpyb_version(void);
+/* Use an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream).
+ * NULL restores the engine's own stream.                                      */
+int mcpyb_set_stream(mcpyb_engine* e, void* cuda_stream);
+int mcpyb_synchronize(mcpyb_engine* e);
+
+/* ---- potentials --------------------------------------------------------- */
+/* ase.calculators.lj.LennardJones(sigma, epsilon, rc, smooth=False); rc <= 0
+ * selects ASE's default 3*sigma.  (Reference call sites:
+ * examples/gcmc_molecule.py:27-31, benchmark/lammps_gcmc_parity.py:197.)      */
+int mcpyb_set_lj(mcpyb_engine* e, double epsilon, double sigma, double rc);
+/* ase.calculators.emt.EMT() with the default parameter table, asap_cutoff=False.
+ * (Reference call sites: tests/test_canonical_nvt.py:26,
+ * docs/examples/gcmc_simulations.rst:31.)                                      */
+int mcpyb_set_emt(mcpyb_engine* e);
+/* Neighbour cutoff in use: LJ rc, EMT rc_list.                               */
+double mcpyb_cutoff(const mcpyb_engine* e);
+/* Derived EMT constants for atomic number Z: out9 = E0,s0,V0,eta2,kappa,lambda,
+ * n0,gamma1,gamma2 (tests compare them with the oracle's).                    */
+int mcpyb_emt_species(const mcpyb_engine* e, int Z, double* out9);
+
+/* ---- total energies: replaces calculator.get_potential_energy(atoms)
+ *      (mcpy/ensembles/base_ensemble.py:190-191) and
+ *      calculator.get_potential_energies(atoms_list)
+ *      (mcpy/ensembles/batched_replica_exchange.py:202,278) ------------------ */
+/* Upload R configurations from host memory, build their cell lists (resident
+ * in HBM afterwards).                                                         */
+int mcpyb_upload_host(mcpyb_engine* e, int R, const int64_t* atom_off,
+                      const double* positions, const int32_t* numbers,
+                      const double* cells /* [R][9] */, const uint8_t* pbc /* [R][3] */);
+/* Same from device memory (positions/numbers device pointers; the small
+ * atom_off / cells / pbc arrays stay on the host).                            */
+int mcpyb_upload_dev(mcpyb_engine* e, int R, const int64_t* atom_off,
+                     const double* d_positions, const int32_t* d_numbers,
+                     const double* cells, const uint8_t* pbc);
+/* Energies of the resident batch -> host array [R] (synchronises).
+ * pairs_out (may be NULL) receives the number of unordered in-cutoff pairs.   */
+int mcpyb_energies_host(mcpyb_engine* e, double* energies_out, int64_t* pairs_out);
+/* Energies of the resident batch -> device array [R], no synchronisation.    */
+int mcpyb_energies_dev(mcpyb_engine* e, double* d_energies_out);
+/* upload + energies in one call: the whole plug-in call with host buffers.   */
+int mcpyb_potential_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off,
+                                  const double* positions, const int32_t* numbers,
+                                  const double* cells, const uint8_t* pbc,
+                                  double* energies_out);
+/* Per-atom energies of the resident batch (ASE's results['energies']) and, for
+ * EMT, the density sums sigma1; either pointer may be NULL. Host arrays [sum N]. */
+int mcpyb_atom_energies_host(mcpyb_engine* e, double* e_atom_out, double* sigma1_out);
+
+/* ---- trial moves: delta E = E(trial) - E(resident)
+ *      (mcpy/ensembles/grand_canonical_ensemble.py:283-284) ------------------
+ * Trial t acts on replica rep[t] (rep may be NULL: replica 0).  It removes the
+ * atoms old_idx[old_off[t]..old_off[t+1]) (indices inside the replica) and adds
+ * atoms at new_pos[new_off[t]..new_off[t+1]) with atomic numbers new_Z (may be
+ * NULL for LJ).  Displacement / rigid-molecule move: both lists, same length;
+ * insertion: new only; deletion: old only.  At most 32 atoms per list.
+ * pairs_out (may be NULL): in-cutoff (moved atom, neighbour) pairs evaluated.  */
+int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep,
+                             const int32_t* old_off, const int32_t* old_idx,
+                             const int32_t* new_off, const double* new_pos,
+                             const int32_t* new_Z,
+                             double* dE_out, int32_t* pairs_out);
+int mcpyb_trial_delta_e_dev(mcpyb_engine* e, int T, const int32_t* d_rep,
+                            const int32_t* d_old_off, const int32_t* d_old_idx,
+                            const int32_t* d_new_off, const double* d_new_pos,
+                            const int32_t* d_new_Z, int n_old_total, int n_new_total,
+                            double* d_dE_out, int32_t* d_pairs_out);
+
+/* ---- neighbour list (bit-exactness check; oracle/neighbors.py) -------------
+ * Lists every image (i, j, S) of replica `rep` of the resident batch with
+ * mode 0: r2 < cutoff^2, 1: r2 <= cutoff^2, 2: sqrt(r2) < cutoff.  cutoff must
+ * not exceed mcpyb_cutoff().  Returns the number of pairs found in *npairs
+ * (may exceed max_pairs: then only max_pairs were written).                   */
+int mcpyb_neighbor_pairs_host(mcpyb_engine* e, int rep, double cutoff, int mode,
+                              int64_t max_pairs, int32_t* i_out, int32_t* j_out,
+                              int32_t* S_out /* [max_pairs][3] */, double* r2_out,
+                              int64_t* npairs);
+
+/* ---- free volume: replaces the cKDTree loops of
+ *      SphericalCell.calculate_volume (mcpy/cell/spherical_cell.py:127-140) and
+ *      CustomCell.calculate_volume (mcpy/cell/custom_cell.py:80-89) -----------
+ * Spheres are (positions[a] - offset) + shifts[s] for every atom a with
+ * radii[a] > 0 and every image shift s < nshift (custom_cell.py:93-107; pass
+ * nshift = 1, shift = 0, offset = 0 for the spherical cell).  A point is covered
+ * iff (dx*dx+dy*dy)+dz*dz < r*r for some sphere.  counts_out[0] = free points,
+ * counts_out[1] = covered points.  covered_out (may be NULL): per-point mask.  */
+int mcpyb_free_volume_count_host(mcpyb_engine* e, const double* points, int64_t P,
+                                 const double* positions, const double* radii, int64_t M,
+                                 const double* offset3, const double* shifts, int nshift,
+                                 int64_t* counts_out, uint8_t* covered_out);
+int mcpyb_free_volume_count_dev(mcpyb_engine* e, const double* d_points, int64_t P,
+                                const double* d_positions, const double* d_radii, int64_t M,
+                                const double* offset3, const double* shifts, int nshift,
+                                uint64_t* d_counts2);
+
+/* ---- instrumentation ---------------------------------------------------- */
+/* Measured FP64 FMA throughput of this GPU (TFLOP/s, 2 flop per DFMA): the
+ * roofline denominator for the pair kernels.                                 */
+int mcpyb_fp64_peak_tflops(mcpyb_engine* e, double* tflops_out);
+/* Number of kernels this engine has launched since creation.                 */
+int64_t mcpyb_launch_count(const mcpyb_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCPY_B200_H */

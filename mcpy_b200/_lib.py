@@ -1,0 +1,111 @@
+"""ctypes binding of the C ABI in ``include/mcpy_b200.h``.
+
+This is the reference-side stub INTEGRATION.md describes: mcpy is pure Python
+(``pyproject.toml:29-34`` has no extension modules), so the binding a maintainer
+adds is a ctypes loader.  There is deliberately no fallback: if the CUDA
+library is missing or no GPU is present the import of the library / creation
+of an engine raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmcpy_b200.so')
+
+# Every symbol include/mcpy_b200.h declares (tests check the library exports all of them).
+SYMBOLS = [
+    'mcpyb_create', 'mcpyb_destroy', 'mcpyb_last_error', 'mcpyb_version', 'mcpyb_set_stream',
+    'mcpyb_synchronize', 'mcpyb_set_lj', 'mcpyb_set_emt', 'mcpyb_cutoff', 'mcpyb_emt_species',
+    'mcpyb_upload_host', 'mcpyb_upload_dev', 'mcpyb_energies_host', 'mcpyb_energies_dev',
+    'mcpyb_potential_energies_host', 'mcpyb_atom_energies_host',
+    'mcpyb_trial_delta_e_host', 'mcpyb_trial_delta_e_dev',
+    'mcpyb_neighbor_pairs_host',
+    'mcpyb_free_volume_count_host', 'mcpyb_free_volume_count_dev',
+    'mcpyb_fp64_peak_tflops', 'mcpyb_launch_count',
+]
+
+_p = C.c_void_p
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    """A call into libmcpy_b200 failed (CUDA error or internal capacity)."""
+
+
+def load():
+    """Load ``libmcpy_b200.so``; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f'{LIB_PATH} is missing. The mcpy_b200 engine is CUDA-only: build it with '
+            '`python -m mcpy_b200.build` (needs nvcc); there is no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    lib.mcpyb_create.argtypes = [C.c_int, C.POINTER(_p)]
+    lib.mcpyb_destroy.argtypes = [_p]
+    lib.mcpyb_destroy.restype = None
+    lib.mcpyb_last_error.argtypes = [_p]
+    lib.mcpyb_last_error.restype = C.c_char_p
+    lib.mcpyb_version.restype = C.c_char_p
+    lib.mcpyb_set_stream.argtypes = [_p, _p]
+    lib.mcpyb_synchronize.argtypes = [_p]
+    lib.mcpyb_set_lj.argtypes = [_p, C.c_double, C.c_double, C.c_double]
+    lib.mcpyb_set_emt.argtypes = [_p]
+    lib.mcpyb_cutoff.argtypes = [_p]
+    lib.mcpyb_cutoff.restype = C.c_double
+    lib.mcpyb_emt_species.argtypes = [_p, C.c_int, _f64p]
+    lib.mcpyb_upload_host.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p]
+    lib.mcpyb_upload_dev.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p]
+    lib.mcpyb_energies_host.argtypes = [_p, _p, _p]
+    lib.mcpyb_energies_dev.argtypes = [_p, _p]
+    lib.mcpyb_potential_energies_host.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p, _p]
+    lib.mcpyb_atom_energies_host.argtypes = [_p, _p, _p]
+    lib.mcpyb_trial_delta_e_host.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p]
+    lib.mcpyb_trial_delta_e_dev.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, _p, _p]
+    lib.mcpyb_neighbor_pairs_host.argtypes = [_p, C.c_int, C.c_double, C.c_int, C.c_int64,
+                                              _p, _p, _p, _p, _i64p]
+    lib.mcpyb_free_volume_count_host.argtypes = [_p, _p, C.c_int64, _p, _p, C.c_int64, _p, _p,
+                                                 C.c_int, _p, _p]
+    lib.mcpyb_free_volume_count_dev.argtypes = [_p, _p, C.c_int64, _p, _p, C.c_int64, _p, _p,
+                                                C.c_int, _p]
+    lib.mcpyb_fp64_peak_tflops.argtypes = [_p, _f64p]
+    lib.mcpyb_launch_count.argtypes = [_p]
+    lib.mcpyb_launch_count.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+def ptr(a):
+    """Raw address of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    return a.ctypes.data
+
+
+def as_f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def as_i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def as_u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)

@@ -1,0 +1,172 @@
+"""``B200Calculator`` -- LJ / EMT energies on a B200 behind mcpy's calculator API.
+
+The drop-in boundary:
+
+* ``get_potential_energy(atoms) -> float`` -- the sole call the ensembles make
+  (``mcpy/ensembles/base_ensemble.py:190-191``, used at
+  ``grand_canonical_ensemble.py:56,283``);
+* ``get_potential_energies(atoms_list, chunk_size=None) -> ndarray`` -- the batched
+  contract of ``BatchedReplicaExchange`` (checked at
+  ``batched_replica_exchange.py:98-102``, called at ``:202,278``; reference
+  implementation ``alchemi_calculator.py:118-155``: empty list -> ``np.empty(0)``,
+  ``chunk_size`` caps the structures per pass);
+* the ASE ``Calculator`` protocol (``calculate`` / ``results`` /
+  ``implemented_properties``) so ``atoms.calc = calc; atoms.get_potential_energy()``
+  works (``mcpy/calculators/base_calculator.py:19-22``,
+  ``canonical_ensemble.py:117-121``).  Forces are not implemented (SURVEY.md 8f
+  row f1), so optimisers raise ``PropertyNotImplementedError`` as ASE does for
+  any energy-only calculator.
+
+Beyond the reference interface, :meth:`trial_delta_energies` exposes the
+batched trial-move kernel (many proposed insertions / deletions / displacements
+scored against one resident configuration in one launch).
+
+``atoms`` is never mutated.  Non-finite energies are returned, not raised
+(``batched_replica_exchange.py:354-362`` handles them).  Nothing here computes
+on the CPU: without the CUDA library or a GPU, construction raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..engine import Engine
+from ..utils.chunking import chunk_ranges
+
+try:                                     # real ASE (or the test shim) when importable
+    from ase.calculators.calculator import Calculator as _AseCalculator
+    from ase.calculators.calculator import all_changes as _all_changes
+except Exception:                        # pragma: no cover - plain duck-typed use
+    _AseCalculator = None
+    _all_changes = ['positions', 'numbers', 'cell', 'pbc', 'initial_charges', 'initial_magmoms']
+
+
+def _config_of(atoms):
+    """(positions, numbers, cell 3x3, pbc) views of an ASE-like ``Atoms``."""
+    pos = np.asarray(atoms.positions, dtype=np.float64)
+    num = np.asarray(atoms.numbers, dtype=np.int32)
+    cell = np.asarray(atoms.cell, dtype=np.float64).reshape(3, 3)
+    pbc = np.asarray(atoms.pbc, dtype=bool).reshape(3)
+    return pos, num, cell, pbc
+
+
+class _B200Core:
+    """Plug-in methods shared by the ASE-derived and the plain class."""
+
+    implemented_properties = ['energy', 'free_energy']
+
+    def _init_engine(self, potential, epsilon, sigma, rc, device, chunk_size):
+        potential = str(potential).lower()
+        if potential not in ('lj', 'lennardjones', 'emt'):
+            raise ValueError(f"potential must be 'lj' or 'emt', got {potential!r}")
+        if chunk_size is not None and chunk_size <= 0:
+            raise ValueError(f'chunk_size must be a positive int or None, got {chunk_size}')
+        self.potential = 'emt' if potential == 'emt' else 'lj'
+        self.chunk_size = chunk_size
+        self.engine = Engine(device)
+        if self.potential == 'lj':
+            self.engine.set_lj(epsilon=epsilon, sigma=sigma, rc=rc)
+            self.lj_parameters = {'epsilon': float(epsilon), 'sigma': float(sigma),
+                                  'rc': self.engine.cutoff}
+        else:
+            self.engine.set_emt()
+        self.n_energy_calls = 0
+
+    # -- mcpy calculator interface -------------------------------------------
+    def get_potential_energy(self, atoms=None, force_consistent=False) -> float:
+        """Total potential energy of ``atoms`` (not mutated)."""
+        if atoms is None:
+            atoms = getattr(self, 'atoms', None)
+            if atoms is None:
+                raise ValueError('get_potential_energy() needs an Atoms object')
+        pos, num, cell, pbc = _config_of(atoms)
+        self.n_energy_calls += 1
+        return float(self.engine.potential_energies([pos], [num], cell.reshape(1, 9),
+                                                    pbc.reshape(1, 3))[0])
+
+    def get_potential_energies(self, atoms_list, chunk_size=None) -> np.ndarray:
+        """Energies of several (ragged) structures, one batched launch per chunk."""
+        if not atoms_list:
+            return np.empty(0, dtype=np.float64)
+        cs = self.chunk_size if chunk_size is None else chunk_size
+        out = []
+        for start, stop in chunk_ranges(len(atoms_list), cs):
+            cfg = [_config_of(a) for a in atoms_list[start:stop]]
+            cells = np.stack([c[2].reshape(9) for c in cfg])
+            pbcs = np.stack([c[3] for c in cfg])
+            out.append(self.engine.potential_energies([c[0] for c in cfg], [c[1] for c in cfg],
+                                                      cells, pbcs))
+            self.n_energy_calls += stop - start
+        return np.concatenate(out)
+
+    # -- batched trial moves (beyond the reference interface) ------------------
+    def set_configuration(self, atoms):
+        """Make ``atoms`` the resident configuration trial moves are scored against."""
+        pos, num, cell, pbc = _config_of(atoms)
+        self.engine.upload([pos], [num], cell.reshape(1, 9), pbc.reshape(1, 3))
+
+    def set_configurations(self, atoms_list):
+        cfg = [_config_of(a) for a in atoms_list]
+        self.engine.upload([c[0] for c in cfg], [c[1] for c in cfg],
+                           np.stack([c[2].reshape(9) for c in cfg]), np.stack([c[3] for c in cfg]))
+
+    def trial_delta_energies(self, trials, rep=None, return_pairs=False):
+        """dE of each trial against the resident configuration(s).
+
+        ``trials`` is a sequence of ``(old_indices, new_positions, new_numbers)``:
+        displacement -> both, insertion -> ``([], pos, Z)``, deletion -> ``(idx, [], [])``.
+        """
+        old_off, new_off = [0], [0]
+        old_idx, new_pos, new_Z = [], [], []
+        for old, pos, Z in trials:
+            old = np.atleast_1d(np.asarray(old, dtype=np.int32)) if np.size(old) else np.zeros(0, np.int32)
+            pos = np.asarray(pos, dtype=np.float64).reshape(-1, 3)
+            Z = np.atleast_1d(np.asarray(Z, dtype=np.int32)) if np.size(Z) else np.zeros(0, np.int32)
+            if len(Z) != len(pos):
+                raise ValueError('one atomic number per new position is required')
+            old_idx.append(old); new_pos.append(pos); new_Z.append(Z)
+            old_off.append(old_off[-1] + len(old)); new_off.append(new_off[-1] + len(pos))
+        cat = lambda xs, shape, dt: (np.concatenate(xs) if xs else np.zeros(shape, dt))
+        return self.engine.trial_delta_e(old_off, cat(old_idx, 0, np.int32), new_off,
+                                         cat(new_pos, (0, 3), np.float64), cat(new_Z, 0, np.int32),
+                                         rep=rep, return_pairs=return_pairs)
+
+
+if _AseCalculator is not None:
+
+    class B200Calculator(_B200Core, _AseCalculator):
+        __doc__ = __doc__
+        implemented_properties = ['energy', 'free_energy']
+        nolabel = True
+
+        def __init__(self, potential='lj', epsilon=1.0, sigma=1.0, rc=None, device=0,
+                     chunk_size=None, **kwargs):
+            _AseCalculator.__init__(self, **kwargs)
+            self._init_engine(potential, epsilon, sigma, rc, device, chunk_size)
+
+        def calculate(self, atoms=None, properties=('energy',), system_changes=_all_changes):
+            _AseCalculator.calculate(self, atoms, properties, system_changes)
+            e = _B200Core.get_potential_energy(self, self.atoms)
+            self.results['energy'] = e
+            self.results['free_energy'] = e
+
+        def get_potential_energy(self, atoms=None, force_consistent=False):
+            # Straight to the engine: mcpy calls this once per trial on a mutated
+            # Atoms, so ASE's result cache (one atoms.copy() + compare per call)
+            # would only add host overhead.
+            return _B200Core.get_potential_energy(self, atoms)
+
+else:
+
+    class B200Calculator(_B200Core):
+        __doc__ = __doc__
+
+        def __init__(self, potential='lj', epsilon=1.0, sigma=1.0, rc=None, device=0,
+                     chunk_size=None, **kwargs):
+            self.results = {}
+            self.atoms = None
+            self._init_engine(potential, epsilon, sigma, rc, device, chunk_size)
+
+        def calculate(self, atoms=None, properties=('energy',), system_changes=_all_changes):
+            self.atoms = atoms
+            e = self.get_potential_energy(atoms)
+            self.results = {'energy': e, 'free_energy': e}

@@ -1,0 +1,4 @@
+"""Sampling-region cells with device free volume (boundary of ``mcpy/cell``)."""
+from .b200_cells import B200SphericalCell, B200CustomCell  # noqa: F401
+
+__all__ = ['B200SphericalCell', 'B200CustomCell']

@@ -1,0 +1,197 @@
+// K1 -- counting-sort cell list, one CTA per replica.
+//
+// Replaces the neighbour search structure the reference rebuilds inside
+// ase.neighborlist.NeighborList (ASE 3.23.0, reached from
+// mcpy/ensembles/base_ensemble.py:190-191) whenever the atom count changes.
+// Steps, all inside one kernel so a rebuild costs one launch:
+//   pack   : raw (x,y,z) + atomic number -> double4 with tag (index, species)
+//   bbox   : fractional min/max along non-periodic axes (block reduction)
+//   grid   : cells per axis = floor(width / rcut'), rcut' = rcut*(1+1e-12)
+//   hash   : per-atom cell id + periodic wrap counts, shared/global histogram
+//   scan   : exclusive prefix sum of the histogram -> cell_start
+//   scatter: atoms to their cell segment
+//   order  : each segment sorted by atom index, so the layout (and therefore
+//            every floating-point sum taken over it) is deterministic.
+#pragma once
+#include "common.cuh"
+
+#define CL_THREADS 1024
+
+__device__ __forceinline__ double block_reduce_minmax(double v, bool is_min, double* sm) {
+    // sm: at least 32 doubles
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_min ? fmin(v, u) : fmax(v, u);
+    }
+    __syncthreads();
+    if (lane == 0) sm[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double r = sm[0];
+    for (int i = 1; i < nw; ++i) r = is_min ? fmin(r, sm[i]) : fmax(r, sm[i]);
+    return r;
+}
+
+// raw_pos: [sum N][3] doubles, raw_Z: [sum N] int32, atom_off: [R+1] ints, geom: [R]
+__global__ void __launch_bounds__(CL_THREADS, 1)
+build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
+                       const int* __restrict__ raw_Z, const int* __restrict__ atom_off,
+                       const CellGeom* __restrict__ geom, const int* __restrict__ z_to_slot,
+                       double rcut) {
+    __shared__ double s_red[32];
+    __shared__ int s_scan[CL_THREADS];
+    __shared__ int s_carry;
+    __shared__ int s_err;
+    const int r = blockIdx.x;
+    const int tid = threadIdx.x;
+    GridDesc& g = b.grid[r];
+    const int off = atom_off[r];
+    const int n = atom_off[r + 1] - off;
+    const CellGeom& cg = geom[r];
+    if (tid == 0) s_err = 0;
+
+    // ---- lattice into the device descriptor
+    if (tid < 9) { g.cell[tid] = cg.cell[tid]; g.inv[tid] = cg.inv[tid]; }
+    if (tid < 3) { g.height[tid] = cg.height[tid]; g.pbc[tid] = cg.pbc[tid]; }
+    if (tid == 0) { g.ortho = cg.ortho; g.n = n; g.atom_off = off; }
+    __syncthreads();
+
+    // ---- pack + bounding box in fractional coordinates (non-periodic axes)
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double x = raw_pos[3 * (size_t)(off + i) + 0];
+        const double y = raw_pos[3 * (size_t)(off + i) + 1];
+        const double z = raw_pos[3 * (size_t)(off + i) + 2];
+        int sp = 0;
+        if (raw_Z != nullptr && z_to_slot != nullptr) {
+            const int Z = raw_Z[off + i];
+            sp = (Z >= 0 && Z < 120) ? z_to_slot[Z] : -1;
+            if (sp < 0) { atomicOr(&s_err, 2); sp = 0; }
+        }
+        b.upos[off + i] = make_double4(x, y, z, make_tag(i, sp, pack_wraps(0, 0, 0)));
+        double f[3];
+        to_frac(g, x, y, z, f);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { lo[d] = fmin(lo[d], f[d]); hi[d] = fmax(hi[d], f[d]); }
+    }
+    double glo[3], ghi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        glo[d] = block_reduce_minmax(lo[d], true, s_red);
+        ghi[d] = block_reduce_minmax(hi[d], false, s_red);
+    }
+
+    // ---- binning grid (thread 0), capped at max_cells
+    if (tid == 0) {
+        const double rc_safe = rcut * (1.0 + 1e-12);
+        double want[3];
+        for (int d = 0; d < 3; ++d) {
+            double width_frac;
+            if (g.pbc[d]) { g.lo[d] = 0.0; width_frac = 1.0; }
+            else if (n > 0) { g.lo[d] = glo[d]; width_frac = ghi[d] - glo[d]; }
+            else { g.lo[d] = 0.0; width_frac = 0.0; }
+            const double width = width_frac * g.height[d];        // Angstrom, perpendicular
+            double nc = floor(width / rc_safe);
+            if (!(nc >= 1.0)) nc = 1.0;
+            if (nc > 1024.0) nc = 1024.0;
+            want[d] = nc;
+            // stencil half width: 1, or the number of periodic images a thin box needs
+            int m = 1;
+            if (g.pbc[d] && width < rc_safe) m = (int)ceil(rc_safe / width);
+            g.m[d] = m;
+            g.scale[d] = 0.0;   // set below
+            // stash width_frac in scale for the second pass
+            g.scale[d] = width_frac;
+        }
+        double total = want[0] * want[1] * want[2];
+        if (total > (double)b.max_cells) {
+            const double f = cbrt((double)b.max_cells / total);
+            for (int d = 0; d < 3; ++d) want[d] = fmax(1.0, floor(want[d] * f));
+            // flooring can still overshoot by rounding; shave the largest axis
+            while (want[0] * want[1] * want[2] > (double)b.max_cells) {
+                int k = 0;
+                if (want[1] > want[k]) k = 1;
+                if (want[2] > want[k]) k = 2;
+                want[k] -= 1.0;
+            }
+        }
+        for (int d = 0; d < 3; ++d) {
+            g.ncell[d] = (int)want[d];
+            const double width_frac = g.scale[d];
+            g.scale[d] = (width_frac > 0.0) ? want[d] / width_frac : 0.0;
+        }
+        g.ncells = g.ncell[0] * g.ncell[1] * g.ncell[2];
+    }
+    __syncthreads();
+
+    const int ncells = g.ncells;
+    int* cstart = b.cell_start + (size_t)r * b.cs_stride;
+    for (int c = tid; c <= ncells; c += blockDim.x) cstart[c] = 0;
+    __syncthreads();
+
+    // ---- hash: cell id + wrap counts, histogram in cstart[c + 1]
+    for (int i = tid; i < n; i += blockDim.x) {
+        double4 q = b.upos[off + i];
+        int c[3], w[3];
+        if (!locate(g, q.x, q.y, q.z, c, w)) atomicOr(&s_err, 4);
+        const long long t = tag_of(q);
+        q.w = make_tag(i, tag_species(t), pack_wraps(w[0], w[1], w[2]));
+        b.upos[off + i] = q;
+        const int id = (c[2] * g.ncell[1] + c[1]) * g.ncell[0] + c[0];
+        b.cid[off + i] = id;
+        atomicAdd(&cstart[id + 1], 1);
+    }
+    __syncthreads();
+
+    // ---- exclusive scan of cstart[1..ncells] (chunked block scan)
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ncells; base += blockDim.x) {
+        const int c = base + tid;
+        const int v = (c < ncells) ? cstart[c + 1] : 0;
+        s_scan[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+            int t = (tid >= o) ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += t;
+            __syncthreads();
+        }
+        const int incl = s_scan[tid] + s_carry;
+        __syncthreads();
+        if (c < ncells) cstart[c + 1] = incl;          // inclusive -> start of next cell
+        if (tid == blockDim.x - 1) s_carry = incl;
+        __syncthreads();
+    }
+    // cstart[c] is now the first slot of cell c (cstart[0] = 0, cstart[ncells] = n)
+
+    // ---- scatter; the per-cell cursors live in the second half of this replica's region
+    int* cursor = cstart + (b.max_cells + 1);
+    for (int c = tid; c < ncells; c += blockDim.x) cursor[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int id = b.cid[off + i];
+        const int slot = cstart[id] + atomicAdd(&cursor[id], 1);
+        b.spos[off + slot] = b.upos[off + i];
+    }
+    __syncthreads();
+
+    // ---- order each segment by atom index (insertion sort, one thread per cell)
+    for (int c = tid; c < ncells; c += blockDim.x) {
+        const int s = cstart[c], e = cstart[c + 1];
+        for (int a = s + 1; a < e; ++a) {
+            const double4 key = b.spos[off + a];
+            const int ki = tag_index(tag_of(key));
+            int p = a - 1;
+            while (p >= s && tag_index(tag_of(b.spos[off + p])) > ki) {
+                b.spos[off + p + 1] = b.spos[off + p];
+                --p;
+            }
+            b.spos[off + p + 1] = key;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) g.error = s_err;
+}

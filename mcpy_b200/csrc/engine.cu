@@ -1,0 +1,855 @@
+// Host side of the engine and the C ABI declared in include/mcpy_b200.h.
+// One translation unit: every kernel is included here so the library is a single
+// nvcc -shared build for sm_100a (see mcpy_b200/build.py).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mcpy_b200.h"
+#include "common.cuh"
+#include "cell_list.cuh"
+#include "stencil.cuh"
+#include "lj_kernels.cuh"
+#include "emt_kernels.cuh"
+#include "free_volume.cuh"
+
+// FP64 pipe microbenchmark: 8 independent DFMA chains per thread (roofline denominator
+// for the pair kernels; MEASURED_PEAKS.json only has HBM and bf16 numbers).
+__global__ void __launch_bounds__(256)
+fp64_fma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        size_t want = cap ? cap : 256;
+        while (want < n) want *= 2;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+    unsigned char* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        size_t want = cap ? cap : 4096;
+        while (want < n) want *= 2;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost((void**)&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- EMT constants (ase.calculators.emt) -----------------
+struct EmtRow { int Z; double E0, s0, V0, eta2, kappa, lambda, n0; };
+const EmtRow kEmtRows[] = {
+    {1,  -3.21, 1.31, 0.132, 2.652, 2.790, 3.892, 0.00547},   // H
+    {6,  -3.50, 1.81, 0.332, 1.652, 2.790, 1.892, 0.01322},   // C
+    {7,  -5.10, 1.88, 0.132, 1.652, 2.790, 1.892, 0.01222},   // N
+    {8,  -4.60, 1.95, 0.332, 1.652, 2.790, 1.892, 0.00850},   // O
+    {13, -3.28, 3.00, 1.493, 1.240, 2.000, 1.169, 0.00700},   // Al
+    {28, -4.44, 2.60, 3.673, 1.669, 2.757, 1.948, 0.01030},   // Ni
+    {29, -3.51, 2.67, 2.476, 1.652, 2.740, 1.906, 0.00910},   // Cu
+    {46, -3.90, 2.87, 2.773, 1.818, 3.107, 2.155, 0.00688},   // Pd
+    {47, -2.96, 3.01, 2.132, 1.652, 2.790, 1.892, 0.00547},   // Ag
+    {78, -5.85, 2.90, 4.067, 1.812, 3.145, 2.192, 0.00802},   // Pt
+    {79, -3.80, 3.00, 2.321, 1.674, 2.873, 2.182, 0.00703},   // Au
+};
+const double kBohr = 0.52917721067;
+const double kEmtBeta = 1.809;
+
+}  // namespace
+
+struct mcpyb_engine {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    // potential
+    int pot_kind = POT_NONE;
+    double rcut = 0.0;
+    LJParams lj{};
+    EmtTable emt_host{};
+    DevBuf<EmtTable> emt_dev;
+    int z_to_slot_host[120];
+    DevBuf<int> z_to_slot;
+
+    // resident batch
+    int R = 0;
+    int total_atoms = 0;
+    int max_cells = 0;
+    bool have_batch = false;
+    bool emt_state_valid = false;     // sigma1 / e_atom describe the resident batch
+    std::vector<int> atom_off_host;
+    DevBuf<GridDesc> grid;
+    DevBuf<double4> upos, spos;
+    DevBuf<int> cid, cell_start, atom_off;
+    DevBuf<CellGeom> geom;
+    DevBuf<double> e_atom, sigma1, E;
+    DevBuf<int> pair_count, status;
+    DevBuf<long long> pairs;
+    DevBuf<unsigned char> stage_dev;      // H2D landing zone: header | positions | numbers
+    PinBuf stage_pin, out_pin;
+
+    // trial staging
+    DevBuf<unsigned char> trial_dev;
+    PinBuf trial_pin, trial_out_pin;
+    DevBuf<double> dE;
+    DevBuf<int> tpairs;
+
+    // neighbour list scratch
+    DevBuf<int> nl_i, nl_j, nl_S;
+    DevBuf<double> nl_r2;
+    DevBuf<unsigned long long> nl_cursor;
+
+    // free volume
+    DevBuf<FvGrid> fv_grid;
+    DevBuf<double4> fv_spheres;
+    DevBuf<int> fv_cell_start, fv_cursor, fv_cid;
+    DevBuf<double> fv_points, fv_pos, fv_radii, fv_small;   // fv_small: offset(3) + shifts(81)
+    DevBuf<unsigned long long> fv_counts;
+    DevBuf<unsigned char> fv_mask;
+    PinBuf fv_pin;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char* what) {
+        return fail(MCPYB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    BatchView view() {
+        BatchView v;
+        v.grid = grid.p; v.upos = upos.p; v.spos = spos.p; v.cell_start = cell_start.p;
+        v.cid = cid.p; v.R = R; v.max_cells = max_cells; v.cs_stride = 2 * (max_cells + 1);
+        return v;
+    }
+};
+
+#define CK(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) return e->cuda_fail(_e, what); } while (0)
+#define LAUNCH_CHECK(what) do { e->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return e->cuda_fail(_e, what); } while (0)
+
+namespace {
+
+// Lattice bookkeeping done once per upload on the host (9 numbers per replica).
+int make_geom(mcpyb_engine* e, const double* cell, const uint8_t* pbc, CellGeom* g) {
+    double c[3][3];
+    for (int i = 0; i < 9; ++i) c[i / 3][i % 3] = cell[i];
+    bool zero[3];
+    for (int d = 0; d < 3; ++d) {
+        zero[d] = (c[d][0] == 0.0 && c[d][1] == 0.0 && c[d][2] == 0.0);
+        if (zero[d] && pbc[d]) return e->fail(MCPYB_ERR_GEOMETRY, "periodic axis %d has a zero lattice vector", d);
+    }
+    auto cross = [](const double* a, const double* b, double* o) {
+        o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    auto norm = [](const double* a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+    // complete missing rows with unit vectors orthogonal to the others
+    int nzero = zero[0] + zero[1] + zero[2];
+    if (nzero == 3) {
+        for (int d = 0; d < 3; ++d) c[d][d] = 1.0;
+    } else if (nzero == 2) {
+        int k = !zero[0] ? 0 : (!zero[1] ? 1 : 2);
+        int a = (k + 1) % 3, b = (k + 2) % 3;
+        int imin = 0;
+        for (int i = 1; i < 3; ++i) if (fabs(c[k][i]) < fabs(c[k][imin])) imin = i;
+        double t[3] = {0, 0, 0};
+        t[imin] = 1.0;
+        double v[3];
+        cross(c[k], t, v);
+        double nv = norm(v);
+        for (int i = 0; i < 3; ++i) c[a][i] = v[i] / nv;
+        cross(c[k], c[a], v);
+        nv = norm(v);
+        for (int i = 0; i < 3; ++i) c[b][i] = v[i] / nv;
+    } else if (nzero == 1) {
+        int k = zero[0] ? 0 : (zero[1] ? 1 : 2);
+        double v[3];
+        cross(c[(k + 1) % 3], c[(k + 2) % 3], v);
+        double nv = norm(v);
+        if (nv == 0.0) return e->fail(MCPYB_ERR_GEOMETRY, "singular cell");
+        for (int i = 0; i < 3; ++i) c[k][i] = v[i] / nv;
+    }
+    const double det = c[0][0] * (c[1][1] * c[2][2] - c[1][2] * c[2][1])
+                     - c[0][1] * (c[1][0] * c[2][2] - c[1][2] * c[2][0])
+                     + c[0][2] * (c[1][0] * c[2][1] - c[1][1] * c[2][0]);
+    if (!(fabs(det) > 0.0) || !isfinite(det)) return e->fail(MCPYB_ERR_GEOMETRY, "singular cell");
+    // inverse: inv[j][d] with frac_d = sum_j p_j inv[j][d]  (p = frac @ cell)
+    double inv[3][3];
+    inv[0][0] = (c[1][1] * c[2][2] - c[1][2] * c[2][1]) / det;
+    inv[0][1] = (c[0][2] * c[2][1] - c[0][1] * c[2][2]) / det;
+    inv[0][2] = (c[0][1] * c[1][2] - c[0][2] * c[1][1]) / det;
+    inv[1][0] = (c[1][2] * c[2][0] - c[1][0] * c[2][2]) / det;
+    inv[1][1] = (c[0][0] * c[2][2] - c[0][2] * c[2][0]) / det;
+    inv[1][2] = (c[0][2] * c[1][0] - c[0][0] * c[1][2]) / det;
+    inv[2][0] = (c[1][0] * c[2][1] - c[1][1] * c[2][0]) / det;
+    inv[2][1] = (c[0][1] * c[2][0] - c[0][0] * c[2][1]) / det;
+    inv[2][2] = (c[0][0] * c[1][1] - c[0][1] * c[1][0]) / det;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { g->cell[3 * i + j] = c[i][j]; g->inv[3 * i + j] = inv[i][j]; }
+    for (int d = 0; d < 3; ++d) {
+        double v[3];
+        cross(c[(d + 1) % 3], c[(d + 2) % 3], v);
+        g->height[d] = fabs(det) / norm(v);
+        g->pbc[d] = pbc[d] ? 1 : 0;
+    }
+    g->ortho = (c[0][1] == 0 && c[0][2] == 0 && c[1][0] == 0 && c[1][2] == 0 && c[2][0] == 0 && c[2][1] == 0);
+    return MCPYB_OK;
+}
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// Reserve every per-batch device array.
+int reserve_batch(mcpyb_engine* e, int R, int total, int max_n) {
+    int mc = next_pow2(max_n > 0 ? max_n : 1);
+    if (mc < 512) mc = 512;
+    if (mc > 32768) mc = 32768;
+    if (mc > e->max_cells) e->max_cells = mc;
+    const size_t cs = 2 * (size_t)(e->max_cells + 1);
+    CK(e->grid.reserve(R), "cudaMalloc grid");
+    CK(e->geom.reserve(R), "cudaMalloc geom");
+    CK(e->atom_off.reserve(R + 1), "cudaMalloc atom_off");
+    CK(e->cell_start.reserve(cs * R), "cudaMalloc cell_start");
+    CK(e->E.reserve(R), "cudaMalloc E");
+    CK(e->status.reserve(R), "cudaMalloc status");
+    CK(e->pairs.reserve(R), "cudaMalloc pairs");
+    const size_t na = total > 0 ? total : 1;
+    CK(e->upos.reserve(na), "cudaMalloc upos");
+    CK(e->spos.reserve(na), "cudaMalloc spos");
+    CK(e->cid.reserve(na), "cudaMalloc cid");
+    CK(e->e_atom.reserve(na), "cudaMalloc e_atom");
+    CK(e->sigma1.reserve(na), "cudaMalloc sigma1");
+    CK(e->pair_count.reserve(na), "cudaMalloc pair_count");
+    return MCPYB_OK;
+}
+
+// Shared tail of the two upload paths: geometry + offsets to the device, one build launch.
+int upload_common(mcpyb_engine* e, int R, const int64_t* atom_off, const double* cells,
+                  const uint8_t* pbc, const double* d_pos, const int32_t* d_Z,
+                  const unsigned char* d_header) {
+    // d_header: [int atom_off[R+1]] padded to 16 | [CellGeom geom[R]]
+    const size_t off_bytes = align_up((size_t)(R + 1) * sizeof(int), 16);
+    const int* d_off = (const int*)d_header;
+    const CellGeom* d_geom = (const CellGeom*)(d_header + off_bytes);
+    (void)atom_off; (void)cells; (void)pbc;
+    build_cell_list_kernel<<<R, CL_THREADS, 0, e->stream>>>(
+        e->view(), d_pos, d_Z, d_off, d_geom, e->z_to_slot.p, e->rcut);
+    LAUNCH_CHECK("build_cell_list_kernel");
+    // keep a device copy of atom_off for the energy kernels
+    CK(cudaMemcpyAsync(e->atom_off.p, d_off, (size_t)(R + 1) * sizeof(int), cudaMemcpyDeviceToDevice,
+                       e->stream), "copy atom_off");
+    e->have_batch = true;
+    e->emt_state_valid = false;
+    return MCPYB_OK;
+}
+
+int validate_batch_args(mcpyb_engine* e, int R, const int64_t* atom_off, int* total, int* max_n) {
+    if (e->pot_kind == POT_NONE) return e->fail(MCPYB_ERR_STATE, "no potential set (call mcpyb_set_lj / mcpyb_set_emt)");
+    if (R < 0) return e->fail(MCPYB_ERR_ARG, "R must be >= 0");
+    if (R > 0 && !atom_off) return e->fail(MCPYB_ERR_ARG, "atom_off is NULL");
+    int mx = 0;
+    for (int r = 0; r < R; ++r) {
+        const int64_t n = atom_off[r + 1] - atom_off[r];
+        if (n < 0) return e->fail(MCPYB_ERR_ARG, "atom_off must be non-decreasing");
+        if (n > 0xFFFFFF) return e->fail(MCPYB_ERR_CAPACITY, "more than 16777215 atoms in one configuration");
+        if (n > mx) mx = (int)n;
+    }
+    if (R > 0 && atom_off[0] != 0) return e->fail(MCPYB_ERR_ARG, "atom_off[0] must be 0");
+    const int64_t tot = R > 0 ? atom_off[R] : 0;
+    if (tot > 0x7FFFFFF0) return e->fail(MCPYB_ERR_CAPACITY, "batch too large");
+    *total = (int)tot;
+    *max_n = mx;
+    return MCPYB_OK;
+}
+
+// Fill the pinned header (atom_off as int32 + geometry) for an upload.
+int fill_header(mcpyb_engine* e, int R, const int64_t* atom_off, const double* cells,
+                const uint8_t* pbc, unsigned char* hdr) {
+    int* off32 = (int*)hdr;
+    for (int r = 0; r <= R; ++r) off32[r] = (int)atom_off[r];
+    CellGeom* g = (CellGeom*)(hdr + align_up((size_t)(R + 1) * sizeof(int), 16));
+    for (int r = 0; r < R; ++r) {
+        int rc = make_geom(e, cells + 9 * r, pbc + 3 * r, g + r);
+        if (rc != MCPYB_OK) return rc;
+    }
+    e->atom_off_host.assign(off32, off32 + R + 1);
+    return MCPYB_OK;
+}
+
+size_t header_bytes(int R) {
+    return align_up(align_up((size_t)(R + 1) * sizeof(int), 16) + (size_t)R * sizeof(CellGeom), 64);
+}
+
+int launch_energies(mcpyb_engine* e) {
+    if (!e->have_batch) return e->fail(MCPYB_ERR_STATE, "no resident batch (call mcpyb_upload_* first)");
+    const int total = e->total_atoms;
+    if (total > 0) {
+        const int warps_per_block = 8;
+        int blocks = (total + warps_per_block - 1) / warps_per_block;
+        if (blocks > 148 * 64) blocks = 148 * 64;
+        if (e->pot_kind == POT_LJ) {
+            lj_atom_energy_kernel<<<blocks, 256, 0, e->stream>>>(
+                e->view(), e->atom_off.p, total, e->lj, e->e_atom.p, e->pair_count.p);
+            LAUNCH_CHECK("lj_atom_energy_kernel");
+        } else {
+            emt_pair_kernel<<<blocks, 256, 0, e->stream>>>(
+                e->view(), e->atom_off.p, total, e->emt_dev.p, e->e_atom.p, e->sigma1.p, e->pair_count.p);
+            LAUNCH_CHECK("emt_pair_kernel");
+            const int eb = (total + 255) / 256;
+            emt_embed_kernel<<<eb, 256, 0, e->stream>>>(
+                e->view(), total, e->emt_dev.p, e->sigma1.p, e->e_atom.p);
+            LAUNCH_CHECK("emt_embed_kernel");
+            e->emt_state_valid = true;
+        }
+    }
+    if (e->R > 0) {
+        reduce_replica_kernel<<<e->R, 256, 0, e->stream>>>(
+            e->e_atom.p, e->atom_off.p, e->E.p, e->pair_count.p, e->pairs.p, e->grid.p, e->status.p);
+        LAUNCH_CHECK("reduce_replica_kernel");
+    }
+    return MCPYB_OK;
+}
+
+int status_to_error(mcpyb_engine* e, int st, int r) {
+    if (st & 2) return e->fail(MCPYB_ERR_SPECIES, "configuration %d contains an atomic number without parameters for this potential", r);
+    if (st & 4) return e->fail(MCPYB_ERR_GEOMETRY, "configuration %d has an atom more than 511 periodic boxes from the cell", r);
+    if (st) return e->fail(MCPYB_ERR_CAPACITY, "configuration %d: internal capacity exceeded (status %d)", r, st);
+    return MCPYB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mcpyb_version(void) { return "mcpy_b200 0.1.0 (sm_100a)"; }
+
+int mcpyb_create(int device, mcpyb_engine** out) {
+    if (!out) return MCPYB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || device < 0 || device >= count) return MCPYB_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return MCPYB_ERR_CUDA;
+    mcpyb_engine* e = new mcpyb_engine();
+    e->device = device;
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete e;
+        return MCPYB_ERR_CUDA;
+    }
+    e->stream = e->own_stream;
+    for (int i = 0; i < 120; ++i) e->z_to_slot_host[i] = -1;
+    *out = e;
+    return MCPYB_OK;
+}
+
+void mcpyb_destroy(mcpyb_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release();
+    e->cid.release(); e->cell_start.release(); e->atom_off.release(); e->geom.release();
+    e->e_atom.release(); e->sigma1.release(); e->E.release(); e->pair_count.release(); e->status.release();
+    e->pairs.release(); e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
+    e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
+    e->nl_i.release(); e->nl_j.release(); e->nl_S.release(); e->nl_r2.release(); e->nl_cursor.release();
+    e->fv_grid.release(); e->fv_spheres.release(); e->fv_cell_start.release(); e->fv_cursor.release();
+    e->fv_cid.release(); e->fv_points.release(); e->fv_pos.release(); e->fv_radii.release(); e->fv_small.release();
+    e->fv_counts.release(); e->fv_mask.release(); e->fv_pin.release();
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+const char* mcpyb_last_error(const mcpyb_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int mcpyb_set_stream(mcpyb_engine* e, void* cuda_stream) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return MCPYB_OK;
+}
+
+int mcpyb_synchronize(mcpyb_engine* e) {
+    if (!e) return MCPYB_ERR_ARG;
+    CK(cudaStreamSynchronize(e->stream), "cudaStreamSynchronize");
+    return MCPYB_OK;
+}
+
+int64_t mcpyb_launch_count(const mcpyb_engine* e) { return e ? e->launches : 0; }
+double mcpyb_cutoff(const mcpyb_engine* e) { return e ? e->rcut : 0.0; }
+
+int mcpyb_set_lj(mcpyb_engine* e, double epsilon, double sigma, double rc) {
+    if (!e) return MCPYB_ERR_ARG;
+    if (!(sigma > 0.0) || !isfinite(epsilon)) return e->fail(MCPYB_ERR_ARG, "sigma must be > 0 and epsilon finite");
+    if (!(rc > 0.0)) rc = 3.0 * sigma;
+    cudaSetDevice(e->device);
+    e->pot_kind = POT_LJ;
+    e->rcut = rc;
+    e->lj.eps4 = 4.0 * epsilon;
+    e->lj.sigma2 = sigma * sigma;
+    e->lj.rc2 = rc * rc;
+    e->lj.rc = rc;
+    e->lj.e0 = 4.0 * epsilon * (pow(sigma / rc, 12) - pow(sigma / rc, 6));
+    for (int i = 0; i < 120; ++i) e->z_to_slot_host[i] = 0;       // LJ is species-blind
+    CK(e->z_to_slot.reserve(120), "cudaMalloc z_to_slot");
+    CK(cudaMemcpyAsync(e->z_to_slot.p, e->z_to_slot_host, sizeof e->z_to_slot_host, cudaMemcpyHostToDevice, e->stream), "upload z_to_slot");
+    CK(cudaStreamSynchronize(e->stream), "sync");
+    e->have_batch = false;
+    return MCPYB_OK;
+}
+
+int mcpyb_set_emt(mcpyb_engine* e) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    EmtTable& t = e->emt_host;
+    memset(&t, 0, sizeof t);
+    double maxseq = 0.0;
+    const int ns = (int)(sizeof kEmtRows / sizeof kEmtRows[0]);
+    for (int k = 0; k < ns; ++k) maxseq = fmax(maxseq, kEmtRows[k].s0 * kBohr);
+    const double rc = kEmtBeta * maxseq * 0.5 * (sqrt(3.0) + sqrt(4.0));
+    const double rr = rc * 2 * sqrt(4.0) / (sqrt(3.0) + sqrt(4.0));
+    const double acut = log(9999.0) / (rr - rc);
+    t.rc = rc; t.acut = acut; t.beta = kEmtBeta; t.rc_list = rc + 0.5; t.nspecies = ns;
+    for (int i = 0; i < 120; ++i) e->z_to_slot_host[i] = -1;
+    for (int k = 0; k < ns; ++k) {
+        const EmtRow& p = kEmtRows[k];
+        EmtSpecies& s = t.sp[k];
+        s.E0 = p.E0; s.s0 = p.s0 * kBohr; s.V0 = p.V0; s.eta2 = p.eta2 / kBohr; s.kappa = p.kappa / kBohr;
+        s.lambda = p.lambda / kBohr; s.n0 = p.n0 / (kBohr * kBohr * kBohr);
+        double g1 = 0.0, g2 = 0.0;
+        const int nn[3] = {12, 6, 24};
+        for (int i = 0; i < 3; ++i) {
+            const double r = s.s0 * kEmtBeta * sqrt((double)(i + 1));
+            const double x = nn[i] / (12 * (1.0 + exp(acut * (r - rc))));
+            g1 += x * exp(-s.eta2 * (r - kEmtBeta * s.s0));
+            g2 += x * exp(-s.kappa / kEmtBeta * (r - kEmtBeta * s.s0));
+        }
+        s.gamma1 = g1; s.gamma2 = g2;
+        e->z_to_slot_host[p.Z] = k;
+    }
+    for (int a = 0; a < ns; ++a)
+        for (int b = 0; b < ns; ++b) t.ksi[a][b] = t.sp[b].n0 / t.sp[a].n0;
+    e->pot_kind = POT_EMT;
+    e->rcut = t.rc_list;
+    CK(e->emt_dev.reserve(1), "cudaMalloc emt table");
+    CK(e->z_to_slot.reserve(120), "cudaMalloc z_to_slot");
+    CK(cudaMemcpyAsync(e->emt_dev.p, &t, sizeof t, cudaMemcpyHostToDevice, e->stream), "upload emt table");
+    CK(cudaMemcpyAsync(e->z_to_slot.p, e->z_to_slot_host, sizeof e->z_to_slot_host, cudaMemcpyHostToDevice, e->stream), "upload z_to_slot");
+    CK(cudaStreamSynchronize(e->stream), "sync");
+    e->have_batch = false;
+    return MCPYB_OK;
+}
+
+int mcpyb_emt_species(const mcpyb_engine* e, int Z, double* out9) {
+    if (!e || !out9 || e->pot_kind != POT_EMT || Z < 0 || Z >= 120 || e->z_to_slot_host[Z] < 0) return MCPYB_ERR_ARG;
+    const EmtSpecies& s = e->emt_host.sp[e->z_to_slot_host[Z]];
+    const double v[9] = {s.E0, s.s0, s.V0, s.eta2, s.kappa, s.lambda, s.n0, s.gamma1, s.gamma2};
+    memcpy(out9, v, sizeof v);
+    return MCPYB_OK;
+}
+
+int mcpyb_upload_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
+                      const int32_t* numbers, const double* cells, const uint8_t* pbc) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    int total = 0, max_n = 0;
+    int rc = validate_batch_args(e, R, atom_off, &total, &max_n);
+    if (rc != MCPYB_OK) return rc;
+    if (R > 0 && (!cells || !pbc)) return e->fail(MCPYB_ERR_ARG, "cells / pbc are NULL");
+    if (total > 0 && !positions) return e->fail(MCPYB_ERR_ARG, "positions is NULL");
+    if (total > 0 && !numbers && e->pot_kind == POT_EMT) return e->fail(MCPYB_ERR_ARG, "EMT needs atomic numbers");
+    e->have_batch = false;
+    rc = reserve_batch(e, R > 0 ? R : 1, total, max_n);
+    if (rc != MCPYB_OK) return rc;
+    e->R = R; e->total_atoms = total;
+    if (R == 0) { e->have_batch = true; e->atom_off_host.assign(1, 0); return MCPYB_OK; }
+    // one pinned block, one H2D copy: header | positions | numbers
+    const size_t hb = header_bytes(R);
+    const size_t pb = align_up((size_t)total * 3 * sizeof(double), 64);
+    const size_t zb = align_up((size_t)total * sizeof(int32_t), 64);
+    const size_t bytes = hb + pb + zb;
+    CK(cudaStreamSynchronize(e->stream), "sync before staging reuse");
+    CK(e->stage_pin.reserve(bytes), "cudaMallocHost stage");
+    CK(e->stage_dev.reserve(bytes), "cudaMalloc stage");
+    rc = fill_header(e, R, atom_off, cells, pbc, e->stage_pin.p);
+    if (rc != MCPYB_OK) return rc;
+    if (total > 0) {
+        memcpy(e->stage_pin.p + hb, positions, (size_t)total * 3 * sizeof(double));
+        if (numbers) memcpy(e->stage_pin.p + hb + pb, numbers, (size_t)total * sizeof(int32_t));
+    }
+    CK(cudaMemcpyAsync(e->stage_dev.p, e->stage_pin.p, bytes, cudaMemcpyHostToDevice, e->stream), "H2D batch");
+    return upload_common(e, R, atom_off, cells, pbc, (const double*)(e->stage_dev.p + hb),
+                         numbers ? (const int32_t*)(e->stage_dev.p + hb + pb) : nullptr, e->stage_dev.p);
+}
+
+int mcpyb_upload_dev(mcpyb_engine* e, int R, const int64_t* atom_off, const double* d_positions,
+                     const int32_t* d_numbers, const double* cells, const uint8_t* pbc) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    int total = 0, max_n = 0;
+    int rc = validate_batch_args(e, R, atom_off, &total, &max_n);
+    if (rc != MCPYB_OK) return rc;
+    if (R > 0 && (!cells || !pbc)) return e->fail(MCPYB_ERR_ARG, "cells / pbc are NULL");
+    if (total > 0 && !d_positions) return e->fail(MCPYB_ERR_ARG, "positions is NULL");
+    if (total > 0 && !d_numbers && e->pot_kind == POT_EMT) return e->fail(MCPYB_ERR_ARG, "EMT needs atomic numbers");
+    e->have_batch = false;
+    rc = reserve_batch(e, R > 0 ? R : 1, total, max_n);
+    if (rc != MCPYB_OK) return rc;
+    e->R = R; e->total_atoms = total;
+    if (R == 0) { e->have_batch = true; e->atom_off_host.assign(1, 0); return MCPYB_OK; }
+    const size_t hb = header_bytes(R);
+    // the previous upload may still be reading the pinned header: wait for it
+    CK(cudaStreamSynchronize(e->stream), "sync before header reuse");
+    CK(e->stage_pin.reserve(hb), "cudaMallocHost stage");
+    CK(e->stage_dev.reserve(hb), "cudaMalloc stage");
+    rc = fill_header(e, R, atom_off, cells, pbc, e->stage_pin.p);
+    if (rc != MCPYB_OK) return rc;
+    CK(cudaMemcpyAsync(e->stage_dev.p, e->stage_pin.p, hb, cudaMemcpyHostToDevice, e->stream), "H2D header");
+    return upload_common(e, R, atom_off, cells, pbc, d_positions, d_numbers, e->stage_dev.p);
+}
+
+int mcpyb_energies_dev(mcpyb_engine* e, double* d_energies_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    int rc = launch_energies(e);
+    if (rc != MCPYB_OK) return rc;
+    if (e->R > 0 && d_energies_out)
+        CK(cudaMemcpyAsync(d_energies_out, e->E.p, (size_t)e->R * sizeof(double), cudaMemcpyDeviceToDevice, e->stream), "D2D energies");
+    return MCPYB_OK;
+}
+
+int mcpyb_energies_host(mcpyb_engine* e, double* energies_out, int64_t* pairs_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    int rc = launch_energies(e);
+    if (rc != MCPYB_OK) return rc;
+    const int R = e->R;
+    if (R == 0) return MCPYB_OK;
+    if (!energies_out) return e->fail(MCPYB_ERR_ARG, "energies_out is NULL");
+    // one pinned block: E[R] | pairs[R] | status[R]
+    const size_t eb = (size_t)R * sizeof(double), pb = (size_t)R * sizeof(long long), sb = (size_t)R * sizeof(int);
+    CK(e->out_pin.reserve(eb + pb + sb), "cudaMallocHost out");
+    CK(cudaMemcpyAsync(e->out_pin.p, e->E.p, eb, cudaMemcpyDeviceToHost, e->stream), "D2H E");
+    CK(cudaMemcpyAsync(e->out_pin.p + eb + pb, e->status.p, sb, cudaMemcpyDeviceToHost, e->stream), "D2H status");
+    if (pairs_out) CK(cudaMemcpyAsync(e->out_pin.p + eb, e->pairs.p, pb, cudaMemcpyDeviceToHost, e->stream), "D2H pairs");
+    CK(cudaStreamSynchronize(e->stream), "sync energies");
+    const int* st = (const int*)(e->out_pin.p + eb + pb);
+    for (int r = 0; r < R; ++r) {
+        rc = status_to_error(e, st[r], r);
+        if (rc != MCPYB_OK) return rc;
+    }
+    memcpy(energies_out, e->out_pin.p, eb);
+    if (pairs_out) memcpy(pairs_out, e->out_pin.p + eb, pb);
+    return MCPYB_OK;
+}
+
+int mcpyb_potential_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
+                                  const int32_t* numbers, const double* cells, const uint8_t* pbc,
+                                  double* energies_out) {
+    int rc = mcpyb_upload_host(e, R, atom_off, positions, numbers, cells, pbc);
+    if (rc != MCPYB_OK) return rc;
+    return mcpyb_energies_host(e, energies_out, nullptr);
+}
+
+int mcpyb_atom_energies_host(mcpyb_engine* e, double* e_atom_out, double* sigma1_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    int rc = launch_energies(e);
+    if (rc != MCPYB_OK) return rc;
+    const size_t nb = (size_t)e->total_atoms * sizeof(double);
+    if (e_atom_out && nb) CK(cudaMemcpyAsync(e_atom_out, e->e_atom.p, nb, cudaMemcpyDeviceToHost, e->stream), "D2H e_atom");
+    if (sigma1_out && nb) {
+        if (e->pot_kind != POT_EMT) return e->fail(MCPYB_ERR_STATE, "sigma1 exists for EMT only");
+        CK(cudaMemcpyAsync(sigma1_out, e->sigma1.p, nb, cudaMemcpyDeviceToHost, e->stream), "D2H sigma1");
+    }
+    CK(cudaStreamSynchronize(e->stream), "sync atom energies");
+    return MCPYB_OK;
+}
+
+// ---- trial moves ---------------------------------------------------------------
+static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int32_t* d_old_off,
+                         const int32_t* d_old_idx, const int32_t* d_new_off, const double* d_new_pos,
+                         const int32_t* d_new_Z, double* d_dE, int32_t* d_pairs) {
+    if (T == 0) return MCPYB_OK;
+    TrialBatch tb;
+    tb.T = T; tb.rep = d_rep; tb.old_off = d_old_off; tb.old_idx = d_old_idx;
+    tb.new_off = d_new_off; tb.new_pos = d_new_pos; tb.new_Z = d_new_Z;
+    if (e->pot_kind == POT_LJ) {
+        if (T >= 148 * 4) {
+            int blocks = (T + 7) / 8;
+            if (blocks > 148 * 32) blocks = 148 * 32;
+            lj_trial_delta_kernel<32><<<blocks, 256, 0, e->stream>>>(e->view(), tb, e->lj, d_dE, d_pairs);
+        } else {
+            lj_trial_delta_kernel<256><<<T, 256, 0, e->stream>>>(e->view(), tb, e->lj, d_dE, d_pairs);
+        }
+        LAUNCH_CHECK("lj_trial_delta_kernel");
+    } else {
+        if (!e->emt_state_valid) {
+            int rc = launch_energies(e);       // sigma1 / e_atom of the resident batch
+            if (rc != MCPYB_OK) return rc;
+        }
+        if (T >= 148 * 4) {
+            int blocks = (T + 7) / 8;
+            if (blocks > 148 * 32) blocks = 148 * 32;
+            emt_trial_delta_kernel<32><<<blocks, 256, 0, e->stream>>>(
+                e->view(), tb, e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p, d_dE, d_pairs);
+        } else {
+            emt_trial_delta_kernel<256><<<T, 256, 0, e->stream>>>(
+                e->view(), tb, e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p, d_dE, d_pairs);
+        }
+        LAUNCH_CHECK("emt_trial_delta_kernel");
+    }
+    return MCPYB_OK;
+}
+
+int mcpyb_trial_delta_e_dev(mcpyb_engine* e, int T, const int32_t* d_rep, const int32_t* d_old_off,
+                            const int32_t* d_old_idx, const int32_t* d_new_off, const double* d_new_pos,
+                            const int32_t* d_new_Z, int n_old_total, int n_new_total,
+                            double* d_dE_out, int32_t* d_pairs_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (!e->have_batch) return e->fail(MCPYB_ERR_STATE, "no resident batch (call mcpyb_upload_* first)");
+    if (T < 0 || (T > 0 && (!d_old_off || !d_new_off || !d_dE_out))) return e->fail(MCPYB_ERR_ARG, "bad trial arguments");
+    if (e->pot_kind == POT_EMT && n_new_total > 0 && !d_new_Z) return e->fail(MCPYB_ERR_ARG, "EMT trials need new_Z");
+    (void)n_old_total;
+    return launch_trials(e, T, d_rep, d_old_off, d_old_idx, d_new_off, d_new_pos, d_new_Z, d_dE_out, d_pairs_out);
+}
+
+int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const int32_t* old_off,
+                             const int32_t* old_idx, const int32_t* new_off, const double* new_pos,
+                             const int32_t* new_Z, double* dE_out, int32_t* pairs_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (!e->have_batch) return e->fail(MCPYB_ERR_STATE, "no resident batch (call mcpyb_upload_* first)");
+    if (T < 0) return e->fail(MCPYB_ERR_ARG, "T must be >= 0");
+    if (T == 0) return MCPYB_OK;
+    if (!old_off || !new_off || !dE_out) return e->fail(MCPYB_ERR_ARG, "old_off / new_off / dE_out are NULL");
+    const int n_old = old_off[T], n_new = new_off[T];
+    if (n_old < 0 || n_new < 0 || old_off[0] != 0 || new_off[0] != 0) return e->fail(MCPYB_ERR_ARG, "bad trial offsets");
+    if ((n_old > 0 && !old_idx) || (n_new > 0 && !new_pos)) return e->fail(MCPYB_ERR_ARG, "old_idx / new_pos are NULL");
+    if (e->pot_kind == POT_EMT && n_new > 0 && !new_Z) return e->fail(MCPYB_ERR_ARG, "EMT trials need new_Z");
+    // validate on the host: replica ids, index ranges, list lengths
+    for (int t = 0; t < T; ++t) {
+        const int r = rep ? rep[t] : 0;
+        if (r < 0 || r >= e->R) return e->fail(MCPYB_ERR_ARG, "trial %d: replica %d out of range", t, r);
+        const int ko = old_off[t + 1] - old_off[t], kn = new_off[t + 1] - new_off[t];
+        if (ko < 0 || kn < 0 || ko > MCPYB_MAX_MOVED || kn > MCPYB_MAX_MOVED)
+            return e->fail(MCPYB_ERR_ARG, "trial %d: moved-atom lists must hold 0..%d atoms", t, MCPYB_MAX_MOVED);
+        const int n = e->atom_off_host[r + 1] - e->atom_off_host[r];
+        for (int k = old_off[t]; k < old_off[t + 1]; ++k)
+            if (old_idx[k] < 0 || old_idx[k] >= n) return e->fail(MCPYB_ERR_ARG, "trial %d: atom index %d out of range (n=%d)", t, old_idx[k], n);
+        if (new_Z && e->pot_kind == POT_EMT)
+            for (int k = new_off[t]; k < new_off[t + 1]; ++k)
+                if (new_Z[k] < 0 || new_Z[k] >= 120 || e->z_to_slot_host[new_Z[k]] < 0)
+                    return e->fail(MCPYB_ERR_SPECIES, "trial %d: atomic number %d has no EMT parameters", t, new_Z[k]);
+    }
+    // pinned block: rep[T] | old_off[T+1] | new_off[T+1] | old_idx | new_Z | new_pos
+    size_t o_rep = 0;
+    size_t o_oo = align_up(o_rep + (size_t)T * 4, 16);
+    size_t o_no = align_up(o_oo + (size_t)(T + 1) * 4, 16);
+    size_t o_oi = align_up(o_no + (size_t)(T + 1) * 4, 16);
+    size_t o_nz = align_up(o_oi + (size_t)n_old * 4, 16);
+    size_t o_np = align_up(o_nz + (size_t)n_new * 4, 16);
+    size_t bytes = align_up(o_np + (size_t)n_new * 24, 64);
+    CK(cudaStreamSynchronize(e->stream), "sync before trial staging reuse");
+    CK(e->trial_pin.reserve(bytes), "cudaMallocHost trials");
+    CK(e->trial_dev.reserve(bytes), "cudaMalloc trials");
+    CK(e->dE.reserve(T), "cudaMalloc dE");
+    CK(e->tpairs.reserve(T), "cudaMalloc trial pairs");
+    unsigned char* h = e->trial_pin.p;
+    if (rep) memcpy(h + o_rep, rep, (size_t)T * 4); else memset(h + o_rep, 0, (size_t)T * 4);
+    memcpy(h + o_oo, old_off, (size_t)(T + 1) * 4);
+    memcpy(h + o_no, new_off, (size_t)(T + 1) * 4);
+    if (n_old) memcpy(h + o_oi, old_idx, (size_t)n_old * 4);
+    if (n_new && new_Z) memcpy(h + o_nz, new_Z, (size_t)n_new * 4);
+    if (n_new) memcpy(h + o_np, new_pos, (size_t)n_new * 24);
+    CK(cudaMemcpyAsync(e->trial_dev.p, h, bytes, cudaMemcpyHostToDevice, e->stream), "H2D trials");
+    unsigned char* d = e->trial_dev.p;
+    int rc = launch_trials(e, T, (const int32_t*)(d + o_rep), (const int32_t*)(d + o_oo), (const int32_t*)(d + o_oi),
+                           (const int32_t*)(d + o_no), (const double*)(d + o_np),
+                           new_Z ? (const int32_t*)(d + o_nz) : nullptr, e->dE.p, e->tpairs.p);
+    if (rc != MCPYB_OK) return rc;
+    const size_t ob = (size_t)T * sizeof(double), pb = (size_t)T * sizeof(int);
+    CK(e->trial_out_pin.reserve(ob + pb), "cudaMallocHost trial out");
+    CK(cudaMemcpyAsync(e->trial_out_pin.p, e->dE.p, ob, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
+    if (pairs_out) CK(cudaMemcpyAsync(e->trial_out_pin.p + ob, e->tpairs.p, pb, cudaMemcpyDeviceToHost, e->stream), "D2H pairs");
+    CK(cudaStreamSynchronize(e->stream), "sync trials");
+    memcpy(dE_out, e->trial_out_pin.p, ob);
+    if (pairs_out) memcpy(pairs_out, e->trial_out_pin.p + ob, pb);
+    return MCPYB_OK;
+}
+
+// ---- neighbour pairs -------------------------------------------------------------
+int mcpyb_neighbor_pairs_host(mcpyb_engine* e, int rep, double cutoff, int mode, int64_t max_pairs,
+                              int32_t* i_out, int32_t* j_out, int32_t* S_out, double* r2_out, int64_t* npairs) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (!e->have_batch) return e->fail(MCPYB_ERR_STATE, "no resident batch");
+    if (rep < 0 || rep >= e->R) return e->fail(MCPYB_ERR_ARG, "replica out of range");
+    if (!(cutoff > 0.0) || cutoff > e->rcut * (1.0 + 1e-12)) return e->fail(MCPYB_ERR_ARG, "cutoff must be in (0, mcpyb_cutoff()]");
+    if (mode < 0 || mode > 2 || max_pairs < 0 || !npairs) return e->fail(MCPYB_ERR_ARG, "bad arguments");
+    const size_t cap = (size_t)(max_pairs > 0 ? max_pairs : 1);
+    CK(e->nl_i.reserve(cap), "cudaMalloc nl"); CK(e->nl_j.reserve(cap), "cudaMalloc nl");
+    CK(e->nl_S.reserve(3 * cap), "cudaMalloc nl"); CK(e->nl_r2.reserve(cap), "cudaMalloc nl");
+    CK(e->nl_cursor.reserve(1), "cudaMalloc nl");
+    CK(cudaMemsetAsync(e->nl_cursor.p, 0, sizeof(unsigned long long), e->stream), "memset cursor");
+    const int n = e->atom_off_host[rep + 1] - e->atom_off_host[rep];
+    if (n > 0) {
+        int blocks = (n + 7) / 8;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        neighbor_pairs_kernel<<<blocks, 256, 0, e->stream>>>(e->view(), rep, cutoff, mode, (long long)max_pairs,
+            e->nl_i.p, e->nl_j.p, e->nl_S.p, e->nl_r2.p, e->nl_cursor.p);
+        LAUNCH_CHECK("neighbor_pairs_kernel");
+    }
+    unsigned long long found = 0;
+    CK(cudaMemcpyAsync(&found, e->nl_cursor.p, sizeof found, cudaMemcpyDeviceToHost, e->stream), "D2H cursor");
+    CK(cudaStreamSynchronize(e->stream), "sync pairs");
+    *npairs = (int64_t)found;
+    const size_t w = (size_t)((int64_t)found < max_pairs ? (int64_t)found : max_pairs);
+    if (w) {
+        CK(cudaMemcpy(i_out, e->nl_i.p, w * 4, cudaMemcpyDeviceToHost), "D2H i");
+        CK(cudaMemcpy(j_out, e->nl_j.p, w * 4, cudaMemcpyDeviceToHost), "D2H j");
+        CK(cudaMemcpy(S_out, e->nl_S.p, w * 12, cudaMemcpyDeviceToHost), "D2H S");
+        if (r2_out) CK(cudaMemcpy(r2_out, e->nl_r2.p, w * 8, cudaMemcpyDeviceToHost), "D2H r2");
+    }
+    return MCPYB_OK;
+}
+
+// ---- free volume -----------------------------------------------------------------
+static int fv_launch(mcpyb_engine* e, const double* d_points, int64_t P, const double* d_pos,
+                     const double* d_radii, int64_t M, const double* offset3, const double* shifts,
+                     int nshift, unsigned long long* d_counts, unsigned char* d_mask) {
+    if (nshift < 1 || nshift > 27) return e->fail(MCPYB_ERR_ARG, "nshift must be in 1..27");
+    if (M * nshift > 0x7FFFFFF0LL) return e->fail(MCPYB_ERR_CAPACITY, "too many exclusion spheres");
+    const int fv_max_cells = 1 << 18;
+    const size_t nsph = (size_t)(M * nshift > 0 ? M * nshift : 1);
+    CK(e->fv_grid.reserve(1), "cudaMalloc fv"); CK(e->fv_spheres.reserve(nsph), "cudaMalloc fv");
+    CK(e->fv_cid.reserve(nsph), "cudaMalloc fv");
+    CK(e->fv_cell_start.reserve(fv_max_cells + 1), "cudaMalloc fv");
+    CK(e->fv_cursor.reserve(fv_max_cells), "cudaMalloc fv");
+    CK(e->fv_small.reserve(3 + 81), "cudaMalloc fv");
+    // offset + shifts: tiny pinned block
+    CK(cudaStreamSynchronize(e->stream), "sync before fv staging reuse");
+    CK(e->fv_pin.reserve((3 + 81) * sizeof(double)), "cudaMallocHost fv");
+    double* hs = (double*)e->fv_pin.p;
+    for (int i = 0; i < 3; ++i) hs[i] = offset3 ? offset3[i] : 0.0;
+    for (int i = 0; i < 3 * nshift; ++i) hs[3 + i] = shifts ? shifts[i] : 0.0;
+    CK(cudaMemcpyAsync(e->fv_small.p, hs, (3 + 3 * (size_t)nshift) * sizeof(double), cudaMemcpyHostToDevice, e->stream), "H2D fv small");
+    fv_build_kernel<<<1, FV_BUILD_THREADS, 0, e->stream>>>(d_pos, d_radii, (int)M, e->fv_small.p, e->fv_small.p + 3, nshift,
+        e->fv_grid.p, e->fv_spheres.p, (int)nsph, e->fv_cell_start.p, e->fv_cursor.p, fv_max_cells, e->fv_cid.p);
+    LAUNCH_CHECK("fv_build_kernel");
+    CK(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), e->stream), "memset counts");
+    if (P > 0) {
+        long long blocks = (P + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        fv_count_kernel<<<(int)blocks, 256, 0, e->stream>>>(d_points, P, e->fv_grid.p, e->fv_spheres.p,
+                                                            e->fv_cell_start.p, d_counts, d_mask);
+        LAUNCH_CHECK("fv_count_kernel");
+    }
+    return MCPYB_OK;
+}
+
+int mcpyb_free_volume_count_dev(mcpyb_engine* e, const double* d_points, int64_t P, const double* d_positions,
+                                const double* d_radii, int64_t M, const double* offset3, const double* shifts,
+                                int nshift, uint64_t* d_counts2) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (P < 0 || M < 0 || !d_counts2 || (P > 0 && !d_points) || (M > 0 && (!d_positions || !d_radii)))
+        return e->fail(MCPYB_ERR_ARG, "bad free-volume arguments");
+    return fv_launch(e, d_points, P, d_positions, d_radii, M, offset3, shifts, nshift,
+                     (unsigned long long*)d_counts2, nullptr);
+}
+
+int mcpyb_free_volume_count_host(mcpyb_engine* e, const double* points, int64_t P, const double* positions,
+                                 const double* radii, int64_t M, const double* offset3, const double* shifts,
+                                 int nshift, int64_t* counts_out, uint8_t* covered_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (P < 0 || M < 0 || !counts_out || (P > 0 && !points) || (M > 0 && (!positions || !radii)))
+        return e->fail(MCPYB_ERR_ARG, "bad free-volume arguments");
+    CK(e->fv_points.reserve((size_t)(P > 0 ? 3 * P : 1)), "cudaMalloc fv points");
+    CK(e->fv_pos.reserve((size_t)(M > 0 ? 3 * M : 1)), "cudaMalloc fv pos");
+    CK(e->fv_radii.reserve((size_t)(M > 0 ? M : 1)), "cudaMalloc fv radii");
+    CK(e->fv_counts.reserve(2), "cudaMalloc fv counts");
+    if (covered_out) CK(e->fv_mask.reserve((size_t)(P > 0 ? P : 1)), "cudaMalloc fv mask");
+    if (P) CK(cudaMemcpyAsync(e->fv_points.p, points, (size_t)P * 24, cudaMemcpyHostToDevice, e->stream), "H2D points");
+    if (M) {
+        CK(cudaMemcpyAsync(e->fv_pos.p, positions, (size_t)M * 24, cudaMemcpyHostToDevice, e->stream), "H2D fv pos");
+        CK(cudaMemcpyAsync(e->fv_radii.p, radii, (size_t)M * 8, cudaMemcpyHostToDevice, e->stream), "H2D fv radii");
+    }
+    int rc = fv_launch(e, e->fv_points.p, P, e->fv_pos.p, e->fv_radii.p, M, offset3, shifts, nshift,
+                       e->fv_counts.p, covered_out ? e->fv_mask.p : nullptr);
+    if (rc != MCPYB_OK) return rc;
+    unsigned long long c[2] = {0, 0};
+    FvGrid g;
+    CK(cudaMemcpyAsync(c, e->fv_counts.p, sizeof c, cudaMemcpyDeviceToHost, e->stream), "D2H counts");
+    CK(cudaMemcpyAsync(&g, e->fv_grid.p, sizeof g, cudaMemcpyDeviceToHost, e->stream), "D2H fv grid");
+    if (covered_out && P) CK(cudaMemcpyAsync(covered_out, e->fv_mask.p, (size_t)P, cudaMemcpyDeviceToHost, e->stream), "D2H mask");
+    CK(cudaStreamSynchronize(e->stream), "sync free volume");
+    if (g.error) return e->fail(MCPYB_ERR_CAPACITY, "free-volume sphere capacity exceeded");
+    counts_out[0] = (int64_t)c[0];
+    counts_out[1] = (int64_t)c[1];
+    return MCPYB_OK;
+}
+
+int mcpyb_fp64_peak_tflops(mcpyb_engine* e, double* tflops_out) {
+    if (!e || !tflops_out) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 14;
+    DevBuf<double> out;
+    CK(out.reserve((size_t)blocks * threads), "cudaMalloc peak");
+    cudaEvent_t t0, t1;
+    CK(cudaEventCreate(&t0), "event"); CK(cudaEventCreate(&t1), "event");
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(t0, e->stream), "record");
+        fp64_fma_peak_kernel<<<blocks, threads, 0, e->stream>>>(out.p, iters, 1.0000001, 1e-9);
+        LAUNCH_CHECK("fp64_fma_peak_kernel");
+        CK(cudaEventRecord(t1, e->stream), "record");
+        CK(cudaEventSynchronize(t1), "sync");
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, t0, t1), "elapsed");
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        if (rep > 0) best = fmax(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    out.release();
+    *tflops_out = best;
+    return MCPYB_OK;
+}
+
+}  // extern "C"

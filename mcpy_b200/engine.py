@@ -1,0 +1,222 @@
+"""Thin Python object around one ``mcpyb_engine`` handle (include/mcpy_b200.h).
+
+Holds no arithmetic: every method marshals numpy buffers into the C ABI and
+raises on a non-zero status.  The calculators and cells in this package are
+written on top of it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineError, as_f64, as_i32, as_i64, as_u8, ptr
+
+_ERR_VALUE = (-2,)            # MCPYB_ERR_ARG -> ValueError, like the reference's bad-argument errors
+
+
+class Engine:
+    """One engine = one CUDA device, one stream, one potential, one resident batch."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.mcpyb_create(int(device), C.byref(h))
+        if rc != 0 or not h:
+            raise EngineError(
+                f'mcpyb_create(device={device}) failed (status {rc}): no usable CUDA device. '
+                'The mcpy_b200 engine has no CPU fallback.')
+        self._h = h
+        self.device = int(device)
+        self.potential = None
+
+    # -- plumbing ------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.mcpyb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        msg = self._lib.mcpyb_last_error(self._h).decode()
+        if rc in _ERR_VALUE:
+            raise ValueError(msg)
+        raise EngineError(f'{msg} (status {rc})')
+
+    def set_stream(self, cuda_stream: int | None):
+        """Enqueue on an existing CUDA stream, e.g. ``torch.cuda.current_stream().cuda_stream``."""
+        self._check(self._lib.mcpyb_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._check(self._lib.mcpyb_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mcpyb_launch_count(self._h))
+
+    def fp64_peak_tflops(self) -> float:
+        """Measured DFMA throughput of this GPU (roofline denominator of the pair kernels)."""
+        out = C.c_double(0.0)
+        self._check(self._lib.mcpyb_fp64_peak_tflops(self._h, C.byref(out)))
+        return float(out.value)
+
+    @property
+    def cutoff(self) -> float:
+        return float(self._lib.mcpyb_cutoff(self._h))
+
+    # -- potentials ----------------------------------------------------------
+    def set_lj(self, epsilon=1.0, sigma=1.0, rc=None):
+        self._check(self._lib.mcpyb_set_lj(self._h, float(epsilon), float(sigma),
+                                           -1.0 if rc is None else float(rc)))
+        self.potential = 'lj'
+
+    def set_emt(self):
+        self._check(self._lib.mcpyb_set_emt(self._h))
+        self.potential = 'emt'
+
+    def emt_species(self, Z: int) -> np.ndarray:
+        out = np.zeros(9)
+        self._check(self._lib.mcpyb_emt_species(self._h, int(Z), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    # -- batches -------------------------------------------------------------
+    @staticmethod
+    def _batch_args(positions_list, numbers_list, cells, pbcs):
+        R = len(positions_list)
+        off = np.zeros(R + 1, dtype=np.int64)
+        for r, p in enumerate(positions_list):
+            off[r + 1] = off[r] + len(p)
+        if R and off[-1]:
+            pos = np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in positions_list])
+            num = np.concatenate([np.asarray(z, dtype=np.int32).reshape(-1) for z in numbers_list])
+        else:
+            pos = np.zeros((0, 3))
+            num = np.zeros(0, dtype=np.int32)
+        cells = as_f64(cells, (R, 9)) if R else np.zeros((0, 9))
+        pbcs = as_u8(np.asarray(pbcs, dtype=bool).reshape(R, 3)) if R else np.zeros((0, 3), np.uint8)
+        return R, off, as_f64(pos), as_i32(num), cells, pbcs
+
+    def upload(self, positions_list, numbers_list, cells, pbcs):
+        """Make R configurations resident in HBM (host buffers -> cell lists)."""
+        R, off, pos, num, cells, pbcs = self._batch_args(positions_list, numbers_list, cells, pbcs)
+        self._keep = (off, pos, num, cells, pbcs)
+        self._check(self._lib.mcpyb_upload_host(self._h, R, ptr(off), ptr(pos), ptr(num),
+                                                ptr(cells), ptr(pbcs)))
+        self._R = R
+        self._ntot = int(off[-1])
+
+    def upload_dev(self, atom_off, d_positions: int, d_numbers: int, cells, pbcs):
+        """Same with device pointers (integers) for positions / numbers."""
+        off = as_i64(atom_off)
+        R = len(off) - 1
+        cells = as_f64(cells, (R, 9))
+        pbcs = as_u8(np.asarray(pbcs, dtype=bool).reshape(R, 3))
+        self._keep = (off, cells, pbcs)
+        self._check(self._lib.mcpyb_upload_dev(self._h, R, ptr(off), C.c_void_p(d_positions),
+                                               C.c_void_p(d_numbers), ptr(cells), ptr(pbcs)))
+        self._R = R
+        self._ntot = int(off[-1])
+
+    def energies(self, return_pairs=False):
+        E = np.empty(self._R, dtype=np.float64)
+        pairs = np.empty(self._R, dtype=np.int64) if return_pairs else None
+        self._check(self._lib.mcpyb_energies_host(self._h, ptr(E), ptr(pairs)))
+        return (E, pairs) if return_pairs else E
+
+    def energies_dev(self, d_out: int):
+        self._check(self._lib.mcpyb_energies_dev(self._h, C.c_void_p(d_out)))
+
+    def potential_energies(self, positions_list, numbers_list, cells, pbcs) -> np.ndarray:
+        """upload + energies in one C call (the whole plug-in call)."""
+        R, off, pos, num, cells, pbcs = self._batch_args(positions_list, numbers_list, cells, pbcs)
+        E = np.empty(R, dtype=np.float64)
+        self._check(self._lib.mcpyb_potential_energies_host(
+            self._h, R, ptr(off), ptr(pos), ptr(num), ptr(cells), ptr(pbcs), ptr(E)))
+        self._R = R
+        self._ntot = int(off[-1])
+        return E
+
+    def atom_energies(self, want_sigma1=False):
+        e = np.empty(self._ntot)
+        s = np.empty(self._ntot) if want_sigma1 else None
+        self._check(self._lib.mcpyb_atom_energies_host(self._h, ptr(e), ptr(s)))
+        return (e, s) if want_sigma1 else e
+
+    # -- trial moves ---------------------------------------------------------
+    def trial_delta_e(self, old_off, old_idx, new_off, new_pos, new_Z=None, rep=None,
+                      return_pairs=False):
+        old_off = as_i32(old_off)
+        new_off = as_i32(new_off)
+        T = len(old_off) - 1
+        if len(new_off) - 1 != T:
+            raise ValueError('old_off and new_off must describe the same number of trials')
+        old_idx = as_i32(old_idx)
+        new_pos = as_f64(new_pos).reshape(-1, 3)
+        new_Z = None if new_Z is None else as_i32(new_Z)
+        rep = None if rep is None else as_i32(rep)
+        if T and (old_off[-1] != len(old_idx) or new_off[-1] != len(new_pos)):
+            raise ValueError('trial offsets do not match the index / position arrays')
+        dE = np.empty(T, dtype=np.float64)
+        pairs = np.empty(T, dtype=np.int32) if return_pairs else None
+        self._check(self._lib.mcpyb_trial_delta_e_host(
+            self._h, T, ptr(rep), ptr(old_off), ptr(old_idx), ptr(new_off), ptr(new_pos),
+            ptr(new_Z), ptr(dE), ptr(pairs)))
+        return (dE, pairs) if return_pairs else dE
+
+    def trial_delta_e_dev(self, T, d_rep, d_old_off, d_old_idx, d_new_off, d_new_pos, d_new_Z,
+                          n_old_total, n_new_total, d_dE, d_pairs=0):
+        v = C.c_void_p
+        self._check(self._lib.mcpyb_trial_delta_e_dev(
+            self._h, int(T), v(d_rep or 0), v(d_old_off), v(d_old_idx or 0), v(d_new_off),
+            v(d_new_pos or 0), v(d_new_Z or 0), int(n_old_total), int(n_new_total),
+            v(d_dE), v(d_pairs or 0)))
+
+    # -- neighbour pairs -----------------------------------------------------
+    def neighbor_pairs(self, rep=0, cutoff=None, mode=0, max_pairs=None):
+        """(i, j, S, r2) of every image within ``cutoff``, sorted like oracle.neighbors."""
+        cutoff = self.cutoff if cutoff is None else float(cutoff)
+        if max_pairs is None:
+            max_pairs = 1 << 22
+        while True:
+            i = np.empty(max_pairs, np.int32)
+            j = np.empty(max_pairs, np.int32)
+            S = np.empty((max_pairs, 3), np.int32)
+            r2 = np.empty(max_pairs, np.float64)
+            n = C.c_int64(0)
+            self._check(self._lib.mcpyb_neighbor_pairs_host(
+                self._h, int(rep), cutoff, int(mode), int(max_pairs), ptr(i), ptr(j), ptr(S),
+                ptr(r2), C.byref(n)))
+            if n.value <= max_pairs:
+                break
+            max_pairs = int(n.value)
+        k = n.value
+        i, j, S, r2 = i[:k].astype(np.int64), j[:k].astype(np.int64), S[:k].astype(np.int64), r2[:k]
+        order = np.lexsort((S[:, 2], S[:, 1], S[:, 0], j, i))
+        return i[order], j[order], S[order], r2[order]
+
+    # -- free volume ---------------------------------------------------------
+    def free_volume_count(self, points, positions, radii, offset=None, shifts=None,
+                          return_mask=False):
+        points = as_f64(points).reshape(-1, 3)
+        positions = as_f64(positions).reshape(-1, 3)
+        radii = as_f64(radii).reshape(-1)
+        if len(radii) != len(positions):
+            raise ValueError('one radius per atom is required')
+        offset = as_f64(np.zeros(3) if offset is None else offset).reshape(3)
+        shifts = as_f64(np.zeros((1, 3)) if shifts is None else shifts).reshape(-1, 3)
+        counts = np.zeros(2, dtype=np.int64)
+        mask = np.empty(len(points), dtype=np.uint8) if return_mask else None
+        self._check(self._lib.mcpyb_free_volume_count_host(
+            self._h, ptr(points), len(points), ptr(positions), ptr(radii), len(positions),
+            ptr(offset), ptr(shifts), len(shifts), ptr(counts), ptr(mask)))
+        if return_mask:
+            return int(counts[0]), int(counts[1]), mask.astype(bool)
+        return int(counts[0]), int(counts[1])

@@ -1,0 +1,116 @@
+"""GPU parity: free-volume counts are bit-exact integers vs scipy cKDTree (the
+reference's own library, mcpy/cell/spherical_cell.py:130-138)."""
+import math
+
+import numpy as np
+import pytest
+
+from mcpy_b200.utils import synthetic
+from oracle import free_volume as ofv
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sphere_counts_match_kdtree_s3(fv_engine):
+    cfg = synthetic.s3_ag_o()
+    rng = np.random.default_rng(3)
+    pts, _ = ofv.sample_sphere_points(rng, 100_000, cfg['sphere_radius'])
+    covered = ofv.covered_mask_kdtree(pts, cfg['positions'], cfg['radii'])
+    n_free, n_cov, mask = fv_engine.free_volume_count(pts, cfg['positions'], cfg['radii'], return_mask=True)
+    assert n_cov == int(covered.sum()) and n_free == int((~covered).sum())
+    assert np.array_equal(mask, covered)
+
+
+def test_boundary_points_are_strict(fv_engine):
+    # points within a few ulps of sphere surfaces: cKDTree's d < r is strict
+    rng = np.random.default_rng(12)
+    atoms = rng.uniform(-5, 5, size=(40, 3))
+    radii = rng.choice([1.3, 2.0, 0.0], size=40)
+    pts = []
+    for a, r in zip(atoms, radii):
+        if r <= 0:
+            continue
+        u = rng.standard_normal((200, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+        p = a + u * r
+        for k in range(-3, 4):
+            q = p.copy()
+            for _ in range(abs(k)):
+                q = np.nextafter(q, a if k < 0 else q + (q - a))
+            pts.append(q)
+    pts = np.concatenate(pts)
+    covered = ofv.covered_mask_kdtree(pts, atoms, radii)
+    brute = ofv.covered_mask_bruteforce(pts, atoms, radii)
+    assert np.array_equal(covered, brute)
+    n_free, n_cov, mask = fv_engine.free_volume_count(pts, atoms, radii, return_mask=True)
+    assert np.array_equal(mask, covered)
+    assert n_cov == int(covered.sum())
+
+
+def test_custom_cell_periodic_images_reference_value(fv_engine):
+    # tests/test_audit_regressions.py:363-372: one r = 2 sphere on the x face of a 10 A cube,
+    # 200 000 points, seed 7 -> |V - 966.49| < 3
+    from mcpy_b200.cell import B200CustomCell
+    from ase import Atoms
+    atoms = Atoms('H', positions=[[0.0, 5.0, 5.0]], cell=[10, 10, 10], pbc=True)
+    cell = B200CustomCell(atoms, custom_height=10.0, bottom_z=0.0, species_radii={'H': 2.0},
+                          mc_sample_points=200_000, seed=7, engine=fv_engine)
+    cell.calculate_volume(atoms)
+    expected = 1000.0 - (4.0 / 3.0) * math.pi * 8.0
+    assert cell.get_volume() == pytest.approx(expected, abs=3.0)
+    rng = np.random.default_rng(7)
+    vol, n_cov = ofv.custom_free_volume(rng, atoms.positions, [2.0], cell.dimensions, cell.offset,
+                                        cell.original_dimensions, atoms.pbc, 200_000)
+    assert cell.last_counts[1] == n_cov
+    assert cell.get_volume() == vol
+
+
+def test_custom_cell_slab_images_and_offset(fv_engine):
+    rng = np.random.default_rng(5)
+    dims = np.array([[11.0, 0, 0], [5.5, 9.5, 0], [0, 0, 30.0]])
+    pos = rng.random((60, 3)) @ dims
+    radii = rng.choice([1.5, 2.2, 0.0], size=60)
+    region = dims.copy(); region[2, 2] = 12.0
+    offset = np.array([0, 0, 6.0])
+    pbc = [True, True, False]
+    prng = np.random.default_rng(9)
+    pts = ofv.sample_box_points(prng, 50_000, region)
+    images = ofv.periodic_images(pos, offset, dims, pbc)
+    rad = np.tile(radii, len(images) // len(pos))
+    covered = ofv.covered_mask_kdtree(pts, images, rad)
+    shifts = np.array([np.array([i, j, 0], float) @ dims for i in (-1, 0, 1) for j in (-1, 0, 1)])
+    n_free, n_cov, mask = fv_engine.free_volume_count(pts, pos, radii, offset=offset, shifts=shifts,
+                                                      return_mask=True)
+    assert np.array_equal(mask, covered)
+
+
+def test_s5_million_points(fv_engine):
+    cfg = synthetic.s5_cupd_co()
+    rng = np.random.default_rng(5)
+    pts, _ = ofv.sample_sphere_points(rng, 1_000_000, cfg['sphere_radius'])
+    covered = ofv.covered_mask_kdtree(pts, cfg['positions'], cfg['radii'])
+    n_free, n_cov = fv_engine.free_volume_count(pts, cfg['positions'], cfg['radii'])
+    assert (n_free, n_cov) == (int((~covered).sum()), int(covered.sum()))
+
+
+def test_spherical_cell_mirror_matches_oracle_and_floor(fv_engine):
+    from mcpy_b200.cell import B200SphericalCell
+    from ase import Atoms
+    cfg = synthetic.s3_ag_o()
+    syms = ['Ag' if z == 47 else 'O' for z in cfg['numbers']]
+    atoms = Atoms(syms, positions=cfg['positions'])
+    cell = B200SphericalCell(atoms, vacuum=3.0, species_radii={'Ag': 2.947, 'O': 0.0},
+                             mc_sample_points=20_000, seed=3, engine=fv_engine)
+    cell.calculate_volume(atoms)
+    rng = np.random.default_rng(3)
+    vol, n_free = ofv.spherical_free_volume(rng, atoms.positions, cfg['radii'], cell.radius, 20_000)
+    assert cell.last_counts[0] == n_free
+    assert cell.get_volume() == vol
+    # zero free volume -> floored at one point's worth (tests/test_zero_free_volume.py:22-51)
+    full = B200SphericalCell(atoms, vacuum=0.0, species_radii={'Ag': 50.0, 'O': 50.0},
+                             mc_sample_points=1000, seed=1, engine=fv_engine)
+    full.calculate_volume(atoms)
+    assert full.get_volume() == full.sphere_volume / 1000
+    # empty atoms -> whole sphere
+    empty = Atoms()
+    full.calculate_volume(empty)
+    assert full.get_volume() == full.sphere_volume

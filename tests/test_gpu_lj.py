@@ -1,0 +1,245 @@
+"""GPU parity: Lennard-Jones energies, neighbour pairs and trial delta-E vs the oracle.
+
+Bars (BASELINE.json north_star): pair sets bit-exact; energies and delta-E within
+1e-10 relative in fp64.
+"""
+import numpy as np
+import pytest
+
+from mcpy_b200.utils import synthetic
+from oracle import cfast
+from oracle import lj as olj
+from oracle.neighbors import neighbor_pairs
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def _rel(a, b, scale=None):
+    scale = max(1.0, abs(b)) if scale is None else scale
+    return abs(a - b) / scale
+
+
+def _energy(engine, pos, cell, pbc, numbers=None):
+    numbers = np.ones(len(pos), np.int32) if numbers is None else numbers
+    return engine.potential_energies([pos], [numbers], np.asarray(cell, float).reshape(1, 9),
+                                     np.asarray(pbc, bool).reshape(1, 3))[0]
+
+
+def test_two_body_probe_matches_lammps_convention(lj_engine):
+    # benchmark/lammps_gcmc_parity.py:285-324: E(r) = 4(r^-12 - r^-6) - 4(3^-12 - 3^-6)
+    lj_engine.set_lj(1.0, 1.0, 3.0)
+    for r in [0.9, 1.0, 1.5, 2.5, 2.99]:
+        pos = np.array([[5, 5, 5], [5, 5, 5 + r]], float)
+        e = _energy(lj_engine, pos, np.diag([20.0] * 3), [1, 1, 1])
+        exact = 4 * (r ** -12 - r ** -6) - 4 * (3.0 ** -12 - 3.0 ** -6)
+        assert abs(e - exact) <= 1e-8 * max(1.0, abs(exact))
+    # beyond the cutoff and exactly at it
+    assert _energy(lj_engine, np.array([[5, 5, 5], [5, 5, 8.5]], float), np.diag([20.0] * 3), [1, 1, 1]) == 0.0
+
+
+def test_ljcalc_configs_match(lj_engine):
+    # benchmark/lammps_gcmc_parity.py:190-203: 5 x 40 atoms, default_rng(99), L = 9, rc = 3
+    lj_engine.set_lj(1.0, 1.0, 3.0)
+    rng = np.random.default_rng(99)
+    L = 9.0
+    for _ in range(5):
+        pos = rng.uniform(0, L, size=(40, 3))
+        e = _energy(lj_engine, pos, np.diag([L] * 3), [1, 1, 1])
+        ref = olj.lj_energy(pos, np.diag([L] * 3), [1, 1, 1], 1.0, 1.0, 3.0)
+        fast = olj.LJCalcRestated(L, 3.0).energy(pos)
+        assert _rel(e, ref) <= RTOL
+        assert _rel(e, fast) <= 1e-9
+
+
+@pytest.mark.parametrize('builder,kw', [(synthetic.s1_argon, {}), (synthetic.s2_lj, {}),
+                                        (synthetic.s2_lj, {'rc': 2 ** (1 / 6)})])
+def test_synthetic_energy_and_pairs(lj_engine, builder, kw):
+    cfg = builder(**kw)
+    lj_engine.set_lj(cfg['epsilon'], cfg['sigma'], cfg['rc'])
+    lj_engine.upload([cfg['positions']], [cfg['numbers']], cfg['cell'].reshape(1, 9), cfg['pbc'].reshape(1, 3))
+    E, pairs = lj_engine.energies(return_pairs=True)
+    ref, ref_pairs = cfast.lj_energy(cfg['positions'], cfg['cell'], cfg['pbc'], cfg['sigma'],
+                                     cfg['epsilon'], cfg['rc'], return_pairs=True)
+    assert int(pairs[0]) == ref_pairs
+    assert _rel(E[0], ref) <= RTOL
+    # pair set bit-exact, including the fp64 r2 of every image
+    gi, gj, gS, gr2 = lj_engine.neighbor_pairs(0, cfg['rc'], mode=1)
+    oi, oj, oS, or2 = cfast.neighbor_pairs(cfg['positions'], cfg['cell'], cfg['pbc'], cfg['rc'], mode=1)
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj) and np.array_equal(gS, oS)
+    assert np.array_equal(gr2, or2)
+
+
+def _random_cfg(rng, n, cell, pbc, spread=1.0):
+    cell = np.asarray(cell, float)
+    frac = rng.random((n, 3)) * spread + (1 - spread) / 2
+    return frac @ cell if np.any(cell) else rng.normal(size=(n, 3)) * 3
+
+
+@pytest.mark.parametrize('case', ['triclinic', 'slab', 'cluster', 'thin', 'unwrapped', 'tiny'])
+def test_geometries(lj_engine, case):
+    rng = np.random.default_rng(11)
+    lj_engine.set_lj(0.7, 1.1, 2.75)
+    if case == 'triclinic':
+        cell = np.array([[9.0, 0, 0], [2.5, 8.5, 0], [1.0, -2.0, 10.0]]); pbc = [1, 1, 1]
+        pos = _random_cfg(rng, 150, cell, pbc)
+    elif case == 'slab':
+        cell = np.diag([8.0, 9.0, 30.0]); pbc = [1, 1, 0]
+        pos = _random_cfg(rng, 120, cell, pbc); pos[:, 2] = rng.uniform(-4, 9, 120)
+    elif case == 'cluster':
+        cell = np.zeros((3, 3)); pbc = [0, 0, 0]
+        pos = rng.normal(size=(90, 3)) * 2.5
+    elif case == 'thin':       # box thinner than the cutoff along y and z: several images
+        cell = np.diag([7.0, 2.1, 1.3]); pbc = [1, 1, 1]
+        pos = _random_cfg(rng, 12, cell, pbc)
+    elif case == 'unwrapped':  # atoms several boxes away from the primary cell
+        cell = np.diag([7.5, 8.0, 6.5]); pbc = [1, 1, 1]
+        pos = _random_cfg(rng, 100, cell, pbc) + rng.integers(-3, 4, size=(100, 3)) * np.diag(cell)
+    else:
+        cell = np.diag([5.0, 5.0, 5.0]); pbc = [1, 1, 1]
+        pos = np.array([[1.0, 2.0, 3.0]])
+    # keep atoms from overlapping absurdly
+    e = _energy(lj_engine, pos, cell, pbc)
+    ref = olj.lj_energy(pos, cell, pbc, 1.1, 0.7, 2.75)
+    assert _rel(e, ref, max(1.0, abs(ref))) <= RTOL
+    gi, gj, gS, gr2 = lj_engine.neighbor_pairs(0, 2.75, mode=1)
+    oi, oj, oS, or2 = neighbor_pairs(pos, cell, pbc, 2.75, inclusive=True)
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj) and np.array_equal(gS, oS)
+    assert np.array_equal(gr2, or2)
+
+
+def test_cutoff_boundary_is_inclusive_and_bit_exact(lj_engine):
+    # pairs placed exactly at r == rc and one ulp either side (ASE keeps r2 <= rc^2)
+    rc = 2.5
+    lj_engine.set_lj(1.0, 1.0, rc)
+    base = np.array([3.0, 3.0, 3.0])
+    pos = [base]
+    for k, d in enumerate([rc, np.nextafter(rc, 0), np.nextafter(rc, 10)]):
+        pos.append(base + np.array([0.0, 0.0, 0.0]) + np.eye(3)[k] * d)
+    pos = np.array(pos)
+    cell = np.diag([40.0] * 3)
+    lj_engine.upload([pos], [np.ones(4, np.int32)], cell.reshape(1, 9), np.ones((1, 3), bool))
+    for mode, kw in [(0, {}), (1, {'inclusive': True}), (2, {'use_sqrt': True})]:
+        gi, gj, gS, gr2 = lj_engine.neighbor_pairs(0, rc, mode=mode)
+        oi, oj, oS, or2 = neighbor_pairs(pos, cell, [1, 1, 1], rc, **kw)
+        assert np.array_equal(gi, oi) and np.array_equal(gj, oj) and np.array_equal(gr2, or2)
+
+
+def test_empty_and_ragged_batch(lj_engine):
+    lj_engine.set_lj(1.0, 1.0, 3.0)
+    rng = np.random.default_rng(3)
+    L = 9.0
+    sizes = [0, 1, 37, 2, 120, 0, 64]
+    poss = [rng.uniform(0, L, size=(n, 3)) for n in sizes]
+    nums = [np.ones(n, np.int32) for n in sizes]
+    cells = np.tile(np.diag([L] * 3).reshape(1, 9), (len(sizes), 1))
+    cells[3] = np.diag([12.0, 9.0, 10.0]).reshape(9)
+    pbcs = np.ones((len(sizes), 3), bool)
+    pbcs[4] = [True, False, True]
+    E = lj_engine.potential_energies(poss, nums, cells, pbcs)
+    for r, n in enumerate(sizes):
+        ref = olj.lj_energy(poss[r], cells[r].reshape(3, 3), pbcs[r], 1.0, 1.0, 3.0)
+        assert _rel(E[r], ref) <= RTOL
+    assert lj_engine.potential_energies([], [], np.zeros((0, 9)), np.zeros((0, 3), bool)).shape == (0,)
+
+
+@pytest.mark.parametrize('builder,kw,ntr', [(synthetic.s1_argon, {}, 48), (synthetic.s2_lj, {}, 24)])
+def test_trial_delta_e_matches_two_full_energies(lj_engine, builder, kw, ntr):
+    cfg = builder(**kw)
+    lj_engine.set_lj(cfg['epsilon'], cfg['sigma'], cfg['rc'])
+    lj_engine.upload([cfg['positions']], [cfg['numbers']], cfg['cell'].reshape(1, 9), cfg['pbc'].reshape(1, 3))
+    tb = synthetic.trial_batch(cfg, ntr, seed=5)
+    for group in ('small', 'large'):
+        if group == 'large':      # >= 592 trials switches to the warp-per-trial kernel
+            reps = 600 // ntr + 1
+            big = {k: v for k, v in tb.items()}
+            big['old_off'] = np.concatenate([[0], np.cumsum(np.tile(np.diff(tb['old_off']), reps))]).astype(np.int32)
+            big['new_off'] = np.concatenate([[0], np.cumsum(np.tile(np.diff(tb['new_off']), reps))]).astype(np.int32)
+            big['old_idx'] = np.tile(tb['old_idx'], reps)
+            big['new_pos'] = np.tile(tb['new_pos'], (reps, 1))
+            big['new_Z'] = np.tile(tb['new_Z'], reps)
+            use = big
+        else:
+            use = tb
+        dE, pairs = lj_engine.trial_delta_e(use['old_off'], use['old_idx'], use['new_off'],
+                                            use['new_pos'], use['new_Z'], return_pairs=True)
+        if group == 'small':
+            E0 = cfast.lj_energy(cfg['positions'], cfg['cell'], cfg['pbc'], cfg['sigma'], cfg['epsilon'], cfg['rc'])
+            first = dE.copy()
+            for t in range(ntr):
+                p1, _ = synthetic.apply_trial(cfg, tb, t)
+                ref = cfast.lj_energy(p1, cfg['cell'], cfg['pbc'], cfg['sigma'], cfg['epsilon'], cfg['rc']) - E0
+                assert abs(dE[t] - ref) <= RTOL * max(1.0, abs(E0), abs(ref)), (t, tb['kind'][t], dE[t], ref)
+        else:
+            assert np.array_equal(dE[:ntr], first)          # both kernels, same bits
+            assert np.array_equal(dE[ntr:2 * ntr], first)
+
+
+def test_rigid_molecule_trials_and_periodic_self_images(lj_engine):
+    # k = 2 and k = 3 moved sets, including a box small enough that moved atoms see
+    # each other's periodic images
+    rng = np.random.default_rng(21)
+    lj_engine.set_lj(1.0, 1.0, 2.5)
+    for L, n in [(9.0, 80), (5.5, 30)]:
+        cell = np.diag([L] * 3)
+        pos = rng.uniform(0, L, size=(n, 3))
+        cfg = dict(positions=pos, numbers=np.ones(n, np.int32), cell=cell, pbc=np.ones(3, bool))
+        lj_engine.upload([pos], [cfg['numbers']], cell.reshape(1, 9), np.ones((1, 3), bool))
+        old_off, new_off, old_idx, new_pos = [0], [0], [], []
+        for k in (2, 3, 2, 3):
+            idx = rng.choice(n, size=k, replace=False)
+            old_idx += list(idx)
+            new_pos += list(pos[idx] + rng.uniform(-0.8, 0.8, size=(1, 3)) + rng.uniform(-0.2, 0.2, size=(k, 3)))
+            old_off.append(len(old_idx)); new_off.append(len(new_pos))
+        # molecule insertion (k = 2) and deletion (k = 3)
+        new_pos += list(rng.uniform(0, L, size=(1, 3)) + np.array([[0, 0, 0], [0, 0, 1.1]]))
+        old_off.append(len(old_idx)); new_off.append(len(new_pos))
+        old_idx += list(rng.choice(n, size=3, replace=False))
+        old_off.append(len(old_idx)); new_off.append(len(new_pos))
+        tb = dict(old_off=np.array(old_off, np.int32), new_off=np.array(new_off, np.int32),
+                  old_idx=np.array(old_idx, np.int32), new_pos=np.array(new_pos),
+                  new_Z=np.ones(len(new_pos), np.int32))
+        dE = lj_engine.trial_delta_e(tb['old_off'], tb['old_idx'], tb['new_off'], tb['new_pos'], tb['new_Z'])
+        E0 = olj.lj_energy(pos, cell, [1, 1, 1], 1.0, 1.0, 2.5)
+        for t in range(len(dE)):
+            p1, _ = synthetic.apply_trial(cfg, tb, t)
+            ref = olj.lj_energy(p1, cell, [1, 1, 1], 1.0, 1.0, 2.5) - E0
+            assert abs(dE[t] - ref) <= RTOL * max(1.0, abs(E0), abs(ref)), (L, t, dE[t], ref)
+
+
+def test_trials_on_a_replica_batch(lj_engine):
+    rng = np.random.default_rng(8)
+    lj_engine.set_lj(1.0, 1.0, 3.0)
+    L = 10.0
+    sizes = [50, 0, 75, 31]
+    poss = [rng.uniform(0, L, size=(n, 3)) for n in sizes]
+    nums = [np.ones(n, np.int32) for n in sizes]
+    cells = np.tile(np.diag([L] * 3).reshape(1, 9), (4, 1))
+    pbcs = np.ones((4, 3), bool)
+    lj_engine.upload(poss, nums, cells, pbcs)
+    rep = np.array([0, 2, 3, 1, 2, 0], np.int32)
+    old_off = np.array([0, 1, 1, 2, 2, 3, 3], np.int32)
+    old_idx = np.array([7, 30, 74], np.int32)
+    new_off = np.array([0, 1, 2, 2, 3, 3, 4], np.int32)
+    new_pos = rng.uniform(0, L, size=(4, 3))
+    dE = lj_engine.trial_delta_e(old_off, old_idx, new_off, new_pos, np.ones(4, np.int32), rep=rep)
+    for t in range(6):
+        r = rep[t]
+        cfg = dict(positions=poss[r], numbers=nums[r])
+        tb = dict(old_off=old_off, old_idx=old_idx, new_off=new_off, new_pos=new_pos, new_Z=np.ones(4, np.int32))
+        p1, _ = synthetic.apply_trial(cfg, tb, t)
+        c = cells[r].reshape(3, 3)
+        ref = olj.lj_energy(p1, c, [1, 1, 1]) - olj.lj_energy(poss[r], c, [1, 1, 1])
+        assert abs(dE[t] - ref) <= RTOL * max(1.0, abs(ref))
+
+
+def test_errors(lj_engine):
+    lj_engine.set_lj(1.0, 1.0, 3.0)
+    pos = np.zeros((2, 3)); pos[1, 0] = 1.2
+    with pytest.raises(Exception):          # periodic axis with zero lattice vector
+        _energy(lj_engine, pos, np.zeros((3, 3)), [1, 1, 1])
+    lj_engine.upload([pos], [np.ones(2, np.int32)], np.diag([9.0] * 3).reshape(1, 9), np.ones((1, 3), bool))
+    with pytest.raises(ValueError):         # atom index out of range
+        lj_engine.trial_delta_e([0, 1], [5], [0, 0], np.zeros((0, 3)), [])
+    with pytest.raises(ValueError):
+        lj_engine.trial_delta_e([0, 0], [], [0, 1], np.zeros((1, 3)), [1], rep=[3])
