@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Benchmark of the mcpy hot path on B200: trial-move delta-E evaluations per second.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "S2"): a 2 000-atom Lennard-Jones
+fluid (eps = sigma = 1, rc = 3, rho* = 0.6, periodic cubic box) and a batch of
+pre-generated GCMC proposals against it -- insertions, deletions and displacements
+in the ratio 1:1:1.  One "step" scores the whole batch once.
+
+  value      whole-job delta-E evaluations / s with the configuration and the
+             proposals already resident in HBM (one kernel launch per step, CUDA
+             events on the launching stream, L2 flushed between steps).
+  e2e        the same metric through the plug-in with HOST buffers: every step
+             uploads the configuration (cell list rebuilt) and the proposals and reads
+             the delta-E array back (B200Calculator.set_configuration +
+             trial_delta_energies -> mcpyb_upload_host + mcpyb_trial_delta_e_host).
+  dropin     what an unmodified mcpy run gets today: one
+             calculator.get_potential_energy(atoms) per trial, sequential, host buffers.
+  roofline   the trial kernel against the FP64 pipe (measured here with a DFMA
+             microbenchmark; MEASURED_PEAKS.json has no FP64 figure).  Tensor cores
+             are not used: nothing on this path is a dense contraction.
+  cpu_baseline / --impl reference
+             the reference's cost of one trial: one full-energy evaluation
+             (grand_canonical_ensemble.py:283-284) by the port of ASE's
+             LennardJones + NeighborList cost structure in oracle/lj.py, one process
+             per host core.  ASE itself (third-party, not vendored) is not installable
+             offline, hence kind = "port".
+
+With N > 1 (torchrun, one rank per GPU) every rank owns its own replica and its own
+proposal batch (weak scaling); there is no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'trial-move dE evals/sec'
+UNIT = 'dE evals/s'
+N_ATOMS = 2000
+RC = 3.0
+RHO = 0.6
+ALG_FLOP_PER_CANDIDATE = 17          # 3 sub + MIC + r2 + compare
+ALG_FLOP_PER_PAIR = 8                # extra work of an in-cutoff pair
+ALG_CANDIDATES_PER_SITE = 27 * RHO * RC ** 3      # 27-cell stencil at cell edge rc
+
+
+def workload_config(trials):
+    return {'workload': 'S2: 2000-atom LJ GCMC (eps=sigma=1, rc=3, rho*=0.6, cubic pbc), '
+                        f'{trials} proposals/step insert:delete:displace = 1:1:1',
+            'n_atoms': N_ATOMS, 'trials_per_step': trials, 'potential': 'ase.LennardJones(rc=3)',
+            'l2': 'flushed between timed steps (256 MiB write); working set itself is L2-resident'}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    """One trial = one full-energy evaluation of the trial configuration."""
+    positions, cell, pbc = args
+    from oracle.lj import AseStyleLJ
+    return AseStyleLJ(1.0, 1.0, RC).energy(positions, cell, pbc)
+
+
+def cpu_reference_rate(cfg, tb, n_sample, pool, cores):
+    from mcpy_b200.utils import synthetic
+    tasks = []
+    for t in range(n_sample):
+        p1, _ = synthetic.apply_trial(cfg, tb, t)
+        tasks.append((p1, cfg['cell'], cfg['pbc']))
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker, tasks, chunksize=max(1, n_sample // (cores * 2)))
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    from mcpy_b200.utils import synthetic
+    cfg = synthetic.s2_lj(N_ATOMS, RC, RHO)
+    cores = os.cpu_count() or 1
+    n_sample = 4 * cores
+    tb = synthetic.trial_batch(cfg, max(n_sample, 64), seed=7)
+    with mp.get_context('fork').Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_reference_rate(cfg, tb, min(cores, n_sample), pool, cores)
+        total_t, total_n = 0.0, 0
+        for _ in range(args.steps):
+            _, dt = cpu_reference_rate(cfg, tb, n_sample, pool, cores)
+            total_t += dt
+            total_n += n_sample
+    value = total_n / total_t
+    sample = (f'{n_sample} of the batch proposals per step, each one full-energy evaluation '
+              f'(ASE-style neighbour-list rebuild + per-atom loop, numpy), {cores} processes')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_t / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': workload_config(args.trials),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(max(mx)) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from mcpy_b200.calculators import B200Calculator
+    from mcpy_b200.utils import synthetic
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the mcpy_b200 engine has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    T = args.trials
+    cfg = synthetic.s2_lj(N_ATOMS, RC, RHO, seed=2 + rank)          # one replica per rank
+    tb = synthetic.trial_batch(cfg, T, seed=7 + 1000 * rank)
+    calc = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=RC, device=local)
+    eng = calc.engine
+    stream = torch.cuda.Stream(device=dev)          # a real (non-legacy) stream: events and the
+    torch.cuda.set_stream(stream)                    # engine's launches share it
+    eng.set_stream(stream.cuda_stream)
+
+    class _Cfg:                       # minimal ASE-shaped view for the plug-in calls
+        def __init__(self, c):
+            self.positions, self.numbers, self.cell, self.pbc = c['positions'], c['numbers'], c['cell'], c['pbc']
+    atoms = _Cfg(cfg)
+
+    # ---- resident inputs for the kernel-only number
+    calc.set_configuration(atoms)
+    d = {k: torch.from_numpy(np.ascontiguousarray(tb[k])).to(dev) for k in
+         ('old_off', 'old_idx', 'new_off', 'new_pos', 'new_Z')}
+    d_dE = torch.empty(T, dtype=torch.float64, device=dev)
+    d_pairs = torch.empty(T, dtype=torch.int32, device=dev)
+    n_old, n_new = int(tb['old_off'][-1]), int(tb['new_off'][-1])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def launch(pairs_ptr=0):
+        eng.trial_delta_e_dev(T, 0, d['old_off'].data_ptr(), d['old_idx'].data_ptr(),
+                              d['new_off'].data_ptr(), d['new_pos'].data_ptr(), d['new_Z'].data_ptr(),
+                              n_old, n_new, d_dE.data_ptr(), pairs_ptr)
+
+    launch(d_pairs.data_ptr())
+    torch.cuda.synchronize()
+    pairs_per_step = int(d_pairs.sum().item())
+    dE_ref = d_dE.clone()
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        launch()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = eng.launch_count
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()                                 # evict the working set from L2
+        starts[k].record(stream)
+        launch()
+        ends[k].record(stream)
+    barrier()
+    gpu_launches = eng.launch_count - launches0
+    kernel_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    kernel_ms = max_over_ranks(kernel_ms)
+    assert torch.equal(d_dE, dE_ref), 'trial kernel is not deterministic'
+    value = world * T * args.steps / (kernel_ms * 1e-3)
+    ms_per_step = kernel_ms / args.steps
+
+    # ---- end to end through the plug-in with host buffers
+    trials_host = {k: np.ascontiguousarray(tb[k]) for k in ('old_off', 'old_idx', 'new_off', 'new_pos', 'new_Z')}
+
+    def e2e_step():
+        calc.set_configuration(atoms)                                 # H2D config + cell list
+        return eng.trial_delta_e(trials_host['old_off'], trials_host['old_idx'], trials_host['new_off'],
+                                 trials_host['new_pos'], trials_host['new_Z'])   # H2D trials, D2H dE
+
+    for _ in range(args.warmup):
+        out = e2e_step()
+    assert np.array_equal(out, dE_ref.cpu().numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * T * args.steps / e2e_s
+    h2d = (N_ATOMS * (24 + 4) + 256) + sum(int(v.nbytes) for v in trials_host.values()) + 4 * T
+    d2h = 8 * T
+
+    # ---- drop-in chain: one get_potential_energy(atoms) per trial, sequential
+    n_chain = min(T, args.chain)
+    chain_cfgs = [synthetic.apply_trial(cfg, tb, t) for t in range(min(n_chain, 256))]
+
+    class _A:
+        pass
+    a = _A()
+    a.cell, a.pbc = cfg['cell'], cfg['pbc']
+    for p1, z1 in chain_cfgs[:8]:
+        a.positions, a.numbers = p1, z1
+        calc.get_potential_energy(a)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_chain):
+        a.positions, a.numbers = chain_cfgs[i % len(chain_cfgs)]
+        calc.get_potential_energy(a)
+    chain_s = max_over_ranks(time.perf_counter() - t0)
+    dropin_value = world * n_chain / chain_s
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the trial kernel (FP64 pipe)
+    sites = n_old + n_new
+    alg_flop = sites * ALG_CANDIDATES_PER_SITE * ALG_FLOP_PER_CANDIDATE + pairs_per_step * ALG_FLOP_PER_PAIR
+    peak = eng.fp64_peak_tflops()
+    achieved = alg_flop / (ms_per_step * 1e-3) / 1e12
+    pair_rate = sum_over_ranks(pairs_per_step) / (ms_per_step * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        n_sample = 4 * cores
+        with mp.get_context('fork').Pool(cores) as pool:
+            cpu_reference_rate(cfg, tb, cores, pool, cores)          # warm the workers
+            rate, dt = cpu_reference_rate(cfg, tb, n_sample, pool, cores)
+        cpu_baseline = {
+            'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'{n_sample} of the batch proposals, one full-energy evaluation each '
+                      f'(ASE-style neighbour-list rebuild + per-atom loop, numpy), {cores} processes, '
+                      f'{dt:.1f} s wall'}
+
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get('lj_trial_delta_kernel_dram_bytes_per_launch')
+        except Exception:
+            traffic = None
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': dict(workload_config(T), replicas_per_gpu=1,
+                       parallelism=f'replica-parallel x{world}, no data-path collective'),
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'api': 'B200Calculator.set_configuration + trial_delta_energies '
+                       '(mcpyb_upload_host + mcpyb_trial_delta_e_host), host numpy buffers',
+                'ms_per_step': 1e3 * e2e_s / args.steps},
+        'dropin': {'value': dropin_value, 'unit': UNIT, 'calls': n_chain,
+                   'api': 'calculator.get_potential_energy(atoms) per trial, sequential '
+                          '(mcpyb_potential_energies_host: H2D config, cell list, energy, D2H)',
+                   'us_per_call': 1e6 * chain_s / n_chain},
+        'pair_interactions_per_s': pair_rate,
+        'pairs_per_step': pairs_per_step,
+        'gpu_launches': int(gpu_launches),
+        'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                     'frac': achieved / peak if peak else None, 'traffic': traffic,
+                     'kernel': 'lj_trial_delta_kernel<32>',
+                     'algorithmic_flop_per_launch': alg_flop,
+                     'peak_source': 'measured here: DFMA microbenchmark (mcpyb_fp64_peak_tflops); '
+                                    'MEASURED_PEAKS.json holds only HBM and bf16 figures',
+                     'note': 'HBM is not the bound: the 64 KB configuration is L1/L2 resident'},
+        'clocks': clocks,
+    }
+    if cpu_baseline is not None:
+        line['cpu_baseline'] = cpu_baseline
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--trials', type=int, default=65536, help='proposals per step')
+    ap.add_argument('--chain', type=int, default=2000, help='sequential drop-in calls to time')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'b200':
+        args.warmup = 3
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -78,10 +78,9 @@ class _B200Core:
             atoms = getattr(self, 'atoms', None)
             if atoms is None:
                 raise ValueError('get_potential_energy() needs an Atoms object')
-        pos, num, cell, pbc = _config_of(atoms)
         self.n_energy_calls += 1
-        return float(self.engine.potential_energies([pos], [num], cell.reshape(1, 9),
-                                                    pbc.reshape(1, 3))[0])
+        return self.engine.potential_energy(atoms.positions, atoms.numbers,
+                                            np.asarray(atoms.cell, dtype=np.float64), atoms.pbc)
 
     def get_potential_energies(self, atoms_list, chunk_size=None) -> np.ndarray:
         """Energies of several (ragged) structures, one batched launch per chunk."""

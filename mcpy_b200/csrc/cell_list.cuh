@@ -167,30 +167,28 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
     }
     // cstart[c] is now the first slot of cell c (cstart[0] = 0, cstart[ncells] = n)
 
-    // ---- scatter; the per-cell cursors live in the second half of this replica's region
+    // ---- scatter (unordered) into the staging array; the per-cell cursors live in the
+    // second half of this replica's cell_start region
     int* cursor = cstart + (b.max_cells + 1);
     for (int c = tid; c < ncells; c += blockDim.x) cursor[c] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += blockDim.x) {
         const int id = b.cid[off + i];
         const int slot = cstart[id] + atomicAdd(&cursor[id], 1);
-        b.spos[off + slot] = b.upos[off + i];
+        b.stmp[off + slot] = b.upos[off + i];
     }
     __syncthreads();
 
-    // ---- order each segment by atom index (insertion sort, one thread per cell)
-    for (int c = tid; c < ncells; c += blockDim.x) {
-        const int s = cstart[c], e = cstart[c + 1];
-        for (int a = s + 1; a < e; ++a) {
-            const double4 key = b.spos[off + a];
-            const int ki = tag_index(tag_of(key));
-            int p = a - 1;
-            while (p >= s && tag_index(tag_of(b.spos[off + p])) > ki) {
-                b.spos[off + p + 1] = b.spos[off + p];
-                --p;
-            }
-            b.spos[off + p + 1] = key;
-        }
+    // ---- order each segment by atom index: rank = #atoms of the segment with a smaller
+    // index (segments hold a few dozen atoms, reads are broadcast-friendly, no serial chain)
+    for (int k = tid; k < n; k += blockDim.x) {
+        const double4 me = b.stmp[off + k];
+        const int mi = tag_index(tag_of(me));
+        const int id = b.cid[off + mi];
+        const int s = cstart[id], e = cstart[id + 1];
+        int rank = 0;
+        for (int a = s; a < e; ++a) rank += (tag_index(tag_of(b.stmp[off + a])) < mi) ? 1 : 0;
+        b.spos[off + s + rank] = me;
     }
     __syncthreads();
     if (tid == 0) g.error = s_err;

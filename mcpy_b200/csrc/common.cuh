@@ -68,6 +68,7 @@ struct BatchView {
     GridDesc* grid;               // [R]
     double4* upos;                // [cap_atoms]
     double4* spos;                // [cap_atoms]
+    double4* stmp;                // [cap_atoms] scratch of the counting sort
     int* cell_start;              // [R * cs_stride]: cell_start (max_cells+1) then scatter cursors
     int* cid;                     // [cap_atoms] scratch: cell id per atom
     int R;

@@ -111,12 +111,15 @@ struct mcpyb_engine {
     bool emt_state_valid = false;     // sigma1 / e_atom describe the resident batch
     std::vector<int> atom_off_host;
     DevBuf<GridDesc> grid;
-    DevBuf<double4> upos, spos;
-    DevBuf<int> cid, cell_start, atom_off;
+    DevBuf<double4> upos, spos, stmp;
+    DevBuf<int> cid, cell_start;
+    const int* d_atom_off = nullptr;      // points into stage_dev (header of the last upload)
     DevBuf<CellGeom> geom;
-    DevBuf<double> e_atom, sigma1, E;
-    DevBuf<int> pair_count, status;
-    DevBuf<long long> pairs;
+    DevBuf<double> e_atom, sigma1;
+    DevBuf<double> E;                     // one block: E[R] | pairs[R] (int64) | status[R] (int32)
+    DevBuf<int> pair_count;
+    long long* pairs_ptr() { return (long long*)(E.p + R); }
+    int* status_ptr() { return (int*)(E.p + 2 * (size_t)R); }
     DevBuf<unsigned char> stage_dev;      // H2D landing zone: header | positions | numbers
     PinBuf stage_pin, out_pin;
 
@@ -154,7 +157,7 @@ struct mcpyb_engine {
     }
     BatchView view() {
         BatchView v;
-        v.grid = grid.p; v.upos = upos.p; v.spos = spos.p; v.cell_start = cell_start.p;
+        v.grid = grid.p; v.upos = upos.p; v.spos = spos.p; v.stmp = stmp.p; v.cell_start = cell_start.p;
         v.cid = cid.p; v.R = R; v.max_cells = max_cells; v.cs_stride = 2 * (max_cells + 1);
         return v;
     }
@@ -242,14 +245,12 @@ int reserve_batch(mcpyb_engine* e, int R, int total, int max_n) {
     const size_t cs = 2 * (size_t)(e->max_cells + 1);
     CK(e->grid.reserve(R), "cudaMalloc grid");
     CK(e->geom.reserve(R), "cudaMalloc geom");
-    CK(e->atom_off.reserve(R + 1), "cudaMalloc atom_off");
     CK(e->cell_start.reserve(cs * R), "cudaMalloc cell_start");
-    CK(e->E.reserve(R), "cudaMalloc E");
-    CK(e->status.reserve(R), "cudaMalloc status");
-    CK(e->pairs.reserve(R), "cudaMalloc pairs");
+    CK(e->E.reserve(3 * (size_t)R), "cudaMalloc E");
     const size_t na = total > 0 ? total : 1;
     CK(e->upos.reserve(na), "cudaMalloc upos");
     CK(e->spos.reserve(na), "cudaMalloc spos");
+    CK(e->stmp.reserve(na), "cudaMalloc stmp");
     CK(e->cid.reserve(na), "cudaMalloc cid");
     CK(e->e_atom.reserve(na), "cudaMalloc e_atom");
     CK(e->sigma1.reserve(na), "cudaMalloc sigma1");
@@ -269,9 +270,7 @@ int upload_common(mcpyb_engine* e, int R, const int64_t* atom_off, const double*
     build_cell_list_kernel<<<R, CL_THREADS, 0, e->stream>>>(
         e->view(), d_pos, d_Z, d_off, d_geom, e->z_to_slot.p, e->rcut);
     LAUNCH_CHECK("build_cell_list_kernel");
-    // keep a device copy of atom_off for the energy kernels
-    CK(cudaMemcpyAsync(e->atom_off.p, d_off, (size_t)(R + 1) * sizeof(int), cudaMemcpyDeviceToDevice,
-                       e->stream), "copy atom_off");
+    e->d_atom_off = d_off;          // stays valid in stage_dev until the next upload
     e->have_batch = true;
     e->emt_state_valid = false;
     return MCPYB_OK;
@@ -323,11 +322,11 @@ int launch_energies(mcpyb_engine* e) {
         if (blocks > 148 * 64) blocks = 148 * 64;
         if (e->pot_kind == POT_LJ) {
             lj_atom_energy_kernel<<<blocks, 256, 0, e->stream>>>(
-                e->view(), e->atom_off.p, total, e->lj, e->e_atom.p, e->pair_count.p);
+                e->view(), e->d_atom_off, total, e->lj, e->e_atom.p, e->pair_count.p);
             LAUNCH_CHECK("lj_atom_energy_kernel");
         } else {
             emt_pair_kernel<<<blocks, 256, 0, e->stream>>>(
-                e->view(), e->atom_off.p, total, e->emt_dev.p, e->e_atom.p, e->sigma1.p, e->pair_count.p);
+                e->view(), e->d_atom_off, total, e->emt_dev.p, e->e_atom.p, e->sigma1.p, e->pair_count.p);
             LAUNCH_CHECK("emt_pair_kernel");
             const int eb = (total + 255) / 256;
             emt_embed_kernel<<<eb, 256, 0, e->stream>>>(
@@ -338,7 +337,7 @@ int launch_energies(mcpyb_engine* e) {
     }
     if (e->R > 0) {
         reduce_replica_kernel<<<e->R, 256, 0, e->stream>>>(
-            e->e_atom.p, e->atom_off.p, e->E.p, e->pair_count.p, e->pairs.p, e->grid.p, e->status.p);
+            e->e_atom.p, e->d_atom_off, e->E.p, e->pair_count.p, e->pairs_ptr(), e->grid.p, e->status_ptr());
         LAUNCH_CHECK("reduce_replica_kernel");
     }
     return MCPYB_OK;
@@ -380,10 +379,10 @@ void mcpyb_destroy(mcpyb_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release();
-    e->cid.release(); e->cell_start.release(); e->atom_off.release(); e->geom.release();
-    e->e_atom.release(); e->sigma1.release(); e->E.release(); e->pair_count.release(); e->status.release();
-    e->pairs.release(); e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
+    e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release(); e->stmp.release();
+    e->cid.release(); e->cell_start.release(); e->geom.release();
+    e->e_atom.release(); e->sigma1.release(); e->E.release(); e->pair_count.release();
+    e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
     e->nl_i.release(); e->nl_j.release(); e->nl_S.release(); e->nl_r2.release(); e->nl_cursor.release();
     e->fv_grid.release(); e->fv_spheres.release(); e->fv_cell_start.release(); e->fv_cursor.release();
@@ -560,12 +559,10 @@ int mcpyb_energies_host(mcpyb_engine* e, double* energies_out, int64_t* pairs_ou
     const int R = e->R;
     if (R == 0) return MCPYB_OK;
     if (!energies_out) return e->fail(MCPYB_ERR_ARG, "energies_out is NULL");
-    // one pinned block: E[R] | pairs[R] | status[R]
+    // one device block -> one pinned block: E[R] | pairs[R] | status[R]
     const size_t eb = (size_t)R * sizeof(double), pb = (size_t)R * sizeof(long long), sb = (size_t)R * sizeof(int);
     CK(e->out_pin.reserve(eb + pb + sb), "cudaMallocHost out");
-    CK(cudaMemcpyAsync(e->out_pin.p, e->E.p, eb, cudaMemcpyDeviceToHost, e->stream), "D2H E");
-    CK(cudaMemcpyAsync(e->out_pin.p + eb + pb, e->status.p, sb, cudaMemcpyDeviceToHost, e->stream), "D2H status");
-    if (pairs_out) CK(cudaMemcpyAsync(e->out_pin.p + eb, e->pairs.p, pb, cudaMemcpyDeviceToHost, e->stream), "D2H pairs");
+    CK(cudaMemcpyAsync(e->out_pin.p, e->E.p, eb + pb + sb, cudaMemcpyDeviceToHost, e->stream), "D2H energies");
     CK(cudaStreamSynchronize(e->stream), "sync energies");
     const int* st = (const int*)(e->out_pin.p + eb + pb);
     for (int r = 0; r < R; ++r) {
@@ -608,29 +605,20 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     TrialBatch tb;
     tb.T = T; tb.rep = d_rep; tb.old_off = d_old_off; tb.old_idx = d_old_idx;
     tb.new_off = d_new_off; tb.new_pos = d_new_pos; tb.new_Z = d_new_Z;
+    // One warp per trial whatever T is: the summation order of a trial -- and therefore
+    // every bit of its delta-E -- does not depend on the batch it arrives in.
+    int blocks = (T + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
     if (e->pot_kind == POT_LJ) {
-        if (T >= 148 * 4) {
-            int blocks = (T + 7) / 8;
-            if (blocks > 148 * 32) blocks = 148 * 32;
-            lj_trial_delta_kernel<32><<<blocks, 256, 0, e->stream>>>(e->view(), tb, e->lj, d_dE, d_pairs);
-        } else {
-            lj_trial_delta_kernel<256><<<T, 256, 0, e->stream>>>(e->view(), tb, e->lj, d_dE, d_pairs);
-        }
+        lj_trial_delta_kernel<32><<<blocks, 256, 0, e->stream>>>(e->view(), tb, e->lj, d_dE, d_pairs);
         LAUNCH_CHECK("lj_trial_delta_kernel");
     } else {
         if (!e->emt_state_valid) {
             int rc = launch_energies(e);       // sigma1 / e_atom of the resident batch
             if (rc != MCPYB_OK) return rc;
         }
-        if (T >= 148 * 4) {
-            int blocks = (T + 7) / 8;
-            if (blocks > 148 * 32) blocks = 148 * 32;
-            emt_trial_delta_kernel<32><<<blocks, 256, 0, e->stream>>>(
-                e->view(), tb, e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p, d_dE, d_pairs);
-        } else {
-            emt_trial_delta_kernel<256><<<T, 256, 0, e->stream>>>(
-                e->view(), tb, e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p, d_dE, d_pairs);
-        }
+        emt_trial_delta_kernel<32><<<blocks, 256, 0, e->stream>>>(
+            e->view(), tb, e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p, d_dE, d_pairs);
         LAUNCH_CHECK("emt_trial_delta_kernel");
     }
     return MCPYB_OK;

@@ -30,6 +30,8 @@ class Engine:
         self._h = h
         self.device = int(device)
         self.potential = None
+        self._off1 = np.zeros(2, dtype=np.int64)      # scratch of the single-configuration fast path
+        self._e1 = np.zeros(1, dtype=np.float64)
 
     # -- plumbing ------------------------------------------------------------
     def close(self):
@@ -143,6 +145,26 @@ class Engine:
         self._R = R
         self._ntot = int(off[-1])
         return E
+
+    def potential_energy(self, positions, numbers, cell, pbc) -> float:
+        """Single configuration, minimal marshalling (the per-trial drop-in call)."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        num = np.ascontiguousarray(numbers, dtype=np.int32)
+        cell = np.ascontiguousarray(cell, dtype=np.float64)
+        pbc = np.ascontiguousarray(pbc, dtype=np.uint8)
+        n = pos.shape[0]
+        if pos.size != 3 * n or num.size != n or cell.size != 9 or pbc.size != 3:
+            raise ValueError('positions (n,3), numbers (n,), cell (3,3), pbc (3,) expected')
+        off = self._off1
+        off[1] = n
+        rc = self._lib.mcpyb_potential_energies_host(
+            self._h, 1, off.ctypes.data, pos.ctypes.data, num.ctypes.data, cell.ctypes.data,
+            pbc.ctypes.data, self._e1.ctypes.data)
+        if rc != 0:
+            self._check(rc)
+        self._R = 1
+        self._ntot = n
+        return float(self._e1[0])
 
     def atom_energies(self, want_sigma1=False):
         e = np.empty(self._ntot)
