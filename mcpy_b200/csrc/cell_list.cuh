@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1)
 build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
                        const int* __restrict__ raw_Z, const int* __restrict__ atom_off,
                        const CellGeom* __restrict__ geom, const int* __restrict__ z_to_slot,
-                       double rcut) {
+                       double rcut, int subdiv) {
     __shared__ double s_red[32];
     __shared__ int s_scan[CL_THREADS];
     __shared__ int s_carry;
@@ -83,27 +83,21 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
         ghi[d] = block_reduce_minmax(hi[d], false, s_red);
     }
 
-    // ---- binning grid (thread 0), capped at max_cells
+    // ---- binning grid (thread 0), capped at max_cells.  Cell edge >= rcut' / subdiv, so the
+    // stencil half width is m = ceil(rcut' / edge) <= subdiv cells (more only for boxes thinner
+    // than the cutoff, where the extra offsets are periodic images of the single cell).
     if (tid == 0) {
         const double rc_safe = rcut * (1.0 + 1e-12);
-        double want[3];
+        double want[3], width[3], width_frac[3];
         for (int d = 0; d < 3; ++d) {
-            double width_frac;
-            if (g.pbc[d]) { g.lo[d] = 0.0; width_frac = 1.0; }
-            else if (n > 0) { g.lo[d] = glo[d]; width_frac = ghi[d] - glo[d]; }
-            else { g.lo[d] = 0.0; width_frac = 0.0; }
-            const double width = width_frac * g.height[d];        // Angstrom, perpendicular
-            double nc = floor(width / rc_safe);
+            if (g.pbc[d]) { g.lo[d] = 0.0; width_frac[d] = 1.0; }
+            else if (n > 0) { g.lo[d] = glo[d]; width_frac[d] = ghi[d] - glo[d]; }
+            else { g.lo[d] = 0.0; width_frac[d] = 0.0; }
+            width[d] = width_frac[d] * g.height[d];               // Angstrom, perpendicular
+            double nc = floor(width[d] * (double)subdiv / rc_safe);
             if (!(nc >= 1.0)) nc = 1.0;
             if (nc > 1024.0) nc = 1024.0;
             want[d] = nc;
-            // stencil half width: 1, or the number of periodic images a thin box needs
-            int m = 1;
-            if (g.pbc[d] && width < rc_safe) m = (int)ceil(rc_safe / width);
-            g.m[d] = m;
-            g.scale[d] = 0.0;   // set below
-            // stash width_frac in scale for the second pass
-            g.scale[d] = width_frac;
         }
         double total = want[0] * want[1] * want[2];
         if (total > (double)b.max_cells) {
@@ -118,9 +112,19 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
             }
         }
         for (int d = 0; d < 3; ++d) {
-            g.ncell[d] = (int)want[d];
-            const double width_frac = g.scale[d];
-            g.scale[d] = (width_frac > 0.0) ? want[d] / width_frac : 0.0;
+            const int nc = (int)want[d];
+            g.ncell[d] = nc;
+            g.scale[d] = (width_frac[d] > 0.0) ? want[d] / width_frac[d] : 0.0;
+            int m;
+            if (g.pbc[d]) {
+                m = (int)ceil(rc_safe * want[d] / width[d]);
+            } else {
+                m = (width[d] > 0.0) ? (int)ceil(rc_safe * want[d] / width[d]) : 0;
+                if (m > nc - 1) m = nc - 1;                      // offsets beyond the grid are clipped anyway
+            }
+            if (m < 0) m = 0;
+            if (m > 64) { m = 64; s_err |= 8; }
+            g.m[d] = m;
         }
         g.ncells = g.ncell[0] * g.ncell[1] * g.ncell[2];
     }
@@ -190,6 +194,31 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
         for (int a = s; a < e; ++a) rank += (tag_index(tag_of(b.stmp[off + a])) < mi) ? 1 : 0;
         b.spos[off + s + rank] = me;
     }
+    __syncthreads();
+
+    // ---- work items of the lane-per-atom kernels: cell c contributes ceil(count/32) chunks of up
+    // to 32 atoms; item_start (exclusive prefix, ncells+1 entries) reuses the cursor region.
+    int* item_start = cursor;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ncells; base += blockDim.x) {
+        const int c = base + tid;
+        const int v = (c < ncells) ? (cstart[c + 1] - cstart[c] + 31) / 32 : 0;
+        s_scan[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+            int t = (tid >= o) ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += t;
+            __syncthreads();
+        }
+        const int incl = s_scan[tid] + s_carry;
+        __syncthreads();
+        if (c < ncells) item_start[c] = incl - v;
+        if (tid == blockDim.x - 1) s_carry = incl;
+        __syncthreads();
+    }
+    if (tid == 0) { item_start[ncells] = s_carry; g.nitems = s_carry; }
     __syncthreads();
     if (tid == 0) g.error = s_err;
 }

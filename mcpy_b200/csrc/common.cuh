@@ -33,6 +33,7 @@ struct GridDesc {
     int n;               // atoms in this replica
     int atom_off;        // first atom of this replica in upos/spos
     int ncells;          // ncell[0]*ncell[1]*ncell[2]
+    int nitems;          // sum over cells of ceil(count / 32): work items of the lane-per-atom kernels
     int error;           // nonzero: capacity exceeded / wrap out of range
 };
 

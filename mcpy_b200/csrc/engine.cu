@@ -15,6 +15,7 @@
 #include "cell_list.cuh"
 #include "stencil.cuh"
 #include "lj_kernels.cuh"
+#include "site_kernels.cuh"
 #include "emt_kernels.cuh"
 #include "free_volume.cuh"
 
@@ -96,6 +97,7 @@ struct mcpyb_engine {
 
     // potential
     int pot_kind = POT_NONE;
+    int subdiv = 1;                       // cells per cutoff length (stencil half width)
     double rcut = 0.0;
     LJParams lj{};
     EmtTable emt_host{};
@@ -106,6 +108,7 @@ struct mcpyb_engine {
     // resident batch
     int R = 0;
     int total_atoms = 0;
+    int max_n = 0;                        // largest configuration of the resident batch
     int max_cells = 0;
     bool have_batch = false;
     bool emt_state_valid = false;     // sigma1 / e_atom describe the resident batch
@@ -128,6 +131,11 @@ struct mcpyb_engine {
     PinBuf trial_pin, trial_out_pin;
     DevBuf<double> dE;
     DevBuf<int> tpairs;
+    // second-generation trial pipeline (site_kernels.cuh)
+    DevBuf<int> tw_int;                   // site_trial | site_bin | sorted | site_cnt | totals
+    DevBuf<int> tw_bins;                  // bin_count | item_start | bin_cursor
+    DevBuf<double4> tw_pos;
+    DevBuf<double> tw_E;
 
     // neighbour list scratch
     DevBuf<int> nl_i, nl_j, nl_S;
@@ -268,7 +276,7 @@ int upload_common(mcpyb_engine* e, int R, const int64_t* atom_off, const double*
     const CellGeom* d_geom = (const CellGeom*)(d_header + off_bytes);
     (void)atom_off; (void)cells; (void)pbc;
     build_cell_list_kernel<<<R, CL_THREADS, 0, e->stream>>>(
-        e->view(), d_pos, d_Z, d_off, d_geom, e->z_to_slot.p, e->rcut);
+        e->view(), d_pos, d_Z, d_off, d_geom, e->z_to_slot.p, e->rcut, e->subdiv);
     LAUNCH_CHECK("build_cell_list_kernel");
     e->d_atom_off = d_off;          // stays valid in stage_dev until the next upload
     e->have_batch = true;
@@ -321,9 +329,13 @@ int launch_energies(mcpyb_engine* e) {
         int blocks = (total + warps_per_block - 1) / warps_per_block;
         if (blocks > 148 * 64) blocks = 148 * 64;
         if (e->pot_kind == POT_LJ) {
-            lj_atom_energy_kernel<<<blocks, 256, 0, e->stream>>>(
-                e->view(), e->d_atom_off, total, e->lj, e->e_atom.p, e->pair_count.p);
-            LAUNCH_CHECK("lj_atom_energy_kernel");
+            // lane-per-atom: work items = (cell, chunk of 32 atoms); grid.y = replica
+            long long est = (long long)(e->max_n < e->max_cells ? e->max_n : e->max_cells) + e->max_n / 32 + 1;
+            int gx = (int)((est + 7) / 8);
+            if (gx > 148 * 8) gx = 148 * 8;
+            if (gx < 1) gx = 1;
+            lj_cell_energy_kernel<<<dim3(gx, e->R), 256, 0, e->stream>>>(e->view(), e->lj, e->e_atom.p, e->pair_count.p);
+            LAUNCH_CHECK("lj_cell_energy_kernel");
         } else {
             emt_pair_kernel<<<blocks, 256, 0, e->stream>>>(
                 e->view(), e->d_atom_off, total, e->emt_dev.p, e->e_atom.p, e->sigma1.p, e->pair_count.p);
@@ -384,6 +396,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     e->e_atom.release(); e->sigma1.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
+    e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release();
     e->nl_i.release(); e->nl_j.release(); e->nl_S.release(); e->nl_r2.release(); e->nl_cursor.release();
     e->fv_grid.release(); e->fv_spheres.release(); e->fv_cell_start.release(); e->fv_cursor.release();
     e->fv_cid.release(); e->fv_points.release(); e->fv_pos.release(); e->fv_radii.release(); e->fv_small.release();
@@ -417,6 +430,7 @@ int mcpyb_set_lj(mcpyb_engine* e, double epsilon, double sigma, double rc) {
     if (!(rc > 0.0)) rc = 3.0 * sigma;
     cudaSetDevice(e->device);
     e->pot_kind = POT_LJ;
+    e->subdiv = 2;
     e->rcut = rc;
     e->lj.eps4 = 4.0 * epsilon;
     e->lj.sigma2 = sigma * sigma;
@@ -463,6 +477,7 @@ int mcpyb_set_emt(mcpyb_engine* e) {
     for (int a = 0; a < ns; ++a)
         for (int b = 0; b < ns; ++b) t.ksi[a][b] = t.sp[b].n0 / t.sp[a].n0;
     e->pot_kind = POT_EMT;
+    e->subdiv = 1;
     e->rcut = t.rc_list;
     CK(e->emt_dev.reserve(1), "cudaMalloc emt table");
     CK(e->z_to_slot.reserve(120), "cudaMalloc z_to_slot");
@@ -494,7 +509,7 @@ int mcpyb_upload_host(mcpyb_engine* e, int R, const int64_t* atom_off, const dou
     e->have_batch = false;
     rc = reserve_batch(e, R > 0 ? R : 1, total, max_n);
     if (rc != MCPYB_OK) return rc;
-    e->R = R; e->total_atoms = total;
+    e->R = R; e->total_atoms = total; e->max_n = max_n;
     if (R == 0) { e->have_batch = true; e->atom_off_host.assign(1, 0); return MCPYB_OK; }
     // one pinned block, one H2D copy: header | positions | numbers
     const size_t hb = header_bytes(R);
@@ -528,7 +543,7 @@ int mcpyb_upload_dev(mcpyb_engine* e, int R, const int64_t* atom_off, const doub
     e->have_batch = false;
     rc = reserve_batch(e, R > 0 ? R : 1, total, max_n);
     if (rc != MCPYB_OK) return rc;
-    e->R = R; e->total_atoms = total;
+    e->R = R; e->total_atoms = total; e->max_n = max_n;
     if (R == 0) { e->have_batch = true; e->atom_off_host.assign(1, 0); return MCPYB_OK; }
     const size_t hb = header_bytes(R);
     // the previous upload may still be reading the pinned header: wait for it
@@ -600,7 +615,8 @@ int mcpyb_atom_energies_host(mcpyb_engine* e, double* e_atom_out, double* sigma1
 // ---- trial moves ---------------------------------------------------------------
 static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int32_t* d_old_off,
                          const int32_t* d_old_idx, const int32_t* d_new_off, const double* d_new_pos,
-                         const int32_t* d_new_Z, double* d_dE, int32_t* d_pairs) {
+                         const int32_t* d_new_Z, int n_old_total, int n_new_total,
+                         double* d_dE, int32_t* d_pairs) {
     if (T == 0) return MCPYB_OK;
     TrialBatch tb;
     tb.T = T; tb.rep = d_rep; tb.old_off = d_old_off; tb.old_idx = d_old_idx;
@@ -610,8 +626,37 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     int blocks = (T + 7) / 8;
     if (blocks > 148 * 32) blocks = 148 * 32;
     if (e->pot_kind == POT_LJ) {
-        lj_trial_delta_kernel<32><<<blocks, 256, 0, e->stream>>>(e->view(), tb, e->lj, d_dE, d_pairs);
-        LAUNCH_CHECK("lj_trial_delta_kernel");
+        const int nsites = n_old_total + n_new_total;
+        TrialWork w;
+        w.nsites = nsites; w.n_old = n_old_total;
+        w.bin_stride = e->max_cells; w.nbins = e->R * e->max_cells;
+        const size_t ns = (size_t)(nsites > 0 ? nsites : 1), nbp = (size_t)w.nbins + 1;
+        CK(e->tw_int.reserve(4 * ns + 4), "cudaMalloc trial work");
+        CK(e->tw_bins.reserve(3 * nbp), "cudaMalloc trial bins");
+        CK(e->tw_pos.reserve(ns), "cudaMalloc trial work");
+        CK(e->tw_E.reserve(ns), "cudaMalloc trial work");
+        w.site_trial = e->tw_int.p; w.site_bin = e->tw_int.p + ns; w.sorted = e->tw_int.p + 2 * ns;
+        w.site_cnt = e->tw_int.p + 3 * ns; w.totals = e->tw_int.p + 4 * ns;
+        w.bin_count = e->tw_bins.p; w.item_start = e->tw_bins.p + nbp; w.bin_cursor = e->tw_bins.p + 2 * nbp;
+        w.site_pos = e->tw_pos.p; w.site_E = e->tw_E.p;
+        CK(cudaMemsetAsync(w.bin_count, 0, nbp * sizeof(int), e->stream), "memset bins");
+        if (nsites > 0) {
+            trial_sites_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(e->view(), tb, w);
+            LAUNCH_CHECK("trial_sites_kernel");
+        }
+        trial_scan_kernel<<<1, 1024, 0, e->stream>>>(w);
+        LAUNCH_CHECK("trial_scan_kernel");
+        if (nsites > 0) {
+            trial_scatter_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(w);
+            LAUNCH_CHECK("trial_scatter_kernel");
+            long long est = nsites / 32 + (nsites < w.nbins ? nsites : w.nbins) + 1;
+            int rb = (int)((est + 7) / 8);
+            if (rb > 148 * 16) rb = 148 * 16;
+            lj_trial_rows_kernel<<<rb, 256, 0, e->stream>>>(e->view(), tb, w, e->lj);
+            LAUNCH_CHECK("lj_trial_rows_kernel");
+        }
+        lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
+        LAUNCH_CHECK("lj_trial_combine_kernel");
     } else {
         if (!e->emt_state_valid) {
             int rc = launch_energies(e);       // sigma1 / e_atom of the resident batch
@@ -633,8 +678,9 @@ int mcpyb_trial_delta_e_dev(mcpyb_engine* e, int T, const int32_t* d_rep, const 
     if (!e->have_batch) return e->fail(MCPYB_ERR_STATE, "no resident batch (call mcpyb_upload_* first)");
     if (T < 0 || (T > 0 && (!d_old_off || !d_new_off || !d_dE_out))) return e->fail(MCPYB_ERR_ARG, "bad trial arguments");
     if (e->pot_kind == POT_EMT && n_new_total > 0 && !d_new_Z) return e->fail(MCPYB_ERR_ARG, "EMT trials need new_Z");
-    (void)n_old_total;
-    return launch_trials(e, T, d_rep, d_old_off, d_old_idx, d_new_off, d_new_pos, d_new_Z, d_dE_out, d_pairs_out);
+    if (n_old_total < 0 || n_new_total < 0) return e->fail(MCPYB_ERR_ARG, "negative site counts");
+    return launch_trials(e, T, d_rep, d_old_off, d_old_idx, d_new_off, d_new_pos, d_new_Z, n_old_total, n_new_total,
+                         d_dE_out, d_pairs_out);
 }
 
 int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const int32_t* old_off,
@@ -689,7 +735,7 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
     unsigned char* d = e->trial_dev.p;
     int rc = launch_trials(e, T, (const int32_t*)(d + o_rep), (const int32_t*)(d + o_oo), (const int32_t*)(d + o_oi),
                            (const int32_t*)(d + o_no), (const double*)(d + o_np),
-                           new_Z ? (const int32_t*)(d + o_nz) : nullptr, e->dE.p, e->tpairs.p);
+                           new_Z ? (const int32_t*)(d + o_nz) : nullptr, n_old, n_new, e->dE.p, e->tpairs.p);
     if (rc != MCPYB_OK) return rc;
     const size_t ob = (size_t)T * sizeof(double), pb = (size_t)T * sizeof(int);
     CK(e->trial_out_pin.reserve(ob + pb), "cudaMallocHost trial out");
