@@ -127,6 +127,19 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
             g.m[d] = m;
         }
         g.ncells = g.ncell[0] * g.ncell[1] * g.ncell[2];
+        // fp32 screening: reference point = grid origin, margin from the largest coordinate
+        double ext = 0.0;
+        int thin = 0;
+        for (int d = 0; d < 3; ++d) {
+            g.origin[d] = g.lo[0] * g.cell[d] + g.lo[1] * g.cell[3 + d] + g.lo[2] * g.cell[6 + d];
+            ext += width_frac[d] * sqrt(g.cell[3 * d] * g.cell[3 * d] + g.cell[3 * d + 1] * g.cell[3 * d + 1]
+                                        + g.cell[3 * d + 2] * g.cell[3 * d + 2]);
+            if (g.pbc[d] && !(g.height[d] > rc_safe)) thin = 1;
+        }
+        g.thin = thin;
+        const double margin = 64.0 * 5.9604644775390625e-08 * (ext + 2.0 * rc_safe) + 1e-30;
+        const double rs = rc_safe + margin;
+        g.screen_r2 = (float)(rs * rs * (1.0 + 1e-6));
     }
     __syncthreads();
 
@@ -193,6 +206,10 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
         int rank = 0;
         for (int a = s; a < e; ++a) rank += (tag_index(tag_of(b.stmp[off + a])) < mi) ? 1 : 0;
         b.spos[off + s + rank] = me;
+        int w0, w1, w2;
+        unpack_wraps(tag_wraps(tag_of(me)), w0, w1, w2);
+        const float3 f = screen_pos(g, me.x, me.y, me.z, w0, w1, w2);
+        b.fpos[off + s + rank] = make_float4(f.x, f.y, f.z, __int_as_float(mi));
     }
     __syncthreads();
 

@@ -34,6 +34,9 @@ struct GridDesc {
     int atom_off;        // first atom of this replica in upos/spos
     int ncells;          // ncell[0]*ncell[1]*ncell[2]
     int nitems;          // sum over cells of ceil(count / 32): work items of the lane-per-atom kernels
+    int thin;            // some periodic height <= rcut': moved atoms can see their own images
+    double origin[3];    // cartesian reference point of the fp32 screening copies (grid origin)
+    float screen_r2;     // (rcut + fp32 error margin)^2: fp32 screen never drops a true pair
     int error;           // nonzero: capacity exceeded / wrap out of range
 };
 
@@ -70,6 +73,7 @@ struct BatchView {
     double4* upos;                // [cap_atoms]
     double4* spos;                // [cap_atoms]
     double4* stmp;                // [cap_atoms] scratch of the counting sort
+    float4* fpos;                 // [cap_atoms] fp32 screening copy of spos: wrapped position - origin, .w = index bits
     int* cell_start;              // [R * cs_stride]: cell_start (max_cells+1) then scatter cursors
     int* cid;                     // [cap_atoms] scratch: cell id per atom
     int R;
@@ -156,6 +160,15 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Wrapped position relative to the grid origin, rounded to fp32 (screening copy).
+__device__ __forceinline__ float3 screen_pos(const GridDesc& g, double x, double y, double z, int w0, int w1, int w2) {
+    const double a = (double)w0, b = (double)w1, c = (double)w2;
+    const double xw = x - (a * g.cell[0] + b * g.cell[3] + c * g.cell[6]) - g.origin[0];
+    const double yw = y - (a * g.cell[1] + b * g.cell[4] + c * g.cell[7]) - g.origin[1];
+    const double zw = z - (a * g.cell[2] + b * g.cell[5] + c * g.cell[8]) - g.origin[2];
+    return make_float3((float)xw, (float)yw, (float)zw);
 }
 
 #define MCPYB_CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)

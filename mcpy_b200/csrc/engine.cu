@@ -115,6 +115,7 @@ struct mcpyb_engine {
     std::vector<int> atom_off_host;
     DevBuf<GridDesc> grid;
     DevBuf<double4> upos, spos, stmp;
+    DevBuf<float4> fpos;
     DevBuf<int> cid, cell_start;
     const int* d_atom_off = nullptr;      // points into stage_dev (header of the last upload)
     DevBuf<CellGeom> geom;
@@ -165,7 +166,7 @@ struct mcpyb_engine {
     }
     BatchView view() {
         BatchView v;
-        v.grid = grid.p; v.upos = upos.p; v.spos = spos.p; v.stmp = stmp.p; v.cell_start = cell_start.p;
+        v.grid = grid.p; v.upos = upos.p; v.spos = spos.p; v.stmp = stmp.p; v.fpos = fpos.p; v.cell_start = cell_start.p;
         v.cid = cid.p; v.R = R; v.max_cells = max_cells; v.cs_stride = 2 * (max_cells + 1);
         return v;
     }
@@ -259,6 +260,7 @@ int reserve_batch(mcpyb_engine* e, int R, int total, int max_n) {
     CK(e->upos.reserve(na), "cudaMalloc upos");
     CK(e->spos.reserve(na), "cudaMalloc spos");
     CK(e->stmp.reserve(na), "cudaMalloc stmp");
+    CK(e->fpos.reserve(na), "cudaMalloc fpos");
     CK(e->cid.reserve(na), "cudaMalloc cid");
     CK(e->e_atom.reserve(na), "cudaMalloc e_atom");
     CK(e->sigma1.reserve(na), "cudaMalloc sigma1");
@@ -331,10 +333,10 @@ int launch_energies(mcpyb_engine* e) {
         if (e->pot_kind == POT_LJ) {
             // lane-per-atom: work items = (cell, chunk of 32 atoms); grid.y = replica
             long long est = (long long)(e->max_n < e->max_cells ? e->max_n : e->max_cells) + e->max_n / 32 + 1;
-            int gx = (int)((est + 7) / 8);
-            if (gx > 148 * 8) gx = 148 * 8;
+            int gx = (int)((est + SITE_WARPS - 1) / SITE_WARPS);
+            if (gx > 148 * 16) gx = 148 * 16;
             if (gx < 1) gx = 1;
-            lj_cell_energy_kernel<<<dim3(gx, e->R), 256, 0, e->stream>>>(e->view(), e->lj, e->e_atom.p, e->pair_count.p);
+            lj_cell_energy_kernel<<<dim3(gx, e->R), 32 * SITE_WARPS, 0, e->stream>>>(e->view(), e->lj, e->e_atom.p, e->pair_count.p);
             LAUNCH_CHECK("lj_cell_energy_kernel");
         } else {
             emt_pair_kernel<<<blocks, 256, 0, e->stream>>>(
@@ -391,7 +393,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release(); e->stmp.release();
+    e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release(); e->stmp.release(); e->fpos.release();
     e->cid.release(); e->cell_start.release(); e->geom.release();
     e->e_atom.release(); e->sigma1.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
@@ -640,19 +642,17 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
         w.bin_count = e->tw_bins.p; w.item_start = e->tw_bins.p + nbp; w.bin_cursor = e->tw_bins.p + 2 * nbp;
         w.site_pos = e->tw_pos.p; w.site_E = e->tw_E.p;
         CK(cudaMemsetAsync(w.bin_count, 0, nbp * sizeof(int), e->stream), "memset bins");
-        if (nsites > 0) {
-            trial_sites_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(e->view(), tb, w);
-            LAUNCH_CHECK("trial_sites_kernel");
-        }
+        trial_sites_kernel<<<(T + 255) / 256, 256, 0, e->stream>>>(e->view(), tb, w);
+        LAUNCH_CHECK("trial_sites_kernel");
         trial_scan_kernel<<<1, 1024, 0, e->stream>>>(w);
         LAUNCH_CHECK("trial_scan_kernel");
         if (nsites > 0) {
             trial_scatter_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(w);
             LAUNCH_CHECK("trial_scatter_kernel");
             long long est = nsites / 32 + (nsites < w.nbins ? nsites : w.nbins) + 1;
-            int rb = (int)((est + 7) / 8);
-            if (rb > 148 * 16) rb = 148 * 16;
-            lj_trial_rows_kernel<<<rb, 256, 0, e->stream>>>(e->view(), tb, w, e->lj);
+            int rb = (int)((est + SITE_WARPS - 1) / SITE_WARPS);
+            if (rb > 148 * 32) rb = 148 * 32;
+            lj_trial_rows_kernel<<<rb, 32 * SITE_WARPS, 0, e->stream>>>(e->view(), tb, w, e->lj);
             LAUNCH_CHECK("lj_trial_rows_kernel");
         }
         lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
