@@ -139,6 +139,33 @@ int mcpyb_free_volume_count_dev(mcpyb_engine* e, const double* d_points, int64_t
                                 const double* offset3, const double* shifts, int nshift,
                                 uint64_t* d_counts2);
 
+/* ---- free volume with the sample points regenerated on the GPU ---------------
+ * The reference draws its points from numpy's PCG64 (np.random.default_rng(seed),
+ * mcpy/cell/cell.py:25).  These two calls take that generator's 128-bit state and
+ * increment (as {high, low} 64-bit words, from Generator.bit_generator.state) and
+ * reproduce the same stream on the device, so no points are uploaded.
+ * Sphere: SphericalCell._sample_sphere_points (spherical_cell.py:88-106): cube rejection,
+ * first P accepted in stream order, + center.  *draws_out = doubles consumed; the host
+ * generator must be advanced by that many (bit_generator.advance).
+ * Box: CustomCell.calculate_volume (custom_cell.py:74-75): rng.random((P,3)) @ dims,
+ * 3 P doubles consumed.                                                        */
+int mcpyb_sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
+                                   const uint64_t* inc_hi_lo, int64_t P, double radius,
+                                   const double* center3, const double* positions,
+                                   const double* radii, int64_t M,
+                                   int64_t* counts_out, int64_t* draws_out);
+int mcpyb_box_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
+                                const uint64_t* inc_hi_lo, int64_t P, const double* dims9,
+                                const double* positions, const double* radii, int64_t M,
+                                const double* offset3, const double* shifts, int nshift,
+                                int64_t* counts_out);
+
+/* Host-side evaluation of the same PCG64 restatement (no GPU needed): n doubles of
+ * Generator.random() after skipping `skip` draws.  Used by the CPU tests to pin the
+ * restatement to numpy.                                                          */
+int mcpyb_pcg64_host_doubles(const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo,
+                             uint64_t skip, int64_t n, double* out);
+
 /* ---- instrumentation ---------------------------------------------------- */
 /* Measured FP64 FMA throughput of this GPU (TFLOP/s, 2 flop per DFMA): the
  * roofline denominator for the pair kernels.                                 */

@@ -18,6 +18,7 @@
 #include "site_kernels.cuh"
 #include "emt_kernels.cuh"
 #include "free_volume.cuh"
+#include "pcg64.cuh"
 
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread (roofline denominator
 // for the pair kernels; MEASURED_PEAKS.json only has HBM and bf16 numbers).
@@ -151,6 +152,9 @@ struct mcpyb_engine {
     DevBuf<unsigned long long> fv_counts;
     DevBuf<unsigned char> fv_mask;
     PinBuf fv_pin;
+    DevBuf<int> pcg_count;
+    DevBuf<long long> pcg_prefix;
+    DevBuf<SphereCtl> pcg_ctl;
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -403,6 +407,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     e->fv_grid.release(); e->fv_spheres.release(); e->fv_cell_start.release(); e->fv_cursor.release();
     e->fv_cid.release(); e->fv_points.release(); e->fv_pos.release(); e->fv_radii.release(); e->fv_small.release();
     e->fv_counts.release(); e->fv_mask.release(); e->fv_pin.release();
+    e->pcg_count.release(); e->pcg_prefix.release(); e->pcg_ctl.release();
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -784,9 +789,9 @@ int mcpyb_neighbor_pairs_host(mcpyb_engine* e, int rep, double cutoff, int mode,
 }
 
 // ---- free volume -----------------------------------------------------------------
-static int fv_launch(mcpyb_engine* e, const double* d_points, int64_t P, const double* d_pos,
-                     const double* d_radii, int64_t M, const double* offset3, const double* shifts,
-                     int nshift, unsigned long long* d_counts, unsigned char* d_mask) {
+// Bin the exclusion spheres (one CTA); afterwards fv_grid / fv_spheres / fv_cell_start are valid.
+static int fv_build(mcpyb_engine* e, const double* d_pos, const double* d_radii, int64_t M,
+                    const double* offset3, const double* shifts, int nshift) {
     if (nshift < 1 || nshift > 27) return e->fail(MCPYB_ERR_ARG, "nshift must be in 1..27");
     if (M * nshift > 0x7FFFFFF0LL) return e->fail(MCPYB_ERR_CAPACITY, "too many exclusion spheres");
     const int fv_max_cells = 1 << 18;
@@ -795,10 +800,10 @@ static int fv_launch(mcpyb_engine* e, const double* d_points, int64_t P, const d
     CK(e->fv_cid.reserve(nsph), "cudaMalloc fv");
     CK(e->fv_cell_start.reserve(fv_max_cells + 1), "cudaMalloc fv");
     CK(e->fv_cursor.reserve(fv_max_cells), "cudaMalloc fv");
-    CK(e->fv_small.reserve(3 + 81), "cudaMalloc fv");
+    CK(e->fv_small.reserve(3 + 81 + 9), "cudaMalloc fv");
     // offset + shifts: tiny pinned block
     CK(cudaStreamSynchronize(e->stream), "sync before fv staging reuse");
-    CK(e->fv_pin.reserve((3 + 81) * sizeof(double)), "cudaMallocHost fv");
+    CK(e->fv_pin.reserve((3 + 81 + 9) * sizeof(double)), "cudaMallocHost fv");
     double* hs = (double*)e->fv_pin.p;
     for (int i = 0; i < 3; ++i) hs[i] = offset3 ? offset3[i] : 0.0;
     for (int i = 0; i < 3 * nshift; ++i) hs[3 + i] = shifts ? shifts[i] : 0.0;
@@ -806,6 +811,14 @@ static int fv_launch(mcpyb_engine* e, const double* d_points, int64_t P, const d
     fv_build_kernel<<<1, FV_BUILD_THREADS, 0, e->stream>>>(d_pos, d_radii, (int)M, e->fv_small.p, e->fv_small.p + 3, nshift,
         e->fv_grid.p, e->fv_spheres.p, (int)nsph, e->fv_cell_start.p, e->fv_cursor.p, fv_max_cells, e->fv_cid.p);
     LAUNCH_CHECK("fv_build_kernel");
+    return MCPYB_OK;
+}
+
+static int fv_launch(mcpyb_engine* e, const double* d_points, int64_t P, const double* d_pos,
+                     const double* d_radii, int64_t M, const double* offset3, const double* shifts,
+                     int nshift, unsigned long long* d_counts, unsigned char* d_mask) {
+    int rc = fv_build(e, d_pos, d_radii, M, offset3, shifts, nshift);
+    if (rc != MCPYB_OK) return rc;
     CK(cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned long long), e->stream), "memset counts");
     if (P > 0) {
         long long blocks = (P + 255) / 256;
@@ -814,6 +827,29 @@ static int fv_launch(mcpyb_engine* e, const double* d_points, int64_t P, const d
                                                             e->fv_cell_start.p, d_counts, d_mask);
         LAUNCH_CHECK("fv_count_kernel");
     }
+    return MCPYB_OK;
+}
+
+static int fv_upload_atoms(mcpyb_engine* e, const double* positions, const double* radii, int64_t M) {
+    CK(e->fv_pos.reserve((size_t)(M > 0 ? 3 * M : 1)), "cudaMalloc fv pos");
+    CK(e->fv_radii.reserve((size_t)(M > 0 ? M : 1)), "cudaMalloc fv radii");
+    CK(e->fv_counts.reserve(2), "cudaMalloc fv counts");
+    if (M) {
+        CK(cudaMemcpyAsync(e->fv_pos.p, positions, (size_t)M * 24, cudaMemcpyHostToDevice, e->stream), "H2D fv pos");
+        CK(cudaMemcpyAsync(e->fv_radii.p, radii, (size_t)M * 8, cudaMemcpyHostToDevice, e->stream), "H2D fv radii");
+    }
+    return MCPYB_OK;
+}
+
+static int fv_read_counts(mcpyb_engine* e, int64_t* counts_out) {
+    unsigned long long c[2] = {0, 0};
+    FvGrid g;
+    CK(cudaMemcpyAsync(c, e->fv_counts.p, sizeof c, cudaMemcpyDeviceToHost, e->stream), "D2H counts");
+    CK(cudaMemcpyAsync(&g, e->fv_grid.p, sizeof g, cudaMemcpyDeviceToHost, e->stream), "D2H fv grid");
+    CK(cudaStreamSynchronize(e->stream), "sync free volume");
+    if (g.error) return e->fail(MCPYB_ERR_CAPACITY, "free-volume sphere capacity exceeded");
+    counts_out[0] = (int64_t)c[0];
+    counts_out[1] = (int64_t)c[1];
     return MCPYB_OK;
 }
 
@@ -836,28 +872,96 @@ int mcpyb_free_volume_count_host(mcpyb_engine* e, const double* points, int64_t 
     if (P < 0 || M < 0 || !counts_out || (P > 0 && !points) || (M > 0 && (!positions || !radii)))
         return e->fail(MCPYB_ERR_ARG, "bad free-volume arguments");
     CK(e->fv_points.reserve((size_t)(P > 0 ? 3 * P : 1)), "cudaMalloc fv points");
-    CK(e->fv_pos.reserve((size_t)(M > 0 ? 3 * M : 1)), "cudaMalloc fv pos");
-    CK(e->fv_radii.reserve((size_t)(M > 0 ? M : 1)), "cudaMalloc fv radii");
-    CK(e->fv_counts.reserve(2), "cudaMalloc fv counts");
     if (covered_out) CK(e->fv_mask.reserve((size_t)(P > 0 ? P : 1)), "cudaMalloc fv mask");
     if (P) CK(cudaMemcpyAsync(e->fv_points.p, points, (size_t)P * 24, cudaMemcpyHostToDevice, e->stream), "H2D points");
-    if (M) {
-        CK(cudaMemcpyAsync(e->fv_pos.p, positions, (size_t)M * 24, cudaMemcpyHostToDevice, e->stream), "H2D fv pos");
-        CK(cudaMemcpyAsync(e->fv_radii.p, radii, (size_t)M * 8, cudaMemcpyHostToDevice, e->stream), "H2D fv radii");
-    }
-    int rc = fv_launch(e, e->fv_points.p, P, e->fv_pos.p, e->fv_radii.p, M, offset3, shifts, nshift,
-                       e->fv_counts.p, covered_out ? e->fv_mask.p : nullptr);
+    int rc = fv_upload_atoms(e, positions, radii, M);
     if (rc != MCPYB_OK) return rc;
-    unsigned long long c[2] = {0, 0};
-    FvGrid g;
-    CK(cudaMemcpyAsync(c, e->fv_counts.p, sizeof c, cudaMemcpyDeviceToHost, e->stream), "D2H counts");
-    CK(cudaMemcpyAsync(&g, e->fv_grid.p, sizeof g, cudaMemcpyDeviceToHost, e->stream), "D2H fv grid");
+    rc = fv_launch(e, e->fv_points.p, P, e->fv_pos.p, e->fv_radii.p, M, offset3, shifts, nshift,
+                   e->fv_counts.p, covered_out ? e->fv_mask.p : nullptr);
+    if (rc != MCPYB_OK) return rc;
     if (covered_out && P) CK(cudaMemcpyAsync(covered_out, e->fv_mask.p, (size_t)P, cudaMemcpyDeviceToHost, e->stream), "D2H mask");
-    CK(cudaStreamSynchronize(e->stream), "sync free volume");
-    if (g.error) return e->fail(MCPYB_ERR_CAPACITY, "free-volume sphere capacity exceeded");
-    counts_out[0] = (int64_t)c[0];
-    counts_out[1] = (int64_t)c[1];
-    return MCPYB_OK;
+    return fv_read_counts(e, counts_out);
+}
+
+int mcpyb_sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo,
+                                   int64_t P, double radius, const double* center3, const double* positions,
+                                   const double* radii, int64_t M, int64_t* counts_out, int64_t* draws_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (P < 0 || M < 0 || !state_hi_lo || !inc_hi_lo || !counts_out || !(radius > 0.0) ||
+        (M > 0 && (!positions || !radii)))
+        return e->fail(MCPYB_ERR_ARG, "bad sphere free-volume arguments");
+    int rc = fv_upload_atoms(e, positions, radii, M);
+    if (rc != MCPYB_OK) return rc;
+    rc = fv_build(e, e->fv_pos.p, e->fv_radii.p, M, nullptr, nullptr, 1);
+    if (rc != MCPYB_OK) return rc;
+    Pcg64 rng;
+    rng.state = ((u128)state_hi_lo[0] << 64) | (u128)state_hi_lo[1];
+    rng.inc = ((u128)inc_hi_lo[0] << 64) | (u128)inc_hi_lo[1];
+    const long long Mc = (long long)(1.5 * (double)P) + 1;          // int(1.5 * n) + 1 candidates per pass
+    const long long nthreads = (Mc + PCG_CHUNK - 1) / PCG_CHUNK;
+    const int blocks = (int)((nthreads + 255) / 256);
+    CK(e->pcg_count.reserve((size_t)nthreads), "cudaMalloc pcg");
+    CK(e->pcg_prefix.reserve((size_t)nthreads), "cudaMalloc pcg");
+    CK(e->pcg_ctl.reserve(1), "cudaMalloc pcg");
+    CK(cudaMemsetAsync(e->pcg_ctl.p, 0, sizeof(SphereCtl), e->stream), "memset ctl");
+    CK(cudaMemsetAsync(e->fv_counts.p, 0, 2 * sizeof(unsigned long long), e->stream), "memset counts");
+    const double cx = center3 ? center3[0] : 0.0, cy = center3 ? center3[1] : 0.0, cz = center3 ? center3[2] : 0.0;
+    SphereCtl ctl;
+    memset(&ctl, 0, sizeof ctl);
+    int launched = 0;
+    while (P > 0) {
+        // two passes are enough in all but astronomically unlikely cases; launch them back to back,
+        // then look (a pass that is not needed consumes no random numbers)
+        for (int k = 0; k < 2; ++k) {
+            pcg_sphere_count_kernel<<<blocks, 256, 0, e->stream>>>(rng, launched, Mc, radius, P, e->pcg_ctl.p, e->pcg_count.p);
+            LAUNCH_CHECK("pcg_sphere_count_kernel");
+            pcg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->pcg_count.p, e->pcg_prefix.p, nthreads, e->pcg_ctl.p);
+            LAUNCH_CHECK("pcg_scan_kernel");
+            pcg_sphere_eval_kernel<<<blocks, 256, 0, e->stream>>>(rng, Mc, radius, P, cx, cy, cz, e->pcg_ctl.p,
+                e->pcg_prefix.p, e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
+            LAUNCH_CHECK("pcg_sphere_eval_kernel");
+            pcg_sphere_commit_kernel<<<1, 1, 0, e->stream>>>(e->pcg_ctl.p, P);
+            LAUNCH_CHECK("pcg_sphere_commit_kernel");
+            ++launched;
+        }
+        CK(cudaMemcpyAsync(&ctl, e->pcg_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, e->stream), "D2H ctl");
+        CK(cudaStreamSynchronize(e->stream), "sync sphere passes");
+        if (ctl.filled >= P) break;
+        if (launched > 64) return e->fail(MCPYB_ERR_STATE, "sphere sampler did not converge");
+    }
+    if (draws_out) *draws_out = 3 * Mc * ctl.passes;
+    return fv_read_counts(e, counts_out);
+}
+
+int mcpyb_box_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo,
+                                int64_t P, const double* dims9, const double* positions, const double* radii,
+                                int64_t M, const double* offset3, const double* shifts, int nshift,
+                                int64_t* counts_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (P < 0 || M < 0 || !state_hi_lo || !inc_hi_lo || !counts_out || !dims9 || (M > 0 && (!positions || !radii)))
+        return e->fail(MCPYB_ERR_ARG, "bad box free-volume arguments");
+    int rc = fv_upload_atoms(e, positions, radii, M);
+    if (rc != MCPYB_OK) return rc;
+    rc = fv_build(e, e->fv_pos.p, e->fv_radii.p, M, offset3, shifts, nshift);
+    if (rc != MCPYB_OK) return rc;
+    // dims ride in the tail of the small block; wait for the H2D that still reads its head
+    CK(cudaStreamSynchronize(e->stream), "sync before dims staging");
+    double* hs = (double*)e->fv_pin.p;
+    for (int i = 0; i < 9; ++i) hs[84 + i] = dims9[i];
+    CK(cudaMemcpyAsync(e->fv_small.p + 84, hs + 84, 9 * sizeof(double), cudaMemcpyHostToDevice, e->stream), "H2D dims");
+    Pcg64 rng;
+    rng.state = ((u128)state_hi_lo[0] << 64) | (u128)state_hi_lo[1];
+    rng.inc = ((u128)inc_hi_lo[0] << 64) | (u128)inc_hi_lo[1];
+    CK(cudaMemsetAsync(e->fv_counts.p, 0, 2 * sizeof(unsigned long long), e->stream), "memset counts");
+    if (P > 0) {
+        const long long nthreads = (P + PCG_CHUNK - 1) / PCG_CHUNK;
+        pcg_box_eval_kernel<<<(int)((nthreads + 255) / 256), 256, 0, e->stream>>>(rng, P, e->fv_small.p + 84,
+            e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
+        LAUNCH_CHECK("pcg_box_eval_kernel");
+    }
+    return fv_read_counts(e, counts_out);
 }
 
 int mcpyb_fp64_peak_tflops(mcpyb_engine* e, double* tflops_out) {
@@ -883,6 +987,15 @@ int mcpyb_fp64_peak_tflops(mcpyb_engine* e, double* tflops_out) {
     cudaEventDestroy(t0); cudaEventDestroy(t1);
     out.release();
     *tflops_out = best;
+    return MCPYB_OK;
+}
+
+int mcpyb_pcg64_host_doubles(const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo, uint64_t skip,
+                             int64_t n, double* out) {
+    if (!state_hi_lo || !inc_hi_lo || n < 0 || (n > 0 && !out)) return MCPYB_ERR_ARG;
+    const u128 inc = ((u128)inc_hi_lo[0] << 64) | (u128)inc_hi_lo[1];
+    u128 st = pcg_advance(((u128)state_hi_lo[0] << 64) | (u128)state_hi_lo[1], inc, skip);
+    for (int64_t i = 0; i < n; ++i) out[i] = pcg_next_double(st, inc);
     return MCPYB_OK;
 }
 

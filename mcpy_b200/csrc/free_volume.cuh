@@ -162,6 +162,58 @@ fv_build_kernel(const double* __restrict__ pos, const double* __restrict__ radii
     }
 }
 
+// true iff some exclusion sphere strictly contains the point
+__device__ __forceinline__ bool fv_point_covered(const FvGrid& g, const double4* __restrict__ spheres,
+                                                 const int* __restrict__ cell_start,
+                                                 double px, double py, double pz) {
+    if (g.natoms <= 0) return false;
+    // raw (unclamped) cell coordinates; the stencil is clipped to the grid
+    const int cx = (int)floor(fmax(-2.0, fmin((px - g.lo[0]) * g.inv_edge[0], (double)g.ncell[0] + 1.0)));
+    const int cy = (int)floor(fmax(-2.0, fmin((py - g.lo[1]) * g.inv_edge[1], (double)g.ncell[1] + 1.0)));
+    const int cz = (int)floor(fmax(-2.0, fmin((pz - g.lo[2]) * g.inv_edge[2], (double)g.ncell[2] + 1.0)));
+    for (int oz = -1; oz <= 1; ++oz) {
+        const int z = cz + oz;
+        if (z < 0 || z >= g.ncell[2]) continue;
+        for (int oy = -1; oy <= 1; ++oy) {
+            const int y = cy + oy;
+            if (y < 0 || y >= g.ncell[1]) continue;
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.ncell[0] - 1);
+            if (x0 > x1) continue;
+            const int row = (z * g.ncell[1] + y) * g.ncell[0];
+            const int beg = cell_start[row + x0], end = cell_start[row + x1 + 1];
+            for (int k = beg; k < end; ++k) {
+                const double4 s = spheres[k];
+                const double dx = __dsub_rn(px, s.x), dy = __dsub_rn(py, s.y), dz = __dsub_rn(pz, s.z);
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (d2 < s.w) return true;
+            }
+        }
+    }
+    return false;
+}
+
+// block sum of (covered, total) -> one 64-bit atomicAdd pair per CTA; all threads must call
+__device__ __forceinline__ void fv_block_accumulate(int covered_local, int total_local, int* s_cnt /* [8] */,
+                                                    unsigned long long* __restrict__ counts) {
+    const int c = warp_sum_int(covered_local);
+    const int t = warp_sum_int(total_local);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    int cb = 0;
+    if (threadIdx.x == 0) for (int w = 0; w < (int)(blockDim.x >> 5); ++w) cb += s_cnt[w];
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tb = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tb += s_cnt[w];
+        if (tb) {
+            atomicAdd(&counts[0], (unsigned long long)(tb - cb));
+            atomicAdd(&counts[1], (unsigned long long)cb);
+        }
+    }
+}
+
 // points [P][3]; counts[0] += free points, counts[1] += covered points.
 __global__ void __launch_bounds__(256)
 fv_count_kernel(const double* __restrict__ points, long long P,
@@ -173,52 +225,11 @@ fv_count_kernel(const double* __restrict__ points, long long P,
     int covered_local = 0, total_local = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P;
          i += (long long)gridDim.x * blockDim.x) {
-        const double px = points[3 * i], py = points[3 * i + 1], pz = points[3 * i + 2];
-        bool covered = false;
-        if (g.natoms > 0) {
-            // raw (unclamped) cell coordinates; the stencil is clipped to the grid
-            const int cx = (int)floor(fmax(-2.0, fmin((px - g.lo[0]) * g.inv_edge[0], (double)g.ncell[0] + 1.0)));
-            const int cy = (int)floor(fmax(-2.0, fmin((py - g.lo[1]) * g.inv_edge[1], (double)g.ncell[1] + 1.0)));
-            const int cz = (int)floor(fmax(-2.0, fmin((pz - g.lo[2]) * g.inv_edge[2], (double)g.ncell[2] + 1.0)));
-            for (int oz = -1; oz <= 1 && !covered; ++oz) {
-                const int z = cz + oz;
-                if (z < 0 || z >= g.ncell[2]) continue;
-                for (int oy = -1; oy <= 1 && !covered; ++oy) {
-                    const int y = cy + oy;
-                    if (y < 0 || y >= g.ncell[1]) continue;
-                    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.ncell[0] - 1);
-                    if (x0 > x1) continue;
-                    const int row = (z * g.ncell[1] + y) * g.ncell[0];
-                    const int beg = cell_start[row + x0], end = cell_start[row + x1 + 1];
-                    for (int k = beg; k < end; ++k) {
-                        const double4 s = spheres[k];
-                        const double dx = __dsub_rn(px, s.x), dy = __dsub_rn(py, s.y), dz = __dsub_rn(pz, s.z);
-                        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)),
-                                                    __dmul_rn(dz, dz));
-                        if (d2 < s.w) { covered = true; break; }
-                    }
-                }
-            }
-        }
+        const bool covered = fv_point_covered(g, spheres, cell_start, points[3 * i], points[3 * i + 1],
+                                              points[3 * i + 2]);
         if (covered_mask) covered_mask[i] = covered ? 1 : 0;
         covered_local += covered ? 1 : 0;
         total_local += 1;
     }
-    // block reduction of two small integers packed in one int (counts < 2^15 per thread is not
-    // guaranteed) -> reduce separately
-    int c = warp_sum_int(covered_local);
-    int t = warp_sum_int(total_local);
-    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
-    __syncthreads();
-    int cb = 0;
-    if (threadIdx.x == 0) for (int w = 0; w < (int)(blockDim.x >> 5); ++w) cb += s_cnt[w];
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = t;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tb = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tb += s_cnt[w];
-        atomicAdd(&counts[0], (unsigned long long)(tb - cb));
-        atomicAdd(&counts[1], (unsigned long long)cb);
-    }
+    fv_block_accumulate(covered_local, total_local, s_cnt, counts);
 }

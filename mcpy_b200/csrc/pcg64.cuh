@@ -1,0 +1,180 @@
+// K8 -- numpy's PCG64 stream regenerated on the GPU, fused with the free-volume count.
+//
+// The reference draws its sample points from np.random.default_rng(seed)
+// (mcpy/cell/cell.py:25): PCG64 = 128-bit LCG, XSL-RR 128/64 output, and
+// Generator.random() = (next_uint64 >> 11) * 2^-53, filled in row-major order.
+//   SphericalCell._sample_sphere_points (spherical_cell.py:88-106): passes of
+//     M = int(1.5 P) + 1 candidates, pts = (u - 0.5) * 2.0 * R, kept when
+//     einsum('ij,ij->i') <= R^2 -- numpy evaluates that as (x*x + z*z) + y*y, unfused
+//     (tests/test_pcg64.py pins this against numpy itself) -- first P kept, in stream order.
+//   CustomCell.calculate_volume (custom_cell.py:74-75): rng.random((P,3)) @ dimensions,
+//     evaluated by the BLAS as fma(u2, d2c, fma(u1, d1c, u0*d0c)) (exact for diagonal cells).
+// Each thread jumps the LCG to its chunk of the stream (O(log n) 128-bit multiplies),
+// so no random numbers cross the PCIe bus or touch HBM; the host generator is advanced
+// by the same number of draws (Generator.bit_generator.advance) to stay in lock-step.
+#pragma once
+#include "common.cuh"
+#include "free_volume.cuh"
+
+typedef unsigned __int128 u128;
+
+struct Pcg64 {
+    u128 state, inc;
+};
+
+__host__ __device__ __forceinline__ u128 pcg_mult() {
+    return ((u128)0x2360ED051FC65DA4ULL << 64) | (u128)0x4385DF649FCCF645ULL;
+}
+
+// state after `delta` steps (Brown's LCG jump-ahead, as in pcg_advance_lcg_128)
+__host__ __device__ inline u128 pcg_advance(u128 state, u128 inc, unsigned long long delta) {
+    u128 cur_mult = pcg_mult(), cur_plus = inc, acc_mult = 1, acc_plus = 0;
+    while (delta > 0) {
+        if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+        cur_plus = (cur_mult + 1) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1;
+    }
+    return acc_mult * state + acc_plus;
+}
+
+__host__ __device__ __forceinline__ double pcg_next_double(u128& state, u128 inc) {
+    state = state * pcg_mult() + inc;
+    const unsigned long long hi = (unsigned long long)(state >> 64), lo = (unsigned long long)state;
+    const unsigned long long x = hi ^ lo;
+    const unsigned rot = (unsigned)(hi >> 58);
+    const unsigned long long out = (x >> rot) | (x << ((64 - rot) & 63));
+    return (double)(out >> 11) * (1.0 / 9007199254740992.0);
+}
+
+#define PCG_CHUNK 64          // candidates / points per thread
+
+struct SphereCtl {
+    long long filled;         // points accepted so far
+    long long passes;         // passes that consumed random numbers
+    long long pass_total;     // accepted candidates of the current pass
+};
+
+__device__ __forceinline__ bool sphere_candidate(u128& st, u128 inc, double R, double R2,
+                                                 double& x, double& y, double& z) {
+    const double u0 = pcg_next_double(st, inc), u1 = pcg_next_double(st, inc), u2 = pcg_next_double(st, inc);
+    x = __dmul_rn(__dmul_rn(__dsub_rn(u0, 0.5), 2.0), R);
+    y = __dmul_rn(__dmul_rn(__dsub_rn(u1, 0.5), 2.0), R);
+    z = __dmul_rn(__dmul_rn(__dsub_rn(u2, 0.5), 2.0), R);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(z, z)), __dmul_rn(y, y));
+    return d2 <= R2;
+}
+
+// pass A: accepted candidates per thread chunk
+__global__ void __launch_bounds__(256)
+pcg_sphere_count_kernel(Pcg64 rng, long long pass, long long M, double R, long long P,
+                        const SphereCtl* __restrict__ ctl, int* __restrict__ acc_count) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long c0 = t * PCG_CHUNK;
+    if (c0 >= M) return;
+    if (ctl->filled >= P) { acc_count[t] = 0; return; }          // nothing needed: consume nothing
+    const long long c1 = min(c0 + (long long)PCG_CHUNK, M);
+    const long long used = ctl->passes;                           // passes already consumed
+    (void)pass;
+    u128 st = pcg_advance(rng.state, rng.inc, (unsigned long long)(3 * (used * M + c0)));
+    const double R2 = __dmul_rn(R, R);
+    int n = 0;
+    for (long long c = c0; c < c1; ++c) {
+        double x, y, z;
+        n += sphere_candidate(st, rng.inc, R, R2, x, y, z) ? 1 : 0;
+    }
+    acc_count[t] = n;
+}
+
+// single block: exclusive scan of acc_count -> acc_prefix, pass_total
+__global__ void __launch_bounds__(1024, 1)
+pcg_scan_kernel(const int* __restrict__ acc_count, long long* __restrict__ acc_prefix, long long nthreads,
+                SphereCtl* __restrict__ ctl) {
+    __shared__ long long s[1024];
+    const int tid = threadIdx.x;
+    const long long per = (nthreads + 1023) / 1024;
+    const long long beg = min((long long)tid * per, nthreads), end = min(beg + per, nthreads);
+    long long sum = 0;
+    for (long long i = beg; i < end; ++i) sum += acc_count[i];
+    s[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const long long v = (tid >= o) ? s[tid - o] : 0;
+        __syncthreads();
+        s[tid] += v;
+        __syncthreads();
+    }
+    long long run = s[tid] - sum;
+    for (long long i = beg; i < end; ++i) { acc_prefix[i] = run; run += acc_count[i]; }
+    if (tid == 1023) ctl->pass_total = s[1023];
+}
+
+// pass B: regenerate, evaluate the accepted candidates whose stream rank is still needed
+__global__ void __launch_bounds__(256)
+pcg_sphere_eval_kernel(Pcg64 rng, long long M, double R, long long P, double cx, double cy, double cz,
+                       const SphereCtl* __restrict__ ctl, const long long* __restrict__ acc_prefix,
+                       const FvGrid* __restrict__ gridp, const double4* __restrict__ spheres,
+                       const int* __restrict__ cell_start, unsigned long long* __restrict__ counts) {
+    __shared__ int s_cnt[8];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long c0 = t * PCG_CHUNK;
+    int covered_local = 0, total_local = 0;
+    const long long need = P - ctl->filled;
+    if (c0 < M && need > 0) {
+        const FvGrid g = *gridp;
+        const long long c1 = min(c0 + (long long)PCG_CHUNK, M);
+        long long rank = acc_prefix[t];
+        if (rank < need) {
+            u128 st = pcg_advance(rng.state, rng.inc, (unsigned long long)(3 * (ctl->passes * M + c0)));
+            const double R2 = __dmul_rn(R, R);
+            for (long long c = c0; c < c1 && rank < need; ++c) {
+                double x, y, z;
+                if (sphere_candidate(st, rng.inc, R, R2, x, y, z)) {
+                    const bool cov = fv_point_covered(g, spheres, cell_start,
+                                                      __dadd_rn(x, cx), __dadd_rn(y, cy), __dadd_rn(z, cz));
+                    covered_local += cov ? 1 : 0;
+                    total_local += 1;
+                    ++rank;
+                }
+            }
+        }
+    }
+    fv_block_accumulate(covered_local, total_local, s_cnt, counts);
+}
+
+// after pass B: book the pass
+__global__ void pcg_sphere_commit_kernel(SphereCtl* ctl, long long P) {
+    const long long need = P - ctl->filled;
+    if (need <= 0) return;
+    ctl->filled += (ctl->pass_total < need) ? ctl->pass_total : need;
+    ctl->passes += 1;
+}
+
+// CustomCell: point i = rng.random(3) @ dims, one kernel
+__global__ void __launch_bounds__(256)
+pcg_box_eval_kernel(Pcg64 rng, long long P, const double* __restrict__ dims /* 9, device */,
+                    const FvGrid* __restrict__ gridp, const double4* __restrict__ spheres,
+                    const int* __restrict__ cell_start, unsigned long long* __restrict__ counts) {
+    __shared__ int s_cnt[8];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i0 = t * PCG_CHUNK;
+    int covered_local = 0, total_local = 0;
+    if (i0 < P) {
+        const FvGrid g = *gridp;
+        const long long i1 = min(i0 + (long long)PCG_CHUNK, P);
+        double d[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) d[k] = dims[k];
+        u128 st = pcg_advance(rng.state, rng.inc, (unsigned long long)(3 * i0));
+        for (long long i = i0; i < i1; ++i) {
+            const double u0 = pcg_next_double(st, rng.inc), u1 = pcg_next_double(st, rng.inc),
+                         u2 = pcg_next_double(st, rng.inc);
+            const double x = fma(u2, d[6], fma(u1, d[3], __dmul_rn(u0, d[0])));
+            const double y = fma(u2, d[7], fma(u1, d[4], __dmul_rn(u0, d[1])));
+            const double z = fma(u2, d[8], fma(u1, d[5], __dmul_rn(u0, d[2])));
+            covered_local += fv_point_covered(g, spheres, cell_start, x, y, z) ? 1 : 0;
+            total_local += 1;
+        }
+    }
+    fv_block_accumulate(covered_local, total_local, s_cnt, counts);
+}

@@ -242,3 +242,44 @@ class Engine:
         if return_mask:
             return int(counts[0]), int(counts[1]), mask.astype(bool)
         return int(counts[0]), int(counts[1])
+
+    # -- free volume with device-regenerated PCG64 points -------------------------
+    @staticmethod
+    def _pcg_words(rng):
+        """(state, inc) of a numpy ``Generator(PCG64)`` as {high, low} uint64 pairs."""
+        st = rng.bit_generator.state
+        if st.get('bit_generator') != 'PCG64':
+            raise ValueError('the cell generator must be numpy PCG64 (np.random.default_rng)')
+        s, i = int(st['state']['state']), int(st['state']['inc'])
+        m = (1 << 64) - 1
+        return (np.array([s >> 64, s & m], dtype=np.uint64), np.array([i >> 64, i & m], dtype=np.uint64))
+
+    def sphere_free_volume_pcg64(self, rng, n_points, radius, center, positions, radii):
+        """SphericalCell sampling + covered test on the device; advances ``rng`` exactly as
+        ``_sample_sphere_points`` would (spherical_cell.py:88-106)."""
+        state, inc = self._pcg_words(rng)
+        positions = as_f64(positions).reshape(-1, 3)
+        radii = as_f64(radii).reshape(-1)
+        center = as_f64(center).reshape(3)
+        counts = np.zeros(2, dtype=np.int64)
+        draws = C.c_int64(0)
+        self._check(self._lib.mcpyb_sphere_free_volume_pcg64(
+            self._h, ptr(state), ptr(inc), int(n_points), float(radius), ptr(center), ptr(positions),
+            ptr(radii), len(positions), ptr(counts), C.byref(draws)))
+        rng.bit_generator.advance(int(draws.value))
+        return int(counts[0]), int(counts[1])
+
+    def box_free_volume_pcg64(self, rng, n_points, dimensions, positions, radii, offset, shifts):
+        """CustomCell sampling + covered test on the device; advances ``rng`` by 3 P draws."""
+        state, inc = self._pcg_words(rng)
+        positions = as_f64(positions).reshape(-1, 3)
+        radii = as_f64(radii).reshape(-1)
+        dims = as_f64(dimensions).reshape(9)
+        offset = as_f64(offset).reshape(3)
+        shifts = as_f64(shifts).reshape(-1, 3)
+        counts = np.zeros(2, dtype=np.int64)
+        self._check(self._lib.mcpyb_box_free_volume_pcg64(
+            self._h, ptr(state), ptr(inc), int(n_points), ptr(dims), ptr(positions), ptr(radii),
+            len(positions), ptr(offset), ptr(shifts), len(shifts), ptr(counts)))
+        rng.bit_generator.advance(3 * int(n_points))
+        return int(counts[0]), int(counts[1])

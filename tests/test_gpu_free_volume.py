@@ -114,3 +114,59 @@ def test_spherical_cell_mirror_matches_oracle_and_floor(fv_engine):
     empty = Atoms()
     full.calculate_volume(empty)
     assert full.get_volume() == full.sphere_volume
+
+
+# ---- K8: sample points regenerated on the GPU from numpy's PCG64 state -------------------
+
+@pytest.mark.parametrize('n_points', [1, 1000, 100_000])
+def test_device_sphere_points_match_numpy_stream(fv_engine, n_points):
+    cfg = synthetic.s3_ag_o()
+    rng_dev = np.random.default_rng(3)
+    rng_ref = np.random.default_rng(3)
+    for _ in range(2):                       # two consecutive refreshes share one stream
+        n_free, n_cov = fv_engine.sphere_free_volume_pcg64(rng_dev, n_points, cfg['sphere_radius'],
+                                                           np.zeros(3), cfg['positions'], cfg['radii'])
+        pts, draws = ofv.sample_sphere_points(rng_ref, n_points, cfg['sphere_radius'])
+        covered = ofv.covered_mask_kdtree(pts, cfg['positions'], cfg['radii'])
+        assert (n_free, n_cov) == (int((~covered).sum()), int(covered.sum()))
+        # the host generator was advanced by exactly what the reference sampler consumes
+        assert rng_dev.bit_generator.state == rng_ref.bit_generator.state
+
+
+def test_device_box_points_match_numpy_stream(fv_engine):
+    rng_pos = np.random.default_rng(5)
+    for dims in (np.diag([11.0, 9.5, 12.0]),
+                 np.array([[11.0, 0, 0], [5.5, 9.5, 0], [0, 0, 12.0]])):     # cubic and hexagonal
+        original = dims.copy(); original[2, 2] = 30.0
+        pos = rng_pos.random((60, 3)) @ original
+        radii = rng_pos.choice([1.5, 2.2, 0.0], size=60)
+        offset = np.array([0, 0, 6.0])
+        pbc = [True, True, False]
+        shifts = np.array([np.array([i, j, 0], float) @ original for i in (-1, 0, 1) for j in (-1, 0, 1)])
+        rng_dev = np.random.default_rng(9)
+        rng_ref = np.random.default_rng(9)
+        n_free, n_cov = fv_engine.box_free_volume_pcg64(rng_dev, 50_000, dims, pos, radii, offset, shifts)
+        pts = ofv.sample_box_points(rng_ref, 50_000, dims)
+        images = ofv.periodic_images(pos, offset, original, pbc)
+        covered = ofv.covered_mask_kdtree(pts, images, np.tile(radii, 9))
+        assert (n_free, n_cov) == (int((~covered).sum()), int(covered.sum()))
+        assert rng_dev.bit_generator.state == rng_ref.bit_generator.state
+
+
+def test_cells_in_device_point_mode_track_the_reference_stream(fv_engine):
+    from mcpy_b200.cell import B200SphericalCell
+    from ase import Atoms
+    cfg = synthetic.s3_ag_o()
+    syms = ['Ag' if z == 47 else 'O' for z in cfg['numbers']]
+    a1 = Atoms(syms, positions=cfg['positions'])
+    a2 = Atoms(syms, positions=cfg['positions'])
+    kw = dict(vacuum=3.0, species_radii={'Ag': 2.947, 'O': 0.0}, mc_sample_points=30_000, seed=11,
+              engine=fv_engine)
+    host = B200SphericalCell(a1, points='host', **kw)
+    dev = B200SphericalCell(a2, points='device', **kw)
+    for _ in range(3):
+        host.calculate_volume(a1)
+        dev.calculate_volume(a2)
+        assert host.last_counts == dev.last_counts and host.get_volume() == dev.get_volume()
+        # insertion points drawn afterwards come from the same stream position
+        assert np.array_equal(host.get_random_point(), dev.get_random_point())
