@@ -1,0 +1,161 @@
+"""Generate golden fixtures by running the UNMODIFIED reference drivers (farrisric/mcpy at
+/root/reference) in the build container, with the CPU oracle as calculator.
+
+    python tests/golden/make_golden.py
+
+The reference needs ``ase`` (absent here, no network); the test-only stand-in under
+``oracle/ase_shim`` supplies ``Atoms`` etc.  Everything numeric that ends up in the fixtures
+comes from the reference's own code paths (moves, cells, ``GrandCanonicalEnsemble``,
+numpy PCG64 / Python MT19937 streams, scipy cKDTree) and from the oracle energies.
+
+Fixtures (small, committed):
+  lj_gcmc_trace.npz   -- 240 trials of LJ GCMC in a periodic box (reference Cell + Insertion /
+                         Deletion / Displacement moves, LJ units): every configuration handed to
+                         compute_energy, the oracle energy, the acceptance inputs, the uniform
+                         draws and the accept / reject decision.
+  emt_sphere_trace.npz -- 220 trials of Ag octahedron + O GCMC with EMT in a SphericalCell:
+                         the same, plus every free-volume refresh (PCG64 state before, atoms,
+                         resulting volume).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'ase_shim'))
+sys.path.insert(0, '/root/reference')
+
+from ase import Atoms  # noqa: E402
+from ase.cluster import Octahedron  # noqa: E402
+from mcpy.cell import Cell, SphericalCell  # noqa: E402
+from mcpy.ensembles import GrandCanonicalEnsemble  # noqa: E402
+from mcpy.moves import DeletionMove, DisplacementMove, InsertionMove, MoveSelector  # noqa: E402
+from oracle import cfast  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+class Recorder:
+    """Calculator that records every configuration it is asked about."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        self.pos, self.num, self.energy = [], [], []
+
+    def get_potential_energy(self, atoms):
+        e = self.fn(atoms)
+        self.pos.append(atoms.positions.copy())
+        self.num.append(atoms.numbers.copy())
+        self.energy.append(e)
+        return e
+
+
+def instrument(g):
+    """Record the acceptance inputs, draws and outcome of every trial."""
+    log = {'dE': [], 'dN': [], 'volume': [], 'species': [], 'n': [], 'accept': [], 'draw': []}
+    orig_cond = g._acceptance_condition
+    orig_uniform = g.rng_acceptance.get_uniform
+    state = {'draw': np.nan}
+
+    def uniform(a=0.0, b=1.0):
+        u = orig_uniform(a, b)
+        state['draw'] = u
+        return u
+
+    def cond(dE, dN, volume, species, n_atoms=None):
+        state['draw'] = np.nan
+        ok = orig_cond(dE, dN, volume, species, n_atoms)
+        for k, v in zip(('dE', 'dN', 'volume', 'species', 'n', 'accept', 'draw'),
+                        (dE, dN, volume, species, n_atoms, bool(ok), state['draw'])):
+            log[k].append(v)
+        return ok
+
+    g.rng_acceptance.get_uniform = uniform
+    g._acceptance_condition = cond
+    return log
+
+
+def pack(rec):
+    off = np.concatenate([[0], np.cumsum([len(p) for p in rec.pos])]).astype(np.int64)
+    return dict(cfg_off=off, cfg_pos=np.concatenate(rec.pos), cfg_num=np.concatenate(rec.num).astype(np.int32),
+                cfg_energy=np.array(rec.energy))
+
+
+def lj_trace():
+    L, rc, T, mu = 9.0, 3.0, 2.0, -2.4       # the reference's LAMMPS-parity box (benchmark/lammps_gcmc_parity.py)
+    rng = np.random.default_rng(5)
+    atoms = Atoms('H60', positions=rng.uniform(0.9, L - 0.9, size=(60, 3)), cell=[L, L, L], pbc=True)
+    rec = Recorder(lambda a: cfast.lj_energy(a.positions, np.asarray(a.cell), a.pbc, 1.0, 1.0, rc))
+    cell = Cell(atoms, seed=7)
+    moves = [InsertionMove(cell, species=['H'], seed=21), DeletionMove(cell, species=['H'], seed=22, min_atoms=1),
+             DisplacementMove(species=['H'], seed=23, max_displacement=0.3)]
+    ms = MoveSelector([1, 1, 1], moves, seed=14, n_moves=1)
+    g = GrandCanonicalEnsemble(atoms=atoms, cells=[cell], units_type='LJ', calculator=rec, mu={'H': mu},
+                               species=['H'], temperature=T, move_selector=ms, random_seed=13,
+                               traj_file=None, outfile=None)
+    log = instrument(g)
+    for _ in range(240):
+        g.do_gcmc_step()
+    d = pack(rec)
+    d.update(cell=np.asarray(atoms.cell), pbc=np.asarray(atoms.pbc), rc=rc, temperature=T, mu=mu,
+             dE=np.array(log['dE']), dN=np.array(log['dN']), volume=np.array(log['volume']),
+             n=np.array(log['n']), accept=np.array(log['accept']), draw=np.array(log['draw']),
+             final_energy=g.E_old, final_n=len(g.atoms))
+    np.savez_compressed(os.path.join(OUT, 'lj_gcmc_trace.npz'), **d)
+    print('lj trace:', len(rec.energy), 'energy calls,', int(np.sum(log['accept'])), 'accepted, final N', len(g.atoms))
+
+
+def emt_trace():
+    atoms = Octahedron('Ag', 4, 1)            # the reference's equivalence-test system
+    radii = {'Ag': 2.947, 'O': 0.0}
+    scell = SphericalCell(atoms, vacuum=3.0, species_radii=radii, mc_sample_points=20_000, seed=17)
+    vol_log = {'state': [], 'pos': [], 'num': [], 'volume': []}
+    orig_calc = scell.calculate_volume
+
+    def calc_volume(a):
+        st = scell._rng.bit_generator.state['state']
+        m = (1 << 64) - 1
+        vol_log['state'].append([st['state'] >> 64, st['state'] & m, st['inc'] >> 64, st['inc'] & m])
+        vol_log['pos'].append(a.positions.copy())
+        vol_log['num'].append(a.numbers.copy())
+        orig_calc(a)
+        vol_log['volume'].append(scell.volume)
+
+    scell.calculate_volume = calc_volume
+    rec = Recorder(lambda a: cfast.emt_energy(a.positions, a.numbers, np.asarray(a.cell), a.pbc))
+    moves = [InsertionMove(scell, species=['O'], seed=31, min_insert=0.5),
+             DeletionMove(scell, species=['O'], seed=32),
+             DisplacementMove(species=['O'], seed=33, max_displacement=0.25,
+                              constraints=list(range(len(atoms))))]
+    ms = MoveSelector([2, 1, 1], moves, seed=34, n_moves=1)
+    g = GrandCanonicalEnsemble(atoms=atoms, cells=[scell], units_type='metal', calculator=rec, mu={'O': 1.2},
+                               species=['O'], temperature=800.0, move_selector=ms, random_seed=35,
+                               traj_file=None, outfile=None)
+    log = instrument(g)
+    for _ in range(220):
+        try:
+            g.do_gcmc_step()
+        except ValueError:
+            # DisplacementMove with no movable O yet raises in the reference; skip such steps
+            continue
+    d = pack(rec)
+    voff = np.concatenate([[0], np.cumsum([len(p) for p in vol_log['pos']])]).astype(np.int64)
+    d.update(cell=np.asarray(atoms.cell), pbc=np.asarray(atoms.pbc), temperature=800.0, mu=1.2,
+             dE=np.array(log['dE']), dN=np.array(log['dN']), volume=np.array(log['volume']),
+             n=np.array(log['n']), accept=np.array(log['accept']), draw=np.array(log['draw']),
+             lambda_O=g.units.lambda_dbs['O'], beta=g.units.beta,
+             sphere_radius=scell.radius, n_points=scell.mc_sample_points,
+             vol_off=voff, vol_pos=np.concatenate(vol_log['pos']),
+             vol_num=np.concatenate(vol_log['num']).astype(np.int32),
+             vol_state=np.array(vol_log['state'], dtype=np.uint64), vol_value=np.array(vol_log['volume']),
+             final_energy=g.E_old, final_n=len(g.atoms))
+    np.savez_compressed(os.path.join(OUT, 'emt_sphere_trace.npz'), **d)
+    print('emt trace:', len(rec.energy), 'energy calls,', int(np.sum(log['accept'])), 'accepted,',
+          len(vol_log['volume']), 'volume refreshes, final N', len(g.atoms))
+
+
+if __name__ == '__main__':
+    lj_trace()
+    emt_trace()
