@@ -120,7 +120,8 @@ struct mcpyb_engine {
     DevBuf<int> cid, cell_start;
     const int* d_atom_off = nullptr;      // points into stage_dev (header of the last upload)
     DevBuf<CellGeom> geom;
-    DevBuf<double> e_atom, sigma1;
+    DevBuf<double> e_atom, sigma1, e_part;
+    DevBuf<int> cnt_part;
     DevBuf<double> E;                     // one block: E[R] | pairs[R] (int64) | status[R] (int32)
     DevBuf<int> pair_count;
     long long* pairs_ptr() { return (long long*)(E.p + R); }
@@ -335,13 +336,20 @@ int launch_energies(mcpyb_engine* e) {
         int blocks = (total + warps_per_block - 1) / warps_per_block;
         if (blocks > 148 * 64) blocks = 148 * 64;
         if (e->pot_kind == POT_LJ) {
-            // lane-per-atom: work items = (cell, chunk of 32 atoms); grid.y = replica
-            long long est = (long long)(e->max_n < e->max_cells ? e->max_n : e->max_cells) + e->max_n / 32 + 1;
+            // lane-per-atom: work items = (cell, chunk of 32 atoms, stencil z-plane); grid.y = replica
+            const int nplanes = 2 * e->subdiv + 1;
+            CK(e->e_part.reserve((size_t)total * nplanes), "cudaMalloc e_part");
+            CK(e->cnt_part.reserve((size_t)total * nplanes), "cudaMalloc cnt_part");
+            long long est = ((long long)(e->max_n < e->max_cells ? e->max_n : e->max_cells) + e->max_n / 32 + 1) * nplanes;
             int gx = (int)((est + SITE_WARPS - 1) / SITE_WARPS);
             if (gx > 148 * 16) gx = 148 * 16;
             if (gx < 1) gx = 1;
-            lj_cell_energy_kernel<<<dim3(gx, e->R), 32 * SITE_WARPS, 0, e->stream>>>(e->view(), e->lj, e->e_atom.p, e->pair_count.p);
+            lj_cell_energy_kernel<<<dim3(gx, e->R), 32 * SITE_WARPS, 0, e->stream>>>(e->view(), e->lj, nplanes,
+                                                                                   e->e_part.p, e->cnt_part.p);
             LAUNCH_CHECK("lj_cell_energy_kernel");
+            lj_fold_planes_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(total, nplanes, e->e_part.p, e->cnt_part.p,
+                                                                              e->e_atom.p, e->pair_count.p);
+            LAUNCH_CHECK("lj_fold_planes_kernel");
         } else {
             emt_pair_kernel<<<blocks, 256, 0, e->stream>>>(
                 e->view(), e->d_atom_off, total, e->emt_dev.p, e->e_atom.p, e->sigma1.p, e->pair_count.p);
@@ -399,7 +407,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     cudaStreamSynchronize(e->stream);
     e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release(); e->stmp.release(); e->fpos.release();
     e->cid.release(); e->cell_start.release(); e->geom.release();
-    e->e_atom.release(); e->sigma1.release(); e->E.release(); e->pair_count.release();
+    e->e_atom.release(); e->sigma1.release(); e->e_part.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
     e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release();
@@ -638,12 +646,14 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
         w.nsites = nsites; w.n_old = n_old_total;
         w.bin_stride = e->max_cells; w.nbins = e->R * e->max_cells;
         const size_t ns = (size_t)(nsites > 0 ? nsites : 1), nbp = (size_t)w.nbins + 1;
-        CK(e->tw_int.reserve(4 * ns + 4), "cudaMalloc trial work");
+        w.nplanes = (nsites >= 4096) ? 1 : 2 * e->subdiv + 1;   // big batches have enough items; small ones need the split for parallelism
+        const size_t nsp = ns * (size_t)w.nplanes;
+        CK(e->tw_int.reserve(3 * ns + nsp + 4), "cudaMalloc trial work");
         CK(e->tw_bins.reserve(3 * nbp), "cudaMalloc trial bins");
         CK(e->tw_pos.reserve(ns), "cudaMalloc trial work");
-        CK(e->tw_E.reserve(ns), "cudaMalloc trial work");
+        CK(e->tw_E.reserve(nsp), "cudaMalloc trial work");
         w.site_trial = e->tw_int.p; w.site_bin = e->tw_int.p + ns; w.sorted = e->tw_int.p + 2 * ns;
-        w.site_cnt = e->tw_int.p + 3 * ns; w.totals = e->tw_int.p + 4 * ns;
+        w.site_cnt = e->tw_int.p + 3 * ns; w.totals = e->tw_int.p + 3 * ns + nsp;
         w.bin_count = e->tw_bins.p; w.item_start = e->tw_bins.p + nbp; w.bin_cursor = e->tw_bins.p + 2 * nbp;
         w.site_pos = e->tw_pos.p; w.site_E = e->tw_E.p;
         CK(cudaMemsetAsync(w.bin_count, 0, nbp * sizeof(int), e->stream), "memset bins");
@@ -654,7 +664,7 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
         if (nsites > 0) {
             trial_scatter_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(w);
             LAUNCH_CHECK("trial_scatter_kernel");
-            long long est = nsites / 32 + (nsites < w.nbins ? nsites : w.nbins) + 1;
+            long long est = ((long long)nsites / 32 + (nsites < w.nbins ? nsites : w.nbins) + 1) * w.nplanes;
             int rb = (int)((est + SITE_WARPS - 1) / SITE_WARPS);
             if (rb > 148 * 32) rb = 148 * 32;
             lj_trial_rows_kernel<<<rb, 32 * SITE_WARPS, 0, e->stream>>>(e->view(), tb, w, e->lj);

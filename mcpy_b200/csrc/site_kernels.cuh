@@ -82,14 +82,17 @@ __device__ __forceinline__ void for_each_piece(const GridDesc& g, const int* __r
     }
 }
 
-// Row sum of one site per lane over the stencil of cell (c0,c1,c2), two phases:
+// Row sum of one site per lane over the stencil of cell (c0,c1,c2), three phases per item:
 //
-//   screen : every candidate of the stencil is tested in fp32 on the wrapped, origin-relative
-//            copies (fpos) against (rcut + margin)^2.  The margin (cell_list.cuh) bounds the fp32
-//            rounding, so the screen never drops a pair the exact test would keep.  Candidates
-//            that pass are appended to the lane's FIFO in shared memory (index only).
-//   exact  : when a FIFO is nearly full (and at the end) all lanes drain theirs: fp64 image
-//            vector in the oracle's operation order, exact cutoff test, exclusions, pair energy,
+//   stage  : one lane per stencil row works out the row's (at most two) contiguous pieces of the
+//            cell-sorted array; the warp copies their fp32 screening records -- with the piece's
+//            image shift already added -- into a dense shared-memory array.
+//   screen : every staged candidate is read with ONE broadcast LDS and tested in fp32 against
+//            (rcut + margin)^2.  The margin (cell_list.cuh) bounds the fp32 rounding, so the screen
+//            never drops a pair the exact test would keep.  Survivors are appended to the lane's
+//            FIFO in shared memory (slot of the atom + slot of the piece).
+//   exact  : when a FIFO is nearly full (and at the end) all lanes drain theirs: fp64 image vector
+//            in the oracle's operation order, exact cutoff test, exclusions, pair energy,
 //            accumulation in candidate order.
 //
 // The screen keeps the warp converged on cheap single-issue instructions; the expensive fp64 path
@@ -97,9 +100,22 @@ __device__ __forceinline__ void for_each_piece(const GridDesc& g, const int* __r
 //   active : this lane holds a site
 //   excl(j): true if atom j must be skipped in EVERY image (moved atoms)
 //   self   : atom index to skip in the zero-shift image only (-1: none)
-#define SITE_QCAP 32              // FIFO entries per lane
+#define SITE_QCAP 32              // FIFO entries per lane (one byte each)
 #define SITE_UNROLL 4
-#define SITE_WARPS 4               // warps per block of the row-sum kernels
+#define SITE_WARPS 4              // warps per block of the row-sum kernels
+#define SITE_MIN_BLOCKS 6         // resident blocks per SM the compiler must allow
+#define SITE_CAND 128             // candidates staged per chunk
+#define SITE_ROWS 8               // stencil rows worked out per batch (one lane each)
+#define SITE_PIECES (2 * SITE_ROWS) // two pieces per stencil row
+
+struct SiteScratch {              // per warp, in shared memory (~8 KB)
+    double4 candd[SITE_CAND];     // staged atoms: original (x, y, z, tag) -- the exact path reads these
+    float4 candf[SITE_CAND];      // fp32 screening copy: wrapped - origin + piece shift; .w = piece slot
+    unsigned char fifo[SITE_QCAP * 32];   // lane-private columns of staged-candidate indices
+    int4 pieces[SITE_PIECES];     // beg, end, unused, kind (0 empty, 1 valid)
+    double dshift[SITE_PIECES][3];// S @ cell of the piece
+    int4 rawS[SITE_PIECES];       // S of the piece
+};
 
 template <class Excl>
 __device__ __forceinline__ void lj_site_rowsum(const GridDesc& g, const double4* __restrict__ spos,
@@ -107,100 +123,93 @@ __device__ __forceinline__ void lj_site_rowsum(const GridDesc& g, const double4*
                                                const int* __restrict__ cstart, const LJParams& p,
                                                int c0, int c1, int c2, int lane, bool active,
                                                double px, double py, double pz, int wsite, int self,
-                                               int* __restrict__ fifo /* [SITE_QCAP][32] of this warp */,
-                                               int4* __restrict__ pieces /* [64] */, float4* __restrict__ shifts /* [64] */,
-                                               int4* __restrict__ rawS /* [32] */,
-                                               Excl&& excl, double& acc, int& cnt) {
+                                               int plane, int nplanes,
+                                               SiteScratch& sc, Excl&& excl, double& acc, int& cnt) {
     int w0, w1, w2;
     unpack_wraps(wsite, w0, w1, w2);
     const float3 pf = screen_pos(g, px, py, pz, w0, w1, w2);
     const float sr2 = g.screen_r2;
     int qn = 0;
 
-    // drain this lane's FIFO: entries are (candidate slot k, packed stencil shift)
+    // exact evaluation of one atom record against this lane's site; `slot` = its stencil piece
+    auto exact = [&](const double4& q, int slot) {
+        const long long tag = tag_of(q);
+        const int j = tag_index(tag);
+        const int wj = tag_wraps(tag);
+        double r2, dx, dy, dz;
+        if (wj == wsite) {
+            const int4 S = sc.rawS[slot];
+            if ((S.x | S.y | S.z) == 0) {       // q + 0.0 == q: skip the three additions, same bits
+                dx = __dsub_rn(q.x, px); dy = __dsub_rn(q.y, py); dz = __dsub_rn(q.z, pz);
+                r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (r2 <= p.rc2 && j != self && !excl(j)) { acc += lj_pair(p, r2); ++cnt; }
+            } else {
+                r2 = image_r2(q.x, q.y, q.z, sc.dshift[slot][0], sc.dshift[slot][1], sc.dshift[slot][2],
+                              px, py, pz, dx, dy, dz);
+                if (r2 <= p.rc2 && !excl(j)) { acc += lj_pair(p, r2); ++cnt; }
+            }
+        } else {                                 // rare: atom or site outside the primary cell
+            const int4 S = sc.rawS[slot];
+            int jx, jy, jz;
+            unpack_wraps(wj, jx, jy, jz);
+            const int T0 = S.x + w0 - jx, T1 = S.y + w1 - jy, T2 = S.z + w2 - jz;
+            double ax, ay, az;
+            shift_vec(g, T0, T1, T2, ax, ay, az);
+            r2 = image_r2(q.x, q.y, q.z, ax, ay, az, px, py, pz, dx, dy, dz);
+            const bool same = (T0 | T1 | T2) == 0;
+            if (r2 <= p.rc2 && !(same && j == self) && !excl(j)) { acc += lj_pair(p, r2); ++cnt; }
+        }
+    };
     auto drain = [&]() {
         const int nmax = __reduce_max_sync(0xffffffffu, qn);
-        for (int i = 0; i < nmax; ++i) {
-            if (i < qn) {
-                const int ent = fifo[i * 32 + lane];
-                const int k = ent & 0xFFFFFF;
-                const int S0 = ((ent >> 24) & 7) - 3, S1 = ((ent >> 27) & 7) - 3;
-                int S2 = (int)(((unsigned)ent) >> 30);     // 2 bits: 0,1,2 -> -1,0,+1 (3: escape)
-                const double4 q = spos[k];
-                const long long tag = tag_of(q);
-                const int j = tag_index(tag);
-                int jx, jy, jz;
-                unpack_wraps(tag_wraps(tag), jx, jy, jz);
-                S2 -= 1;
-                const int T0 = S0 + w0 - jx, T1 = S1 + w1 - jy, T2 = S2 + w2 - jz;
-                double r2, dx, dy, dz;
-                if ((T0 | T1 | T2) == 0) {          // q + 0.0 == q: skip the three additions, same bits
-                    dx = __dsub_rn(q.x, px); dy = __dsub_rn(q.y, py); dz = __dsub_rn(q.z, pz);
-                    r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                    if (r2 <= p.rc2 && j != self && !excl(j)) { acc += lj_pair(p, r2); ++cnt; }
-                } else {
-                    double ax, ay, az;
-                    shift_vec(g, T0, T1, T2, ax, ay, az);
-                    r2 = image_r2(q.x, q.y, q.z, ax, ay, az, px, py, pz, dx, dy, dz);
-                    if (r2 <= p.rc2 && !excl(j)) { acc += lj_pair(p, r2); ++cnt; }
-                }
-            }
+        // two entries per trip: their loads and fp64 chains are independent and overlap
+        for (int i = 0; i < nmax; i += 2) {
+            const bool ha = i < qn, hb = i + 1 < qn;
+            const int ia = ha ? sc.fifo[i * 32 + lane] : 0;
+            const int ib = hb ? sc.fifo[(i + 1) * 32 + lane] : 0;
+            const double4 qa = sc.candd[ia], qb = sc.candd[ib];
+            const int sa = __float_as_int(sc.candf[ia].w), sb = __float_as_int(sc.candf[ib].w);
+            if (ha) exact(qa, sa);
+            if (hb) exact(qb, sb);
         }
         qn = 0;
     };
-
-    // exact path for one piece whose shift does not fit the packed FIFO entry (very thin boxes)
-    auto exact_piece = [&](int beg, int end, int S0, int S1, int S2) {
-        drain();
-        for (int k = beg; k < end; ++k) {
-            const double4 q = spos[k];
-            const long long tag = tag_of(q);
-            const int j = tag_index(tag);
-            int jx, jy, jz;
-            unpack_wraps(tag_wraps(tag), jx, jy, jz);
-            const int T0 = S0 + w0 - jx, T1 = S1 + w1 - jy, T2 = S2 + w2 - jz;
-            double ax, ay, az, dx, dy, dz;
-            shift_vec(g, T0, T1, T2, ax, ay, az);
-            const double r2 = image_r2(q.x, q.y, q.z, ax, ay, az, px, py, pz, dx, dy, dz);
-            const bool same = (T0 | T1 | T2) == 0;
-            if (active && r2 <= p.rc2 && !(same && j == self) && !excl(j)) { acc += lj_pair(p, r2); ++cnt; }
-        }
+    auto test = [&](int i) {
+        const float4 c = sc.candf[i];                              // uniform address: one broadcast LDS
+        const float dx = c.x - pf.x, dy = c.y - pf.y, dz = c.z - pf.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (active && r2 <= sr2) { sc.fifo[qn * 32 + lane] = (unsigned char)i; ++qn; }
     };
-    // fp32 screen of one piece; (fx,fy,fz) = float(S @ cell), spack = packed S for the FIFO
-    auto screen_piece = [&](int beg, int end, float fx, float fy, float fz, int spack) {
-        const float qx = pf.x - fx, qy = pf.y - fy, qz = pf.z - fz;    // d = f - (pf - s)
-        auto test = [&](int k) {
-            const float4 f = __ldg(&fpos[k]);                      // uniform address: one broadcast
-            const float dx = f.x - qx, dy = f.y - qy, dz = f.z - qz;
-            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            if (active && r2 <= sr2) { fifo[qn * 32 + lane] = k | spack; ++qn; }
-        };
-        int k = beg;
-        for (; k + SITE_UNROLL <= end; k += SITE_UNROLL) {
+    // screen the staged chunk, then drain: FIFO entries index the chunk, so it must be empty
+    // before the chunk is overwritten
+    auto screen_staged = [&](int n) {
+        int i = 0;
+        for (; i + SITE_UNROLL <= n; i += SITE_UNROLL) {
             if (__any_sync(0xffffffffu, qn > SITE_QCAP - SITE_UNROLL)) drain();
 #pragma unroll
-            for (int u = 0; u < SITE_UNROLL; ++u) test(k + u);
+            for (int u = 0; u < SITE_UNROLL; ++u) test(i + u);
         }
-        if (k < end) {
+        if (i < n) {
             if (__any_sync(0xffffffffu, qn > SITE_QCAP - SITE_UNROLL)) drain();
-            for (; k < end; ++k) test(k);
+            for (; i < n; ++i) test(i);
         }
+        drain();
     };
 
-    // ---- stencil rows: one lane per row works out its (at most two) contiguous pieces and
-    // publishes them in shared memory; the warp then walks the list with broadcast reads.
     const int n0 = g.ncell[0], n1 = g.ncell[1], n2 = g.ncell[2];
     const int m0 = g.m[0], m1 = g.m[1], m2 = g.m[2];
     const int wr1 = 2 * m1 + 1, wr2 = 2 * m2 + 1;
-    const int nrows = wr1 * wr2;
+    // this work item owns the z-planes plane, plane + nplanes, ... of the stencil (normally one)
+    const int nz = (wr2 - plane + nplanes - 1) / nplanes;
+    const int nrows = (plane < wr2) ? wr1 * nz : 0;
     const bool perx = g.pbc[0] != 0;
     const bool simple_x = !perx || n0 >= 2 * m0 + 1;
-    for (int base = 0; base < nrows; base += 32) {
+    for (int base = 0; base < nrows; base += SITE_ROWS) {
         const int row = base + lane;
         int begA = 0, endA = 0, begB = 0, endB = 0, SxB = 0, Sy = 0, Sz = 0, rowoff = 0;
-        bool valid = row < nrows;
+        bool valid = lane < SITE_ROWS && row < nrows;
         if (valid) {
-            int cy = c1 + (row % wr1) - m1, cz = c2 + (row / wr1) - m2;
+            int cy = c1 + (row % wr1) - m1, cz = c2 + (plane + (row / wr1) * nplanes) - m2;
             if (g.pbc[1]) { Sy = floor_div(cy, n1); cy -= Sy * n1; }
             else if (cy < 0 || cy >= n1) valid = false;
             if (g.pbc[2]) { Sz = floor_div(cz, n2); cz -= Sz * n2; }
@@ -219,36 +228,51 @@ __device__ __forceinline__ void lj_site_rowsum(const GridDesc& g, const double4*
                 }
             }
         }
-        const bool packable = (Sy >= -3 && Sy <= 3 && Sz >= -1 && Sz <= 1);
+        const int nr = min(SITE_ROWS, nrows - base);
         if (simple_x) {
-            // publish: slot 2*lane = piece A (Sx = 0), slot 2*lane+1 = piece B (Sx = SxB)
+          if (lane < SITE_ROWS) {
+            // publish: slot 2*lane = piece A (Sx = 0), slot 2*lane + 1 = piece B (Sx = SxB)
             double ax, ay, az, bx, by, bz;
             shift_vec(g, 0, Sy, Sz, ax, ay, az);
             shift_vec(g, SxB, Sy, Sz, bx, by, bz);
-            const int flag = valid ? (packable ? 1 : 2) : 0;
-            pieces[2 * lane] = make_int4(begA, (valid ? endA : begA), ((0 + 3) << 24) | ((Sy + 3) << 27) | ((Sz + 1) << 30), flag);
-            pieces[2 * lane + 1] = make_int4(begB, (valid ? endB : begB), ((SxB + 3) << 24) | ((Sy + 3) << 27) | ((Sz + 1) << 30), flag);
-            shifts[2 * lane] = make_float4((float)ax, (float)ay, (float)az, 0.f);
-            shifts[2 * lane + 1] = make_float4((float)bx, (float)by, (float)bz, 0.f);
-            // raw S for the unpackable case
-            rawS[lane] = make_int4(SxB, Sy, Sz, 0);
+            const int kind = valid ? 1 : 0;
+            sc.pieces[2 * lane] = make_int4(begA, valid ? endA : begA, 0, kind);
+            sc.pieces[2 * lane + 1] = make_int4(begB, valid ? endB : begB, 0, kind);
+            sc.dshift[2 * lane][0] = ax; sc.dshift[2 * lane][1] = ay; sc.dshift[2 * lane][2] = az;
+            sc.dshift[2 * lane + 1][0] = bx; sc.dshift[2 * lane + 1][1] = by; sc.dshift[2 * lane + 1][2] = bz;
+            sc.rawS[2 * lane] = make_int4(0, Sy, Sz, 0);
+            sc.rawS[2 * lane + 1] = make_int4(SxB, Sy, Sz, 0);
+          }
             __syncwarp();
-            const int nr = min(32, nrows - base);
+            int nst = 0;
             for (int sl = 0; sl < 2 * nr; ++sl) {
-                const int4 pc = pieces[sl];
+                const int4 pc = sc.pieces[sl];
                 if (pc.x >= pc.y) continue;
-                if (pc.w == 1) {
-                    const float4 sh = shifts[sl];
-                    screen_piece(pc.x, pc.y, sh.x, sh.y, sh.z, pc.z);
-                } else {
-                    const int4 rs = rawS[sl >> 1];
-                    exact_piece(pc.x, pc.y, (sl & 1) ? rs.x : 0, rs.y, rs.z);
+                const float fx = (float)sc.dshift[sl][0], fy = (float)sc.dshift[sl][1], fz = (float)sc.dshift[sl][2];
+                int beg = pc.x;
+                while (beg < pc.y) {
+                    const int take = min(SITE_CAND - nst, pc.y - beg);
+                    for (int k = beg + lane; k < beg + take; k += 32) {
+                        const float4 f = __ldg(&fpos[k]);
+                        sc.candd[nst + (k - beg)] = spos[k];
+                        sc.candf[nst + (k - beg)] = make_float4(f.x + fx, f.y + fy, f.z + fz, __int_as_float(sl));
+                    }
+                    nst += take;
+                    beg += take;
+                    if (nst == SITE_CAND) {
+                        __syncwarp();
+                        screen_staged(nst);
+                        nst = 0;
+                        __syncwarp();
+                    }
                 }
             }
             __syncwarp();
+            screen_staged(nst);
+            __syncwarp();
         } else {
-            // box thinner than the stencil along x: every offset is its own image (rare, exact path)
-            const int nr = min(32, nrows - base);
+            // box thinner than the stencil along x: every offset is its own image; exact path
+            // directly (rare, tiny systems)
             for (int rr = 0; rr < nr; ++rr) {
                 if (!__shfl_sync(0xffffffffu, (int)valid, rr)) continue;
                 const int sy = __shfl_sync(0xffffffffu, Sy, rr), sz = __shfl_sync(0xffffffffu, Sz, rr);
@@ -258,12 +282,20 @@ __device__ __forceinline__ void lj_site_rowsum(const GridDesc& g, const double4*
                     const int sx = floor_div(cx, n0);
                     cx -= sx * n0;
                     const int bb = cstart[ro + cx], ee = cstart[ro + cx + 1];
-                    if (bb < ee) exact_piece(bb, ee, sx, sy, sz);
+                    if (bb >= ee) continue;
+                    if (lane == 0) {
+                        sc.rawS[0] = make_int4(sx, sy, sz, 0);
+                        double ax, ay, az;
+                        shift_vec(g, sx, sy, sz, ax, ay, az);
+                        sc.dshift[0][0] = ax; sc.dshift[0][1] = ay; sc.dshift[0][2] = az;
+                    }
+                    __syncwarp();
+                    if (active) for (int k = bb; k < ee; ++k) exact(spos[k], 0);
+                    __syncwarp();
                 }
             }
         }
     }
-    drain();
 }
 
 __device__ __forceinline__ int upper_cell_of_item(const int* __restrict__ item_start, int ncells, int item) {
@@ -279,12 +311,10 @@ __device__ __forceinline__ int upper_cell_of_item(const int* __restrict__ item_s
 // K2 (second generation): per-atom energies.  blockIdx.y = replica; warps stride over
 // the replica's work items (cell, chunk of <= 32 atoms of that cell).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * SITE_WARPS)
-lj_cell_energy_kernel(BatchView b, LJParams p, double* __restrict__ e_atom, int* __restrict__ pair_count) {
-    __shared__ int s_fifo[SITE_WARPS][SITE_QCAP * 32];
-    __shared__ int4 s_pieces[SITE_WARPS][64];
-    __shared__ float4 s_shifts[SITE_WARPS][64];
-    __shared__ int4 s_rawS[SITE_WARPS][32];
+__global__ void __launch_bounds__(32 * SITE_WARPS, SITE_MIN_BLOCKS)
+lj_cell_energy_kernel(BatchView b, LJParams p, int nplanes, double* __restrict__ e_part,
+                      int* __restrict__ cnt_part) {
+    __shared__ SiteScratch s_scratch[SITE_WARPS];
     const int r = blockIdx.y;
     const GridDesc& g = b.grid[r];
     const int off = g.atom_off;
@@ -295,7 +325,9 @@ lj_cell_energy_kernel(BatchView b, LJParams p, double* __restrict__ e_atom, int*
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int n0 = g.ncell[0], n1 = g.ncell[1];
-    for (int item = warp; item < g.nitems; item += nwarps) {
+    const int nwork = g.nitems * nplanes;
+    for (int wi = warp; wi < nwork; wi += nwarps) {
+        const int item = wi / nplanes, plane = wi - item * nplanes;
         const int c = upper_cell_of_item(item_start, g.ncells, item);
         const int chunk = item - item_start[c];
         const int k = cstart[c] + chunk * 32 + lane;
@@ -309,13 +341,27 @@ lj_cell_energy_kernel(BatchView b, LJParams p, double* __restrict__ e_atom, int*
         // idle lanes carry the common wrap value so they never take the slow image path
         lj_site_rowsum(g, spos, b.fpos + off, cstart, p, c0, c1, c2, lane, active, me.x, me.y, me.z,
                        active ? tag_wraps(tag) : pack_wraps(0, 0, 0), active ? tag_index(tag) : -1,
-                       s_fifo[threadIdx.x >> 5], s_pieces[threadIdx.x >> 5], s_shifts[threadIdx.x >> 5],
-                       s_rawS[threadIdx.x >> 5], [](int) { return false; }, acc, cnt);
+                       plane, nplanes, s_scratch[threadIdx.x >> 5], [](int) { return false; }, acc, cnt);
         if (active) {
-            e_atom[off + tag_index(tag)] = 0.5 * acc;
-            if (pair_count) pair_count[off + tag_index(tag)] = cnt;
+            const size_t o = (size_t)(off + tag_index(tag)) * nplanes + plane;
+            e_part[o] = acc;
+            cnt_part[o] = cnt;
         }
     }
+}
+
+// e_atom[a] = 0.5 * sum_planes e_part[a][plane] (fixed order); one thread per atom
+__global__ void __launch_bounds__(256)
+lj_fold_planes_kernel(int total_atoms, int nplanes, const double* __restrict__ e_part,
+                      const int* __restrict__ cnt_part, double* __restrict__ e_atom,
+                      int* __restrict__ pair_count) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= total_atoms) return;
+    double s = 0.0;
+    int c = 0;
+    for (int pl = 0; pl < nplanes; ++pl) { s += e_part[(size_t)a * nplanes + pl]; c += cnt_part[(size_t)a * nplanes + pl]; }
+    e_atom[a] = 0.5 * s;
+    pair_count[a] = c;
 }
 
 // ---------------------------------------------------------------------------
@@ -338,8 +384,9 @@ struct TrialWork {
     int* item_start;       // [nbins + 1]
     int* bin_cursor;       // [nbins]
     int* sorted;           // [nsites] site ids grouped by bin
-    double* site_E;        // [nsites] row sums
-    int* site_cnt;         // [nsites] in-cutoff pairs of the row
+    int nplanes;           // stencil z-planes: one work item per (bin, chunk, plane)
+    double* site_E;        // [nsites][nplanes] partial row sums
+    int* site_cnt;         // [nsites][nplanes] in-cutoff pairs
     int* totals;           // [0] = number of work items
 };
 
@@ -418,17 +465,15 @@ trial_scatter_kernel(TrialWork w) {
     w.sorted[w.bin_count[bin] + atomicAdd(&w.bin_cursor[bin], 1)] = s;
 }
 
-__global__ void __launch_bounds__(32 * SITE_WARPS)
+__global__ void __launch_bounds__(32 * SITE_WARPS, SITE_MIN_BLOCKS)
 lj_trial_rows_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) {
-    __shared__ int s_fifo[SITE_WARPS][SITE_QCAP * 32];
-    __shared__ int4 s_pieces[SITE_WARPS][64];
-    __shared__ float4 s_shifts[SITE_WARPS][64];
-    __shared__ int4 s_rawS[SITE_WARPS][32];
+    __shared__ SiteScratch s_scratch[SITE_WARPS];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int nitems = w.totals[0];
-    for (int item = warp; item < nitems; item += nwarps) {
+    const int nwork = w.totals[0] * w.nplanes;
+    for (int wi = warp; wi < nwork; wi += nwarps) {
+        const int item = wi / w.nplanes, plane = wi - item * w.nplanes;
         const int bin = upper_cell_of_item(w.item_start, w.nbins, item);
         const int chunk = item - w.item_start[bin];
         const int r = bin / w.bin_stride, c = bin - r * w.bin_stride;
@@ -453,14 +498,13 @@ lj_trial_rows_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) {
         int cnt = 0;
         const bool multi = (oe - ob) > 1;
         lj_site_rowsum(g, b.spos + off, b.fpos + off, cstart, p, c0, c1, c2, lane, active, me.x, me.y, me.z,
-                       wsite, -1, s_fifo[threadIdx.x >> 5], s_pieces[threadIdx.x >> 5], s_shifts[threadIdx.x >> 5],
-                       s_rawS[threadIdx.x >> 5],
+                       wsite, -1, plane, w.nplanes, s_scratch[threadIdx.x >> 5],
                        [&](int j) {
                            if (j == ex0) return true;
                            if (multi) for (int e = ob + 1; e < oe; ++e) if (tb.old_idx[e] == j) return true;
                            return false;
                        }, acc, cnt);
-        if (active) { w.site_E[s] = acc; w.site_cnt[s] = cnt; }
+        if (active) { w.site_E[(size_t)s * w.nplanes + plane] = acc; w.site_cnt[(size_t)s * w.nplanes + plane] = cnt; }
     }
 }
 
@@ -476,8 +520,16 @@ lj_trial_combine_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p,
     const int nb = tb.new_off[t], ne = tb.new_off[t + 1];
     double plus = 0.0, minus = 0.0;
     int cnt = 0;
-    for (int k = nb; k < ne; ++k) { plus += w.site_E[w.n_old + k]; cnt += w.site_cnt[w.n_old + k]; }
-    for (int k = ob; k < oe; ++k) { minus += w.site_E[k]; cnt += w.site_cnt[k]; }
+    auto row_of = [&](int sidx, double& e) {           // planes in fixed order
+        double row = 0.0;
+        for (int pl = 0; pl < w.nplanes; ++pl) {
+            row += w.site_E[(size_t)sidx * w.nplanes + pl];
+            cnt += w.site_cnt[(size_t)sidx * w.nplanes + pl];
+        }
+        e += row;
+    };
+    for (int k = nb; k < ne; ++k) row_of(w.n_old + k, plus);
+    for (int k = ob; k < oe; ++k) row_of(k, minus);
     // pairs inside the moved sets (and their periodic self images); a single moved atom can only
     // see its own image when the box is thinner than the cutoff
     if (!g.thin && (ne - nb) <= 1 && (oe - ob) <= 1) {
