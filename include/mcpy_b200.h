@@ -160,6 +160,14 @@ int mcpyb_box_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
                                 const double* offset3, const double* shifts, int nshift,
                                 int64_t* counts_out);
 
+/* ---- min_insert test: replaces the distance loop of InsertionMove.do_trial_move
+ *      (mcpy/moves/insertion_move.py:54-62) and MoleculeInsertionMove
+ *      (molecule_insertion_move.py:61-72).  For each of C candidate points: the smallest
+ *      squared image distance to the atoms of replica `rep` with mask[j] != 0 (all atoms if
+ *      mask is NULL) that lie within mcpyb_cutoff(); +inf if none does.                */
+int mcpyb_min_dist2_host(mcpyb_engine* e, int rep, const double* points, int64_t C,
+                         const uint8_t* mask, double* out_d2);
+
 /* Host-side evaluation of the same PCG64 restatement (no GPU needed): n doubles of
  * Generator.random() after skipping `skip` draws.  Used by the CPU tests to pin the
  * restatement to numpy.                                                          */

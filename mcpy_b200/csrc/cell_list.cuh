@@ -34,6 +34,33 @@ __device__ __forceinline__ double block_reduce_minmax(double v, bool is_min, dou
     return r;
 }
 
+// Inclusive block scan (warp shuffles + one partial per warp); s_w holds >= 32 ints.
+// Every thread of the block must call it; ends with the block synchronised.
+__device__ __forceinline__ int block_inclusive_scan(int v, int* s_w) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    __syncthreads();                       // s_w may still be read from a previous call
+    if (lane == 31) s_w[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        int x = (lane < nw) ? s_w[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += t;
+        }
+        s_w[lane] = x;
+    }
+    __syncthreads();
+    if (wid > 0) v += s_w[wid - 1];
+    return v;
+}
+
 // raw_pos: [sum N][3] doubles, raw_Z: [sum N] int32, atom_off: [R+1] ints, geom: [R]
 __global__ void __launch_bounds__(CL_THREADS, 1)
 build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
@@ -168,15 +195,8 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
     for (int base = 0; base < ncells; base += blockDim.x) {
         const int c = base + tid;
         const int v = (c < ncells) ? cstart[c + 1] : 0;
-        s_scan[tid] = v;
-        __syncthreads();
-        for (int o = 1; o < (int)blockDim.x; o <<= 1) {
-            int t = (tid >= o) ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += t;
-            __syncthreads();
-        }
-        const int incl = s_scan[tid] + s_carry;
+        const int scanned = block_inclusive_scan(v, s_scan);
+        const int incl = scanned + s_carry;
         __syncthreads();
         if (c < ncells) cstart[c + 1] = incl;          // inclusive -> start of next cell
         if (tid == blockDim.x - 1) s_carry = incl;
@@ -221,15 +241,8 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
     for (int base = 0; base < ncells; base += blockDim.x) {
         const int c = base + tid;
         const int v = (c < ncells) ? (cstart[c + 1] - cstart[c] + 31) / 32 : 0;
-        s_scan[tid] = v;
-        __syncthreads();
-        for (int o = 1; o < (int)blockDim.x; o <<= 1) {
-            int t = (tid >= o) ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += t;
-            __syncthreads();
-        }
-        const int incl = s_scan[tid] + s_carry;
+        const int scanned = block_inclusive_scan(v, s_scan);
+        const int incl = scanned + s_carry;
         __syncthreads();
         if (c < ncells) item_start[c] = incl - v;
         if (tid == blockDim.x - 1) s_carry = incl;

@@ -347,9 +347,6 @@ int launch_energies(mcpyb_engine* e) {
             lj_cell_energy_kernel<<<dim3(gx, e->R), 32 * SITE_WARPS, 0, e->stream>>>(e->view(), e->lj, nplanes,
                                                                                    e->e_part.p, e->cnt_part.p);
             LAUNCH_CHECK("lj_cell_energy_kernel");
-            lj_fold_planes_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(total, nplanes, e->e_part.p, e->cnt_part.p,
-                                                                              e->e_atom.p, e->pair_count.p);
-            LAUNCH_CHECK("lj_fold_planes_kernel");
         } else {
             emt_pair_kernel<<<blocks, 256, 0, e->stream>>>(
                 e->view(), e->d_atom_off, total, e->emt_dev.p, e->e_atom.p, e->sigma1.p, e->pair_count.p);
@@ -363,7 +360,8 @@ int launch_energies(mcpyb_engine* e) {
     }
     if (e->R > 0) {
         reduce_replica_kernel<<<e->R, 256, 0, e->stream>>>(
-            e->e_atom.p, e->d_atom_off, e->E.p, e->pair_count.p, e->pairs_ptr(), e->grid.p, e->status_ptr());
+            e->e_atom.p, e->d_atom_off, e->E.p, e->pair_count.p, e->pairs_ptr(), e->grid.p, e->status_ptr(),
+            e->pot_kind == POT_LJ && e->total_atoms > 0 ? e->e_part.p : nullptr, e->cnt_part.p, 2 * e->subdiv + 1);
         LAUNCH_CHECK("reduce_replica_kernel");
     }
     return MCPYB_OK;
@@ -997,6 +995,34 @@ int mcpyb_fp64_peak_tflops(mcpyb_engine* e, double* tflops_out) {
     cudaEventDestroy(t0); cudaEventDestroy(t1);
     out.release();
     *tflops_out = best;
+    return MCPYB_OK;
+}
+
+int mcpyb_min_dist2_host(mcpyb_engine* e, int rep, const double* points, int64_t C,
+                         const uint8_t* mask, double* out_d2) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (!e->have_batch) return e->fail(MCPYB_ERR_STATE, "no resident batch (call mcpyb_upload_* first)");
+    if (rep < 0 || rep >= e->R) return e->fail(MCPYB_ERR_ARG, "replica out of range");
+    if (C < 0 || (C > 0 && (!points || !out_d2))) return e->fail(MCPYB_ERR_ARG, "bad min-distance arguments");
+    if (C == 0) return MCPYB_OK;
+    const int n = e->atom_off_host[rep + 1] - e->atom_off_host[rep];
+    DevBuf<double> d_pts, d_out;
+    DevBuf<unsigned char> d_mask;
+    CK(d_pts.reserve((size_t)3 * C), "cudaMalloc points"); CK(d_out.reserve((size_t)C), "cudaMalloc out");
+    CK(cudaMemcpyAsync(d_pts.p, points, (size_t)C * 24, cudaMemcpyHostToDevice, e->stream), "H2D points");
+    if (mask && n > 0) {
+        CK(d_mask.reserve((size_t)n), "cudaMalloc mask");
+        CK(cudaMemcpyAsync(d_mask.p, mask, (size_t)n, cudaMemcpyHostToDevice, e->stream), "H2D mask");
+    }
+    long long blocks = (C + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    min_dist2_kernel<<<(int)blocks, 256, 0, e->stream>>>(e->view(), rep, d_pts.p, (int)C,
+                                                         (mask && n > 0) ? d_mask.p : nullptr, e->rcut, d_out.p);
+    LAUNCH_CHECK("min_dist2_kernel");
+    CK(cudaMemcpyAsync(out_d2, d_out.p, (size_t)C * 8, cudaMemcpyDeviceToHost, e->stream), "D2H min d2");
+    CK(cudaStreamSynchronize(e->stream), "sync min d2");
+    d_pts.release(); d_out.release(); d_mask.release();
     return MCPYB_OK;
 }
 

@@ -84,11 +84,14 @@ lj_atom_energy_kernel(BatchView b, const int* __restrict__ atom_off, int total_a
 }
 
 // Fixed-order per-replica reduction: E[r] = sum_i e_atom[off+i]; one CTA per replica.
+// With e_part != nullptr it first folds the stencil-plane partials of the lane-per-atom LJ kernel:
+// e_atom[a] = 0.5 * sum_planes e_part[a][plane], pair_count[a] = sum_planes cnt_part[a][plane].
 __global__ void __launch_bounds__(256)
-reduce_replica_kernel(const double* __restrict__ e_atom, const int* __restrict__ atom_off,
-                      double* __restrict__ E, const int* __restrict__ pair_count,
+reduce_replica_kernel(double* __restrict__ e_atom, const int* __restrict__ atom_off,
+                      double* __restrict__ E, int* __restrict__ pair_count,
                       long long* __restrict__ pairs, const GridDesc* __restrict__ grid,
-                      int* __restrict__ status) {
+                      int* __restrict__ status, const double* __restrict__ e_part,
+                      const int* __restrict__ cnt_part, int nplanes) {
     __shared__ double s[8];
     __shared__ long long sc[8];
     const int r = blockIdx.x;
@@ -96,6 +99,16 @@ reduce_replica_kernel(const double* __restrict__ e_atom, const int* __restrict__
     double acc = 0.0;
     long long cnt = 0;
     for (int a = beg + threadIdx.x; a < end; a += blockDim.x) {
+        if (e_part) {
+            double sp = 0.0;
+            int c = 0;
+            for (int pl = 0; pl < nplanes; ++pl) {
+                sp += e_part[(size_t)a * nplanes + pl];
+                c += cnt_part[(size_t)a * nplanes + pl];
+            }
+            e_atom[a] = 0.5 * sp;
+            pair_count[a] = c;
+        }
         acc += e_atom[a];
         if (pair_count) cnt += pair_count[a];
     }
@@ -306,5 +319,35 @@ neighbor_pairs_kernel(BatchView b, int r, double rc, int mode, long long max_pai
                     }
                 }
             });
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K9: min_insert test of InsertionMove / MoleculeInsertionMove
+// (mcpy/moves/insertion_move.py:54-62, molecule_insertion_move.py:61-72): for each candidate
+// point, the smallest squared image distance to the atoms selected by `mask` (all atoms when
+// mask == nullptr) that lie within the engine cutoff; +inf when there is none.  One warp per
+// candidate point; the cell list limits the search to the stencil.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+min_dist2_kernel(BatchView b, int r, const double* __restrict__ points, int C,
+                 const unsigned char* __restrict__ mask, double rcut, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const GridDesc& g = b.grid[r];
+    const int off = g.atom_off;
+    const int* cstart = b.cell_start + (size_t)r * b.cs_stride;
+    const double rc2 = rcut * rcut;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int c = warp; c < C; c += nwarps) {
+        double best = inf;
+        for_each_candidate(g, b.spos + off, cstart, points[3 * c], points[3 * c + 1], points[3 * c + 2], lane, 32,
+            [&](const Cand& cd) {
+                if (cd.r2 <= rc2 && (!mask || mask[tag_index(cd.tag)])) best = fmin(best, cd.r2);
+            });
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (lane == 0) out[c] = best;
     }
 }

@@ -283,3 +283,14 @@ class Engine:
             len(positions), ptr(offset), ptr(shifts), len(shifts), ptr(counts)))
         rng.bit_generator.advance(3 * int(n_points))
         return int(counts[0]), int(counts[1])
+
+    # -- min_insert distance test ---------------------------------------------------
+    def min_dist2(self, points, rep=0, mask=None) -> np.ndarray:
+        """Smallest squared image distance from each point to the (masked) atoms of the
+        resident replica ``rep`` within the cutoff; ``inf`` where no atom is that close."""
+        points = as_f64(points).reshape(-1, 3)
+        mask = None if mask is None else as_u8(np.asarray(mask, dtype=bool))
+        out = np.empty(len(points), dtype=np.float64)
+        self._check(self._lib.mcpyb_min_dist2_host(self._h, int(rep), ptr(points), len(points),
+                                                   ptr(mask), ptr(out)))
+        return out

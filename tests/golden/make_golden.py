@@ -31,7 +31,8 @@ from ase import Atoms  # noqa: E402
 from ase.cluster import Octahedron  # noqa: E402
 from mcpy.cell import Cell, SphericalCell  # noqa: E402
 from mcpy.ensembles import GrandCanonicalEnsemble  # noqa: E402
-from mcpy.moves import DeletionMove, DisplacementMove, InsertionMove, MoveSelector  # noqa: E402
+from mcpy.moves import (DeletionMove, DisplacementMove, InsertionMove, MoleculeInsertionMove,  # noqa: E402
+                        MoveSelector)
 from oracle import cfast  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -156,6 +157,52 @@ def emt_trace():
           len(vol_log['volume']), 'volume refreshes, final N', len(g.atoms))
 
 
+def _pcg_words(rng):
+    st = rng.bit_generator.state['state']
+    m = (1 << 64) - 1
+    return [st['state'] >> 64, st['state'] & m, st['inc'] >> 64, st['inc'] & m]
+
+
+def insertion_trace():
+    """Reference InsertionMove / MoleculeInsertionMove with min_insert in a dense periodic box:
+    configuration and generator states after every proposal."""
+    L = 8.0
+    rng = np.random.default_rng(4)
+    base = Atoms('H150', positions=rng.uniform(0, L, size=(150, 3)), cell=[L, L, L], pbc=True)
+    out = dict(L=L, base=base.positions.copy())
+    a = base.copy()
+    c = Cell(a, species_radii={'H': 1.0}, seed=9)
+    m = InsertionMove(c, species=['H'], seed=5, min_insert=1.15)
+    pos, ok, states = [], [], []
+    for _ in range(12):
+        r = m.do_trial_move(a)
+        ok.append(r[0] is not False)
+        pos.append(a.positions.copy())
+        states.append(_pcg_words(c._rng))
+    out.update(atom_off=np.concatenate([[0], np.cumsum([len(p) for p in pos])]), atom_pos=np.concatenate(pos),
+               atom_ok=np.array(ok), atom_cell_state=np.array(states, dtype=np.uint64))
+    dimer = Atoms('H2', positions=[[0, 0, 0], [0, 0, 0.9]])
+    a = base.copy()
+    c = Cell(a, species_radii={'H': 1.0}, seed=19)
+    m = MoleculeInsertionMove(c, dimer, 'H2', seed=6, min_insert=1.1)
+    pos, ok, states, pystates, counts = [], [], [], [], []
+    for _ in range(8):
+        r = m.do_trial_move(a)
+        ok.append(r[0] is not False)
+        pos.append(a.positions.copy())
+        states.append(_pcg_words(c._rng))
+        st = m.rng.random.getstate()
+        pystates.append(np.array(st[1], dtype=np.uint64))
+        counts.append(-1 if m.last_exchange_count is None else m.last_exchange_count)
+    out.update(mol_off=np.concatenate([[0], np.cumsum([len(p) for p in pos])]), mol_pos=np.concatenate(pos),
+               mol_ok=np.array(ok), mol_cell_state=np.array(states, dtype=np.uint64),
+               mol_py_state=np.array(pystates), mol_count=np.array(counts),
+               mol_ids=np.asarray(a.arrays['molecule_id']))
+    np.savez_compressed(os.path.join(OUT, 'insertion_trace.npz'), **out)
+    print('insertion trace:', int(np.sum(out['atom_ok'])), 'of 12 atoms,', int(np.sum(out['mol_ok'])), 'of 8 dimers placed')
+
+
 if __name__ == '__main__':
     lj_trace()
     emt_trace()
+    insertion_trace()
