@@ -309,6 +309,12 @@ def run_b200(args):
 
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- secondary workloads of the same path (rank 0 only, untimed by the driver's metric):
+    # EMT energies / trial dE on S3 (Ag140 + O) and S5 (~10.8k-atom CuPd + CO), free volume on both
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        extra = secondary_workloads(local)
+
     # ---- roofline of the trial kernel (FP64 pipe)
     sites = n_old + n_new
     alg_flop = sites * ALG_CANDIDATES_PER_SITE * ALG_FLOP_PER_CANDIDATE + pairs_per_step * ALG_FLOP_PER_PAIR
@@ -371,10 +377,64 @@ def run_b200(args):
     }
     if cpu_baseline is not None:
         line['cpu_baseline'] = cpu_baseline
+    if extra:
+        line['secondary'] = extra
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _time(fn, reps):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def secondary_workloads(device):
+    """EMT and free-volume numbers next to their CPU counterparts (small, bounded samples)."""
+    from scipy.spatial import cKDTree
+
+    from mcpy_b200 import Engine
+    from mcpy_b200.utils import synthetic
+    out = {}
+    eng = Engine(device)
+    eng.set_emt()
+    for name, cfg, T in (('S3_Ag140_O20', synthetic.s3_ag_o(), 4096), ('S5_CuPd_CO_10825', synthetic.s5_cupd_co(), 4096)):
+        pos, num, cell, pbc = cfg['positions'], cfg['numbers'], cfg['cell'], cfg['pbc']
+        t_e = _time(lambda: eng.potential_energy(pos, num, cell, pbc), 5)
+        eng.upload([pos], [num], cell.reshape(1, 9), pbc.reshape(1, 3))
+        eng.energies()
+        tb = synthetic.trial_batch(cfg, T, seed=11, insert_Z=8)
+        args = (tb['old_off'], tb['old_idx'], tb['new_off'], tb['new_pos'], tb['new_Z'])
+        t_t = _time(lambda: eng.trial_delta_e(*args), 3)
+        # free volume: host points uploaded vs PCG64 regenerated on the device, vs scipy cKDTree
+        P = int(cfg['mc_sample_points'])
+        rng = np.random.default_rng(3)
+        t_dev = _time(lambda: eng.sphere_free_volume_pcg64(rng, P, cfg['sphere_radius'], np.zeros(3), pos, cfg['radii']), 3)
+
+        def cpu_fv():
+            pts = (np.random.default_rng(3).random((int(1.5 * P) + 1, 3)) - 0.5) * 2.0 * cfg['sphere_radius']
+            pts = pts[np.einsum('ij,ij->i', pts, pts) <= cfg['sphere_radius'] ** 2][:P]
+            cov = np.zeros(len(pts), bool)
+            for r in np.unique(cfg['radii']):
+                if r > 0:
+                    d, _ = cKDTree(pos[cfg['radii'] == r]).query(pts, k=1, distance_upper_bound=float(r))
+                    cov |= np.isfinite(d)
+            return cov.sum()
+        t_cpu = _time(cpu_fv, 1)
+        out[name] = {
+            'n_atoms': int(len(pos)),
+            'emt_energy_calls_per_s_host_buffers': 1.0 / t_e,
+            'emt_trial_dE_evals_per_s_host_buffers': T / t_t,
+            'free_volume_points': P,
+            'free_volume_points_per_s_device_pcg64': P / t_dev,
+            'free_volume_points_per_s_cpu_ckdtree_1core': P / t_cpu,
+        }
+    eng.close()
+    return out
 
 
 def main():
@@ -386,6 +446,7 @@ def main():
     ap.add_argument('--trials', type=int, default=65536, help='proposals per step')
     ap.add_argument('--chain', type=int, default=2000, help='sequential drop-in calls to time')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary EMT / free-volume numbers')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3

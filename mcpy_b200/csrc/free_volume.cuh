@@ -13,6 +13,7 @@
 //                   warp ballot -> block sum -> one 64-bit atomicAdd per CTA.
 #pragma once
 #include "common.cuh"
+#include "cell_list.cuh"      // block_reduce_minmax, block_inclusive_scan
 
 struct FvGrid {
     double lo[3];
@@ -135,15 +136,8 @@ fv_build_kernel(const double* __restrict__ pos, const double* __restrict__ radii
     __syncthreads();
     for (int base = 0; base < ncells; base += blockDim.x) {
         const int c = base + tid;
-        s_scan[tid] = (c < ncells) ? cell_start[c + 1] : 0;
-        __syncthreads();
-        for (int o = 1; o < (int)blockDim.x; o <<= 1) {
-            int t = (tid >= o) ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += t;
-            __syncthreads();
-        }
-        const int incl = s_scan[tid] + s_carry;
+        const int scanned = block_inclusive_scan((c < ncells) ? cell_start[c + 1] : 0, s_scan);
+        const int incl = scanned + s_carry;
         __syncthreads();
         if (c < ncells) cell_start[c + 1] = incl;
         if (tid == blockDim.x - 1) s_carry = incl;

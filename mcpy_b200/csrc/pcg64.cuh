@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "free_volume.cuh"
+#include "cell_list.cuh"      // block_inclusive_scan
 
 typedef unsigned __int128 u128;
 
@@ -47,7 +48,8 @@ __host__ __device__ __forceinline__ double pcg_next_double(u128& state, u128 inc
     return (double)(out >> 11) * (1.0 / 9007199254740992.0);
 }
 
-#define PCG_CHUNK 64          // candidates / points per thread
+#define PCG_CHUNK 8           // candidates / points per thread (jump-ahead amortised over 8)
+#define PCG_BLOCK 256         // threads per block -> 2048 candidates per block
 
 struct SphereCtl {
     long long filled;         // points accepted so far
@@ -65,37 +67,47 @@ __device__ __forceinline__ bool sphere_candidate(u128& st, u128 inc, double R, d
     return d2 <= R2;
 }
 
-// pass A: accepted candidates per thread chunk
-__global__ void __launch_bounds__(256)
-pcg_sphere_count_kernel(Pcg64 rng, long long pass, long long M, double R, long long P,
-                        const SphereCtl* __restrict__ ctl, int* __restrict__ acc_count) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long c0 = t * PCG_CHUNK;
-    if (c0 >= M) return;
-    if (ctl->filled >= P) { acc_count[t] = 0; return; }          // nothing needed: consume nothing
-    const long long c1 = min(c0 + (long long)PCG_CHUNK, M);
-    const long long used = ctl->passes;                           // passes already consumed
-    (void)pass;
-    u128 st = pcg_advance(rng.state, rng.inc, (unsigned long long)(3 * (used * M + c0)));
-    const double R2 = __dmul_rn(R, R);
-    int n = 0;
-    for (long long c = c0; c < c1; ++c) {
-        double x, y, z;
-        n += sphere_candidate(st, rng.inc, R, R2, x, y, z) ? 1 : 0;
-    }
-    acc_count[t] = n;
+__device__ __forceinline__ int block_sum_int(int v, int* s_w /* [32] */) {
+    v = warp_sum_int(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_w[w];
+    return t;
 }
 
-// single block: exclusive scan of acc_count -> acc_prefix, pass_total
+// pass A: accepted candidates per BLOCK of 2048 candidates
+__global__ void __launch_bounds__(PCG_BLOCK)
+pcg_sphere_count_kernel(Pcg64 rng, long long M, double R, long long P,
+                        const SphereCtl* __restrict__ ctl, int* __restrict__ block_count) {
+    __shared__ int s_w[32];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long c0 = t * PCG_CHUNK;
+    int n = 0;
+    if (c0 < M && ctl->filled < P) {                              // a pass that is not needed consumes nothing
+        const long long c1 = min(c0 + (long long)PCG_CHUNK, M);
+        u128 st = pcg_advance(rng.state, rng.inc, (unsigned long long)(3 * (ctl->passes * M + c0)));
+        const double R2 = __dmul_rn(R, R);
+        for (long long c = c0; c < c1; ++c) {
+            double x, y, z;
+            n += sphere_candidate(st, rng.inc, R, R2, x, y, z) ? 1 : 0;
+        }
+    }
+    const int tot = block_sum_int(n, s_w);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of block_count -> block_prefix, pass_total
 __global__ void __launch_bounds__(1024, 1)
-pcg_scan_kernel(const int* __restrict__ acc_count, long long* __restrict__ acc_prefix, long long nthreads,
+pcg_scan_kernel(const int* __restrict__ block_count, long long* __restrict__ block_prefix, long long nblocks,
                 SphereCtl* __restrict__ ctl) {
     __shared__ long long s[1024];
     const int tid = threadIdx.x;
-    const long long per = (nthreads + 1023) / 1024;
-    const long long beg = min((long long)tid * per, nthreads), end = min(beg + per, nthreads);
+    const long long per = (nblocks + 1023) / 1024;
+    const long long beg = min((long long)tid * per, nblocks), end = min(beg + per, nblocks);
     long long sum = 0;
-    for (long long i = beg; i < end; ++i) sum += acc_count[i];
+    for (long long i = beg; i < end; ++i) sum += block_count[i];
     s[tid] = sum;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
@@ -105,35 +117,52 @@ pcg_scan_kernel(const int* __restrict__ acc_count, long long* __restrict__ acc_p
         __syncthreads();
     }
     long long run = s[tid] - sum;
-    for (long long i = beg; i < end; ++i) { acc_prefix[i] = run; run += acc_count[i]; }
+    for (long long i = beg; i < end; ++i) { block_prefix[i] = run; run += block_count[i]; }
     if (tid == 1023) ctl->pass_total = s[1023];
 }
 
-// pass B: regenerate, evaluate the accepted candidates whose stream rank is still needed
-__global__ void __launch_bounds__(256)
+// pass B: regenerate, rank the accepted candidates in stream order, evaluate those still needed
+__global__ void __launch_bounds__(PCG_BLOCK)
 pcg_sphere_eval_kernel(Pcg64 rng, long long M, double R, long long P, double cx, double cy, double cz,
-                       const SphereCtl* __restrict__ ctl, const long long* __restrict__ acc_prefix,
+                       const SphereCtl* __restrict__ ctl, const long long* __restrict__ block_prefix,
                        const FvGrid* __restrict__ gridp, const double4* __restrict__ spheres,
                        const int* __restrict__ cell_start, unsigned long long* __restrict__ counts) {
     __shared__ int s_cnt[8];
+    __shared__ int s_scan[32];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long c0 = t * PCG_CHUNK;
-    int covered_local = 0, total_local = 0;
     const long long need = P - ctl->filled;
-    if (c0 < M && need > 0) {
-        const FvGrid g = *gridp;
-        const long long c1 = min(c0 + (long long)PCG_CHUNK, M);
-        long long rank = acc_prefix[t];
-        if (rank < need) {
+    int covered_local = 0, total_local = 0;
+    if (need > 0 && block_prefix[blockIdx.x] < need) {            // block-uniform
+        double px[PCG_CHUNK], py[PCG_CHUNK], pz[PCG_CHUNK];
+        unsigned acc_mask = 0;
+        int n = 0;
+        if (c0 < M) {
+            const long long c1 = min(c0 + (long long)PCG_CHUNK, M);
             u128 st = pcg_advance(rng.state, rng.inc, (unsigned long long)(3 * (ctl->passes * M + c0)));
             const double R2 = __dmul_rn(R, R);
-            for (long long c = c0; c < c1 && rank < need; ++c) {
-                double x, y, z;
-                if (sphere_candidate(st, rng.inc, R, R2, x, y, z)) {
-                    const bool cov = fv_point_covered(g, spheres, cell_start,
-                                                      __dadd_rn(x, cx), __dadd_rn(y, cy), __dadd_rn(z, cz));
-                    covered_local += cov ? 1 : 0;
-                    total_local += 1;
+#pragma unroll
+            for (int k = 0; k < PCG_CHUNK; ++k) {
+                if (c0 + k < c1 && sphere_candidate(st, rng.inc, R, R2, px[k], py[k], pz[k])) {
+                    acc_mask |= 1u << k;
+                    ++n;
+                }
+            }
+        }
+        // exclusive rank of this thread's first accepted candidate inside the block
+        const int incl = block_inclusive_scan(n, s_scan);
+        long long rank = block_prefix[blockIdx.x] + (incl - n);
+        if (rank < need) {
+            const FvGrid g = *gridp;
+#pragma unroll
+            for (int k = 0; k < PCG_CHUNK; ++k) {
+                if ((acc_mask >> k) & 1u) {
+                    if (rank < need) {
+                        const bool cov = fv_point_covered(g, spheres, cell_start, __dadd_rn(px[k], cx),
+                                                          __dadd_rn(py[k], cy), __dadd_rn(pz[k], cz));
+                        covered_local += cov ? 1 : 0;
+                        total_local += 1;
+                    }
                     ++rank;
                 }
             }
@@ -151,7 +180,7 @@ __global__ void pcg_sphere_commit_kernel(SphereCtl* ctl, long long P) {
 }
 
 // CustomCell: point i = rng.random(3) @ dims, one kernel
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PCG_BLOCK)
 pcg_box_eval_kernel(Pcg64 rng, long long P, const double* __restrict__ dims /* 9, device */,
                     const FvGrid* __restrict__ gridp, const double4* __restrict__ spheres,
                     const int* __restrict__ cell_start, unsigned long long* __restrict__ counts) {
