@@ -53,6 +53,7 @@ enum PotKind { POT_NONE = 0, POT_LJ = 1, POT_EMT = 2 };
 
 struct EmtSpecies {      // derived constants of ase.calculators.emt
     double E0, s0, V0, eta2, kappa, lambda, n0, gamma1, gamma2;
+    double inv_gamma1, inv_gamma2;
 };
 
 struct Potential {

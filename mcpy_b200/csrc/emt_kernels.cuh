@@ -18,7 +18,7 @@
 #include "lj_kernels.cuh"      // TrialBatch, group_sum, find_replica
 
 struct EmtTable {
-    double rc, rc_list, acut, beta;
+    double rc, rc_list, acut, beta, inv_beta;
     int nspecies;
     EmtSpecies sp[MCPYB_MAX_SPECIES];
     double ksi[MCPYB_MAX_SPECIES][MCPYB_MAX_SPECIES];   // ksi[a][b] = n0_b / n0_a
@@ -31,9 +31,11 @@ __device__ __forceinline__ void emt_row_terms(const EmtTable& t, int a, int b, d
     const EmtSpecies& pb = t.sp[b];
     const double ksi = t.ksi[a][b];
     const double x = exp(t.acut * (r - t.rc));
-    const double theta = 1.0 / (1.0 + x);
-    depair = -(0.5 * pa.V0 * exp(-pb.kappa * (r / t.beta - pb.s0)) * ksi / pa.gamma2 * theta);
-    dsigma = exp(-pb.eta2 * (r - t.beta * pb.s0)) * ksi * theta / pa.gamma1;
+    const double theta = fast_rcp(1.0 + x);
+    // the three divisions of ASE's expression (r / beta, / gamma2, / gamma1) become multiplications
+    // by reciprocals that are within an ulp: 1e-16 relative, far inside the 1e-10 bar
+    depair = -(0.5 * pa.V0 * exp(-pb.kappa * (r * t.inv_beta - pb.s0)) * ksi * pa.inv_gamma2 * theta);
+    dsigma = exp(-pb.eta2 * (r - t.beta * pb.s0)) * ksi * theta * pa.inv_gamma1;
 }
 
 __device__ __forceinline__ double emt_embed(const EmtTable& t, int a, double sigma1) {
@@ -266,3 +268,9 @@ emt_trial_delta_kernel(BatchView b, TrialBatch tb, const EmtTable* __restrict__ 
         }
     }
 }
+
+// Note (round 1): a lane-per-site variant of these kernels (the scheme of site_kernels.cuh) was
+// built and measured: with cell edge = rc_list only ~17 of 32 lanes hold an atom and the per-hit
+// functor (three exp, two embeddings) is register-hungry; it ran 185 us against 100 us for
+// emt_pair_kernel on the 10 825-atom S5 configuration and 4x slower on trial batches, so EMT stays
+// on the warp-per-site traversal (profiles/README.md).

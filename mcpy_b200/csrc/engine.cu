@@ -348,18 +348,20 @@ int launch_energies(mcpyb_engine* e) {
                                                                                    e->e_part.p, e->cnt_part.p);
             LAUNCH_CHECK("lj_cell_energy_kernel");
         } else {
+            // EMT keeps the warp-per-atom traversal: with ~17 atoms per cell (edge = rc_list) the
+            // lane-per-atom kernel (emt_cell_pair_kernel) leaves half the lanes idle and measured
+            // 185 us against 100 us on the 10 825-atom S5 configuration (profiles/README.md).
             emt_pair_kernel<<<blocks, 256, 0, e->stream>>>(
                 e->view(), e->d_atom_off, total, e->emt_dev.p, e->e_atom.p, e->sigma1.p, e->pair_count.p);
             LAUNCH_CHECK("emt_pair_kernel");
             const int eb = (total + 255) / 256;
-            emt_embed_kernel<<<eb, 256, 0, e->stream>>>(
-                e->view(), total, e->emt_dev.p, e->sigma1.p, e->e_atom.p);
+            emt_embed_kernel<<<eb, 256, 0, e->stream>>>(e->view(), total, e->emt_dev.p, e->sigma1.p, e->e_atom.p);
             LAUNCH_CHECK("emt_embed_kernel");
             e->emt_state_valid = true;
         }
     }
     if (e->R > 0) {
-        reduce_replica_kernel<<<e->R, 256, 0, e->stream>>>(
+        reduce_replica_kernel<<<e->R, e->max_n > 1024 ? 1024 : 256, 0, e->stream>>>(
             e->e_atom.p, e->d_atom_off, e->E.p, e->pair_count.p, e->pairs_ptr(), e->grid.p, e->status_ptr(),
             e->pot_kind == POT_LJ && e->total_atoms > 0 ? e->e_part.p : nullptr, e->cnt_part.p, 2 * e->subdiv + 1);
         LAUNCH_CHECK("reduce_replica_kernel");
@@ -469,7 +471,7 @@ int mcpyb_set_emt(mcpyb_engine* e) {
     const double rc = kEmtBeta * maxseq * 0.5 * (sqrt(3.0) + sqrt(4.0));
     const double rr = rc * 2 * sqrt(4.0) / (sqrt(3.0) + sqrt(4.0));
     const double acut = log(9999.0) / (rr - rc);
-    t.rc = rc; t.acut = acut; t.beta = kEmtBeta; t.rc_list = rc + 0.5; t.nspecies = ns;
+    t.rc = rc; t.acut = acut; t.beta = kEmtBeta; t.inv_beta = 1.0 / kEmtBeta; t.rc_list = rc + 0.5; t.nspecies = ns;
     for (int i = 0; i < 120; ++i) e->z_to_slot_host[i] = -1;
     for (int k = 0; k < ns; ++k) {
         const EmtRow& p = kEmtRows[k];
@@ -484,7 +486,7 @@ int mcpyb_set_emt(mcpyb_engine* e) {
             g1 += x * exp(-s.eta2 * (r - kEmtBeta * s.s0));
             g2 += x * exp(-s.kappa / kEmtBeta * (r - kEmtBeta * s.s0));
         }
-        s.gamma1 = g1; s.gamma2 = g2;
+        s.gamma1 = g1; s.gamma2 = g2; s.inv_gamma1 = 1.0 / g1; s.inv_gamma2 = 1.0 / g2;
         e->z_to_slot_host[p.Z] = k;
     }
     for (int a = 0; a < ns; ++a)
@@ -638,46 +640,51 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     // every bit of its delta-E -- does not depend on the batch it arrives in.
     int blocks = (T + 7) / 8;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    if (e->pot_kind == POT_LJ) {
-        const int nsites = n_old_total + n_new_total;
-        TrialWork w;
-        w.nsites = nsites; w.n_old = n_old_total;
-        w.bin_stride = e->max_cells; w.nbins = e->R * e->max_cells;
-        const size_t ns = (size_t)(nsites > 0 ? nsites : 1), nbp = (size_t)w.nbins + 1;
-        w.nplanes = (nsites >= 4096) ? 1 : 2 * e->subdiv + 1;   // big batches have enough items; small ones need the split for parallelism
-        const size_t nsp = ns * (size_t)w.nplanes;
-        CK(e->tw_int.reserve(3 * ns + nsp + 4), "cudaMalloc trial work");
-        CK(e->tw_bins.reserve(3 * nbp), "cudaMalloc trial bins");
-        CK(e->tw_pos.reserve(ns), "cudaMalloc trial work");
-        CK(e->tw_E.reserve(nsp), "cudaMalloc trial work");
-        w.site_trial = e->tw_int.p; w.site_bin = e->tw_int.p + ns; w.sorted = e->tw_int.p + 2 * ns;
-        w.site_cnt = e->tw_int.p + 3 * ns; w.totals = e->tw_int.p + 3 * ns + nsp;
-        w.bin_count = e->tw_bins.p; w.item_start = e->tw_bins.p + nbp; w.bin_cursor = e->tw_bins.p + 2 * nbp;
-        w.site_pos = e->tw_pos.p; w.site_E = e->tw_E.p;
-        CK(cudaMemsetAsync(w.bin_count, 0, nbp * sizeof(int), e->stream), "memset bins");
-        trial_sites_kernel<<<(T + 255) / 256, 256, 0, e->stream>>>(e->view(), tb, w);
-        LAUNCH_CHECK("trial_sites_kernel");
-        trial_scan_kernel<<<1, 1024, 0, e->stream>>>(w);
-        LAUNCH_CHECK("trial_scan_kernel");
+    if (e->pot_kind == POT_EMT && !e->emt_state_valid) {
+        int rc = launch_energies(e);           // sigma1 / e_atom of the resident batch
+        if (rc != MCPYB_OK) return rc;
+    }
+    const int nsites = n_old_total + n_new_total;
+    if (e->pot_kind == POT_EMT) {
+        // one warp per trial, lanes over the candidates (see the note at the end of emt_kernels.cuh)
+        emt_trial_delta_kernel<32><<<blocks, 256, 0, e->stream>>>(
+            e->view(), tb, e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p, d_dE, d_pairs);
+        LAUNCH_CHECK("emt_trial_delta_kernel");
+        return MCPYB_OK;
+    }
+    TrialWork w;
+    w.nsites = nsites; w.n_old = n_old_total;
+    w.bin_stride = e->max_cells; w.nbins = e->R * e->max_cells;
+    const size_t ns = (size_t)(nsites > 0 ? nsites : 1), nbp = (size_t)w.nbins + 1;
+    w.nplanes = (nsites >= 4096) ? 1 : 2 * e->subdiv + 1;   // big batches have enough items; small ones need the split for parallelism
+    const size_t nsp = ns * (size_t)w.nplanes;
+    CK(e->tw_int.reserve(3 * ns + nsp + 4), "cudaMalloc trial work");
+    CK(e->tw_bins.reserve(3 * nbp), "cudaMalloc trial bins");
+    CK(e->tw_pos.reserve(ns), "cudaMalloc trial work");
+    CK(e->tw_E.reserve(nsp), "cudaMalloc trial work");
+    w.site_trial = e->tw_int.p; w.site_bin = e->tw_int.p + ns; w.sorted = e->tw_int.p + 2 * ns;
+    w.site_cnt = e->tw_int.p + 3 * ns; w.totals = e->tw_int.p + 3 * ns + nsp;
+    w.bin_count = e->tw_bins.p; w.item_start = e->tw_bins.p + nbp; w.bin_cursor = e->tw_bins.p + 2 * nbp;
+    w.site_pos = e->tw_pos.p; w.site_E = e->tw_E.p;
+    CK(cudaMemsetAsync(w.bin_count, 0, nbp * sizeof(int), e->stream), "memset bins");
+    trial_sites_kernel<<<(T + 255) / 256, 256, 0, e->stream>>>(e->view(), tb, w);
+    LAUNCH_CHECK("trial_sites_kernel");
+    trial_scan_kernel<<<1, 1024, 0, e->stream>>>(w);
+    LAUNCH_CHECK("trial_scan_kernel");
+    long long est = ((long long)nsites / 32 + (nsites < w.nbins ? nsites : w.nbins) + 1) * w.nplanes;
+    int rb = (int)((est + SITE_WARPS - 1) / SITE_WARPS);
+    if (rb > 148 * 32) rb = 148 * 32;
+    if (nsites > 0) {
+        trial_scatter_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(w);
+        LAUNCH_CHECK("trial_scatter_kernel");
+    }
+    {
         if (nsites > 0) {
-            trial_scatter_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(w);
-            LAUNCH_CHECK("trial_scatter_kernel");
-            long long est = ((long long)nsites / 32 + (nsites < w.nbins ? nsites : w.nbins) + 1) * w.nplanes;
-            int rb = (int)((est + SITE_WARPS - 1) / SITE_WARPS);
-            if (rb > 148 * 32) rb = 148 * 32;
             lj_trial_rows_kernel<<<rb, 32 * SITE_WARPS, 0, e->stream>>>(e->view(), tb, w, e->lj);
             LAUNCH_CHECK("lj_trial_rows_kernel");
         }
         lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
         LAUNCH_CHECK("lj_trial_combine_kernel");
-    } else {
-        if (!e->emt_state_valid) {
-            int rc = launch_energies(e);       // sigma1 / e_atom of the resident batch
-            if (rc != MCPYB_OK) return rc;
-        }
-        emt_trial_delta_kernel<32><<<blocks, 256, 0, e->stream>>>(
-            e->view(), tb, e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p, d_dE, d_pairs);
-        LAUNCH_CHECK("emt_trial_delta_kernel");
     }
     return MCPYB_OK;
 }

@@ -86,14 +86,14 @@ lj_atom_energy_kernel(BatchView b, const int* __restrict__ atom_off, int total_a
 // Fixed-order per-replica reduction: E[r] = sum_i e_atom[off+i]; one CTA per replica.
 // With e_part != nullptr it first folds the stencil-plane partials of the lane-per-atom LJ kernel:
 // e_atom[a] = 0.5 * sum_planes e_part[a][plane], pair_count[a] = sum_planes cnt_part[a][plane].
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 reduce_replica_kernel(double* __restrict__ e_atom, const int* __restrict__ atom_off,
                       double* __restrict__ E, int* __restrict__ pair_count,
                       long long* __restrict__ pairs, const GridDesc* __restrict__ grid,
                       int* __restrict__ status, const double* __restrict__ e_part,
                       const int* __restrict__ cnt_part, int nplanes) {
-    __shared__ double s[8];
-    __shared__ long long sc[8];
+    __shared__ double s[32];
+    __shared__ long long sc[32];
     const int r = blockIdx.x;
     const int beg = atom_off[r], end = atom_off[r + 1];
     double acc = 0.0;

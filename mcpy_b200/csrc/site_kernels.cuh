@@ -117,14 +117,20 @@ struct SiteScratch {              // per warp, in shared memory (~8 KB)
     int4 rawS[SITE_PIECES];       // S of the piece
 };
 
-template <class Excl>
-__device__ __forceinline__ void lj_site_rowsum(const GridDesc& g, const double4* __restrict__ spos,
-                                               const float4* __restrict__ fpos,
-                                               const int* __restrict__ cstart, const LJParams& p,
-                                               int c0, int c1, int c2, int lane, bool active,
-                                               double px, double py, double pz, int wsite, int self,
-                                               int plane, int nplanes,
-                                               SiteScratch& sc, Excl&& excl, double& acc, int& cnt) {
+// within(r2) -> bool : the exact cutoff test (LJ: r2 <= rc^2, EMT: sqrt(r2) < rc_list)
+// hit(q, ax, ay, az, r2): one neighbour image inside the cutoff; q = its atom record, (ax,ay,az) =
+//                         S @ cell of the image (absolute image position = q + a)
+// plane_done()  : all rows of one stencil z-plane have been evaluated (FIFO drained) -- callers
+//                 fold their per-plane partial sums here, which makes a row sum independent of how
+//                 the planes are distributed over work items
+template <class Within, class Hit, class PlaneDone>
+__device__ __forceinline__ void site_rowsum(const GridDesc& g, const double4* __restrict__ spos,
+                                            const float4* __restrict__ fpos,
+                                            const int* __restrict__ cstart,
+                                            int c0, int c1, int c2, int lane, bool active,
+                                            double px, double py, double pz, int wsite, int self,
+                                            int plane, int nplanes,
+                                            SiteScratch& sc, Within&& within, Hit&& hit, PlaneDone&& plane_done) {
     int w0, w1, w2;
     unpack_wraps(wsite, w0, w1, w2);
     const float3 pf = screen_pos(g, px, py, pz, w0, w1, w2);
@@ -142,11 +148,11 @@ __device__ __forceinline__ void lj_site_rowsum(const GridDesc& g, const double4*
             if ((S.x | S.y | S.z) == 0) {       // q + 0.0 == q: skip the three additions, same bits
                 dx = __dsub_rn(q.x, px); dy = __dsub_rn(q.y, py); dz = __dsub_rn(q.z, pz);
                 r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if (r2 <= p.rc2 && j != self && !excl(j)) { acc += lj_pair(p, r2); ++cnt; }
+                if (within(r2) && j != self) hit(q, 0.0, 0.0, 0.0, r2);
             } else {
-                r2 = image_r2(q.x, q.y, q.z, sc.dshift[slot][0], sc.dshift[slot][1], sc.dshift[slot][2],
-                              px, py, pz, dx, dy, dz);
-                if (r2 <= p.rc2 && !excl(j)) { acc += lj_pair(p, r2); ++cnt; }
+                const double ax = sc.dshift[slot][0], ay = sc.dshift[slot][1], az = sc.dshift[slot][2];
+                r2 = image_r2(q.x, q.y, q.z, ax, ay, az, px, py, pz, dx, dy, dz);
+                if (within(r2)) hit(q, ax, ay, az, r2);
             }
         } else {                                 // rare: atom or site outside the primary cell
             const int4 S = sc.rawS[slot];
@@ -157,7 +163,7 @@ __device__ __forceinline__ void lj_site_rowsum(const GridDesc& g, const double4*
             shift_vec(g, T0, T1, T2, ax, ay, az);
             r2 = image_r2(q.x, q.y, q.z, ax, ay, az, px, py, pz, dx, dy, dz);
             const bool same = (T0 | T1 | T2) == 0;
-            if (r2 <= p.rc2 && !(same && j == self) && !excl(j)) { acc += lj_pair(p, r2); ++cnt; }
+            if (within(r2) && !(same && j == self)) hit(q, ax, ay, az, r2);
         }
     };
     auto drain = [&]() {
@@ -200,16 +206,16 @@ __device__ __forceinline__ void lj_site_rowsum(const GridDesc& g, const double4*
     const int m0 = g.m[0], m1 = g.m[1], m2 = g.m[2];
     const int wr1 = 2 * m1 + 1, wr2 = 2 * m2 + 1;
     // this work item owns the z-planes plane, plane + nplanes, ... of the stencil (normally one)
-    const int nz = (wr2 - plane + nplanes - 1) / nplanes;
-    const int nrows = (plane < wr2) ? wr1 * nz : 0;
     const bool perx = g.pbc[0] != 0;
     const bool simple_x = !perx || n0 >= 2 * m0 + 1;
+    const int nrows = wr1;                       // rows of one z-plane
+    for (int zp = plane; zp < wr2; zp += nplanes) {
     for (int base = 0; base < nrows; base += SITE_ROWS) {
         const int row = base + lane;
         int begA = 0, endA = 0, begB = 0, endB = 0, SxB = 0, Sy = 0, Sz = 0, rowoff = 0;
         bool valid = lane < SITE_ROWS && row < nrows;
         if (valid) {
-            int cy = c1 + (row % wr1) - m1, cz = c2 + (plane + (row / wr1) * nplanes) - m2;
+            int cy = c1 + row - m1, cz = c2 + zp - m2;
             if (g.pbc[1]) { Sy = floor_div(cy, n1); cy -= Sy * n1; }
             else if (cy < 0 || cy >= n1) valid = false;
             if (g.pbc[2]) { Sz = floor_div(cz, n2); cz -= Sz * n2; }
@@ -296,6 +302,8 @@ __device__ __forceinline__ void lj_site_rowsum(const GridDesc& g, const double4*
             }
         }
     }
+    plane_done();
+    }
 }
 
 __device__ __forceinline__ int upper_cell_of_item(const int* __restrict__ item_start, int ncells, int item) {
@@ -336,15 +344,18 @@ lj_cell_energy_kernel(BatchView b, LJParams p, int nplanes, double* __restrict__
         if (active) me = spos[k];
         const long long tag = tag_of(me);
         const int c0 = c % n0, c1 = (c / n0) % n1, c2 = c / (n0 * n1);
-        double acc = 0.0;
+        double acc = 0.0, tot = 0.0;
         int cnt = 0;
         // idle lanes carry the common wrap value so they never take the slow image path
-        lj_site_rowsum(g, spos, b.fpos + off, cstart, p, c0, c1, c2, lane, active, me.x, me.y, me.z,
-                       active ? tag_wraps(tag) : pack_wraps(0, 0, 0), active ? tag_index(tag) : -1,
-                       plane, nplanes, s_scratch[threadIdx.x >> 5], [](int) { return false; }, acc, cnt);
+        site_rowsum(g, spos, b.fpos + off, cstart, c0, c1, c2, lane, active, me.x, me.y, me.z,
+                    active ? tag_wraps(tag) : pack_wraps(0, 0, 0), active ? tag_index(tag) : -1,
+                    plane, nplanes, s_scratch[threadIdx.x >> 5],
+                    [&](double r2) { return r2 <= p.rc2; },
+                    [&](const double4&, double, double, double, double r2) { acc += lj_pair(p, r2); ++cnt; },
+                    [&]() { tot += acc; acc = 0.0; });
         if (active) {
             const size_t o = (size_t)(off + tag_index(tag)) * nplanes + plane;
-            e_part[o] = acc;
+            e_part[o] = tot;
             cnt_part[o] = cnt;
         }
     }
@@ -494,17 +505,22 @@ lj_trial_rows_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) {
         const int n0 = g.ncell[0], n1 = g.ncell[1];
         const int c0 = c % n0, c1 = (c / n0) % n1, c2 = c / (n0 * n1);
         const int wsite = active ? (int)__double_as_longlong(me.w) : pack_wraps(0, 0, 0);
-        double acc = 0.0;
+        double acc = 0.0, tot = 0.0;
         int cnt = 0;
         const bool multi = (oe - ob) > 1;
-        lj_site_rowsum(g, b.spos + off, b.fpos + off, cstart, p, c0, c1, c2, lane, active, me.x, me.y, me.z,
-                       wsite, -1, plane, w.nplanes, s_scratch[threadIdx.x >> 5],
-                       [&](int j) {
-                           if (j == ex0) return true;
-                           if (multi) for (int e = ob + 1; e < oe; ++e) if (tb.old_idx[e] == j) return true;
-                           return false;
-                       }, acc, cnt);
-        if (active) { w.site_E[(size_t)s * w.nplanes + plane] = acc; w.site_cnt[(size_t)s * w.nplanes + plane] = cnt; }
+        auto excl = [&](int j) {
+            if (j == ex0) return true;
+            if (multi) for (int e = ob + 1; e < oe; ++e) if (tb.old_idx[e] == j) return true;
+            return false;
+        };
+        site_rowsum(g, b.spos + off, b.fpos + off, cstart, c0, c1, c2, lane, active, me.x, me.y, me.z,
+                    wsite, -1, plane, w.nplanes, s_scratch[threadIdx.x >> 5],
+                    [&](double r2) { return r2 <= p.rc2; },
+                    [&](const double4& q, double, double, double, double r2) {
+                        if (!excl(tag_index(tag_of(q)))) { acc += lj_pair(p, r2); ++cnt; }
+                    },
+                    [&]() { tot += acc; acc = 0.0; });
+        if (active) { w.site_E[(size_t)s * w.nplanes + plane] = tot; w.site_cnt[(size_t)s * w.nplanes + plane] = cnt; }
     }
 }
 
