@@ -62,32 +62,51 @@ __device__ __forceinline__ int block_inclusive_scan(int v, int* s_w) {
 }
 
 // raw_pos: [sum N][3] doubles, raw_Z: [sum N] int32, atom_off: [R+1] ints, geom: [R]
+//
+// CS = 1 : one CTA per replica (many small replicas: R CTAs run side by side).
+// CS = 8 : one thread-block CLUSTER of 8 CTAs per replica for large configurations.  The per-atom
+//          phases are strided over all 8 x 1024 threads; phases meet at cluster barriers
+//          (barrier.cluster, release/acquire at cluster scope -- the arrays exchanged between CTAs
+//          live in global memory), the two short scans run on CTA 0.  bbox[r][8][6] is scratch.
+template <int CS>
 __global__ void __launch_bounds__(CL_THREADS, 1)
 build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
                        const int* __restrict__ raw_Z, const int* __restrict__ atom_off,
                        const CellGeom* __restrict__ geom, const int* __restrict__ z_to_slot,
-                       double rcut, int subdiv) {
+                       double rcut, int subdiv, double* __restrict__ bbox) {
     __shared__ double s_red[32];
     __shared__ int s_scan[CL_THREADS];
     __shared__ int s_carry;
     __shared__ int s_err;
-    const int r = blockIdx.x;
+    const int r = blockIdx.x / CS;
+    const int rank = blockIdx.x % CS;                 // == cluster block rank (1-D clusters)
     const int tid = threadIdx.x;
+    const int gtid = rank * CL_THREADS + tid;
+    const int gstride = CS * CL_THREADS;
+    auto sync_all = [&]() {
+        if (CS == 1) { __syncthreads(); }
+        else {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        }
+    };
     GridDesc& g = b.grid[r];
     const int off = atom_off[r];
     const int n = atom_off[r + 1] - off;
     const CellGeom& cg = geom[r];
     if (tid == 0) s_err = 0;
 
-    // ---- lattice into the device descriptor
-    if (tid < 9) { g.cell[tid] = cg.cell[tid]; g.inv[tid] = cg.inv[tid]; }
-    if (tid < 3) { g.height[tid] = cg.height[tid]; g.pbc[tid] = cg.pbc[tid]; }
-    if (tid == 0) { g.ortho = cg.ortho; g.n = n; g.atom_off = off; }
-    __syncthreads();
+    // ---- lattice into the device descriptor (every CTA keeps what it needs in registers too)
+    if (rank == 0) {
+        if (tid < 9) { g.cell[tid] = cg.cell[tid]; g.inv[tid] = cg.inv[tid]; }
+        if (tid < 3) { g.height[tid] = cg.height[tid]; g.pbc[tid] = cg.pbc[tid]; }
+        if (tid == 0) { g.ortho = cg.ortho; g.n = n; g.atom_off = off; g.error = 0; }
+    }
+    sync_all();
 
     // ---- pack + bounding box in fractional coordinates (non-periodic axes)
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (int i = tid; i < n; i += blockDim.x) {
+    for (int i = gtid; i < n; i += gstride) {
         const double x = raw_pos[3 * (size_t)(off + i) + 0];
         const double y = raw_pos[3 * (size_t)(off + i) + 1];
         const double z = raw_pos[3 * (size_t)(off + i) + 2];
@@ -109,11 +128,22 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
         glo[d] = block_reduce_minmax(lo[d], true, s_red);
         ghi[d] = block_reduce_minmax(hi[d], false, s_red);
     }
+    if (CS > 1) {
+        if (tid == 0) {
+            double* bb = bbox + ((size_t)r * CS + rank) * 6;
+            for (int d = 0; d < 3; ++d) { bb[d] = glo[d]; bb[3 + d] = ghi[d]; }
+        }
+        sync_all();
+        for (int k = 0; k < CS; ++k) {
+            const double* bb = bbox + ((size_t)r * CS + k) * 6;
+            for (int d = 0; d < 3; ++d) { glo[d] = fmin(glo[d], bb[d]); ghi[d] = fmax(ghi[d], bb[3 + d]); }
+        }
+    }
 
-    // ---- binning grid (thread 0), capped at max_cells.  Cell edge >= rcut' / subdiv, so the
+    // ---- binning grid (one thread), capped at max_cells.  Cell edge >= rcut' / subdiv, so the
     // stencil half width is m = ceil(rcut' / edge) <= subdiv cells (more only for boxes thinner
     // than the cutoff, where the extra offsets are periodic images of the single cell).
-    if (tid == 0) {
+    if (rank == 0 && tid == 0) {
         const double rc_safe = rcut * (1.0 + 1e-12);
         double want[3], width[3], width_frac[3];
         for (int d = 0; d < 3; ++d) {
@@ -168,15 +198,16 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
         const double rs = rc_safe + margin;
         g.screen_r2 = (float)(rs * rs * (1.0 + 1e-6));
     }
-    __syncthreads();
+    sync_all();
 
     const int ncells = g.ncells;
     int* cstart = b.cell_start + (size_t)r * b.cs_stride;
-    for (int c = tid; c <= ncells; c += blockDim.x) cstart[c] = 0;
-    __syncthreads();
+    int* cursor = cstart + (b.max_cells + 1);        // second half: scatter cursors, later item_start
+    for (int c = gtid; c <= ncells; c += gstride) { cstart[c] = 0; if (c < ncells) cursor[c] = 0; }
+    sync_all();
 
     // ---- hash: cell id + wrap counts, histogram in cstart[c + 1]
-    for (int i = tid; i < n; i += blockDim.x) {
+    for (int i = gtid; i < n; i += gstride) {
         double4 q = b.upos[off + i];
         int c[3], w[3];
         if (!locate(g, q.x, q.y, q.z, c, w)) atomicOr(&s_err, 4);
@@ -187,68 +218,69 @@ build_cell_list_kernel(BatchView b, const double* __restrict__ raw_pos,
         b.cid[off + i] = id;
         atomicAdd(&cstart[id + 1], 1);
     }
-    __syncthreads();
+    sync_all();
 
-    // ---- exclusive scan of cstart[1..ncells] (chunked block scan)
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < ncells; base += blockDim.x) {
-        const int c = base + tid;
-        const int v = (c < ncells) ? cstart[c + 1] : 0;
-        const int scanned = block_inclusive_scan(v, s_scan);
-        const int incl = scanned + s_carry;
+    // ---- exclusive scan of cstart[1..ncells] (chunked block scan on CTA 0)
+    if (rank == 0) {
+        if (tid == 0) s_carry = 0;
         __syncthreads();
-        if (c < ncells) cstart[c + 1] = incl;          // inclusive -> start of next cell
-        if (tid == blockDim.x - 1) s_carry = incl;
-        __syncthreads();
+        for (int base = 0; base < ncells; base += blockDim.x) {
+            const int c = base + tid;
+            const int v = (c < ncells) ? cstart[c + 1] : 0;
+            const int scanned = block_inclusive_scan(v, s_scan);
+            const int incl = scanned + s_carry;
+            __syncthreads();
+            if (c < ncells) cstart[c + 1] = incl;          // inclusive -> start of next cell
+            if (tid == blockDim.x - 1) s_carry = incl;
+            __syncthreads();
+        }
     }
+    sync_all();
     // cstart[c] is now the first slot of cell c (cstart[0] = 0, cstart[ncells] = n)
 
-    // ---- scatter (unordered) into the staging array; the per-cell cursors live in the
-    // second half of this replica's cell_start region
-    int* cursor = cstart + (b.max_cells + 1);
-    for (int c = tid; c < ncells; c += blockDim.x) cursor[c] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) {
+    // ---- scatter (unordered) into the staging array
+    for (int i = gtid; i < n; i += gstride) {
         const int id = b.cid[off + i];
         const int slot = cstart[id] + atomicAdd(&cursor[id], 1);
         b.stmp[off + slot] = b.upos[off + i];
     }
-    __syncthreads();
+    sync_all();
 
     // ---- order each segment by atom index: rank = #atoms of the segment with a smaller
     // index (segments hold a few dozen atoms, reads are broadcast-friendly, no serial chain)
-    for (int k = tid; k < n; k += blockDim.x) {
+    for (int k = gtid; k < n; k += gstride) {
         const double4 me = b.stmp[off + k];
         const int mi = tag_index(tag_of(me));
         const int id = b.cid[off + mi];
         const int s = cstart[id], e = cstart[id + 1];
-        int rank = 0;
-        for (int a = s; a < e; ++a) rank += (tag_index(tag_of(b.stmp[off + a])) < mi) ? 1 : 0;
-        b.spos[off + s + rank] = me;
+        int rk = 0;
+        for (int a = s; a < e; ++a) rk += (tag_index(tag_of(b.stmp[off + a])) < mi) ? 1 : 0;
+        b.spos[off + s + rk] = me;
         int w0, w1, w2;
         unpack_wraps(tag_wraps(tag_of(me)), w0, w1, w2);
         const float3 f = screen_pos(g, me.x, me.y, me.z, w0, w1, w2);
-        b.fpos[off + s + rank] = make_float4(f.x, f.y, f.z, __int_as_float(mi));
+        b.fpos[off + s + rk] = make_float4(f.x, f.y, f.z, __int_as_float(mi));
     }
-    __syncthreads();
+    sync_all();      // every CTA is done with the cursors before they become item_start
 
     // ---- work items of the lane-per-atom kernels: cell c contributes ceil(count/32) chunks of up
     // to 32 atoms; item_start (exclusive prefix, ncells+1 entries) reuses the cursor region.
-    int* item_start = cursor;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < ncells; base += blockDim.x) {
-        const int c = base + tid;
-        const int v = (c < ncells) ? (cstart[c + 1] - cstart[c] + 31) / 32 : 0;
-        const int scanned = block_inclusive_scan(v, s_scan);
-        const int incl = scanned + s_carry;
+    if (rank == 0) {
+        int* item_start = cursor;
+        if (tid == 0) s_carry = 0;
         __syncthreads();
-        if (c < ncells) item_start[c] = incl - v;
-        if (tid == blockDim.x - 1) s_carry = incl;
-        __syncthreads();
+        for (int base = 0; base < ncells; base += blockDim.x) {
+            const int c = base + tid;
+            const int v = (c < ncells) ? (cstart[c + 1] - cstart[c] + 31) / 32 : 0;
+            const int scanned = block_inclusive_scan(v, s_scan);
+            const int incl = scanned + s_carry;
+            __syncthreads();
+            if (c < ncells) item_start[c] = incl - v;
+            if (tid == blockDim.x - 1) s_carry = incl;
+            __syncthreads();
+        }
+        if (tid == 0) { item_start[ncells] = s_carry; g.nitems = s_carry; }
     }
-    if (tid == 0) { item_start[ncells] = s_carry; g.nitems = s_carry; }
     __syncthreads();
-    if (tid == 0) g.error = s_err;
+    if (tid == 0 && s_err) atomicOr(&g.error, s_err);
 }

@@ -120,6 +120,7 @@ struct mcpyb_engine {
     DevBuf<int> cid, cell_start;
     const int* d_atom_off = nullptr;      // points into stage_dev (header of the last upload)
     DevBuf<CellGeom> geom;
+    DevBuf<double> bbox;                  // cluster build scratch
     DevBuf<double> e_atom, sigma1, e_part;
     DevBuf<int> cnt_part;
     DevBuf<double> E;                     // one block: E[R] | pairs[R] (int64) | status[R] (int32)
@@ -282,9 +283,24 @@ int upload_common(mcpyb_engine* e, int R, const int64_t* atom_off, const double*
     const int* d_off = (const int*)d_header;
     const CellGeom* d_geom = (const CellGeom*)(d_header + off_bytes);
     (void)atom_off; (void)cells; (void)pbc;
-    build_cell_list_kernel<<<R, CL_THREADS, 0, e->stream>>>(
-        e->view(), d_pos, d_Z, d_off, d_geom, e->z_to_slot.p, e->rcut, e->subdiv);
-    LAUNCH_CHECK("build_cell_list_kernel");
+    if (e->max_n >= 4096) {
+        // large configurations: one 8-CTA thread-block cluster per replica
+        CK(e->bbox.reserve((size_t)R * 8 * 6), "cudaMalloc bbox");
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(R * 8); cfg.blockDim = dim3(CL_THREADS); cfg.stream = e->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, build_cell_list_kernel<8>, e->view(), d_pos, (const int*)d_Z, d_off, d_geom,
+                              (const int*)e->z_to_slot.p, e->rcut, e->subdiv, e->bbox.p), "launch build (cluster)");
+        e->launches++;
+    } else {
+        build_cell_list_kernel<1><<<R, CL_THREADS, 0, e->stream>>>(
+            e->view(), d_pos, d_Z, d_off, d_geom, e->z_to_slot.p, e->rcut, e->subdiv, nullptr);
+        LAUNCH_CHECK("build_cell_list_kernel");
+    }
     e->d_atom_off = d_off;          // stays valid in stage_dev until the next upload
     e->have_batch = true;
     e->emt_state_valid = false;
@@ -406,7 +422,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release(); e->stmp.release(); e->fpos.release();
-    e->cid.release(); e->cell_start.release(); e->geom.release();
+    e->cid.release(); e->cell_start.release(); e->geom.release(); e->bbox.release();
     e->e_atom.release(); e->sigma1.release(); e->e_part.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();

@@ -134,16 +134,18 @@ int oracle_lj_energy(const double* pos, int n, const double* cell, const uint8_t
     cut_t c = {1, rc, rc * rc};
     int* w = wrap_counts(pos, n, &g);
     const double e0 = 4 * eps * (pow(sigma / rc, 12) - pow(sigma / rc, 6));
-    double* en = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    /* per-atom sums as in ASE; long double accumulators keep the O(N^2) loop's rounding out of
+     * the comparison (the quantity defined is the exact sum of the fp64 pair terms) */
+    long double* en = (long double*)calloc((size_t)(n > 0 ? n : 1), sizeof(long double));
     int64_t k = 0;
     PAIR_LOOP_BEGIN
         const double t = sigma * sigma / r2, c6 = t * t * t, c12 = c6 * c6;
         en[i] += 0.5 * (4 * eps * (c12 - c6) - e0);
         ++k;
     PAIR_LOOP_END
-    double E = 0;
+    long double E = 0;
     for (int i = 0; i < n; ++i) E += en[i];
-    *energy = E;
+    *energy = (double)E;
     if (npairs) *npairs = k / 2;
     free(en); free(w);
     return 0;
@@ -158,7 +160,7 @@ int oracle_emt_energy(const double* pos, const int32_t* slot, int n, const doubl
     cut_t c = {2, rc_list, rc_list * rc_list};
     int* w = wrap_counts(pos, n, &g);
     double* sig = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
-    double E = 0;
+    long double E = 0;          /* long double: see oracle_lj_energy */
     int64_t k = 0;
     PAIR_LOOP_BEGIN
         const double* pa = table + 9 * slot[i];
@@ -175,7 +177,7 @@ int oracle_emt_energy(const double* pos, const int32_t* slot, int n, const doubl
         const double ds = -log(sig[i] / 12) / (beta * p[3]), x = p[5] * ds;
         E += p[0] * ((1 + x) * exp(-x) - 1) + 6 * p[2] * exp(-p[4] * ds);
     }
-    *energy = E;
+    *energy = (double)E;
     if (sigma1_out) memcpy(sigma1_out, sig, (size_t)n * sizeof(double));
     if (npairs) *npairs = k / 2;
     free(sig); free(w);

@@ -139,3 +139,29 @@ def test_thin_box_reports_nan(emt_engine):
     emt_engine.upload([pos], [np.full(32, 29, np.int32)], (np.eye(3) * 2 * a).reshape(1, 9), np.ones((1, 3), bool))
     dE = emt_engine.trial_delta_e([0, 1], [3], [0, 1], [pos[3] + 0.1], [29])
     assert np.isnan(dE[0])
+
+
+def test_s5_ten_thousand_atoms_cluster_build(emt_engine):
+    """~10.8k-atom CuPd + CO (BASELINE config 4): the cell list is built by an 8-CTA cluster."""
+    from oracle import cfast
+    cfg = synthetic.s5_cupd_co()
+    emt_engine.upload([cfg['positions']], [cfg['numbers']], cfg['cell'].reshape(1, 9), cfg['pbc'].reshape(1, 3))
+    E, pairs = emt_engine.energies(return_pairs=True)
+    ref, sigma_ref, npairs = cfast.emt_energy(cfg['positions'], cfg['numbers'], cfg['cell'], cfg['pbc'],
+                                              return_details=True)
+    assert int(pairs[0]) == npairs
+    assert abs(E[0] - ref) <= RTOL * max(1.0, abs(ref))
+    _, sigma1 = emt_engine.atom_energies(want_sigma1=True)
+    np.testing.assert_allclose(sigma1, sigma_ref, rtol=1e-11, atol=1e-300)
+    # a few CO moves against it (rigid translation, deletion, insertion)
+    n = len(cfg['positions'])
+    co = cfg['positions'][n - 2:]
+    tb = dict(old_off=np.array([0, 2, 4, 4], np.int32), old_idx=np.array([n - 2, n - 1, n - 4, n - 3], np.int32),
+              new_off=np.array([0, 2, 2, 4], np.int32),
+              new_pos=np.concatenate([co + [0.2, -0.1, 0.15], co + [3.0, 2.0, 1.0]]),
+              new_Z=np.array([6, 8, 6, 8], np.int32))
+    dE = emt_engine.trial_delta_e(tb['old_off'], tb['old_idx'], tb['new_off'], tb['new_pos'], tb['new_Z'])
+    for t in range(3):
+        p1, n1 = synthetic.apply_trial(cfg, tb, t)
+        r = cfast.emt_energy(p1, n1, cfg['cell'], cfg['pbc']) - ref
+        assert abs(dE[t] - r) <= RTOL * max(1.0, abs(ref)), (t, dE[t], r)

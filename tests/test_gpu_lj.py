@@ -244,3 +244,26 @@ def test_errors(lj_engine):
         lj_engine.trial_delta_e([0, 1], [5], [0, 0], np.zeros((0, 3)), [])
     with pytest.raises(ValueError):
         lj_engine.trial_delta_e([0, 0], [], [0, 1], np.zeros((1, 3)), [1], rep=[3])
+
+
+def test_large_periodic_box_cluster_build(lj_engine):
+    """N >= 4096 switches the cell-list build to an 8-CTA thread-block cluster."""
+    cfg = synthetic.s2_lj(n=6000, rc=2.5, rho=0.7, seed=9)
+    lj_engine.set_lj(1.0, 1.0, 2.5)
+    lj_engine.upload([cfg['positions']], [cfg['numbers']], cfg['cell'].reshape(1, 9), cfg['pbc'].reshape(1, 3))
+    E, pairs = lj_engine.energies(return_pairs=True)
+    ref, ref_pairs = cfast.lj_energy(cfg['positions'], cfg['cell'], cfg['pbc'], 1.0, 1.0, 2.5, return_pairs=True)
+    assert int(pairs[0]) == ref_pairs
+    assert _rel(E[0], ref) <= RTOL
+    gi, gj, gS, gr2 = lj_engine.neighbor_pairs(0, 2.5, mode=1)
+    oi, oj, oS, or2 = cfast.neighbor_pairs(cfg['positions'], cfg['cell'], cfg['pbc'], 2.5, mode=1)
+    assert np.array_equal(gi, oi) and np.array_equal(gj, oj) and np.array_equal(gS, oS) and np.array_equal(gr2, or2)
+    # two big replicas and a small one in one batch
+    small = synthetic.s2_lj(n=300, rc=2.5, rho=0.5, seed=3)
+    Eb = lj_engine.potential_energies([cfg['positions'], small['positions'], cfg['positions'][:5000]],
+                                      [cfg['numbers'], small['numbers'], cfg['numbers'][:5000]],
+                                      np.stack([cfg['cell'].reshape(9), small['cell'].reshape(9), cfg['cell'].reshape(9)]),
+                                      np.ones((3, 3), bool))
+    assert Eb[0] == E[0]
+    assert _rel(Eb[1], cfast.lj_energy(small['positions'], small['cell'], small['pbc'], 1.0, 1.0, 2.5)) <= RTOL
+    assert _rel(Eb[2], cfast.lj_energy(cfg['positions'][:5000], cfg['cell'], cfg['pbc'], 1.0, 1.0, 2.5)) <= RTOL
