@@ -434,6 +434,26 @@ def secondary_workloads(device):
             'free_volume_points_per_s_cpu_ckdtree_1core': P / t_cpu,
         }
     eng.close()
+    # S4: 64 replicas x 2000-atom LJ through the batched plug-in call (one launch set for all)
+    from mcpy_b200.calculators import B200Calculator
+    calc = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=RC, device=device)
+
+    class _A:
+        pass
+    reps = []
+    for k in range(64):
+        c = synthetic.s2_lj(N_ATOMS, RC, RHO, seed=100 + k)
+        a = _A()
+        a.positions, a.numbers, a.cell, a.pbc = c['positions'], c['numbers'], c['cell'], c['pbc']
+        reps.append(a)
+    t_b = _time(lambda: calc.get_potential_energies(reps), 5)
+    t_1 = _time(lambda: [calc.get_potential_energy(a) for a in reps[:8]], 3) / 8
+    out['S4_64_replicas_x_2000_LJ'] = {
+        'batched_call_ms': 1e3 * t_b,
+        'replica_energies_per_s_batched': 64 / t_b,
+        'replica_energies_per_s_one_by_one': 1.0 / t_1,
+    }
+    calc.engine.close()
     return out
 
 

@@ -98,7 +98,9 @@ struct mcpyb_engine {
 
     // potential
     int pot_kind = POT_NONE;
-    int subdiv = 1;                       // cells per cutoff length (stencil half width)
+    int subdiv = 1;                       // cells per cutoff length of the RESIDENT cell list
+    int subdiv_trials = 1;                // ... wanted when trial moves will be scored against it
+    int subdiv_energy = 1;                // ... wanted for upload + total energies in one call
     double rcut = 0.0;
     LJParams lj{};
     EmtTable emt_host{};
@@ -461,7 +463,10 @@ int mcpyb_set_lj(mcpyb_engine* e, double epsilon, double sigma, double rc) {
     if (!(rc > 0.0)) rc = 3.0 * sigma;
     cudaSetDevice(e->device);
     e->pot_kind = POT_LJ;
-    e->subdiv = 2;
+    // Trial batches put many sites in every cell, so fine cells (edge rc/2) pay: 343 instead of 844
+    // candidates per site.  Total energies have one site per atom: coarse cells (edge rc) fill the
+    // 32 lanes of a work item (31 atoms per cell at rho* = 0.6) where fine cells leave 29 idle.
+    e->subdiv_trials = 2; e->subdiv_energy = 1; e->subdiv = 2;
     e->rcut = rc;
     e->lj.eps4 = 4.0 * epsilon;
     e->lj.sigma2 = sigma * sigma;
@@ -508,7 +513,7 @@ int mcpyb_set_emt(mcpyb_engine* e) {
     for (int a = 0; a < ns; ++a)
         for (int b = 0; b < ns; ++b) t.ksi[a][b] = t.sp[b].n0 / t.sp[a].n0;
     e->pot_kind = POT_EMT;
-    e->subdiv = 1;
+    e->subdiv_trials = 1; e->subdiv_energy = 1; e->subdiv = 1;
     e->rcut = t.rc_list;
     CK(e->emt_dev.reserve(1), "cudaMalloc emt table");
     CK(e->z_to_slot.reserve(120), "cudaMalloc z_to_slot");
@@ -527,9 +532,10 @@ int mcpyb_emt_species(const mcpyb_engine* e, int Z, double* out9) {
     return MCPYB_OK;
 }
 
-int mcpyb_upload_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
-                      const int32_t* numbers, const double* cells, const uint8_t* pbc) {
+static int upload_host_impl(mcpyb_engine* e, int subdiv, int R, const int64_t* atom_off, const double* positions,
+                            const int32_t* numbers, const double* cells, const uint8_t* pbc) {
     if (!e) return MCPYB_ERR_ARG;
+    e->subdiv = subdiv;
     cudaSetDevice(e->device);
     int total = 0, max_n = 0;
     int rc = validate_batch_args(e, R, atom_off, &total, &max_n);
@@ -561,10 +567,17 @@ int mcpyb_upload_host(mcpyb_engine* e, int R, const int64_t* atom_off, const dou
                          numbers ? (const int32_t*)(e->stage_dev.p + hb + pb) : nullptr, e->stage_dev.p);
 }
 
+int mcpyb_upload_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
+                      const int32_t* numbers, const double* cells, const uint8_t* pbc) {
+    if (!e) return MCPYB_ERR_ARG;
+    return upload_host_impl(e, e->subdiv_trials, R, atom_off, positions, numbers, cells, pbc);
+}
+
 int mcpyb_upload_dev(mcpyb_engine* e, int R, const int64_t* atom_off, const double* d_positions,
                      const int32_t* d_numbers, const double* cells, const uint8_t* pbc) {
     if (!e) return MCPYB_ERR_ARG;
     cudaSetDevice(e->device);
+    e->subdiv = e->subdiv_trials;
     int total = 0, max_n = 0;
     int rc = validate_batch_args(e, R, atom_off, &total, &max_n);
     if (rc != MCPYB_OK) return rc;
@@ -623,7 +636,12 @@ int mcpyb_energies_host(mcpyb_engine* e, double* energies_out, int64_t* pairs_ou
 int mcpyb_potential_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
                                   const int32_t* numbers, const double* cells, const uint8_t* pbc,
                                   double* energies_out) {
-    int rc = mcpyb_upload_host(e, R, atom_off, positions, numbers, cells, pbc);
+    if (!e) return MCPYB_ERR_ARG;
+    // few atoms: latency matters, fine cells give more (shorter) work items; many atoms (replica
+    // batches): throughput matters, coarse cells keep the lanes full
+    const int64_t tot = (R > 0 && atom_off) ? atom_off[R] : 0;
+    int rc = upload_host_impl(e, tot >= 8192 ? e->subdiv_energy : e->subdiv_trials, R, atom_off, positions,
+                              numbers, cells, pbc);
     if (rc != MCPYB_OK) return rc;
     return mcpyb_energies_host(e, energies_out, nullptr);
 }
