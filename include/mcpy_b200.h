@@ -89,6 +89,17 @@ int mcpyb_potential_energies_host(mcpyb_engine* e, int R, const int64_t* atom_of
                                   const double* positions, const int32_t* numbers,
                                   const double* cells, const uint8_t* pbc,
                                   double* energies_out);
+/* Incremental form of the single-configuration call, for the one-call-per-trial pattern of
+ * GrandCanonicalEnsemble.do_gcmc_step (grand_canonical_ensemble.py:244-308).  The engine keeps a
+ * fully evaluated base configuration resident, aligns the incoming one with it on the host and
+ * returns E_base + dE(base -> incoming); it re-bases (full evaluation) when more than a few atoms
+ * differ or the box changes.  Same result as mcpyb_potential_energies_host to rounding (one full
+ * evaluation plus one delta, no drift).  *path_out (may be NULL): 0 full, 1 incremental,
+ * 2 identical to the base.  Any mcpyb_upload_* call resets the tracker.                        */
+int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const int32_t* numbers,
+                              int n, const double* cell9, const uint8_t* pbc3,
+                              double* energy_out, int* path_out);
+
 /* Per-atom energies of the resident batch (ASE's results['energies']) and, for
  * EMT, the density sums sigma1; either pointer may be NULL. Host arrays [sum N]. */
 int mcpyb_atom_energies_host(mcpyb_engine* e, double* e_atom_out, double* sigma1_out);

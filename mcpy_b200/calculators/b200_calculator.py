@@ -54,7 +54,7 @@ class _B200Core:
 
     implemented_properties = ['energy', 'free_energy']
 
-    def _init_engine(self, potential, epsilon, sigma, rc, device, chunk_size):
+    def _init_engine(self, potential, epsilon, sigma, rc, device, chunk_size, incremental=True):
         potential = str(potential).lower()
         if potential not in ('lj', 'lennardjones', 'emt'):
             raise ValueError(f"potential must be 'lj' or 'emt', got {potential!r}")
@@ -70,6 +70,8 @@ class _B200Core:
         else:
             self.engine.set_emt()
         self.n_energy_calls = 0
+        self.incremental = bool(incremental)
+        self.path_counts = [0, 0, 0]          # full evaluations, incremental, identical-to-base
 
     # -- mcpy calculator interface -------------------------------------------
     def get_potential_energy(self, atoms=None, force_consistent=False) -> float:
@@ -79,8 +81,13 @@ class _B200Core:
             if atoms is None:
                 raise ValueError('get_potential_energy() needs an Atoms object')
         self.n_energy_calls += 1
-        return self.engine.potential_energy(atoms.positions, atoms.numbers,
-                                            np.asarray(atoms.cell, dtype=np.float64), atoms.pbc)
+        cell = np.asarray(atoms.cell, dtype=np.float64)
+        if self.incremental:
+            # one resident base + a delta per call; same numbers as the full path to rounding
+            e, path = self.engine.tracked_energy(atoms.positions, atoms.numbers, cell, atoms.pbc)
+            self.path_counts[path] += 1
+            return e
+        return self.engine.potential_energy(atoms.positions, atoms.numbers, cell, atoms.pbc)
 
     def get_potential_energies(self, atoms_list, chunk_size=None) -> np.ndarray:
         """Energies of several (ragged) structures, one batched launch per chunk."""
@@ -138,9 +145,9 @@ if _AseCalculator is not None:
         nolabel = True
 
         def __init__(self, potential='lj', epsilon=1.0, sigma=1.0, rc=None, device=0,
-                     chunk_size=None, **kwargs):
+                     chunk_size=None, incremental=True, **kwargs):
             _AseCalculator.__init__(self, **kwargs)
-            self._init_engine(potential, epsilon, sigma, rc, device, chunk_size)
+            self._init_engine(potential, epsilon, sigma, rc, device, chunk_size, incremental)
 
         def calculate(self, atoms=None, properties=('energy',), system_changes=_all_changes):
             _AseCalculator.calculate(self, atoms, properties, system_changes)
@@ -160,10 +167,10 @@ else:
         __doc__ = __doc__
 
         def __init__(self, potential='lj', epsilon=1.0, sigma=1.0, rc=None, device=0,
-                     chunk_size=None, **kwargs):
+                     chunk_size=None, incremental=True, **kwargs):
             self.results = {}
             self.atoms = None
-            self._init_engine(potential, epsilon, sigma, rc, device, chunk_size)
+            self._init_engine(potential, epsilon, sigma, rc, device, chunk_size, incremental)
 
         def calculate(self, atoms=None, properties=('energy',), system_changes=_all_changes):
             self.atoms = atoms

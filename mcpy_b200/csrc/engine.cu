@@ -132,6 +132,15 @@ struct mcpyb_engine {
     DevBuf<unsigned char> stage_dev;      // H2D landing zone: header | positions | numbers
     PinBuf stage_pin, out_pin;
 
+    // incremental drop-in path (mcpyb_tracked_energy_host): host mirror of the resident base
+    bool trk_valid = false;
+    std::vector<double> trk_pos;
+    std::vector<int32_t> trk_Z;
+    double trk_cell[9];
+    uint8_t trk_pbc[3];
+    double trk_E = 0.0;
+    long long trk_full = 0, trk_incremental = 0;
+
     // trial staging
     DevBuf<unsigned char> trial_dev;
     PinBuf trial_pin, trial_out_pin;
@@ -536,6 +545,7 @@ static int upload_host_impl(mcpyb_engine* e, int subdiv, int R, const int64_t* a
                             const int32_t* numbers, const double* cells, const uint8_t* pbc) {
     if (!e) return MCPYB_ERR_ARG;
     e->subdiv = subdiv;
+    e->trk_valid = false;
     cudaSetDevice(e->device);
     int total = 0, max_n = 0;
     int rc = validate_batch_args(e, R, atom_off, &total, &max_n);
@@ -578,6 +588,7 @@ int mcpyb_upload_dev(mcpyb_engine* e, int R, const int64_t* atom_off, const doub
     if (!e) return MCPYB_ERR_ARG;
     cudaSetDevice(e->device);
     e->subdiv = e->subdiv_trials;
+    e->trk_valid = false;
     int total = 0, max_n = 0;
     int rc = validate_batch_args(e, R, atom_off, &total, &max_n);
     if (rc != MCPYB_OK) return rc;
@@ -798,6 +809,95 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
     CK(cudaStreamSynchronize(e->stream), "sync trials");
     memcpy(dE_out, e->trial_out_pin.p, ob);
     if (pairs_out) memcpy(pairs_out, e->trial_out_pin.p + ob, pb);
+    return MCPYB_OK;
+}
+
+// ---- incremental drop-in path ------------------------------------------------------
+// calculator.get_potential_energy(atoms) is called once per trial move on a configuration that
+// differs from the previous ones by a handful of atoms (grand_canonical_ensemble.py:244-308).
+// The engine keeps one fully evaluated BASE configuration resident.  Each call aligns the incoming
+// configuration with the base on the host (rows equal within 1e-10 A and same species match; ASE's
+// `del` removes rows, `+=` appends, displacements keep the row), and returns
+// E_base + dE(base -> incoming) from the trial kernels.  There is no accept / reject inference and
+// no drift: every answer is one full evaluation plus ONE delta.  When the difference grows beyond a
+// few atoms (accepted moves accumulate) the incoming configuration becomes the new base.
+int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const int32_t* numbers, int n,
+                              const double* cell9, const uint8_t* pbc3, double* energy_out, int* path_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (n < 0 || !cell9 || !pbc3 || !energy_out || (n > 0 && !positions)) return e->fail(MCPYB_ERR_ARG, "bad arguments");
+    if (e->pot_kind == POT_NONE) return e->fail(MCPYB_ERR_STATE, "no potential set");
+    if (e->pot_kind == POT_EMT && n > 0 && !numbers) return e->fail(MCPYB_ERR_ARG, "EMT needs atomic numbers");
+    const double tol = 1e-10;
+    const int kRebase = 8;                       // moved atoms (old + new) beyond which we re-base
+    auto zof = [&](int j) { return numbers ? numbers[j] : 0; };
+    bool same_box = e->trk_valid && memcmp(e->trk_cell, cell9, sizeof e->trk_cell) == 0 &&
+                    memcmp(e->trk_pbc, pbc3, 3) == 0 && e->have_batch && e->R == 1;
+    int32_t old_idx[2 * MCPYB_MAX_MOVED];
+    int new_row[2 * MCPYB_MAX_MOVED];
+    int n_old = 0, n_new = 0;
+    bool incremental = same_box;
+    if (incremental) {
+        const int nB = (int)e->trk_Z.size();
+        const double* B = e->trk_pos.data();
+        auto match = [&](int i, int j) {
+            return e->trk_Z[i] == zof(j) && fabs(B[3 * i] - positions[3 * j]) <= tol &&
+                   fabs(B[3 * i + 1] - positions[3 * j + 1]) <= tol && fabs(B[3 * i + 2] - positions[3 * j + 2]) <= tol;
+        };
+        int i = 0, j = 0;
+        while (incremental && i < nB && j < n) {
+            if (match(i, j)) { ++i; ++j; continue; }
+            if (n_old + n_new + 2 > kRebase) { incremental = false; break; }
+            if (i + 1 < nB && match(i + 1, j)) { old_idx[n_old++] = i++; continue; }          // row deleted
+            if (j + 1 < n && match(i, j + 1)) { new_row[n_new++] = j++; continue; }           // row inserted
+            old_idx[n_old++] = i++; new_row[n_new++] = j++;                                  // row displaced
+        }
+        while (incremental && i < nB) { if (n_old + n_new + 1 > kRebase) incremental = false; else old_idx[n_old++] = i++; }
+        while (incremental && j < n) { if (n_old + n_new + 1 > kRebase) incremental = false; else new_row[n_new++] = j++; }
+    }
+    if (incremental && n_old == 0 && n_new == 0) {
+        *energy_out = e->trk_E;
+        if (path_out) *path_out = 2;
+        return MCPYB_OK;
+    }
+    if (incremental) {
+        int32_t old_off[2] = {0, n_old}, new_off[2] = {0, n_new};
+        double new_pos[3 * 2 * MCPYB_MAX_MOVED];
+        int32_t new_Z[2 * MCPYB_MAX_MOVED];
+        for (int k = 0; k < n_new; ++k) {
+            for (int c = 0; c < 3; ++c) new_pos[3 * k + c] = positions[3 * new_row[k] + c];
+            new_Z[k] = zof(new_row[k]);
+        }
+        double dE = 0.0;
+        const bool keep = e->trk_valid;
+        int rc = mcpyb_trial_delta_e_host(e, 1, nullptr, old_off, old_idx, new_off, new_pos,
+                                          numbers ? new_Z : nullptr, &dE, nullptr);
+        e->trk_valid = keep;
+        if (rc != MCPYB_OK) return rc;
+        if (isfinite(dE) || e->pot_kind == POT_LJ) {      // EMT reports NaN when the box is too thin
+            *energy_out = e->trk_E + dE;
+            if (path_out) *path_out = 1;
+            e->trk_incremental++;
+            return MCPYB_OK;
+        }
+    }
+    // full evaluation; the incoming configuration becomes the base
+    const int64_t off[2] = {0, n};
+    int rc = upload_host_impl(e, e->subdiv_trials, 1, off, positions, numbers, cell9, pbc3);
+    if (rc != MCPYB_OK) return rc;
+    double E = 0.0;
+    rc = mcpyb_energies_host(e, &E, nullptr);
+    if (rc != MCPYB_OK) return rc;
+    e->trk_pos.assign(positions, positions + 3 * (size_t)n);
+    e->trk_Z.resize((size_t)n);
+    for (int j = 0; j < n; ++j) e->trk_Z[j] = zof(j);
+    memcpy(e->trk_cell, cell9, sizeof e->trk_cell);
+    memcpy(e->trk_pbc, pbc3, 3);
+    e->trk_E = E;
+    e->trk_valid = true;
+    e->trk_full++;
+    *energy_out = E;
+    if (path_out) *path_out = 0;
     return MCPYB_OK;
 }
 

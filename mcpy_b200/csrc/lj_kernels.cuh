@@ -176,10 +176,33 @@ __device__ __forceinline__ void intra_set_lj(const GridDesc& g, const LJParams& 
                                              int gl, int G, double& acc, int& cnt) {
     if (k == 0) return;
     int nim[3];
+    bool mic_only = true;          // every periodic height >= 2 rc: at most the minimum image is in range
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < 3; ++d) {
         nim[d] = g.pbc[d] ? (int)ceil(p.rc * (1.0 + 1e-12) / g.height[d]) : 0;
-    if (k == 1 && (nim[0] | nim[1] | nim[2]) == 0) return;
+        if (g.pbc[d] && !(g.height[d] >= 2.0 * p.rc * (1.0 + 1e-12))) mic_only = false;
+    }
+    if (mic_only) {
+        // pairs a < a2, minimum image only; an atom cannot see its own images
+        const int npair = k * (k - 1) / 2;
+        for (int pr = gl; pr < npair; pr += G) {
+            int a = 0, rem = pr;
+            while (rem >= k - 1 - a) { rem -= (k - 1 - a); ++a; }
+            const int a2 = a + 1 + rem;
+            double xa, ya, za, xb, yb, zb;
+            pos(a, xa, ya, za);
+            pos(a2, xb, yb, zb);
+            double f[3];
+            to_frac(g, xb - xa, yb - ya, zb - za, f);
+            const int s0 = g.pbc[0] ? -(int)rint(f[0]) : 0, s1 = g.pbc[1] ? -(int)rint(f[1]) : 0,
+                      s2 = g.pbc[2] ? -(int)rint(f[2]) : 0;
+            double sx, sy, sz, dx, dy, dz;
+            shift_vec(g, s0, s1, s2, sx, sy, sz);
+            const double r2 = image_r2(xb, yb, zb, sx, sy, sz, xa, ya, za, dx, dy, dz);
+            if (r2 <= p.rc2) { acc += lj_pair(p, r2); ++cnt; }
+        }
+        return;
+    }
     const int w0 = 2 * nim[0] + 1, w1 = 2 * nim[1] + 1, w2 = 2 * nim[2] + 1;
     const int nimg = w0 * w1 * w2;
     const int npair = k * (k + 1) / 2;

@@ -32,6 +32,7 @@ class Engine:
         self.potential = None
         self._off1 = np.zeros(2, dtype=np.int64)      # scratch of the single-configuration fast path
         self._e1 = np.zeros(1, dtype=np.float64)
+        self._path = C.c_int(0)
 
     # -- plumbing ------------------------------------------------------------
     def close(self):
@@ -165,6 +166,24 @@ class Engine:
         self._R = 1
         self._ntot = n
         return float(self._e1[0])
+
+    def tracked_energy(self, positions, numbers, cell, pbc):
+        """Single configuration through the incremental path (base + one delta); returns
+        ``(energy, path)`` with path 0 = full evaluation, 1 = incremental, 2 = identical to the base."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        num = np.ascontiguousarray(numbers, dtype=np.int32)
+        cell = np.ascontiguousarray(cell, dtype=np.float64)
+        pbc = np.ascontiguousarray(pbc, dtype=np.uint8)
+        n = pos.shape[0]
+        if pos.size != 3 * n or num.size != n or cell.size != 9 or pbc.size != 3:
+            raise ValueError('positions (n,3), numbers (n,), cell (3,3), pbc (3,) expected')
+        rc = self._lib.mcpyb_tracked_energy_host(self._h, pos.ctypes.data, num.ctypes.data, n,
+                                                 cell.ctypes.data, pbc.ctypes.data, self._e1.ctypes.data,
+                                                 C.byref(self._path))
+        if rc != 0:
+            self._check(rc)
+        self._R, self._ntot = 1, n
+        return float(self._e1[0]), int(self._path.value)
 
     def atom_energies(self, want_sigma1=False):
         e = np.empty(self._ntot)

@@ -1,0 +1,17 @@
+"""Profiling helper (not a test): the incremental drop-in chain."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from mcpy_b200 import Engine
+from mcpy_b200.utils import synthetic
+cfg = synthetic.s2_lj()
+eng = Engine(0); eng.set_lj(1.0, 1.0, 3.0)
+tb = synthetic.trial_batch(cfg, 64, seed=7)
+cfgs = [synthetic.apply_trial(cfg, tb, t) for t in range(64)]
+paths = [0, 0, 0]
+for rep in range(3):
+    t0 = time.perf_counter()
+    for p, z in cfgs:
+        e, path = eng.tracked_energy(p, z, cfg['cell'], cfg['pbc']); paths[path] += 1
+    dt = (time.perf_counter() - t0) / len(cfgs)
+print('us/call', dt * 1e6, paths)

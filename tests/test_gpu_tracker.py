@@ -1,0 +1,61 @@
+"""GPU: the incremental drop-in path (mcpyb_tracked_energy_host) against the full path on a chain
+of GCMC-like configurations: displacements, insertions, deletions, accepted moves that accumulate,
+ULP-level perturbation of every coordinate (atoms.wrap()), box changes."""
+import numpy as np
+import pytest
+
+from mcpy_b200 import Engine
+from mcpy_b200.utils import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('potential', ['lj', 'emt'])
+def test_tracked_chain_equals_full_evaluations(potential):
+    rng = np.random.default_rng(17)
+    if potential == 'lj':
+        cfg = synthetic.s1_argon()
+        setup = lambda e: e.set_lj(cfg['epsilon'], cfg['sigma'], cfg['rc'])
+        new_Z, step = 18, 0.8
+    else:
+        cfg = synthetic.s3_ag_o()
+        setup = lambda e: e.set_emt()
+        new_Z, step = 8, 0.3
+    trk, full = Engine(0), Engine(0)
+    setup(trk); setup(full)
+    cell, pbc = cfg['cell'], cfg['pbc']
+    pos, num = cfg['positions'].copy(), cfg['numbers'].copy()
+    paths = [0, 0, 0]
+    for it in range(160):
+        tp, tn = pos.copy(), num.copy()
+        kind = rng.integers(4)
+        if kind == 0:                                  # displacement
+            i = rng.integers(len(tp)); tp[i] += rng.uniform(-step, step, 3)
+        elif kind == 1:                                # insertion (appended, like atoms += Atoms(...))
+            p = tp[rng.integers(len(tp))] + rng.uniform(-3, 3, 3)
+            tp = np.concatenate([tp, [p]]); tn = np.concatenate([tn, [new_Z]]).astype(np.int32)
+        elif kind == 2 and len(tp) > 5:                # deletion (row removed, like del atoms[i])
+            i = rng.integers(len(tp)); tp = np.delete(tp, i, axis=0); tn = np.delete(tn, i)
+        else:                                          # two atoms at once (rigid pair move)
+            i = rng.choice(len(tp), 2, replace=False); tp[i] += rng.uniform(-step, step, 3)
+        e_t, path = trk.tracked_energy(tp, tn, cell, pbc)
+        paths[path] += 1
+        e_f = full.potential_energy(tp, tn, cell, pbc)
+        assert abs(e_t - e_f) <= 1e-10 * max(1.0, abs(e_f)), (it, kind, path, e_t, e_f)
+        if rng.random() < 0.5:                         # accepted: the trial becomes the state ...
+            pos, num = tp, tn
+            if potential == 'lj':                      # ... and atoms.wrap() perturbs every coordinate
+                L = cell[0, 0]
+                pos = (np.linalg.solve(cell.T, pos.T).T % 1.0) @ cell
+        # the same configuration asked twice in a row costs nothing
+        if it % 37 == 0:
+            e2, p2 = trk.tracked_energy(tp, tn, cell, pbc)
+            assert e2 == e_t and p2 in (2, 1, 0)
+    assert paths[1] > 100 and paths[0] >= 2          # mostly incremental, re-based a few times
+    # a different box invalidates the base
+    cell2 = cell.copy()
+    if potential == 'lj':
+        cell2[0, 0] *= 1.01
+        e_t, path = trk.tracked_energy(pos, num, cell2, pbc)
+        assert path == 0 and abs(e_t - full.potential_energy(pos, num, cell2, pbc)) <= 1e-10 * max(1.0, abs(e_t))
+    trk.close(); full.close()
