@@ -260,6 +260,13 @@ def run_b200(args):
         ends[k].record(stream)
     barrier()
     gpu_launches = eng.launch_count - launches0
+    # per-stage device times of the same step (separate, untimed pass: events between the launches)
+    eng.stage_timing(True)
+    for _ in range(max(3, args.steps // 2)):
+        flush.zero_()
+        launch()
+        stage_ms, stage_calls = eng.stage_timing(True)
+    eng.stage_timing(False)
     kernel_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     kernel_ms = max_over_ranks(kernel_ms)
     assert torch.equal(d_dE, dE_ref), 'trial kernel is not deterministic'
@@ -363,6 +370,7 @@ def run_b200(args):
                    'api': 'calculator.get_potential_energy(atoms) per trial, sequential '
                           '(mcpyb_potential_energies_host: H2D config, cell list, energy, D2H)',
                    'us_per_call': 1e6 * chain_s / n_chain},
+        'stages_ms': {k: round(v, 5) for k, v in stage_ms.items()},
         'pair_interactions_per_s': pair_rate,
         'pairs_per_step': pairs_per_step,
         'gpu_launches': int(gpu_launches),

@@ -26,7 +26,7 @@ SYMBOLS = [
     'mcpyb_neighbor_pairs_host',
     'mcpyb_free_volume_count_host', 'mcpyb_free_volume_count_dev',
     'mcpyb_sphere_free_volume_pcg64', 'mcpyb_box_free_volume_pcg64',
-    'mcpyb_min_dist2_host', 'mcpyb_pcg64_host_doubles', 'mcpyb_fp64_peak_tflops', 'mcpyb_launch_count',
+    'mcpyb_min_dist2_host', 'mcpyb_pcg64_host_doubles', 'mcpyb_fp64_peak_tflops', 'mcpyb_stage_timing', 'mcpyb_launch_count',
 ]
 
 _p = C.c_void_p
@@ -87,6 +87,7 @@ def load():
     lib.mcpyb_min_dist2_host.argtypes = [_p, C.c_int, _p, C.c_int64, _p, _p]
     lib.mcpyb_pcg64_host_doubles.argtypes = [_p, _p, C.c_uint64, C.c_int64, _p]
     lib.mcpyb_fp64_peak_tflops.argtypes = [_p, _f64p]
+    lib.mcpyb_stage_timing.argtypes = [_p, C.c_int, _p, _p]
     lib.mcpyb_launch_count.argtypes = [_p]
     lib.mcpyb_launch_count.restype = C.c_int64
     _lib = lib

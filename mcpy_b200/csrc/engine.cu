@@ -16,6 +16,7 @@
 #include "stencil.cuh"
 #include "lj_kernels.cuh"
 #include "site_kernels.cuh"
+#include "rows_block.cuh"
 #include "emt_kernels.cuh"
 #include "free_volume.cuh"
 #include "pcg64.cuh"
@@ -101,6 +102,7 @@ struct mcpyb_engine {
     int subdiv = 1;                       // cells per cutoff length of the RESIDENT cell list
     int subdiv_trials = 1;                // ... wanted when trial moves will be scored against it
     int subdiv_energy = 1;                // ... wanted for upload + total energies in one call
+    int rb_slices = 2;                    // candidate-list slices per work item of the CTA row-sum kernel
     double rcut = 0.0;
     LJParams lj{};
     EmtTable emt_host{};
@@ -141,6 +143,13 @@ struct mcpyb_engine {
     double trk_E = 0.0;
     long long trk_full = 0, trk_incremental = 0;
 
+    // instrumentation: CUDA events between the launches of the trial pipeline (mcpyb_stage_timing)
+    bool stage_timing = false;
+    cudaEvent_t stage_ev[7] = {};
+    int stage_n = 0;                      // events recorded by the last launch_trials
+    double stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    long long stage_calls = 0;
+
     // trial staging
     DevBuf<unsigned char> trial_dev;
     PinBuf trial_pin, trial_out_pin;
@@ -149,7 +158,9 @@ struct mcpyb_engine {
     // second-generation trial pipeline (site_kernels.cuh)
     DevBuf<int> tw_int;                   // site_trial | site_bin | sorted | site_cnt | totals
     DevBuf<int> tw_bins;                  // bin_count | item_start | bin_cursor
-    DevBuf<double4> tw_pos;
+    DevBuf<double4> tw_pos, tw_spos;
+    DevBuf<int4> tw_meta;
+    DevBuf<int2> tw_items;
     DevBuf<double> tw_E;
 
     // neighbour list scratch
@@ -437,7 +448,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     e->e_atom.release(); e->sigma1.release(); e->e_part.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
-    e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release();
+    e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release(); e->tw_spos.release(); e->tw_meta.release(); e->tw_items.release();
     e->nl_i.release(); e->nl_j.release(); e->nl_S.release(); e->nl_r2.release(); e->nl_cursor.release();
     e->fv_grid.release(); e->fv_spheres.release(); e->fv_cell_start.release(); e->fv_cursor.release();
     e->fv_cid.release(); e->fv_points.release(); e->fv_pos.release(); e->fv_radii.release(); e->fv_small.release();
@@ -701,7 +712,11 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     w.nsites = nsites; w.n_old = n_old_total;
     w.bin_stride = e->max_cells; w.nbins = e->R * e->max_cells;
     const size_t ns = (size_t)(nsites > 0 ? nsites : 1), nbp = (size_t)w.nbins + 1;
-    w.nplanes = (nsites >= 4096) ? 1 : 2 * e->subdiv + 1;   // big batches have enough items; small ones need the split for parallelism
+    // big batches: one CTA per (cell, <= 128 sites) with the stencil staged once (rows_block.cuh);
+    // small ones: warp items split over the stencil z-planes for parallelism (site_kernels.cuh)
+    const bool block_rows = nsites >= 4096;
+    w.nplanes = block_rows ? e->rb_slices : 2 * e->subdiv + 1;
+    w.item_shift = block_rows ? RB_SITES_SHIFT : 5;
     const size_t nsp = ns * (size_t)w.nplanes;
     CK(e->tw_int.reserve(3 * ns + nsp + 4), "cudaMalloc trial work");
     CK(e->tw_bins.reserve(3 * nbp), "cudaMalloc trial bins");
@@ -711,25 +726,46 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     w.site_cnt = e->tw_int.p + 3 * ns; w.totals = e->tw_int.p + 3 * ns + nsp;
     w.bin_count = e->tw_bins.p; w.item_start = e->tw_bins.p + nbp; w.bin_cursor = e->tw_bins.p + 2 * nbp;
     w.site_pos = e->tw_pos.p; w.site_E = e->tw_E.p;
+    w.item_tab = nullptr; w.sorted_pos = nullptr; w.sorted_meta = nullptr;
+    if (block_rows) {
+        const size_t max_items = (ns >> RB_SITES_SHIFT) + (ns < nbp ? ns : nbp) + 1;
+        CK(e->tw_items.reserve(max_items), "cudaMalloc trial items");
+        CK(e->tw_spos.reserve(ns), "cudaMalloc trial work");
+        CK(e->tw_meta.reserve(ns), "cudaMalloc trial work");
+        w.item_tab = e->tw_items.p; w.sorted_pos = e->tw_spos.p; w.sorted_meta = e->tw_meta.p;
+    }
+    e->stage_n = 0;
+    auto mark = [&]() { if (e->stage_timing && e->stage_n < 7) cudaEventRecord(e->stage_ev[e->stage_n++], e->stream); };
+    mark();
     CK(cudaMemsetAsync(w.bin_count, 0, nbp * sizeof(int), e->stream), "memset bins");
+    mark();
     trial_sites_kernel<<<(T + 255) / 256, 256, 0, e->stream>>>(e->view(), tb, w);
     LAUNCH_CHECK("trial_sites_kernel");
+    mark();
     trial_scan_kernel<<<1, 1024, 0, e->stream>>>(w);
     LAUNCH_CHECK("trial_scan_kernel");
-    long long est = ((long long)nsites / 32 + (nsites < w.nbins ? nsites : w.nbins) + 1) * w.nplanes;
+    mark();
+    long long est = ((long long)(nsites >> w.item_shift) + (nsites < w.nbins ? nsites : w.nbins) + 1) * w.nplanes;
     int rb = (int)((est + SITE_WARPS - 1) / SITE_WARPS);
     if (rb > 148 * 32) rb = 148 * 32;
+    if (block_rows) rb = (int)(est < 148 * RB_MIN_BLOCKS * 8 ? est : 148 * RB_MIN_BLOCKS * 8);
     if (nsites > 0) {
-        trial_scatter_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(w);
+        trial_scatter_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(tb, w);
         LAUNCH_CHECK("trial_scatter_kernel");
     }
+    mark();
     {
-        if (nsites > 0) {
+        if (nsites > 0 && block_rows) {
+            lj_trial_rows_block_kernel<RB_UNROLL, RB_MIN_BLOCKS><<<rb, RB_THREADS, 0, e->stream>>>(e->view(), tb, w, e->lj);
+            LAUNCH_CHECK("lj_trial_rows_block_kernel");
+        } else if (nsites > 0) {
             lj_trial_rows_kernel<<<rb, 32 * SITE_WARPS, 0, e->stream>>>(e->view(), tb, w, e->lj);
             LAUNCH_CHECK("lj_trial_rows_kernel");
         }
+        mark();
         lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
         LAUNCH_CHECK("lj_trial_combine_kernel");
+        mark();
     }
     return MCPYB_OK;
 }
@@ -1136,6 +1172,37 @@ int mcpyb_fp64_peak_tflops(mcpyb_engine* e, double* tflops_out) {
     cudaEventDestroy(t0); cudaEventDestroy(t1);
     out.release();
     *tflops_out = best;
+    return MCPYB_OK;
+}
+
+// Stage timing of the LJ trial pipeline: memset | sites | scan | scatter | rows | combine.
+// enable != 0 switches event recording on; a later call folds the events of the most recent trial
+// launch into the running sums (after synchronising the stream) and returns the mean ms per stage.
+int mcpyb_stage_timing(mcpyb_engine* e, int enable, double* mean_ms_out6, int64_t* calls_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (enable && !e->stage_timing) {
+        for (int i = 0; i < 7; ++i) CK(cudaEventCreate(&e->stage_ev[i]), "cudaEventCreate");
+        e->stage_timing = true;
+        e->stage_n = 0;
+    }
+    if (e->stage_timing && e->stage_n == 7) {
+        CK(cudaStreamSynchronize(e->stream), "sync stage timing");
+        for (int i = 0; i < 6; ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e->stage_ev[i], e->stage_ev[i + 1]), "cudaEventElapsedTime");
+            e->stage_ms[i] += ms;
+        }
+        e->stage_calls++;
+        e->stage_n = 0;
+    }
+    if (mean_ms_out6)
+        for (int i = 0; i < 6; ++i) mean_ms_out6[i] = e->stage_calls ? e->stage_ms[i] / (double)e->stage_calls : 0.0;
+    if (calls_out) *calls_out = e->stage_calls;
+    if (!enable && e->stage_timing) {
+        for (int i = 0; i < 7; ++i) cudaEventDestroy(e->stage_ev[i]);
+        e->stage_timing = false;
+    }
     return MCPYB_OK;
 }
 

@@ -1,0 +1,368 @@
+// K3 / K6, third generation: trial-move row sums, one CTA per (cell, group of <= 128 sites).
+//
+// The second-generation kernel (site_kernels.cuh: fp32 screen + per-lane FIFO + exact drain) was
+// bound by instruction issue and latency, not by a math pipe: 20 k warp instructions per 32 sites,
+// issue-active 52-57 %, FP64 pipe 15 % (profiles/r1_v8_*).  A tighter FIFO version of it (38 M -> 31 M
+// instructions) ran no faster.  On B200 the FP64 pipe is only 2x narrower than the FP32 one, so this
+// kernel drops the screen altogether and feeds the FP64 pipe directly:
+//
+//   * the CTA stages the whole stencil of its cell ONCE in shared memory: exact records with the image
+//     shift already added in fp64, (q + S@cell) in the oracle's operation order;
+//   * each warp holds 32 sites of that cell, one per lane, and visits every staged candidate with two
+//     broadcast LDS.128 and ~15 FP64-pipe instructions: d = qs - p, fused r2, reciprocal, c6, and two
+//     masked accumulators (sum c12, sum c6).  No divergence, no FIFO, four candidates in flight;
+//   * membership r2 <= rc^2 must match the oracle bit for bit, energies only to 1e-10: the loop decides
+//     on a fused r2 and re-derives r2 in the oracle's unfused arithmetic (rb_exact_r2) for the rare
+//     candidate within a few ulps of the cutoff.  Sites outside the primary periodic cell are wrapped
+//     first and get a wider re-check band, so they cost nothing extra.
+//
+// The staged-candidate list of a cell (z-plane, row, main piece, wrapped piece, cell-sorted order) can
+// be cut into w.nplanes equal slices, one work item each.  A site's row sum is the fixed-order fold over
+// the slices of sequentially accumulated sums -- a function of the site and the configuration only,
+// independent of the lane, the warp and the batch the site arrives in.
+//
+// Boxes thinner than the stencil along x, or stencils with more than RB_MAXPIECES pieces, take the
+// generic per-lane traversal (tiny systems).
+#pragma once
+#include "common.cuh"
+#include "stencil.cuh"
+#include "lj_kernels.cuh"
+#include "site_kernels.cuh"
+
+#define RB_WARPS 4
+#define RB_THREADS (32 * RB_WARPS)
+#define RB_SITES RB_THREADS       // sites per work item
+#define RB_SITES_SHIFT 7
+#define RB_CAND 512               // staged candidates per chunk
+#define RB_UNROLL 4
+#define RB_MAXPIECES 128
+#define RB_MIN_BLOCKS 6
+
+template <int N> struct IntC { static constexpr int value = N; };
+
+struct RowsBlockSmem {
+    double4 candd[RB_CAND];                     // q + S@cell (exact, unfused), .w = tag
+    int cinfo[RB_CAND];                         // cell-sorted slot | piece << 24 (borderline re-check)
+    int pbeg[RB_MAXPIECES];                     // first cell-sorted slot of the piece
+    int pstart[RB_MAXPIECES + 1];               // staged offset of the piece
+    int pS[RB_MAXPIECES];                       // image shift of the piece (pack_wraps)
+    double pshift[RB_MAXPIECES][3];             // S @ cell
+    float wbox[RB_WARPS][6];                    // per-warp bounding boxes of the sites
+    int wcnt[RB_WARPS];                         // survivors per warp of a staging round
+    int total;
+};
+
+// r2 of staged candidate i against a site in the oracle's exact arithmetic: image shift
+// T = S_piece + w_site - w_j rebuilt from the raw record, unfused (dx*dx + dy*dy) + dz*dz.
+__device__ __noinline__ double rb_exact_r2(const GridDesc& g, const double4* __restrict__ spos,
+                                           const RowsBlockSmem& sm, int i, double px, double py, double pz,
+                                           int wsite) {
+    const int packed = sm.cinfo[i];
+    const double4 q = spos[packed & 0xFFFFFF];
+    int sx, sy, sz, jx, jy, jz, w0, w1, w2;
+    unpack_wraps(sm.pS[packed >> 24], sx, sy, sz);
+    unpack_wraps(tag_wraps(tag_of(q)), jx, jy, jz);
+    unpack_wraps(wsite, w0, w1, w2);
+    double ax, ay, az, dx, dy, dz;
+    shift_vec(g, sx + w0 - jx, sy + w1 - jy, sz + w2 - jz, ax, ay, az);
+    return image_r2(q.x, q.y, q.z, ax, ay, az, px, py, pz, dx, dy, dz);
+}
+
+// Generic traversal for one site (thin boxes, oversized stencils): exact arithmetic directly.
+// Returns the same accumulators as the fast path: sum c6^2, sum c6, pairs.
+__device__ __noinline__ void rb_generic_row(const GridDesc& g, const double4* __restrict__ spos,
+                                            const int* __restrict__ cstart, const LJParams& p,
+                                            double px, double py, double pz,
+                                            const int* __restrict__ old_idx, int ob, int oe,
+                                            double& acc12, double& acc6, int& cnt) {
+    double a12 = 0.0, a6 = 0.0;
+    int c = 0;
+    for_each_candidate(g, spos, cstart, px, py, pz, 0, 1, [&](const Cand& cd) {
+        if (cd.r2 <= p.rc2) {
+            const int j = tag_index(cd.tag);
+            bool ex = false;
+            for (int e = ob; e < oe; ++e) ex |= (old_idx[e] == j);
+            if (!ex) {
+                const double t = p.sigma2 * fast_rcp(cd.r2);
+                const double c6 = t * t * t;
+                a12 = fma(c6, c6, a12); a6 += c6; ++c;
+            }
+        }
+    });
+    acc12 = a12; acc6 = a6; cnt = c;
+}
+
+template <int RBU, int MINB>
+__global__ void __launch_bounds__(RB_THREADS, MINB)
+lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) {
+    __shared__ RowsBlockSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nq = w.nplanes;                     // slices of the candidate list, one work item each
+    const int nwork = w.totals[0] * nq;
+    for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const int item = wi / nq, slice = wi - item * nq;
+        const int2 it = w.item_tab[item];
+        const int bin = it.x, group = it.y;
+        const int r = bin / w.bin_stride, c = bin - r * w.bin_stride;
+        const GridDesc& g = b.grid[r];
+        const int off = g.atom_off;
+        const int* cstart = b.cell_start + (size_t)r * b.cs_stride;
+        const double4* spos = b.spos + off;
+        const int n0 = g.ncell[0], n1 = g.ncell[1], n2 = g.ncell[2];
+        const int m0 = g.m[0], m1 = g.m[1], m2 = g.m[2];
+        const int c0 = c % n0, c1 = (c / n0) % n1, c2 = c / (n0 * n1);
+        const int wr1 = 2 * m1 + 1, wr2 = 2 * m2 + 1, nrows = wr1 * wr2;
+        const bool perx = g.pbc[0] != 0;
+        const bool fast = (!perx || n0 >= 2 * m0 + 1) && 2 * nrows <= RB_MAXPIECES;
+
+        // ---- this thread's site
+        const int kbeg = w.bin_count[bin] + group * RB_SITES, kend = w.bin_count[bin + 1];
+        const bool active = kbeg + tid < kend;
+        const bool warp_active = kbeg + wid * 32 < kend;
+        int s = 0, ob = 0, oe = 0, ex0 = -1, wsite = pack_wraps(0, 0, 0);
+        double px = 0.0, py = 0.0, pz = 0.0;
+        if (active) {
+            const double4 me = w.sorted_pos[kbeg + tid];
+            const int4 mt = w.sorted_meta[kbeg + tid];
+            px = me.x; py = me.y; pz = me.z;
+            wsite = (int)__double_as_longlong(me.w);
+            s = mt.x; ex0 = mt.y; ob = mt.z; oe = mt.w;
+        }
+        double acc12 = 0.0, acc6 = 0.0;
+        int cnt = 0;
+
+        if (!fast) {
+            if (active && slice == 0)
+                rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, acc12, acc6, cnt);
+        } else {
+            // ---- stencil pieces: lane l of warp 0 owns rows 2l, 2l+1 = pieces 4l .. 4l+3
+            if (wid == 0) {
+                int beg[4] = {0, 0, 0, 0}, len[4] = {0, 0, 0, 0}, Sx[4] = {0, 0, 0, 0}, Sy[2] = {0, 0}, Sz[2] = {0, 0};
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int row = 2 * lane + j;
+                    if (row < nrows) {
+                        int cy = c1 + (row % wr1) - m1, cz = c2 + (row / wr1) - m2;
+                        bool valid = true;
+                        if (g.pbc[1]) { Sy[j] = floor_div(cy, n1); cy -= Sy[j] * n1; }
+                        else if (cy < 0 || cy >= n1) valid = false;
+                        if (g.pbc[2]) { Sz[j] = floor_div(cz, n2); cz -= Sz[j] * n2; }
+                        else if (cz < 0 || cz >= n2) valid = false;
+                        if (valid) {
+                            const int rowoff = (cz * n1 + cy) * n0;
+                            const int lo = c0 - m0, hi = c0 + m0;
+                            const int a0 = max(lo, 0), a1 = min(hi, n0 - 1);
+                            beg[2 * j] = cstart[rowoff + a0];
+                            len[2 * j] = cstart[rowoff + a1 + 1] - beg[2 * j];
+                            if (perx) {
+                                if (lo < 0) {
+                                    beg[2 * j + 1] = cstart[rowoff + lo + n0];
+                                    len[2 * j + 1] = cstart[rowoff + n0] - beg[2 * j + 1];
+                                    Sx[2 * j + 1] = -1;
+                                } else if (hi >= n0) {
+                                    beg[2 * j + 1] = cstart[rowoff];
+                                    len[2 * j + 1] = cstart[rowoff + hi - n0 + 1] - beg[2 * j + 1];
+                                    Sx[2 * j + 1] = 1;
+                                }
+                            }
+                        }
+                    }
+                }
+                const int mine = len[0] + len[1] + len[2] + len[3];
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                int base = incl - mine;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int pc = 4 * lane + j;
+                    if (pc < 2 * nrows) {
+                        sm.pstart[pc] = base;
+                        sm.pbeg[pc] = beg[j];
+                        sm.pS[pc] = pack_wraps(Sx[j], Sy[j >> 1], Sz[j >> 1]);
+                        double ax, ay, az;
+                        shift_vec(g, Sx[j], Sy[j >> 1], Sz[j >> 1], ax, ay, az);
+                        sm.pshift[pc][0] = ax; sm.pshift[pc][1] = ay; sm.pshift[pc][2] = az;
+                    }
+                    base += len[j];
+                }
+                if (lane == 31) { sm.pstart[2 * nrows] = incl; sm.total = incl; }
+            }
+            __syncthreads();
+            const int total = sm.total, npieces = 2 * nrows;
+
+            // ---- per-lane constants.  The loop works with the site wrapped into the primary cell
+            // (qx, qy, qz) and a fused r2; both differ from the oracle's value by rounding only.
+            // `in` is decided on the bit pattern of r2 (positive doubles order like integers):
+            // below lo_bits -> inside, above hi_bits -> outside, in between -> exact re-check.
+            double qx = 3.0e150, qy = 3.0e150, qz = 3.0e150;     // idle lanes: r2 overflows, never inside
+            double band = 16.0;                                    // ulps, relative to rc^2
+            if (active) {
+                qx = px; qy = py; qz = pz;
+                if (wsite != pack_wraps(0, 0, 0)) {
+                    int w0, w1, w2;
+                    unpack_wraps(wsite, w0, w1, w2);
+                    const double a = (double)w0, bb = (double)w1, cc = (double)w2;
+                    qx = px - (a * g.cell[0] + bb * g.cell[3] + cc * g.cell[6]);
+                    qy = py - (a * g.cell[1] + bb * g.cell[4] + cc * g.cell[7]);
+                    qz = pz - (a * g.cell[2] + bb * g.cell[5] + cc * g.cell[8]);
+                    band += 64.0 * (fabs(px) + fabs(py) + fabs(pz) + fabs(qx) + fabs(qy) + fabs(qz)) / p.rc;
+                }
+            }
+            const double bw = p.rc2 * band * 2.220446049250313e-16;
+            const long long lo_bits = __double_as_longlong(p.rc2 - bw), hi_bits = __double_as_longlong(p.rc2 + bw);
+            const bool multi = (oe - ob) > 1;
+
+            // ---- bounding box of this CTA's (wrapped) sites, rounded outward to fp32.  A candidate
+            // farther than rc from the box is farther than rc from every site: it is dropped at staging
+            // (its masked contribution would be +0.0 to every accumulator, so no sum changes).
+            {
+                float lo3[3] = {__double2float_rd(qx), __double2float_rd(qy), __double2float_rd(qz)};
+                float hi3[3] = {__double2float_ru(qx), __double2float_ru(qy), __double2float_ru(qz)};
+                if (!active) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { lo3[d] = 3.0e38f; hi3[d] = -3.0e38f; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        lo3[d] = fminf(lo3[d], __shfl_xor_sync(0xffffffffu, lo3[d], o));
+                        hi3[d] = fmaxf(hi3[d], __shfl_xor_sync(0xffffffffu, hi3[d], o));
+                    }
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { sm.wbox[wid][d] = lo3[d]; sm.wbox[wid][3 + d] = hi3[d]; }
+                }
+            }
+            __syncthreads();
+            double blo[3], bhi[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                float l = sm.wbox[0][d], h = sm.wbox[0][3 + d];
+#pragma unroll
+                for (int ww = 1; ww < RB_WARPS; ++ww) { l = fminf(l, sm.wbox[ww][d]); h = fmaxf(h, sm.wbox[ww][3 + d]); }
+                blo[d] = (double)l; bhi[d] = (double)h;
+            }
+            const double keep_r2 = p.rc2 * (1.0 + 1e-9);
+            const int lo_hi = (int)(lo_bits >> 32), hi_hi = (int)(hi_bits >> 32);
+
+            // this work item's slice of the stencil's candidate list: a function of the cell alone
+            const int cfirst = (int)(((long long)total * slice) / nq), clast = (int)(((long long)total * (slice + 1)) / nq);
+            int gi0 = cfirst;
+            while (gi0 < clast) {
+                // ---- stage: test RB_THREADS candidates per round, keep the survivors in list order
+                int nst = 0;
+                while (gi0 < clast && nst + RB_THREADS <= RB_CAND) {
+                    const int gi = gi0 + tid;
+                    bool keep = false;
+                    double4 q = make_double4(0.0, 0.0, 0.0, 0.0);
+                    int info = 0;
+                    if (gi < clast) {
+                        int lo = 0, hi = npieces;                 // pstart[lo] <= gi < pstart[hi]
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (sm.pstart[mid] <= gi) lo = mid; else hi = mid;
+                        }
+                        const int k = sm.pbeg[lo] + (gi - sm.pstart[lo]);
+                        q = spos[k];
+                        double ax = sm.pshift[lo][0], ay = sm.pshift[lo][1], az = sm.pshift[lo][2];
+                        const long long tag = tag_of(q);
+                        const int wj = tag_wraps(tag);
+                        if (wj != pack_wraps(0, 0, 0)) {          // atom stored outside the primary cell
+                            int sx, sy, sz, jx, jy, jz;
+                            unpack_wraps(sm.pS[lo], sx, sy, sz);
+                            unpack_wraps(wj, jx, jy, jz);
+                            shift_vec(g, sx - jx, sy - jy, sz - jz, ax, ay, az);
+                        }
+                        q.x = __dadd_rn(q.x, ax); q.y = __dadd_rn(q.y, ay); q.z = __dadd_rn(q.z, az);
+                        q.w = __longlong_as_double((long long)tag_index(tag));     // low word = atom index
+                        info = k | (lo << 24);
+                        const double ex = fmax(fmax(blo[0] - q.x, q.x - bhi[0]), 0.0);
+                        const double ey = fmax(fmax(blo[1] - q.y, q.y - bhi[1]), 0.0);
+                        const double ez = fmax(fmax(blo[2] - q.z, q.z - bhi[2]), 0.0);
+                        keep = fma(ez, ez, fma(ey, ey, ex * ex)) <= keep_r2;
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (lane == 0) sm.wcnt[wid] = __popc(bal);
+                    __syncthreads();
+                    int before = 0, all = 0;
+#pragma unroll
+                    for (int ww = 0; ww < RB_WARPS; ++ww) {
+                        const int cw = sm.wcnt[ww];
+                        before += (ww < wid) ? cw : 0;
+                        all += cw;
+                    }
+                    if (keep) {
+                        const int slot = nst + before + __popc(bal & ((1u << lane) - 1u));
+                        sm.candd[slot] = q;
+                        sm.cinfo[slot] = info;
+                    }
+                    nst += all;
+                    gi0 += RB_THREADS;
+                    __syncthreads();                               // wcnt is rewritten next round
+                }
+                const int n = nst;
+                if (warp_active) {
+                    // U candidates per trip, branch-free unless some lane needs the rare fix-ups, so the
+                    // U dependent FP64 chains interleave
+                    auto visit = [&](int i, auto U_) {
+                        constexpr int U = decltype(U_)::value;
+                        double r2[U];
+                        int jj[U];
+                        bool in[U];
+                        bool fix = multi;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const double4 q = sm.candd[i + u];    // uniform address: two broadcast LDS.128
+                            const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
+                            r2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
+                            const int rh = __double2hiint(r2[u]);  // positive doubles order like their bits
+                            in[u] = rh < lo_hi;
+                            fix = fix || (!in[u] && rh <= hi_hi);  // high word ties: full compare below
+                            jj[u] = __double2loint(q.w);
+                        }
+                        if (__any_sync(0xffffffffu, fix)) {
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const long long rb = __double_as_longlong(r2[u]);
+                                in[u] = rb < lo_bits;
+                                // within rounding of the cutoff: the oracle's arithmetic decides
+                                if (!in[u] && rb <= hi_bits)
+                                    in[u] = rb_exact_r2(g, spos, sm, i + u, px, py, pz, wsite) <= p.rc2;
+                                if (multi && in[u])
+                                    for (int e = ob + 1; e < oe; ++e) if (tb.old_idx[e] == jj[u]) in[u] = false;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const bool hit = in[u] && (jj[u] != ex0);
+                            // a miss is evaluated at r2 ~ 9e307: its reciprocal flushes to zero, so c6 = 0
+                            const double rm = __hiloint2double(hit ? __double2hiint(r2[u]) : 0x7fe00000, __double2loint(r2[u]));
+                            const double t = p.sigma2 * fast_rcp(rm);
+                            const double c6 = t * t * t;
+                            acc12 = fma(c6, c6, acc12);
+                            acc6 += c6;
+                            cnt += hit ? 1 : 0;
+                        }
+                    };
+                    int i = 0;
+                    for (; i + RBU <= n; i += RBU) visit(i, IntC<RBU>());
+                    for (; i < n; ++i) visit(i, IntC<1>());
+                }
+                __syncthreads();
+            }
+        }
+        if (active) {
+            // row = 4 eps (sum c12 - sum c6) - e0 * pairs
+            const double row = fma(p.eps4, acc12 - acc6, -p.e0 * (double)cnt);
+            w.site_E[(size_t)s * nq + slice] = row;
+            w.site_cnt[(size_t)s * nq + slice] = cnt;
+        }
+        __syncthreads();                                          // the piece table is rewritten next
+    }
+}

@@ -396,9 +396,14 @@ struct TrialWork {
     int* bin_cursor;       // [nbins]
     int* sorted;           // [nsites] site ids grouped by bin
     int nplanes;           // stencil z-planes: one work item per (bin, chunk, plane)
+    int item_shift;        // sites per work item = 1 << item_shift (5: warp items, 7: CTA items)
     double* site_E;        // [nsites][nplanes] partial row sums
     int* site_cnt;         // [nsites][nplanes] in-cutoff pairs
     int* totals;           // [0] = number of work items
+    // CTA row-sum kernel (rows_block.cuh): its prologue reads these instead of chasing pointers
+    int2* item_tab;        // [items] (bin, group of the bin's sites); nullptr: not wanted
+    double4* sorted_pos;   // [nsites] site_pos in bin order
+    int4* sorted_meta;     // [nsites] (site id, first excluded atom or -1, old_off[t], old_off[t+1]) in bin order
 };
 
 __device__ __forceinline__ int owner_of(const int* __restrict__ off, int T, int k) {
@@ -450,7 +455,8 @@ trial_scan_kernel(TrialWork w) {
     const int per = (w.nbins + 1023) / 1024;
     const int beg = min(tid * per, w.nbins), end = min(beg + per, w.nbins);
     int sa = 0, sb = 0;
-    for (int i = beg; i < end; ++i) { const int c = w.bin_count[i]; sa += c; sb += (c + 31) >> 5; }
+    const int ish = w.item_shift, iround = (1 << ish) - 1;
+    for (int i = beg; i < end; ++i) { const int c = w.bin_count[i]; sa += c; sb += (c + iround) >> ish; }
     s_a[tid] = sa; s_b[tid] = sb;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
@@ -463,17 +469,26 @@ trial_scan_kernel(TrialWork w) {
     for (int i = beg; i < end; ++i) {
         const int c = w.bin_count[i];
         w.bin_count[i] = ra; w.item_start[i] = rb; w.bin_cursor[i] = 0;
-        ra += c; rb += (c + 31) >> 5;
+        const int ni = (c + iround) >> ish;
+        if (w.item_tab) for (int gq = 0; gq < ni; ++gq) w.item_tab[rb + gq] = make_int2(i, gq);
+        ra += c; rb += ni;
     }
     if (tid == 1023) { w.bin_count[w.nbins] = s_a[1023]; w.item_start[w.nbins] = s_b[1023]; w.totals[0] = s_b[1023]; }
 }
 
 __global__ void __launch_bounds__(256)
-trial_scatter_kernel(TrialWork w) {
+trial_scatter_kernel(TrialBatch tb, TrialWork w) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= w.nsites) return;
     const int bin = w.site_bin[s];
-    w.sorted[w.bin_count[bin] + atomicAdd(&w.bin_cursor[bin], 1)] = s;
+    const int k = w.bin_count[bin] + atomicAdd(&w.bin_cursor[bin], 1);
+    w.sorted[k] = s;
+    if (w.sorted_pos) {
+        w.sorted_pos[k] = w.site_pos[s];
+        const int t = w.site_trial[s];
+        const int ob = tb.old_off[t], oe = tb.old_off[t + 1];
+        w.sorted_meta[k] = make_int4(s, oe > ob ? tb.old_idx[ob] : -1, ob, oe);
+    }
 }
 
 __global__ void __launch_bounds__(32 * SITE_WARPS, SITE_MIN_BLOCKS)
