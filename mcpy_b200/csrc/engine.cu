@@ -152,6 +152,7 @@ struct mcpyb_engine {
     long long stage_calls = 0;
 
     // trial staging
+    cudaEvent_t trial_ev = nullptr;
     DevBuf<unsigned char> trial_dev;
     PinBuf trial_pin, trial_out_pin;
     DevBuf<double> dE;
@@ -160,6 +161,7 @@ struct mcpyb_engine {
     DevBuf<int> tw_int;                   // site_trial | sorted | site_cnt | totals
     DevBuf<int> tw_bins;                  // bin_count | item_start
     DevBuf<int4> tw_a;
+    DevBuf<int> tw_hist;
     DevBuf<unsigned long long> tw_err;    // [0] armed error word, [1] its value after the last launch
     int tw_stamp = 0;
     DevBuf<double4> tw_pos, tw_spos;
@@ -452,12 +454,13 @@ void mcpyb_destroy(mcpyb_engine* e) {
     e->e_atom.release(); e->sigma1.release(); e->e_part.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
-    e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release(); e->tw_spos.release(); e->tw_meta.release(); e->tw_items.release(); e->tw_a.release(); e->tw_err.release();
+    e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release(); e->tw_spos.release(); e->tw_meta.release(); e->tw_items.release(); e->tw_a.release(); e->tw_err.release(); e->tw_hist.release();
     e->nl_i.release(); e->nl_j.release(); e->nl_S.release(); e->nl_r2.release(); e->nl_cursor.release();
     e->fv_grid.release(); e->fv_spheres.release(); e->fv_cell_start.release(); e->fv_cursor.release();
     e->fv_cid.release(); e->fv_points.release(); e->fv_pos.release(); e->fv_radii.release(); e->fv_small.release();
     e->fv_counts.release(); e->fv_mask.release(); e->fv_pin.release();
     e->pcg_count.release(); e->pcg_prefix.release(); e->pcg_ctl.release();
+    if (e->trial_ev) cudaEventDestroy(e->trial_ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -723,11 +726,12 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     w.item_shift = block_rows ? RB_SITES_SHIFT : 5;
     const size_t nsp = ns * (size_t)w.nplanes;
     CK(e->tw_int.reserve(2 * ns + nsp + 4), "cudaMalloc trial work");
+    CK(e->tw_bins.reserve(2 * nbp), "cudaMalloc trial bins");
     {
-        const size_t had = e->tw_bins.cap;
-        CK(e->tw_bins.reserve(2 * nbp), "cudaMalloc trial bins");
-        if (e->tw_bins.cap != had)           // fresh histogram: zero once, the combine kernel keeps it zero
-            CK(cudaMemsetAsync(e->tw_bins.p, 0, e->tw_bins.cap * sizeof(int), e->stream), "memset bins");
+        const size_t had = e->tw_hist.cap;
+        CK(e->tw_hist.reserve(nbp * TRIAL_HIST_STRIDE), "cudaMalloc trial histogram");
+        if (e->tw_hist.cap != had)           // fresh histogram: zero once, the scan kernel keeps it zero
+            CK(cudaMemsetAsync(e->tw_hist.p, 0, e->tw_hist.cap * sizeof(int), e->stream), "memset histogram");
     }
     if (!e->tw_err.p) {
         CK(e->tw_err.reserve(2), "cudaMalloc trial status");
@@ -744,7 +748,7 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     w.n_new = n_new_total;
     w.site_trial = e->tw_int.p; w.sorted = e->tw_int.p + ns;
     w.site_cnt = e->tw_int.p + 2 * ns; w.totals = e->tw_int.p + 2 * ns + nsp;
-    w.bin_count = e->tw_bins.p; w.item_start = e->tw_bins.p + nbp;
+    w.hist = e->tw_hist.p; w.bin_count = e->tw_bins.p; w.item_start = e->tw_bins.p + nbp;
     w.site_pos = e->tw_pos.p; w.site_a = e->tw_a.p; w.site_E = e->tw_E.p;
     w.err = e->tw_err.p; w.err_out = d_status ? d_status : e->tw_err.p + 1;
     e->tw_stamp = (e->tw_stamp % 0x3FFFFFF) + 1;
@@ -851,24 +855,41 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
     CK(e->dE.reserve((size_t)T + 1), "cudaMalloc dE");          // dE[T] carries the device status word
     CK(e->tpairs.reserve(T), "cudaMalloc trial pairs");
     unsigned char* h = e->trial_pin.p;
-    if (rep) memcpy(h + o_rep, rep, (size_t)T * 4); else memset(h + o_rep, 0, (size_t)T * 4);
-    memcpy(h + o_oo, old_off, (size_t)(T + 1) * 4);
-    memcpy(h + o_no, new_off, (size_t)(T + 1) * 4);
-    if (n_old) memcpy(h + o_oi, old_idx, (size_t)n_old * 4);
-    if (n_new && new_Z) memcpy(h + o_nz, new_Z, (size_t)n_new * 4);
-    if (n_new) memcpy(h + o_np, new_pos, (size_t)n_new * 24);
-    CK(cudaMemcpyAsync(e->trial_dev.p, h, bytes, cudaMemcpyHostToDevice, e->stream), "H2D trials");
     unsigned char* d = e->trial_dev.p;
-    int rc = launch_trials(e, T, (const int32_t*)(d + o_rep), (const int32_t*)(d + o_oo), (const int32_t*)(d + o_oi),
+    // stage piece by piece: the H2D copy of one piece runs while the host copies the next one
+    auto stage = [&](size_t off, const void* src, size_t nbytes) -> cudaError_t {
+        const size_t piece = 512u << 10;
+        for (size_t done = 0; done < nbytes; done += piece) {
+            const size_t nb = nbytes - done < piece ? nbytes - done : piece;
+            memcpy(h + off + done, (const unsigned char*)src + done, nb);
+            cudaError_t ce = cudaMemcpyAsync(d + off + done, h + off + done, nb, cudaMemcpyHostToDevice, e->stream);
+            if (ce != cudaSuccess) return ce;
+        }
+        return cudaSuccess;
+    };
+    if (rep) CK(stage(o_rep, rep, (size_t)T * 4), "H2D trials");
+    CK(stage(o_oo, old_off, (size_t)(T + 1) * 4), "H2D trials");
+    CK(stage(o_no, new_off, (size_t)(T + 1) * 4), "H2D trials");
+    if (n_old) CK(stage(o_oi, old_idx, (size_t)n_old * 4), "H2D trials");
+    if (n_new && new_Z && e->pot_kind == POT_EMT) CK(stage(o_nz, new_Z, (size_t)n_new * 4), "H2D trials");
+    if (n_new) CK(stage(o_np, new_pos, (size_t)n_new * 24), "H2D trials");
+    int rc = launch_trials(e, T, rep ? (const int32_t*)(d + o_rep) : nullptr, (const int32_t*)(d + o_oo), (const int32_t*)(d + o_oi),
                            (const int32_t*)(d + o_no), (const double*)(d + o_np),
-                           new_Z ? (const int32_t*)(d + o_nz) : nullptr, n_old, n_new, e->dE.p, e->tpairs.p,
+                           (new_Z && e->pot_kind == POT_EMT) ? (const int32_t*)(d + o_nz) : nullptr, n_old, n_new, e->dE.p, e->tpairs.p,
                            (unsigned long long*)(e->dE.p + T));
     if (rc != MCPYB_OK) return rc;
     const size_t ob = (size_t)(T + 1) * sizeof(double), pb = (size_t)T * sizeof(int);
     CK(e->trial_out_pin.reserve(ob + pb), "cudaMallocHost trial out");
-    CK(cudaMemcpyAsync(e->trial_out_pin.p, e->dE.p, ob, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
+    // status word first, then dE in two halves: the host copies half 1 out while half 2 is in flight
+    const size_t half = ((size_t)T / 2) * sizeof(double), full = (size_t)T * sizeof(double);
+    if (!e->trial_ev) CK(cudaEventCreateWithFlags(&e->trial_ev, cudaEventDisableTiming), "cudaEventCreate");
+    CK(cudaMemcpyAsync(e->trial_out_pin.p + full, e->dE.p + T, sizeof(double), cudaMemcpyDeviceToHost, e->stream), "D2H status");
+    CK(cudaMemcpyAsync(e->trial_out_pin.p, e->dE.p, half, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
+    CK(cudaEventRecord(e->trial_ev, e->stream), "cudaEventRecord");
+    CK(cudaMemcpyAsync(e->trial_out_pin.p + half, (const unsigned char*)e->dE.p + half, full - half, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
     if (pairs_out) CK(cudaMemcpyAsync(e->trial_out_pin.p + ob, e->tpairs.p, pb, cudaMemcpyDeviceToHost, e->stream), "D2H pairs");
-    CK(cudaStreamSynchronize(e->stream), "sync trials");
+    CK(cudaEventSynchronize(e->trial_ev), "sync trials (first half)");
+
     if (dev_checked) {
         unsigned long long st;
         memcpy(&st, e->trial_out_pin.p + (size_t)T * sizeof(double), sizeof st);
@@ -879,7 +900,9 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
             return e->fail(MCPYB_ERR_ARG, "trial %d: atom index out of range", t);
         }
     }
-    memcpy(dE_out, e->trial_out_pin.p, (size_t)T * sizeof(double));
+    memcpy(dE_out, e->trial_out_pin.p, half);
+    CK(cudaStreamSynchronize(e->stream), "sync trials");
+    memcpy((unsigned char*)dE_out + half, e->trial_out_pin.p + half, full - half);
     if (pairs_out) memcpy(pairs_out, e->trial_out_pin.p + ob, pb);
     return MCPYB_OK;
 }

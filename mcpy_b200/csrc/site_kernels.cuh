@@ -383,6 +383,8 @@ lj_fold_planes_kernel(int total_atoms, int nplanes, const double* __restrict__ e
 //   4 lj_trial_rows_kernel one warp per (bin, chunk of 32 sites): row sums, one site per lane
 //   5 lj_trial_combine_kernel  one thread per trial: sum(new rows) - sum(old rows) + moved-set pairs
 // ---------------------------------------------------------------------------
+#define TRIAL_HIST_STRIDE 8
+
 struct TrialWork {
     int nsites;            // n_old_total + n_new_total; sites [0, n_old) are old, the rest new
     int n_old;
@@ -393,7 +395,10 @@ struct TrialWork {
     int4* site_a;          // [nsites] (bin, rank inside the bin, first excluded atom or -1, old_off[t])
     double4* site_pos;     // [nsites] (x, y, z, .w = packed wraps | moved-atom count << 32 | stamp << 38)
     int stamp;             // 1 .. 2^26-1, new for every launch: sites left over from earlier launches are ignored
-    int* bin_count;        // [nbins + 1]  histogram (zero on entry; the combine kernel re-zeroes it), then bin_start
+    int* hist;             // [nbins * TRIAL_HIST_STRIDE] site histogram, one 32-byte sector per bin (atomics on
+                           // neighbouring bins of one sector serialise in L2: 8 us of a 19 us kernel); zero on
+                           // entry, re-zeroed by the scan kernel once it has read it
+    int* bin_count;        // [nbins + 1]  bin_start (exclusive prefix of the histogram)
     int* item_start;       // [nbins + 1]
     int* sorted;           // [nsites] site ids grouped by bin
     int nplanes;           // partial sums per site: stencil z-planes (warp kernel) or list slices (CTA kernel)
@@ -467,7 +472,7 @@ trial_sites_kernel(BatchView b, TrialBatch tb, TrialWork w) {
         int c[3], wr[3];
         locate(g, x, y, z, c, wr);
         const int bin = r * w.bin_stride + (c[2] * g.ncell[1] + c[1]) * g.ncell[0] + c[0];
-        const int rank = atomicAdd(&w.bin_count[bin], 1);
+        const int rank = atomicAdd(&w.hist[(size_t)bin * TRIAL_HIST_STRIDE], 1);
         w.site_trial[s] = t;
         w.site_a[s] = make_int4(bin, rank, ex0, ob);
         w.site_pos[s] = make_double4(x, y, z, __longlong_as_double((long long)pack_wraps(wr[0], wr[1], wr[2]) | cnt_bits));
@@ -483,7 +488,7 @@ trial_scan_kernel(TrialWork w) {
     const int beg = min(tid * per, w.nbins), end = min(beg + per, w.nbins);
     int sa = 0, sb = 0;
     const int ish = w.item_shift, iround = (1 << ish) - 1;
-    for (int i = beg; i < end; ++i) { const int c = w.bin_count[i]; sa += c; sb += (c + iround) >> ish; }
+    for (int i = beg; i < end; ++i) { const int c = w.hist[(size_t)i * TRIAL_HIST_STRIDE]; sa += c; sb += (c + iround) >> ish; }
     s_a[tid] = sa; s_b[tid] = sb;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
@@ -494,7 +499,8 @@ trial_scan_kernel(TrialWork w) {
     }
     int ra = s_a[tid] - sa, rb = s_b[tid] - sb;      // exclusive prefix of this thread's run
     for (int i = beg; i < end; ++i) {
-        const int c = w.bin_count[i];
+        const int c = w.hist[(size_t)i * TRIAL_HIST_STRIDE];
+        w.hist[(size_t)i * TRIAL_HIST_STRIDE] = 0;
         w.bin_count[i] = ra; w.item_start[i] = rb;
         const int ni = (c + iround) >> ish;
         if (w.item_tab) for (int gq = 0; gq < ni; ++gq) w.item_tab[rb + gq] = make_int2(i, gq);
@@ -577,8 +583,6 @@ __global__ void __launch_bounds__(128)
 lj_trial_combine_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p,
                         double* __restrict__ dE, int* __restrict__ npairs) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    // the histogram must be zero when the next trial launch starts
-    for (int i = t; i <= w.nbins; i += gridDim.x * blockDim.x) w.bin_count[i] = 0;
     if (t >= tb.T) return;
     const int r = tb.rep ? tb.rep[t] : 0;
     const int ob = tb.old_off[t], oe = tb.old_off[t + 1];
