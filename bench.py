@@ -10,17 +10,21 @@ pre-generated GCMC proposals against it -- insertions, deletions and displacemen
 in the ratio 1:1:1.  One "step" scores the whole batch once.
 
   value      whole-job delta-E evaluations / s with the configuration and the
-             proposals already resident in HBM (one kernel launch per step, CUDA
-             events on the launching stream, L2 flushed between steps).
+             proposals already resident in HBM (the five launches of the trial
+             pipeline per step, CUDA events on the launching stream, L2 flushed
+             between steps).
   e2e        the same metric through the plug-in with HOST buffers: every step
              uploads the configuration (cell list rebuilt) and the proposals and reads
              the delta-E array back (B200Calculator.set_configuration +
              trial_delta_energies -> mcpyb_upload_host + mcpyb_trial_delta_e_host).
   dropin     what an unmodified mcpy run gets today: one
-             calculator.get_potential_energy(atoms) per trial, sequential, host buffers.
-  roofline   the trial kernel against the FP64 pipe (measured here with a DFMA
-             microbenchmark; MEASURED_PEAKS.json has no FP64 figure).  Tensor cores
-             are not used: nothing on this path is a dense contraction.
+             calculator.get_potential_energy(atoms) per trial, sequential, host buffers
+             (the engine answers with its resident base + one single-launch delta).
+  stages_ms  device time of each launch of the pipeline (CUDA events between them).
+  roofline   the dominant kernel (the row sums) against the FP64 pipe: algorithmic flop
+             per launch / its own event-timed duration, over the DFMA rate measured in
+             this process (MEASURED_PEAKS.json has no FP64 figure).  Tensor cores are
+             not used: nothing on this path is a dense contraction.
   cpu_baseline / --impl reference
              the reference's cost of one trial: one full-energy evaluation
              (grand_canonical_ensemble.py:283-284) by the port of ASE's
@@ -326,7 +330,8 @@ def run_b200(args):
     sites = n_old + n_new
     alg_flop = sites * ALG_CANDIDATES_PER_SITE * ALG_FLOP_PER_CANDIDATE + pairs_per_step * ALG_FLOP_PER_PAIR
     peak = eng.fp64_peak_tflops()
-    achieved = alg_flop / (ms_per_step * 1e-3) / 1e12
+    rows_ms = stage_ms['row_sums']
+    achieved = alg_flop / (rows_ms * 1e-3) / 1e12
     pair_rate = sum_over_ranks(pairs_per_step) / (ms_per_step * 1e-3)
 
     if rank != 0:
@@ -352,7 +357,7 @@ def run_b200(args):
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get('lj_trial_delta_kernel_dram_bytes_per_launch')
+            traffic = json.load(open(tpath)).get('lj_trial_rows_block_kernel_dram_bytes_per_launch')
         except Exception:
             traffic = None
 
@@ -368,7 +373,10 @@ def run_b200(args):
                 'ms_per_step': 1e3 * e2e_s / args.steps},
         'dropin': {'value': dropin_value, 'unit': UNIT, 'calls': n_chain,
                    'api': 'calculator.get_potential_energy(atoms) per trial, sequential '
-                          '(mcpyb_potential_energies_host: H2D config, cell list, energy, D2H)',
+                          '(mcpyb_tracked_energy_host: resident base + one delta; the trial rides in the '
+                          'kernel parameters, the result lands in pinned host memory)',
+                   'paths': {'full': calc.path_counts[0], 'incremental': calc.path_counts[1],
+                             'identical': calc.path_counts[2]},
                    'us_per_call': 1e6 * chain_s / n_chain},
         'stages_ms': {k: round(v, 5) for k, v in stage_ms.items()},
         'pair_interactions_per_s': pair_rate,
@@ -376,11 +384,16 @@ def run_b200(args):
         'gpu_launches': int(gpu_launches),
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': achieved / peak if peak else None, 'traffic': traffic,
-                     'kernel': 'lj_trial_delta_kernel<32>',
+                     'kernel': 'lj_trial_rows_block_kernel<4,6>',
+                     'kernel_ms': rows_ms, 'kernel_share_of_step': rows_ms / sum(stage_ms.values()),
                      'algorithmic_flop_per_launch': alg_flop,
+                     'step_achieved': alg_flop / (ms_per_step * 1e-3) / 1e12,
                      'peak_source': 'measured here: DFMA microbenchmark (mcpyb_fp64_peak_tflops); '
                                     'MEASURED_PEAKS.json holds only HBM and bf16 figures',
-                     'note': 'HBM is not the bound: the 64 KB configuration is L1/L2 resident'},
+                     'note': 'HBM is not the bound: the 64 KB configuration is L1/L2 resident; algorithmic flop '
+                             'follow SURVEY 8d (27-cell stencil at cell edge rc: 437 candidates x 17 flop per site '
+                             '+ 8 per in-cutoff pair); the kernel itself visits ~200 candidates per site after '
+                             'pruning, see profiles/ for the FP64-pipe counters'},
         'clocks': clocks,
     }
     if cpu_baseline is not None:

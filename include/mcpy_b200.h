@@ -189,10 +189,10 @@ int mcpyb_pcg64_host_doubles(const uint64_t* state_hi_lo, const uint64_t* inc_hi
 /* Measured FP64 FMA throughput of this GPU (TFLOP/s, 2 flop per DFMA): the
  * roofline denominator for the pair kernels.                                 */
 int mcpyb_fp64_peak_tflops(mcpyb_engine* e, double* tflops_out);
-/* Per-stage device time of the LJ trial pipeline (CUDA events between its launches):
- * memset | trial_sites | trial_scan | trial_scatter | row sums | combine.  enable != 0 turns the
+/* Per-stage device time of the batched LJ trial pipeline (CUDA events between its launches):
+ * trial_sites | trial_scan | trial_scatter | row sums | combine.  enable != 0 turns the
  * recording on; every call folds the most recent trial launch into running means (ms).          */
-int mcpyb_stage_timing(mcpyb_engine* e, int enable, double* mean_ms_out6, int64_t* calls_out);
+int mcpyb_stage_timing(mcpyb_engine* e, int enable, double* mean_ms_out5, int64_t* calls_out);
 /* Number of kernels this engine has launched since creation.                 */
 int64_t mcpyb_launch_count(const mcpyb_engine* e);
 

@@ -146,9 +146,9 @@ struct mcpyb_engine {
 
     // instrumentation: CUDA events between the launches of the trial pipeline (mcpyb_stage_timing)
     bool stage_timing = false;
-    cudaEvent_t stage_ev[7] = {};
+    cudaEvent_t stage_ev[6] = {};
     int stage_n = 0;                      // events recorded by the last launch_trials
-    double stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    double stage_ms[5] = {0, 0, 0, 0, 0};
     long long stage_calls = 0;
 
     // trial staging
@@ -691,6 +691,34 @@ int mcpyb_atom_energies_host(mcpyb_engine* e, double* e_atom_out, double* sigma1
 }
 
 // ---- trial moves ---------------------------------------------------------------
+// Per-site partial sums, status words and the slicing shared by every LJ trial path.
+static int prepare_rows_work(mcpyb_engine* e, int nsites, int n_old_total, int n_new_total,
+                             unsigned long long* d_status, TrialWork* wp) {
+    TrialWork& w = *wp;
+    memset(&w, 0, sizeof w);
+    w.nsites = nsites; w.n_old = n_old_total; w.n_new = n_new_total;
+    w.bin_stride = e->max_cells; w.nbins = e->R * e->max_cells;
+    const size_t ns = (size_t)(nsites > 0 ? nsites : 1), nbp = (size_t)w.nbins + 1;
+    // every path cuts a cell's candidate list into the same slices, so a trial's bits do not depend on
+    // the batch it arrives in
+    w.nplanes = e->rb_slices;
+    w.item_shift = RB_SITES_SHIFT;
+    const size_t nsp = ns * (size_t)w.nplanes;
+    CK(e->tw_int.reserve(2 * ns + nsp + 4), "cudaMalloc trial work");
+    CK(e->tw_E.reserve(nsp), "cudaMalloc trial work");
+    if (!e->tw_err.p) {
+        // [0] armed error word, [1] its value after the last launch (both ~0 = none), [2] CTA counter
+        CK(e->tw_err.reserve(3), "cudaMalloc trial status");
+        CK(cudaMemsetAsync(e->tw_err.p, 0xFF, 2 * sizeof(unsigned long long), e->stream), "memset trial status");
+        CK(cudaMemsetAsync(e->tw_err.p + 2, 0, sizeof(unsigned long long), e->stream), "memset trial status");
+    }
+    w.site_trial = e->tw_int.p; w.sorted = e->tw_int.p + ns;
+    w.site_cnt = e->tw_int.p + 2 * ns; w.totals = e->tw_int.p + 2 * ns + nsp;
+    w.site_E = e->tw_E.p;
+    w.err = e->tw_err.p; w.err_out = d_status ? d_status : e->tw_err.p + 1;
+    return MCPYB_OK;
+}
+
 static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int32_t* d_old_off,
                          const int32_t* d_old_idx, const int32_t* d_new_off, const double* d_new_pos,
                          const int32_t* d_new_Z, int n_old_total, int n_new_total,
@@ -716,26 +744,32 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
         return MCPYB_OK;
     }
     TrialWork w;
-    w.nsites = nsites; w.n_old = n_old_total;
-    w.bin_stride = e->max_cells; w.nbins = e->R * e->max_cells;
+    {
+        int rc = prepare_rows_work(e, nsites, n_old_total, n_new_total, d_status, &w);
+        if (rc != MCPYB_OK) return rc;
+    }
     const size_t ns = (size_t)(nsites > 0 ? nsites : 1), nbp = (size_t)w.nbins + 1;
-    // big batches: one CTA per (cell, <= 128 sites) with the stencil staged once (rows_block.cuh);
-    // small ones: warp items split over the stencil z-planes for parallelism (site_kernels.cuh)
-    const bool block_rows = nsites >= 4096;
-    w.nplanes = block_rows ? e->rb_slices : 2 * e->subdiv + 1;
-    w.item_shift = block_rows ? RB_SITES_SHIFT : 5;
-    const size_t nsp = ns * (size_t)w.nplanes;
-    CK(e->tw_int.reserve(2 * ns + nsp + 4), "cudaMalloc trial work");
+    e->stage_n = 0;
+    if (nsites <= RS_MAX_SITES) {
+        // a handful of sites (the one-call-per-trial chain): one launch does everything
+        if (nsites > 0) {
+            lj_trial_small_kernel<<<nsites, RS_THREADS, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs,
+                                                                         (int*)(e->tw_err.p + 2));
+            LAUNCH_CHECK("lj_trial_small_kernel");
+        } else {
+            lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
+            LAUNCH_CHECK("lj_trial_combine_kernel");
+            if (d_status) CK(cudaMemsetAsync(d_status, 0xFF, sizeof(unsigned long long), e->stream), "memset status");
+        }
+        return MCPYB_OK;
+    }
+    // batches: counting sort of the sites by cell, then one CTA per (cell, <= 128 sites, list slice)
     CK(e->tw_bins.reserve(2 * nbp), "cudaMalloc trial bins");
     {
         const size_t had = e->tw_hist.cap;
         CK(e->tw_hist.reserve(nbp * TRIAL_HIST_STRIDE), "cudaMalloc trial histogram");
         if (e->tw_hist.cap != had)           // fresh histogram: zero once, the scan kernel keeps it zero
             CK(cudaMemsetAsync(e->tw_hist.p, 0, e->tw_hist.cap * sizeof(int), e->stream), "memset histogram");
-    }
-    if (!e->tw_err.p) {
-        CK(e->tw_err.reserve(2), "cudaMalloc trial status");
-        CK(cudaMemsetAsync(e->tw_err.p, 0xFF, 2 * sizeof(unsigned long long), e->stream), "memset trial status");
     }
     {
         const size_t had = e->tw_pos.cap;
@@ -744,26 +778,16 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
             CK(cudaMemsetAsync(e->tw_pos.p, 0, e->tw_pos.cap * sizeof(double4), e->stream), "memset trial sites");
     }
     CK(e->tw_a.reserve(ns), "cudaMalloc trial work");
-    CK(e->tw_E.reserve(nsp), "cudaMalloc trial work");
-    w.n_new = n_new_total;
-    w.site_trial = e->tw_int.p; w.sorted = e->tw_int.p + ns;
-    w.site_cnt = e->tw_int.p + 2 * ns; w.totals = e->tw_int.p + 2 * ns + nsp;
     w.hist = e->tw_hist.p; w.bin_count = e->tw_bins.p; w.item_start = e->tw_bins.p + nbp;
-    w.site_pos = e->tw_pos.p; w.site_a = e->tw_a.p; w.site_E = e->tw_E.p;
-    w.err = e->tw_err.p; w.err_out = d_status ? d_status : e->tw_err.p + 1;
+    w.site_pos = e->tw_pos.p; w.site_a = e->tw_a.p;
     e->tw_stamp = (e->tw_stamp % 0x3FFFFFF) + 1;
     w.stamp = e->tw_stamp;
-    w.item_tab = nullptr; w.sorted_pos = nullptr; w.sorted_meta = nullptr;
-    if (block_rows) {
-        const size_t max_items = (ns >> RB_SITES_SHIFT) + (ns < nbp ? ns : nbp) + 1;
-        CK(e->tw_items.reserve(max_items), "cudaMalloc trial items");
-        CK(e->tw_spos.reserve(ns), "cudaMalloc trial work");
-        CK(e->tw_meta.reserve(ns), "cudaMalloc trial work");
-        w.item_tab = e->tw_items.p; w.sorted_pos = e->tw_spos.p; w.sorted_meta = e->tw_meta.p;
-    }
-    e->stage_n = 0;
-    auto mark = [&]() { if (e->stage_timing && e->stage_n < 7) cudaEventRecord(e->stage_ev[e->stage_n++], e->stream); };
-    mark();
+    const size_t max_items = (ns >> RB_SITES_SHIFT) + (ns < nbp ? ns : nbp) + 1;
+    CK(e->tw_items.reserve(max_items), "cudaMalloc trial items");
+    CK(e->tw_spos.reserve(ns), "cudaMalloc trial work");
+    CK(e->tw_meta.reserve(ns), "cudaMalloc trial work");
+    w.item_tab = e->tw_items.p; w.sorted_pos = e->tw_spos.p; w.sorted_meta = e->tw_meta.p;
+    auto mark = [&]() { if (e->stage_timing && e->stage_n < 6) cudaEventRecord(e->stage_ev[e->stage_n++], e->stream); };
     mark();
     trial_sites_kernel<<<(T + 255) / 256, 256, 0, e->stream>>>(e->view(), tb, w);
     LAUNCH_CHECK("trial_sites_kernel");
@@ -771,28 +795,17 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     trial_scan_kernel<<<1, 1024, 0, e->stream>>>(w);
     LAUNCH_CHECK("trial_scan_kernel");
     mark();
-    long long est = ((long long)(nsites >> w.item_shift) + (nsites < w.nbins ? nsites : w.nbins) + 1) * w.nplanes;
-    int rb = (int)((est + SITE_WARPS - 1) / SITE_WARPS);
-    if (rb > 148 * 32) rb = 148 * 32;
-    if (block_rows) rb = (int)(est < 148 * RB_MIN_BLOCKS * 8 ? est : 148 * RB_MIN_BLOCKS * 8);
-    if (nsites > 0) {
-        trial_scatter_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(tb, w);
-        LAUNCH_CHECK("trial_scatter_kernel");
-    }
+    trial_scatter_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(tb, w);
+    LAUNCH_CHECK("trial_scatter_kernel");
     mark();
-    {
-        if (nsites > 0 && block_rows) {
-            lj_trial_rows_block_kernel<RB_UNROLL, RB_MIN_BLOCKS><<<rb, RB_THREADS, 0, e->stream>>>(e->view(), tb, w, e->lj);
-            LAUNCH_CHECK("lj_trial_rows_block_kernel");
-        } else if (nsites > 0) {
-            lj_trial_rows_kernel<<<rb, 32 * SITE_WARPS, 0, e->stream>>>(e->view(), tb, w, e->lj);
-            LAUNCH_CHECK("lj_trial_rows_kernel");
-        }
-        mark();
-        lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
-        LAUNCH_CHECK("lj_trial_combine_kernel");
-        mark();
-    }
+    const long long est = (long long)max_items * w.nplanes;
+    const int rb = (int)(est < 148 * RB_MIN_BLOCKS * 8 ? est : 148 * RB_MIN_BLOCKS * 8);
+    lj_trial_rows_block_kernel<RB_UNROLL, RB_MIN_BLOCKS><<<rb, RB_THREADS, 0, e->stream>>>(e->view(), tb, w, e->lj);
+    LAUNCH_CHECK("lj_trial_rows_block_kernel");
+    mark();
+    lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
+    LAUNCH_CHECK("lj_trial_combine_kernel");
+    mark();
     return MCPYB_OK;
 }
 
@@ -867,12 +880,23 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
         }
         return cudaSuccess;
     };
-    if (rep) CK(stage(o_rep, rep, (size_t)T * 4), "H2D trials");
-    CK(stage(o_oo, old_off, (size_t)(T + 1) * 4), "H2D trials");
-    CK(stage(o_no, new_off, (size_t)(T + 1) * 4), "H2D trials");
-    if (n_old) CK(stage(o_oi, old_idx, (size_t)n_old * 4), "H2D trials");
-    if (n_new && new_Z && e->pot_kind == POT_EMT) CK(stage(o_nz, new_Z, (size_t)n_new * 4), "H2D trials");
-    if (n_new) CK(stage(o_np, new_pos, (size_t)n_new * 24), "H2D trials");
+    const bool small = bytes <= (64u << 10);          // latency path: one H2D, one D2H
+    if (small) {
+        if (rep) memcpy(h + o_rep, rep, (size_t)T * 4);
+        memcpy(h + o_oo, old_off, (size_t)(T + 1) * 4);
+        memcpy(h + o_no, new_off, (size_t)(T + 1) * 4);
+        if (n_old) memcpy(h + o_oi, old_idx, (size_t)n_old * 4);
+        if (n_new && new_Z) memcpy(h + o_nz, new_Z, (size_t)n_new * 4);
+        if (n_new) memcpy(h + o_np, new_pos, (size_t)n_new * 24);
+        CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, e->stream), "H2D trials");
+    } else {
+        if (rep) CK(stage(o_rep, rep, (size_t)T * 4), "H2D trials");
+        CK(stage(o_oo, old_off, (size_t)(T + 1) * 4), "H2D trials");
+        CK(stage(o_no, new_off, (size_t)(T + 1) * 4), "H2D trials");
+        if (n_old) CK(stage(o_oi, old_idx, (size_t)n_old * 4), "H2D trials");
+        if (n_new && new_Z && e->pot_kind == POT_EMT) CK(stage(o_nz, new_Z, (size_t)n_new * 4), "H2D trials");
+        if (n_new) CK(stage(o_np, new_pos, (size_t)n_new * 24), "H2D trials");
+    }
     int rc = launch_trials(e, T, rep ? (const int32_t*)(d + o_rep) : nullptr, (const int32_t*)(d + o_oo), (const int32_t*)(d + o_oi),
                            (const int32_t*)(d + o_no), (const double*)(d + o_np),
                            (new_Z && e->pot_kind == POT_EMT) ? (const int32_t*)(d + o_nz) : nullptr, n_old, n_new, e->dE.p, e->tpairs.p,
@@ -882,14 +906,19 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
     CK(e->trial_out_pin.reserve(ob + pb), "cudaMallocHost trial out");
     // status word first, then dE in two halves: the host copies half 1 out while half 2 is in flight
     const size_t half = ((size_t)T / 2) * sizeof(double), full = (size_t)T * sizeof(double);
-    if (!e->trial_ev) CK(cudaEventCreateWithFlags(&e->trial_ev, cudaEventDisableTiming), "cudaEventCreate");
-    CK(cudaMemcpyAsync(e->trial_out_pin.p + full, e->dE.p + T, sizeof(double), cudaMemcpyDeviceToHost, e->stream), "D2H status");
-    CK(cudaMemcpyAsync(e->trial_out_pin.p, e->dE.p, half, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
-    CK(cudaEventRecord(e->trial_ev, e->stream), "cudaEventRecord");
-    CK(cudaMemcpyAsync(e->trial_out_pin.p + half, (const unsigned char*)e->dE.p + half, full - half, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
-    if (pairs_out) CK(cudaMemcpyAsync(e->trial_out_pin.p + ob, e->tpairs.p, pb, cudaMemcpyDeviceToHost, e->stream), "D2H pairs");
-    CK(cudaEventSynchronize(e->trial_ev), "sync trials (first half)");
-
+    if (small) {
+        CK(cudaMemcpyAsync(e->trial_out_pin.p, e->dE.p, ob, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
+        if (pairs_out) CK(cudaMemcpyAsync(e->trial_out_pin.p + ob, e->tpairs.p, pb, cudaMemcpyDeviceToHost, e->stream), "D2H pairs");
+        CK(cudaStreamSynchronize(e->stream), "sync trials");
+    } else {
+        if (!e->trial_ev) CK(cudaEventCreateWithFlags(&e->trial_ev, cudaEventDisableTiming), "cudaEventCreate");
+        CK(cudaMemcpyAsync(e->trial_out_pin.p + full, e->dE.p + T, sizeof(double), cudaMemcpyDeviceToHost, e->stream), "D2H status");
+        CK(cudaMemcpyAsync(e->trial_out_pin.p, e->dE.p, half, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
+        CK(cudaEventRecord(e->trial_ev, e->stream), "cudaEventRecord");
+        CK(cudaMemcpyAsync(e->trial_out_pin.p + half, (const unsigned char*)e->dE.p + half, full - half, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
+        if (pairs_out) CK(cudaMemcpyAsync(e->trial_out_pin.p + ob, e->tpairs.p, pb, cudaMemcpyDeviceToHost, e->stream), "D2H pairs");
+        CK(cudaEventSynchronize(e->trial_ev), "sync trials (first half)");
+    }
     if (dev_checked) {
         unsigned long long st;
         memcpy(&st, e->trial_out_pin.p + (size_t)T * sizeof(double), sizeof st);
@@ -901,7 +930,7 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
         }
     }
     memcpy(dE_out, e->trial_out_pin.p, half);
-    CK(cudaStreamSynchronize(e->stream), "sync trials");
+    if (!small) CK(cudaStreamSynchronize(e->stream), "sync trials");
     memcpy((unsigned char*)dE_out + half, e->trial_out_pin.p + half, full - half);
     if (pairs_out) memcpy(pairs_out, e->trial_out_pin.p + ob, pb);
     return MCPYB_OK;
@@ -965,10 +994,34 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
         }
         double dE = 0.0;
         const bool keep = e->trk_valid;
-        int rc = mcpyb_trial_delta_e_host(e, 1, nullptr, old_off, old_idx, new_off, new_pos,
+        int rc;
+        if (e->pot_kind == POT_LJ && n_old <= TINY_MAX_MOVED && n_new <= TINY_MAX_MOVED) {
+            // the trial rides in the kernel parameters, the result lands in pinned host memory:
+            // one launch and one stream synchronisation per call
+            TinyTrial tt;
+            memset(&tt, 0, sizeof tt);
+            tt.old_off[1] = n_old; tt.new_off[1] = n_new;
+            for (int k = 0; k < n_old; ++k) tt.old_idx[k] = old_idx[k];
+            for (int k = 0; k < 3 * n_new; ++k) tt.new_pos[k] = new_pos[k];
+            CK(e->trial_out_pin.reserve(64), "cudaMallocHost trial out");
+            double* h_dE = (double*)e->trial_out_pin.p;
+            unsigned long long* h_status = (unsigned long long*)(e->trial_out_pin.p + 8);
+            TrialWork w;
+            rc = prepare_rows_work(e, n_old + n_new, n_old, n_new, h_status, &w);
+            if (rc != MCPYB_OK) return rc;
+            lj_trial_tiny_kernel<<<n_old + n_new, RS_THREADS, 0, e->stream>>>(e->view(), tt, w, e->lj, h_dE,
+                                                                             (int*)(e->tw_err.p + 2));
+            LAUNCH_CHECK("lj_trial_tiny_kernel");
+            CK(cudaStreamSynchronize(e->stream), "sync tiny trial");
+            if (*h_status != ~0ULL) return e->fail(MCPYB_ERR_ARG, "tracked trial rejected on the device (status %llu)", *h_status);
+            dE = *h_dE;
+        } else {
+            rc = mcpyb_trial_delta_e_host(e, 1, nullptr, old_off, old_idx, new_off, new_pos,
                                           numbers ? new_Z : nullptr, &dE, nullptr);
+            e->trk_valid = keep;
+            if (rc != MCPYB_OK) return rc;
+        }
         e->trk_valid = keep;
-        if (rc != MCPYB_OK) return rc;
         if (isfinite(dE) || e->pot_kind == POT_LJ) {      // EMT reports NaN when the box is too thin
             *energy_out = e->trk_E + dE;
             if (path_out) *path_out = 1;
@@ -1234,20 +1287,20 @@ int mcpyb_fp64_peak_tflops(mcpyb_engine* e, double* tflops_out) {
     return MCPYB_OK;
 }
 
-// Stage timing of the LJ trial pipeline: memset | sites | scan | scatter | rows | combine.
+// Stage timing of the batched LJ trial pipeline: sites | scan | scatter | rows | combine.
 // enable != 0 switches event recording on; a later call folds the events of the most recent trial
 // launch into the running sums (after synchronising the stream) and returns the mean ms per stage.
-int mcpyb_stage_timing(mcpyb_engine* e, int enable, double* mean_ms_out6, int64_t* calls_out) {
+int mcpyb_stage_timing(mcpyb_engine* e, int enable, double* mean_ms_out5, int64_t* calls_out) {
     if (!e) return MCPYB_ERR_ARG;
     cudaSetDevice(e->device);
     if (enable && !e->stage_timing) {
-        for (int i = 0; i < 7; ++i) CK(cudaEventCreate(&e->stage_ev[i]), "cudaEventCreate");
+        for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&e->stage_ev[i]), "cudaEventCreate");
         e->stage_timing = true;
         e->stage_n = 0;
     }
-    if (e->stage_timing && e->stage_n == 7) {
+    if (e->stage_timing && e->stage_n == 6) {
         CK(cudaStreamSynchronize(e->stream), "sync stage timing");
-        for (int i = 0; i < 6; ++i) {
+        for (int i = 0; i < 5; ++i) {
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, e->stage_ev[i], e->stage_ev[i + 1]), "cudaEventElapsedTime");
             e->stage_ms[i] += ms;
@@ -1255,11 +1308,11 @@ int mcpyb_stage_timing(mcpyb_engine* e, int enable, double* mean_ms_out6, int64_
         e->stage_calls++;
         e->stage_n = 0;
     }
-    if (mean_ms_out6)
-        for (int i = 0; i < 6; ++i) mean_ms_out6[i] = e->stage_calls ? e->stage_ms[i] / (double)e->stage_calls : 0.0;
+    if (mean_ms_out5)
+        for (int i = 0; i < 5; ++i) mean_ms_out5[i] = e->stage_calls ? e->stage_ms[i] / (double)e->stage_calls : 0.0;
     if (calls_out) *calls_out = e->stage_calls;
     if (!enable && e->stage_timing) {
-        for (int i = 0; i < 7; ++i) cudaEventDestroy(e->stage_ev[i]);
+        for (int i = 0; i < 6; ++i) cudaEventDestroy(e->stage_ev[i]);
         e->stage_timing = false;
     }
     return MCPYB_OK;

@@ -40,27 +40,96 @@
 
 template <int N> struct IntC { static constexpr int value = N; };
 
+// The stencil of a cell as contiguous pieces of the cell-sorted array: rows (y, z offsets, z-plane major),
+// each a main piece (image shift 0 along x) and the piece that wraps around the periodic x boundary.
+struct RbPieces {
+    int pbeg[RB_MAXPIECES];                     // first cell-sorted slot of the piece
+    int pstart[RB_MAXPIECES + 1];               // offset of the piece in the stencil's candidate list
+    int pS[RB_MAXPIECES];                       // image shift of the piece (pack_wraps)
+    double pshift[RB_MAXPIECES][3];             // S @ cell
+    int total;                                  // candidates in the stencil
+};
+
 struct RowsBlockSmem {
     double4 candd[RB_CAND];                     // q + S@cell (exact, unfused), .w = tag
     int cinfo[RB_CAND];                         // cell-sorted slot | piece << 24 (borderline re-check)
-    int pbeg[RB_MAXPIECES];                     // first cell-sorted slot of the piece
-    int pstart[RB_MAXPIECES + 1];               // staged offset of the piece
-    int pS[RB_MAXPIECES];                       // image shift of the piece (pack_wraps)
-    double pshift[RB_MAXPIECES][3];             // S @ cell
+    RbPieces pc;
     float wbox[RB_WARPS][6];                    // per-warp bounding boxes of the sites
     int wcnt[RB_WARPS];                         // survivors per warp of a staging round
-    int total;
 };
+
+// Lane l of the calling warp owns rows 2l, 2l+1 = pieces 4l .. 4l+3 (needs 2 * rows <= RB_MAXPIECES and
+// a box at least as wide as the stencil along x).
+__device__ __forceinline__ void rb_build_pieces(RbPieces& pc, const GridDesc& g, const int* __restrict__ cstart,
+                                        int c0, int c1, int c2, int lane) {
+    const int n0 = g.ncell[0], n1 = g.ncell[1], n2 = g.ncell[2];
+    const int m0 = g.m[0], m1 = g.m[1], m2 = g.m[2];
+    const int wr1 = 2 * m1 + 1, wr2 = 2 * m2 + 1, nrows = wr1 * wr2;
+    const bool perx = g.pbc[0] != 0;
+
+    int beg[4] = {0, 0, 0, 0}, len[4] = {0, 0, 0, 0}, Sx[4] = {0, 0, 0, 0}, Sy[2] = {0, 0}, Sz[2] = {0, 0};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int row = 2 * lane + j;
+        if (row < nrows) {
+            int cy = c1 + (row % wr1) - m1, cz = c2 + (row / wr1) - m2;
+            bool valid = true;
+            if (g.pbc[1]) { Sy[j] = floor_div(cy, n1); cy -= Sy[j] * n1; }
+            else if (cy < 0 || cy >= n1) valid = false;
+            if (g.pbc[2]) { Sz[j] = floor_div(cz, n2); cz -= Sz[j] * n2; }
+            else if (cz < 0 || cz >= n2) valid = false;
+            if (valid) {
+                const int rowoff = (cz * n1 + cy) * n0;
+                const int lo = c0 - m0, hi = c0 + m0;
+                const int a0 = max(lo, 0), a1 = min(hi, n0 - 1);
+                beg[2 * j] = cstart[rowoff + a0];
+                len[2 * j] = cstart[rowoff + a1 + 1] - beg[2 * j];
+                if (perx) {
+                    if (lo < 0) {
+                        beg[2 * j + 1] = cstart[rowoff + lo + n0];
+                        len[2 * j + 1] = cstart[rowoff + n0] - beg[2 * j + 1];
+                        Sx[2 * j + 1] = -1;
+                    } else if (hi >= n0) {
+                        beg[2 * j + 1] = cstart[rowoff];
+                        len[2 * j + 1] = cstart[rowoff + hi - n0 + 1] - beg[2 * j + 1];
+                        Sx[2 * j + 1] = 1;
+                    }
+                }
+            }
+        }
+    }
+    const int mine = len[0] + len[1] + len[2] + len[3];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    int base = incl - mine;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ip = 4 * lane + j;
+        if (ip < 2 * nrows) {
+            pc.pstart[ip] = base;
+            pc.pbeg[ip] = beg[j];
+            pc.pS[ip] = pack_wraps(Sx[j], Sy[j >> 1], Sz[j >> 1]);
+            double ax, ay, az;
+            shift_vec(g, Sx[j], Sy[j >> 1], Sz[j >> 1], ax, ay, az);
+            pc.pshift[ip][0] = ax; pc.pshift[ip][1] = ay; pc.pshift[ip][2] = az;
+        }
+        base += len[j];
+    }
+    if (lane == 31) { pc.pstart[2 * nrows] = incl; pc.total = incl; }
+}
 
 // r2 of staged candidate i against a site in the oracle's exact arithmetic: image shift
 // T = S_piece + w_site - w_j rebuilt from the raw record, unfused (dx*dx + dy*dy) + dz*dz.
 __device__ __noinline__ double rb_exact_r2(const GridDesc& g, const double4* __restrict__ spos,
-                                           const RowsBlockSmem& sm, int i, double px, double py, double pz,
+                                           const RbPieces& pc, int packed, double px, double py, double pz,
                                            int wsite) {
-    const int packed = sm.cinfo[i];
     const double4 q = spos[packed & 0xFFFFFF];
     int sx, sy, sz, jx, jy, jz, w0, w1, w2;
-    unpack_wraps(sm.pS[packed >> 24], sx, sy, sz);
+    unpack_wraps(pc.pS[packed >> 24], sx, sy, sz);
     unpack_wraps(tag_wraps(tag_of(q)), jx, jy, jz);
     unpack_wraps(wsite, w0, w1, w2);
     double ax, ay, az, dx, dy, dz;
@@ -135,64 +204,10 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
             if (active && slice == 0)
                 rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, acc12, acc6, cnt);
         } else {
-            // ---- stencil pieces: lane l of warp 0 owns rows 2l, 2l+1 = pieces 4l .. 4l+3
-            if (wid == 0) {
-                int beg[4] = {0, 0, 0, 0}, len[4] = {0, 0, 0, 0}, Sx[4] = {0, 0, 0, 0}, Sy[2] = {0, 0}, Sz[2] = {0, 0};
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int row = 2 * lane + j;
-                    if (row < nrows) {
-                        int cy = c1 + (row % wr1) - m1, cz = c2 + (row / wr1) - m2;
-                        bool valid = true;
-                        if (g.pbc[1]) { Sy[j] = floor_div(cy, n1); cy -= Sy[j] * n1; }
-                        else if (cy < 0 || cy >= n1) valid = false;
-                        if (g.pbc[2]) { Sz[j] = floor_div(cz, n2); cz -= Sz[j] * n2; }
-                        else if (cz < 0 || cz >= n2) valid = false;
-                        if (valid) {
-                            const int rowoff = (cz * n1 + cy) * n0;
-                            const int lo = c0 - m0, hi = c0 + m0;
-                            const int a0 = max(lo, 0), a1 = min(hi, n0 - 1);
-                            beg[2 * j] = cstart[rowoff + a0];
-                            len[2 * j] = cstart[rowoff + a1 + 1] - beg[2 * j];
-                            if (perx) {
-                                if (lo < 0) {
-                                    beg[2 * j + 1] = cstart[rowoff + lo + n0];
-                                    len[2 * j + 1] = cstart[rowoff + n0] - beg[2 * j + 1];
-                                    Sx[2 * j + 1] = -1;
-                                } else if (hi >= n0) {
-                                    beg[2 * j + 1] = cstart[rowoff];
-                                    len[2 * j + 1] = cstart[rowoff + hi - n0 + 1] - beg[2 * j + 1];
-                                    Sx[2 * j + 1] = 1;
-                                }
-                            }
-                        }
-                    }
-                }
-                const int mine = len[0] + len[1] + len[2] + len[3];
-                int incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                int base = incl - mine;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int pc = 4 * lane + j;
-                    if (pc < 2 * nrows) {
-                        sm.pstart[pc] = base;
-                        sm.pbeg[pc] = beg[j];
-                        sm.pS[pc] = pack_wraps(Sx[j], Sy[j >> 1], Sz[j >> 1]);
-                        double ax, ay, az;
-                        shift_vec(g, Sx[j], Sy[j >> 1], Sz[j >> 1], ax, ay, az);
-                        sm.pshift[pc][0] = ax; sm.pshift[pc][1] = ay; sm.pshift[pc][2] = az;
-                    }
-                    base += len[j];
-                }
-                if (lane == 31) { sm.pstart[2 * nrows] = incl; sm.total = incl; }
-            }
+            // ---- stencil pieces (warp 0)
+            if (wid == 0) rb_build_pieces(sm.pc, g, cstart, c0, c1, c2, lane);
             __syncthreads();
-            const int total = sm.total, npieces = 2 * nrows;
+            const int total = sm.pc.total, npieces = 2 * nrows;
 
             // ---- per-lane constants.  The loop works with the site wrapped into the primary cell
             // (qx, qy, qz) and a fused r2; both differ from the oracle's value by rounding only.
@@ -266,16 +281,16 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
                         int lo = 0, hi = npieces;                 // pstart[lo] <= gi < pstart[hi]
                         while (hi - lo > 1) {
                             const int mid = (lo + hi) >> 1;
-                            if (sm.pstart[mid] <= gi) lo = mid; else hi = mid;
+                            if (sm.pc.pstart[mid] <= gi) lo = mid; else hi = mid;
                         }
-                        const int k = sm.pbeg[lo] + (gi - sm.pstart[lo]);
+                        const int k = sm.pc.pbeg[lo] + (gi - sm.pc.pstart[lo]);
                         q = spos[k];
-                        double ax = sm.pshift[lo][0], ay = sm.pshift[lo][1], az = sm.pshift[lo][2];
+                        double ax = sm.pc.pshift[lo][0], ay = sm.pc.pshift[lo][1], az = sm.pc.pshift[lo][2];
                         const long long tag = tag_of(q);
                         const int wj = tag_wraps(tag);
                         if (wj != pack_wraps(0, 0, 0)) {          // atom stored outside the primary cell
                             int sx, sy, sz, jx, jy, jz;
-                            unpack_wraps(sm.pS[lo], sx, sy, sz);
+                            unpack_wraps(sm.pc.pS[lo], sx, sy, sz);
                             unpack_wraps(wj, jx, jy, jz);
                             shift_vec(g, sx - jx, sy - jy, sz - jz, ax, ay, az);
                         }
@@ -333,7 +348,7 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
                                 in[u] = rb < lo_bits;
                                 // within rounding of the cutoff: the oracle's arithmetic decides
                                 if (!in[u] && rb <= hi_bits)
-                                    in[u] = rb_exact_r2(g, spos, sm, i + u, px, py, pz, wsite) <= p.rc2;
+                                    in[u] = rb_exact_r2(g, spos, sm.pc, sm.cinfo[i + u], px, py, pz, wsite) <= p.rc2;
                                 if (multi && in[u])
                                     for (int e = ob + 1; e < oe; ++e) if (tb.old_idx[e] == jj[u]) in[u] = false;
                             }
@@ -365,4 +380,192 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
         }
         __syncthreads();                                          // the piece table is rewritten next
     }
+}
+
+// ---------------------------------------------------------------------------
+// Small batches (the one-call-per-trial pattern of GrandCanonicalEnsemble.do_gcmc_step, a handful of
+// sites): ONE launch.  One CTA per site spreads the stencil's candidates over its threads, evaluates
+// them with the arithmetic of the kernel above (wrapped site, fused r2, bit-pattern membership with
+// the exact re-check, same reciprocal and c6), leaves c6 of every candidate (0 for a miss) in shared
+// memory in list order, and one thread per slice then runs the same sequential accumulation
+// acc12 = fma(c6, c6, acc12), acc6 += c6 -- so a site's partial sums carry the same bits as in a large
+// batch.  The last CTA to finish (threadfence + counter) combines the rows into dE for every trial and
+// publishes the validation status: no histogram, scan, scatter or separate combine launch.
+// ---------------------------------------------------------------------------
+#define RS_THREADS 128
+#define RS_MAX_SITES 128           // batches up to this many sites take the single-launch kernel
+#define RS_CAND 1024              // candidates of one stencil held in shared memory per chunk
+
+struct RowsSmallSmem {
+    RbPieces pc;
+    double c6[RS_CAND];
+    unsigned char hit[RS_CAND];
+    double part12[8], part6[8];
+    int partc[8];
+    int last;
+};
+
+__device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const BatchView& b, const TrialBatch& tb,
+                                                    const TrialWork& w, const LJParams& p,
+                                                    double* __restrict__ dE, int* __restrict__ npairs,
+                                                    int* __restrict__ done_counter) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int s = blockIdx.x;                          // site: [0, n_old) old, then new
+    const int nq = w.nplanes;
+    // ---- owning trial (T is small: binary search over the offsets)
+    const bool is_old = s < w.n_old;
+    const int t = is_old ? owner_of(tb.old_off, tb.T, s) : owner_of(tb.new_off, tb.T, s - w.n_old);
+    const int r = tb.rep ? tb.rep[t] : 0;
+    const int ob = tb.old_off[t], oe = tb.old_off[t + 1];
+    const int nb = tb.new_off[t], ne = tb.new_off[t + 1];
+    bool ok = !trial_invalid(b, tb, w, r, ob, oe, nb, ne);
+    ok = ok && (is_old ? (s >= ob && s < oe) : (s - w.n_old >= nb && s - w.n_old < ne));
+    double acc12[8], acc6[8];
+    int cnt[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { acc12[q] = 0.0; acc6[q] = 0.0; cnt[q] = 0; }
+    if (ok) {
+        const GridDesc& g = b.grid[r];
+        const int off = g.atom_off;
+        const int* cstart = b.cell_start + (size_t)r * b.cs_stride;
+        const double4* spos = b.spos + off;
+        double px, py, pz;
+        if (is_old) { const double4 q = b.upos[off + tb.old_idx[s]]; px = q.x; py = q.y; pz = q.z; }
+        else { const int k = s - w.n_old; px = tb.new_pos[3 * k]; py = tb.new_pos[3 * k + 1]; pz = tb.new_pos[3 * k + 2]; }
+        int c[3], wr[3];
+        locate(g, px, py, pz, c, wr);
+        const int wsite = pack_wraps(wr[0], wr[1], wr[2]);
+        const int n0 = g.ncell[0], m0 = g.m[0];
+        const int nrows = (2 * g.m[1] + 1) * (2 * g.m[2] + 1);
+        const bool fast = (!g.pbc[0] || n0 >= 2 * m0 + 1) && 2 * nrows <= RB_MAXPIECES;
+        if (!fast) {
+            if (tid == 0) rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, acc12[0], acc6[0], cnt[0]);
+        } else {
+            if (wid == 0) rb_build_pieces(sm.pc, g, cstart, c[0], c[1], c[2], lane);
+            __syncthreads();
+            const int total = sm.pc.total, npieces = 2 * nrows;
+            // per-site constants, as in lj_trial_rows_block_kernel
+            double qx = px, qy = py, qz = pz, band = 16.0;
+            if (wsite != pack_wraps(0, 0, 0)) {
+                const double a = (double)wr[0], bb = (double)wr[1], cc = (double)wr[2];
+                qx = px - (a * g.cell[0] + bb * g.cell[3] + cc * g.cell[6]);
+                qy = py - (a * g.cell[1] + bb * g.cell[4] + cc * g.cell[7]);
+                qz = pz - (a * g.cell[2] + bb * g.cell[5] + cc * g.cell[8]);
+                band += 64.0 * (fabs(px) + fabs(py) + fabs(pz) + fabs(qx) + fabs(qy) + fabs(qz)) / p.rc;
+            }
+            const double bw = p.rc2 * band * 2.220446049250313e-16;
+            const long long lo_bits = __double_as_longlong(p.rc2 - bw), hi_bits = __double_as_longlong(p.rc2 + bw);
+            for (int cbase = 0; cbase < total; cbase += RS_CAND) {
+                const int n = min(RS_CAND, total - cbase);
+                for (int i = tid; i < n; i += RS_THREADS) {
+                    const int gi = cbase + i;
+                    int lo = 0, hi = npieces;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (sm.pc.pstart[mid] <= gi) lo = mid; else hi = mid;
+                    }
+                    const int k = sm.pc.pbeg[lo] + (gi - sm.pc.pstart[lo]);
+                    double4 q = spos[k];
+                    double ax = sm.pc.pshift[lo][0], ay = sm.pc.pshift[lo][1], az = sm.pc.pshift[lo][2];
+                    const long long tag = tag_of(q);
+                    const int wj = tag_wraps(tag);
+                    if (wj != pack_wraps(0, 0, 0)) {
+                        int sx, sy, sz, jx, jy, jz;
+                        unpack_wraps(sm.pc.pS[lo], sx, sy, sz);
+                        unpack_wraps(wj, jx, jy, jz);
+                        shift_vec(g, sx - jx, sy - jy, sz - jz, ax, ay, az);
+                    }
+                    const double dx = __dadd_rn(q.x, ax) - qx, dy = __dadd_rn(q.y, ay) - qy, dz = __dadd_rn(q.z, az) - qz;
+                    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    const long long rb = __double_as_longlong(r2);
+                    bool in = rb < lo_bits;
+                    if (!in && rb <= hi_bits) in = rb_exact_r2(g, spos, sm.pc, k | (lo << 24), px, py, pz, wsite) <= p.rc2;
+                    const int j = tag_index(tag);
+                    for (int e = ob; e < oe; ++e) if (tb.old_idx[e] == j) in = false;
+                    double c6 = 0.0;
+                    if (in) { const double tt = p.sigma2 * fast_rcp(r2); c6 = tt * tt * tt; }
+                    sm.c6[i] = c6;
+                    sm.hit[i] = in ? 1 : 0;
+                }
+                __syncthreads();
+                // slice q of the list covers [total*q/nq, total*(q+1)/nq): thread q accumulates it in order
+                if (tid < nq && tid < 8) {
+                    const int cf = (int)(((long long)total * tid) / nq), cl = (int)(((long long)total * (tid + 1)) / nq);
+                    const int i0 = max(cf, cbase) - cbase, i1 = min(cl, cbase + n) - cbase;
+                    double a12 = 0.0, a6 = 0.0;
+                    int cc = 0;
+                    // carried across chunks through the registers of thread q (static indexing)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (q == tid) { a12 = acc12[q]; a6 = acc6[q]; cc = cnt[q]; }
+                    for (int i = i0; i < i1; ++i) {
+                        const double c6 = sm.c6[i];
+                        a12 = fma(c6, c6, a12);
+                        a6 += c6;
+                        cc += sm.hit[i];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (q == tid) { acc12[q] = a12; acc6[q] = a6; cnt[q] = cc; }
+                }
+                __syncthreads();
+            }
+        }
+        // thread q holds slice q (generic path: thread 0 holds everything in slice 0)
+        if (tid < nq && tid < 8) {
+            double a12 = 0.0, a6 = 0.0;
+            int cc = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (q == tid) { a12 = acc12[q]; a6 = acc6[q]; cc = cnt[q]; }
+            w.site_E[(size_t)s * nq + tid] = fma(p.eps4, a12 - a6, -p.e0 * (double)cc);
+            w.site_cnt[(size_t)s * nq + tid] = cc;
+        }
+    }
+    // ---- the last CTA to arrive combines every trial
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sm.last = (atomicAdd(done_counter, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!sm.last) return;
+    __threadfence();
+    unsigned long long first_bad = ~0ULL;
+    for (int tt = tid; tt < tb.T; tt += RS_THREADS) {
+        const int rr = tb.rep ? tb.rep[tt] : 0;
+        const int bad = trial_invalid(b, tb, w, rr, tb.old_off[tt], tb.old_off[tt + 1], tb.new_off[tt], tb.new_off[tt + 1]);
+        if (bad) first_bad = min(first_bad, ((unsigned long long)tt << 8) | (unsigned long long)bad);
+        combine_trial(b, tb, w, p, tt, dE, npairs);
+    }
+    if (first_bad != ~0ULL) atomicMin(w.err, first_bad);
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long ev = *w.err;
+        if (w.err_out) *w.err_out = ev;
+        *w.err = ~0ULL;
+        *done_counter = 0;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+lj_trial_small_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p,
+                      double* __restrict__ dE, int* __restrict__ npairs, int* __restrict__ done_counter) {
+    __shared__ RowsSmallSmem sm;
+    lj_trial_small_body(sm, b, tb, w, p, dE, npairs, done_counter);
+}
+
+// One trial whose description travels in the kernel's parameter space and whose result is written
+// straight into pinned host memory: no H2D or D2H copy on the latency-bound single-chain path
+// (mcpyb_tracked_energy_host).
+#define TINY_MAX_MOVED 8
+struct TinyTrial {
+    int old_off[2], new_off[2];
+    int old_idx[TINY_MAX_MOVED];
+    double new_pos[3 * TINY_MAX_MOVED];
+};
+
+__global__ void __launch_bounds__(RS_THREADS)
+lj_trial_tiny_kernel(BatchView b, const __grid_constant__ TinyTrial tt, TrialWork w, LJParams p,
+                     double* __restrict__ dE_host, int* __restrict__ done_counter) {
+    __shared__ RowsSmallSmem sm;
+    TrialBatch tb;
+    tb.T = 1; tb.rep = nullptr; tb.old_off = tt.old_off; tb.old_idx = tt.old_idx;
+    tb.new_off = tt.new_off; tb.new_pos = tt.new_pos; tb.new_Z = nullptr;
+    lj_trial_small_body(sm, b, tb, w, p, dE_host, nullptr, done_counter);
 }

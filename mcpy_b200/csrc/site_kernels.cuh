@@ -376,11 +376,11 @@ lj_fold_planes_kernel(int total_atoms, int nplanes, const double* __restrict__ e
 }
 
 // ---------------------------------------------------------------------------
-// K3 / K6 (second generation): batched trial moves in five small launches.
-//   1 trial_sites_kernel   one thread per site: position, owning trial, bin = (replica, cell)
-//   2 trial_scan_kernel    one CTA: exclusive scans of the bin histogram -> bin_start, item_start
-//   3 trial_scatter_kernel sites to their bin
-//   4 lj_trial_rows_kernel one warp per (bin, chunk of 32 sites): row sums, one site per lane
+// K3 / K6: batched trial moves in five launches (a handful of sites: one, lj_trial_small_kernel).
+//   1 trial_sites_kernel   one thread per trial: its sites' positions, bin = (replica, cell), rank in the bin
+//   2 trial_scan_kernel    one CTA: exclusive scans of the bin histogram -> bin_start, work items
+//   3 trial_scatter_kernel site records to their bin
+//   4 lj_trial_rows_block_kernel (rows_block.cuh)  one CTA per (bin, <= 128 sites, list slice): row sums
 //   5 lj_trial_combine_kernel  one thread per trial: sum(new rows) - sum(old rows) + moved-set pairs
 // ---------------------------------------------------------------------------
 #define TRIAL_HIST_STRIDE 8
@@ -531,59 +531,10 @@ trial_scatter_kernel(TrialBatch tb, TrialWork w) {
     }
 }
 
-__global__ void __launch_bounds__(32 * SITE_WARPS, SITE_MIN_BLOCKS)
-lj_trial_rows_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) {
-    __shared__ SiteScratch s_scratch[SITE_WARPS];
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int nwork = w.totals[0] * w.nplanes;
-    for (int wi = warp; wi < nwork; wi += nwarps) {
-        const int item = wi / w.nplanes, plane = wi - item * w.nplanes;
-        const int bin = upper_cell_of_item(w.item_start, w.nbins, item);
-        const int chunk = item - w.item_start[bin];
-        const int r = bin / w.bin_stride, c = bin - r * w.bin_stride;
-        const GridDesc& g = b.grid[r];
-        const int off = g.atom_off;
-        const int* cstart = b.cell_start + (size_t)r * b.cs_stride;
-        const int k = w.bin_count[bin] + chunk * 32 + lane;
-        const bool active = k < w.bin_count[bin + 1];
-        int s = 0, ob = 0, oe = 0, ex0 = -1;
-        double4 me = make_double4(0.0, 0.0, 0.0, 0.0);
-        if (active) {
-            s = w.sorted[k];
-            me = w.site_pos[s];
-            const int t = w.site_trial[s];
-            ob = tb.old_off[t]; oe = tb.old_off[t + 1];
-            if (oe > ob) ex0 = tb.old_idx[ob];
-        }
-        const int n0 = g.ncell[0], n1 = g.ncell[1];
-        const int c0 = c % n0, c1 = (c / n0) % n1, c2 = c / (n0 * n1);
-        const int wsite = active ? (int)(__double_as_longlong(me.w) & 0xFFFFFFFFLL) : pack_wraps(0, 0, 0);
-        double acc = 0.0, tot = 0.0;
-        int cnt = 0;
-        const bool multi = (oe - ob) > 1;
-        auto excl = [&](int j) {
-            if (j == ex0) return true;
-            if (multi) for (int e = ob + 1; e < oe; ++e) if (tb.old_idx[e] == j) return true;
-            return false;
-        };
-        site_rowsum(g, b.spos + off, b.fpos + off, cstart, c0, c1, c2, lane, active, me.x, me.y, me.z,
-                    wsite, -1, plane, w.nplanes, s_scratch[threadIdx.x >> 5],
-                    [&](double r2) { return r2 <= p.rc2; },
-                    [&](const double4& q, double, double, double, double r2) {
-                        if (!excl(tag_index(tag_of(q)))) { acc += lj_pair(p, r2); ++cnt; }
-                    },
-                    [&]() { tot += acc; acc = 0.0; });
-        if (active) { w.site_E[(size_t)s * w.nplanes + plane] = tot; w.site_cnt[(size_t)s * w.nplanes + plane] = cnt; }
-    }
-}
-
-__global__ void __launch_bounds__(128)
-lj_trial_combine_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p,
-                        double* __restrict__ dE, int* __restrict__ npairs) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= tb.T) return;
+// dE of one trial from its sites' partial row sums: sum(new rows) - sum(old rows) + moved-set pairs.
+__device__ __forceinline__ void combine_trial(const BatchView& b, const TrialBatch& tb, const TrialWork& w,
+                                              const LJParams& p, int t, double* __restrict__ dE,
+                                              int* __restrict__ npairs) {
     const int r = tb.rep ? tb.rep[t] : 0;
     const int ob = tb.old_off[t], oe = tb.old_off[t + 1];
     const int nb = tb.new_off[t], ne = tb.new_off[t + 1];
@@ -624,4 +575,12 @@ lj_trial_combine_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p,
         }, 0, 1, minus, cnt);
     dE[t] = plus - minus;
     if (npairs) npairs[t] = cnt;
+}
+
+__global__ void __launch_bounds__(128)
+lj_trial_combine_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p,
+                        double* __restrict__ dE, int* __restrict__ npairs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tb.T) return;
+    combine_trial(b, tb, w, p, t, dE, npairs);
 }

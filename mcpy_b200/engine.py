@@ -65,11 +65,11 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.mcpyb_launch_count(self._h))
 
-    STAGES = ('memset', 'trial_sites', 'trial_scan', 'trial_scatter', 'row_sums', 'combine')
+    STAGES = ('trial_sites', 'trial_scan', 'trial_scatter', 'row_sums', 'combine')
 
     def stage_timing(self, enable=True):
         """Fold the last trial launch into the per-stage running means; returns ``({stage: ms}, calls)``."""
-        out = np.zeros(6)
+        out = np.zeros(5)
         calls = C.c_int64(0)
         self._check(self._lib.mcpyb_stage_timing(self._h, 1 if enable else 0, out.ctypes.data, C.byref(calls)))
         return dict(zip(self.STAGES, out.tolist())), int(calls.value)
