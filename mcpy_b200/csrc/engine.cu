@@ -1196,7 +1196,11 @@ int mcpyb_sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
     rng.state = ((u128)state_hi_lo[0] << 64) | (u128)state_hi_lo[1];
     rng.inc = ((u128)inc_hi_lo[0] << 64) | (u128)inc_hi_lo[1];
     const long long Mc = (long long)(1.5 * (double)P) + 1;          // int(1.5 * n) + 1 candidates per pass
-    const long long nthreads = (Mc + PCG_CHUNK - 1) / PCG_CHUNK;
+    // short chunks while the problem is small (more threads to hide the stencil-walk latency), long ones
+    // once there are threads to spare
+    const int chunk = Mc >= (4LL << 20) ? 8 : 2;
+    const PcgStrideTable tbl = pcg_stride_table(rng.inc, chunk);
+    const long long nthreads = (Mc + chunk - 1) / chunk;
     const int blocks = (int)((nthreads + PCG_BLOCK - 1) / PCG_BLOCK);
     CK(e->pcg_count.reserve((size_t)blocks), "cudaMalloc pcg");
     CK(e->pcg_prefix.reserve((size_t)blocks), "cudaMalloc pcg");
@@ -1211,11 +1215,14 @@ int mcpyb_sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
         // two passes are enough in all but astronomically unlikely cases; launch them back to back,
         // then look (a pass that is not needed consumes no random numbers)
         for (int k = 0; k < 2; ++k) {
-            pcg_sphere_count_kernel<<<blocks, PCG_BLOCK, 0, e->stream>>>(rng, Mc, radius, P, e->pcg_ctl.p, e->pcg_count.p);
+            if (chunk == 8) pcg_sphere_count_kernel<8><<<blocks, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, P, e->pcg_ctl.p, e->pcg_count.p);
+            else pcg_sphere_count_kernel<2><<<blocks, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, P, e->pcg_ctl.p, e->pcg_count.p);
             LAUNCH_CHECK("pcg_sphere_count_kernel");
             pcg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->pcg_count.p, e->pcg_prefix.p, blocks, e->pcg_ctl.p);
             LAUNCH_CHECK("pcg_scan_kernel");
-            pcg_sphere_eval_kernel<<<blocks, PCG_BLOCK, 0, e->stream>>>(rng, Mc, radius, P, cx, cy, cz, e->pcg_ctl.p,
+            if (chunk == 8) pcg_sphere_eval_kernel<8><<<blocks, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, P, cx, cy, cz, e->pcg_ctl.p,
+                e->pcg_prefix.p, e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
+            else pcg_sphere_eval_kernel<2><<<blocks, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, P, cx, cy, cz, e->pcg_ctl.p,
                 e->pcg_prefix.p, e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
             LAUNCH_CHECK("pcg_sphere_eval_kernel");
             pcg_sphere_commit_kernel<<<1, 1, 0, e->stream>>>(e->pcg_ctl.p, P);
@@ -1253,8 +1260,13 @@ int mcpyb_box_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo, co
     rng.inc = ((u128)inc_hi_lo[0] << 64) | (u128)inc_hi_lo[1];
     CK(cudaMemsetAsync(e->fv_counts.p, 0, 2 * sizeof(unsigned long long), e->stream), "memset counts");
     if (P > 0) {
-        const long long nthreads = (P + PCG_CHUNK - 1) / PCG_CHUNK;
-        pcg_box_eval_kernel<<<(int)((nthreads + PCG_BLOCK - 1) / PCG_BLOCK), PCG_BLOCK, 0, e->stream>>>(rng, P, e->fv_small.p + 84,
+        const int chunk = P >= (4LL << 20) ? 8 : 2;
+        const PcgStrideTable tbl = pcg_stride_table(rng.inc, chunk);
+        const long long nthreads = (P + chunk - 1) / chunk;
+        const int nblk = (int)((nthreads + PCG_BLOCK - 1) / PCG_BLOCK);
+        if (chunk == 8) pcg_box_eval_kernel<8><<<nblk, PCG_BLOCK, 0, e->stream>>>(rng, tbl, P, e->fv_small.p + 84,
+            e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
+        else pcg_box_eval_kernel<2><<<nblk, PCG_BLOCK, 0, e->stream>>>(rng, tbl, P, e->fv_small.p + 84,
             e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
         LAUNCH_CHECK("pcg_box_eval_kernel");
     }

@@ -165,22 +165,32 @@ __device__ __forceinline__ bool fv_point_covered(const FvGrid& g, const double4*
     const int cx = (int)floor(fmax(-2.0, fmin((px - g.lo[0]) * g.inv_edge[0], (double)g.ncell[0] + 1.0)));
     const int cy = (int)floor(fmax(-2.0, fmin((py - g.lo[1]) * g.inv_edge[1], (double)g.ncell[1] + 1.0)));
     const int cz = (int)floor(fmax(-2.0, fmin((pz - g.lo[2]) * g.inv_edge[2], (double)g.ncell[2] + 1.0)));
-    for (int oz = -1; oz <= 1; ++oz) {
-        const int z = cz + oz;
-        if (z < 0 || z >= g.ncell[2]) continue;
-        for (int oy = -1; oy <= 1; ++oy) {
-            const int y = cy + oy;
-            if (y < 0 || y >= g.ncell[1]) continue;
-            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.ncell[0] - 1);
-            if (x0 > x1) continue;
+    // nine rows of three x-adjacent cells, the point's own row first (a covered point is usually covered
+    // by an atom of its own neighbourhood -- the answer is an any(), so the order is free); all eighteen
+    // row bounds are fetched before the first sphere so their latencies overlap
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.ncell[0] - 1);
+    if (x0 > x1) return false;
+    int beg[9], end[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        // order: (0,0) (0,-1) (0,1) (-1,0) (1,0) (-1,-1) (-1,1) (1,-1) (1,1) as (oy, oz)
+        const int oy = (r == 3 || r == 5 || r == 6) ? -1 : ((r == 4 || r == 7 || r == 8) ? 1 : 0);
+        const int oz = (r == 1 || r == 5 || r == 7) ? -1 : ((r == 2 || r == 6 || r == 8) ? 1 : 0);
+        const int y = cy + oy, z = cz + oz;
+        beg[r] = 0; end[r] = 0;
+        if (y >= 0 && y < g.ncell[1] && z >= 0 && z < g.ncell[2]) {
             const int row = (z * g.ncell[1] + y) * g.ncell[0];
-            const int beg = cell_start[row + x0], end = cell_start[row + x1 + 1];
-            for (int k = beg; k < end; ++k) {
-                const double4 s = spheres[k];
-                const double dx = __dsub_rn(px, s.x), dy = __dsub_rn(py, s.y), dz = __dsub_rn(pz, s.z);
-                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if (d2 < s.w) return true;
-            }
+            beg[r] = cell_start[row + x0];
+            end[r] = cell_start[row + x1 + 1];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        for (int k = beg[r]; k < end[r]; ++k) {
+            const double4 s = spheres[k];
+            const double dx = __dsub_rn(px, s.x), dy = __dsub_rn(py, s.y), dz = __dsub_rn(pz, s.z);
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (d2 < s.w) return true;
         }
     }
     return false;

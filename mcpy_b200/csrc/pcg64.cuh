@@ -9,7 +9,7 @@
 //     (tests/test_pcg64.py pins this against numpy itself) -- first P kept, in stream order.
 //   CustomCell.calculate_volume (custom_cell.py:74-75): rng.random((P,3)) @ dimensions,
 //     evaluated by the BLAS as fma(u2, d2c, fma(u1, d1c, u0*d0c)) (exact for diagonal cells).
-// Each thread jumps the LCG to its chunk of the stream (O(log n) 128-bit multiplies),
+// Each thread jumps the LCG to its chunk of the stream (two-level jump-ahead, below),
 // so no random numbers cross the PCIe bus or touch HBM; the host generator is advanced
 // by the same number of draws (Generator.bit_generator.advance) to stay in lock-step.
 #pragma once
@@ -48,8 +48,47 @@ __host__ __device__ __forceinline__ double pcg_next_double(u128& state, u128 inc
     return (double)(out >> 11) * (1.0 / 9007199254740992.0);
 }
 
-#define PCG_CHUNK 8           // candidates / points per thread (jump-ahead amortised over 8)
-#define PCG_BLOCK 256         // threads per block -> 2048 candidates per block
+#define PCG_BLOCK 256         // threads per block; a thread owns CHUNK consecutive candidates / points
+
+// Two-level jump-ahead.  The full O(log n) jump to a block's first candidate is done by ONE thread per
+// block; every thread then hops tid * 3 * CHUNK draws further with at most eight multiply-adds from a
+// table of (A^n, plus_n), n = (3 * CHUNK) << k, prepared on the host for this stream's increment.  The
+// per-thread cost no longer grows with the stream position, which is what lets small problems use
+// short chunks (more threads in flight to hide the latency of the stencil walk).
+struct PcgStrideTable {
+    u128 mult[8], plus[8];
+};
+
+// coefficients of `delta` LCG steps: state' = mult * state + plus
+__host__ __device__ inline void pcg_jump_coeffs(u128 inc, unsigned long long delta, u128& mult, u128& plus) {
+    u128 cur_mult = pcg_mult(), cur_plus = inc, acc_mult = 1, acc_plus = 0;
+    while (delta > 0) {
+        if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+        cur_plus = (cur_mult + 1) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1;
+    }
+    mult = acc_mult; plus = acc_plus;
+}
+
+inline PcgStrideTable pcg_stride_table(u128 inc, int chunk) {
+    PcgStrideTable t;
+    for (int k = 0; k < 8; ++k) pcg_jump_coeffs(inc, (unsigned long long)(3 * chunk) << k, t.mult[k], t.plus[k]);
+    return t;
+}
+
+// state at the first draw of this thread's chunk; block_first_draw = draws consumed before the block's
+// first candidate.  All threads of the block must call it (one __syncthreads).
+__device__ __forceinline__ u128 pcg_thread_state(const Pcg64& rng, const PcgStrideTable& tbl,
+                                                 unsigned long long block_first_draw, u128* s_base) {
+    if (threadIdx.x == 0) *s_base = pcg_advance(rng.state, rng.inc, block_first_draw);
+    __syncthreads();
+    u128 st = *s_base;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if ((threadIdx.x >> k) & 1) st = st * tbl.mult[k] + tbl.plus[k];
+    return st;
+}
 
 struct SphereCtl {
     long long filled;         // points accepted so far
@@ -77,17 +116,21 @@ __device__ __forceinline__ int block_sum_int(int v, int* s_w /* [32] */) {
     return t;
 }
 
-// pass A: accepted candidates per BLOCK of 2048 candidates
+// pass A: accepted candidates per BLOCK of PCG_BLOCK * CHUNK candidates
+template <int CHUNK>
 __global__ void __launch_bounds__(PCG_BLOCK)
-pcg_sphere_count_kernel(Pcg64 rng, long long M, double R, long long P,
+pcg_sphere_count_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, long long P,
                         const SphereCtl* __restrict__ ctl, int* __restrict__ block_count) {
     __shared__ int s_w[32];
+    __shared__ u128 s_base;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long c0 = t * PCG_CHUNK;
+    const long long c0 = t * CHUNK;
     int n = 0;
-    if (c0 < M && ctl->filled < P) {                              // a pass that is not needed consumes nothing
-        const long long c1 = min(c0 + (long long)PCG_CHUNK, M);
-        u128 st = pcg_advance(rng.state, rng.inc, (unsigned long long)(3 * (ctl->passes * M + c0)));
+    const bool wanted = ctl->filled < P;                          // a pass that is not needed consumes nothing
+    u128 st = 0;
+    if (wanted) st = pcg_thread_state(rng, tbl, (unsigned long long)(3 * (ctl->passes * M + (long long)blockIdx.x * PCG_BLOCK * CHUNK)), &s_base);
+    if (c0 < M && wanted) {
+        const long long c1 = min(c0 + (long long)CHUNK, M);
         const double R2 = __dmul_rn(R, R);
         for (long long c = c0; c < c1; ++c) {
             double x, y, z;
@@ -122,27 +165,29 @@ pcg_scan_kernel(const int* __restrict__ block_count, long long* __restrict__ blo
 }
 
 // pass B: regenerate, rank the accepted candidates in stream order, evaluate those still needed
+template <int CHUNK>
 __global__ void __launch_bounds__(PCG_BLOCK)
-pcg_sphere_eval_kernel(Pcg64 rng, long long M, double R, long long P, double cx, double cy, double cz,
+pcg_sphere_eval_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, long long P, double cx, double cy, double cz,
                        const SphereCtl* __restrict__ ctl, const long long* __restrict__ block_prefix,
                        const FvGrid* __restrict__ gridp, const double4* __restrict__ spheres,
                        const int* __restrict__ cell_start, unsigned long long* __restrict__ counts) {
     __shared__ int s_cnt[8];
     __shared__ int s_scan[32];
+    __shared__ u128 s_base;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long c0 = t * PCG_CHUNK;
+    const long long c0 = t * CHUNK;
     const long long need = P - ctl->filled;
     int covered_local = 0, total_local = 0;
     if (need > 0 && block_prefix[blockIdx.x] < need) {            // block-uniform
-        double px[PCG_CHUNK], py[PCG_CHUNK], pz[PCG_CHUNK];
+        double px[CHUNK], py[CHUNK], pz[CHUNK];
         unsigned acc_mask = 0;
         int n = 0;
+        u128 st = pcg_thread_state(rng, tbl, (unsigned long long)(3 * (ctl->passes * M + (long long)blockIdx.x * PCG_BLOCK * CHUNK)), &s_base);
         if (c0 < M) {
-            const long long c1 = min(c0 + (long long)PCG_CHUNK, M);
-            u128 st = pcg_advance(rng.state, rng.inc, (unsigned long long)(3 * (ctl->passes * M + c0)));
+            const long long c1 = min(c0 + (long long)CHUNK, M);
             const double R2 = __dmul_rn(R, R);
 #pragma unroll
-            for (int k = 0; k < PCG_CHUNK; ++k) {
+            for (int k = 0; k < CHUNK; ++k) {
                 if (c0 + k < c1 && sphere_candidate(st, rng.inc, R, R2, px[k], py[k], pz[k])) {
                     acc_mask |= 1u << k;
                     ++n;
@@ -155,7 +200,7 @@ pcg_sphere_eval_kernel(Pcg64 rng, long long M, double R, long long P, double cx,
         if (rank < need) {
             const FvGrid g = *gridp;
 #pragma unroll
-            for (int k = 0; k < PCG_CHUNK; ++k) {
+            for (int k = 0; k < CHUNK; ++k) {
                 if ((acc_mask >> k) & 1u) {
                     if (rank < need) {
                         const bool cov = fv_point_covered(g, spheres, cell_start, __dadd_rn(px[k], cx),
@@ -180,21 +225,23 @@ __global__ void pcg_sphere_commit_kernel(SphereCtl* ctl, long long P) {
 }
 
 // CustomCell: point i = rng.random(3) @ dims, one kernel
+template <int CHUNK>
 __global__ void __launch_bounds__(PCG_BLOCK)
-pcg_box_eval_kernel(Pcg64 rng, long long P, const double* __restrict__ dims /* 9, device */,
+pcg_box_eval_kernel(Pcg64 rng, PcgStrideTable tbl, long long P, const double* __restrict__ dims /* 9, device */,
                     const FvGrid* __restrict__ gridp, const double4* __restrict__ spheres,
                     const int* __restrict__ cell_start, unsigned long long* __restrict__ counts) {
     __shared__ int s_cnt[8];
+    __shared__ u128 s_base;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long i0 = t * PCG_CHUNK;
+    const long long i0 = t * CHUNK;
     int covered_local = 0, total_local = 0;
+    u128 st = pcg_thread_state(rng, tbl, (unsigned long long)(3 * (long long)blockIdx.x * PCG_BLOCK * CHUNK), &s_base);
     if (i0 < P) {
         const FvGrid g = *gridp;
-        const long long i1 = min(i0 + (long long)PCG_CHUNK, P);
+        const long long i1 = min(i0 + (long long)CHUNK, P);
         double d[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) d[k] = dims[k];
-        u128 st = pcg_advance(rng.state, rng.inc, (unsigned long long)(3 * i0));
         for (long long i = i0; i < i1; ++i) {
             const double u0 = pcg_next_double(st, rng.inc), u1 = pcg_next_double(st, rng.inc),
                          u2 = pcg_next_double(st, rng.inc);
