@@ -181,7 +181,7 @@ struct mcpyb_engine {
     DevBuf<double> fv_points, fv_pos, fv_radii, fv_small;   // fv_small: offset(3) + shifts(81)
     DevBuf<unsigned long long> fv_counts;
     DevBuf<unsigned char> fv_mask;
-    PinBuf fv_pin;
+    PinBuf fv_pin, fv_atoms_pin, fv_out_pin;
     DevBuf<int> pcg_count;
     DevBuf<long long> pcg_prefix;
     DevBuf<SphereCtl> pcg_ctl;
@@ -458,7 +458,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     e->nl_i.release(); e->nl_j.release(); e->nl_S.release(); e->nl_r2.release(); e->nl_cursor.release();
     e->fv_grid.release(); e->fv_spheres.release(); e->fv_cell_start.release(); e->fv_cursor.release();
     e->fv_cid.release(); e->fv_points.release(); e->fv_pos.release(); e->fv_radii.release(); e->fv_small.release();
-    e->fv_counts.release(); e->fv_mask.release(); e->fv_pin.release();
+    e->fv_counts.release(); e->fv_mask.release(); e->fv_pin.release(); e->fv_atoms_pin.release(); e->fv_out_pin.release();
     e->pcg_count.release(); e->pcg_prefix.release(); e->pcg_ctl.release();
     if (e->trial_ev) cudaEventDestroy(e->trial_ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -1097,15 +1097,25 @@ static int fv_build(mcpyb_engine* e, const double* d_pos, const double* d_radii,
     CK(e->fv_cid.reserve(nsph), "cudaMalloc fv");
     CK(e->fv_cell_start.reserve(fv_max_cells + 1), "cudaMalloc fv");
     CK(e->fv_cursor.reserve(fv_max_cells), "cudaMalloc fv");
-    CK(e->fv_small.reserve(3 + 81 + 9), "cudaMalloc fv");
-    // offset + shifts: tiny pinned block
-    CK(cudaStreamSynchronize(e->stream), "sync before fv staging reuse");
-    CK(e->fv_pin.reserve((3 + 81 + 9) * sizeof(double)), "cudaMallocHost fv");
-    double* hs = (double*)e->fv_pin.p;
-    for (int i = 0; i < 3; ++i) hs[i] = offset3 ? offset3[i] : 0.0;
-    for (int i = 0; i < 3 * nshift; ++i) hs[3 + i] = shifts ? shifts[i] : 0.0;
-    CK(cudaMemcpyAsync(e->fv_small.p, hs, (3 + 3 * (size_t)nshift) * sizeof(double), cudaMemcpyHostToDevice, e->stream), "H2D fv small");
-    fv_build_kernel<<<1, FV_BUILD_THREADS, 0, e->stream>>>(d_pos, d_radii, (int)M, e->fv_small.p, e->fv_small.p + 3, nshift,
+    if (!e->fv_small.p) {
+        // offset(3) | shifts(81) | dims(9) | six zeros (offset and the single shift of the plain case)
+        CK(e->fv_small.reserve(3 + 81 + 9 + 6), "cudaMalloc fv");
+        CK(cudaMemsetAsync(e->fv_small.p, 0, e->fv_small.cap * sizeof(double), e->stream), "memset fv small");
+    }
+    const double* d_offset = e->fv_small.p + 93;
+    const double* d_shifts = e->fv_small.p + 96;
+    if (offset3 || shifts) {
+        // offset + shifts: tiny pinned block
+        CK(cudaStreamSynchronize(e->stream), "sync before fv staging reuse");
+        CK(e->fv_pin.reserve((3 + 81 + 9) * sizeof(double)), "cudaMallocHost fv");
+        double* hs = (double*)e->fv_pin.p;
+        for (int i = 0; i < 3; ++i) hs[i] = offset3 ? offset3[i] : 0.0;
+        for (int i = 0; i < 3 * nshift; ++i) hs[3 + i] = shifts ? shifts[i] : 0.0;
+        CK(cudaMemcpyAsync(e->fv_small.p, hs, (3 + 3 * (size_t)nshift) * sizeof(double), cudaMemcpyHostToDevice, e->stream), "H2D fv small");
+        d_offset = e->fv_small.p;
+        d_shifts = e->fv_small.p + 3;
+    }
+    fv_build_kernel<<<1, FV_BUILD_THREADS, 0, e->stream>>>(d_pos, d_radii, (int)M, d_offset, d_shifts, nshift,
         e->fv_grid.p, e->fv_spheres.p, (int)nsph, e->fv_cell_start.p, e->fv_cursor.p, fv_max_cells, e->fv_cid.p);
     LAUNCH_CHECK("fv_build_kernel");
     return MCPYB_OK;
@@ -1132,19 +1142,30 @@ static int fv_upload_atoms(mcpyb_engine* e, const double* positions, const doubl
     CK(e->fv_radii.reserve((size_t)(M > 0 ? M : 1)), "cudaMalloc fv radii");
     CK(e->fv_counts.reserve(2), "cudaMalloc fv counts");
     if (M) {
-        CK(cudaMemcpyAsync(e->fv_pos.p, positions, (size_t)M * 24, cudaMemcpyHostToDevice, e->stream), "H2D fv pos");
-        CK(cudaMemcpyAsync(e->fv_radii.p, radii, (size_t)M * 8, cudaMemcpyHostToDevice, e->stream), "H2D fv radii");
+        // pinned staging: a pageable source makes cudaMemcpyAsync stage and block inside the driver
+        CK(cudaStreamSynchronize(e->stream), "sync before fv atom staging reuse");
+        CK(e->fv_atoms_pin.reserve((size_t)M * 32), "cudaMallocHost fv atoms");
+        memcpy(e->fv_atoms_pin.p, positions, (size_t)M * 24);
+        memcpy(e->fv_atoms_pin.p + (size_t)M * 24, radii, (size_t)M * 8);
+        CK(cudaMemcpyAsync(e->fv_pos.p, e->fv_atoms_pin.p, (size_t)M * 24, cudaMemcpyHostToDevice, e->stream), "H2D fv pos");
+        CK(cudaMemcpyAsync(e->fv_radii.p, e->fv_atoms_pin.p + (size_t)M * 24, (size_t)M * 8, cudaMemcpyHostToDevice, e->stream), "H2D fv radii");
     }
     return MCPYB_OK;
 }
 
-static int fv_read_counts(mcpyb_engine* e, int64_t* counts_out) {
-    unsigned long long c[2] = {0, 0};
-    FvGrid g;
-    CK(cudaMemcpyAsync(c, e->fv_counts.p, sizeof c, cudaMemcpyDeviceToHost, e->stream), "D2H counts");
-    CK(cudaMemcpyAsync(&g, e->fv_grid.p, sizeof g, cudaMemcpyDeviceToHost, e->stream), "D2H fv grid");
+// counts and the grid's error flag come back through one pinned block (a pageable destination would
+// make each copy synchronous); `ctl_out` additionally fetches the sphere sampler's control block
+static int fv_read_counts(mcpyb_engine* e, int64_t* counts_out, SphereCtl* ctl_out = nullptr) {
+    CK(e->fv_out_pin.reserve(256), "cudaMallocHost fv out");
+    unsigned long long* c = (unsigned long long*)e->fv_out_pin.p;
+    FvGrid* g = (FvGrid*)(e->fv_out_pin.p + 16);
+    SphereCtl* ctl = (SphereCtl*)(e->fv_out_pin.p + 16 + ((sizeof(FvGrid) + 15) / 16) * 16);
+    CK(cudaMemcpyAsync(c, e->fv_counts.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream), "D2H counts");
+    CK(cudaMemcpyAsync(g, e->fv_grid.p, sizeof(FvGrid), cudaMemcpyDeviceToHost, e->stream), "D2H fv grid");
+    if (ctl_out) CK(cudaMemcpyAsync(ctl, e->pcg_ctl.p, sizeof(SphereCtl), cudaMemcpyDeviceToHost, e->stream), "D2H ctl");
     CK(cudaStreamSynchronize(e->stream), "sync free volume");
-    if (g.error) return e->fail(MCPYB_ERR_CAPACITY, "free-volume sphere capacity exceeded");
+    if (ctl_out) *ctl_out = *ctl;
+    if (g->error) return e->fail(MCPYB_ERR_CAPACITY, "free-volume sphere capacity exceeded");
     counts_out[0] = (int64_t)c[0];
     counts_out[1] = (int64_t)c[1];
     return MCPYB_OK;
@@ -1202,39 +1223,36 @@ int mcpyb_sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
     const PcgStrideTable tbl = pcg_stride_table(rng.inc, chunk);
     const long long nthreads = (Mc + chunk - 1) / chunk;
     const int blocks = (int)((nthreads + PCG_BLOCK - 1) / PCG_BLOCK);
-    CK(e->pcg_count.reserve((size_t)blocks), "cudaMalloc pcg");
-    CK(e->pcg_prefix.reserve((size_t)blocks), "cudaMalloc pcg");
+    CK(e->pcg_count.reserve(2 * (size_t)blocks), "cudaMalloc pcg");
+    CK(e->pcg_prefix.reserve(2 * (size_t)blocks), "cudaMalloc pcg");
     CK(e->pcg_ctl.reserve(1), "cudaMalloc pcg");
     CK(cudaMemsetAsync(e->pcg_ctl.p, 0, sizeof(SphereCtl), e->stream), "memset ctl");
     CK(cudaMemsetAsync(e->fv_counts.p, 0, 2 * sizeof(unsigned long long), e->stream), "memset counts");
     const double cx = center3 ? center3[0] : 0.0, cy = center3 ? center3[1] : 0.0, cz = center3 ? center3[2] : 0.0;
     SphereCtl ctl;
     memset(&ctl, 0, sizeof ctl);
-    int launched = 0;
+    int rounds = 0;
+    const dim3 grid2(blocks, 2);
     while (P > 0) {
-        // two passes are enough in all but astronomically unlikely cases; launch them back to back,
-        // then look (a pass that is not needed consumes no random numbers)
-        for (int k = 0; k < 2; ++k) {
-            if (chunk == 8) pcg_sphere_count_kernel<8><<<blocks, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, P, e->pcg_ctl.p, e->pcg_count.p);
-            else pcg_sphere_count_kernel<2><<<blocks, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, P, e->pcg_ctl.p, e->pcg_count.p);
-            LAUNCH_CHECK("pcg_sphere_count_kernel");
-            pcg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->pcg_count.p, e->pcg_prefix.p, blocks, e->pcg_ctl.p);
-            LAUNCH_CHECK("pcg_scan_kernel");
-            if (chunk == 8) pcg_sphere_eval_kernel<8><<<blocks, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, P, cx, cy, cz, e->pcg_ctl.p,
-                e->pcg_prefix.p, e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
-            else pcg_sphere_eval_kernel<2><<<blocks, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, P, cx, cy, cz, e->pcg_ctl.p,
-                e->pcg_prefix.p, e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
-            LAUNCH_CHECK("pcg_sphere_eval_kernel");
-            pcg_sphere_commit_kernel<<<1, 1, 0, e->stream>>>(e->pcg_ctl.p, P);
-            LAUNCH_CHECK("pcg_sphere_commit_kernel");
-            ++launched;
-        }
-        CK(cudaMemcpyAsync(&ctl, e->pcg_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, e->stream), "D2H ctl");
-        CK(cudaStreamSynchronize(e->stream), "sync sphere passes");
+        // one round = two passes of the reference loop (enough in all but astronomically unlikely
+        // cases): count, scan + bookkeeping, evaluate; then look
+        if (chunk == 8) pcg_sphere_count_kernel<8><<<grid2, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, P, e->pcg_ctl.p, e->pcg_count.p);
+        else pcg_sphere_count_kernel<2><<<grid2, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, P, e->pcg_ctl.p, e->pcg_count.p);
+        LAUNCH_CHECK("pcg_sphere_count_kernel");
+        pcg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->pcg_count.p, e->pcg_prefix.p, blocks, P, e->pcg_ctl.p);
+        LAUNCH_CHECK("pcg_scan_kernel");
+        if (chunk == 8) pcg_sphere_eval_kernel<8><<<grid2, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, cx, cy, cz, e->pcg_ctl.p,
+            e->pcg_prefix.p, e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
+        else pcg_sphere_eval_kernel<2><<<grid2, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, cx, cy, cz, e->pcg_ctl.p,
+            e->pcg_prefix.p, e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
+        LAUNCH_CHECK("pcg_sphere_eval_kernel");
+        rc = fv_read_counts(e, counts_out, &ctl);
+        if (rc != MCPYB_OK) return rc;
         if (ctl.filled >= P) break;
-        if (launched > 64) return e->fail(MCPYB_ERR_STATE, "sphere sampler did not converge");
+        if (++rounds > 32) return e->fail(MCPYB_ERR_STATE, "sphere sampler did not converge");
     }
     if (draws_out) *draws_out = 3 * Mc * ctl.passes;
+    if (P > 0) return MCPYB_OK;
     return fv_read_counts(e, counts_out);
 }
 
@@ -1252,6 +1270,7 @@ int mcpyb_box_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo, co
     if (rc != MCPYB_OK) return rc;
     // dims ride in the tail of the small block; wait for the H2D that still reads its head
     CK(cudaStreamSynchronize(e->stream), "sync before dims staging");
+    CK(e->fv_pin.reserve((3 + 81 + 9) * sizeof(double)), "cudaMallocHost fv");
     double* hs = (double*)e->fv_pin.p;
     for (int i = 0; i < 9; ++i) hs[84 + i] = dims9[i];
     CK(cudaMemcpyAsync(e->fv_small.p + 84, hs + 84, 9 * sizeof(double), cudaMemcpyHostToDevice, e->stream), "H2D dims");

@@ -90,10 +90,14 @@ __device__ __forceinline__ u128 pcg_thread_state(const Pcg64& rng, const PcgStri
     return st;
 }
 
+// Control block of the sphere sampler.  One round of launches covers TWO passes of the reference's
+// `while len(pts) < n` loop (spherical_cell.py:93-106; at 1.5x oversampling the second pass is needed
+// unless n is tiny): grid.y = pass of the round.  A pass that is not needed consumes no random numbers.
 struct SphereCtl {
-    long long filled;         // points accepted so far
-    long long passes;         // passes that consumed random numbers
-    long long pass_total;     // accepted candidates of the current pass
+    long long filled;         // points accepted so far (all rounds)
+    long long passes;         // passes that consumed random numbers (all rounds)
+    long long base_pass;      // `passes` at the start of the current round
+    long long need[2];        // points still wanted from pass 0 / 1 of the current round (<= 0: pass unused)
 };
 
 __device__ __forceinline__ bool sphere_candidate(u128& st, u128 inc, double R, double R2,
@@ -116,7 +120,7 @@ __device__ __forceinline__ int block_sum_int(int v, int* s_w /* [32] */) {
     return t;
 }
 
-// pass A: accepted candidates per BLOCK of PCG_BLOCK * CHUNK candidates
+// pass A: accepted candidates per BLOCK of PCG_BLOCK * CHUNK candidates; blockIdx.y = pass of the round
 template <int CHUNK>
 __global__ void __launch_bounds__(PCG_BLOCK)
 pcg_sphere_count_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, long long P,
@@ -126,9 +130,10 @@ pcg_sphere_count_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, lo
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long c0 = t * CHUNK;
     int n = 0;
-    const bool wanted = ctl->filled < P;                          // a pass that is not needed consumes nothing
+    const bool wanted = ctl->filled < P;                          // grid-uniform
+    const long long pass = ctl->passes + blockIdx.y;
     u128 st = 0;
-    if (wanted) st = pcg_thread_state(rng, tbl, (unsigned long long)(3 * (ctl->passes * M + (long long)blockIdx.x * PCG_BLOCK * CHUNK)), &s_base);
+    if (wanted) st = pcg_thread_state(rng, tbl, (unsigned long long)(3 * (pass * M + (long long)blockIdx.x * PCG_BLOCK * CHUNK)), &s_base);
     if (c0 < M && wanted) {
         const long long c1 = min(c0 + (long long)CHUNK, M);
         const double R2 = __dmul_rn(R, R);
@@ -138,36 +143,54 @@ pcg_sphere_count_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, lo
         }
     }
     const int tot = block_sum_int(n, s_w);
-    if (threadIdx.x == 0) block_count[blockIdx.x] = tot;
+    if (threadIdx.x == 0) block_count[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
 }
 
-// single block: exclusive scan of block_count -> block_prefix, pass_total
+// single block: per-pass exclusive scans of block_count -> block_prefix, then the bookkeeping of the
+// round: how many points each pass still has to deliver, how many passes consumed random numbers
 __global__ void __launch_bounds__(1024, 1)
 pcg_scan_kernel(const int* __restrict__ block_count, long long* __restrict__ block_prefix, long long nblocks,
-                SphereCtl* __restrict__ ctl) {
+                long long P, SphereCtl* __restrict__ ctl) {
     __shared__ long long s[1024];
+    __shared__ long long s_total[2];
     const int tid = threadIdx.x;
     const long long per = (nblocks + 1023) / 1024;
     const long long beg = min((long long)tid * per, nblocks), end = min(beg + per, nblocks);
-    long long sum = 0;
-    for (long long i = beg; i < end; ++i) sum += block_count[i];
-    s[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const long long v = (tid >= o) ? s[tid - o] : 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int* bc = block_count + (size_t)pass * nblocks;
+        long long* bp = block_prefix + (size_t)pass * nblocks;
+        long long sum = 0;
+        for (long long i = beg; i < end; ++i) sum += bc[i];
+        s[tid] = sum;
         __syncthreads();
-        s[tid] += v;
+        for (int o = 1; o < 1024; o <<= 1) {
+            const long long v = (tid >= o) ? s[tid - o] : 0;
+            __syncthreads();
+            s[tid] += v;
+            __syncthreads();
+        }
+        long long run = s[tid] - sum;
+        for (long long i = beg; i < end; ++i) { bp[i] = run; run += bc[i]; }
+        if (tid == 1023) s_total[pass] = s[1023];
         __syncthreads();
     }
-    long long run = s[tid] - sum;
-    for (long long i = beg; i < end; ++i) { block_prefix[i] = run; run += block_count[i]; }
-    if (tid == 1023) ctl->pass_total = s[1023];
+    if (tid == 0) {
+        const long long need0 = P - ctl->filled;
+        const long long take0 = need0 > 0 ? min(s_total[0], need0) : 0;
+        const long long need1 = need0 - take0;                    // > 0: the second pass is drawn too
+        const long long take1 = need1 > 0 ? min(s_total[1], need1) : 0;
+        ctl->base_pass = ctl->passes;
+        ctl->need[0] = need0;
+        ctl->need[1] = need1;
+        ctl->passes += (need0 > 0 ? 1 : 0) + (need1 > 0 ? 1 : 0);
+        ctl->filled += take0 + take1;
+    }
 }
 
 // pass B: regenerate, rank the accepted candidates in stream order, evaluate those still needed
 template <int CHUNK>
 __global__ void __launch_bounds__(PCG_BLOCK)
-pcg_sphere_eval_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, long long P, double cx, double cy, double cz,
+pcg_sphere_eval_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, double cx, double cy, double cz,
                        const SphereCtl* __restrict__ ctl, const long long* __restrict__ block_prefix,
                        const FvGrid* __restrict__ gridp, const double4* __restrict__ spheres,
                        const int* __restrict__ cell_start, unsigned long long* __restrict__ counts) {
@@ -176,13 +199,15 @@ pcg_sphere_eval_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, lon
     __shared__ u128 s_base;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long c0 = t * CHUNK;
-    const long long need = P - ctl->filled;
+    const long long need = ctl->need[blockIdx.y];
+    const long long first = block_prefix[(size_t)blockIdx.y * gridDim.x + blockIdx.x];
     int covered_local = 0, total_local = 0;
-    if (need > 0 && block_prefix[blockIdx.x] < need) {            // block-uniform
+    if (need > 0 && first < need) {                               // block-uniform
         double px[CHUNK], py[CHUNK], pz[CHUNK];
         unsigned acc_mask = 0;
         int n = 0;
-        u128 st = pcg_thread_state(rng, tbl, (unsigned long long)(3 * (ctl->passes * M + (long long)blockIdx.x * PCG_BLOCK * CHUNK)), &s_base);
+        const long long pass = ctl->base_pass + blockIdx.y;
+        u128 st = pcg_thread_state(rng, tbl, (unsigned long long)(3 * (pass * M + (long long)blockIdx.x * PCG_BLOCK * CHUNK)), &s_base);
         if (c0 < M) {
             const long long c1 = min(c0 + (long long)CHUNK, M);
             const double R2 = __dmul_rn(R, R);
@@ -196,7 +221,7 @@ pcg_sphere_eval_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, lon
         }
         // exclusive rank of this thread's first accepted candidate inside the block
         const int incl = block_inclusive_scan(n, s_scan);
-        long long rank = block_prefix[blockIdx.x] + (incl - n);
+        long long rank = first + (incl - n);
         if (rank < need) {
             const FvGrid g = *gridp;
 #pragma unroll
@@ -214,14 +239,6 @@ pcg_sphere_eval_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, lon
         }
     }
     fv_block_accumulate(covered_local, total_local, s_cnt, counts);
-}
-
-// after pass B: book the pass
-__global__ void pcg_sphere_commit_kernel(SphereCtl* ctl, long long P) {
-    const long long need = P - ctl->filled;
-    if (need <= 0) return;
-    ctl->filled += (ctl->pass_total < need) ? ctl->pass_total : need;
-    ctl->passes += 1;
 }
 
 // CustomCell: point i = rng.random(3) @ dims, one kernel
