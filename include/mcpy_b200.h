@@ -100,6 +100,16 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
                               int n, const double* cell9, const uint8_t* pbc3,
                               double* energy_out, int* path_out);
 
+/* Forces of the resident batch, host array [sum N][3] (eV/A): ASE's results['forces'] of
+ * LennardJones / EMT.  Replaces the forces the ASE calculators hand to the optimisers behind
+ * BaseCalculator.get_potential_energy (mcpy/calculators/base_calculator.py:14-22) and
+ * CanonicalEnsemble.relax (mcpy/ensembles/canonical_ensemble.py:115-123).                     */
+int mcpyb_forces_host(mcpyb_engine* e, double* forces_out);
+/* Upload + energies + forces in one call (Calculator.calculate(atoms, ['energy', 'forces'])). */
+int mcpyb_energy_forces_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
+                             const int32_t* numbers, const double* cells, const uint8_t* pbc,
+                             double* energies_out, double* forces_out);
+
 /* Per-atom energies of the resident batch (ASE's results['energies']) and, for
  * EMT, the density sums sigma1; either pointer may be NULL. Host arrays [sum N]. */
 int mcpyb_atom_energies_host(mcpyb_engine* e, double* e_atom_out, double* sigma1_out);

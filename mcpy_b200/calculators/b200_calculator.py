@@ -52,7 +52,7 @@ def _config_of(atoms):
 class _B200Core:
     """Plug-in methods shared by the ASE-derived and the plain class."""
 
-    implemented_properties = ['energy', 'free_energy']
+    implemented_properties = ['energy', 'free_energy', 'forces']
 
     def _init_engine(self, potential, epsilon, sigma, rc, device, chunk_size, incremental=True):
         potential = str(potential).lower()
@@ -88,6 +88,21 @@ class _B200Core:
             self.path_counts[path] += 1
             return e
         return self.engine.potential_energy(atoms.positions, atoms.numbers, cell, atoms.pbc)
+
+    def get_forces(self, atoms=None) -> np.ndarray:
+        """Forces ``(n, 3)`` of ``atoms`` (ASE ``LennardJones`` / ``EMT`` ``results['forces']``): what the
+        optimisers behind ``BaseCalculator.get_potential_energy`` (``base_calculator.py:14-22``) and
+        ``CanonicalEnsemble.relax`` (``canonical_ensemble.py:115-123``) ask for."""
+        return self.get_energy_and_forces(atoms)[1]
+
+    def get_energy_and_forces(self, atoms=None):
+        if atoms is None:
+            atoms = getattr(self, 'atoms', None)
+            if atoms is None:
+                raise ValueError('get_forces() needs an Atoms object')
+        self.n_energy_calls += 1
+        cell = np.asarray(atoms.cell, dtype=np.float64)
+        return self.engine.energy_forces(atoms.positions, atoms.numbers, cell, atoms.pbc)
 
     def get_potential_energies(self, atoms_list, chunk_size=None) -> np.ndarray:
         """Energies of several (ragged) structures, one batched launch per chunk."""
@@ -141,7 +156,7 @@ if _AseCalculator is not None:
 
     class B200Calculator(_B200Core, _AseCalculator):
         __doc__ = __doc__
-        implemented_properties = ['energy', 'free_energy']
+        implemented_properties = ['energy', 'free_energy', 'forces']
         nolabel = True
 
         def __init__(self, potential='lj', epsilon=1.0, sigma=1.0, rc=None, device=0,
@@ -151,7 +166,11 @@ if _AseCalculator is not None:
 
         def calculate(self, atoms=None, properties=('energy',), system_changes=_all_changes):
             _AseCalculator.calculate(self, atoms, properties, system_changes)
-            e = _B200Core.get_potential_energy(self, self.atoms)
+            if 'forces' in properties:
+                e, f = _B200Core.get_energy_and_forces(self, self.atoms)
+                self.results['forces'] = f
+            else:
+                e = _B200Core.get_potential_energy(self, self.atoms)
             self.results['energy'] = e
             self.results['free_energy'] = e
 
@@ -174,5 +193,9 @@ else:
 
         def calculate(self, atoms=None, properties=('energy',), system_changes=_all_changes):
             self.atoms = atoms
-            e = self.get_potential_energy(atoms)
-            self.results = {'energy': e, 'free_energy': e}
+            if 'forces' in properties:
+                e, f = self.get_energy_and_forces(atoms)
+                self.results = {'energy': e, 'free_energy': e, 'forces': f}
+            else:
+                e = self.get_potential_energy(atoms)
+                self.results = {'energy': e, 'free_energy': e}

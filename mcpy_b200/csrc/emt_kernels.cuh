@@ -101,6 +101,81 @@ emt_embed_kernel(BatchView b, int total_atoms, const EmtTable* __restrict__ tp,
 }
 
 // ---------------------------------------------------------------------------
+// EMT forces (ase.calculators.emt.EMT.interact1 / interact2, ASE 3.23.0), per-atom rows over the
+// both-ways neighbourhood.  With d = pos_j + S @ cell - pos_i, r = |d|, x = exp(acut (r - rc)),
+// theta = 1 / (1 + x), a / b the species of i / j:
+//   y1 = 0.5 V0_a exp(-kappa_b (r/beta - s0_b)) ksi_ab / gamma2_a theta,  y2 = the same with a <-> b
+//   pair term      g  = (y1 kappa_b + y2 kappa_a) / beta + (y1 + y2) acut theta x
+//   z1 = exp(-eta2_b (r - beta s0_b)) ksi_ab / gamma1_a theta deds[i],     z2 = the same with a <-> b, deds[j]
+//   embedding term f2 = (z1 eta2_b + z2 eta2_a) + (z1 + z2) acut theta x
+//   F_i = sum_j (g - f2) d / r,     deds[a] = dE_c / dsigma1 (0 for an isolated atom)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+emt_deds_kernel(BatchView b, int total_atoms, const EmtTable* __restrict__ tp,
+                const double* __restrict__ sigma1, double* __restrict__ deds) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= total_atoms) return;
+    const EmtTable& t = *tp;
+    const EmtSpecies& p = t.sp[tag_species(tag_of(b.upos[a]))];
+    const double s1 = sigma1[a];
+    double v = 0.0;
+    if (s1 > 0.0) {
+        const double ds = -log(s1 / 12.0) / (t.beta * p.eta2);
+        const double x = p.lambda * ds;
+        const double y = exp(-x);
+        const double z = 6.0 * p.V0 * exp(-p.kappa * ds);
+        v = (x * y * p.E0 * p.lambda + p.kappa * z) / (s1 * t.beta * p.eta2);
+    }
+    deds[a] = v;
+}
+
+__global__ void __launch_bounds__(256)
+emt_forces_kernel(BatchView b, const int* __restrict__ atom_off, int total_atoms,
+                  const EmtTable* __restrict__ tp, const double* __restrict__ deds,
+                  double* __restrict__ forces) {
+    const EmtTable& t = *tp;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const double rcl = t.rc_list;
+    for (int a = warp; a < total_atoms; a += nwarps) {
+        const int r = find_replica(atom_off, b.R, a);
+        const GridDesc& g = b.grid[r];
+        const int off = g.atom_off;
+        const int i = a - off;
+        const double4 me = b.upos[a];
+        const int sa = tag_species(tag_of(me));
+        const EmtSpecies& pa = t.sp[sa];
+        const double dea = deds[a];
+        const int* cstart = b.cell_start + (size_t)r * b.cs_stride;
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        for_each_candidate(g, b.spos + off, cstart, me.x, me.y, me.z, lane, 32,
+            [&](const Cand& c) {
+                const double rr = sqrt(c.r2);
+                const int j = tag_index(c.tag);
+                if (rr < rcl && !(c.same_image && j == i)) {
+                    const int sb = tag_species(c.tag);
+                    const EmtSpecies& pb = t.sp[sb];
+                    const double kab = t.ksi[sa][sb], kba = t.ksi[sb][sa];
+                    const double x = exp(t.acut * (rr - t.rc));
+                    const double theta = fast_rcp(1.0 + x);
+                    const double cut = t.acut * theta * x;
+                    const double y1 = 0.5 * pa.V0 * exp(-pb.kappa * (rr * t.inv_beta - pb.s0)) * kab * pa.inv_gamma2 * theta;
+                    const double y2 = 0.5 * pb.V0 * exp(-pa.kappa * (rr * t.inv_beta - pa.s0)) * kba * pb.inv_gamma2 * theta;
+                    const double gp = (y1 * pb.kappa + y2 * pa.kappa) * t.inv_beta + (y1 + y2) * cut;
+                    const double z1 = exp(-pb.eta2 * (rr - t.beta * pb.s0)) * kab * pa.inv_gamma1 * theta * dea;
+                    const double z2 = exp(-pa.eta2 * (rr - t.beta * pa.s0)) * kba * pb.inv_gamma1 * theta * deds[off + j];
+                    const double f2 = (z1 * pb.eta2 + z2 * pa.eta2) + (z1 + z2) * cut;
+                    const double w = (gp - f2) / rr;
+                    fx = fma(w, c.dx, fx); fy = fma(w, c.dy, fy); fz = fma(w, c.dz, fz);
+                }
+            });
+        fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+        if (lane == 0) { forces[3 * (size_t)a] = fx; forces[3 * (size_t)a + 1] = fy; forces[3 * (size_t)a + 2] = fz; }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // EMT trial delta-E.  Needs the resident sigma1[] and e_atom[] of the batch.
 //   dE = sum_{new a} (e_pair_a + embed(sigma1_a))  -  sum_{old b} e_atom[b]
 //      + sum_{unmoved j near a site} [ d e_pair_j + embed(sigma1_j + d sigma1_j) - embed(sigma1_j) ]

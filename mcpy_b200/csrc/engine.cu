@@ -126,7 +126,7 @@ struct mcpyb_engine {
     const int* d_atom_off = nullptr;      // points into stage_dev (header of the last upload)
     DevBuf<CellGeom> geom;
     DevBuf<double> bbox;                  // cluster build scratch
-    DevBuf<double> e_atom, sigma1, e_part;
+    DevBuf<double> e_atom, sigma1, e_part, deds, forces;
     DevBuf<int> cnt_part;
     DevBuf<double> E;                     // one block: E[R] | pairs[R] (int64) | status[R] (int32)
     DevBuf<int> pair_count;
@@ -451,7 +451,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     cudaStreamSynchronize(e->stream);
     e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release(); e->stmp.release(); e->fpos.release();
     e->cid.release(); e->cell_start.release(); e->geom.release(); e->bbox.release();
-    e->e_atom.release(); e->sigma1.release(); e->e_part.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
+    e->e_atom.release(); e->sigma1.release(); e->e_part.release(); e->deds.release(); e->forces.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
     e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release(); e->tw_spos.release(); e->tw_meta.release(); e->tw_items.release(); e->tw_a.release(); e->tw_err.release(); e->tw_hist.release();
@@ -688,6 +688,61 @@ int mcpyb_atom_energies_host(mcpyb_engine* e, double* e_atom_out, double* sigma1
     }
     CK(cudaStreamSynchronize(e->stream), "sync atom energies");
     return MCPYB_OK;
+}
+
+// ---- forces ------------------------------------------------------------------------
+// Forces of the resident batch, [sum N][3], for the ASE Calculator protocol (`atoms.calc = calc`,
+// optimisers in CanonicalEnsemble.relax, canonical_ensemble.py:115-123).  EMT needs sigma1 of the
+// batch first (one energy pass if it is not resident).
+static int launch_forces(mcpyb_engine* e) {
+    if (!e->have_batch) return e->fail(MCPYB_ERR_STATE, "no resident batch (call mcpyb_upload_* first)");
+    const int total = e->total_atoms;
+    CK(e->forces.reserve(3 * (size_t)(total > 0 ? total : 1)), "cudaMalloc forces");
+    if (total == 0) return MCPYB_OK;
+    int blocks = (total + 7) / 8;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    if (e->pot_kind == POT_LJ) {
+        lj_forces_kernel<<<blocks, 256, 0, e->stream>>>(e->view(), e->d_atom_off, total, e->lj, e->forces.p);
+        LAUNCH_CHECK("lj_forces_kernel");
+    } else {
+        if (!e->emt_state_valid) {
+            int rc = launch_energies(e);
+            if (rc != MCPYB_OK) return rc;
+        }
+        CK(e->deds.reserve((size_t)total), "cudaMalloc deds");
+        emt_deds_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(e->view(), total, e->emt_dev.p, e->sigma1.p, e->deds.p);
+        LAUNCH_CHECK("emt_deds_kernel");
+        emt_forces_kernel<<<blocks, 256, 0, e->stream>>>(e->view(), e->d_atom_off, total, e->emt_dev.p, e->deds.p, e->forces.p);
+        LAUNCH_CHECK("emt_forces_kernel");
+    }
+    return MCPYB_OK;
+}
+
+int mcpyb_forces_host(mcpyb_engine* e, double* forces_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    int rc = launch_forces(e);
+    if (rc != MCPYB_OK) return rc;
+    const size_t nb = 3 * (size_t)e->total_atoms * sizeof(double);
+    if (nb == 0) return MCPYB_OK;
+    if (!forces_out) return e->fail(MCPYB_ERR_ARG, "forces_out is NULL");
+    CK(e->out_pin.reserve(nb), "cudaMallocHost out");
+    CK(cudaMemcpyAsync(e->out_pin.p, e->forces.p, nb, cudaMemcpyDeviceToHost, e->stream), "D2H forces");
+    CK(cudaStreamSynchronize(e->stream), "sync forces");
+    int st = 0;                           // species / geometry errors surface through the energy path's status
+    (void)st;
+    memcpy(forces_out, e->out_pin.p, nb);
+    return MCPYB_OK;
+}
+
+// Upload + energies + forces in one call: what Calculator.calculate(atoms, ['energy', 'forces']) needs.
+int mcpyb_energy_forces_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
+                             const int32_t* numbers, const double* cells, const uint8_t* pbc,
+                             double* energies_out, double* forces_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    int rc = mcpyb_potential_energies_host(e, R, atom_off, positions, numbers, cells, pbc, energies_out);
+    if (rc != MCPYB_OK) return rc;
+    return mcpyb_forces_host(e, forces_out);
 }
 
 // ---- trial moves ---------------------------------------------------------------

@@ -83,6 +83,41 @@ lj_atom_energy_kernel(BatchView b, const int* __restrict__ atom_off, int total_a
     }
 }
 
+// ---------------------------------------------------------------------------
+// LJ forces (ase.calculators.lj.LennardJones, smooth=False):
+//   F_i = sum_j  -24 eps (2 c12 - c6) / r2 * d_ij,   d_ij = pos_j + S @ cell - pos_i,  r2 <= rc^2,
+// the input of the relax-then-energy contract (mcpy/calculators/base_calculator.py:14-22,
+// CanonicalEnsemble.relax canonical_ensemble.py:115-123).  One warp per atom; forces[3a .. 3a+2].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lj_forces_kernel(BatchView b, const int* __restrict__ atom_off, int total_atoms,
+                 LJParams p, double* __restrict__ forces) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int a = warp; a < total_atoms; a += nwarps) {
+        const int r = find_replica(atom_off, b.R, a);
+        const GridDesc& g = b.grid[r];
+        const int off = g.atom_off;
+        const int i = a - off;
+        const double4 me = b.upos[a];
+        const int* cstart = b.cell_start + (size_t)r * b.cs_stride;
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        for_each_candidate(g, b.spos + off, cstart, me.x, me.y, me.z, lane, 32,
+            [&](const Cand& c) {
+                if (c.r2 <= p.rc2 && !(c.same_image && tag_index(c.tag) == i)) {
+                    const double inv = fast_rcp(c.r2);
+                    const double t = p.sigma2 * inv;
+                    const double c6 = t * t * t;
+                    const double w = -6.0 * p.eps4 * fma(2.0 * c6, c6, -c6) * inv;     // -24 eps (2 c12 - c6) / r2
+                    fx = fma(w, c.dx, fx); fy = fma(w, c.dy, fy); fz = fma(w, c.dz, fz);
+                }
+            });
+        fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+        if (lane == 0) { forces[3 * (size_t)a] = fx; forces[3 * (size_t)a + 1] = fy; forces[3 * (size_t)a + 2] = fz; }
+    }
+}
+
 // Fixed-order per-replica reduction: E[r] = sum_i e_atom[off+i]; one CTA per replica.
 // With e_part != nullptr it first folds the stencil-plane partials of the lane-per-atom LJ kernel:
 // e_atom[a] = 0.5 * sum_planes e_part[a][plane], pair_count[a] = sum_planes cnt_part[a][plane].

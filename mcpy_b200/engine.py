@@ -194,6 +194,30 @@ class Engine:
         self._R, self._ntot = 1, n
         return float(self._e1[0]), int(self._path.value)
 
+    def forces(self) -> np.ndarray:
+        """Forces of the resident batch, ``(sum N, 3)`` (ASE's ``results['forces']``)."""
+        f = np.empty((self._ntot, 3))
+        self._check(self._lib.mcpyb_forces_host(self._h, ptr(f)))
+        return f
+
+    def energy_forces(self, positions, numbers, cell, pbc):
+        """Single configuration: ``(energy, forces (n, 3))`` in one call."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        num = np.ascontiguousarray(numbers, dtype=np.int32)
+        cell = np.ascontiguousarray(cell, dtype=np.float64)
+        pbc = np.ascontiguousarray(pbc, dtype=np.uint8)
+        n = pos.shape[0]
+        if pos.size != 3 * n or num.size != n or cell.size != 9 or pbc.size != 3:
+            raise ValueError('positions (n,3), numbers (n,), cell (3,3), pbc (3,) expected')
+        off = self._off1
+        off[1] = n
+        f = np.empty((n, 3))
+        self._check(self._lib.mcpyb_energy_forces_host(
+            self._h, 1, off.ctypes.data, pos.ctypes.data, num.ctypes.data, cell.ctypes.data,
+            pbc.ctypes.data, self._e1.ctypes.data, f.ctypes.data))
+        self._R, self._ntot = 1, n
+        return float(self._e1[0]), f
+
     def atom_energies(self, want_sigma1=False):
         e = np.empty(self._ntot)
         s = np.empty(self._ntot) if want_sigma1 else None

@@ -134,6 +134,62 @@ def emt_energy(positions, numbers, cell, pbc, return_details=False):
     return float(energy)
 
 
+def emt_forces(positions, numbers, cell, pbc):
+    """Forces of ``ase.calculators.emt.EMT`` (ASE 3.23.0): ``interact1`` adds the pair-energy force
+    ``((y1 kappa_b + y2 kappa_a) / beta + (y1 + y2) acut theta x) d / r`` to atom a and its negative
+    to b; after the embedding pass has set ``deds[a] = dE_c/dsigma1`` (0 for an isolated atom),
+    ``interact2`` subtracts ``((y1' eta2_b + y2' eta2_a) + (y1' + y2') acut theta x) d / r`` with
+    ``y1' = dsigma1_a(pair) * deds[a]``, ``y2' = dsigma1_b(pair) * deds[b]``; ``d = pos_b + S @ cell - pos_a``
+    over the half list.  Checked against finite differences of ``emt_energy`` in
+    ``tests/test_oracle_forces.py`` (the reference's tests assert no EMT force value)."""
+    from .neighbors import complete_cell
+    pos = np.asarray(positions, dtype=np.float64).reshape(-1, 3)
+    numbers = np.asarray(numbers).reshape(-1)
+    n = len(pos)
+    F = np.zeros((n, 3))
+    if n == 0:
+        return F
+    rc, rc_list, acut = cutoffs()
+    par = {int(Z): species_parameters(Z) for Z in np.unique(numbers)}
+    cellc = complete_cell(np.array(cell, dtype=np.float64).reshape(3, 3), pbc)
+    i, j, S, r2 = neighbor_pairs(pos, cell, pbc, rc_list, use_sqrt=True, half=True)
+    if len(i) == 0:
+        return F
+    _, sigma1, _ = emt_energy(pos, numbers, cell, pbc, return_details=True)
+    deds = np.zeros(n)
+    for a in range(n):
+        p = par[int(numbers[a])]
+        if sigma1[a] <= 0.0:
+            continue
+        ds = -log(sigma1[a] / 12) / (BETA * p['eta2'])
+        x = p['lambda'] * ds
+        y = exp(-x)
+        z = 6 * p['V0'] * exp(-p['kappa'] * ds)
+        deds[a] = (x * y * p['E0'] * p['lambda'] + p['kappa'] * z) / (sigma1[a] * BETA * p['eta2'])
+    r = np.sqrt(r2)
+    d = (pos[j] + S @ cellc) - pos[i]
+    P = lambda key, idx: np.array([par[int(z)][key] for z in numbers[idx]])
+    V0a, V0b = P('V0', i), P('V0', j)
+    ka, kb = P('kappa', i), P('kappa', j)
+    s0a, s0b = P('s0', i), P('s0', j)
+    e2a, e2b = P('eta2', i), P('eta2', j)
+    g1a, g1b = P('gamma1', i), P('gamma1', j)
+    g2a, g2b = P('gamma2', i), P('gamma2', j)
+    ksi = P('n0', j) / P('n0', i)
+    x = np.exp(acut * (r - rc))
+    theta = 1.0 / (1.0 + x)
+    y1 = 0.5 * V0a * np.exp(-kb * (r / BETA - s0b)) * ksi / g2a * theta
+    y2 = 0.5 * V0b * np.exp(-ka * (r / BETA - s0a)) / ksi / g2b * theta
+    f1 = (y1 * kb + y2 * ka) / BETA + (y1 + y2) * acut * theta * x
+    z1 = np.exp(-e2b * (r - BETA * s0b)) * ksi / g1a * theta * deds[i]
+    z2 = np.exp(-e2a * (r - BETA * s0a)) / ksi / g1b * theta * deds[j]
+    f2 = (z1 * e2b + z2 * e2a) + (z1 + z2) * acut * theta * x
+    f = ((f1 - f2) / r)[:, None] * d
+    np.add.at(F, i, f)
+    np.add.at(F, j, -f)
+    return F
+
+
 def emt_delta_e(pos_old, num_old, pos_new, num_new, cell, pbc):
     """``E(new) - E(old)`` (``grand_canonical_ensemble.py:283-284``)."""
     return emt_energy(pos_new, num_new, cell, pbc) - emt_energy(pos_old, num_old, cell, pbc)

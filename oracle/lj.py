@@ -68,6 +68,32 @@ def lj_energy(positions, cell, pbc, sigma=1.0, epsilon=1.0, rc=None,
     return E
 
 
+def lj_forces(positions, cell, pbc, sigma=1.0, epsilon=1.0, rc=None):
+    """Forces of ASE LennardJones(smooth=False) (``ase/calculators/lj.py``, ASE 3.23.0):
+    ``pairwise_forces = (-24 eps (2 c12 - c6) / r2)[:, None] * distance_vectors`` with
+    ``distance_vectors = pos[j] + S @ cell - pos[i]`` summed over the both-ways list of atom i
+    (``c6`` zeroed where ``r2 > rc**2``).  Needed by the relax-then-energy contract of
+    ``mcpy/calculators/base_calculator.py:14-22`` and ``CanonicalEnsemble.relax``
+    (``canonical_ensemble.py:115-123``)."""
+    if rc is None:
+        rc = 3 * sigma
+    pos = np.asarray(positions, dtype=np.float64).reshape(-1, 3)
+    n = len(pos)
+    F = np.zeros((n, 3))
+    if n == 0:
+        return F
+    cell = np.array(cell, dtype=np.float64).reshape(3, 3)
+    i, j, S, r2 = neighbor_pairs(pos, cell, pbc, rc, inclusive=True)
+    if len(i) == 0:
+        return F
+    d = (pos[j] + S @ complete_cell(cell, pbc)) - pos[i]
+    c6 = (sigma ** 2 / r2) ** 3
+    c12 = c6 ** 2
+    w = -24 * epsilon * (2 * c12 - c6) / r2
+    np.add.at(F, i, w[:, None] * d)
+    return F
+
+
 def lj_delta_e(pos_old, pos_new, cell, pbc, sigma=1.0, epsilon=1.0, rc=None):
     """``E(new) - E(old)`` by two full evaluations
     (``grand_canonical_ensemble.py:283-284``)."""
