@@ -431,6 +431,15 @@ def secondary_workloads(device):
         tb = synthetic.trial_batch(cfg, T, seed=11, insert_Z=8)
         args = (tb['old_off'], tb['old_idx'], tb['new_off'], tb['new_pos'], tb['new_Z'])
         t_t = _time(lambda: eng.trial_delta_e(*args), 3)
+        # the sequential one-call-per-trial chain of an unmodified run (resident base + one delta)
+        chain = [synthetic.apply_trial(cfg, tb, t) for t in range(64)]
+        for p1, z1 in chain[:4]:
+            eng.tracked_energy(p1, z1, cell, pbc)
+        t0 = time.perf_counter()
+        for rep_ in range(4):
+            for p1, z1 in chain:
+                eng.tracked_energy(p1, z1, cell, pbc)
+        t_chain = (time.perf_counter() - t0) / (4 * len(chain))
         # free volume: host points uploaded vs PCG64 regenerated on the device, vs scipy cKDTree
         P = int(cfg['mc_sample_points'])
         rng = np.random.default_rng(3)
@@ -450,6 +459,7 @@ def secondary_workloads(device):
             'n_atoms': int(len(pos)),
             'emt_energy_calls_per_s_host_buffers': 1.0 / t_e,
             'emt_trial_dE_evals_per_s_host_buffers': T / t_t,
+            'emt_dropin_chain_us_per_call': 1e6 * t_chain,
             'free_volume_points': P,
             'free_volume_points_per_s_device_pcg64': P / t_dev,
             'free_volume_points_per_s_cpu_ckdtree_1core': P / t_cpu,

@@ -186,16 +186,18 @@ emt_forces_kernel(BatchView b, const int* __restrict__ atom_off, int total_atoms
 // thin for that the trial reports NaN (the caller then recomputes totals).
 // ---------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(256)
-emt_trial_delta_kernel(BatchView b, TrialBatch tb, const EmtTable* __restrict__ tp,
-                       const int* __restrict__ z_to_slot, const double* __restrict__ sigma1,
-                       const double* __restrict__ e_atom, double* __restrict__ dE,
-                       int* __restrict__ npairs) {
-    __shared__ double s_part[8];
-    __shared__ int s_parti[8];
+__device__ __forceinline__ void emt_trial_delta_body(const BatchView& b, const TrialBatch& tb,
+                                                     const EmtTable* __restrict__ tp,
+                                                     const int* __restrict__ z_to_slot,
+                                                     const double* __restrict__ sigma1,
+                                                     const double* __restrict__ e_atom, double* __restrict__ dE,
+                                                     int* __restrict__ npairs, double* s_part, int* s_parti) {
     const EmtTable& t = *tp;
     const double rcl = t.rc_list;
     const int gl = threadIdx.x % G;
+    // a CTA-wide group walks a site's stencil row-wise: warp w takes the rows w, w + 8, ... with its 32 lanes
+    const int TL = G > 32 ? 32 : G, tl = G > 32 ? (gl & 31) : gl;
+    const int trows = G > 32 ? G / 32 : 1, trow0 = G > 32 ? (gl >> 5) : 0;
     const int group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int ngroups = (gridDim.x * blockDim.x) / G;
     for (int tr = group; tr < tb.T; tr += ngroups) {
@@ -253,7 +255,7 @@ emt_trial_delta_kernel(BatchView b, TrialBatch tb, const EmtTable* __restrict__ 
                 double px, py, pz, sg; int spa;
                 site(s, px, py, pz, spa, sg);
                 double sig = 0.0, ep = 0.0;
-                for_each_candidate(g, spos, cstart, px, py, pz, gl, G,
+                for_each_candidate(g, spos, cstart, px, py, pz, tl, TL,
                     [&](const Cand& c) {
                         const double rr = sqrt(c.r2);
                         if (rr < rcl && !(kold && excluded(tag_index(c.tag)))) {
@@ -261,7 +263,7 @@ emt_trial_delta_kernel(BatchView b, TrialBatch tb, const EmtTable* __restrict__ 
                             emt_row_terms(t, spa, tag_species(c.tag), rr, ds, de);
                             sig += ds; ep += de; ++cnt;
                         }
-                    });
+                    }, trow0, trows);
                 // other new atoms (and periodic self images): directed terms into this atom
                 int nim[3];
                 for (int d = 0; d < 3; ++d) nim[d] = g.pbc[d] ? (int)ceil(rcl * (1.0 + 1e-12) / g.height[d]) : 0;
@@ -300,7 +302,7 @@ emt_trial_delta_kernel(BatchView b, TrialBatch tb, const EmtTable* __restrict__ 
             for (int s = 0; s < nsites; ++s) {
                 double px, py, pz, sgn; int sps;
                 site(s, px, py, pz, sps, sgn);
-                for_each_candidate(g, spos, cstart, px, py, pz, gl, G,
+                for_each_candidate(g, spos, cstart, px, py, pz, tl, TL,
                     [&](const Cand& c) {
                         const double rr = sqrt(c.r2);
                         if (!(rr < rcl)) return;
@@ -332,7 +334,7 @@ emt_trial_delta_kernel(BatchView b, TrialBatch tb, const EmtTable* __restrict__ 
                         }
                         const double s_old = sigma1[off + j];
                         acc += dep + (emt_embed(t, spj, s_old + dsig) - emt_embed(t, spj, s_old));
-                    });
+                    }, trow0, trows);
             }
         }
         const double tot = group_sum<G>(acc, s_part, gl);
@@ -342,6 +344,40 @@ emt_trial_delta_kernel(BatchView b, TrialBatch tb, const EmtTable* __restrict__ 
             if (npairs) npairs[tr] = c;
         }
     }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+emt_trial_delta_kernel(BatchView b, TrialBatch tb, const EmtTable* __restrict__ tp,
+                       const int* __restrict__ z_to_slot, const double* __restrict__ sigma1,
+                       const double* __restrict__ e_atom, double* __restrict__ dE,
+                       int* __restrict__ npairs) {
+    __shared__ double s_part[8];
+    __shared__ int s_parti[8];
+    emt_trial_delta_body<G>(b, tb, tp, z_to_slot, sigma1, e_atom, dE, npairs, s_part, s_parti);
+}
+
+// One trial on the latency-bound single-chain path (mcpyb_tracked_energy_host): the whole CTA works on
+// it (G = 256), its description rides in the kernel parameters and dE is written straight to pinned
+// host memory -- one launch and one stream synchronisation per call, no H2D / D2H copies.
+#define EMT_TINY_MAX_MOVED 8
+struct EmtTinyTrial {
+    int old_off[2], new_off[2];
+    int old_idx[EMT_TINY_MAX_MOVED];
+    int new_Z[EMT_TINY_MAX_MOVED];
+    double new_pos[3 * EMT_TINY_MAX_MOVED];
+};
+
+__global__ void __launch_bounds__(256)
+emt_trial_tiny_kernel(BatchView b, const __grid_constant__ EmtTinyTrial tt, const EmtTable* __restrict__ tp,
+                      const int* __restrict__ z_to_slot, const double* __restrict__ sigma1,
+                      const double* __restrict__ e_atom, double* __restrict__ dE_host) {
+    __shared__ double s_part[8];
+    __shared__ int s_parti[8];
+    TrialBatch tb;
+    tb.T = 1; tb.rep = nullptr; tb.old_off = tt.old_off; tb.old_idx = tt.old_idx;
+    tb.new_off = tt.new_off; tb.new_pos = tt.new_pos; tb.new_Z = tt.new_Z;
+    emt_trial_delta_body<256>(b, tb, tp, z_to_slot, sigma1, e_atom, dE_host, nullptr, s_part, s_parti);
 }
 
 // Note (round 1): a lane-per-site variant of these kernels (the scheme of site_kernels.cuh) was

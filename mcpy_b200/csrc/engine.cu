@@ -93,6 +93,7 @@ const double kEmtBeta = 1.809;
 
 struct mcpyb_engine {
     int device = 0;
+    int num_sms = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -435,6 +436,7 @@ int mcpyb_create(int device, mcpyb_engine** out) {
     if (cudaSetDevice(device) != cudaSuccess) return MCPYB_ERR_CUDA;
     mcpyb_engine* e = new mcpyb_engine();
     e->device = device;
+    { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) e->num_sms = sms; }
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete e;
         return MCPYB_ERR_CUDA;
@@ -854,7 +856,7 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     LAUNCH_CHECK("trial_scatter_kernel");
     mark();
     const long long est = (long long)max_items * w.nplanes;
-    const int rb = (int)(est < 148 * RB_MIN_BLOCKS * 8 ? est : 148 * RB_MIN_BLOCKS * 8);
+    const int rb = (int)(est < e->num_sms * RB_MIN_BLOCKS ? est : e->num_sms * RB_MIN_BLOCKS);
     lj_trial_rows_block_kernel<RB_UNROLL, RB_MIN_BLOCKS><<<rb, RB_THREADS, 0, e->stream>>>(e->view(), tb, w, e->lj);
     LAUNCH_CHECK("lj_trial_rows_block_kernel");
     mark();
@@ -1069,6 +1071,28 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
             LAUNCH_CHECK("lj_trial_tiny_kernel");
             CK(cudaStreamSynchronize(e->stream), "sync tiny trial");
             if (*h_status != ~0ULL) return e->fail(MCPYB_ERR_ARG, "tracked trial rejected on the device (status %llu)", *h_status);
+            dE = *h_dE;
+        } else if (e->pot_kind == POT_EMT && n_old <= EMT_TINY_MAX_MOVED && n_new <= EMT_TINY_MAX_MOVED) {
+            bool species_ok = true;
+            for (int k = 0; k < n_new; ++k)
+                species_ok = species_ok && new_Z[k] >= 0 && new_Z[k] < 120 && e->z_to_slot_host[new_Z[k]] >= 0;
+            if (!species_ok) return e->fail(MCPYB_ERR_SPECIES, "an inserted atom has no EMT parameters");
+            EmtTinyTrial tt;
+            memset(&tt, 0, sizeof tt);
+            tt.old_off[1] = n_old; tt.new_off[1] = n_new;
+            for (int k = 0; k < n_old; ++k) tt.old_idx[k] = old_idx[k];
+            for (int k = 0; k < n_new; ++k) tt.new_Z[k] = new_Z[k];
+            for (int k = 0; k < 3 * n_new; ++k) tt.new_pos[k] = new_pos[k];
+            CK(e->trial_out_pin.reserve(64), "cudaMallocHost trial out");
+            double* h_dE = (double*)e->trial_out_pin.p;
+            if (!e->emt_state_valid) {
+                rc = launch_energies(e);           // sigma1 / e_atom of the resident base
+                if (rc != MCPYB_OK) return rc;
+            }
+            emt_trial_tiny_kernel<<<1, 256, 0, e->stream>>>(e->view(), tt, e->emt_dev.p, e->z_to_slot.p,
+                                                            e->sigma1.p, e->e_atom.p, h_dE);
+            LAUNCH_CHECK("emt_trial_tiny_kernel");
+            CK(cudaStreamSynchronize(e->stream), "sync tiny trial");
             dE = *h_dE;
         } else {
             rc = mcpyb_trial_delta_e_host(e, 1, nullptr, old_off, old_idx, new_off, new_pos,

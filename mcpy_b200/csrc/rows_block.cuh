@@ -168,7 +168,15 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nq = w.nplanes;                     // slices of the candidate list, one work item each
     const int nwork = w.totals[0] * nq;
-    for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    // persistent CTAs pull work items from a device counter (zeroed by the scan kernel): the grid is
+    // sized by the SM count, not by the host's upper bound on the item count, so no CTA is launched
+    // only to find nothing to do, and the tail is one item long
+    __shared__ int s_wi;
+    for (;;) {
+        if (tid == 0) s_wi = atomicAdd(&w.totals[1], 1);
+        __syncthreads();
+        const int wi = s_wi;
+        if (wi >= nwork) break;
         const int item = wi / nq, slice = wi - item * nq;
         const int2 it = w.item_tab[item];
         const int bin = it.x, group = it.y;
@@ -378,7 +386,7 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
             w.site_E[(size_t)s * nq + slice] = row;
             w.site_cnt[(size_t)s * nq + slice] = cnt;
         }
-        __syncthreads();                                          // the piece table is rewritten next
+        __syncthreads();                                          // the piece table and s_wi are rewritten next
     }
 }
 

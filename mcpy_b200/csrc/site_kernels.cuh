@@ -405,7 +405,7 @@ struct TrialWork {
     int item_shift;        // sites per work item = 1 << item_shift (5: warp items, 7: CTA items)
     double* site_E;        // [nsites][nplanes] partial row sums
     int* site_cnt;         // [nsites][nplanes] in-cutoff pairs
-    int* totals;           // [0] = number of work items
+    int* totals;           // [0] = number of work items, [1] = work counter of the persistent row-sum CTAs
     // device-side validation: first offending trial << 8 | code (1 replica, 2 list length / offsets,
     // 3 atom index); ~0 = none.  The scan kernel moves it to err_out and re-arms it.
     unsigned long long* err;
@@ -506,7 +506,7 @@ trial_scan_kernel(TrialWork w) {
         if (w.item_tab) for (int gq = 0; gq < ni; ++gq) w.item_tab[rb + gq] = make_int2(i, gq);
         ra += c; rb += ni;
     }
-    if (tid == 1023) { w.bin_count[w.nbins] = s_a[1023]; w.item_start[w.nbins] = s_b[1023]; w.totals[0] = s_b[1023]; }
+    if (tid == 1023) { w.bin_count[w.nbins] = s_a[1023]; w.item_start[w.nbins] = s_b[1023]; w.totals[0] = s_b[1023]; w.totals[1] = 0; }
     if (tid == 0) {
         const unsigned long long ev = *w.err;
         if (w.err_out) *w.err_out = ev;

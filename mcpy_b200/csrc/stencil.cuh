@@ -30,7 +30,11 @@ struct Cand {
 template <class F>
 __device__ __forceinline__ void for_each_candidate(
         const GridDesc& g, const double4* __restrict__ spos, const int* __restrict__ cstart,
-        double px, double py, double pz, int lane, int nlanes, F&& f) {
+        double px, double py, double pz, int lane, int nlanes, F&& f,
+        int row0 = 0, int rowstep = 1) {
+    // row0 / rowstep: visit only the (y, z) rows ri with ri % rowstep == row0, so that several warps
+    // can share one site row-wise (each with nlanes = 32) instead of queueing on the rows one by one
+    int ri = -1;
     int c[3], w[3];
     locate(g, px, py, pz, c, w);
     const int wsite = pack_wraps(w[0], w[1], w[2]);
@@ -43,6 +47,8 @@ __device__ __forceinline__ void for_each_candidate(
             int cy = c[1] + oy, Sy = 0;
             if (g.pbc[1]) { Sy = floor_div(cy, n1); cy -= Sy * n1; }
             else if (cy < 0 || cy >= n1) continue;
+            ++ri;
+            if (rowstep > 1 && (ri % rowstep) != row0) continue;
             const int row = (cz * n1 + cy) * n0;
             // walk the x offsets, merging consecutive cells with the same image shift
             int seg_first = 0, seg_last = -2, seg_S = 0;
