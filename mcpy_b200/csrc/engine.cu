@@ -1194,9 +1194,25 @@ static int fv_build(mcpyb_engine* e, const double* d_pos, const double* d_radii,
         d_offset = e->fv_small.p;
         d_shifts = e->fv_small.p + 3;
     }
-    fv_build_kernel<<<1, FV_BUILD_THREADS, 0, e->stream>>>(d_pos, d_radii, (int)M, d_offset, d_shifts, nshift,
-        e->fv_grid.p, e->fv_spheres.p, (int)nsph, e->fv_cell_start.p, e->fv_cursor.p, fv_max_cells, e->fv_cid.p);
-    LAUNCH_CHECK("fv_build_kernel");
+    if (M * nshift >= 4096) {
+        // large sphere sets: one 8-CTA thread-block cluster
+        CK(e->bbox.reserve(64), "cudaMalloc fv partials");
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(8); cfg.blockDim = dim3(FV_BUILD_THREADS); cfg.stream = e->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, fv_build_kernel<8>, d_pos, d_radii, (int)M, d_offset, d_shifts, nshift,
+                              e->fv_grid.p, e->fv_spheres.p, (int)nsph, e->fv_cell_start.p, e->fv_cursor.p,
+                              fv_max_cells, e->fv_cid.p, e->bbox.p), "launch fv build (cluster)");
+        e->launches++;
+    } else {
+        fv_build_kernel<1><<<1, FV_BUILD_THREADS, 0, e->stream>>>(d_pos, d_radii, (int)M, d_offset, d_shifts, nshift,
+            e->fv_grid.p, e->fv_spheres.p, (int)nsph, e->fv_cell_start.p, e->fv_cursor.p, fv_max_cells, e->fv_cid.p, nullptr);
+        LAUNCH_CHECK("fv_build_kernel");
+    }
     return MCPYB_OK;
 }
 

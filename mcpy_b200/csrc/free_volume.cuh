@@ -6,9 +6,9 @@
 // strict comparison cKDTree.query(distance_upper_bound=r) implements
 // (SURVEY.md 8c), so the counts are bit-exact integers.
 //
-// fv_build_kernel : one CTA bins the (imaged) exclusion spheres on a grid of
-//                   edge >= r_max (counting sort, order inside a cell is
-//                   irrelevant for an any()).
+// fv_build_kernel : one CTA (or an 8-CTA cluster for large sets) bins the (imaged)
+//                   exclusion spheres on a grid of edge >= r_max (counting sort,
+//                   order inside a cell is irrelevant for an any()).
 // fv_count_kernel : one thread per sample point, 27-cell stencil, early exit,
 //                   warp ballot -> block sum -> one 64-bit atomicAdd per CTA.
 #pragma once
@@ -28,23 +28,40 @@ struct FvGrid {
 
 // pos [M][3], radii [M]; images: (pos - offset) + shifts[s], s < nshift.
 // spheres out: double4 (x, y, z, r*r) in cell order; cell_start [max_cells+1]; cursor [max_cells]
+//
+// CS = 1 : one CTA.
+// CS = 8 : one thread-block cluster of 8 CTAs for large sphere sets (the 10 825-atom S5 build took 97 us
+//          in one CTA).  The per-sphere phases are strided over all 8 x 1024 threads and meet at cluster
+//          barriers (release / acquire at cluster scope; everything exchanged lives in global memory);
+//          the scan runs on CTA 0.  part[8][8] is scratch for the bounding-box partials.
+template <int CS>
 __global__ void __launch_bounds__(FV_BUILD_THREADS, 1)
 fv_build_kernel(const double* __restrict__ pos, const double* __restrict__ radii, int M,
                 const double* __restrict__ offset, const double* __restrict__ shifts, int nshift,
                 FvGrid* __restrict__ grid, double4* __restrict__ spheres, int sphere_cap,
                 int* __restrict__ cell_start, int* __restrict__ cursor, int max_cells,
-                int* __restrict__ cid) {
+                int* __restrict__ cid, double* __restrict__ part) {
     __shared__ double s_red[32];
     __shared__ int s_scan[FV_BUILD_THREADS];
     __shared__ int s_carry;
     const int tid = threadIdx.x;
+    const int rank = blockIdx.x % CS;
+    const long long gtid = (long long)rank * FV_BUILD_THREADS + tid;
+    const long long gstride = (long long)CS * FV_BUILD_THREADS;
+    auto sync_all = [&]() {
+        if (CS == 1) { __syncthreads(); }
+        else {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        }
+    };
     const double ox = offset[0], oy = offset[1], oz = offset[2];
     const long long total = (long long)M * nshift;
 
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     double rmax = 0.0;
     int mine = 0;
-    for (long long e = tid; e < total; e += blockDim.x) {
+    for (long long e = gtid; e < total; e += gstride) {
         const int a = (int)(e % M), s = (int)(e / M);
         const double r = radii[a];
         if (!(r > 0.0)) continue;
@@ -63,17 +80,32 @@ fv_build_kernel(const double* __restrict__ pos, const double* __restrict__ radii
         ghi[d] = block_reduce_minmax(hi[d], false, s_red);
     }
     rmax = block_reduce_minmax(rmax, false, s_red);
-    // total sphere count
+    // sphere count of this CTA
     s_scan[tid] = mine;
     __syncthreads();
     for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
         if (tid < o) s_scan[tid] += s_scan[tid + o];
         __syncthreads();
     }
-    const int nsph = s_scan[0];
+    int nsph = s_scan[0];
     __syncthreads();
+    if (CS > 1) {
+        if (tid == 0) {
+            double* pp = part + 8 * rank;
+            for (int d = 0; d < 3; ++d) { pp[d] = glo[d]; pp[3 + d] = ghi[d]; }
+            pp[6] = rmax; pp[7] = (double)nsph;
+        }
+        sync_all();
+        nsph = 0;
+        for (int k = 0; k < CS; ++k) {
+            const double* pp = part + 8 * k;
+            for (int d = 0; d < 3; ++d) { glo[d] = fmin(glo[d], pp[d]); ghi[d] = fmax(ghi[d], pp[3 + d]); }
+            rmax = fmax(rmax, pp[6]);
+            nsph += (int)pp[7];
+        }
+    }
 
-    if (tid == 0) {
+    if (rank == 0 && tid == 0) {
         grid->natoms = nsph;
         grid->error = (nsph > sphere_cap) ? 1 : 0;
         const double edge_min = rmax * (1.0 + 1e-12);
@@ -104,12 +136,12 @@ fv_build_kernel(const double* __restrict__ pos, const double* __restrict__ radii
         }
         grid->ncells = grid->ncell[0] * grid->ncell[1] * grid->ncell[2];
     }
-    __syncthreads();
-    if (grid->error) return;
+    sync_all();
+    if (grid->error) return;                 // uniform over the cluster
     const int ncells = grid->ncells;
-    for (int c = tid; c <= ncells; c += blockDim.x) cell_start[c] = 0;
-    for (int c = tid; c < ncells; c += blockDim.x) cursor[c] = 0;
-    __syncthreads();
+    for (long long c = gtid; c <= ncells; c += gstride) cell_start[c] = 0;
+    for (long long c = gtid; c < ncells; c += gstride) cursor[c] = 0;
+    sync_all();
 
     auto cell_of = [&](double x, double y, double z) {
         int cx = (int)floor((x - grid->lo[0]) * grid->inv_edge[0]);
@@ -120,7 +152,7 @@ fv_build_kernel(const double* __restrict__ pos, const double* __restrict__ radii
         cz = max(0, min(grid->ncell[2] - 1, cz));
         return (cz * grid->ncell[1] + cy) * grid->ncell[0] + cx;
     };
-    for (long long e = tid; e < total; e += blockDim.x) {
+    for (long long e = gtid; e < total; e += gstride) {
         const int a = (int)(e % M), s = (int)(e / M);
         const double r = radii[a];
         if (!(r > 0.0)) { cid[e] = -1; continue; }
@@ -131,19 +163,22 @@ fv_build_kernel(const double* __restrict__ pos, const double* __restrict__ radii
         cid[e] = id;
         atomicAdd(&cell_start[id + 1], 1);
     }
-    __syncthreads();
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < ncells; base += blockDim.x) {
-        const int c = base + tid;
-        const int scanned = block_inclusive_scan((c < ncells) ? cell_start[c + 1] : 0, s_scan);
-        const int incl = scanned + s_carry;
+    sync_all();
+    if (rank == 0) {
+        if (tid == 0) s_carry = 0;
         __syncthreads();
-        if (c < ncells) cell_start[c + 1] = incl;
-        if (tid == blockDim.x - 1) s_carry = incl;
-        __syncthreads();
+        for (int base = 0; base < ncells; base += blockDim.x) {
+            const int c = base + tid;
+            const int scanned = block_inclusive_scan((c < ncells) ? cell_start[c + 1] : 0, s_scan);
+            const int incl = scanned + s_carry;
+            __syncthreads();
+            if (c < ncells) cell_start[c + 1] = incl;
+            if (tid == blockDim.x - 1) s_carry = incl;
+            __syncthreads();
+        }
     }
-    for (long long e = tid; e < total; e += blockDim.x) {
+    sync_all();
+    for (long long e = gtid; e < total; e += gstride) {
         const int id = cid[e];
         if (id < 0) continue;
         const int a = (int)(e % M), s = (int)(e / M);
