@@ -465,27 +465,55 @@ def secondary_workloads(device):
             'free_volume_points_per_s_cpu_ckdtree_1core': P / t_cpu,
         }
     eng.close()
-    # S4: 64 replicas x 2000-atom LJ through the batched plug-in call (one launch set for all)
+    # S4: 64 replicas x 2000-atom LJ through the batched plug-in call.  Each call carries ONE trial move
+    # per replica, as BatchedReplicaExchange._batched_single_move issues them
+    # (batched_replica_exchange.py:235-302): full recomputation vs resident bases + one batched delta.
     from mcpy_b200.calculators import B200Calculator
-    calc = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=RC, device=device)
 
     class _A:
         pass
-    reps = []
+    base, calls = [], []
     for k in range(64):
         c = synthetic.s2_lj(N_ATOMS, RC, RHO, seed=100 + k)
-        a = _A()
-        a.positions, a.numbers, a.cell, a.pbc = c['positions'], c['numbers'], c['cell'], c['pbc']
-        reps.append(a)
-    t_b = _time(lambda: calc.get_potential_energies(reps), 5)
-    t_1 = _time(lambda: [calc.get_potential_energy(a) for a in reps[:8]], 3) / 8
+        tbk = synthetic.trial_batch(c, 8, seed=300 + k)
+        base.append(c)
+        calls.append([synthetic.apply_trial(c, tbk, t) for t in range(8)])
+
+    def batch_of(t):
+        reps = []
+        for k in range(64):
+            a = _A()
+            a.positions, a.numbers = calls[k][t]
+            a.cell, a.pbc = base[k]['cell'], base[k]['pbc']
+            reps.append(a)
+        return reps
+    batches = [batch_of(t) for t in range(8)]
+    res = {}
+    for label, inc in (('full_recompute', False), ('resident_bases', True)):
+        calc = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=RC, device=device, incremental=inc)
+        for bt in batches[:2]:
+            calc.get_potential_energies(bt)
+        t0 = time.perf_counter()
+        for rep_ in range(3):
+            for bt in batches:
+                res[label + '_E'] = calc.get_potential_energies(bt)
+        res[label] = (time.perf_counter() - t0) / (3 * len(batches))
+        if inc:
+            res['paths'] = list(calc.path_counts)
+            t_1 = _time(lambda: [calc.get_potential_energy(a) for a in batches[0][:8]], 3) / 8
+        calc.engine.close()
+    scale = np.maximum(1.0, np.abs(res['full_recompute_E']))
+    assert np.all(np.abs(res['resident_bases_E'] - res['full_recompute_E']) <= 1e-10 * scale)
     out['S4_64_replicas_x_2000_LJ'] = {
-        'batched_call_ms': 1e3 * t_b,
-        'replica_energies_per_s_batched': 64 / t_b,
+        'batched_call_ms_full_recompute': 1e3 * res['full_recompute'],
+        'batched_call_ms_resident_bases': 1e3 * res['resident_bases'],
+        'replica_energies_per_s_batched': 64 / res['resident_bases'],
+        'replica_energies_per_s_batched_full_recompute': 64 / res['full_recompute'],
         'replica_energies_per_s_one_by_one': 1.0 / t_1,
+        'paths_full_incremental_identical': res['paths'],
     }
-    calc.engine.close()
     return out
+
 
 
 def main():

@@ -110,6 +110,16 @@ int mcpyb_energy_forces_host(mcpyb_engine* e, int R, const int64_t* atom_off, co
                              const int32_t* numbers, const double* cells, const uint8_t* pbc,
                              double* energies_out, double* forces_out);
 
+/* Batched incremental form for get_potential_energies(atoms_list) (BatchedReplicaExchange
+ * ._batched_single_move, batched_replica_exchange.py:235-302): R resident bases, one batched delta
+ * launch per call; configurations are matched with the base in their own slot first, then with any
+ * other (replica exchange swaps configurations between slots); a configuration more than a few atoms
+ * away from every base re-bases the whole batch with a full evaluation.  paths_out[r] (may be NULL):
+ * 0 full, 1 incremental, 2 identical to its base.  Any mcpyb_upload_* call resets the bases.       */
+int mcpyb_tracked_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
+                                const int32_t* numbers, const double* cells, const uint8_t* pbc,
+                                double* energies_out, int* paths_out);
+
 /* Per-atom energies of the resident batch (ASE's results['energies']) and, for
  * EMT, the density sums sigma1; either pointer may be NULL. Host arrays [sum N]. */
 int mcpyb_atom_energies_host(mcpyb_engine* e, double* e_atom_out, double* sigma1_out);

@@ -111,11 +111,21 @@ class _B200Core:
         cs = self.chunk_size if chunk_size is None else chunk_size
         out = []
         for start, stop in chunk_ranges(len(atoms_list), cs):
-            cfg = [_config_of(a) for a in atoms_list[start:stop]]
-            cells = np.stack([c[2].reshape(9) for c in cfg])
-            pbcs = np.stack([c[3] for c in cfg])
-            out.append(self.engine.potential_energies([c[0] for c in cfg], [c[1] for c in cfg],
-                                                      cells, pbcs))
+            chunk = atoms_list[start:stop]
+            # marshalling dominates this call (64 x 2000 atoms: ~0.75 ms of a 1.1 ms call when every
+            # Atoms is converted on its own), so convert once per batch, not once per replica
+            pos_list = [a.positions for a in chunk]
+            num_list = [a.numbers for a in chunk]
+            cells = np.array([np.asarray(a.cell, dtype=np.float64).reshape(9) for a in chunk])
+            pbcs = np.array([np.asarray(a.pbc, dtype=bool).reshape(3) for a in chunk])
+            if self.incremental and start == 0 and stop == len(atoms_list):
+                # the whole batch in one piece: resident bases + one batched delta launch
+                en, paths = self.engine.tracked_energies(pos_list, num_list, cells, pbcs)
+                for pth in paths:
+                    self.path_counts[int(pth)] += 1
+                out.append(en)
+            else:
+                out.append(self.engine.potential_energies(pos_list, num_list, cells, pbcs))
             self.n_energy_calls += stop - start
         return np.concatenate(out)
 

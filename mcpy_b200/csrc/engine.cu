@@ -144,6 +144,13 @@ struct mcpyb_engine {
     uint8_t trk_pbc[3];
     double trk_E = 0.0;
     long long trk_full = 0, trk_incremental = 0;
+    // ... and of a resident BATCH of bases (mcpyb_tracked_energies_host): slot r holds rows
+    // [trkb_off[r], trkb_off[r+1]) of trkb_pos / trkb_Z
+    bool trkb_valid = false;
+    std::vector<double> trkb_pos, trkb_cell, trkb_E;
+    std::vector<int32_t> trkb_Z;
+    std::vector<int64_t> trkb_off;
+    std::vector<uint8_t> trkb_pbc;
 
     // instrumentation: CUDA events between the launches of the trial pipeline (mcpyb_stage_timing)
     bool stage_timing = false;
@@ -566,6 +573,7 @@ static int upload_host_impl(mcpyb_engine* e, int subdiv, int R, const int64_t* a
     if (!e) return MCPYB_ERR_ARG;
     e->subdiv = subdiv;
     e->trk_valid = false;
+    e->trkb_valid = false;
     cudaSetDevice(e->device);
     int total = 0, max_n = 0;
     int rc = validate_batch_args(e, R, atom_off, &total, &max_n);
@@ -609,6 +617,7 @@ int mcpyb_upload_dev(mcpyb_engine* e, int R, const int64_t* atom_off, const doub
     cudaSetDevice(e->device);
     e->subdiv = e->subdiv_trials;
     e->trk_valid = false;
+    e->trkb_valid = false;
     int total = 0, max_n = 0;
     int rc = validate_batch_args(e, R, atom_off, &total, &max_n);
     if (rc != MCPYB_OK) return rc;
@@ -1125,6 +1134,131 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
     e->trk_full++;
     *energy_out = E;
     if (path_out) *path_out = 0;
+    return MCPYB_OK;
+}
+
+// Align an incoming configuration P with a base B: rows equal within 1e-10 A and of the same species
+// match; unmatched base rows are removed, unmatched incoming rows added (any such description gives
+// the right energy difference).  Returns false when more than `limit` atoms differ.
+static bool align_rows(const double* B, const int32_t* BZ, int nB, const double* P, const int32_t* PZ, int n,
+                       int limit, int32_t* old_idx, int* new_row, int& n_old, int& n_new) {
+    const double tol = 1e-10;
+    auto match = [&](int i, int j) {
+        return BZ[i] == (PZ ? PZ[j] : 0) && fabs(B[3 * i] - P[3 * j]) <= tol &&
+               fabs(B[3 * i + 1] - P[3 * j + 1]) <= tol && fabs(B[3 * i + 2] - P[3 * j + 2]) <= tol;
+    };
+    n_old = n_new = 0;
+    int i = 0, j = 0;
+    while (i < nB && j < n) {
+        // unchanged stretches are bit-identical almost always: compare 64 rows at a time
+        {
+            const int run = (nB - i < n - j ? nB - i : n - j);
+            int k = 0;
+            while (k + 64 <= run && memcmp(B + 3 * (size_t)(i + k), P + 3 * (size_t)(j + k), 64 * 24) == 0 &&
+                   (!PZ || memcmp(BZ + i + k, PZ + j + k, 64 * sizeof(int32_t)) == 0)) k += 64;
+            i += k; j += k;                       // (without numbers every stored species is 0 as well)
+            if (i >= nB || j >= n) break;
+        }
+        if (match(i, j)) { ++i; ++j; continue; }
+        if (n_old + n_new + 2 > limit) return false;
+        if (i + 1 < nB && match(i + 1, j)) { old_idx[n_old++] = i++; continue; }          // row deleted
+        if (j + 1 < n && match(i, j + 1)) { new_row[n_new++] = j++; continue; }           // row inserted
+        old_idx[n_old++] = i++; new_row[n_new++] = j++;                                  // row displaced
+    }
+    while (i < nB) { if (n_old + n_new + 1 > limit) return false; old_idx[n_old++] = i++; }
+    while (j < n) { if (n_old + n_new + 1 > limit) return false; new_row[n_new++] = j++; }
+    return true;
+}
+
+// Batched form of mcpyb_tracked_energy_host for get_potential_energies(atoms_list)
+// (batched_replica_exchange.py:277-278): the engine keeps R fully evaluated base configurations
+// resident and answers each incoming configuration with E_base + dE(base -> incoming) from ONE batched
+// trial launch.  An incoming configuration is matched with the base in its own slot first, then with any
+// other base of similar size (replica exchange swaps configurations between slots).  When some
+// configuration differs from every base by more than a few atoms, the whole incoming batch is
+// evaluated in full and becomes the new set of bases.  paths_out[r] (may be NULL): 0 full,
+// 1 incremental, 2 identical to its base.
+int mcpyb_tracked_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
+                                const int32_t* numbers, const double* cells, const uint8_t* pbc,
+                                double* energies_out, int* paths_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (R < 0 || (R > 0 && (!atom_off || !cells || !pbc || !energies_out))) return e->fail(MCPYB_ERR_ARG, "bad arguments");
+    if (e->pot_kind == POT_NONE) return e->fail(MCPYB_ERR_STATE, "no potential set");
+    if (R == 0) return MCPYB_OK;
+    const int kLimit = 16;                       // moved atoms (old + new) per configuration before a re-base
+    const int Rb = e->trkb_valid ? (int)e->trkb_E.size() : 0;
+    bool incremental = e->trkb_valid && e->have_batch && e->R == Rb && Rb > 0;
+    std::vector<int32_t> t_rep, t_old_off(1, 0), t_new_off(1, 0), t_old_idx, t_new_Z;
+    std::vector<double> t_new_pos;
+    std::vector<int> slot_of(R, -1), trial_of(R, -1);
+    if (incremental) {
+        int32_t old_idx[kLimit];
+        int new_row[kLimit];
+        for (int r = 0; r < R && incremental; ++r) {
+            const int n = (int)(atom_off[r + 1] - atom_off[r]);
+            const double* P = positions + 3 * atom_off[r];
+            const int32_t* PZ = numbers ? numbers + atom_off[r] : nullptr;
+            int n_old = 0, n_new = 0, found = -1;
+            for (int probe = 0; probe <= Rb && found < 0; ++probe) {
+                const int q = probe == 0 ? r : probe - 1;                 // own slot first
+                if (q >= Rb || (probe > 0 && q == r)) continue;
+                const int nB = (int)(e->trkb_off[q + 1] - e->trkb_off[q]);
+                if (abs(nB - n) > kLimit) continue;
+                if (memcmp(&e->trkb_cell[9 * (size_t)q], cells + 9 * (size_t)r, 9 * sizeof(double)) != 0 ||
+                    memcmp(&e->trkb_pbc[3 * (size_t)q], pbc + 3 * (size_t)r, 3) != 0) continue;
+                if (align_rows(&e->trkb_pos[3 * (size_t)e->trkb_off[q]], &e->trkb_Z[(size_t)e->trkb_off[q]], nB,
+                               P, PZ, n, kLimit, old_idx, new_row, n_old, n_new)) found = q;
+            }
+            if (found < 0) { incremental = false; break; }
+            slot_of[r] = found;
+            if (n_old == 0 && n_new == 0) continue;                       // identical to its base
+            trial_of[r] = (int)t_rep.size();
+            t_rep.push_back(found);
+            for (int k = 0; k < n_old; ++k) t_old_idx.push_back(old_idx[k]);
+            for (int k = 0; k < n_new; ++k) {
+                for (int c = 0; c < 3; ++c) t_new_pos.push_back(P[3 * new_row[k] + c]);
+                t_new_Z.push_back(PZ ? PZ[new_row[k]] : 0);
+            }
+            t_old_off.push_back((int32_t)t_old_idx.size());
+            t_new_off.push_back((int32_t)t_new_Z.size());
+        }
+    }
+    if (incremental) {
+        const int T = (int)t_rep.size();
+        std::vector<double> dE((size_t)(T > 0 ? T : 1), 0.0);
+        bool finite = true;
+        if (T > 0) {
+            const bool keep = e->trkb_valid;
+            int rc = mcpyb_trial_delta_e_host(e, T, t_rep.data(), t_old_off.data(), t_old_idx.data(), t_new_off.data(),
+                                              t_new_pos.data(), numbers ? t_new_Z.data() : nullptr, dE.data(), nullptr);
+            e->trkb_valid = keep;
+            if (rc != MCPYB_OK) return rc;
+            if (e->pot_kind == POT_EMT) for (int t = 0; t < T; ++t) finite = finite && isfinite(dE[t]);   // thin box -> NaN
+        }
+        if (finite) {
+            for (int r = 0; r < R; ++r) {
+                energies_out[r] = e->trkb_E[slot_of[r]] + (trial_of[r] >= 0 ? dE[trial_of[r]] : 0.0);
+                if (paths_out) paths_out[r] = trial_of[r] >= 0 ? 1 : 2;
+            }
+            e->trk_incremental += T;
+            return MCPYB_OK;
+        }
+    }
+    // full evaluation; the incoming batch becomes the set of bases
+    int rc = mcpyb_potential_energies_host(e, R, atom_off, positions, numbers, cells, pbc, energies_out);
+    if (rc != MCPYB_OK) return rc;
+    const size_t total = (size_t)atom_off[R];
+    e->trkb_pos.assign(positions, positions + 3 * total);
+    e->trkb_Z.assign(total, 0);
+    if (numbers) e->trkb_Z.assign(numbers, numbers + total);
+    e->trkb_off.assign(atom_off, atom_off + R + 1);
+    e->trkb_cell.assign(cells, cells + 9 * (size_t)R);
+    e->trkb_pbc.assign(pbc, pbc + 3 * (size_t)R);
+    e->trkb_E.assign(energies_out, energies_out + R);
+    e->trkb_valid = true;
+    e->trk_full += R;
+    if (paths_out) for (int r = 0; r < R; ++r) paths_out[r] = 0;
     return MCPYB_OK;
 }
 

@@ -107,8 +107,9 @@ class Engine:
         for r, p in enumerate(positions_list):
             off[r + 1] = off[r] + len(p)
         if R and off[-1]:
-            pos = np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in positions_list])
-            num = np.concatenate([np.asarray(z, dtype=np.int32).reshape(-1) for z in numbers_list])
+            # one concatenation and one dtype conversion for the whole batch
+            pos = np.concatenate(positions_list).reshape(-1, 3)
+            num = np.concatenate(numbers_list).reshape(-1)
         else:
             pos = np.zeros((0, 3))
             num = np.zeros(0, dtype=np.int32)
@@ -155,6 +156,18 @@ class Engine:
         self._R = R
         self._ntot = int(off[-1])
         return E
+
+    def tracked_energies(self, positions_list, numbers_list, cells, pbcs):
+        """Batch through the incremental path (resident bases + one batched delta launch); returns
+        ``(energies, paths)`` with paths 0 = full evaluation, 1 = incremental, 2 = identical to its base."""
+        R, off, pos, num, cells, pbcs = self._batch_args(positions_list, numbers_list, cells, pbcs)
+        E = np.empty(R, dtype=np.float64)
+        paths = np.zeros(R, dtype=np.int32)
+        self._check(self._lib.mcpyb_tracked_energies_host(
+            self._h, R, ptr(off), ptr(pos), ptr(num), ptr(cells), ptr(pbcs), ptr(E), ptr(paths)))
+        self._R = R
+        self._ntot = int(off[-1])
+        return E, paths
 
     def potential_energy(self, positions, numbers, cell, pbc) -> float:
         """Single configuration, minimal marshalling (the per-trial drop-in call)."""

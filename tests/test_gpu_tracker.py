@@ -59,3 +59,56 @@ def test_tracked_chain_equals_full_evaluations(potential):
         e_t, path = trk.tracked_energy(pos, num, cell2, pbc)
         assert path == 0 and abs(e_t - full.potential_energy(pos, num, cell2, pbc)) <= 1e-10 * max(1.0, abs(e_t))
     trk.close(); full.close()
+
+
+@pytest.mark.parametrize('potential', ['lj', 'emt'])
+def test_tracked_batch_equals_full_evaluations(potential):
+    """get_potential_energies through resident bases: per-replica moves that accumulate, replicas
+    swapping slots (replica exchange), ragged sizes, a subset of the replicas, a re-base."""
+    rng = np.random.default_rng(23)
+    R = 6
+    if potential == 'lj':
+        cfgs = [synthetic.s2_lj(300 + 7 * r, 3.0, 0.5, seed=50 + r) for r in range(R)]
+        setup = lambda e: e.set_lj(1.0, 1.0, 3.0)
+        new_Z, step = 1, 0.4
+    else:
+        cfgs = [synthetic.s3_ag_o() for _ in range(R)]
+        for r, c in enumerate(cfgs):
+            c['positions'] = c['positions'] + rng.normal(0, 0.02, c['positions'].shape)
+        setup = lambda e: e.set_emt()
+        new_Z, step = 8, 0.3
+    trk, full = Engine(0), Engine(0)
+    setup(trk); setup(full)
+    pos = [c['positions'].copy() for c in cfgs]
+    num = [np.asarray(c['numbers'], np.int32).copy() for c in cfgs]
+    cells = np.stack([c['cell'].reshape(9) for c in cfgs])
+    pbcs = np.stack([c['pbc'] for c in cfgs])
+    paths = np.zeros(3, int)
+    for it in range(60):
+        tp, tn = [p.copy() for p in pos], [z.copy() for z in num]
+        for r in range(R):                                  # one trial move per replica
+            kind = rng.integers(3)
+            if kind == 0:
+                i = rng.integers(len(tp[r])); tp[r][i] += rng.uniform(-step, step, 3)
+            elif kind == 1:
+                p = tp[r][rng.integers(len(tp[r]))] + rng.uniform(-2.5, 2.5, 3)
+                tp[r] = np.concatenate([tp[r], [p]]); tn[r] = np.concatenate([tn[r], [new_Z]]).astype(np.int32)
+            elif len(tp[r]) > 5:
+                i = rng.integers(len(tp[r])); tp[r] = np.delete(tp[r], i, axis=0); tn[r] = np.delete(tn[r], i)
+        sel = list(range(R)) if it % 11 else [0, 2, 3]      # sometimes only a subset is evaluated
+        e_t, pth = trk.tracked_energies([tp[r] for r in sel], [tn[r] for r in sel], cells[sel], pbcs[sel])
+        e_f = full.potential_energies([tp[r] for r in sel], [tn[r] for r in sel], cells[sel], pbcs[sel])
+        assert np.all(np.abs(e_t - e_f) <= 1e-10 * np.maximum(1.0, np.abs(e_f))), (it, e_t - e_f)
+        for x in pth:
+            paths[x] += 1
+        for r in sel:                                       # accept about half of the moves
+            if rng.random() < 0.5:
+                pos[r], num[r] = tp[r], tn[r]
+        if it % 9 == 8:                                     # replica exchange: two slots swap configurations
+            i, j = rng.choice(R, 2, replace=False)
+            pos[i], pos[j] = pos[j], pos[i]
+            num[i], num[j] = num[j], num[i]
+            if potential == 'lj':                           # boxes differ per replica: they travel with the configuration
+                cells[[i, j]] = cells[[j, i]]
+    assert paths[1] > 150 and paths[0] >= R                 # mostly incremental, re-based at least once
+    trk.close(); full.close()
