@@ -1019,7 +1019,7 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
     if (e->pot_kind == POT_NONE) return e->fail(MCPYB_ERR_STATE, "no potential set");
     if (e->pot_kind == POT_EMT && n > 0 && !numbers) return e->fail(MCPYB_ERR_ARG, "EMT needs atomic numbers");
     const double tol = 1e-10;
-    const int kRebase = 8;                       // moved atoms (old + new) beyond which we re-base
+    const int kRebase = 16;                      // moved atoms (old + new) beyond which we re-base
     auto zof = [&](int j) { return numbers ? numbers[j] : 0; };
     bool same_box = e->trk_valid && memcmp(e->trk_cell, cell9, sizeof e->trk_cell) == 0 &&
                     memcmp(e->trk_pbc, pbc3, 3) == 0 && e->have_batch && e->R == 1;

@@ -331,46 +331,57 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
                 }
                 const int n = nst;
                 if (warp_active) {
-                    // U candidates per trip, branch-free unless some lane needs the rare fix-ups, so the
-                    // U dependent FP64 chains interleave
+                    // U candidates per trip, branch-free, so the U dependent FP64 chains interleave.  The
+                    // trip is handed to `rare` when some lane has a candidate whose high word of r2 falls
+                    // in the window [hi(lo_bits), hi(hi_bits)] (full compare, exact re-check) or belongs
+                    // to a multi-atom move (exclusion list).
+                    const unsigned amb_width = (unsigned)(hi_hi - lo_hi);
+                    auto rare = [&](int i, int U) {
+                        for (int u = 0; u < U; ++u) {
+                            const double4 q = sm.candd[i + u];
+                            const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
+                            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                            const long long rb = __double_as_longlong(r2);
+                            bool in = rb < lo_bits;
+                            if (!in && rb <= hi_bits)        // within rounding of the cutoff: the oracle's arithmetic decides
+                                in = rb_exact_r2(g, spos, sm.pc, sm.cinfo[i + u], px, py, pz, wsite) <= p.rc2;
+                            const int j = __double2loint(q.w);
+                            in = in && (j != ex0);
+                            if (multi && in)
+                                for (int e = ob + 1; e < oe; ++e) if (tb.old_idx[e] == j) in = false;
+                            const double rm = __hiloint2double(in ? __double2hiint(r2) : 0x7fe00000, __double2loint(r2));
+                            const double t = p.sigma2 * fast_rcp(rm);
+                            const double c6 = t * t * t;
+                            acc12 = fma(c6, c6, acc12);
+                            acc6 += c6;
+                            cnt += in ? 1 : 0;
+                        }
+                    };
                     auto visit = [&](int i, auto U_) {
                         constexpr int U = decltype(U_)::value;
                         double r2[U];
-                        int jj[U];
-                        bool in[U];
-                        bool fix = multi;
+                        int jj[U], rh[U];
+                        unsigned amb = multi ? 0u : 0xffffffffu;   // min over the trip of (hi(r2) - lo_hi), unsigned
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
                             const double4 q = sm.candd[i + u];    // uniform address: two broadcast LDS.128
                             const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
                             r2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
-                            const int rh = __double2hiint(r2[u]);  // positive doubles order like their bits
-                            in[u] = rh < lo_hi;
-                            fix = fix || (!in[u] && rh <= hi_hi);  // high word ties: full compare below
+                            rh[u] = __double2hiint(r2[u]);        // positive doubles order like their bits
+                            amb = min(amb, (unsigned)(rh[u] - lo_hi));
                             jj[u] = __double2loint(q.w);
                         }
-                        if (__any_sync(0xffffffffu, fix)) {
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                const long long rb = __double_as_longlong(r2[u]);
-                                in[u] = rb < lo_bits;
-                                // within rounding of the cutoff: the oracle's arithmetic decides
-                                if (!in[u] && rb <= hi_bits)
-                                    in[u] = rb_exact_r2(g, spos, sm.pc, sm.cinfo[i + u], px, py, pz, wsite) <= p.rc2;
-                                if (multi && in[u])
-                                    for (int e = ob + 1; e < oe; ++e) if (tb.old_idx[e] == jj[u]) in[u] = false;
-                            }
-                        }
+                        if (__any_sync(0xffffffffu, amb <= amb_width)) { rare(i, U); return; }
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
-                            const bool hit = in[u] && (jj[u] != ex0);
+                            const bool hit = rh[u] < lo_hi && jj[u] != ex0;
                             // a miss is evaluated at r2 ~ 9e307: its reciprocal flushes to zero, so c6 = 0
-                            const double rm = __hiloint2double(hit ? __double2hiint(r2[u]) : 0x7fe00000, __double2loint(r2[u]));
+                            const double rm = __hiloint2double(hit ? rh[u] : 0x7fe00000, __double2loint(r2[u]));
                             const double t = p.sigma2 * fast_rcp(rm);
                             const double c6 = t * t * t;
                             acc12 = fma(c6, c6, acc12);
                             acc6 += c6;
-                            cnt += hit ? 1 : 0;
+                            if (hit) ++cnt;
                         }
                     };
                     int i = 0;
