@@ -10,7 +10,10 @@
 #include <string>
 #include <vector>
 
-#include <chrono>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include "../../include/mcpy_b200.h"
 #include "common.cuh"
 #include "cell_list.cuh"
@@ -67,6 +70,62 @@ struct PinBuf {
         return e;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// A few helper threads for the large host-side copies of the batched calls (user arrays -> pinned
+// staging and back): one core moves ~20 GB/s, which made the staging copy the longest single item of an
+// end-to-end trial call.  Workers sleep on a condition variable between calls.
+class CopyPool {
+public:
+    explicit CopyPool(int nworkers) {
+        for (int i = 0; i < nworkers; ++i) threads_.emplace_back([this]() { loop(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    // memcpy(dst, src, n) split over the workers and the caller
+    void copy(void* dst, const void* src, size_t n) {
+        const size_t min_part = 128u << 10;
+        int parts = (int)(n / min_part);
+        if (parts > (int)threads_.size() + 1) parts = (int)threads_.size() + 1;
+        if (parts <= 1) { memcpy(dst, src, n); return; }
+        const size_t each = ((n / parts) + 63) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (int p = 1; p < parts; ++p) {
+                const size_t beg = each * p, len = (p == parts - 1) ? n - beg : each;
+                jobs_.push_back({(unsigned char*)dst + beg, (const unsigned char*)src + beg, len});
+            }
+            pending_.fetch_add(parts - 1);
+        }
+        cv_.notify_all();
+        memcpy(dst, src, each);
+        while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    }
+private:
+    struct Job { unsigned char* dst; const unsigned char* src; size_t n; };
+    void loop() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [this]() { return stop_ || !jobs_.empty(); });
+                if (stop_ && jobs_.empty()) return;
+                j = jobs_.back();
+                jobs_.pop_back();
+            }
+            memcpy(j.dst, j.src, j.n);
+            pending_.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::vector<Job> jobs_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::atomic<int> pending_{0};
+    bool stop_ = false;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -160,6 +219,8 @@ struct mcpyb_engine {
     long long stage_calls = 0;
 
     // trial staging
+    CopyPool* copy_pool = nullptr;        // created on the first large batched call
+    bool trial_staging_busy = false;      // a host trial call returned early with copies in flight
     cudaEvent_t trial_ev = nullptr;
     DevBuf<unsigned char> trial_dev;
     PinBuf trial_pin, trial_out_pin;
@@ -469,6 +530,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     e->fv_cid.release(); e->fv_points.release(); e->fv_pos.release(); e->fv_radii.release(); e->fv_small.release();
     e->fv_counts.release(); e->fv_mask.release(); e->fv_pin.release(); e->fv_atoms_pin.release(); e->fv_out_pin.release();
     e->pcg_count.release(); e->pcg_prefix.release(); e->pcg_ctl.release();
+    delete e->copy_pool;
     if (e->trial_ev) cudaEventDestroy(e->trial_ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -568,6 +630,16 @@ int mcpyb_emt_species(const mcpyb_engine* e, int Z, double* out9) {
     return MCPYB_OK;
 }
 
+// helper threads for host copies of a megabyte or more (nullptr: copy inline)
+static CopyPool* copy_pool_for(mcpyb_engine* e, size_t bytes) {
+    if (bytes < (1u << 20)) return nullptr;
+    if (!e->copy_pool) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        e->copy_pool = new CopyPool(hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
+    }
+    return e->copy_pool;
+}
+
 static int upload_host_impl(mcpyb_engine* e, int subdiv, int R, const int64_t* atom_off, const double* positions,
                             const int32_t* numbers, const double* cells, const uint8_t* pbc) {
     if (!e) return MCPYB_ERR_ARG;
@@ -597,7 +669,9 @@ static int upload_host_impl(mcpyb_engine* e, int subdiv, int R, const int64_t* a
     rc = fill_header(e, R, atom_off, cells, pbc, e->stage_pin.p);
     if (rc != MCPYB_OK) return rc;
     if (total > 0) {
-        memcpy(e->stage_pin.p + hb, positions, (size_t)total * 3 * sizeof(double));
+        CopyPool* pool = copy_pool_for(e, (size_t)total * 24);
+        if (pool) pool->copy(e->stage_pin.p + hb, positions, (size_t)total * 3 * sizeof(double));
+        else memcpy(e->stage_pin.p + hb, positions, (size_t)total * 3 * sizeof(double));
         if (numbers) memcpy(e->stage_pin.p + hb + pb, numbers, (size_t)total * sizeof(int32_t));
     }
     CK(cudaMemcpyAsync(e->stage_dev.p, e->stage_pin.p, bytes, cudaMemcpyHostToDevice, e->stream), "H2D batch");
@@ -928,7 +1002,14 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
     size_t o_nz = align_up(o_oi + (size_t)n_old * 4, 16);
     size_t o_np = align_up(o_nz + (size_t)n_new * 4, 16);
     size_t bytes = align_up(o_np + (size_t)n_new * 24, 64);
-    CK(cudaStreamSynchronize(e->stream), "sync before trial staging reuse");
+    // every host trial call ends with a stream synchronisation, so the staging buffers are free here
+    // unless a call returned early
+    if (e->trial_staging_busy) CK(cudaStreamSynchronize(e->stream), "sync before trial staging reuse");
+    e->trial_staging_busy = true;
+    CopyPool* pool = copy_pool_for(e, bytes);
+    auto hcopy = [&](void* dst, const void* src, size_t nbytes) {
+        if (pool) pool->copy(dst, src, nbytes); else memcpy(dst, src, nbytes);
+    };
     CK(e->trial_pin.reserve(bytes), "cudaMallocHost trials");
     CK(e->trial_dev.reserve(bytes), "cudaMalloc trials");
     CK(e->dE.reserve((size_t)T + 1), "cudaMalloc dE");          // dE[T] carries the device status word
@@ -940,7 +1021,7 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
         const size_t piece = 512u << 10;
         for (size_t done = 0; done < nbytes; done += piece) {
             const size_t nb = nbytes - done < piece ? nbytes - done : piece;
-            memcpy(h + off + done, (const unsigned char*)src + done, nb);
+            hcopy(h + off + done, (const unsigned char*)src + done, nb);
             cudaError_t ce = cudaMemcpyAsync(d + off + done, h + off + done, nb, cudaMemcpyHostToDevice, e->stream);
             if (ce != cudaSuccess) return ce;
         }
@@ -995,10 +1076,11 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
             return e->fail(MCPYB_ERR_ARG, "trial %d: atom index out of range", t);
         }
     }
-    memcpy(dE_out, e->trial_out_pin.p, half);
+    hcopy(dE_out, e->trial_out_pin.p, half);
     if (!small) CK(cudaStreamSynchronize(e->stream), "sync trials");
-    memcpy((unsigned char*)dE_out + half, e->trial_out_pin.p + half, full - half);
+    hcopy((unsigned char*)dE_out + half, e->trial_out_pin.p + half, full - half);
     if (pairs_out) memcpy(pairs_out, e->trial_out_pin.p + ob, pb);
+    e->trial_staging_busy = false;
     return MCPYB_OK;
 }
 
