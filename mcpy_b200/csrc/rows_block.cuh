@@ -237,7 +237,10 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
             }
             const double bw = p.rc2 * band * 2.220446049250313e-16;
             const long long lo_bits = __double_as_longlong(p.rc2 - bw), hi_bits = __double_as_longlong(p.rc2 + bw);
-            const bool multi = (oe - ob) > 1;
+            // moves of up to two atoms (atomic moves, diatomic molecules) exclude through two registers;
+            // larger rigid molecules walk their exclusion list on the slow path
+            const bool multi = (oe - ob) > 2;
+            const int ex1 = (oe - ob) > 1 ? tb.old_idx[ob + 1] : -1;
 
             // ---- bounding box of this CTA's (wrapped) sites, rounded outward to fp32.  A candidate
             // farther than rc from the box is farther than rc from every site: it is dropped at staging
@@ -346,9 +349,9 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
                             if (!in && rb <= hi_bits)        // within rounding of the cutoff: the oracle's arithmetic decides
                                 in = rb_exact_r2(g, spos, sm.pc, sm.cinfo[i + u], px, py, pz, wsite) <= p.rc2;
                             const int j = __double2loint(q.w);
-                            in = in && (j != ex0);
+                            in = in && (j != ex0) && (j != ex1);
                             if (multi && in)
-                                for (int e = ob + 1; e < oe; ++e) if (tb.old_idx[e] == j) in = false;
+                                for (int e = ob + 2; e < oe; ++e) if (tb.old_idx[e] == j) in = false;
                             const double rm = __hiloint2double(in ? __double2hiint(r2) : 0x7fe00000, __double2loint(r2));
                             const double t = p.sigma2 * fast_rcp(rm);
                             const double c6 = t * t * t;
@@ -374,7 +377,7 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
                         if (__any_sync(0xffffffffu, amb <= amb_width)) { rare(i, U); return; }
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
-                            const bool hit = rh[u] < lo_hi && jj[u] != ex0;
+                            const bool hit = rh[u] < lo_hi && jj[u] != ex0 && jj[u] != ex1;
                             // a miss is evaluated at r2 ~ 9e307: its reciprocal flushes to zero, so c6 = 0
                             const double rm = __hiloint2double(hit ? rh[u] : 0x7fe00000, __double2loint(r2[u]));
                             const double t = p.sigma2 * fast_rcp(rm);
