@@ -178,6 +178,7 @@ struct mcpyb_engine {
     int max_cells = 0;
     bool have_batch = false;
     bool emt_state_valid = false;     // sigma1 / e_atom describe the resident batch
+    bool status_checked = false;      // the build status of the resident batch has been read back
     std::vector<int> atom_off_host;
     DevBuf<GridDesc> grid;
     DevBuf<double4> upos, spos, stmp;
@@ -401,6 +402,7 @@ int upload_common(mcpyb_engine* e, int R, const int64_t* atom_off, const double*
     e->d_atom_off = d_off;          // stays valid in stage_dev until the next upload
     e->have_batch = true;
     e->emt_state_valid = false;
+    e->status_checked = false;
     return MCPYB_OK;
 }
 
@@ -744,6 +746,7 @@ int mcpyb_energies_host(mcpyb_engine* e, double* energies_out, int64_t* pairs_ou
     }
     memcpy(energies_out, e->out_pin.p, eb);
     if (pairs_out) memcpy(pairs_out, e->out_pin.p + eb, pb);
+    e->status_checked = true;
     return MCPYB_OK;
 }
 
@@ -806,7 +809,14 @@ static int launch_forces(mcpyb_engine* e) {
 int mcpyb_forces_host(mcpyb_engine* e, double* forces_out) {
     if (!e) return MCPYB_ERR_ARG;
     cudaSetDevice(e->device);
-    int rc = launch_forces(e);
+    int rc;
+    if (!e->status_checked) {
+        // species / geometry errors of the resident batch surface through the energy path's status
+        std::vector<double> tmp((size_t)(e->R > 0 ? e->R : 1));
+        rc = mcpyb_energies_host(e, tmp.data(), nullptr);
+        if (rc != MCPYB_OK) return rc;
+    }
+    rc = launch_forces(e);
     if (rc != MCPYB_OK) return rc;
     const size_t nb = 3 * (size_t)e->total_atoms * sizeof(double);
     if (nb == 0) return MCPYB_OK;
@@ -814,8 +824,6 @@ int mcpyb_forces_host(mcpyb_engine* e, double* forces_out) {
     CK(e->out_pin.reserve(nb), "cudaMallocHost out");
     CK(cudaMemcpyAsync(e->out_pin.p, e->forces.p, nb, cudaMemcpyDeviceToHost, e->stream), "D2H forces");
     CK(cudaStreamSynchronize(e->stream), "sync forces");
-    int st = 0;                           // species / geometry errors surface through the energy path's status
-    (void)st;
     memcpy(forces_out, e->out_pin.p, nb);
     return MCPYB_OK;
 }
@@ -867,8 +875,6 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     TrialBatch tb;
     tb.T = T; tb.rep = d_rep; tb.old_off = d_old_off; tb.old_idx = d_old_idx;
     tb.new_off = d_new_off; tb.new_pos = d_new_pos; tb.new_Z = d_new_Z;
-    // One warp per trial whatever T is: the summation order of a trial -- and therefore
-    // every bit of its delta-E -- does not depend on the batch it arrives in.
     int blocks = (T + 7) / 8;
     if (blocks > 148 * 32) blocks = 148 * 32;
     if (e->pot_kind == POT_EMT && !e->emt_state_valid) {
