@@ -16,6 +16,11 @@ Fixtures (small, committed):
   emt_sphere_trace.npz -- 220 trials of Ag octahedron + O GCMC with EMT in a SphericalCell:
                          the same, plus every free-volume refresh (PCG64 state before, atoms,
                          resulting volume).
+  insertion_trace.npz -- reference InsertionMove / MoleculeInsertionMove with min_insert.
+  molecule_moves_trace.npz -- reference MoleculeDisplacementMove (free and capped rotation) and
+                         MoleculeDeletionMove on dimers in a periodic box and in a SphericalCell,
+                         with atoms.wrap() between moves: configuration, molecule ids, Python
+                         MT19937 state, outcome and last_exchange_count after every proposal.
 """
 import os
 import sys
@@ -32,7 +37,7 @@ from ase.cluster import Octahedron  # noqa: E402
 from mcpy.cell import Cell, SphericalCell  # noqa: E402
 from mcpy.ensembles import GrandCanonicalEnsemble  # noqa: E402
 from mcpy.moves import (DeletionMove, DisplacementMove, InsertionMove, MoleculeInsertionMove,  # noqa: E402
-                        MoveSelector)
+                        MoleculeDeletionMove, MoleculeDisplacementMove, MoveSelector)
 from oracle import cfast  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -202,7 +207,72 @@ def insertion_trace():
     print('insertion trace:', int(np.sum(out['atom_ok'])), 'of 12 atoms,', int(np.sum(out['mol_ok'])), 'of 8 dimers placed')
 
 
+def molecule_system(kind):
+    """60 atoms + 24 dimers; 'box': periodic cube with the whole-box Cell, 'sphere': open cluster in a
+    SphericalCell.  Returned together with the cell (shared by the generator and the replay test)."""
+    rng = np.random.default_rng(12)
+    L = 9.0
+    free = rng.uniform(0, L, size=(60, 3))
+    centres = rng.uniform(0, L, size=(24, 3))
+    axes = rng.normal(size=(24, 3))
+    axes /= np.linalg.norm(axes, axis=1)[:, None]
+    pos = [free]
+    ids = [np.full(60, -1)]
+    for m in range(24):
+        pos.append(np.array([centres[m] - 0.45 * axes[m], centres[m] + 0.45 * axes[m]]))
+        ids.append(np.full(2, m))
+    pos = np.concatenate(pos)
+    symbols = ['H'] * 60 + ['C', 'O'] * 24
+    if kind == 'box':
+        a = Atoms(symbols, positions=pos, cell=[L, L, L], pbc=True)
+        a.wrap()
+        a.new_array('molecule_id', np.concatenate(ids).astype(int))
+        c = Cell(a, species_radii={'H': 1.0, 'C': 0.0, 'O': 0.0}, seed=21)
+    else:
+        a = Atoms(symbols, positions=pos - pos.mean(axis=0), cell=[0, 0, 0], pbc=False)
+        a.new_array('molecule_id', np.concatenate(ids).astype(int))
+        c = SphericalCell(a, vacuum=-3.0, species_radii={'H': 1.0, 'C': 0.0, 'O': 0.0}, mc_sample_points=1000, seed=22)
+    return a, c
+
+
+def molecule_moves_trace():
+    out = {}
+    co = Atoms('CO', positions=[[0, 0, 0], [0, 0, 0.9]])
+    for kind in ('box', 'sphere'):
+        a, c = molecule_system(kind)
+        moves = [MoleculeDisplacementMove(c, co, 'CO', seed=31, max_displacement=0.6),
+                 MoleculeDisplacementMove(c, co, 'CO', seed=32, max_displacement=0.4, max_angle=0.6),
+                 MoleculeDeletionMove(c, co, 'CO', seed=33, min_molecules=3)]
+        order = np.random.default_rng(7).integers(0, 3, size=60)
+        order[order == 2] = np.where(np.random.default_rng(8).random(np.sum(order == 2)) < 0.5, 2, 0)
+        pos, off, ok, states, counts, idsout = [], [0], [], [], [], []
+        for k in order:
+            m = moves[int(k)]
+            r = m.do_trial_move(a)
+            ok.append(r[0] is not False)
+            if r[0] is not False and kind == 'box':
+                a.wrap()                                   # accepted periodic moves are wrapped by the ensemble
+            pos.append(a.positions.copy())
+            off.append(off[-1] + len(a))
+            idsout.append(np.asarray(a.arrays['molecule_id']).copy())
+            states.append(np.array(m.rng.random.getstate()[1], dtype=np.uint64))
+            lc = getattr(m, 'last_exchange_count', None)
+            counts.append(-1 if lc is None else lc)
+        out.update({f'{kind}_order': order, f'{kind}_pos': np.concatenate(pos), f'{kind}_off': np.array(off),
+                    f'{kind}_ok': np.array(ok), f'{kind}_state': np.array(states),
+                    f'{kind}_count': np.array(counts), f'{kind}_ids': np.concatenate(idsout)})
+        print(f'molecule trace ({kind}):', int(np.sum(ok)), 'of', len(order), 'proposals made;',
+              len(a), 'atoms left')
+    np.savez_compressed(os.path.join(OUT, 'molecule_moves_trace.npz'), **out)
+
+
 if __name__ == '__main__':
-    lj_trace()
-    emt_trace()
-    insertion_trace()
+    which = sys.argv[1:] or ['lj', 'emt', 'insertion', 'molecules']
+    if 'lj' in which:
+        lj_trace()
+    if 'emt' in which:
+        emt_trace()
+    if 'insertion' in which:
+        insertion_trace()
+    if 'molecules' in which:
+        molecule_moves_trace()
