@@ -185,6 +185,15 @@ int mcpyb_sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
                                    const double* center3, const double* positions,
                                    const double* radii, int64_t M,
                                    int64_t* counts_out, int64_t* draws_out);
+/* DomeCell.calculate_volume (mcpy/cell/dome_cell.py:106-138): the same full-ball stream as the
+ * sphere call, but a point with z < bottom_z is drawn and then ignored.  counts_out[0] = free points
+ * at or above bottom_z, counts_out[1] = covered points at or above it; the reference normalises by
+ * the full-ball P (dome_cell.py:136).                                               */
+int mcpyb_dome_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
+                                 const uint64_t* inc_hi_lo, int64_t P, double radius,
+                                 const double* center3, double bottom_z, const double* positions,
+                                 const double* radii, int64_t M,
+                                 int64_t* counts_out, int64_t* draws_out);
 int mcpyb_box_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
                                 const uint64_t* inc_hi_lo, int64_t P, const double* dims9,
                                 const double* positions, const double* radii, int64_t M,

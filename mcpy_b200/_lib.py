@@ -26,7 +26,7 @@ SYMBOLS = [
     'mcpyb_trial_delta_e_host', 'mcpyb_trial_delta_e_dev',
     'mcpyb_neighbor_pairs_host',
     'mcpyb_free_volume_count_host', 'mcpyb_free_volume_count_dev',
-    'mcpyb_sphere_free_volume_pcg64', 'mcpyb_box_free_volume_pcg64',
+    'mcpyb_sphere_free_volume_pcg64', 'mcpyb_dome_free_volume_pcg64', 'mcpyb_box_free_volume_pcg64',
     'mcpyb_min_dist2_host', 'mcpyb_pcg64_host_doubles', 'mcpyb_fp64_peak_tflops', 'mcpyb_stage_timing', 'mcpyb_launch_count',
 ]
 
@@ -86,6 +86,8 @@ def load():
                                                 C.c_int, _p]
     lib.mcpyb_sphere_free_volume_pcg64.argtypes = [_p, _p, _p, C.c_int64, C.c_double, _p, _p, _p,
                                                    C.c_int64, _p, _p]
+    lib.mcpyb_dome_free_volume_pcg64.argtypes = [_p, _p, _p, C.c_int64, C.c_double, _p, C.c_double, _p, _p,
+                                                 C.c_int64, _p, _p]
     lib.mcpyb_box_free_volume_pcg64.argtypes = [_p, _p, _p, C.c_int64, _p, _p, _p, C.c_int64, _p, _p,
                                                 C.c_int, _p]
     lib.mcpyb_min_dist2_host.argtypes = [_p, C.c_int, _p, C.c_int64, _p, _p]

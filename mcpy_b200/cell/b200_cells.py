@@ -174,6 +174,78 @@ class B200SphericalCell(_B200CellBase):
                                               self.sphere_volume)
 
 
+class B200DomeCell(B200SphericalCell):
+    """Drop-in for ``mcpy.cell.DomeCell`` (``dome_cell.py:8-138``): the ball around the centroid of
+    the particle species, clipped at the support surface ``z >= bottom_z``.  Unlike the spherical
+    cell it does NOT translate the atoms."""
+
+    def __init__(self, atoms, particle_species, bottom_z, vacuum, species_radii,
+                 mc_sample_points: int = 100_000, seed=None, engine=None, device=0, points='host'):
+        _B200CellBase.__init__(self, atoms, species_radii, seed, engine, device, points)
+        from ase.data import atomic_numbers
+        zs = [atomic_numbers[s] for s in self._species_list(particle_species) if s in atomic_numbers]
+        particle_mask = np.isin(np.asarray(atoms.numbers), zs)
+        if not particle_mask.any():
+            raise ValueError(
+                f'No atoms of particle_species={self._species_list(particle_species)} found in the cell.')
+        particle_pos = atoms.positions[particle_mask]
+        self.center = particle_pos.mean(axis=0)
+        self.bottom_z = float(bottom_z)
+        self.radius = float(np.linalg.norm(particle_pos - self.center, axis=1).max() + vacuum)
+        self.species_radii = species_radii
+        self.mc_sample_points = int(mc_sample_points)
+        self.sphere_volume = (4.0 / 3.0) * np.pi * (self.radius ** 3)
+        self.volume = self.sphere_volume
+
+    def is_point_inside(self, point):
+        if point[2] < self.bottom_z:
+            return False
+        d = point - self.center
+        return float(np.dot(d, d)) <= self.radius ** 2
+
+    def get_random_point(self):
+        """Full-ball cube-root sampler with rejection below the surface (``dome_cell.py:65-77``)."""
+        while True:
+            direction = self._rng.standard_normal(3)
+            direction /= np.linalg.norm(direction)
+            r = self.radius * (self._rng.random() ** (1.0 / 3.0))
+            point = self.center + r * direction
+            if point[2] >= self.bottom_z:
+                return point
+
+    def get_atoms_specie_inside_cell(self, atoms, specie):
+        if len(atoms) == 0:
+            return np.empty(0, dtype=int)
+        mask = self._species_mask(atoms, specie)
+        d = atoms.positions - self.center
+        mask &= np.einsum('ij,ij->i', d, d) <= self.radius ** 2
+        mask &= atoms.positions[:, 2] >= self.bottom_z
+        return np.where(mask)[0]
+
+    def calculate_volume(self, atoms):
+        """Free dome volume = (#uncovered points above the surface / P of the FULL ball) * sphere
+        volume, floored (``dome_cell.py:106-138``).  Without atoms: the dome fraction of the ball."""
+        n_atoms = len(atoms)
+        radii = self._radii_for(atoms) if n_atoms else np.empty(0)
+        if self.points == 'device':
+            n_free, n_cov = self.engine.dome_free_volume_pcg64(
+                self._rng, self.mc_sample_points, self.radius, self.center, self.bottom_z,
+                atoms.positions.reshape(-1, 3), radii)
+        else:
+            pts = self._sample_sphere_points(self.mc_sample_points)
+            pts = pts[pts[:, 2] >= self.bottom_z]
+            if n_atoms:
+                n_free, n_cov = self.engine.free_volume_count(pts, atoms.positions, radii)
+            else:
+                n_free, n_cov = len(pts), 0
+        self.last_counts = (n_free, n_cov)
+        if n_atoms == 0:
+            self.volume = (float(n_free) / self.mc_sample_points) * self.sphere_volume
+            return
+        free_fraction = float(n_free) / self.mc_sample_points
+        self.volume = self._clamp_free_volume(free_fraction * self.sphere_volume, self.sphere_volume)
+
+
 class B200CustomCell(_B200CellBase):
     """Drop-in for ``mcpy.cell.CustomCell`` (``custom_cell.py:7-162``)."""
 

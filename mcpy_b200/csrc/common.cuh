@@ -172,4 +172,11 @@ __device__ __forceinline__ float3 screen_pos(const GridDesc& g, double x, double
     return make_float3((float)xw, (float)yw, (float)zw);
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still draining; pdl_wait() blocks until the
+// predecessor has completed and its writes are visible, pdl_trigger() lets the successor start launching.
+// Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 #define MCPYB_CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)

@@ -21,6 +21,7 @@
 #include "lj_kernels.cuh"
 #include "site_kernels.cuh"
 #include "rows_block.cuh"
+#include "rows_pipe.cuh"
 #include "emt_kernels.cuh"
 #include "free_volume.cuh"
 #include "pcg64.cuh"
@@ -164,6 +165,22 @@ struct mcpyb_engine {
     int subdiv_trials = 1;                // ... wanted when trial moves will be scored against it
     int subdiv_energy = 1;                // ... wanted for upload + total energies in one call
     int rb_slices = 2;                    // candidate-list slices per work item of the CTA row-sum kernel
+    // tuning switches (environment, read once at creation; the defaults are the measured best):
+    //   MCPYB_ROWS=pipe    producer/consumer row-sum kernel (rows_pipe.cuh) instead of the CTA-per-cell one
+    //   MCPYB_PDL=0        ordinary stream-ordered launches instead of programmatic dependent launch
+    //   MCPYB_RB_SLICES=n  candidate-list slices per work item (1..8)
+    //   MCPYB_EXPAND=0     no per-configuration stencil lists (the producer warp stages from the cell list)
+    bool rows_pipe = false;
+    bool use_pdl = true;
+    bool use_expand = true;
+    int rows_pipe_blocks = RP_MIN_BLOCKS;
+    // stencil lists of the resident batch (rows_block.cuh): built when a SECOND trial batch is scored against
+    // the same resident configuration -- one batch per upload (the end-to-end pattern) does not amortise them
+    bool exp_valid = false;
+    int exp_batches = 0;                  // batched trial launches since the last upload
+    DevBuf<double4> exp_q;
+    DevBuf<int2> exp_info, exp_head;
+    DevBuf<unsigned long long> exp_cursor;
     double rcut = 0.0;
     LJParams lj{};
     EmtTable emt_host{};
@@ -403,6 +420,8 @@ int upload_common(mcpyb_engine* e, int R, const int64_t* atom_off, const double*
     e->have_batch = true;
     e->emt_state_valid = false;
     e->status_checked = false;
+    e->exp_valid = false;
+    e->exp_batches = 0;
     return MCPYB_OK;
 }
 
@@ -507,6 +526,15 @@ int mcpyb_create(int device, mcpyb_engine** out) {
     mcpyb_engine* e = new mcpyb_engine();
     e->device = device;
     { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) e->num_sms = sms; }
+    if (const char* v = getenv("MCPYB_ROWS")) e->rows_pipe = strcmp(v, "pipe") == 0;
+    if (const char* v = getenv("MCPYB_PDL")) e->use_pdl = atoi(v) != 0;
+    if (const char* v = getenv("MCPYB_EXPAND")) e->use_expand = atoi(v) != 0;
+    if (const char* v = getenv("MCPYB_RB_SLICES")) { const int n = atoi(v); if (n >= 1 && n <= 8) e->rb_slices = n; }
+    if (const char* v = getenv("MCPYB_RP_BLOCKS")) { const int n = atoi(v); if (n >= 1 && n <= 8) e->rows_pipe_blocks = n; }
+    cudaFuncSetAttribute(lj_trial_rows_pipe_kernel<RB_UNROLL, RP_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(RowsPipeSmem));
+    cudaFuncSetAttribute(lj_trial_rows_pipe_kernel<RB_UNROLL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(RowsPipeSmem));
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete e;
         return MCPYB_ERR_CUDA;
@@ -523,6 +551,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     cudaStreamSynchronize(e->stream);
     e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release(); e->stmp.release(); e->fpos.release();
     e->cid.release(); e->cell_start.release(); e->geom.release(); e->bbox.release();
+    e->exp_q.release(); e->exp_info.release(); e->exp_head.release(); e->exp_cursor.release();
     e->e_atom.release(); e->sigma1.release(); e->e_part.release(); e->deds.release(); e->forces.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
@@ -934,23 +963,75 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     CK(e->tw_meta.reserve(ns), "cudaMalloc trial work");
     w.item_tab = e->tw_items.p; w.sorted_pos = e->tw_spos.p; w.sorted_meta = e->tw_meta.p;
     auto mark = [&]() { if (e->stage_timing && e->stage_n < 6) cudaEventRecord(e->stage_ev[e->stage_n++], e->stream); };
+    // Programmatic dependent launch: each kernel of the pipeline may be scheduled while its predecessor
+    // drains (every one of them starts with pdl_wait()), which takes the launch gaps out of the step.
+    // Off while the stages are being timed one by one.
+    const bool pdl = e->use_pdl && !e->stage_timing;
+    cudaLaunchAttribute pdl_attr[1];
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    auto config = [&](int grid, int block, size_t smem) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
+        cfg.attrs = pdl_attr; cfg.numAttrs = pdl ? 1 : 0;
+        return cfg;
+    };
+    const BatchView bv = e->view();
+    StencilLists xl;
+    memset(&xl, 0, sizeof xl);
+    if (e->use_expand && (e->exp_valid || ++e->exp_batches >= 2)) {
+        // every cell's stencil as one ordered run of candidate records, once per resident configuration
+        long long cap = (long long)e->total_atoms * 128;          // (2m+1)^3 = 125 cells see each atom at m = 2
+        if (cap > (32LL << 20)) cap = 32LL << 20;                  // 1.3 GB; cells beyond it are staged on the fly
+        if (cap < 1) cap = 1;
+        CK(e->exp_q.reserve((size_t)cap), "cudaMalloc stencil lists");
+        CK(e->exp_info.reserve((size_t)cap), "cudaMalloc stencil lists");
+        CK(e->exp_head.reserve((size_t)w.nbins), "cudaMalloc stencil lists");
+        CK(e->exp_cursor.reserve(1), "cudaMalloc stencil lists");
+        xl.q = e->exp_q.p; xl.info = e->exp_info.p; xl.head = e->exp_head.p; xl.cursor = e->exp_cursor.p; xl.cap = cap;
+        if (!e->exp_valid) {
+            CK(cudaMemsetAsync(e->exp_cursor.p, 0, sizeof(unsigned long long), e->stream), "memset stencil cursor");
+            int blocks_x = (w.nbins + EX_WARPS - 1) / EX_WARPS;
+            if (blocks_x > e->num_sms * 8) blocks_x = e->num_sms * 8;
+            expand_stencils_kernel<<<blocks_x, 32 * EX_WARPS, 0, e->stream>>>(bv, xl, w.nbins, w.bin_stride);
+            LAUNCH_CHECK("expand_stencils_kernel");
+            e->exp_valid = true;
+        }
+    }
     mark();
-    trial_sites_kernel<<<(T + 255) / 256, 256, 0, e->stream>>>(e->view(), tb, w);
-    LAUNCH_CHECK("trial_sites_kernel");
+    { cudaLaunchConfig_t cfg = config((T + 255) / 256, 256, 0);
+      CK(cudaLaunchKernelEx(&cfg, trial_sites_kernel, bv, tb, w), "launch trial_sites_kernel"); e->launches++; }
     mark();
-    trial_scan_kernel<<<1, 1024, 0, e->stream>>>(w);
-    LAUNCH_CHECK("trial_scan_kernel");
+    { cudaLaunchConfig_t cfg = config(1, 1024, 0);
+      CK(cudaLaunchKernelEx(&cfg, trial_scan_kernel, w), "launch trial_scan_kernel"); e->launches++; }
     mark();
-    trial_scatter_kernel<<<(nsites + 255) / 256, 256, 0, e->stream>>>(tb, w);
-    LAUNCH_CHECK("trial_scatter_kernel");
+    { cudaLaunchConfig_t cfg = config((nsites + 255) / 256, 256, 0);
+      CK(cudaLaunchKernelEx(&cfg, trial_scatter_kernel, tb, w), "launch trial_scatter_kernel"); e->launches++; }
     mark();
     const long long est = (long long)max_items * w.nplanes;
-    const int rb = (int)(est < e->num_sms * RB_MIN_BLOCKS ? est : e->num_sms * RB_MIN_BLOCKS);
-    lj_trial_rows_block_kernel<RB_UNROLL, RB_MIN_BLOCKS><<<rb, RB_THREADS, 0, e->stream>>>(e->view(), tb, w, e->lj);
-    LAUNCH_CHECK("lj_trial_rows_block_kernel");
+    if (e->rows_pipe) {
+        // persistent producer / consumer CTAs (rows_pipe.cuh)
+        const long long cap = (long long)e->num_sms * e->rows_pipe_blocks;
+        cudaLaunchConfig_t cfg = config((int)(est < cap ? est : cap), RP_THREADS, sizeof(RowsPipeSmem));
+        if (e->rows_pipe_blocks <= 3)          // fewer CTAs per SM, no register spills
+            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_pipe_kernel<RB_UNROLL, 3>, bv, tb, w, e->lj, xl),
+               "launch lj_trial_rows_pipe_kernel");
+        else
+            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_pipe_kernel<RB_UNROLL, RP_MIN_BLOCKS>, bv, tb, w, e->lj, xl),
+               "launch lj_trial_rows_pipe_kernel");
+        e->launches++;
+    } else {
+        const int rb = (int)(est < e->num_sms * RB_MIN_BLOCKS ? est : e->num_sms * RB_MIN_BLOCKS);
+        cudaLaunchConfig_t cfg = config(rb, RB_THREADS, 0);
+        CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_block_kernel<RB_UNROLL, RB_MIN_BLOCKS>, bv, tb, w, e->lj, xl),
+           "launch lj_trial_rows_block_kernel");
+        e->launches++;
+    }
     mark();
-    lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
-    LAUNCH_CHECK("lj_trial_combine_kernel");
+    { cudaLaunchConfig_t cfg = config((T + 127) / 128, 128, 0);
+      CK(cudaLaunchKernelEx(&cfg, lj_trial_combine_kernel, bv, tb, w, e->lj, d_dE, d_pairs), "launch lj_trial_combine_kernel");
+      e->launches++; }
     mark();
     return MCPYB_OK;
 }
@@ -1518,12 +1599,13 @@ int mcpyb_free_volume_count_host(mcpyb_engine* e, const double* points, int64_t 
     return fv_read_counts(e, counts_out);
 }
 
-int mcpyb_sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo,
-                                   int64_t P, double radius, const double* center3, const double* positions,
-                                   const double* radii, int64_t M, int64_t* counts_out, int64_t* draws_out) {
+static int sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo,
+                                    int64_t P, double radius, const double* center3, double zmin,
+                                    const double* positions, const double* radii, int64_t M,
+                                    int64_t* counts_out, int64_t* draws_out) {
     if (!e) return MCPYB_ERR_ARG;
     cudaSetDevice(e->device);
-    if (P < 0 || M < 0 || !state_hi_lo || !inc_hi_lo || !counts_out || !(radius > 0.0) ||
+    if (zmin != zmin || P < 0 || M < 0 || !state_hi_lo || !inc_hi_lo || !counts_out || !(radius > 0.0) ||
         (M > 0 && (!positions || !radii)))
         return e->fail(MCPYB_ERR_ARG, "bad sphere free-volume arguments");
     int rc = fv_upload_atoms(e, positions, radii, M);
@@ -1558,9 +1640,9 @@ int mcpyb_sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
         LAUNCH_CHECK("pcg_sphere_count_kernel");
         pcg_scan_kernel<<<1, 1024, 0, e->stream>>>(e->pcg_count.p, e->pcg_prefix.p, blocks, P, e->pcg_ctl.p);
         LAUNCH_CHECK("pcg_scan_kernel");
-        if (chunk == 8) pcg_sphere_eval_kernel<8><<<grid2, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, cx, cy, cz, e->pcg_ctl.p,
+        if (chunk == 8) pcg_sphere_eval_kernel<8><<<grid2, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, cx, cy, cz, zmin, e->pcg_ctl.p,
             e->pcg_prefix.p, e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
-        else pcg_sphere_eval_kernel<2><<<grid2, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, cx, cy, cz, e->pcg_ctl.p,
+        else pcg_sphere_eval_kernel<2><<<grid2, PCG_BLOCK, 0, e->stream>>>(rng, tbl, Mc, radius, cx, cy, cz, zmin, e->pcg_ctl.p,
             e->pcg_prefix.p, e->fv_grid.p, e->fv_spheres.p, e->fv_cell_start.p, e->fv_counts.p);
         LAUNCH_CHECK("pcg_sphere_eval_kernel");
         rc = fv_read_counts(e, counts_out, &ctl);
@@ -1571,6 +1653,21 @@ int mcpyb_sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
     if (draws_out) *draws_out = 3 * Mc * ctl.passes;
     if (P > 0) return MCPYB_OK;
     return fv_read_counts(e, counts_out);
+}
+
+int mcpyb_sphere_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo,
+                                   int64_t P, double radius, const double* center3, const double* positions,
+                                   const double* radii, int64_t M, int64_t* counts_out, int64_t* draws_out) {
+    return sphere_free_volume_pcg64(e, state_hi_lo, inc_hi_lo, P, radius, center3, -HUGE_VAL, positions, radii, M,
+                                    counts_out, draws_out);
+}
+
+int mcpyb_dome_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo,
+                                 int64_t P, double radius, const double* center3, double bottom_z,
+                                 const double* positions, const double* radii, int64_t M,
+                                 int64_t* counts_out, int64_t* draws_out) {
+    return sphere_free_volume_pcg64(e, state_hi_lo, inc_hi_lo, P, radius, center3, bottom_z, positions, radii, M,
+                                    counts_out, draws_out);
 }
 
 int mcpyb_box_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo, const uint64_t* inc_hi_lo,

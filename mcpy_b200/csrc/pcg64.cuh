@@ -191,6 +191,7 @@ pcg_scan_kernel(const int* __restrict__ block_count, long long* __restrict__ blo
 template <int CHUNK>
 __global__ void __launch_bounds__(PCG_BLOCK)
 pcg_sphere_eval_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, double cx, double cy, double cz,
+                       double zmin /* DomeCell: points with z < zmin are drawn but not counted; -inf otherwise */,
                        const SphereCtl* __restrict__ ctl, const long long* __restrict__ block_prefix,
                        const FvGrid* __restrict__ gridp, const double4* __restrict__ spheres,
                        const int* __restrict__ cell_start, unsigned long long* __restrict__ counts) {
@@ -227,9 +228,10 @@ pcg_sphere_eval_kernel(Pcg64 rng, PcgStrideTable tbl, long long M, double R, dou
 #pragma unroll
             for (int k = 0; k < CHUNK; ++k) {
                 if ((acc_mask >> k) & 1u) {
-                    if (rank < need) {
+                    const double z = __dadd_rn(pz[k], cz);
+                    if (rank < need && z >= zmin) {
                         const bool cov = fv_point_covered(g, spheres, cell_start, __dadd_rn(px[k], cx),
-                                                          __dadd_rn(py[k], cy), __dadd_rn(pz[k], cz));
+                                                          __dadd_rn(py[k], cy), z);
                         covered_local += cov ? 1 : 0;
                         total_local += 1;
                     }

@@ -52,7 +52,7 @@ struct RbPieces {
 
 struct RowsBlockSmem {
     double4 candd[RB_CAND];                     // q + S@cell (exact, unfused), .w = tag
-    int cinfo[RB_CAND];                         // cell-sorted slot | piece << 24 (borderline re-check)
+    int2 cinfo[RB_CAND];                        // (cell-sorted slot, packed image shift of the piece): borderline re-check
     RbPieces pc;
     float wbox[RB_WARPS][6];                    // per-warp bounding boxes of the sites
     int wcnt[RB_WARPS];                         // survivors per warp of a staging round
@@ -137,6 +137,20 @@ __device__ __noinline__ double rb_exact_r2(const GridDesc& g, const double4* __r
     return image_r2(q.x, q.y, q.z, ax, ay, az, px, py, pz, dx, dy, dz);
 }
 
+// The site wrapped into the primary periodic cell and the width (ulps of rc^2) of the band in which the
+// fused r2 of the loops below is re-checked in the oracle's arithmetic.  ONE out-of-line copy: every row-sum
+// kernel (batched, pipelined, single-launch) and the pipelined kernel's bounding box see the same bits.
+__device__ __noinline__ void rb_wrap_site(const GridDesc& g, double rc, double px, double py, double pz, int wsite,
+                                          double& qx, double& qy, double& qz, double& band) {
+    int w0, w1, w2;
+    unpack_wraps(wsite, w0, w1, w2);
+    const double a = (double)w0, bb = (double)w1, cc = (double)w2;
+    qx = px - (a * g.cell[0] + bb * g.cell[3] + cc * g.cell[6]);
+    qy = py - (a * g.cell[1] + bb * g.cell[4] + cc * g.cell[7]);
+    qz = pz - (a * g.cell[2] + bb * g.cell[5] + cc * g.cell[8]);
+    band = 16.0 + 64.0 * (fabs(px) + fabs(py) + fabs(pz) + fabs(qx) + fabs(qy) + fabs(qz)) / rc;
+}
+
 // Generic traversal for one site (thin boxes, oversized stencils): exact arithmetic directly.
 // Returns the same accumulators as the fast path: sum c6^2, sum c6, pairs.
 __device__ __noinline__ void rb_generic_row(const GridDesc& g, const double4* __restrict__ spos,
@@ -161,22 +175,120 @@ __device__ __noinline__ void rb_generic_row(const GridDesc& g, const double4* __
     acc12 = a12; acc6 = a6; cnt = c;
 }
 
+// The stencil of every cell, written out once per resident configuration (expand_stencils_kernel): the
+// candidate records the row-sum kernel would otherwise re-derive for every work item of every launch
+// (piece table, a binary search and a gather per candidate, image shift) as one contiguous, ordered run
+// per cell.  40 bytes per record, (2m+1)^3 cells' worth of atoms per cell: 10 MB for the 2 000-atom LJ box,
+// L2-resident.  A cell whose list does not fit the buffer (or whose box needs the generic traversal) has
+// head.x < 0 and is staged on the fly as before.
+struct StencilLists {
+    double4* q;                                // q + S@cell (exact, unfused), .w low word = atom index
+    int2* info;                                // (cell-sorted slot, packed image shift of the piece)
+    int2* head;                                // [R * bin_stride] (first record, records) of the cell; nullptr: no lists
+    unsigned long long* cursor;                // allocation cursor, zeroed before the expansion
+    long long cap;                             // records the buffers hold
+};
+
+// Candidate gi of the stencil described by the piece table: the staged record and its re-check info.
+__device__ __forceinline__ void rp_stage_candidate(const GridDesc& g, const double4* __restrict__ spos,
+                                                   const RbPieces& pc, int npieces, int gi, double4& q, int2& info) {
+    int lo = 0, hi = npieces;                  // pstart[lo] <= gi < pstart[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pc.pstart[mid] <= gi) lo = mid; else hi = mid;
+    }
+    const int k = pc.pbeg[lo] + (gi - pc.pstart[lo]);
+    q = spos[k];
+    double ax = pc.pshift[lo][0], ay = pc.pshift[lo][1], az = pc.pshift[lo][2];
+    const int pS = pc.pS[lo];
+    const long long tag = tag_of(q);
+    const int wj = tag_wraps(tag);
+    if (wj != pack_wraps(0, 0, 0)) {           // atom stored outside the primary cell
+        int sx, sy, sz, jx, jy, jz;
+        unpack_wraps(pS, sx, sy, sz);
+        unpack_wraps(wj, jx, jy, jz);
+        shift_vec(g, sx - jx, sy - jy, sz - jz, ax, ay, az);
+    }
+    q.x = __dadd_rn(q.x, ax); q.y = __dadd_rn(q.y, ay); q.z = __dadd_rn(q.z, az);
+    q.w = __longlong_as_double((long long)tag_index(tag));       // low word = atom index
+    info = make_int2(k, pS);
+}
+
+#define EX_WARPS 4
+// One warp per (replica, cell): piece table, then the whole stencil in list order.
+__global__ void __launch_bounds__(32 * EX_WARPS)
+expand_stencils_kernel(BatchView b, StencilLists x, int nbins, int bin_stride) {
+    __shared__ RbPieces pcs[EX_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    RbPieces& pc = pcs[wid];
+    for (int bin = blockIdx.x * EX_WARPS + wid; bin < nbins; bin += gridDim.x * EX_WARPS) {
+        const int r = bin / bin_stride, c = bin - r * bin_stride;
+        const GridDesc& g = b.grid[r];
+        int2 head = make_int2(-1, 0);
+        const int n0 = g.ncell[0], n1 = g.ncell[1];
+        const int m0 = g.m[0], m1 = g.m[1], m2 = g.m[2];
+        const int nrows = (2 * m1 + 1) * (2 * m2 + 1);
+        const bool fast = (!g.pbc[0] || n0 >= 2 * m0 + 1) && 2 * nrows <= RB_MAXPIECES;
+        if (c < g.ncells && fast) {
+            const int* cstart = b.cell_start + (size_t)r * b.cs_stride;
+            const double4* spos = b.spos + g.atom_off;
+            const int c0 = c % n0, c1 = (c / n0) % n1, c2 = c / (n0 * n1);
+            __syncwarp();                           // the previous bin's table is no longer read
+            rb_build_pieces(pc, g, cstart, c0, c1, c2, lane);
+            __syncwarp();
+            const int total = pc.total, npieces = 2 * nrows;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(x.cursor, (unsigned long long)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (unsigned long long)total <= (unsigned long long)x.cap) {
+                for (int gi = lane; gi < total; gi += 32) {
+                    double4 q;
+                    int2 info;
+                    rp_stage_candidate(g, spos, pc, npieces, gi, q, info);
+                    x.q[base + gi] = q;
+                    x.info[base + gi] = info;
+                }
+                head = make_int2((int)base, total);
+            }
+        }
+        if (lane == 0) x.head[bin] = head;
+    }
+}
+
+// rb_exact_r2 with the piece's image shift taken from the staged record instead of the piece table
+__device__ __noinline__ double rp_exact_r2(const GridDesc& g, const double4* __restrict__ spos, int2 info,
+                                           double px, double py, double pz, int wsite) {
+    const double4 q = spos[info.x];
+    int sx, sy, sz, jx, jy, jz, w0, w1, w2;
+    unpack_wraps(info.y, sx, sy, sz);
+    unpack_wraps(tag_wraps(tag_of(q)), jx, jy, jz);
+    unpack_wraps(wsite, w0, w1, w2);
+    double ax, ay, az, dx, dy, dz;
+    shift_vec(g, sx + w0 - jx, sy + w1 - jy, sz + w2 - jz, ax, ay, az);
+    return image_r2(q.x, q.y, q.z, ax, ay, az, px, py, pz, dx, dy, dz);
+}
+
 template <int RBU, int MINB>
 __global__ void __launch_bounds__(RB_THREADS, MINB)
-lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) {
+lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, StencilLists x) {
     __shared__ RowsBlockSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_wait();
+    pdl_trigger();
     const int nq = w.nplanes;                     // slices of the candidate list, one work item each
     const int nwork = w.totals[0] * nq;
-    // persistent CTAs pull work items from a device counter (zeroed by the scan kernel): the grid is
-    // sized by the SM count, not by the host's upper bound on the item count, so no CTA is launched
-    // only to find nothing to do, and the tail is one item long
+    // persistent CTAs: the first work item is the CTA's own index, the following ones come from a device
+    // counter (zeroed by the scan kernel), claimed one item AHEAD so that the atomic's round trip hides
+    // behind the current item.  The grid is sized by the SM count, not by the host's upper bound on the
+    // item count, so no CTA is launched only to find nothing to do, and the tail is one item long.
     __shared__ int s_wi;
+    int next_wi = blockIdx.x;
     for (;;) {
-        if (tid == 0) s_wi = atomicAdd(&w.totals[1], 1);
+        if (tid == 0) s_wi = next_wi;
         __syncthreads();
         const int wi = s_wi;
         if (wi >= nwork) break;
+        if (tid == 0) next_wi = (int)gridDim.x + atomicAdd(&w.totals[1], 1);
         const int item = wi / nq, slice = wi - item * nq;
         const int2 it = w.item_tab[item];
         const int bin = it.x, group = it.y;
@@ -212,10 +324,16 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
             if (active && slice == 0)
                 rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, acc12, acc6, cnt);
         } else {
-            // ---- stencil pieces (warp 0)
-            if (wid == 0) rb_build_pieces(sm.pc, g, cstart, c0, c1, c2, lane);
-            __syncthreads();
-            const int total = sm.pc.total, npieces = 2 * nrows;
+            // ---- the cell's stencil: its expanded list if there is one, else the piece table (warp 0)
+            const int2 head = x.head ? x.head[bin] : make_int2(-1, 0);
+            const bool listed = head.x >= 0;
+            if (!listed) {
+                if (wid == 0) rb_build_pieces(sm.pc, g, cstart, c0, c1, c2, lane);
+                __syncthreads();
+            }
+            const int total = listed ? head.y : sm.pc.total, npieces = 2 * nrows;
+            const double4* xq = x.q + (listed ? head.x : 0);
+            const int2* xi = x.info + (listed ? head.x : 0);
 
             // ---- per-lane constants.  The loop works with the site wrapped into the primary cell
             // (qx, qy, qz) and a fused r2; both differ from the oracle's value by rounding only.
@@ -225,15 +343,7 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
             double band = 16.0;                                    // ulps, relative to rc^2
             if (active) {
                 qx = px; qy = py; qz = pz;
-                if (wsite != pack_wraps(0, 0, 0)) {
-                    int w0, w1, w2;
-                    unpack_wraps(wsite, w0, w1, w2);
-                    const double a = (double)w0, bb = (double)w1, cc = (double)w2;
-                    qx = px - (a * g.cell[0] + bb * g.cell[3] + cc * g.cell[6]);
-                    qy = py - (a * g.cell[1] + bb * g.cell[4] + cc * g.cell[7]);
-                    qz = pz - (a * g.cell[2] + bb * g.cell[5] + cc * g.cell[8]);
-                    band += 64.0 * (fabs(px) + fabs(py) + fabs(pz) + fabs(qx) + fabs(qy) + fabs(qz)) / p.rc;
-                }
+                if (wsite != pack_wraps(0, 0, 0)) rb_wrap_site(g, p.rc, px, py, pz, wsite, qx, qy, qz, band);
             }
             const double bw = p.rc2 * band * 2.220446049250313e-16;
             const long long lo_bits = __double_as_longlong(p.rc2 - bw), hi_bits = __double_as_longlong(p.rc2 + bw);
@@ -266,15 +376,20 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
                 }
             }
             __syncthreads();
-            double blo[3], bhi[3];
+            // The pruning test runs in fp32: candidates rounded to nearest, the box rounded outward, and the
+            // radius carries a margin for the rounding of coordinates as large as any that can pass.
+            float blo[3], bhi[3], maxabs = 0.0f;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 float l = sm.wbox[0][d], h = sm.wbox[0][3 + d];
 #pragma unroll
                 for (int ww = 1; ww < RB_WARPS; ++ww) { l = fminf(l, sm.wbox[ww][d]); h = fmaxf(h, sm.wbox[ww][3 + d]); }
-                blo[d] = (double)l; bhi[d] = (double)h;
+                blo[d] = l; bhi[d] = h;
+                maxabs = fmaxf(maxabs, fmaxf(fabsf(l), fabsf(h)));
             }
-            const double keep_r2 = p.rc2 * (1.0 + 1e-9);
+            const float rcf = __double2float_ru(p.rc);
+            const float keep_r = rcf * 1.000002f + 1.0e-6f * (maxabs + rcf);
+            const float keep_r2 = keep_r * keep_r * 1.000001f;
             const int lo_hi = (int)(lo_bits >> 32), hi_hi = (int)(hi_bits >> 32);
 
             // this work item's slice of the stencil's candidate list: a function of the cell alone
@@ -287,31 +402,15 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
                     const int gi = gi0 + tid;
                     bool keep = false;
                     double4 q = make_double4(0.0, 0.0, 0.0, 0.0);
-                    int info = 0;
+                    int2 info = make_int2(0, 0);
                     if (gi < clast) {
-                        int lo = 0, hi = npieces;                 // pstart[lo] <= gi < pstart[hi]
-                        while (hi - lo > 1) {
-                            const int mid = (lo + hi) >> 1;
-                            if (sm.pc.pstart[mid] <= gi) lo = mid; else hi = mid;
-                        }
-                        const int k = sm.pc.pbeg[lo] + (gi - sm.pc.pstart[lo]);
-                        q = spos[k];
-                        double ax = sm.pc.pshift[lo][0], ay = sm.pc.pshift[lo][1], az = sm.pc.pshift[lo][2];
-                        const long long tag = tag_of(q);
-                        const int wj = tag_wraps(tag);
-                        if (wj != pack_wraps(0, 0, 0)) {          // atom stored outside the primary cell
-                            int sx, sy, sz, jx, jy, jz;
-                            unpack_wraps(sm.pc.pS[lo], sx, sy, sz);
-                            unpack_wraps(wj, jx, jy, jz);
-                            shift_vec(g, sx - jx, sy - jy, sz - jz, ax, ay, az);
-                        }
-                        q.x = __dadd_rn(q.x, ax); q.y = __dadd_rn(q.y, ay); q.z = __dadd_rn(q.z, az);
-                        q.w = __longlong_as_double((long long)tag_index(tag));     // low word = atom index
-                        info = k | (lo << 24);
-                        const double ex = fmax(fmax(blo[0] - q.x, q.x - bhi[0]), 0.0);
-                        const double ey = fmax(fmax(blo[1] - q.y, q.y - bhi[1]), 0.0);
-                        const double ez = fmax(fmax(blo[2] - q.z, q.z - bhi[2]), 0.0);
-                        keep = fma(ez, ez, fma(ey, ey, ex * ex)) <= keep_r2;
+                        if (listed) { q = xq[gi]; info = xi[gi]; }
+                        else rp_stage_candidate(g, spos, sm.pc, npieces, gi, q, info);
+                        const float xf = __double2float_rn(q.x), yf = __double2float_rn(q.y), zf = __double2float_rn(q.z);
+                        const float ex = fmaxf(fmaxf(blo[0] - xf, xf - bhi[0]), 0.0f);
+                        const float ey = fmaxf(fmaxf(blo[1] - yf, yf - bhi[1]), 0.0f);
+                        const float ez = fmaxf(fmaxf(blo[2] - zf, zf - bhi[2]), 0.0f);
+                        keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= keep_r2;
                     }
                     const unsigned bal = __ballot_sync(0xffffffffu, keep);
                     if (lane == 0) sm.wcnt[wid] = __popc(bal);
@@ -347,7 +446,7 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p) 
                             const long long rb = __double_as_longlong(r2);
                             bool in = rb < lo_bits;
                             if (!in && rb <= hi_bits)        // within rounding of the cutoff: the oracle's arithmetic decides
-                                in = rb_exact_r2(g, spos, sm.pc, sm.cinfo[i + u], px, py, pz, wsite) <= p.rc2;
+                                in = rp_exact_r2(g, spos, sm.cinfo[i + u], px, py, pz, wsite) <= p.rc2;
                             const int j = __double2loint(q.w);
                             in = in && (j != ex0) && (j != ex1);
                             if (multi && in)
@@ -468,13 +567,7 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
             const int total = sm.pc.total, npieces = 2 * nrows;
             // per-site constants, as in lj_trial_rows_block_kernel
             double qx = px, qy = py, qz = pz, band = 16.0;
-            if (wsite != pack_wraps(0, 0, 0)) {
-                const double a = (double)wr[0], bb = (double)wr[1], cc = (double)wr[2];
-                qx = px - (a * g.cell[0] + bb * g.cell[3] + cc * g.cell[6]);
-                qy = py - (a * g.cell[1] + bb * g.cell[4] + cc * g.cell[7]);
-                qz = pz - (a * g.cell[2] + bb * g.cell[5] + cc * g.cell[8]);
-                band += 64.0 * (fabs(px) + fabs(py) + fabs(pz) + fabs(qx) + fabs(qy) + fabs(qz)) / p.rc;
-            }
+            if (wsite != pack_wraps(0, 0, 0)) rb_wrap_site(g, p.rc, px, py, pz, wsite, qx, qy, qz, band);
             const double bw = p.rc2 * band * 2.220446049250313e-16;
             const long long lo_bits = __double_as_longlong(p.rc2 - bw), hi_bits = __double_as_longlong(p.rc2 + bw);
             for (int cbase = 0; cbase < total; cbase += RS_CAND) {

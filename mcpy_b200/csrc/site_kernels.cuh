@@ -445,6 +445,8 @@ __device__ __forceinline__ int trial_invalid(const BatchView& b, const TrialBatc
 __global__ void __launch_bounds__(256)
 trial_sites_kernel(BatchView b, TrialBatch tb, TrialWork w) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     if (t >= tb.T) return;
     const int r = tb.rep ? tb.rep[t] : 0;
     const int ob = tb.old_off[t], oe = tb.old_off[t + 1];
@@ -483,6 +485,8 @@ __global__ void __launch_bounds__(1024, 1)
 trial_scan_kernel(TrialWork w) {
     __shared__ int s_a[1024], s_b[1024];
     const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     // each thread owns a contiguous run of bins so the scan is two passes over registers/global
     const int per = (w.nbins + 1023) / 1024;
     const int beg = min(tid * per, w.nbins), end = min(beg + per, w.nbins);
@@ -517,6 +521,8 @@ trial_scan_kernel(TrialWork w) {
 __global__ void __launch_bounds__(256)
 trial_scatter_kernel(TrialBatch tb, TrialWork w) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     if (s >= w.nsites) return;
     const int4 a = w.site_a[s];
     const double4 ps = w.site_pos[s];
@@ -581,6 +587,8 @@ __global__ void __launch_bounds__(128)
 lj_trial_combine_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p,
                         double* __restrict__ dE, int* __restrict__ npairs) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     if (t >= tb.T) return;
     combine_trial(b, tb, w, p, t, dE, npairs);
 }

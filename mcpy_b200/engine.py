@@ -334,6 +334,22 @@ class Engine:
         rng.bit_generator.advance(int(draws.value))
         return int(counts[0]), int(counts[1])
 
+    def dome_free_volume_pcg64(self, rng, n_points, radius, center, bottom_z, positions, radii):
+        """DomeCell sampling + covered test on the device (dome_cell.py:106-138): the full-ball
+        stream of ``_sample_sphere_points``, points below ``bottom_z`` ignored.  Returns
+        (free, covered) among the points at or above ``bottom_z``; advances ``rng`` like the host."""
+        state, inc = self._pcg_words(rng)
+        positions = as_f64(positions).reshape(-1, 3)
+        radii = as_f64(radii).reshape(-1)
+        center = as_f64(center).reshape(3)
+        counts = np.zeros(2, dtype=np.int64)
+        draws = C.c_int64(0)
+        self._check(self._lib.mcpyb_dome_free_volume_pcg64(
+            self._h, ptr(state), ptr(inc), int(n_points), float(radius), ptr(center), float(bottom_z),
+            ptr(positions), ptr(radii), len(positions), ptr(counts), C.byref(draws)))
+        rng.bit_generator.advance(int(draws.value))
+        return int(counts[0]), int(counts[1])
+
     def box_free_volume_pcg64(self, rng, n_points, dimensions, positions, radii, offset, shifts):
         """CustomCell sampling + covered test on the device; advances ``rng`` by 3 P draws."""
         state, inc = self._pcg_words(rng)

@@ -134,3 +134,20 @@ def custom_free_volume(rng, positions, radii, dimensions, offset,
     occupied_fraction = float(n_cov) / n_points
     return clamp_free_volume(cell_volume * (1.0 - occupied_fraction),
                              cell_volume, n_points), n_cov
+
+
+def dome_free_volume(rng, positions, radii, radius, center, bottom_z, n_points, brute=False):
+    """``DomeCell.calculate_volume`` (``dome_cell.py:106-138``): full-ball sample, points below
+    ``bottom_z`` dropped, free fraction normalised by the FULL-ball point count (``:136``).
+    Returns ``(volume, n_free_above, n_above)``; advances ``rng`` exactly as the reference."""
+    sphere_volume = (4.0 / 3.0) * np.pi * (radius ** 3)
+    pts, _ = sample_sphere_points(rng, n_points, radius, center)
+    pts = pts[pts[:, 2] >= bottom_z]
+    n_above = len(pts)
+    if len(positions) == 0:
+        return (float(n_above) / n_points) * sphere_volume, n_above, n_above
+    fn = covered_mask_bruteforce if brute else covered_mask_kdtree
+    covered = fn(pts, positions, radii)
+    n_free = int(np.count_nonzero(~covered))
+    free_fraction = float(n_free) / n_points
+    return clamp_free_volume(free_fraction * sphere_volume, sphere_volume, n_points), n_free, n_above

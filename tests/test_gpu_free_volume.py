@@ -170,3 +170,43 @@ def test_cells_in_device_point_mode_track_the_reference_stream(fv_engine):
         assert host.last_counts == dev.last_counts and host.get_volume() == dev.get_volume()
         # insertion points drawn afterwards come from the same stream position
         assert np.array_equal(host.get_random_point(), dev.get_random_point())
+
+
+def test_dome_cell_matches_oracle_in_both_point_modes(fv_engine):
+    """B200DomeCell (dome_cell.py:8-138): same integer counts, same volume, same stream position as
+    the oracle restatement (itself pinned to the unmodified DomeCell in test_oracle_free_volume.py)."""
+    from mcpy_b200.cell import B200DomeCell
+    from ase import Atoms
+    ag = np.array([[14.0, 10.0, 0.5], [14.0, 10.0, 5.0], [16.0, 10.0, 2.5], [12.0, 10.0, 2.5],
+                   [14.0, 12.0, 2.5], [14.0, 8.0, 2.5]])
+    xs = np.linspace(1.0, 19.0, 7)
+    support = [(x, y, 0.0) for x in xs for y in xs]
+    atoms = Atoms(['Al'] * len(support) + ['Ag'] * len(ag), positions=support + [tuple(p) for p in ag],
+                  cell=[20, 20, 20], pbc=True)
+    radii_map = {'Al': 1.0, 'Ag': 1.0, 'O': 0.0}
+    radii = np.array([radii_map[s] for s in atoms.get_chemical_symbols()])
+    before = atoms.positions.copy()
+    for mode in ('host', 'device'):
+        cell = B200DomeCell(atoms, particle_species='Ag', bottom_z=0.0, vacuum=1.0, species_radii=radii_map,
+                            mc_sample_points=50_000, seed=4, engine=fv_engine, points=mode)
+        assert np.array_equal(atoms.positions, before)            # the dome does not translate the atoms
+        np.testing.assert_allclose(cell.center, ag.mean(axis=0), atol=1e-12)
+        rng = np.random.default_rng(4)
+        for _ in range(2):
+            cell.calculate_volume(atoms)
+            vol, n_free, n_above = ofv.dome_free_volume(rng, atoms.positions, radii, cell.radius, cell.center,
+                                                        0.0, 50_000)
+            assert cell.last_counts[0] == n_free and sum(cell.last_counts) == n_above
+            assert cell.get_volume() == vol
+        cell.calculate_volume(Atoms())                            # empty: dome fraction of the ball
+        vol, n_free, n_above = ofv.dome_free_volume(rng, np.zeros((0, 3)), [], cell.radius, cell.center, 0.0, 50_000)
+        assert cell.get_volume() == vol and cell.last_counts == (n_above, 0)
+        assert rng.bit_generator.state == cell._rng.bit_generator.state
+        p = cell.get_random_point()
+        assert p[2] >= 0.0 and cell.is_point_inside(p)
+        below = cell.center.copy(); below[2] = -0.5
+        assert not cell.is_point_inside(below)
+        trial = atoms.copy()
+        trial += Atoms('O', positions=[p])
+        trial += Atoms('O', positions=[below])
+        assert list(cell.get_atoms_specie_inside_cell(trial, ['O'])) == [len(atoms)]

@@ -50,3 +50,43 @@ def test_sphere_sampler_consumes_the_stream_like_the_reference():
     rng2 = np.random.default_rng(5)
     rng2.random(draws)
     assert rng.random() == rng2.random()
+
+
+def _supported_particle():
+    # the fixture of the reference's tests/test_dome_cell.py:17-40: Al support layer, off-centre Ag cluster
+    from ase import Atoms
+    ag = np.array([[14.0, 10.0, 0.5], [14.0, 10.0, 5.0], [16.0, 10.0, 2.5], [12.0, 10.0, 2.5],
+                   [14.0, 12.0, 2.5], [14.0, 8.0, 2.5]])
+    xs = np.linspace(1.0, 19.0, 7)
+    support = [(x, y, 0.0) for x in xs for y in xs]
+    return Atoms(['Al'] * len(support) + ['Ag'] * len(ag), positions=support + [tuple(p) for p in ag],
+                 cell=[20, 20, 20], pbc=True), ag
+
+
+def test_dome_oracle_equals_the_reference_class():
+    """oracle.dome_free_volume == the unmodified mcpy.cell.DomeCell (same seed, same stream)."""
+    import os, sys
+    if not os.path.isdir('/root/reference/mcpy'):
+        pytest.skip('reference checkout not present (GPU box)')
+    sys.path.insert(0, '/root/reference')
+    try:
+        from mcpy.cell import DomeCell
+    finally:
+        sys.path.remove('/root/reference')
+    atoms, ag = _supported_particle()
+    radii_map = {'Al': 1.0, 'Ag': 1.0, 'O': 0.0}
+    ref = DomeCell(atoms, particle_species='Ag', bottom_z=0.0, vacuum=1.0, species_radii=radii_map,
+                   mc_sample_points=20_000, seed=4)
+    rng = np.random.default_rng(4)
+    radii = np.array([radii_map[s] for s in atoms.get_chemical_symbols()])
+    for _ in range(2):
+        ref.calculate_volume(atoms)
+        vol, n_free, n_above = ofv.dome_free_volume(rng, atoms.positions, radii, ref.radius, ref.center,
+                                                    0.0, 20_000)
+        assert vol == ref.get_volume() and 0 < n_free < n_above < 20_000
+    assert rng.bit_generator.state == ref._rng.bit_generator.state
+    # no atoms: the dome fraction of the ball (dome_cell.py:118-121)
+    from ase import Atoms
+    ref.calculate_volume(Atoms())
+    vol, n_free, n_above = ofv.dome_free_volume(rng, np.zeros((0, 3)), [], ref.radius, ref.center, 0.0, 20_000)
+    assert vol == ref.get_volume() and n_free == n_above
