@@ -278,12 +278,17 @@ def run_b200(args):
     ms_per_step = kernel_ms / args.steps
 
     # ---- end to end through the plug-in with host buffers
-    trials_host = {k: np.ascontiguousarray(tb[k]) for k in ('old_off', 'old_idx', 'new_off', 'new_pos', 'new_Z')}
+    # the step's inputs and its result live in page-locked host arrays (mcpy_b200.pinned_copy): the engine
+    # hands them to the copy engine as they are; pageable numpy arrays would be staged first ('e2e_pageable')
+    from mcpy_b200 import pinned_copy, pinned_empty
+    trials_pageable = {k: np.ascontiguousarray(tb[k]) for k in ('old_off', 'old_idx', 'new_off', 'new_pos', 'new_Z')}
+    trials_host = {k: pinned_copy(v) for k, v in trials_pageable.items()}
+    dE_host = pinned_empty(T, np.float64)
 
-    def e2e_step():
+    def e2e_step(tr=trials_host, out=dE_host):
         calc.set_configuration(atoms)                                 # H2D config + cell list
-        return eng.trial_delta_e(trials_host['old_off'], trials_host['old_idx'], trials_host['new_off'],
-                                 trials_host['new_pos'], trials_host['new_Z'])   # H2D trials, D2H dE
+        return eng.trial_delta_e(tr['old_off'], tr['old_idx'], tr['new_off'],
+                                 tr['new_pos'], tr['new_Z'], out=out)            # H2D trials, D2H dE
 
     for _ in range(args.warmup):
         out = e2e_step()
@@ -296,6 +301,16 @@ def run_b200(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = world * T * args.steps / e2e_s
+    # the same call with ordinary (pageable) numpy arrays, for the record
+    for _ in range(args.warmup):
+        out = e2e_step(trials_pageable, None)
+    assert np.array_equal(out, dE_ref.cpu().numpy())
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step(trials_pageable, None)
+    torch.cuda.synchronize()
+    e2e_pageable_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
     h2d = (N_ATOMS * (24 + 4) + 256) + sum(int(v.nbytes) for v in trials_host.values()) + 4 * T
     d2h = 8 * T
 
@@ -368,9 +383,13 @@ def run_b200(args):
         'config': dict(workload_config(T), replicas_per_gpu=1,
                        parallelism=f'replica-parallel x{world}, no data-path collective'),
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'api': 'B200Calculator.set_configuration + trial_delta_energies '
-                       '(mcpyb_upload_host + mcpyb_trial_delta_e_host), host numpy buffers',
-                'ms_per_step': 1e3 * e2e_s / args.steps},
+                'api': 'B200Calculator.set_configuration + Engine.trial_delta_e '
+                       '(mcpyb_upload_host + mcpyb_trial_delta_e_host), host numpy arrays in page-locked memory '
+                       '(mcpy_b200.pinned_copy / pinned_empty)',
+                'ms_per_step': 1e3 * e2e_s / args.steps,
+                'pageable': {'value': world * T * args.steps / e2e_pageable_s,
+                             'ms_per_step': 1e3 * e2e_pageable_s / args.steps,
+                             'note': 'same calls with ordinary numpy arrays: staged through pinned memory inside the engine'}},
         'dropin': {'value': dropin_value, 'unit': UNIT, 'calls': n_chain,
                    'api': 'calculator.get_potential_energy(atoms) per trial, sequential '
                           '(mcpyb_tracked_energy_host: resident base + one delta; the trial rides in the '

@@ -21,6 +21,7 @@
 #ifndef MCPY_B200_H
 #define MCPY_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -142,6 +143,15 @@ int mcpyb_trial_delta_e_dev(mcpyb_engine* e, int T, const int32_t* d_rep,
                             const int32_t* d_new_off, const double* d_new_pos,
                             const int32_t* d_new_Z, int n_old_total, int n_new_total,
                             double* d_dE_out, int32_t* d_pairs_out);
+
+/* ---- page-locked host buffers ------------------------------------------------------------
+ * The "_host" entry points accept any host memory.  Arrays that are page-locked (allocated here, or by
+ * cudaHostAlloc / cudaHostRegister) are read and written by the copy engine where they are; pageable
+ * arrays pass through a pinned staging block inside the engine (one extra host copy each way).
+ * mcpyb_trial_delta_e_host takes the direct path when every array of the call is page-locked.
+ * Returns NULL when the allocation fails.                                                  */
+void* mcpyb_alloc_pinned(size_t bytes);
+void mcpyb_free_pinned(void* p);
 
 /* ---- neighbour list (bit-exactness check; oracle/neighbors.py) -------------
  * Lists every image (i, j, S) of replica `rep` of the resident batch with

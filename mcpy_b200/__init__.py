@@ -8,6 +8,7 @@ importing the package never touches the GPU, creating an engine does, and
 there is no CPU fallback.
 """
 from .engine import Engine, EngineError  # noqa: F401
+from ._lib import pinned_copy, pinned_empty  # noqa: F401
 
 __version__ = '0.1.0'
 __all__ = ['Engine', 'EngineError']

@@ -27,6 +27,7 @@ SYMBOLS = [
     'mcpyb_neighbor_pairs_host',
     'mcpyb_free_volume_count_host', 'mcpyb_free_volume_count_dev',
     'mcpyb_sphere_free_volume_pcg64', 'mcpyb_dome_free_volume_pcg64', 'mcpyb_box_free_volume_pcg64',
+    'mcpyb_alloc_pinned', 'mcpyb_free_pinned',
     'mcpyb_min_dist2_host', 'mcpyb_pcg64_host_doubles', 'mcpyb_fp64_peak_tflops', 'mcpyb_stage_timing', 'mcpyb_launch_count',
 ]
 
@@ -90,6 +91,10 @@ def load():
                                                  C.c_int64, _p, _p]
     lib.mcpyb_box_free_volume_pcg64.argtypes = [_p, _p, _p, C.c_int64, _p, _p, _p, C.c_int64, _p, _p,
                                                 C.c_int, _p]
+    lib.mcpyb_alloc_pinned.argtypes = [C.c_size_t]
+    lib.mcpyb_alloc_pinned.restype = C.c_void_p
+    lib.mcpyb_free_pinned.argtypes = [_p]
+    lib.mcpyb_free_pinned.restype = None
     lib.mcpyb_min_dist2_host.argtypes = [_p, C.c_int, _p, C.c_int64, _p, _p]
     lib.mcpyb_pcg64_host_doubles.argtypes = [_p, _p, C.c_uint64, C.c_int64, _p]
     lib.mcpyb_fp64_peak_tflops.argtypes = [_p, _f64p]
@@ -98,6 +103,30 @@ def load():
     lib.mcpyb_launch_count.restype = C.c_int64
     _lib = lib
     return lib
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """An uninitialised numpy array in page-locked host memory (``mcpyb_alloc_pinned``): the ``_host`` calls
+    DMA such arrays where they are instead of staging them.  Freed when the array is collected."""
+    import weakref
+    lib = load()
+    dtype = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    addr = lib.mcpyb_alloc_pinned(max(nbytes, 1))
+    if not addr:
+        raise MemoryError(f'could not page-lock {nbytes} bytes of host memory')
+    buf = (C.c_char * max(nbytes, 1)).from_address(addr)
+    weakref.finalize(buf, lib.mcpyb_free_pinned, addr)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+
+def pinned_copy(a, dtype=None):
+    """``a`` copied into a page-locked array of the same shape."""
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, dtype or a.dtype)
+    out[...] = a
+    return out
 
 
 def ptr(a):

@@ -671,6 +671,15 @@ static CopyPool* copy_pool_for(mcpyb_engine* e, size_t bytes) {
     return e->copy_pool;
 }
 
+// Page-locked host memory (cudaHostAlloc / cudaHostRegister / mcpyb_alloc_pinned) can be handed to the copy
+// engine as it is; anything else has to pass through a pinned staging block first.
+static bool is_pinned_host(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 static int upload_host_impl(mcpyb_engine* e, int subdiv, int R, const int64_t* atom_off, const double* positions,
                             const int32_t* numbers, const double* cells, const uint8_t* pbc) {
     if (!e) return MCPYB_ERR_ARG;
@@ -1115,6 +1124,11 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
         return cudaSuccess;
     };
     const bool small = bytes <= (64u << 10);          // latency path: one H2D, one D2H
+    // Caller's arrays already page-locked (mcpyb_alloc_pinned, cudaHostRegister): the copy engine reads
+    // them where they are -- no staging copy, which for a 65 536-trial batch is a third of the call.
+    const bool direct = !small && is_pinned_host(old_off) && is_pinned_host(new_off) && (!rep || is_pinned_host(rep)) &&
+                        (!n_old || is_pinned_host(old_idx)) && (!n_new || is_pinned_host(new_pos)) &&
+                        (!(n_new && new_Z && e->pot_kind == POT_EMT) || is_pinned_host(new_Z));
     if (small) {
         if (rep) memcpy(h + o_rep, rep, (size_t)T * 4);
         memcpy(h + o_oo, old_off, (size_t)(T + 1) * 4);
@@ -1123,6 +1137,14 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
         if (n_new && new_Z) memcpy(h + o_nz, new_Z, (size_t)n_new * 4);
         if (n_new) memcpy(h + o_np, new_pos, (size_t)n_new * 24);
         CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, e->stream), "H2D trials");
+    } else if (direct) {
+        if (rep) CK(cudaMemcpyAsync(d + o_rep, rep, (size_t)T * 4, cudaMemcpyHostToDevice, e->stream), "H2D trials");
+        CK(cudaMemcpyAsync(d + o_oo, old_off, (size_t)(T + 1) * 4, cudaMemcpyHostToDevice, e->stream), "H2D trials");
+        CK(cudaMemcpyAsync(d + o_no, new_off, (size_t)(T + 1) * 4, cudaMemcpyHostToDevice, e->stream), "H2D trials");
+        if (n_old) CK(cudaMemcpyAsync(d + o_oi, old_idx, (size_t)n_old * 4, cudaMemcpyHostToDevice, e->stream), "H2D trials");
+        if (n_new && new_Z && e->pot_kind == POT_EMT)
+            CK(cudaMemcpyAsync(d + o_nz, new_Z, (size_t)n_new * 4, cudaMemcpyHostToDevice, e->stream), "H2D trials");
+        if (n_new) CK(cudaMemcpyAsync(d + o_np, new_pos, (size_t)n_new * 24, cudaMemcpyHostToDevice, e->stream), "H2D trials");
     } else {
         if (rep) CK(stage(o_rep, rep, (size_t)T * 4), "H2D trials");
         CK(stage(o_oo, old_off, (size_t)(T + 1) * 4), "H2D trials");
@@ -1140,9 +1162,16 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
     CK(e->trial_out_pin.reserve(ob + pb), "cudaMallocHost trial out");
     // status word first, then dE in two halves: the host copies half 1 out while half 2 is in flight
     const size_t half = ((size_t)T / 2) * sizeof(double), full = (size_t)T * sizeof(double);
+    const bool out_direct = !small && is_pinned_host(dE_out) && (!pairs_out || is_pinned_host(pairs_out));
     if (small) {
         CK(cudaMemcpyAsync(e->trial_out_pin.p, e->dE.p, ob, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
         if (pairs_out) CK(cudaMemcpyAsync(e->trial_out_pin.p + ob, e->tpairs.p, pb, cudaMemcpyDeviceToHost, e->stream), "D2H pairs");
+        CK(cudaStreamSynchronize(e->stream), "sync trials");
+    } else if (out_direct) {
+        // page-locked result arrays: dE lands in the caller's buffer, only the status word is staged
+        CK(cudaMemcpyAsync(e->trial_out_pin.p + full, e->dE.p + T, sizeof(double), cudaMemcpyDeviceToHost, e->stream), "D2H status");
+        CK(cudaMemcpyAsync(dE_out, e->dE.p, full, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
+        if (pairs_out) CK(cudaMemcpyAsync(pairs_out, e->tpairs.p, pb, cudaMemcpyDeviceToHost, e->stream), "D2H pairs");
         CK(cudaStreamSynchronize(e->stream), "sync trials");
     } else {
         if (!e->trial_ev) CK(cudaEventCreateWithFlags(&e->trial_ev, cudaEventDisableTiming), "cudaEventCreate");
@@ -1163,10 +1192,12 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
             return e->fail(MCPYB_ERR_ARG, "trial %d: atom index out of range", t);
         }
     }
-    hcopy(dE_out, e->trial_out_pin.p, half);
-    if (!small) CK(cudaStreamSynchronize(e->stream), "sync trials");
-    hcopy((unsigned char*)dE_out + half, e->trial_out_pin.p + half, full - half);
-    if (pairs_out) memcpy(pairs_out, e->trial_out_pin.p + ob, pb);
+    if (!out_direct) {
+        hcopy(dE_out, e->trial_out_pin.p, half);
+        if (!small) CK(cudaStreamSynchronize(e->stream), "sync trials");
+        hcopy((unsigned char*)dE_out + half, e->trial_out_pin.p + half, full - half);
+        if (pairs_out) memcpy(pairs_out, e->trial_out_pin.p + ob, pb);
+    }
     e->trial_staging_busy = false;
     return MCPYB_OK;
 }
@@ -1704,6 +1735,16 @@ int mcpyb_box_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo, co
         LAUNCH_CHECK("pcg_box_eval_kernel");
     }
     return fv_read_counts(e, counts_out);
+}
+
+void* mcpyb_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes > 0 ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void mcpyb_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int mcpyb_fp64_peak_tflops(mcpyb_engine* e, double* tflops_out) {

@@ -239,7 +239,9 @@ class Engine:
 
     # -- trial moves ---------------------------------------------------------
     def trial_delta_e(self, old_off, old_idx, new_off, new_pos, new_Z=None, rep=None,
-                      return_pairs=False):
+                      return_pairs=False, out=None):
+        """dE of T trial moves against the resident batch (``mcpyb_trial_delta_e_host``).  Arrays from
+        ``pinned_empty`` / ``pinned_copy`` (and an ``out`` of that kind) are DMA'd where they are."""
         old_off = as_i32(old_off)
         new_off = as_i32(new_off)
         T = len(old_off) - 1
@@ -251,7 +253,9 @@ class Engine:
         rep = None if rep is None else as_i32(rep)
         if T and (old_off[-1] != len(old_idx) or new_off[-1] != len(new_pos)):
             raise ValueError('trial offsets do not match the index / position arrays')
-        dE = np.empty(T, dtype=np.float64)
+        if out is not None and (out.dtype != np.float64 or out.shape != (T,) or not out.flags.c_contiguous):
+            raise ValueError('out must be a C-contiguous float64 array of one value per trial')
+        dE = np.empty(T, dtype=np.float64) if out is None else out
         pairs = np.empty(T, dtype=np.int32) if return_pairs else None
         self._check(self._lib.mcpyb_trial_delta_e_host(
             self._h, T, ptr(rep), ptr(old_off), ptr(old_idx), ptr(new_off), ptr(new_pos),
