@@ -240,6 +240,10 @@ struct mcpyb_engine {
     CopyPool* copy_pool = nullptr;        // created on the first large batched call
     bool trial_staging_busy = false;      // a host trial call returned early with copies in flight
     cudaEvent_t trial_ev = nullptr;
+    // large trial batches travel on their own stream, so that their H2D copy overlaps whatever the engine's
+    // stream is still doing (the upload + cell-list build of the configuration they are scored against)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev = nullptr;
     DevBuf<unsigned char> trial_dev;
     PinBuf trial_pin, trial_out_pin;
     DevBuf<double> dE;
@@ -563,6 +567,8 @@ void mcpyb_destroy(mcpyb_engine* e) {
     e->pcg_count.release(); e->pcg_prefix.release(); e->pcg_ctl.release();
     delete e->copy_pool;
     if (e->trial_ev) cudaEventDestroy(e->trial_ev);
+    if (e->copy_ev) cudaEventDestroy(e->copy_ev);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -1009,14 +1015,16 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
         }
     }
     mark();
-    { cudaLaunchConfig_t cfg = config((T + 255) / 256, 256, 0);
-      CK(cudaLaunchKernelEx(&cfg, trial_sites_kernel, bv, tb, w), "launch trial_sites_kernel"); e->launches++; }
-    mark();
-    { cudaLaunchConfig_t cfg = config(1, 1024, 0);
-      CK(cudaLaunchKernelEx(&cfg, trial_scan_kernel, w), "launch trial_scan_kernel"); e->launches++; }
-    mark();
-    { cudaLaunchConfig_t cfg = config((nsites + 255) / 256, 256, 0);
-      CK(cudaLaunchKernelEx(&cfg, trial_scatter_kernel, tb, w), "launch trial_scatter_kernel"); e->launches++; }
+    {
+        { cudaLaunchConfig_t cfg = config((T + 255) / 256, 256, 0);
+          CK(cudaLaunchKernelEx(&cfg, trial_sites_kernel, bv, tb, w), "launch trial_sites_kernel"); e->launches++; }
+        mark();
+        { cudaLaunchConfig_t cfg = config(1, 1024, 0);
+          CK(cudaLaunchKernelEx(&cfg, trial_scan_kernel, w), "launch trial_scan_kernel"); e->launches++; }
+        mark();
+        { cudaLaunchConfig_t cfg = config((nsites + 255) / 256, 256, 0);
+          CK(cudaLaunchKernelEx(&cfg, trial_scatter_kernel, tb, w), "launch trial_scatter_kernel"); e->launches++; }
+    }
     mark();
     const long long est = (long long)max_items * w.nplanes;
     if (e->rows_pipe) {
@@ -1100,7 +1108,10 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
     size_t bytes = align_up(o_np + (size_t)n_new * 24, 64);
     // every host trial call ends with a stream synchronisation, so the staging buffers are free here
     // unless a call returned early
-    if (e->trial_staging_busy) CK(cudaStreamSynchronize(e->stream), "sync before trial staging reuse");
+    if (e->trial_staging_busy) {
+        CK(cudaStreamSynchronize(e->stream), "sync before trial staging reuse");
+        if (e->copy_stream) CK(cudaStreamSynchronize(e->copy_stream), "sync before trial staging reuse");
+    }
     e->trial_staging_busy = true;
     CopyPool* pool = copy_pool_for(e, bytes);
     auto hcopy = [&](void* dst, const void* src, size_t nbytes) {
@@ -1112,18 +1123,23 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
     CK(e->tpairs.reserve(T), "cudaMalloc trial pairs");
     unsigned char* h = e->trial_pin.p;
     unsigned char* d = e->trial_dev.p;
+    const bool small = bytes <= (64u << 10);          // latency path: one H2D, one D2H
+    if (!small && !e->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate (copy)");
+        CK(cudaEventCreateWithFlags(&e->copy_ev, cudaEventDisableTiming), "cudaEventCreate (copy)");
+    }
+    cudaStream_t cs = small ? e->stream : e->copy_stream;
     // stage piece by piece: the H2D copy of one piece runs while the host copies the next one
     auto stage = [&](size_t off, const void* src, size_t nbytes) -> cudaError_t {
         const size_t piece = 512u << 10;
         for (size_t done = 0; done < nbytes; done += piece) {
             const size_t nb = nbytes - done < piece ? nbytes - done : piece;
             hcopy(h + off + done, (const unsigned char*)src + done, nb);
-            cudaError_t ce = cudaMemcpyAsync(d + off + done, h + off + done, nb, cudaMemcpyHostToDevice, e->stream);
+            cudaError_t ce = cudaMemcpyAsync(d + off + done, h + off + done, nb, cudaMemcpyHostToDevice, cs);
             if (ce != cudaSuccess) return ce;
         }
         return cudaSuccess;
     };
-    const bool small = bytes <= (64u << 10);          // latency path: one H2D, one D2H
     // Caller's arrays already page-locked (mcpyb_alloc_pinned, cudaHostRegister): the copy engine reads
     // them where they are -- no staging copy, which for a 65 536-trial batch is a third of the call.
     const bool direct = !small && is_pinned_host(old_off) && is_pinned_host(new_off) && (!rep || is_pinned_host(rep)) &&
@@ -1138,13 +1154,13 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
         if (n_new) memcpy(h + o_np, new_pos, (size_t)n_new * 24);
         CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, e->stream), "H2D trials");
     } else if (direct) {
-        if (rep) CK(cudaMemcpyAsync(d + o_rep, rep, (size_t)T * 4, cudaMemcpyHostToDevice, e->stream), "H2D trials");
-        CK(cudaMemcpyAsync(d + o_oo, old_off, (size_t)(T + 1) * 4, cudaMemcpyHostToDevice, e->stream), "H2D trials");
-        CK(cudaMemcpyAsync(d + o_no, new_off, (size_t)(T + 1) * 4, cudaMemcpyHostToDevice, e->stream), "H2D trials");
-        if (n_old) CK(cudaMemcpyAsync(d + o_oi, old_idx, (size_t)n_old * 4, cudaMemcpyHostToDevice, e->stream), "H2D trials");
+        if (rep) CK(cudaMemcpyAsync(d + o_rep, rep, (size_t)T * 4, cudaMemcpyHostToDevice, cs), "H2D trials");
+        CK(cudaMemcpyAsync(d + o_oo, old_off, (size_t)(T + 1) * 4, cudaMemcpyHostToDevice, cs), "H2D trials");
+        CK(cudaMemcpyAsync(d + o_no, new_off, (size_t)(T + 1) * 4, cudaMemcpyHostToDevice, cs), "H2D trials");
+        if (n_old) CK(cudaMemcpyAsync(d + o_oi, old_idx, (size_t)n_old * 4, cudaMemcpyHostToDevice, cs), "H2D trials");
         if (n_new && new_Z && e->pot_kind == POT_EMT)
-            CK(cudaMemcpyAsync(d + o_nz, new_Z, (size_t)n_new * 4, cudaMemcpyHostToDevice, e->stream), "H2D trials");
-        if (n_new) CK(cudaMemcpyAsync(d + o_np, new_pos, (size_t)n_new * 24, cudaMemcpyHostToDevice, e->stream), "H2D trials");
+            CK(cudaMemcpyAsync(d + o_nz, new_Z, (size_t)n_new * 4, cudaMemcpyHostToDevice, cs), "H2D trials");
+        if (n_new) CK(cudaMemcpyAsync(d + o_np, new_pos, (size_t)n_new * 24, cudaMemcpyHostToDevice, cs), "H2D trials");
     } else {
         if (rep) CK(stage(o_rep, rep, (size_t)T * 4), "H2D trials");
         CK(stage(o_oo, old_off, (size_t)(T + 1) * 4), "H2D trials");
@@ -1152,6 +1168,10 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
         if (n_old) CK(stage(o_oi, old_idx, (size_t)n_old * 4), "H2D trials");
         if (n_new && new_Z && e->pot_kind == POT_EMT) CK(stage(o_nz, new_Z, (size_t)n_new * 4), "H2D trials");
         if (n_new) CK(stage(o_np, new_pos, (size_t)n_new * 24), "H2D trials");
+    }
+    if (!small) {
+        CK(cudaEventRecord(e->copy_ev, cs), "cudaEventRecord (copy)");
+        CK(cudaStreamWaitEvent(e->stream, e->copy_ev, 0), "cudaStreamWaitEvent (copy)");
     }
     int rc = launch_trials(e, T, rep ? (const int32_t*)(d + o_rep) : nullptr, (const int32_t*)(d + o_oo), (const int32_t*)(d + o_oi),
                            (const int32_t*)(d + o_no), (const double*)(d + o_np),

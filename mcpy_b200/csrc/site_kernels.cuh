@@ -442,12 +442,7 @@ __device__ __forceinline__ int trial_invalid(const BatchView& b, const TrialBatc
     return bad;
 }
 
-__global__ void __launch_bounds__(256)
-trial_sites_kernel(BatchView b, TrialBatch tb, TrialWork w) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    pdl_wait();
-    pdl_trigger();
-    if (t >= tb.T) return;
+__device__ __forceinline__ void trial_sites_body(const BatchView& b, const TrialBatch& tb, const TrialWork& w, int t) {
     const int r = tb.rep ? tb.rep[t] : 0;
     const int ob = tb.old_off[t], oe = tb.old_off[t + 1];
     const int nb = tb.new_off[t], ne = tb.new_off[t + 1];
@@ -481,21 +476,28 @@ trial_sites_kernel(BatchView b, TrialBatch tb, TrialWork w) {
     }
 }
 
-__global__ void __launch_bounds__(1024, 1)
-trial_scan_kernel(TrialWork w) {
-    __shared__ int s_a[1024], s_b[1024];
-    const int tid = threadIdx.x;
+__global__ void __launch_bounds__(256)
+trial_sites_kernel(BatchView b, TrialBatch tb, TrialWork w) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_wait();
     pdl_trigger();
+    if (t >= tb.T) return;
+    trial_sites_body(b, tb, w, t);
+}
+
+// One CTA of NT threads: exclusive scans of the bin histogram -> bin starts, work items; re-zeroes the histogram.
+template <int NT>
+__device__ __forceinline__ void trial_scan_body(const TrialWork& w, int* s_a, int* s_b) {
+    const int tid = threadIdx.x;
     // each thread owns a contiguous run of bins so the scan is two passes over registers/global
-    const int per = (w.nbins + 1023) / 1024;
+    const int per = (w.nbins + NT - 1) / NT;
     const int beg = min(tid * per, w.nbins), end = min(beg + per, w.nbins);
     int sa = 0, sb = 0;
     const int ish = w.item_shift, iround = (1 << ish) - 1;
     for (int i = beg; i < end; ++i) { const int c = w.hist[(size_t)i * TRIAL_HIST_STRIDE]; sa += c; sb += (c + iround) >> ish; }
     s_a[tid] = sa; s_b[tid] = sb;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
+    for (int o = 1; o < NT; o <<= 1) {
         const int ta = (tid >= o) ? s_a[tid - o] : 0, tb2 = (tid >= o) ? s_b[tid - o] : 0;
         __syncthreads();
         s_a[tid] += ta; s_b[tid] += tb2;
@@ -510,7 +512,7 @@ trial_scan_kernel(TrialWork w) {
         if (w.item_tab) for (int gq = 0; gq < ni; ++gq) w.item_tab[rb + gq] = make_int2(i, gq);
         ra += c; rb += ni;
     }
-    if (tid == 1023) { w.bin_count[w.nbins] = s_a[1023]; w.item_start[w.nbins] = s_b[1023]; w.totals[0] = s_b[1023]; w.totals[1] = 0; }
+    if (tid == NT - 1) { w.bin_count[w.nbins] = s_a[NT - 1]; w.item_start[w.nbins] = s_b[NT - 1]; w.totals[0] = s_b[NT - 1]; w.totals[1] = 0; }
     if (tid == 0) {
         const unsigned long long ev = *w.err;
         if (w.err_out) *w.err_out = ev;
@@ -518,12 +520,15 @@ trial_scan_kernel(TrialWork w) {
     }
 }
 
-__global__ void __launch_bounds__(256)
-trial_scatter_kernel(TrialBatch tb, TrialWork w) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(1024, 1)
+trial_scan_kernel(TrialWork w) {
+    __shared__ int s_a[1024], s_b[1024];
     pdl_wait();
     pdl_trigger();
-    if (s >= w.nsites) return;
+    trial_scan_body<1024>(w, s_a, s_b);
+}
+
+__device__ __forceinline__ void trial_scatter_body(const TrialWork& w, int s) {
     const int4 a = w.site_a[s];
     const double4 ps = w.site_pos[s];
     const long long wbits = __double_as_longlong(ps.w);
@@ -535,6 +540,15 @@ trial_scatter_kernel(TrialBatch tb, TrialWork w) {
         w.sorted_pos[k] = make_double4(ps.x, ps.y, ps.z, __longlong_as_double(wbits & 0xFFFFFFFFLL));
         w.sorted_meta[k] = make_int4(s, a.z, a.w, a.w + count);
     }
+}
+
+__global__ void __launch_bounds__(256)
+trial_scatter_kernel(TrialBatch tb, TrialWork w) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
+    if (s >= w.nsites) return;
+    trial_scatter_body(w, s);
 }
 
 // dE of one trial from its sites' partial row sums: sum(new rows) - sum(old rows) + moved-set pairs.
