@@ -21,7 +21,6 @@
 #include "lj_kernels.cuh"
 #include "site_kernels.cuh"
 #include "rows_block.cuh"
-#include "rows_pipe.cuh"
 #include "emt_kernels.cuh"
 #include "free_volume.cuh"
 #include "pcg64.cuh"
@@ -166,14 +165,11 @@ struct mcpyb_engine {
     int subdiv_energy = 1;                // ... wanted for upload + total energies in one call
     int rb_slices = 2;                    // candidate-list slices per work item of the CTA row-sum kernel
     // tuning switches (environment, read once at creation; the defaults are the measured best):
-    //   MCPYB_ROWS=pipe    producer/consumer row-sum kernel (rows_pipe.cuh) instead of the CTA-per-cell one
     //   MCPYB_PDL=0        ordinary stream-ordered launches instead of programmatic dependent launch
     //   MCPYB_RB_SLICES=n  candidate-list slices per work item (1..8)
-    //   MCPYB_EXPAND=0     no per-configuration stencil lists (the producer warp stages from the cell list)
-    bool rows_pipe = false;
+    //   MCPYB_EXPAND=0     no per-configuration stencil lists (every work item stages from the cell list)
     bool use_pdl = true;
     bool use_expand = true;
-    int rows_pipe_blocks = RP_MIN_BLOCKS;
     // stencil lists of the resident batch (rows_block.cuh): built when a SECOND trial batch is scored against
     // the same resident configuration -- one batch per upload (the end-to-end pattern) does not amortise them
     bool exp_valid = false;
@@ -530,15 +526,9 @@ int mcpyb_create(int device, mcpyb_engine** out) {
     mcpyb_engine* e = new mcpyb_engine();
     e->device = device;
     { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) e->num_sms = sms; }
-    if (const char* v = getenv("MCPYB_ROWS")) e->rows_pipe = strcmp(v, "pipe") == 0;
     if (const char* v = getenv("MCPYB_PDL")) e->use_pdl = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_EXPAND")) e->use_expand = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_RB_SLICES")) { const int n = atoi(v); if (n >= 1 && n <= 8) e->rb_slices = n; }
-    if (const char* v = getenv("MCPYB_RP_BLOCKS")) { const int n = atoi(v); if (n >= 1 && n <= 8) e->rows_pipe_blocks = n; }
-    cudaFuncSetAttribute(lj_trial_rows_pipe_kernel<RB_UNROLL, RP_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(RowsPipeSmem));
-    cudaFuncSetAttribute(lj_trial_rows_pipe_kernel<RB_UNROLL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(RowsPipeSmem));
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete e;
         return MCPYB_ERR_CUDA;
@@ -972,7 +962,7 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     w.site_pos = e->tw_pos.p; w.site_a = e->tw_a.p;
     e->tw_stamp = (e->tw_stamp % 0x3FFFFFF) + 1;
     w.stamp = e->tw_stamp;
-    const size_t max_items = (ns >> RB_SITES_SHIFT) + (ns < nbp ? ns : nbp) + 1;
+    const size_t max_items = (ns >> w.item_shift) + (ns < nbp ? ns : nbp) + 1;
     CK(e->tw_items.reserve(max_items), "cudaMalloc trial items");
     CK(e->tw_spos.reserve(ns), "cudaMalloc trial work");
     CK(e->tw_meta.reserve(ns), "cudaMalloc trial work");
@@ -1027,18 +1017,7 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     }
     mark();
     const long long est = (long long)max_items * w.nplanes;
-    if (e->rows_pipe) {
-        // persistent producer / consumer CTAs (rows_pipe.cuh)
-        const long long cap = (long long)e->num_sms * e->rows_pipe_blocks;
-        cudaLaunchConfig_t cfg = config((int)(est < cap ? est : cap), RP_THREADS, sizeof(RowsPipeSmem));
-        if (e->rows_pipe_blocks <= 3)          // fewer CTAs per SM, no register spills
-            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_pipe_kernel<RB_UNROLL, 3>, bv, tb, w, e->lj, xl),
-               "launch lj_trial_rows_pipe_kernel");
-        else
-            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_pipe_kernel<RB_UNROLL, RP_MIN_BLOCKS>, bv, tb, w, e->lj, xl),
-               "launch lj_trial_rows_pipe_kernel");
-        e->launches++;
-    } else {
+    {
         const int rb = (int)(est < e->num_sms * RB_MIN_BLOCKS ? est : e->num_sms * RB_MIN_BLOCKS);
         cudaLaunchConfig_t cfg = config(rb, RB_THREADS, 0);
         CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_block_kernel<RB_UNROLL, RB_MIN_BLOCKS>, bv, tb, w, e->lj, xl),
