@@ -371,13 +371,18 @@ struct EmtTinyTrial {
 __global__ void __launch_bounds__(256)
 emt_trial_tiny_kernel(BatchView b, const __grid_constant__ EmtTinyTrial tt, const EmtTable* __restrict__ tp,
                       const int* __restrict__ z_to_slot, const double* __restrict__ sigma1,
-                      const double* __restrict__ e_atom, double* __restrict__ dE_host) {
+                      const double* __restrict__ e_atom, double* __restrict__ dE_host,
+                      volatile unsigned int* done_flag, unsigned int seq) {
     __shared__ double s_part[8];
     __shared__ int s_parti[8];
     TrialBatch tb;
     tb.T = 1; tb.rep = nullptr; tb.old_off = tt.old_off; tb.old_idx = tt.old_idx;
     tb.new_off = tt.new_off; tb.new_pos = tt.new_pos; tb.new_Z = tt.new_Z;
     emt_trial_delta_body<256>(b, tb, tp, z_to_slot, sigma1, e_atom, dE_host, nullptr, s_part, s_parti);
+    // the host polls this word instead of waiting for the kernel to retire (engine.cu, wait_flag)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && done_flag) { *done_flag = seq; __threadfence_system(); }
 }
 
 // Note (round 1): a lane-per-site variant of these kernels (the scheme of site_kernels.cuh) was

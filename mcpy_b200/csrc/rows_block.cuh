@@ -529,7 +529,8 @@ struct RowsSmallSmem {
 __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const BatchView& b, const TrialBatch& tb,
                                                     const TrialWork& w, const LJParams& p,
                                                     double* __restrict__ dE, int* __restrict__ npairs,
-                                                    int* __restrict__ done_counter) {
+                                                    int* __restrict__ done_counter,
+                                                    volatile unsigned int* done_flag = nullptr, unsigned int seq = 0) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int s = blockIdx.x;                          // site: [0, n_old) old, then new
     const int nq = w.nplanes;
@@ -649,12 +650,19 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
         combine_trial(b, tb, w, p, tt, dE, npairs);
     }
     if (first_bad != ~0ULL) atomicMin(w.err, first_bad);
+    if (done_flag) __threadfence_system();        // dE (pinned host memory) before the sequence word below
     __syncthreads();
     if (tid == 0) {
         const unsigned long long ev = *w.err;
         if (w.err_out) *w.err_out = ev;
         *w.err = ~0ULL;
         *done_counter = 0;
+        if (done_flag) {
+            // the host polls this word instead of waiting for the kernel to retire (engine.cu, wait_flag)
+            __threadfence_system();
+            *done_flag = seq;
+            __threadfence_system();
+        }
     }
 }
 
@@ -677,10 +685,11 @@ struct TinyTrial {
 
 __global__ void __launch_bounds__(RS_THREADS)
 lj_trial_tiny_kernel(BatchView b, const __grid_constant__ TinyTrial tt, TrialWork w, LJParams p,
-                     double* __restrict__ dE_host, int* __restrict__ done_counter) {
+                     double* __restrict__ dE_host, int* __restrict__ done_counter,
+                     volatile unsigned int* done_flag, unsigned int seq) {
     __shared__ RowsSmallSmem sm;
     TrialBatch tb;
     tb.T = 1; tb.rep = nullptr; tb.old_off = tt.old_off; tb.old_idx = tt.old_idx;
     tb.new_off = tt.new_off; tb.new_pos = tt.new_pos; tb.new_Z = nullptr;
-    lj_trial_small_body(sm, b, tb, w, p, dE_host, nullptr, done_counter);
+    lj_trial_small_body(sm, b, tb, w, p, dE_host, nullptr, done_counter, done_flag, seq);
 }
