@@ -531,6 +531,25 @@ def secondary_workloads(device):
         'replica_energies_per_s_one_by_one': 1.0 / t_1,
         'paths_full_incremental_identical': res['paths'],
     }
+    # relax-then-energy (BaseCalculator.get_potential_energy, base_calculator.py:14-22): LBFGS steps per second with
+    # the loop inside the engine, next to the same force evaluations issued one Python call at a time
+    relax = {}
+    for name, cfg, pot in (('S1_argon_500_LJ', synthetic.s1_argon(), 'lj'), ('S3_Ag140_O20_EMT', synthetic.s3_ag_o(), 'emt')):
+        eng = Engine(device)
+        if pot == 'lj':
+            eng.set_lj(cfg['epsilon'], cfg['sigma'], cfg['rc'])
+        else:
+            eng.set_emt()
+        pos, num, cell, pbc = cfg['positions'], cfg['numbers'], cfg['cell'], cfg['pbc']
+        eng.relax_lbfgs(pos, num, cell, pbc, fmax=0.0, steps=5)
+        t0 = time.perf_counter()
+        _, _, nst, _ = eng.relax_lbfgs(pos, num, cell, pbc, fmax=0.0, steps=40)
+        t_loop = (time.perf_counter() - t0) / (nst + 1)
+        t_call = _time(lambda: eng.energy_forces(pos, num, cell, pbc), 20)
+        relax[name] = {'n_atoms': int(len(pos)), 'lbfgs_us_per_step_engine_loop': 1e6 * t_loop,
+                       'energy_forces_us_per_python_call': 1e6 * t_call}
+        eng.close()
+    out['relax_then_energy'] = relax
     return out
 
 

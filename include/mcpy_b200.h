@@ -111,6 +111,19 @@ int mcpyb_energy_forces_host(mcpyb_engine* e, int R, const int64_t* atom_off, co
                              const int32_t* numbers, const double* cells, const uint8_t* pbc,
                              double* energies_out, double* forces_out);
 
+/* Relax-then-energy: BaseCalculator.get_potential_energy (mcpy/calculators/base_calculator.py:14-22) and
+ * CanonicalEnsemble.relax (mcpy/ensembles/canonical_ensemble.py:115-123) run ase.optimize.LBFGS on every trial
+ * configuration and then read its energy.  This call does both: ASE's LBFGS iteration without line search
+ * (H0 = 1/alpha, `memory` curvature pairs, longest atomic step clipped to maxstep, damping; ASE defaults
+ * maxstep 0.2, memory 100, alpha 70, damping 1), converged when max_i |f_i| < fmax, at most max_steps steps
+ * (0 = single point).  positions [n][3] are relaxed IN PLACE, as the optimiser does to atoms.positions;
+ * fixed (may be NULL): n bytes, nonzero = the atom is held (ase.constraints.FixAtoms).
+ * energy_out: energy of the final positions; steps_out / fmax_out (may be NULL): steps taken, final max |f|. */
+int mcpyb_relax_lbfgs_host(mcpyb_engine* e, double* positions, const int32_t* numbers, int n,
+                           const double* cell9, const uint8_t* pbc3, const uint8_t* fixed,
+                           double fmax, int max_steps, double maxstep, int memory, double alpha,
+                           double damping, double* energy_out, int* steps_out, double* fmax_out);
+
 /* Batched incremental form for get_potential_energies(atoms_list) (BatchedReplicaExchange
  * ._batched_single_move, batched_replica_exchange.py:235-302): R resident bases, one batched delta
  * launch per call; configurations are matched with the base in their own slot first, then with any

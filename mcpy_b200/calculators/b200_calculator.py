@@ -13,9 +13,9 @@ The drop-in boundary:
 * the ASE ``Calculator`` protocol (``calculate`` / ``results`` /
   ``implemented_properties``) so ``atoms.calc = calc; atoms.get_potential_energy()``
   works (``mcpy/calculators/base_calculator.py:19-22``,
-  ``canonical_ensemble.py:117-121``).  Forces are not implemented (SURVEY.md 8f
-  row f1), so optimisers raise ``PropertyNotImplementedError`` as ASE does for
-  any energy-only calculator.
+  ``canonical_ensemble.py:117-121``), forces included, so ASE's optimisers can drive it.
+  :class:`B200RelaxCalculator` is the relax-then-energy adapter of
+  ``base_calculator.py:6-22`` with the LBFGS loop inside the engine.
 
 Beyond the reference interface, :meth:`trial_delta_energies` exposes the
 batched trial-move kernel (many proposed insertions / deletions / displacements
@@ -209,3 +209,53 @@ else:
             else:
                 e = self.get_potential_energy(atoms)
                 self.results = {'energy': e, 'free_energy': e}
+
+
+class B200RelaxCalculator:
+    """Relax-then-energy adapter: the drop-in for ``mcpy.calculators.BaseCalculator(calculator, steps, fmax)``
+    (``mcpy/calculators/base_calculator.py:6-22``; ADR ``docs/adr/0002-trial-energy-is-lbfgs-relaxed.md``) with an
+    ASE ``LennardJones`` / ``EMT`` calculator inside.
+
+    ``get_potential_energy(atoms)`` relaxes ``atoms`` IN PLACE with ASE's LBFGS iteration (no line search, ASE
+    defaults ``maxstep=0.2``, ``memory=100``, ``alpha=70``, ``damping=1``) for at most ``steps`` steps or until
+    ``max |f| < fmax``, honouring ``FixAtoms`` constraints, and returns the energy of the relaxed positions --
+    what ``LBFGS(atoms).run(steps=steps, fmax=fmax); atoms.get_potential_energy()`` does, as one
+    ``mcpyb_relax_lbfgs_host`` call instead of one Python round trip per optimiser step.  ``steps=0`` is the
+    single-point energy (``atoms`` untouched), as in the reference.
+    """
+
+    def __init__(self, potential='lj', steps=100, fmax=0.05, epsilon=1.0, sigma=1.0, rc=None, device=0,
+                 maxstep=0.2, memory=100, alpha=70.0, damping=1.0, calculator=None):
+        if steps < 0:
+            raise ValueError(f'steps must be >= 0, got {steps}')
+        if not fmax >= 0.0:
+            raise ValueError(f'fmax must be >= 0, got {fmax}')
+        # an existing B200Calculator (and its engine) may be shared
+        self.calculator = calculator if calculator is not None else B200Calculator(
+            potential, epsilon=epsilon, sigma=sigma, rc=rc, device=device, incremental=False)
+        self.engine = self.calculator.engine
+        self.steps, self.fmax = int(steps), float(fmax)
+        self.maxstep, self.memory, self.alpha, self.damping = float(maxstep), int(memory), float(alpha), float(damping)
+        self.last_steps = 0               # optimiser steps of the last call
+        self.last_fmax = float('nan')     # max |f| at its final positions
+
+    @staticmethod
+    def _fixed_indices(atoms):
+        idx = []
+        for c in getattr(atoms, 'constraints', None) or []:
+            if type(c).__name__ != 'FixAtoms':
+                raise ValueError(f'B200RelaxCalculator supports FixAtoms constraints only, got {type(c).__name__}')
+            idx.extend(int(i) for i in c.get_indices())
+        return idx or None
+
+    def get_potential_energy(self, atoms) -> float:
+        cell = np.asarray(atoms.cell, dtype=np.float64)
+        if self.steps == 0 or len(atoms) == 0:
+            self.last_steps, self.last_fmax = 0, float('nan')
+            return self.engine.potential_energy(atoms.positions, atoms.numbers, cell, atoms.pbc)
+        e, pos, self.last_steps, self.last_fmax = self.engine.relax_lbfgs(
+            atoms.positions, atoms.numbers, cell, atoms.pbc, fmax=self.fmax, steps=self.steps,
+            fixed=self._fixed_indices(atoms), maxstep=self.maxstep, memory=self.memory, alpha=self.alpha,
+            damping=self.damping)
+        atoms.positions[...] = pos        # the optimiser writes the relaxed geometry back (base_calculator.py:19-21)
+        return e

@@ -874,6 +874,121 @@ int mcpyb_energy_forces_host(mcpyb_engine* e, int R, const int64_t* atom_off, co
     return mcpyb_forces_host(e, forces_out);
 }
 
+// upload + energy + forces of ONE configuration with a single stream synchronisation (the optimiser loop below:
+// mcpyb_energy_forces_host synchronises after the energies to check the build status before it launches the
+// force kernels; from the second evaluation of a relaxation on, species and box are known to be good and only
+// the geometry can still fail, which the energy kernels tolerate -- the status is checked after the fact).
+static int energy_forces_one_sync(mcpyb_engine* e, const int64_t* off, const double* positions, const int32_t* numbers,
+                                  const double* cell9, const uint8_t* pbc3, double* energy_out, double* forces_out) {
+    int rc = upload_host_impl(e, off[1] >= 8192 ? e->subdiv_energy : e->subdiv_trials, 1, off, positions, numbers, cell9, pbc3);
+    if (rc != MCPYB_OK) return rc;
+    rc = launch_energies(e);
+    if (rc != MCPYB_OK) return rc;
+    rc = launch_forces(e);
+    if (rc != MCPYB_OK) return rc;
+    const size_t blk = align_up(sizeof(double) + sizeof(long long) + sizeof(int), 64);
+    const size_t nb = 3 * (size_t)e->total_atoms * sizeof(double);
+    CK(e->out_pin.reserve(blk + nb), "cudaMallocHost out");
+    CK(cudaMemcpyAsync(e->out_pin.p, e->E.p, sizeof(double) + sizeof(long long) + sizeof(int), cudaMemcpyDeviceToHost, e->stream), "D2H energy");
+    if (nb) CK(cudaMemcpyAsync(e->out_pin.p + blk, e->forces.p, nb, cudaMemcpyDeviceToHost, e->stream), "D2H forces");
+    CK(cudaStreamSynchronize(e->stream), "sync energy + forces");
+    rc = status_to_error(e, *(const int*)(e->out_pin.p + sizeof(double) + sizeof(long long)), 0);
+    if (rc != MCPYB_OK) return rc;
+    e->status_checked = true;
+    memcpy(energy_out, e->out_pin.p, sizeof(double));
+    if (nb) memcpy(forces_out, e->out_pin.p + blk, nb);
+    return MCPYB_OK;
+}
+
+// ---- relax-then-energy ---------------------------------------------------------------
+// BaseCalculator.get_potential_energy (mcpy/calculators/base_calculator.py:14-22) and CanonicalEnsemble.relax
+// (mcpy/ensembles/canonical_ensemble.py:115-123) hand every trial configuration to ase.optimize.LBFGS before
+// they read its energy.  Through the ASE protocol that is one Python round trip per optimiser step; here the
+// optimiser loop lives next to the force kernels: each step is one upload + cell list + energy + forces of the
+// current positions (mcpyb_energy_forces_host), and the two-loop recursion over 3n doubles runs on the host
+// between them (a few microseconds at these sizes -- far below one kernel launch per dot product).
+// The iteration is ASE 3.23's LBFGS without line search [recalled, ase/optimize/lbfgs.py; restated in
+// oracle/lbfgs.py]: H0 = 1/alpha, at most `memory` (s, y) pairs, step p = -H g scaled so that no atom moves
+// farther than maxstep, damping; converged when max_i |f_i| < fmax, checked before every step; at most
+// max_steps steps.  Atoms with fixed[i] != 0 feel no force and do not move (FixAtoms).
+int mcpyb_relax_lbfgs_host(mcpyb_engine* e, double* positions, const int32_t* numbers, int n, const double* cell9,
+                           const uint8_t* pbc3, const uint8_t* fixed, double fmax, int max_steps, double maxstep,
+                           int memory, double alpha, double damping, double* energy_out, int* steps_out,
+                           double* fmax_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    if (n < 0 || !cell9 || !pbc3 || !energy_out || (n > 0 && !positions)) return e->fail(MCPYB_ERR_ARG, "bad arguments");
+    if (!(fmax >= 0.0) || max_steps < 0 || !(maxstep > 0.0) || memory < 1 || !(alpha > 0.0) || !(damping > 0.0))
+        return e->fail(MCPYB_ERR_ARG, "bad optimiser parameters");
+    const int64_t off[2] = {0, n};
+    const size_t m3 = 3 * (size_t)n;
+    std::vector<double> f(m3), r0, f0, q(m3), z(m3), a;
+    std::vector<std::vector<double>> S, Y;
+    std::vector<double> rho;
+    double E = 0.0;
+    bool trusted = false;                        // species / box accepted by a first, fully checked evaluation
+    auto evaluate = [&]() -> int {
+        int rc = trusted ? energy_forces_one_sync(e, off, positions, numbers, cell9, pbc3, &E, f.data())
+                         : mcpyb_energy_forces_host(e, 1, off, positions, numbers, cell9, pbc3, &E, f.data());
+        if (rc != MCPYB_OK) return rc;
+        trusted = true;
+        if (fixed) for (int i = 0; i < n; ++i) if (fixed[i]) f[3 * i] = f[3 * i + 1] = f[3 * i + 2] = 0.0;
+        return MCPYB_OK;
+    };
+    auto fmax2_of = [&]() {
+        double m = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double v = f[3 * i] * f[3 * i] + f[3 * i + 1] * f[3 * i + 1] + f[3 * i + 2] * f[3 * i + 2];
+            if (!(v <= m)) m = v;                 // NaN propagates: never converged, the step limit ends the loop
+        }
+        return m;
+    };
+    auto dot = [&](const double* u, const double* v) { double t = 0.0; for (size_t k = 0; k < m3; ++k) t += u[k] * v[k]; return t; };
+    int rc = evaluate();
+    if (rc != MCPYB_OK) return rc;
+    int iteration = 0, nsteps = 0;
+    while (n > 0 && nsteps < max_steps && !(fmax2_of() < fmax * fmax)) {
+        // update(): curvature pair of the previous step
+        if (iteration > 0) {
+            std::vector<double> s0(m3), y0(m3);
+            for (size_t k = 0; k < m3; ++k) { s0[k] = positions[k] - r0[k]; y0[k] = f0[k] - f[k]; }
+            rho.push_back(1.0 / dot(y0.data(), s0.data()));
+            S.push_back(std::move(s0)); Y.push_back(std::move(y0));
+        }
+        if (iteration > memory) { S.erase(S.begin()); Y.erase(Y.begin()); rho.erase(rho.begin()); }
+        const int loopmax = (int)S.size() < (memory < iteration ? memory : iteration) ? (int)S.size() : (memory < iteration ? memory : iteration);
+        a.assign((size_t)(loopmax > 0 ? loopmax : 1), 0.0);
+        for (size_t k = 0; k < m3; ++k) q[k] = -f[k];
+        for (int i = loopmax - 1; i >= 0; --i) {
+            a[i] = rho[i] * dot(S[i].data(), q.data());
+            for (size_t k = 0; k < m3; ++k) q[k] -= a[i] * Y[i][k];
+        }
+        const double H0 = 1.0 / alpha;
+        for (size_t k = 0; k < m3; ++k) z[k] = H0 * q[k];
+        for (int i = 0; i < loopmax; ++i) {
+            const double bb = rho[i] * dot(Y[i].data(), z.data());
+            for (size_t k = 0; k < m3; ++k) z[k] += S[i][k] * (a[i] - bb);
+        }
+        // determine_step(): p = -z, scaled so that the longest atomic step is maxstep
+        double longest = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double l = sqrt(z[3 * i] * z[3 * i] + z[3 * i + 1] * z[3 * i + 1] + z[3 * i + 2] * z[3 * i + 2]);
+            if (l > longest) longest = l;
+        }
+        const double scale = (longest >= maxstep ? maxstep / longest : 1.0) * damping;
+        r0.assign(positions, positions + m3);
+        f0 = f;
+        for (size_t k = 0; k < m3; ++k) positions[k] = r0[k] + (-z[k]) * scale;
+        ++iteration;
+        rc = evaluate();
+        if (rc != MCPYB_OK) return rc;
+        ++nsteps;
+    }
+    *energy_out = E;
+    if (steps_out) *steps_out = nsteps;
+    if (fmax_out) *fmax_out = sqrt(fmax2_of());
+    return MCPYB_OK;
+}
+
 // ---- trial moves ---------------------------------------------------------------
 // Per-site partial sums, status words and the slicing shared by every LJ trial path.
 static int prepare_rows_work(mcpyb_engine* e, int nsites, int n_old_total, int n_new_total,

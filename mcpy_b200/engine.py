@@ -231,6 +231,30 @@ class Engine:
         self._R, self._ntot = 1, n
         return float(self._e1[0]), f
 
+    def relax_lbfgs(self, positions, numbers, cell, pbc, fmax=0.05, steps=100_000_000, fixed=None,
+                    maxstep=0.2, memory=100, alpha=70.0, damping=1.0):
+        """``ase.optimize.LBFGS(atoms).run(fmax, steps)`` followed by the energy, in one C call
+        (``mcpyb_relax_lbfgs_host``).  Returns ``(energy, relaxed positions (n, 3), steps taken, final max |f|)``;
+        ``positions`` itself is not modified."""
+        pos = np.array(positions, dtype=np.float64, order='C', copy=True)
+        num = np.ascontiguousarray(numbers, dtype=np.int32)
+        cell = np.ascontiguousarray(cell, dtype=np.float64)
+        pbc = np.ascontiguousarray(pbc, dtype=np.uint8)
+        n = pos.shape[0]
+        if pos.size != 3 * n or num.size != n or cell.size != 9 or pbc.size != 3:
+            raise ValueError('positions (n,3), numbers (n,), cell (3,3), pbc (3,) expected')
+        fx = None
+        if fixed is not None:
+            fx = np.zeros(n, dtype=np.uint8)
+            fx[np.asarray(fixed, dtype=int)] = 1
+        nsteps, fm = C.c_int(0), C.c_double(0.0)
+        self._check(self._lib.mcpyb_relax_lbfgs_host(
+            self._h, pos.ctypes.data, num.ctypes.data, n, cell.ctypes.data, pbc.ctypes.data, ptr(fx),
+            float(fmax), int(min(steps, 2**31 - 1)), float(maxstep), int(memory), float(alpha), float(damping),
+            self._e1.ctypes.data, C.byref(nsteps), C.byref(fm)))
+        self._R, self._ntot = 1, n
+        return float(self._e1[0]), pos, int(nsteps.value), float(fm.value)
+
     def atom_energies(self, want_sigma1=False):
         e = np.empty(self._ntot)
         s = np.empty(self._ntot) if want_sigma1 else None

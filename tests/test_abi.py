@@ -49,3 +49,10 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def test_pinned_allocation_is_declared_and_exported():
+    # mcpyb_alloc_pinned needs a CUDA runtime context to succeed; here only the binding is checked
+    from mcpy_b200 import _lib
+    lib = _lib.load()
+    assert lib.mcpyb_alloc_pinned.restype is not None and hasattr(lib, 'mcpyb_free_pinned')

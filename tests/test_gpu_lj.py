@@ -267,3 +267,35 @@ def test_large_periodic_box_cluster_build(lj_engine):
     assert Eb[0] == E[0]
     assert _rel(Eb[1], cfast.lj_energy(small['positions'], small['cell'], small['pbc'], 1.0, 1.0, 2.5)) <= RTOL
     assert _rel(Eb[2], cfast.lj_energy(cfg['positions'][:5000], cfg['cell'], cfg['pbc'], 1.0, 1.0, 2.5)) <= RTOL
+
+
+def test_stencil_lists_pinned_arrays_and_repeated_batches_give_the_same_bits(lj_engine):
+    """The first batch against a freshly uploaded configuration stages every stencil from the cell list, the
+    following ones read the per-configuration stencil lists (rows_block.cuh, expand_stencils_kernel); page-locked
+    caller arrays take the direct DMA path of mcpyb_trial_delta_e_host.  None of that may change a bit, and a
+    sample of the batch is checked against two full oracle energies."""
+    from mcpy_b200 import pinned_copy, pinned_empty
+    cfg = synthetic.s2_lj()
+    lj_engine.set_lj(cfg['epsilon'], cfg['sigma'], cfg['rc'])
+    lj_engine.upload([cfg['positions']], [cfg['numbers']], cfg['cell'].reshape(1, 9), cfg['pbc'].reshape(1, 3))
+    T = 20_000                                    # > 64 KB of arguments: the large-batch path
+    tb = synthetic.trial_batch(cfg, T, seed=11)
+    args = [tb[k] for k in ('old_off', 'old_idx', 'new_off', 'new_pos', 'new_Z')]
+    first = lj_engine.trial_delta_e(*args)                        # no lists yet
+    second = lj_engine.trial_delta_e(*args)                       # lists built by this call
+    third = lj_engine.trial_delta_e(*args)
+    assert np.array_equal(first, second) and np.array_equal(first, third)
+    out = pinned_empty(T, np.float64)
+    out[:] = np.nan
+    res = lj_engine.trial_delta_e(*[pinned_copy(a) for a in args], out=out)
+    assert res is out and np.array_equal(out, first)
+    # a fresh upload drops the lists; the answer does not move
+    lj_engine.upload([cfg['positions']], [cfg['numbers']], cfg['cell'].reshape(1, 9), cfg['pbc'].reshape(1, 3))
+    assert np.array_equal(lj_engine.trial_delta_e(*args), first)
+    E0 = cfast.lj_energy(cfg['positions'], cfg['cell'], cfg['pbc'], cfg['sigma'], cfg['epsilon'], cfg['rc'])
+    for t in range(0, T, T // 16):
+        p1, _ = synthetic.apply_trial(cfg, tb, t)
+        ref = cfast.lj_energy(p1, cfg['cell'], cfg['pbc'], cfg['sigma'], cfg['epsilon'], cfg['rc']) - E0
+        assert abs(first[t] - ref) <= RTOL * max(1.0, abs(E0), abs(ref)), (t, tb['kind'][t], first[t], ref)
+    with pytest.raises(ValueError):
+        lj_engine.trial_delta_e(*args, out=np.empty(T - 1))
