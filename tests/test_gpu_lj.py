@@ -299,3 +299,57 @@ def test_stencil_lists_pinned_arrays_and_repeated_batches_give_the_same_bits(lj_
         assert abs(first[t] - ref) <= RTOL * max(1.0, abs(E0), abs(ref)), (t, tb['kind'][t], first[t], ref)
     with pytest.raises(ValueError):
         lj_engine.trial_delta_e(*args, out=np.empty(T - 1))
+
+
+def test_full_size_batch_properties(lj_engine):
+    """BASELINE's headline size (65 536 proposals against the 2 000-atom S2 box), where two oracle energies per
+    trial are out of reach: size-independent properties instead.
+      * order: permuting the batch permutes the answers, bit for bit;
+      * identity: displacing an atom onto its own position costs exactly 0.0;
+      * round trip: dE(insert p | C) = -dE(delete it | C + p), to 1e-10;
+      * composition: dE(move i -> b | C) = dE(delete i | C) + dE(insert b | C - i), to 1e-10."""
+    cfg = synthetic.s2_lj()
+    pos, num, cell, pbc = cfg['positions'], cfg['numbers'], cfg['cell'], cfg['pbc']
+    lj_engine.set_lj(cfg['epsilon'], cfg['sigma'], cfg['rc'])
+    up = lambda p: lj_engine.upload([p], [np.ones(len(p), np.int32)], cell.reshape(1, 9), pbc.reshape(1, 3))
+    up(pos)
+    T = 65536
+    tb = synthetic.trial_batch(cfg, T, seed=7)
+    keys = ('old_off', 'old_idx', 'new_off', 'new_pos', 'new_Z')
+    dE = lj_engine.trial_delta_e(*[tb[k] for k in keys])
+    assert np.all(np.isfinite(dE))
+    # ---- order
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(T)
+    no, nn = np.diff(tb['old_off']), np.diff(tb['new_off'])
+    old_rows = np.concatenate([np.arange(tb['old_off'][t], tb['old_off'][t + 1]) for t in perm]).astype(int)
+    new_rows = np.concatenate([np.arange(tb['new_off'][t], tb['new_off'][t + 1]) for t in perm]).astype(int)
+    pb = dict(old_off=np.concatenate([[0], np.cumsum(no[perm])]).astype(np.int32), old_idx=tb['old_idx'][old_rows],
+              new_off=np.concatenate([[0], np.cumsum(nn[perm])]).astype(np.int32), new_pos=tb['new_pos'][new_rows],
+              new_Z=tb['new_Z'][new_rows])
+    assert np.array_equal(lj_engine.trial_delta_e(*[pb[k] for k in keys]), dE[perm])
+    # ---- identity
+    n = len(pos)
+    idx = np.arange(n, dtype=np.int32)
+    off = np.arange(n + 1, dtype=np.int32)
+    same = lj_engine.trial_delta_e(off, idx, off, pos[idx], np.ones(n, np.int32))
+    assert np.all(same == 0.0)
+    # ---- round trip and composition on a sample of the batch
+    ins = [t for t in range(T) if no[t] == 0 and nn[t] == 1][:24]
+    mov = [t for t in range(T) if no[t] == 1 and nn[t] == 1][:24]
+    one = np.array([0, 1], np.int32)
+    zero = np.array([0, 0], np.int32)
+    for t in ins:
+        p = tb['new_pos'][tb['new_off'][t]]
+        up(np.vstack([pos, p]))
+        back = lj_engine.trial_delta_e(one, np.array([n], np.int32), zero, np.zeros((0, 3)), np.zeros(0, np.int32))[0]
+        assert abs(dE[t] + back) <= RTOL * max(1.0, abs(dE[t])), (t, dE[t], back)
+    up(pos)
+    for t in mov:
+        i = int(tb['old_idx'][tb['old_off'][t]])
+        b = tb['new_pos'][tb['new_off'][t]]
+        d_del = lj_engine.trial_delta_e(one, np.array([i], np.int32), zero, np.zeros((0, 3)), np.zeros(0, np.int32))[0]
+        up(np.delete(pos, i, axis=0))
+        d_ins = lj_engine.trial_delta_e(zero, np.zeros(0, np.int32), one, b.reshape(1, 3), np.ones(1, np.int32))[0]
+        up(pos)
+        assert abs(dE[t] - (d_del + d_ins)) <= RTOL * max(1.0, abs(d_del), abs(d_ins)), (t, dE[t], d_del, d_ins)
