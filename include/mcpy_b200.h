@@ -134,6 +134,15 @@ int mcpyb_tracked_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off,
                                 const int32_t* numbers, const double* cells, const uint8_t* pbc,
                                 double* energies_out, int* paths_out);
 
+/* The same with the caller's OWN per-configuration arrays, read where they are (no concatenated copy: for
+ * 64 x 2 000 atoms building one costs more host time than the rest of the call).  positions_of[r] -> n_atoms[r]
+ * rows of 3 doubles (atoms.positions), numbers_of[r] -> n_atoms[r] atomic numbers, int32 or int64
+ * (numbers_are_int64 != 0: what ase.Atoms.numbers holds); numbers_of may be NULL for LJ.                       */
+int mcpyb_tracked_energies_rows_host(mcpyb_engine* e, int R, const double* const* positions_of,
+                                     const void* const* numbers_of, int numbers_are_int64,
+                                     const int64_t* n_atoms, const double* cells, const uint8_t* pbc,
+                                     double* energies_out, int* paths_out);
+
 /* Per-atom energies of the resident batch (ASE's results['energies']) and, for
  * EMT, the density sums sigma1; either pointer may be NULL. Host arrays [sum N]. */
 int mcpyb_atom_energies_host(mcpyb_engine* e, double* e_atom_out, double* sigma1_out);

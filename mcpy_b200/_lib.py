@@ -22,7 +22,7 @@ SYMBOLS = [
     'mcpyb_synchronize', 'mcpyb_set_lj', 'mcpyb_set_emt', 'mcpyb_cutoff', 'mcpyb_emt_species',
     'mcpyb_upload_host', 'mcpyb_upload_dev', 'mcpyb_energies_host', 'mcpyb_energies_dev',
     'mcpyb_potential_energies_host', 'mcpyb_tracked_energy_host', 'mcpyb_atom_energies_host',
-    'mcpyb_tracked_energies_host', 'mcpyb_forces_host', 'mcpyb_energy_forces_host', 'mcpyb_relax_lbfgs_host',
+    'mcpyb_tracked_energies_host', 'mcpyb_tracked_energies_rows_host', 'mcpyb_forces_host', 'mcpyb_energy_forces_host', 'mcpyb_relax_lbfgs_host',
     'mcpyb_trial_delta_e_host', 'mcpyb_trial_delta_e_dev',
     'mcpyb_neighbor_pairs_host',
     'mcpyb_free_volume_count_host', 'mcpyb_free_volume_count_dev',
@@ -75,6 +75,7 @@ def load():
     lib.mcpyb_tracked_energy_host.argtypes = [_p, _p, _p, C.c_int, _p, _p, _p, _p]
     lib.mcpyb_atom_energies_host.argtypes = [_p, _p, _p]
     lib.mcpyb_tracked_energies_host.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p, _p, _p]
+    lib.mcpyb_tracked_energies_rows_host.argtypes = [_p, C.c_int, _p, _p, C.c_int, _p, _p, _p, _p, _p]
     lib.mcpyb_forces_host.argtypes = [_p, _p]
     lib.mcpyb_energy_forces_host.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p, _p, _p]
     lib.mcpyb_relax_lbfgs_host.argtypes = [_p, _p, _p, C.c_int, _p, _p, _p, C.c_double, C.c_int, C.c_double,

@@ -1487,11 +1487,13 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
 // Align an incoming configuration P with a base B: rows equal within 1e-10 A and of the same species
 // match; unmatched base rows are removed, unmatched incoming rows added (any such description gives
 // the right energy difference).  Returns false when more than `limit` atoms differ.
-static bool align_rows(const double* B, const int32_t* BZ, int nB, const double* P, const int32_t* PZ, int n,
+extern "C++" {
+template <class ZT>
+static bool align_rows(const double* B, const int32_t* BZ, int nB, const double* P, const ZT* PZ, int n,
                        int limit, int32_t* old_idx, int* new_row, int& n_old, int& n_new) {
     const double tol = 1e-10;
     auto match = [&](int i, int j) {
-        return BZ[i] == (PZ ? PZ[j] : 0) && fabs(B[3 * i] - P[3 * j]) <= tol &&
+        return (long long)BZ[i] == (PZ ? (long long)PZ[j] : 0LL) && fabs(B[3 * i] - P[3 * j]) <= tol &&
                fabs(B[3 * i + 1] - P[3 * j + 1]) <= tol && fabs(B[3 * i + 2] - P[3 * j + 2]) <= tol;
     };
     n_old = n_new = 0;
@@ -1501,8 +1503,14 @@ static bool align_rows(const double* B, const int32_t* BZ, int nB, const double*
         {
             const int run = (nB - i < n - j ? nB - i : n - j);
             int k = 0;
+            auto same_species = [&](int i0, int j0) {
+                if (!PZ) return true;
+                if (sizeof(ZT) == sizeof(int32_t)) return memcmp(BZ + i0, PZ + j0, 64 * sizeof(int32_t)) == 0;
+                for (int q = 0; q < 64; ++q) if ((long long)BZ[i0 + q] != (long long)PZ[j0 + q]) return false;
+                return true;
+            };
             while (k + 64 <= run && memcmp(B + 3 * (size_t)(i + k), P + 3 * (size_t)(j + k), 64 * 24) == 0 &&
-                   (!PZ || memcmp(BZ + i + k, PZ + j + k, 64 * sizeof(int32_t)) == 0)) k += 64;
+                   same_species(i + k, j + k)) k += 64;
             i += k; j += k;                       // (without numbers every stored species is 0 as well)
             if (i >= nB || j >= n) break;
         }
@@ -1525,27 +1533,27 @@ static bool align_rows(const double* B, const int32_t* BZ, int nB, const double*
 // configuration differs from every base by more than a few atoms, the whole incoming batch is
 // evaluated in full and becomes the new set of bases.  paths_out[r] (may be NULL): 0 full,
 // 1 incremental, 2 identical to its base.
-int mcpyb_tracked_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
-                                const int32_t* numbers, const double* cells, const uint8_t* pbc,
-                                double* energies_out, int* paths_out) {
-    if (!e) return MCPYB_ERR_ARG;
-    cudaSetDevice(e->device);
-    if (R < 0 || (R > 0 && (!atom_off || !cells || !pbc || !energies_out))) return e->fail(MCPYB_ERR_ARG, "bad arguments");
-    if (e->pot_kind == POT_NONE) return e->fail(MCPYB_ERR_STATE, "no potential set");
-    if (R == 0) return MCPYB_OK;
+// Core of the two entry points below.  Configuration r is n_of[r] rows at pos_of[r] (positions) and num_of[r]
+// (atomic numbers, int32 or int64 -- ASE keeps int64; may be NULL for LJ): either slices of one concatenated
+// array or the caller's own per-configuration arrays, read where they are.
+template <class ZT>
+static int tracked_energies_core(mcpyb_engine* e, int R, const double* const* pos_of, const ZT* const* num_of,
+                                 const int64_t* n_of, const double* cells, const uint8_t* pbc,
+                                 double* energies_out, int* paths_out) {
     const int kLimit = 16;                       // moved atoms (old + new) per configuration before a re-base
     const int Rb = e->trkb_valid ? (int)e->trkb_E.size() : 0;
     bool incremental = e->trkb_valid && e->have_batch && e->R == Rb && Rb > 0;
     std::vector<int32_t> t_rep, t_old_off(1, 0), t_new_off(1, 0), t_old_idx, t_new_Z;
     std::vector<double> t_new_pos;
     std::vector<int> slot_of(R, -1), trial_of(R, -1);
+    const bool have_numbers = num_of != nullptr;
     if (incremental) {
         int32_t old_idx[kLimit];
         int new_row[kLimit];
         for (int r = 0; r < R && incremental; ++r) {
-            const int n = (int)(atom_off[r + 1] - atom_off[r]);
-            const double* P = positions + 3 * atom_off[r];
-            const int32_t* PZ = numbers ? numbers + atom_off[r] : nullptr;
+            const int n = (int)n_of[r];
+            const double* P = pos_of[r];
+            const ZT* PZ = have_numbers ? num_of[r] : nullptr;
             int n_old = 0, n_new = 0, found = -1;
             for (int probe = 0; probe <= Rb && found < 0; ++probe) {
                 const int q = probe == 0 ? r : probe - 1;                 // own slot first
@@ -1554,8 +1562,8 @@ int mcpyb_tracked_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off,
                 if (abs(nB - n) > kLimit) continue;
                 if (memcmp(&e->trkb_cell[9 * (size_t)q], cells + 9 * (size_t)r, 9 * sizeof(double)) != 0 ||
                     memcmp(&e->trkb_pbc[3 * (size_t)q], pbc + 3 * (size_t)r, 3) != 0) continue;
-                if (align_rows(&e->trkb_pos[3 * (size_t)e->trkb_off[q]], &e->trkb_Z[(size_t)e->trkb_off[q]], nB,
-                               P, PZ, n, kLimit, old_idx, new_row, n_old, n_new)) found = q;
+                if (align_rows<ZT>(&e->trkb_pos[3 * (size_t)e->trkb_off[q]], &e->trkb_Z[(size_t)e->trkb_off[q]], nB,
+                                   P, PZ, n, kLimit, old_idx, new_row, n_old, n_new)) found = q;
             }
             if (found < 0) { incremental = false; break; }
             slot_of[r] = found;
@@ -1565,7 +1573,7 @@ int mcpyb_tracked_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off,
             for (int k = 0; k < n_old; ++k) t_old_idx.push_back(old_idx[k]);
             for (int k = 0; k < n_new; ++k) {
                 for (int c = 0; c < 3; ++c) t_new_pos.push_back(P[3 * new_row[k] + c]);
-                t_new_Z.push_back(PZ ? PZ[new_row[k]] : 0);
+                t_new_Z.push_back(PZ ? (int32_t)PZ[new_row[k]] : 0);
             }
             t_old_off.push_back((int32_t)t_old_idx.size());
             t_new_off.push_back((int32_t)t_new_Z.size());
@@ -1578,7 +1586,7 @@ int mcpyb_tracked_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off,
         if (T > 0) {
             const bool keep = e->trkb_valid;
             int rc = mcpyb_trial_delta_e_host(e, T, t_rep.data(), t_old_off.data(), t_old_idx.data(), t_new_off.data(),
-                                              t_new_pos.data(), numbers ? t_new_Z.data() : nullptr, dE.data(), nullptr);
+                                              t_new_pos.data(), have_numbers ? t_new_Z.data() : nullptr, dE.data(), nullptr);
             e->trkb_valid = keep;
             if (rc != MCPYB_OK) return rc;
             if (e->pot_kind == POT_EMT) for (int t = 0; t < T; ++t) finite = finite && isfinite(dE[t]);   // thin box -> NaN
@@ -1592,14 +1600,22 @@ int mcpyb_tracked_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off,
             return MCPYB_OK;
         }
     }
-    // full evaluation; the incoming batch becomes the set of bases
-    int rc = mcpyb_potential_energies_host(e, R, atom_off, positions, numbers, cells, pbc, energies_out);
+    // full evaluation; the incoming batch becomes the set of bases (gathered straight into their host mirror)
+    std::vector<int64_t> off((size_t)R + 1, 0);
+    for (int r = 0; r < R; ++r) off[r + 1] = off[r] + n_of[r];
+    const size_t total = (size_t)off[R];
+    std::vector<double> pos_all(3 * total);
+    std::vector<int32_t> z_all(total, 0);
+    for (int r = 0; r < R; ++r) {
+        if (n_of[r]) memcpy(&pos_all[3 * (size_t)off[r]], pos_of[r], (size_t)n_of[r] * 24);
+        if (have_numbers) for (int64_t k = 0; k < n_of[r]; ++k) z_all[(size_t)(off[r] + k)] = (int32_t)num_of[r][k];
+    }
+    int rc = mcpyb_potential_energies_host(e, R, off.data(), pos_all.data(), have_numbers ? z_all.data() : nullptr,
+                                           cells, pbc, energies_out);
     if (rc != MCPYB_OK) return rc;
-    const size_t total = (size_t)atom_off[R];
-    e->trkb_pos.assign(positions, positions + 3 * total);
-    e->trkb_Z.assign(total, 0);
-    if (numbers) e->trkb_Z.assign(numbers, numbers + total);
-    e->trkb_off.assign(atom_off, atom_off + R + 1);
+    e->trkb_pos.swap(pos_all);
+    e->trkb_Z.swap(z_all);
+    e->trkb_off.swap(off);
     e->trkb_cell.assign(cells, cells + 9 * (size_t)R);
     e->trkb_pbc.assign(pbc, pbc + 3 * (size_t)R);
     e->trkb_E.assign(energies_out, energies_out + R);
@@ -1607,6 +1623,49 @@ int mcpyb_tracked_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off,
     e->trk_full += R;
     if (paths_out) for (int r = 0; r < R; ++r) paths_out[r] = 0;
     return MCPYB_OK;
+}
+
+}  // extern "C++"
+
+int mcpyb_tracked_energies_host(mcpyb_engine* e, int R, const int64_t* atom_off, const double* positions,
+                                const int32_t* numbers, const double* cells, const uint8_t* pbc,
+                                double* energies_out, int* paths_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (R < 0 || (R > 0 && (!atom_off || !cells || !pbc || !energies_out))) return e->fail(MCPYB_ERR_ARG, "bad arguments");
+    if (e->pot_kind == POT_NONE) return e->fail(MCPYB_ERR_STATE, "no potential set");
+    if (R == 0) return MCPYB_OK;
+    std::vector<const double*> pos_of((size_t)R);
+    std::vector<const int32_t*> num_of((size_t)R);
+    std::vector<int64_t> n_of((size_t)R);
+    for (int r = 0; r < R; ++r) {
+        pos_of[r] = positions + 3 * atom_off[r];
+        num_of[r] = numbers ? numbers + atom_off[r] : nullptr;
+        n_of[r] = atom_off[r + 1] - atom_off[r];
+        if (n_of[r] < 0) return e->fail(MCPYB_ERR_ARG, "atom_off must be non-decreasing");
+    }
+    return tracked_energies_core<int32_t>(e, R, pos_of.data(), numbers ? num_of.data() : nullptr, n_of.data(), cells, pbc,
+                                          energies_out, paths_out);
+}
+
+int mcpyb_tracked_energies_rows_host(mcpyb_engine* e, int R, const double* const* positions_of,
+                                     const void* const* numbers_of, int numbers_are_int64, const int64_t* n_atoms,
+                                     const double* cells, const uint8_t* pbc, double* energies_out, int* paths_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (R < 0 || (R > 0 && (!positions_of || !n_atoms || !cells || !pbc || !energies_out))) return e->fail(MCPYB_ERR_ARG, "bad arguments");
+    if (e->pot_kind == POT_NONE) return e->fail(MCPYB_ERR_STATE, "no potential set");
+    if (R == 0) return MCPYB_OK;
+    for (int r = 0; r < R; ++r) {
+        if (n_atoms[r] < 0 || (n_atoms[r] > 0 && (!positions_of[r] || (numbers_of && !numbers_of[r]))))
+            return e->fail(MCPYB_ERR_ARG, "configuration %d: bad row pointers", r);
+    }
+    if (e->pot_kind == POT_EMT && !numbers_of) return e->fail(MCPYB_ERR_ARG, "EMT needs atomic numbers");
+    if (numbers_are_int64)
+        return tracked_energies_core<int64_t>(e, R, positions_of, (const int64_t* const*)numbers_of, n_atoms, cells, pbc,
+                                              energies_out, paths_out);
+    return tracked_energies_core<int32_t>(e, R, positions_of, (const int32_t* const*)numbers_of, n_atoms, cells, pbc,
+                                          energies_out, paths_out);
 }
 
 // ---- neighbour pairs -------------------------------------------------------------

@@ -160,6 +160,22 @@ class Engine:
     def tracked_energies(self, positions_list, numbers_list, cells, pbcs):
         """Batch through the incremental path (resident bases + one batched delta launch); returns
         ``(energies, paths)`` with paths 0 = full evaluation, 1 = incremental, 2 = identical to its base."""
+        R = len(positions_list)
+        rows = self._row_pointers(positions_list, numbers_list) if R else None
+        if rows is not None:
+            # every configuration is already a C-contiguous float64 / int32-or-int64 array (what ase.Atoms
+            # holds): the engine reads them where they are -- concatenating 64 x 2 000 atoms costs ~0.4 ms,
+            # more than the rest of the call
+            pos_ptrs, num_ptrs, is64, n_of = rows
+            cells = as_f64(cells, (R, 9))
+            pbcs = as_u8(np.asarray(pbcs, dtype=bool).reshape(R, 3))
+            E = np.empty(R, dtype=np.float64)
+            paths = np.zeros(R, dtype=np.int32)
+            self._check(self._lib.mcpyb_tracked_energies_rows_host(
+                self._h, R, ptr(pos_ptrs), ptr(num_ptrs), is64, ptr(n_of), ptr(cells), ptr(pbcs), ptr(E), ptr(paths)))
+            self._R = R
+            self._ntot = int(n_of.sum())
+            return E, paths
         R, off, pos, num, cells, pbcs = self._batch_args(positions_list, numbers_list, cells, pbcs)
         E = np.empty(R, dtype=np.float64)
         paths = np.zeros(R, dtype=np.int32)
@@ -168,6 +184,32 @@ class Engine:
         self._R = R
         self._ntot = int(off[-1])
         return E, paths
+
+    @staticmethod
+    def _row_pointers(positions_list, numbers_list):
+        """(position pointers, number pointers, numbers-are-int64 flag, rows per configuration) when every array can
+        be read in place, else None (the caller concatenates)."""
+        R = len(positions_list)
+        pp = np.empty(R, dtype=np.uintp)
+        zp = np.empty(R, dtype=np.uintp)
+        n_of = np.empty(R, dtype=np.int64)
+        f64, zdt = np.dtype(np.float64), None
+        for r in range(R):
+            p, z = positions_list[r], numbers_list[r]
+            if not (isinstance(p, np.ndarray) and isinstance(z, np.ndarray)) or p.dtype != f64 or p.ndim != 2 \
+                    or p.shape[1] != 3 or not p.flags.c_contiguous or not z.flags.c_contiguous \
+                    or z.shape != (p.shape[0],):
+                return None
+            if zdt is None:
+                zdt = z.dtype
+                if zdt not in (np.dtype(np.int32), np.dtype(np.int64)):
+                    return None
+            elif z.dtype != zdt:
+                return None
+            pp[r] = p.__array_interface__['data'][0]
+            zp[r] = z.__array_interface__['data'][0]
+            n_of[r] = p.shape[0]
+        return pp, zp, int(zdt == np.dtype(np.int64)), n_of
 
     def potential_energy(self, positions, numbers, cell, pbc) -> float:
         """Single configuration, minimal marshalling (the per-trial drop-in call)."""

@@ -61,10 +61,12 @@ def test_tracked_chain_equals_full_evaluations(potential):
     trk.close(); full.close()
 
 
-@pytest.mark.parametrize('potential', ['lj', 'emt'])
-def test_tracked_batch_equals_full_evaluations(potential):
+@pytest.mark.parametrize('potential,zdt', [('lj', np.int32), ('lj', np.int64), ('emt', np.int64)])
+def test_tracked_batch_equals_full_evaluations(potential, zdt):
     """get_potential_energies through resident bases: per-replica moves that accumulate, replicas
-    swapping slots (replica exchange), ragged sizes, a subset of the replicas, a re-base."""
+    swapping slots (replica exchange), ragged sizes, a subset of the replicas, a re-base.  The configurations
+    are read where they are (mcpyb_tracked_energies_rows_host; int32 or ASE's int64 atomic numbers); every
+    seventh call hands over a non-contiguous array, which takes the concatenating entry point."""
     rng = np.random.default_rng(23)
     R = 6
     if potential == 'lj':
@@ -80,7 +82,7 @@ def test_tracked_batch_equals_full_evaluations(potential):
     trk, full = Engine(0), Engine(0)
     setup(trk); setup(full)
     pos = [c['positions'].copy() for c in cfgs]
-    num = [np.asarray(c['numbers'], np.int32).copy() for c in cfgs]
+    num = [np.asarray(c['numbers'], zdt).copy() for c in cfgs]
     cells = np.stack([c['cell'].reshape(9) for c in cfgs])
     pbcs = np.stack([c['pbc'] for c in cfgs])
     paths = np.zeros(3, int)
@@ -92,11 +94,17 @@ def test_tracked_batch_equals_full_evaluations(potential):
                 i = rng.integers(len(tp[r])); tp[r][i] += rng.uniform(-step, step, 3)
             elif kind == 1:
                 p = tp[r][rng.integers(len(tp[r]))] + rng.uniform(-2.5, 2.5, 3)
-                tp[r] = np.concatenate([tp[r], [p]]); tn[r] = np.concatenate([tn[r], [new_Z]]).astype(np.int32)
+                tp[r] = np.concatenate([tp[r], [p]]); tn[r] = np.concatenate([tn[r], [new_Z]]).astype(zdt)
             elif len(tp[r]) > 5:
                 i = rng.integers(len(tp[r])); tp[r] = np.delete(tp[r], i, axis=0); tn[r] = np.delete(tn[r], i)
         sel = list(range(R)) if it % 11 else [0, 2, 3]      # sometimes only a subset is evaluated
-        e_t, pth = trk.tracked_energies([tp[r] for r in sel], [tn[r] for r in sel], cells[sel], pbcs[sel])
+        given = [tp[r] for r in sel]
+        if it % 7 == 6:                                     # a strided view: not readable in place
+            wide = np.zeros((len(given[0]), 6)); wide[:, ::2] = given[0]; given[0] = wide[:, ::2]
+            assert Engine._row_pointers(given, [tn[r] for r in sel]) is None
+        else:
+            assert Engine._row_pointers(given, [tn[r] for r in sel]) is not None
+        e_t, pth = trk.tracked_energies(given, [tn[r] for r in sel], cells[sel], pbcs[sel])
         e_f = full.potential_energies([tp[r] for r in sel], [tn[r] for r in sel], cells[sel], pbcs[sel])
         assert np.all(np.abs(e_t - e_f) <= 1e-10 * np.maximum(1.0, np.abs(e_f))), (it, e_t - e_f)
         for x in pth:
