@@ -454,6 +454,16 @@ __device__ __forceinline__ void trial_sites_body(const BatchView& b, const Trial
     const GridDesc& g = b.grid[r];
     const int ex0 = oe > ob ? tb.old_idx[ob] : -1;
     const long long cnt_bits = ((long long)(oe - ob) << 32) | ((long long)w.stamp << 38);
+    auto bin_of = [&](double x, double y, double z, int wr[3]) {
+        int c[3];
+        locate(g, x, y, z, c, wr);
+        return r * w.bin_stride + (c[2] * g.ncell[1] + c[1]) * g.ncell[0] + c[0];
+    };
+    auto record = [&](int s, int bin, int rank, double x, double y, double z, const int wr[3]) {
+        w.site_trial[s] = t;
+        w.site_a[s] = make_int4(bin, rank, ex0, ob);
+        w.site_pos[s] = make_double4(x, y, z, __longlong_as_double((long long)pack_wraps(wr[0], wr[1], wr[2]) | cnt_bits));
+    };
     for (int i = ob; i < oe + (ne - nb); ++i) {
         int s;
         double x, y, z;
@@ -466,13 +476,10 @@ __device__ __forceinline__ void trial_sites_body(const BatchView& b, const Trial
             s = w.n_old + k;
             x = tb.new_pos[3 * k]; y = tb.new_pos[3 * k + 1]; z = tb.new_pos[3 * k + 2];
         }
-        int c[3], wr[3];
-        locate(g, x, y, z, c, wr);
-        const int bin = r * w.bin_stride + (c[2] * g.ncell[1] + c[1]) * g.ncell[0] + c[0];
+        int wr[3];
+        const int bin = bin_of(x, y, z, wr);
         const int rank = atomicAdd(&w.hist[(size_t)bin * TRIAL_HIST_STRIDE], 1);
-        w.site_trial[s] = t;
-        w.site_a[s] = make_int4(bin, rank, ex0, ob);
-        w.site_pos[s] = make_double4(x, y, z, __longlong_as_double((long long)pack_wraps(wr[0], wr[1], wr[2]) | cnt_bits));
+        record(s, bin, rank, x, y, z, wr);
     }
 }
 
@@ -488,33 +495,60 @@ trial_sites_kernel(BatchView b, TrialBatch tb, TrialWork w) {
 // One CTA of NT threads: exclusive scans of the bin histogram -> bin starts, work items; re-zeroes the histogram.
 template <int NT>
 __device__ __forceinline__ void trial_scan_body(const TrialWork& w, int* s_a, int* s_b) {
-    const int tid = threadIdx.x;
-    // each thread owns a contiguous run of bins so the scan is two passes over registers/global
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // each thread owns a contiguous run of bins; the counts of short runs (the usual case: two bins per
+    // thread for a 2 000-atom box) stay in registers, so the histogram is read once
     const int per = (w.nbins + NT - 1) / NT;
     const int beg = min(tid * per, w.nbins), end = min(beg + per, w.nbins);
-    int sa = 0, sb = 0;
+    unsigned long long ev = ~0ULL;
+    if (tid == 0) ev = *w.err;                       // independent of the scan: in flight alongside it
+    int sa = 0, sb = 0, c4[4] = {0, 0, 0, 0};
     const int ish = w.item_shift, iround = (1 << ish) - 1;
-    for (int i = beg; i < end; ++i) { const int c = w.hist[(size_t)i * TRIAL_HIST_STRIDE]; sa += c; sb += (c + iround) >> ish; }
-    s_a[tid] = sa; s_b[tid] = sb;
-    __syncthreads();
-    for (int o = 1; o < NT; o <<= 1) {
-        const int ta = (tid >= o) ? s_a[tid - o] : 0, tb2 = (tid >= o) ? s_b[tid - o] : 0;
-        __syncthreads();
-        s_a[tid] += ta; s_b[tid] += tb2;
-        __syncthreads();
-    }
-    int ra = s_a[tid] - sa, rb = s_b[tid] - sb;      // exclusive prefix of this thread's run
     for (int i = beg; i < end; ++i) {
         const int c = w.hist[(size_t)i * TRIAL_HIST_STRIDE];
-        w.hist[(size_t)i * TRIAL_HIST_STRIDE] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (i - beg == k) c4[k] = c;
+        sa += c; sb += (c + iround) >> ish;
+    }
+    // block-wide exclusive scan of (sa, sb): shuffles inside the warps, one warp over the warp totals
+    int ia = sa, ib = sb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb2 = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb2; }
+    }
+    if (lane == 31) { s_a[wid] = ia; s_b[wid] = ib; }
+    __syncthreads();
+    if (wid == 0) {
+        int va = lane < NT / 32 ? s_a[lane] : 0, vb = lane < NT / 32 ? s_b[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ta = __shfl_up_sync(0xffffffffu, va, o), tb2 = __shfl_up_sync(0xffffffffu, vb, o);
+            if (lane >= o) { va += ta; vb += tb2; }
+        }
+        if (lane < NT / 32) { s_a[lane] = va; s_b[lane] = vb; }        // inclusive totals of warps 0 .. lane
+    }
+    __syncthreads();
+    int ra = (wid ? s_a[wid - 1] : 0) + ia - sa, rb = (wid ? s_b[wid - 1] : 0) + ib - sb;   // exclusive prefix of this run
+    for (int i = beg; i < end; ++i) {
+        int c = 0;
+        if (i - beg < 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (i - beg == k) c = c4[k];
+        } else {
+            c = w.hist[(size_t)i * TRIAL_HIST_STRIDE];
+        }
+        if (c) w.hist[(size_t)i * TRIAL_HIST_STRIDE] = 0;
         w.bin_count[i] = ra; w.item_start[i] = rb;
         const int ni = (c + iround) >> ish;
         if (w.item_tab) for (int gq = 0; gq < ni; ++gq) w.item_tab[rb + gq] = make_int2(i, gq);
         ra += c; rb += ni;
     }
-    if (tid == NT - 1) { w.bin_count[w.nbins] = s_a[NT - 1]; w.item_start[w.nbins] = s_b[NT - 1]; w.totals[0] = s_b[NT - 1]; w.totals[1] = 0; }
+    if (tid == NT - 1) {
+        const int ta = s_a[NT / 32 - 1], tb2 = s_b[NT / 32 - 1];
+        w.bin_count[w.nbins] = ta; w.item_start[w.nbins] = tb2; w.totals[0] = tb2; w.totals[1] = 0;
+    }
     if (tid == 0) {
-        const unsigned long long ev = *w.err;
         if (w.err_out) *w.err_out = ev;
         *w.err = ~0ULL;
     }
