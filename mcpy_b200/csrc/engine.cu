@@ -882,10 +882,24 @@ static int energy_forces_one_sync(mcpyb_engine* e, const int64_t* off, const dou
                                   const double* cell9, const uint8_t* pbc3, double* energy_out, double* forces_out) {
     int rc = upload_host_impl(e, off[1] >= 8192 ? e->subdiv_energy : e->subdiv_trials, 1, off, positions, numbers, cell9, pbc3);
     if (rc != MCPYB_OK) return rc;
-    rc = launch_energies(e);
-    if (rc != MCPYB_OK) return rc;
-    rc = launch_forces(e);
-    if (rc != MCPYB_OK) return rc;
+    if (e->pot_kind == POT_LJ && e->total_atoms > 0 && e->total_atoms <= 8192) {
+        // one pass over the pairs gives forces and energies (lj_energy_forces_kernel); the reduction adds them up
+        const int total = e->total_atoms;
+        CK(e->forces.reserve(3 * (size_t)total), "cudaMalloc forces");
+        int blocks = total < e->num_sms * 16 ? total : e->num_sms * 16;
+        lj_energy_forces_kernel<<<blocks, 32 * EF_WARPS, 0, e->stream>>>(e->view(), e->d_atom_off, total, e->lj,
+                                                                        e->forces.p, e->e_atom.p, e->pair_count.p);
+        LAUNCH_CHECK("lj_energy_forces_kernel");
+        reduce_replica_kernel<<<e->R, e->max_n > 1024 ? 1024 : 256, 0, e->stream>>>(
+            e->e_atom.p, e->d_atom_off, e->E.p, e->pair_count.p, e->pairs_ptr(), e->grid.p, e->status_ptr(),
+            nullptr, nullptr, 0);
+        LAUNCH_CHECK("reduce_replica_kernel");
+    } else {
+        rc = launch_energies(e);
+        if (rc != MCPYB_OK) return rc;
+        rc = launch_forces(e);
+        if (rc != MCPYB_OK) return rc;
+    }
     const size_t blk = align_up(sizeof(double) + sizeof(long long) + sizeof(int), 64);
     const size_t nb = 3 * (size_t)e->total_atoms * sizeof(double);
     CK(e->out_pin.reserve(blk + nb), "cudaMallocHost out");

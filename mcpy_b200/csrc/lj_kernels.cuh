@@ -118,6 +118,60 @@ lj_forces_kernel(BatchView b, const int* __restrict__ atom_off, int total_atoms,
     }
 }
 
+// Energy AND forces in one pass for the relaxation loop (mcpyb_relax_lbfgs_host): the pair loop that gives the
+// force also gives the pair energy, so the separate energy kernel (31 of ~100 us of GPU time per optimiser step at
+// 500 atoms) disappears.  A relaxation works on ONE small configuration, where a warp per atom leaves the GPU
+// empty (500 warps on 148 SMs): here a CTA of EF_WARPS warps shares one atom, warp w walking the stencil rows
+// w, w + EF_WARPS, ...; the warps' partial sums are folded in warp order, so the result does not depend on timing.
+// e_atom[a] = 0.5 * sum of pair energies (ASE's results['energies']), pair_count[a] = in-cutoff pairs.
+#define EF_WARPS 4
+__global__ void __launch_bounds__(32 * EF_WARPS)
+lj_energy_forces_kernel(BatchView b, const int* __restrict__ atom_off, int total_atoms, LJParams p,
+                        double* __restrict__ forces, double* __restrict__ e_atom, int* __restrict__ pair_count) {
+    __shared__ double s_part[EF_WARPS][4];
+    __shared__ int s_cnt[EF_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int a = blockIdx.x; a < total_atoms; a += gridDim.x) {
+        const int r = find_replica(atom_off, b.R, a);
+        const GridDesc& g = b.grid[r];
+        const int off = g.atom_off;
+        const int i = a - off;
+        const double4 me = b.upos[a];
+        const int* cstart = b.cell_start + (size_t)r * b.cs_stride;
+        double fx = 0.0, fy = 0.0, fz = 0.0, en = 0.0;
+        int cnt = 0;
+        for_each_candidate(g, b.spos + off, cstart, me.x, me.y, me.z, lane, 32,
+            [&](const Cand& c) {
+                if (c.r2 <= p.rc2 && !(c.same_image && tag_index(c.tag) == i)) {
+                    const double inv = fast_rcp(c.r2);
+                    const double t = p.sigma2 * inv;
+                    const double c6 = t * t * t;
+                    const double w = -6.0 * p.eps4 * fma(2.0 * c6, c6, -c6) * inv;     // -24 eps (2 c12 - c6) / r2
+                    fx = fma(w, c.dx, fx); fy = fma(w, c.dy, fy); fz = fma(w, c.dz, fz);
+                    en += fma(p.eps4, fma(c6, c6, -c6), -p.e0);                          // 4 eps (c12 - c6) - e0
+                    ++cnt;
+                }
+            }, wid, EF_WARPS);
+        fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz); en = warp_sum(en); cnt = warp_sum_int(cnt);
+        if (lane == 0) { s_part[wid][0] = fx; s_part[wid][1] = fy; s_part[wid][2] = fz; s_part[wid][3] = en; s_cnt[wid] = cnt; }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double v = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < EF_WARPS; ++ww) v += s_part[ww][threadIdx.x];
+            if (threadIdx.x < 3) forces[3 * (size_t)a + threadIdx.x] = v;
+            else e_atom[a] = 0.5 * v;
+        }
+        if (threadIdx.x == 4) {
+            int c = 0;
+#pragma unroll
+            for (int ww = 0; ww < EF_WARPS; ++ww) c += s_cnt[ww];
+            pair_count[a] = c;
+        }
+        __syncthreads();
+    }
+}
+
 // Fixed-order per-replica reduction: E[r] = sum_i e_atom[off+i]; one CTA per replica.
 // With e_part != nullptr it first folds the stencil-plane partials of the lane-per-atom LJ kernel:
 // e_atom[a] = 0.5 * sum_planes e_part[a][plane], pair_count[a] = sum_planes cnt_part[a][plane].
