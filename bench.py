@@ -403,7 +403,7 @@ def run_b200(args):
         'gpu_launches': int(gpu_launches),
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': achieved / peak if peak else None, 'traffic': traffic,
-                     'kernel': 'lj_trial_rows_block_kernel<4,6>',
+                     'kernel': 'lj_trial_rows_block_kernel<4,12>',
                      'kernel_ms': rows_ms, 'kernel_share_of_step': rows_ms / sum(stage_ms.values()),
                      'algorithmic_flop_per_launch': alg_flop,
                      'step_achieved': alg_flop / (ms_per_step * 1e-3) / 1e12,

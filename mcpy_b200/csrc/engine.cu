@@ -1015,6 +1015,7 @@ static int prepare_rows_work(mcpyb_engine* e, int nsites, int n_old_total, int n
     // every path cuts a cell's candidate list into the same slices, so a trial's bits do not depend on
     // the batch it arrives in
     w.nplanes = e->rb_slices;
+    w.item_slices = e->rb_slices;            // one work item walks all slices of its cell (one header for both)
     w.item_shift = RB_SITES_SHIFT;
     const size_t nsp = ns * (size_t)w.nplanes;
     CK(e->tw_int.reserve(2 * ns + nsp + 4), "cudaMalloc trial work");
@@ -1074,7 +1075,7 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
         }
         return MCPYB_OK;
     }
-    // batches: counting sort of the sites by cell, then one CTA per (cell, <= 128 sites, list slice)
+    // batches: counting sort of the sites by cell, then one CTA per (cell, <= RB_SITES sites)
     CK(e->tw_bins.reserve(2 * nbp), "cudaMalloc trial bins");
     {
         const size_t had = e->tw_hist.cap;
@@ -1147,7 +1148,7 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
           CK(cudaLaunchKernelEx(&cfg, trial_scatter_kernel, tb, w), "launch trial_scatter_kernel"); e->launches++; }
     }
     mark();
-    const long long est = (long long)max_items * w.nplanes;
+    const long long est = (long long)max_items * (w.nplanes / w.item_slices);
     {
         const int rb = (int)(est < e->num_sms * RB_MIN_BLOCKS ? est : e->num_sms * RB_MIN_BLOCKS);
         cudaLaunchConfig_t cfg = config(rb, RB_THREADS, 0);

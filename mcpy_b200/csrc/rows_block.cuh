@@ -1,4 +1,4 @@
-// K3 / K6, third generation: trial-move row sums, one CTA per (cell, group of <= 128 sites).
+// K3 / K6, third generation: trial-move row sums, one CTA per (cell, group of <= RB_SITES sites).
 //
 // The second-generation kernel (site_kernels.cuh: fp32 screen + per-lane FIFO + exact drain) was
 // bound by instruction issue and latency, not by a math pipe: 20 k warp instructions per 32 sites,
@@ -29,14 +29,18 @@
 #include "lj_kernels.cuh"
 #include "site_kernels.cuh"
 
-#define RB_WARPS 4
+// Two warps per CTA, twelve CTAs per SM (measured against 4 x 6: 48.8 -> 44.8 us): a cell's sites rarely fill four
+// warps, and a warp without sites holds registers through the whole loop of its CTA.
+#ifndef RB_WARPS
+#define RB_WARPS 2
+#define RB_SITES_SHIFT 6
+#define RB_CAND 256               // staged candidates per chunk
+#define RB_MIN_BLOCKS 12
+#endif
 #define RB_THREADS (32 * RB_WARPS)
 #define RB_SITES RB_THREADS       // sites per work item
-#define RB_SITES_SHIFT 7
-#define RB_CAND 512               // staged candidates per chunk
 #define RB_UNROLL 4
 #define RB_MAXPIECES 128
-#define RB_MIN_BLOCKS 6
 
 template <int N> struct IntC { static constexpr int value = N; };
 
@@ -276,7 +280,11 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, 
     pdl_wait();
     pdl_trigger();
     const int nq = w.nplanes;                     // slices of the candidate list, one work item each
-    const int nwork = w.totals[0] * nq;
+    // a work item covers item_slices consecutive slices of its cell's list (one header -- sites, bounding box, list
+    // head -- for all of them); every slice is still accumulated and stored on its own, so the bits of a row sum do
+    // not depend on how the slices are grouped into items
+    const int isl = w.item_slices, ngr = nq / isl;
+    const int nwork = w.totals[0] * ngr;
     // persistent CTAs: the first work item is the CTA's own index, the following ones come from a device
     // counter (zeroed by the scan kernel), claimed one item AHEAD so that the atomic's round trip hides
     // behind the current item.  The grid is sized by the SM count, not by the host's upper bound on the
@@ -289,7 +297,7 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, 
         const int wi = s_wi;
         if (wi >= nwork) break;
         if (tid == 0) next_wi = (int)gridDim.x + atomicAdd(&w.totals[1], 1);
-        const int item = wi / nq, slice = wi - item * nq;
+        const int item = wi / ngr, slice0 = (wi - item * ngr) * isl;
         const int2 it = w.item_tab[item];
         const int bin = it.x, group = it.y;
         const int r = bin / w.bin_stride, c = bin - r * w.bin_stride;
@@ -319,10 +327,22 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, 
         }
         double acc12 = 0.0, acc6 = 0.0;
         int cnt = 0;
+        auto store_row = [&](int slice) {
+            if (active) {
+                // row = 4 eps (sum c12 - sum c6) - e0 * pairs
+                const double row = fma(p.eps4, acc12 - acc6, -p.e0 * (double)cnt);
+                w.site_E[(size_t)s * nq + slice] = row;
+                w.site_cnt[(size_t)s * nq + slice] = cnt;
+            }
+        };
 
         if (!fast) {
-            if (active && slice == 0)
-                rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, acc12, acc6, cnt);
+            for (int slice = slice0; slice < slice0 + isl; ++slice) {
+                acc12 = 0.0; acc6 = 0.0; cnt = 0;
+                if (active && slice == 0)
+                    rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, acc12, acc6, cnt);
+                store_row(slice);
+            }
         } else {
             // ---- the cell's stencil: its expanded list if there is one, else the piece table (warp 0)
             const int2 head = x.head ? x.head[bin] : make_int2(-1, 0);
@@ -392,7 +412,9 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, 
             const float keep_r2 = keep_r * keep_r * 1.000001f;
             const int lo_hi = (int)(lo_bits >> 32), hi_hi = (int)(hi_bits >> 32);
 
-            // this work item's slice of the stencil's candidate list: a function of the cell alone
+            for (int slice = slice0; slice < slice0 + isl; ++slice) {
+            acc12 = 0.0; acc6 = 0.0; cnt = 0;
+            // slice of the stencil's candidate list: a function of the cell alone
             const int cfirst = (int)(((long long)total * slice) / nq), clast = (int)(((long long)total * (slice + 1)) / nq);
             int gi0 = cfirst;
             while (gi0 < clast) {
@@ -492,12 +514,8 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, 
                 }
                 __syncthreads();
             }
-        }
-        if (active) {
-            // row = 4 eps (sum c12 - sum c6) - e0 * pairs
-            const double row = fma(p.eps4, acc12 - acc6, -p.e0 * (double)cnt);
-            w.site_E[(size_t)s * nq + slice] = row;
-            w.site_cnt[(size_t)s * nq + slice] = cnt;
+            store_row(slice);
+            }
         }
         __syncthreads();                                          // the piece table and s_wi are rewritten next
     }

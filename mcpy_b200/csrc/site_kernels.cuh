@@ -380,7 +380,7 @@ lj_fold_planes_kernel(int total_atoms, int nplanes, const double* __restrict__ e
 //   1 trial_sites_kernel   one thread per trial: its sites' positions, bin = (replica, cell), rank in the bin
 //   2 trial_scan_kernel    one CTA: exclusive scans of the bin histogram -> bin_start, work items
 //   3 trial_scatter_kernel site records to their bin
-//   4 lj_trial_rows_block_kernel (rows_block.cuh)  one CTA per (bin, <= 128 sites, list slice): row sums
+//   4 lj_trial_rows_block_kernel (rows_block.cuh)  one CTA per (bin, <= 64 sites): row sums, slice by slice
 //   5 lj_trial_combine_kernel  one thread per trial: sum(new rows) - sum(old rows) + moved-set pairs
 // ---------------------------------------------------------------------------
 #define TRIAL_HIST_STRIDE 8
@@ -402,7 +402,8 @@ struct TrialWork {
     int* item_start;       // [nbins + 1]
     int* sorted;           // [nsites] site ids grouped by bin
     int nplanes;           // partial sums per site: stencil z-planes (warp kernel) or list slices (CTA kernel)
-    int item_shift;        // sites per work item = 1 << item_shift (5: warp items, 7: CTA items)
+    int item_slices;       // slices one work item of the CTA kernel covers (divides nplanes)
+    int item_shift;        // sites per work item = 1 << item_shift (5: warp items, RB_SITES_SHIFT: CTA items)
     double* site_E;        // [nsites][nplanes] partial row sums
     int* site_cnt;         // [nsites][nplanes] in-cutoff pairs
     int* totals;           // [0] = number of work items, [1] = work counter of the persistent row-sum CTAs
