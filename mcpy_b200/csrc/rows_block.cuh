@@ -39,7 +39,9 @@
 #endif
 #define RB_THREADS (32 * RB_WARPS)
 #define RB_SITES RB_THREADS       // sites per work item
+#ifndef RB_UNROLL
 #define RB_UNROLL 4
+#endif
 #define RB_MAXPIECES 128
 
 template <int N> struct IntC { static constexpr int value = N; };
@@ -413,108 +415,108 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, 
             const int lo_hi = (int)(lo_bits >> 32), hi_hi = (int)(hi_bits >> 32);
 
             for (int slice = slice0; slice < slice0 + isl; ++slice) {
-            acc12 = 0.0; acc6 = 0.0; cnt = 0;
-            // slice of the stencil's candidate list: a function of the cell alone
-            const int cfirst = (int)(((long long)total * slice) / nq), clast = (int)(((long long)total * (slice + 1)) / nq);
-            int gi0 = cfirst;
-            while (gi0 < clast) {
-                // ---- stage: test RB_THREADS candidates per round, keep the survivors in list order
-                int nst = 0;
-                while (gi0 < clast && nst + RB_THREADS <= RB_CAND) {
-                    const int gi = gi0 + tid;
-                    bool keep = false;
-                    double4 q = make_double4(0.0, 0.0, 0.0, 0.0);
-                    int2 info = make_int2(0, 0);
-                    if (gi < clast) {
-                        if (listed) { q = xq[gi]; info = xi[gi]; }
-                        else rp_stage_candidate(g, spos, sm.pc, npieces, gi, q, info);
-                        const float xf = __double2float_rn(q.x), yf = __double2float_rn(q.y), zf = __double2float_rn(q.z);
-                        const float ex = fmaxf(fmaxf(blo[0] - xf, xf - bhi[0]), 0.0f);
-                        const float ey = fmaxf(fmaxf(blo[1] - yf, yf - bhi[1]), 0.0f);
-                        const float ez = fmaxf(fmaxf(blo[2] - zf, zf - bhi[2]), 0.0f);
-                        keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= keep_r2;
+                acc12 = 0.0; acc6 = 0.0; cnt = 0;
+                // slice of the stencil's candidate list: a function of the cell alone
+                const int cfirst = (int)(((long long)total * slice) / nq), clast = (int)(((long long)total * (slice + 1)) / nq);
+                int gi0 = cfirst;
+                while (gi0 < clast) {
+                    // ---- stage: test RB_THREADS candidates per round, keep the survivors in list order
+                    int nst = 0;
+                    while (gi0 < clast && nst + RB_THREADS <= RB_CAND) {
+                        const int gi = gi0 + tid;
+                        bool keep = false;
+                        double4 q = make_double4(0.0, 0.0, 0.0, 0.0);
+                        int2 info = make_int2(0, 0);
+                        if (gi < clast) {
+                            if (listed) { q = xq[gi]; info = xi[gi]; }
+                            else rp_stage_candidate(g, spos, sm.pc, npieces, gi, q, info);
+                            const float xf = __double2float_rn(q.x), yf = __double2float_rn(q.y), zf = __double2float_rn(q.z);
+                            const float ex = fmaxf(fmaxf(blo[0] - xf, xf - bhi[0]), 0.0f);
+                            const float ey = fmaxf(fmaxf(blo[1] - yf, yf - bhi[1]), 0.0f);
+                            const float ez = fmaxf(fmaxf(blo[2] - zf, zf - bhi[2]), 0.0f);
+                            keep = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) <= keep_r2;
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                        if (lane == 0) sm.wcnt[wid] = __popc(bal);
+                        __syncthreads();
+                        int before = 0, all = 0;
+    #pragma unroll
+                        for (int ww = 0; ww < RB_WARPS; ++ww) {
+                            const int cw = sm.wcnt[ww];
+                            before += (ww < wid) ? cw : 0;
+                            all += cw;
+                        }
+                        if (keep) {
+                            const int slot = nst + before + __popc(bal & ((1u << lane) - 1u));
+                            sm.candd[slot] = q;
+                            sm.cinfo[slot] = info;
+                        }
+                        nst += all;
+                        gi0 += RB_THREADS;
+                        __syncthreads();                               // wcnt is rewritten next round
                     }
-                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                    if (lane == 0) sm.wcnt[wid] = __popc(bal);
+                    const int n = nst;
+                    if (warp_active) {
+                        // U candidates per trip, branch-free, so the U dependent FP64 chains interleave.  The
+                        // trip is handed to `rare` when some lane has a candidate whose high word of r2 falls
+                        // in the window [hi(lo_bits), hi(hi_bits)] (full compare, exact re-check) or belongs
+                        // to a multi-atom move (exclusion list).
+                        const unsigned amb_width = (unsigned)(hi_hi - lo_hi);
+                        auto rare = [&](int i, int U) {
+                            for (int u = 0; u < U; ++u) {
+                                const double4 q = sm.candd[i + u];
+                                const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
+                                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                                const long long rb = __double_as_longlong(r2);
+                                bool in = rb < lo_bits;
+                                if (!in && rb <= hi_bits)        // within rounding of the cutoff: the oracle's arithmetic decides
+                                    in = rp_exact_r2(g, spos, sm.cinfo[i + u], px, py, pz, wsite) <= p.rc2;
+                                const int j = __double2loint(q.w);
+                                in = in && (j != ex0) && (j != ex1);
+                                if (multi && in)
+                                    for (int e = ob + 2; e < oe; ++e) if (tb.old_idx[e] == j) in = false;
+                                const double rm = __hiloint2double(in ? __double2hiint(r2) : 0x7fe00000, __double2loint(r2));
+                                const double t = p.sigma2 * fast_rcp(rm);
+                                const double c6 = t * t * t;
+                                acc12 = fma(c6, c6, acc12);
+                                acc6 += c6;
+                                cnt += in ? 1 : 0;
+                            }
+                        };
+                        auto visit = [&](int i, auto U_) {
+                            constexpr int U = decltype(U_)::value;
+                            double r2[U];
+                            int jj[U], rh[U];
+                            unsigned amb = multi ? 0u : 0xffffffffu;   // min over the trip of (hi(r2) - lo_hi), unsigned
+    #pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const double4 q = sm.candd[i + u];    // uniform address: two broadcast LDS.128
+                                const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
+                                r2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
+                                rh[u] = __double2hiint(r2[u]);        // positive doubles order like their bits
+                                amb = min(amb, (unsigned)(rh[u] - lo_hi));
+                                jj[u] = __double2loint(q.w);
+                            }
+                            if (__any_sync(0xffffffffu, amb <= amb_width)) { rare(i, U); return; }
+    #pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const bool hit = rh[u] < lo_hi && jj[u] != ex0 && jj[u] != ex1;
+                                // a miss is evaluated at r2 ~ 9e307: its reciprocal flushes to zero, so c6 = 0
+                                const double rm = __hiloint2double(hit ? rh[u] : 0x7fe00000, __double2loint(r2[u]));
+                                const double t = p.sigma2 * fast_rcp(rm);
+                                const double c6 = t * t * t;
+                                acc12 = fma(c6, c6, acc12);
+                                acc6 += c6;
+                                if (hit) ++cnt;
+                            }
+                        };
+                        int i = 0;
+                        for (; i + RBU <= n; i += RBU) visit(i, IntC<RBU>());
+                        for (; i < n; ++i) visit(i, IntC<1>());
+                    }
                     __syncthreads();
-                    int before = 0, all = 0;
-#pragma unroll
-                    for (int ww = 0; ww < RB_WARPS; ++ww) {
-                        const int cw = sm.wcnt[ww];
-                        before += (ww < wid) ? cw : 0;
-                        all += cw;
-                    }
-                    if (keep) {
-                        const int slot = nst + before + __popc(bal & ((1u << lane) - 1u));
-                        sm.candd[slot] = q;
-                        sm.cinfo[slot] = info;
-                    }
-                    nst += all;
-                    gi0 += RB_THREADS;
-                    __syncthreads();                               // wcnt is rewritten next round
                 }
-                const int n = nst;
-                if (warp_active) {
-                    // U candidates per trip, branch-free, so the U dependent FP64 chains interleave.  The
-                    // trip is handed to `rare` when some lane has a candidate whose high word of r2 falls
-                    // in the window [hi(lo_bits), hi(hi_bits)] (full compare, exact re-check) or belongs
-                    // to a multi-atom move (exclusion list).
-                    const unsigned amb_width = (unsigned)(hi_hi - lo_hi);
-                    auto rare = [&](int i, int U) {
-                        for (int u = 0; u < U; ++u) {
-                            const double4 q = sm.candd[i + u];
-                            const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
-                            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                            const long long rb = __double_as_longlong(r2);
-                            bool in = rb < lo_bits;
-                            if (!in && rb <= hi_bits)        // within rounding of the cutoff: the oracle's arithmetic decides
-                                in = rp_exact_r2(g, spos, sm.cinfo[i + u], px, py, pz, wsite) <= p.rc2;
-                            const int j = __double2loint(q.w);
-                            in = in && (j != ex0) && (j != ex1);
-                            if (multi && in)
-                                for (int e = ob + 2; e < oe; ++e) if (tb.old_idx[e] == j) in = false;
-                            const double rm = __hiloint2double(in ? __double2hiint(r2) : 0x7fe00000, __double2loint(r2));
-                            const double t = p.sigma2 * fast_rcp(rm);
-                            const double c6 = t * t * t;
-                            acc12 = fma(c6, c6, acc12);
-                            acc6 += c6;
-                            cnt += in ? 1 : 0;
-                        }
-                    };
-                    auto visit = [&](int i, auto U_) {
-                        constexpr int U = decltype(U_)::value;
-                        double r2[U];
-                        int jj[U], rh[U];
-                        unsigned amb = multi ? 0u : 0xffffffffu;   // min over the trip of (hi(r2) - lo_hi), unsigned
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            const double4 q = sm.candd[i + u];    // uniform address: two broadcast LDS.128
-                            const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
-                            r2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
-                            rh[u] = __double2hiint(r2[u]);        // positive doubles order like their bits
-                            amb = min(amb, (unsigned)(rh[u] - lo_hi));
-                            jj[u] = __double2loint(q.w);
-                        }
-                        if (__any_sync(0xffffffffu, amb <= amb_width)) { rare(i, U); return; }
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            const bool hit = rh[u] < lo_hi && jj[u] != ex0 && jj[u] != ex1;
-                            // a miss is evaluated at r2 ~ 9e307: its reciprocal flushes to zero, so c6 = 0
-                            const double rm = __hiloint2double(hit ? rh[u] : 0x7fe00000, __double2loint(r2[u]));
-                            const double t = p.sigma2 * fast_rcp(rm);
-                            const double c6 = t * t * t;
-                            acc12 = fma(c6, c6, acc12);
-                            acc6 += c6;
-                            if (hit) ++cnt;
-                        }
-                    };
-                    int i = 0;
-                    for (; i + RBU <= n; i += RBU) visit(i, IntC<RBU>());
-                    for (; i < n; ++i) visit(i, IntC<1>());
-                }
-                __syncthreads();
-            }
-            store_row(slice);
+                store_row(slice);
             }
         }
         __syncthreads();                                          // the piece table and s_wi are rewritten next
