@@ -16,10 +16,14 @@
 //     candidate within a few ulps of the cutoff.  Sites outside the primary periodic cell are wrapped
 //     first and get a wider re-check band, so they cost nothing extra.
 //
-// The staged-candidate list of a cell (z-plane, row, main piece, wrapped piece, cell-sorted order) can
-// be cut into w.nplanes equal slices, one work item each.  A site's row sum is the fixed-order fold over
-// the slices of sequentially accumulated sums -- a function of the site and the configuration only,
-// independent of the lane, the warp and the batch the site arrives in.
+// The staged-candidate list of a cell (z-plane, row, main piece, wrapped piece, cell-sorted order) is cut
+// into w.nplanes equal slices; a work item walks w.item_slices of them one after the other behind one
+// header.  A site's row sum is the fixed-order fold over the slices of sequentially accumulated sums -- a
+// function of the site and the configuration only, independent of the lane, the warp, the batch the site
+// arrives in and of how slices are grouped into work items.
+//
+// From the second batch against a resident configuration the stencil is not rebuilt from the cell list
+// but read from the per-configuration StencilLists below (one ordered, coalesced run per cell).
 //
 // Boxes thinner than the stencil along x, or stencils with more than RB_MAXPIECES pieces, take the
 // generic per-lane traversal (tiny systems).
