@@ -73,9 +73,10 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-// A few helper threads for the large host-side copies of the batched calls (user arrays -> pinned
-// staging and back): one core moves ~20 GB/s, which made the staging copy the longest single item of an
-// end-to-end trial call.  Workers sleep on a condition variable between calls.
+// A few helper threads for the large host-side passes of the batched calls (user arrays -> pinned staging
+// and back; the row-by-row comparison of 64 incoming configurations with their resident bases): one core
+// moves ~20 GB/s, which made such a pass the longest single item of a call.  Workers sleep on a condition
+// variable between calls.
 class CopyPool {
 public:
     explicit CopyPool(int nworkers) {
@@ -105,8 +106,25 @@ public:
         memcpy(dst, src, each);
         while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
     }
+    // fn(ctx, i) for i in [0, n), interleaved over the workers and the caller
+    void parallel_for(int n, void (*fn)(void*, int), void* ctx) {
+        int parts = (int)threads_.size() + 1;
+        if (parts > n) parts = n;
+        if (parts <= 1) { for (int i = 0; i < n; ++i) fn(ctx, i); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            for (int p = 1; p < parts; ++p) jobs_.push_back({nullptr, nullptr, 0, fn, ctx, p, parts, n});
+            pending_.fetch_add(parts - 1);
+        }
+        cv_.notify_all();
+        for (int i = 0; i < n; i += parts) fn(ctx, i);
+        while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    }
 private:
-    struct Job { unsigned char* dst; const unsigned char* src; size_t n; };
+    struct Job {
+        unsigned char* dst; const unsigned char* src; size_t n;
+        void (*fn)(void*, int) = nullptr; void* ctx = nullptr; int first = 0, step = 1, count = 0;
+    };
     void loop() {
         for (;;) {
             Job j;
@@ -117,7 +135,8 @@ private:
                 j = jobs_.back();
                 jobs_.pop_back();
             }
-            memcpy(j.dst, j.src, j.n);
+            if (j.fn) { for (int i = j.first; i < j.count; i += j.step) j.fn(j.ctx, i); }
+            else memcpy(j.dst, j.src, j.n);
             pending_.fetch_sub(1, std::memory_order_release);
         }
     }
@@ -1562,23 +1581,50 @@ static int tracked_energies_core(mcpyb_engine* e, int R, const double* const* po
     std::vector<double> t_new_pos;
     std::vector<int> slot_of(R, -1), trial_of(R, -1);
     const bool have_numbers = num_of != nullptr;
-    if (incremental) {
+    // Every configuration against the base in its OWN slot first -- the usual case, independent per
+    // configuration and memory-bound on the host (64 x 2 000 atoms: 6 MB touched), so spread over the helper
+    // threads; the ones that do not match there are then tried against the other bases one by one.
+    struct Own {
         int32_t old_idx[kLimit];
         int new_row[kLimit];
+        int n_old = 0, n_new = 0;
+        bool ok = false;
+    };
+    std::vector<Own> own(incremental ? (size_t)R : 0);
+    auto try_slot = [&](int r, int q, int32_t* old_idx, int* new_row, int& n_old, int& n_new) -> bool {
+        if (q >= Rb) return false;
+        const int n = (int)n_of[r];
+        const int nB = (int)(e->trkb_off[q + 1] - e->trkb_off[q]);
+        if (abs(nB - n) > kLimit) return false;
+        if (memcmp(&e->trkb_cell[9 * (size_t)q], cells + 9 * (size_t)r, 9 * sizeof(double)) != 0 ||
+            memcmp(&e->trkb_pbc[3 * (size_t)q], pbc + 3 * (size_t)r, 3) != 0) return false;
+        return align_rows<ZT>(&e->trkb_pos[3 * (size_t)e->trkb_off[q]], &e->trkb_Z[(size_t)e->trkb_off[q]], nB,
+                              pos_of[r], have_numbers ? num_of[r] : nullptr, n, kLimit, old_idx, new_row, n_old, n_new);
+    };
+    if (incremental) {
+        struct Ctx { decltype(try_slot)* f; std::vector<Own>* own; } ctx{&try_slot, &own};
+        auto body = [](void* c, int r) {
+            Ctx& x = *(Ctx*)c;
+            Own& o = (*x.own)[r];
+            o.ok = (*x.f)(r, r, o.old_idx, o.new_row, o.n_old, o.n_new);
+        };
+        size_t touched = 0;
+        for (int r = 0; r < R; ++r) touched += (size_t)n_of[r] * 48;
+        CopyPool* pool = copy_pool_for(e, touched);
+        if (pool) pool->parallel_for(R, body, &ctx); else for (int r = 0; r < R; ++r) body(&ctx, r);
+    }
+    if (incremental) {
+        int32_t old_idx_buf[kLimit];
+        int new_row_buf[kLimit];
         for (int r = 0; r < R && incremental; ++r) {
-            const int n = (int)n_of[r];
             const double* P = pos_of[r];
             const ZT* PZ = have_numbers ? num_of[r] : nullptr;
-            int n_old = 0, n_new = 0, found = -1;
-            for (int probe = 0; probe <= Rb && found < 0; ++probe) {
-                const int q = probe == 0 ? r : probe - 1;                 // own slot first
-                if (q >= Rb || (probe > 0 && q == r)) continue;
-                const int nB = (int)(e->trkb_off[q + 1] - e->trkb_off[q]);
-                if (abs(nB - n) > kLimit) continue;
-                if (memcmp(&e->trkb_cell[9 * (size_t)q], cells + 9 * (size_t)r, 9 * sizeof(double)) != 0 ||
-                    memcmp(&e->trkb_pbc[3 * (size_t)q], pbc + 3 * (size_t)r, 3) != 0) continue;
-                if (align_rows<ZT>(&e->trkb_pos[3 * (size_t)e->trkb_off[q]], &e->trkb_Z[(size_t)e->trkb_off[q]], nB,
-                                   P, PZ, n, kLimit, old_idx, new_row, n_old, n_new)) found = q;
+            int n_old = own[r].n_old, n_new = own[r].n_new, found = own[r].ok ? r : -1;
+            const int32_t* old_idx = own[r].old_idx;
+            const int* new_row = own[r].new_row;
+            for (int q = 0; q < Rb && found < 0; ++q) {                   // another slot's base (replica exchange)
+                if (q == r) continue;
+                if (try_slot(r, q, old_idx_buf, new_row_buf, n_old, n_new)) { found = q; old_idx = old_idx_buf; new_row = new_row_buf; }
             }
             if (found < 0) { incremental = false; break; }
             slot_of[r] = found;
