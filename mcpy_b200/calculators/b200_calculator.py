@@ -116,8 +116,12 @@ class _B200Core:
             # Atoms is converted on its own), so convert once per batch, not once per replica
             pos_list = [a.positions for a in chunk]
             num_list = [a.numbers for a in chunk]
-            cells = np.array([np.asarray(a.cell, dtype=np.float64).reshape(9) for a in chunk])
-            pbcs = np.array([np.asarray(a.pbc, dtype=bool).reshape(3) for a in chunk])
+            cells = np.empty((len(chunk), 3, 3))
+            pbcs = np.empty((len(chunk), 3), dtype=bool)
+            for r, a in enumerate(chunk):
+                cells[r] = a.cell
+                pbcs[r] = a.pbc
+            cells = cells.reshape(len(chunk), 9)
             if self.incremental and start == 0 and stop == len(atoms_list):
                 # the whole batch in one piece: resident bases + one batched delta launch
                 en, paths = self.engine.tracked_energies(pos_list, num_list, cells, pbcs)

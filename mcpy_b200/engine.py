@@ -13,6 +13,8 @@ import numpy as np
 from . import _lib
 from ._lib import EngineError, as_f64, as_i32, as_i64, as_u8, ptr
 
+_F64, _I32, _I64 = np.dtype(np.float64), np.dtype(np.int32), np.dtype(np.int64)
+
 _ERR_VALUE = (-2,)            # MCPYB_ERR_ARG -> ValueError, like the reference's bad-argument errors
 
 
@@ -190,26 +192,34 @@ class Engine:
         """(position pointers, number pointers, numbers-are-int64 flag, rows per configuration) when every array can
         be read in place, else None (the caller concatenates)."""
         R = len(positions_list)
-        pp = np.empty(R, dtype=np.uintp)
-        zp = np.empty(R, dtype=np.uintp)
-        n_of = np.empty(R, dtype=np.int64)
-        f64, zdt = np.dtype(np.float64), None
+        pp, zp, n_of = [0] * R, [0] * R, [0] * R
+        nd, f64, i32, i64 = np.ndarray, _F64, _I32, _I64
+        addr, cbuf = C.addressof, C.c_char.from_buffer       # 0.45 us an address; .ctypes.data costs 1 us
+        zdt = None
         for r in range(R):
             p, z = positions_list[r], numbers_list[r]
-            if not (isinstance(p, np.ndarray) and isinstance(z, np.ndarray)) or p.dtype != f64 or p.ndim != 2 \
-                    or p.shape[1] != 3 or not p.flags.c_contiguous or not z.flags.c_contiguous \
-                    or z.shape != (p.shape[0],):
+            if type(p) is not nd or type(z) is not nd or p.dtype is not f64 or p.ndim != 2:
+                return None
+            n = p.shape[0]
+            if p.shape[1] != 3 or z.shape != (n,) or not p.flags.c_contiguous or not z.flags.c_contiguous:
                 return None
             if zdt is None:
                 zdt = z.dtype
-                if zdt not in (np.dtype(np.int32), np.dtype(np.int64)):
+                if zdt is not i32 and zdt is not i64:
                     return None
-            elif z.dtype != zdt:
+            elif z.dtype is not zdt:
                 return None
-            pp[r] = p.__array_interface__['data'][0]
-            zp[r] = z.__array_interface__['data'][0]
-            n_of[r] = p.shape[0]
-        return pp, zp, int(zdt == np.dtype(np.int64)), n_of
+            try:
+                pp[r] = addr(cbuf(p)) if n else 0
+                zp[r] = addr(cbuf(z)) if n else 0
+            except (TypeError, ValueError):                    # read-only array: no writable buffer export
+                pp[r] = p.__array_interface__['data'][0]
+                zp[r] = z.__array_interface__['data'][0]
+            n_of[r] = n
+        pp = np.array(pp, dtype=np.uintp)
+        zp = np.array(zp, dtype=np.uintp)
+        n_of = np.array(n_of, dtype=np.int64)
+        return pp, zp, int(zdt is _I64), n_of
 
     def potential_energy(self, positions, numbers, cell, pbc) -> float:
         """Single configuration, minimal marshalling (the per-trial drop-in call)."""
