@@ -15,6 +15,16 @@ from ._lib import EngineError, as_f64, as_i32, as_i64, as_u8, ptr
 
 _F64, _I32, _I64 = np.dtype(np.float64), np.dtype(np.int32), np.dtype(np.int64)
 
+
+def _address(a):
+    """Address of a C-contiguous numpy array's data (None for an empty one)."""
+    if a.size == 0:
+        return None
+    try:
+        return C.addressof(C.c_char.from_buffer(a))
+    except (TypeError, ValueError):                            # read-only array: no writable buffer export
+        return a.ctypes.data
+
 _ERR_VALUE = (-2,)            # MCPYB_ERR_ARG -> ValueError, like the reference's bad-argument errors
 
 
@@ -35,6 +45,8 @@ class Engine:
         self._off1 = np.zeros(2, dtype=np.int64)      # scratch of the single-configuration fast path
         self._e1 = np.zeros(1, dtype=np.float64)
         self._path = C.c_int(0)
+        self._e1_ptr = self._e1.ctypes.data
+        self._path_ref = C.byref(self._path)
 
     # -- plumbing ------------------------------------------------------------
     def close(self):
@@ -251,13 +263,14 @@ class Engine:
         n = pos.shape[0]
         if pos.size != 3 * n or num.size != n or cell.size != 9 or pbc.size != 3:
             raise ValueError('positions (n,3), numbers (n,), cell (3,3), pbc (3,) expected')
-        rc = self._lib.mcpyb_tracked_energy_host(self._h, pos.ctypes.data, num.ctypes.data, n,
-                                                 cell.ctypes.data, pbc.ctypes.data, self._e1.ctypes.data,
-                                                 C.byref(self._path))
+        # this call runs once per Monte-Carlo trial: addresses through the buffer protocol (0.45 us each, .ctypes.data
+        # costs 1 us) and the two output pointers kept from construction
+        rc = self._lib.mcpyb_tracked_energy_host(self._h, _address(pos), _address(num), n, _address(cell),
+                                                 _address(pbc), self._e1_ptr, self._path_ref)
         if rc != 0:
             self._check(rc)
         self._R, self._ntot = 1, n
-        return float(self._e1[0]), int(self._path.value)
+        return float(self._e1[0]), self._path.value
 
     def forces(self) -> np.ndarray:
         """Forces of the resident batch, ``(sum N, 3)`` (ASE's ``results['forces']``)."""
