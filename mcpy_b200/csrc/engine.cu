@@ -1052,6 +1052,35 @@ static int prepare_rows_work(mcpyb_engine* e, int nsites, int n_old_total, int n
     return MCPYB_OK;
 }
 
+// The per-configuration stencil lists of the resident batch (rows_block.cuh), built when a SECOND trial launch
+// meets the same resident configuration (one launch per upload does not amortise the 15 us of
+// expand_stencils_kernel).  *xl is left zeroed -- every work item stages from the cell list -- until they exist.
+// `few_sites`: the single-launch kernels of the one-call-per-trial chain, which re-base every few dozen calls:
+// worth it for the configurations such a chain runs on, not for a 100 000-atom batch.
+static int stencil_lists(mcpyb_engine* e, bool few_sites, StencilLists* xl) {
+    memset(xl, 0, sizeof *xl);
+    if (!e->use_expand || e->pot_kind != POT_LJ || !e->have_batch || e->total_atoms <= 0) return MCPYB_OK;
+    if (few_sites && e->total_atoms > 20000) return MCPYB_OK;
+    if (!e->exp_valid && ++e->exp_batches < 2) return MCPYB_OK;
+    const int nbins = e->R * e->max_cells;
+    long long cap = (long long)e->total_atoms * 128;              // (2m+1)^3 = 125 cells see each atom at m = 2
+    if (cap > (32LL << 20)) cap = 32LL << 20;                      // 1.3 GB; cells beyond it are staged on the fly
+    CK(e->exp_q.reserve((size_t)cap), "cudaMalloc stencil lists");
+    CK(e->exp_info.reserve((size_t)cap), "cudaMalloc stencil lists");
+    CK(e->exp_head.reserve((size_t)nbins), "cudaMalloc stencil lists");
+    CK(e->exp_cursor.reserve(1), "cudaMalloc stencil lists");
+    xl->q = e->exp_q.p; xl->info = e->exp_info.p; xl->head = e->exp_head.p; xl->cursor = e->exp_cursor.p; xl->cap = cap;
+    if (!e->exp_valid) {
+        CK(cudaMemsetAsync(e->exp_cursor.p, 0, sizeof(unsigned long long), e->stream), "memset stencil cursor");
+        int blocks_x = (nbins + EX_WARPS - 1) / EX_WARPS;
+        if (blocks_x > e->num_sms * 8) blocks_x = e->num_sms * 8;
+        expand_stencils_kernel<<<blocks_x, 32 * EX_WARPS, 0, e->stream>>>(e->view(), *xl, nbins, e->max_cells);
+        LAUNCH_CHECK("expand_stencils_kernel");
+        e->exp_valid = true;
+    }
+    return MCPYB_OK;
+}
+
 static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int32_t* d_old_off,
                          const int32_t* d_old_idx, const int32_t* d_new_off, const double* d_new_pos,
                          const int32_t* d_new_Z, int n_old_total, int n_new_total,
@@ -1084,8 +1113,11 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     if (nsites <= RS_MAX_SITES) {
         // a handful of sites (the one-call-per-trial chain): one launch does everything
         if (nsites > 0) {
+            StencilLists xs;
+            int rc = stencil_lists(e, true, &xs);
+            if (rc != MCPYB_OK) return rc;
             lj_trial_small_kernel<<<nsites, RS_THREADS, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs,
-                                                                         (int*)(e->tw_err.p + 2));
+                                                                         (int*)(e->tw_err.p + 2), xs);
             LAUNCH_CHECK("lj_trial_small_kernel");
         } else {
             lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
@@ -1135,25 +1167,9 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     };
     const BatchView bv = e->view();
     StencilLists xl;
-    memset(&xl, 0, sizeof xl);
-    if (e->use_expand && (e->exp_valid || ++e->exp_batches >= 2)) {
-        // every cell's stencil as one ordered run of candidate records, once per resident configuration
-        long long cap = (long long)e->total_atoms * 128;          // (2m+1)^3 = 125 cells see each atom at m = 2
-        if (cap > (32LL << 20)) cap = 32LL << 20;                  // 1.3 GB; cells beyond it are staged on the fly
-        if (cap < 1) cap = 1;
-        CK(e->exp_q.reserve((size_t)cap), "cudaMalloc stencil lists");
-        CK(e->exp_info.reserve((size_t)cap), "cudaMalloc stencil lists");
-        CK(e->exp_head.reserve((size_t)w.nbins), "cudaMalloc stencil lists");
-        CK(e->exp_cursor.reserve(1), "cudaMalloc stencil lists");
-        xl.q = e->exp_q.p; xl.info = e->exp_info.p; xl.head = e->exp_head.p; xl.cursor = e->exp_cursor.p; xl.cap = cap;
-        if (!e->exp_valid) {
-            CK(cudaMemsetAsync(e->exp_cursor.p, 0, sizeof(unsigned long long), e->stream), "memset stencil cursor");
-            int blocks_x = (w.nbins + EX_WARPS - 1) / EX_WARPS;
-            if (blocks_x > e->num_sms * 8) blocks_x = e->num_sms * 8;
-            expand_stencils_kernel<<<blocks_x, 32 * EX_WARPS, 0, e->stream>>>(bv, xl, w.nbins, w.bin_stride);
-            LAUNCH_CHECK("expand_stencils_kernel");
-            e->exp_valid = true;
-        }
+    {
+        int rc = stencil_lists(e, false, &xl);
+        if (rc != MCPYB_OK) return rc;
     }
     mark();
     {
@@ -1453,8 +1469,11 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
             volatile unsigned int* h_flag = (volatile unsigned int*)(e->trial_out_pin.p + 16);
             const unsigned int seq = ++e->tiny_seq;
             *h_flag = seq - 1;                        // whatever the (possibly fresh) pinned block held
+            StencilLists xs;
+            rc = stencil_lists(e, true, &xs);
+            if (rc != MCPYB_OK) return rc;
             lj_trial_tiny_kernel<<<n_old + n_new, RS_THREADS, 0, e->stream>>>(e->view(), tt, w, e->lj, h_dE,
-                                                                             (int*)(e->tw_err.p + 2), h_flag, seq);
+                                                                             (int*)(e->tw_err.p + 2), xs, h_flag, seq);
             LAUNCH_CHECK("lj_trial_tiny_kernel");
             if (!wait_flag(h_flag, seq)) CK(cudaStreamSynchronize(e->stream), "sync tiny trial");
             if (*h_status != ~0ULL) return e->fail(MCPYB_ERR_ARG, "tracked trial rejected on the device (status %llu)", *h_status);

@@ -553,7 +553,7 @@ struct RowsSmallSmem {
 __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const BatchView& b, const TrialBatch& tb,
                                                     const TrialWork& w, const LJParams& p,
                                                     double* __restrict__ dE, int* __restrict__ npairs,
-                                                    int* __restrict__ done_counter,
+                                                    int* __restrict__ done_counter, const StencilLists& x,
                                                     volatile unsigned int* done_flag = nullptr, unsigned int seq = 0) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int s = blockIdx.x;                          // site: [0, n_old) old, then new
@@ -587,9 +587,18 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
         if (!fast) {
             if (tid == 0) rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, acc12[0], acc6[0], cnt[0]);
         } else {
-            if (wid == 0) rb_build_pieces(sm.pc, g, cstart, c[0], c[1], c[2], lane);
-            __syncthreads();
-            const int total = sm.pc.total, npieces = 2 * nrows;
+            // the cell's stencil: its per-configuration list when there is one (one coalesced read, no piece
+            // table, no search), else built here from the cell list
+            const int cell_bin = r * w.bin_stride + (c[2] * g.ncell[1] + c[1]) * g.ncell[0] + c[0];
+            const int2 head = x.head ? x.head[cell_bin] : make_int2(-1, 0);
+            const bool listed = head.x >= 0;
+            if (!listed) {
+                if (wid == 0) rb_build_pieces(sm.pc, g, cstart, c[0], c[1], c[2], lane);
+                __syncthreads();
+            }
+            const int total = listed ? head.y : sm.pc.total, npieces = 2 * nrows;
+            const double4* xq = x.q + (listed ? head.x : 0);
+            const int2* xi = x.info + (listed ? head.x : 0);
             // per-site constants, as in lj_trial_rows_block_kernel
             double qx = px, qy = py, qz = pz, band = 16.0;
             if (wsite != pack_wraps(0, 0, 0)) rb_wrap_site(g, p.rc, px, py, pz, wsite, qx, qy, qz, band);
@@ -599,28 +608,16 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
                 const int n = min(RS_CAND, total - cbase);
                 for (int i = tid; i < n; i += RS_THREADS) {
                     const int gi = cbase + i;
-                    int lo = 0, hi = npieces;
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (sm.pc.pstart[mid] <= gi) lo = mid; else hi = mid;
-                    }
-                    const int k = sm.pc.pbeg[lo] + (gi - sm.pc.pstart[lo]);
-                    double4 q = spos[k];
-                    double ax = sm.pc.pshift[lo][0], ay = sm.pc.pshift[lo][1], az = sm.pc.pshift[lo][2];
-                    const long long tag = tag_of(q);
-                    const int wj = tag_wraps(tag);
-                    if (wj != pack_wraps(0, 0, 0)) {
-                        int sx, sy, sz, jx, jy, jz;
-                        unpack_wraps(sm.pc.pS[lo], sx, sy, sz);
-                        unpack_wraps(wj, jx, jy, jz);
-                        shift_vec(g, sx - jx, sy - jy, sz - jz, ax, ay, az);
-                    }
-                    const double dx = __dadd_rn(q.x, ax) - qx, dy = __dadd_rn(q.y, ay) - qy, dz = __dadd_rn(q.z, az) - qz;
+                    double4 q;
+                    int2 info = make_int2(0, 0);
+                    if (listed) q = xq[gi];
+                    else rp_stage_candidate(g, spos, sm.pc, npieces, gi, q, info);
+                    const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
                     const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
                     const long long rb = __double_as_longlong(r2);
                     bool in = rb < lo_bits;
-                    if (!in && rb <= hi_bits) in = rb_exact_r2(g, spos, sm.pc, k | (lo << 24), px, py, pz, wsite) <= p.rc2;
-                    const int j = tag_index(tag);
+                    if (!in && rb <= hi_bits) in = rp_exact_r2(g, spos, listed ? xi[gi] : info, px, py, pz, wsite) <= p.rc2;
+                    const int j = __double2loint(q.w);
                     for (int e = ob; e < oe; ++e) if (tb.old_idx[e] == j) in = false;
                     double c6 = 0.0;
                     if (in) { const double tt = p.sigma2 * fast_rcp(r2); c6 = tt * tt * tt; }
@@ -692,9 +689,9 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
 
 __global__ void __launch_bounds__(RS_THREADS)
 lj_trial_small_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p,
-                      double* __restrict__ dE, int* __restrict__ npairs, int* __restrict__ done_counter) {
+                      double* __restrict__ dE, int* __restrict__ npairs, int* __restrict__ done_counter, StencilLists x) {
     __shared__ RowsSmallSmem sm;
-    lj_trial_small_body(sm, b, tb, w, p, dE, npairs, done_counter);
+    lj_trial_small_body(sm, b, tb, w, p, dE, npairs, done_counter, x);
 }
 
 // One trial whose description travels in the kernel's parameter space and whose result is written
@@ -709,11 +706,11 @@ struct TinyTrial {
 
 __global__ void __launch_bounds__(RS_THREADS)
 lj_trial_tiny_kernel(BatchView b, const __grid_constant__ TinyTrial tt, TrialWork w, LJParams p,
-                     double* __restrict__ dE_host, int* __restrict__ done_counter,
+                     double* __restrict__ dE_host, int* __restrict__ done_counter, StencilLists x,
                      volatile unsigned int* done_flag, unsigned int seq) {
     __shared__ RowsSmallSmem sm;
     TrialBatch tb;
     tb.T = 1; tb.rep = nullptr; tb.old_off = tt.old_off; tb.old_idx = tt.old_idx;
     tb.new_off = tt.new_off; tb.new_pos = tt.new_pos; tb.new_Z = nullptr;
-    lj_trial_small_body(sm, b, tb, w, p, dE_host, nullptr, done_counter, done_flag, seq);
+    lj_trial_small_body(sm, b, tb, w, p, dE_host, nullptr, done_counter, x, done_flag, seq);
 }
