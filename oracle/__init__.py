@@ -21,14 +21,17 @@ published algorithm of those classes and are pinned by
   equal to ASE within 1e-9 (``:190-203``);
 * the LAMMPS two-body probe values (``benchmark/lammps_gcmc_parity.py:285-324``);
 * the EMT known answers ``E_EMT(O2)/2 = +0.46 eV`` (``docs/make_figures.py:334``)
-  and ``E_EMT(N2, d=1.10 A) = 0.440343572 eV`` (ASE's own tutorial value);
+  and the energies / optimiser fmax values ASE's documentation prints for its EMT
+  tutorials (N2 on Cu(111), H2O, Au on Al(100), bulk Cu, the Ag equation of state),
+  reproduced to the last printed digit -- see ``tests/test_oracle_emt.py``;
 * for the free volume, ``scipy.spatial.cKDTree`` -- the very library the
   reference calls (``mcpy/cell/spherical_cell.py:130-138``) -- is installed, so
   :mod:`oracle.free_volume` runs the reference's algorithm verbatim in spirit
   and is additionally pinned by ``tests/test_audit_regressions.py:363-372``.
 
-Parity status: LJ and free volume are pinned by reference golden values; the
-EMT energy is pinned only by the two prose values above and the neighbour list
-has no reference test at all ("parity unpinned" for those two beyond the
-invariants in ``tests/test_oracle_*.py``).  See DESIGN.md section 3.
+Parity status: LJ and free volume are pinned by reference golden values; EMT
+energies and forces by ASE's documented tutorial outputs (7 species, 6-9 digits)
+plus the algorithm's identities for the remaining metals; the neighbour list has
+no reference test at all -- it is pinned through the energies above (a missed or
+doubled pair changes them) and its brute-force definition.  See DESIGN.md section 3.
 """
