@@ -1,97 +1,103 @@
 """Replica exchange sharded over GPUs: one process per GPU, replicas block-partitioned.
 
-Multi-GPU counterpart of ``BatchedReplicaExchange``
-(``mcpy/ensembles/batched_replica_exchange.py``), SURVEY.md section 8e:
+``ShardedReplicaExchange`` IS the reference's ``BatchedReplicaExchange``
+(``mcpy/ensembles/batched_replica_exchange.py``) run on the local shard of the ladder: it
+subclasses it, builds only the replicas of ``shard_range(R, rank, world)`` and inherits ``run``,
+``_rebatch_initial_energies``, ``_batched_gcmc_step``, ``_batched_single_move`` (ONE batched
+``calculator.get_potential_energies`` call per sub-move, ``:235-302``) and the per-replica /
+per-run output unchanged.  There is no data-path collective.  Only the exchange step is
+overridden:
 
-* rank g owns the replicas ``shard_range(R, g, G)`` and runs their trial moves locally --
-  propose on the host, ONE batched ``calculator.get_potential_energies`` call per
-  sub-move (``_batched_single_move``, reference ``:235-302``), per-replica acceptance;
-  there is no data-path collective;
-* every ``exchange_interval`` steps the ranks ``all_gather`` one fixed-size fp64 record
-  per replica ``[E_old, beta, N_s.., mu_s.., Lambda_s..]`` (a few hundred bytes over
+* every ``exchange_interval`` steps the ranks ``all_gather`` one fixed-size fp64 record per
+  replica ``[E_old, beta, N_s.., mu_s.., Lambda_s.., has_mu_s..]`` (a few hundred bytes over
   NCCL / NVLink; latency-bound) -- the only collective;
-* every rank then evaluates the SAME deterministic pairing and Metropolis test with a
-  generator seeded identically on all ranks (the reference's ``self.rng``, ``:110,311,370``),
-  using the reference's exponent (``_accept_swap`` ``:320-370``), so all ranks agree
-  without further communication;
-* an accepted pair that straddles two ranks ships its configuration point-to-point
-  (positions, numbers, extra per-atom arrays, E_old, n_atoms); contiguous sharding makes
-  only the G-1 boundary pairs cross-rank.  Like the reference (``_swap_states``
-  ``:401-410``) temperatures / mu stay with the slot and both slots refresh their free
-  volume after a swap.
+* every rank then evaluates the SAME pairing and Metropolis test with the reference's
+  master-seeded generator (``self.rng``, ``:110,311,370``: identical on every rank) and the
+  reference's exponent (``_accept_swap`` ``:320-370``), so all ranks agree without further
+  communication;
+* an accepted pair that straddles two ranks ships its state point-to-point -- the ``Atoms``
+  object as a whole (positions, numbers, per-atom arrays, cell, pbc, constraints, info), ``E_old``
+  and ``n_atoms``, what ``_swap_states`` (``:401-410``) exchanges and what the MPI driver's
+  ``sendrecv`` carries (``replica_exchange.py:188-192``).  Contiguous sharding makes only the
+  G-1 boundary pairs cross-rank.  Temperatures / mu stay with the slot and both slots refresh
+  their free volume after a swap.
 
-Replica objects are the reference's ``GrandCanonicalEnsemble`` (or anything with the
-same attributes); they are built by ``gcmc_factory(T=..., rank=i)`` / ``(mu=..., rank=i)``
-exactly as for the reference class, but only for the local indices.
+Per-rank files: ``outfile`` and ``global_minimum_file`` get a ``.rank<g>`` suffix when
+``world_size > 1`` (each rank logs its own replicas; indices in those files are local).
 """
 from __future__ import annotations
 
 import logging
+import pickle
+import time
 from typing import Callable, Dict, List, Optional
 
 import numpy as np
+
+try:
+    from mcpy.ensembles.batched_replica_exchange import BatchedReplicaExchange
+except ImportError as exc:                                   # pragma: no cover
+    raise ImportError('mcpy_b200.ensembles.ShardedReplicaExchange extends BatchedReplicaExchange of '
+                      'farrisric/mcpy: the `mcpy` package (and its dependency `ase`) must be importable') from exc
 
 from ..utils.chunking import shard_range
 
 logger = logging.getLogger(__name__)
 
 
-class _SharedRandom:
-    """``mcpy.utils.RandomNumberGenerator`` draws: ``random.Random(seed).uniform(0, 1)``."""
-
-    def __init__(self, seed):
-        from random import Random
-        self.random = Random(seed)
-
-    def get_uniform(self, a=0.0, b=1.0):
-        return self.random.uniform(a, b)
-
-
 def swap_exponent(rec_i, rec_j, n_species):
     """ln(w'/w) of exchanging the configurations of slots i and j.
 
-    ``rec = [E, beta, N_1..N_S, mu_1..mu_S, Lambda_1..Lambda_S]``.  Restates
-    ``BatchedReplicaExchange._accept_swap`` / ``_de_broglie_cross_term``
-    (``batched_replica_exchange.py:339-353, 372-386``) in the same operation order:
+    ``rec = [E, beta, N_1..N_S, mu_1..mu_S, Lambda_1..Lambda_S, has_1..has_S]`` (``has_s`` = slot
+    has a chemical potential for species s; a record without the ``has`` block means "all"; a
+    ``Lambda`` the replica's units do not define travels as NaN).
+    Same operation order as ``BatchedReplicaExchange._accept_swap`` / ``_de_broglie_cross_term``
+    (``batched_replica_exchange.py:339-353, 372-386``):
     ``beta_i Phi_ii + beta_j Phi_jj - beta_i Phi_ji - beta_j Phi_ij`` with
-    ``Phi_Z^(k) = E_Z - sum_s mu_k,s N_Z,s`` accumulated species by species, plus
-    ``3 sum_s (N_X,s - N_Y,s) ln(Lambda_i,s / Lambda_j,s)`` when the betas differ.
+    ``Phi_Z^(k) = E_Z - sum_{s in mu_k} mu_k,s N_Z,s`` accumulated species by species, plus
+    ``3 sum_{s in mu_i} (N_X,s - N_Y,s) ln(Lambda_i,s / Lambda_j,s)`` when the betas differ.
     """
     S = n_species
     Ei, bi, Ni, mui, Li = rec_i[0], rec_i[1], rec_i[2:2 + S], rec_i[2 + S:2 + 2 * S], rec_i[2 + 2 * S:2 + 3 * S]
     Ej, bj, Nj, muj, Lj = rec_j[0], rec_j[1], rec_j[2:2 + S], rec_j[2 + S:2 + 2 * S], rec_j[2 + 2 * S:2 + 3 * S]
+    has_i = rec_i[2 + 3 * S:2 + 4 * S] if len(rec_i) >= 2 + 4 * S else np.ones(S)
+    has_j = rec_j[2 + 3 * S:2 + 4 * S] if len(rec_j) >= 2 + 4 * S else np.ones(S)
 
-    def phi(E, N, mu):
+    def phi(E, N, mu, has):
         score = E
         for s in range(S):
-            score -= mu[s] * N[s]
+            if has[s]:
+                score -= mu[s] * N[s]
         return score
 
-    phi_ii, phi_jj = phi(Ei, Ni, mui), phi(Ej, Nj, muj)
-    phi_ji, phi_ij = phi(Ej, Nj, mui), phi(Ei, Ni, muj)
+    phi_ii, phi_jj = phi(Ei, Ni, mui, has_i), phi(Ej, Nj, muj, has_j)
+    phi_ji, phi_ij = phi(Ej, Nj, mui, has_i), phi(Ei, Ni, muj, has_j)
     delta = bi * phi_ii + bj * phi_jj - bi * phi_ji - bj * phi_ij
     if bi != bj:
         term = 0.0
         for s in range(S):
+            if not has_i[s]:
+                continue
             dn = int(Ni[s]) - int(Nj[s])
             if dn:
+                if np.isnan(Li[s]) or np.isnan(Lj[s]):      # the reference's lambda_dbs[specie] lookup fails here
+                    raise KeyError(f'a replica has no de Broglie wavelength for species #{s} of the ladder')
                 term += 3.0 * dn * np.log(Li[s] / Lj[s])
         delta += term
     return delta
 
 
-class ShardedReplicaExchange:
+class ShardedReplicaExchange(BatchedReplicaExchange):
     def __init__(self, gcmc_factory: Callable, calculator, temperatures: Optional[List[float]] = None,
                  mus: Optional[List[Dict[str, float]]] = None, gcmc_steps: int = 100,
-                 exchange_interval: int = 10, seed: int = 31, rank: Optional[int] = None,
-                 world_size: Optional[int] = None, group=None, device: str = 'cpu') -> None:
+                 exchange_interval: int = 10, outfile: Optional[str] = None, write_out_interval: int = 20,
+                 seed: int = 31, global_minimum_file: Optional[str] = None, consolidate_logging: bool = True,
+                 rank: Optional[int] = None, world_size: Optional[int] = None, group=None,
+                 device: str = 'cpu') -> None:
         if temperatures is None and mus is None:
             raise ValueError('Provide either temperatures or mus (one per replica).')
         if temperatures is not None and mus is not None:
             raise ValueError('Pass temperatures OR mus, not both.')
-        if not hasattr(calculator, 'get_potential_energies'):
-            raise TypeError('calculator must implement get_potential_energies(atoms_list). '
-                            'Use B200Calculator or wrap your calculator.')
         self._dist = None
         if world_size is None:
             try:
@@ -108,30 +114,35 @@ class ShardedReplicaExchange:
             self._dist = dist
         self.rank, self.world_size, self.group, self.device = int(rank), int(world_size), group, device
         ladder = list(temperatures) if temperatures is not None else list(mus)
-        self.temperatures = list(temperatures) if temperatures is not None else None
-        self.mus = list(mus) if mus is not None else None
-        self.n_replicas = len(ladder)
-        self.lo, self.hi = shard_range(self.n_replicas, self.rank, self.world_size)
-        key = 'T' if temperatures is not None else 'mu'
-        self.replicas = [gcmc_factory(**{key: ladder[i]}, rank=i) for i in range(self.lo, self.hi)]
-        shared = [a for a in ('atoms', 'move_selector')
-                  if len({id(getattr(r, a, None)) for r in self.replicas}) < len(self.replicas)]
-        if shared:
-            raise ValueError(f"replicas share {', '.join(shared)}; gcmc_factory must build a fresh "
-                             'ensemble with its own atoms, cells and move_selector per replica')
-        self.calculator = calculator
-        self.gcmc_steps = gcmc_steps
-        self.exchange_interval = exchange_interval
-        self.rng = _SharedRandom(seed)                 # identical stream on every rank
-        self.exchange_attempts = [0] * self.n_replicas
-        self.exchange_successes = [0] * self.n_replicas
-        self.swap_log = []                             # (step, i, j, delta, accepted) on every rank
-        self._re_step = 0
+        self.n_replicas_total = len(ladder)
+        self.lo, self.hi = shard_range(self.n_replicas_total, self.rank, self.world_size)
+        lo = self.lo
+
+        def local_factory(rank=0, **kw):          # the reference numbers replicas 0..R-1 through `rank`
+            return gcmc_factory(rank=lo + rank, **kw)
+
+        def per_rank(name):
+            return name if name is None or self.world_size == 1 else f'{name}.rank{self.rank}'
+
+        key = 'temperatures' if temperatures is not None else 'mus'
+        super().__init__(local_factory, calculator, **{key: ladder[self.lo:self.hi]}, gcmc_steps=gcmc_steps,
+                         exchange_interval=exchange_interval, outfile=per_rank(outfile),
+                         write_out_interval=write_out_interval, seed=seed,
+                         global_minimum_file=per_rank(global_minimum_file),
+                         consolidate_logging=consolidate_logging)
+        self.global_attempts = [0] * self.n_replicas_total
+        self.global_successes = [0] * self.n_replicas_total
+        self.swap_log = []                             # (step, i, j, delta, accepted), identical on every rank
+        self.species = None
+        self.collective_seconds = 0.0                  # all_gather of the records (+ the host<->device hops around it)
+        self.transport_seconds = 0.0                   # point-to-point state transport of cross-rank swaps
+        self.exchange_rounds = 0
+        self._gather_buf = None
 
     # ------------------------------------------------------------------ helpers
     def owner(self, i: int) -> int:
         for g in range(self.world_size):
-            lo, hi = shard_range(self.n_replicas, g, self.world_size)
+            lo, hi = shard_range(self.n_replicas_total, g, self.world_size)
             if lo <= i < hi:
                 return g
         raise IndexError(i)
@@ -140,8 +151,8 @@ class ShardedReplicaExchange:
         return self.replicas[i - self.lo]
 
     def _species(self) -> List[str]:
-        """Species in the order the replicas' ``_mu`` dicts list them (the reference sums
-        ``mu_s N_s`` in that order, ``grand_canonical_ensemble.py:188-195``)."""
+        """Union of the replicas' ``_mu`` keys in first-seen order (the reference sums ``mu_s N_s`` in dict
+        order, ``grand_canonical_ensemble.py:188-195``)."""
         keys: List[str] = []
         for r in self.replicas:
             for k in (getattr(r, '_mu', None) or {}):
@@ -157,131 +168,75 @@ class ShardedReplicaExchange:
                         keys.append(k)
         return keys
 
-    # ------------------------------------------------------------------ run
-    def run(self) -> None:
-        for r in self.replicas:
-            getattr(r, 'initialize_run', lambda: None)()
-        self.species = self._species()
-        self._rebatch_initial_energies()
-        try:
-            for step in range(self.gcmc_steps):
-                self._batched_gcmc_step()
-                if step > 0 and step % self.exchange_interval == 0:
-                    self._attempt_exchanges(step)
-                self._re_step += 1
-        finally:
-            for r in self.replicas:
-                getattr(r, 'finalize_run', lambda: None)()
-
-    def _rebatch_initial_energies(self) -> None:
-        if not self.replicas:
-            return
-        energies = self.calculator.get_potential_energies([r.atoms for r in self.replicas])
-        for r, E in zip(self.replicas, energies):
-            r.E_old = float(E)
-
-    # ----------------------------------------------------------- batched MC
     def _batched_gcmc_step(self) -> None:
-        if not self.replicas:
-            return
-        n_sub = max(r.move_selector.n_moves for r in self.replicas)
-        for k in range(n_sub):
-            self._batched_single_move([i for i, r in enumerate(self.replicas)
-                                       if k < r.move_selector.n_moves])
-        for r in self.replicas:
-            r._step = getattr(r, '_step', 0) + 1
-
-    def _batched_single_move(self, active: List[int]) -> None:
-        """Propose on each active local replica, ONE batched energy call, per-replica acceptance
-        (reference ``_batched_single_move``, ``batched_replica_exchange.py:235-302``)."""
-        snapshots, constraint_snapshots, trial_meta = {}, {}, {}
-        for i in active:
-            r = self.replicas[i]
-            snapshots[i] = {k: v.copy() for k, v in r.atoms.arrays.items()}
-            constraint_snapshots[i] = [c.copy() for c in getattr(r.atoms, 'constraints', [])]
-            result = r.move_selector.do_trial_move(r.atoms)
-            atoms_new, delta_particles, species = result if isinstance(result, tuple) else (result, 0, None)
-            if atoms_new is False or atoms_new is None:
-                r.atoms.arrays = snapshots[i]
-                if hasattr(r.atoms, 'set_constraint'):
-                    r.atoms.set_constraint(constraint_snapshots[i])
-                continue
-            if atoms_new is not r.atoms:
-                raise RuntimeError('GCMC moves must mutate the passed atoms in place')
-            trial_meta[i] = (delta_particles, species)
-        viable = [i for i in active if i in trial_meta]
-        if not viable:
-            return
-        energies = self.calculator.get_potential_energies([self.replicas[i].atoms for i in viable])
-        for i, E_new in zip(viable, energies):
-            r = self.replicas[i]
-            delta_particles, species = trial_meta[i]
-            delta_E = float(E_new) - r.E_old
-            volume = r.move_selector.get_volume()
-            n_exchange = r.move_selector.get_exchange_count()
-            if n_exchange is None:
-                n_exchange = r.n_atoms
-            if r._acceptance_condition(delta_E, delta_particles, volume, species, n_exchange):
-                if getattr(r, '_wrap_on_accept', False):
-                    r.atoms.wrap()
-                r.n_atoms = len(r.atoms)
-                r.E_old = float(E_new)
-                r.move_selector.acceptance_counter()
-                r.calculate_cells_volume(r.atoms)
-                getattr(r, '_record_minimum', lambda a, e: None)(r.atoms, r.E_old)
-            else:
-                r.atoms.arrays = snapshots[i]
-                if hasattr(r.atoms, 'set_constraint'):
-                    r.atoms.set_constraint(constraint_snapshots[i])
+        if self.replicas:                              # a rank may own no replica (R < world size)
+            super()._batched_gcmc_step()
 
     # --------------------------------------------------------- exchange
     def _record(self, r) -> np.ndarray:
         S = len(self.species)
-        rec = np.zeros(2 + 3 * S)
+        rec = np.zeros(2 + 4 * S)
         rec[0], rec[1] = r.E_old, r.units.beta
         mu = getattr(r, '_mu', None) or {}
         for k, s in enumerate(self.species):
+            # counted for EVERY species of the ladder: the cross terms score this configuration with the
+            # neighbour's chemical potentials (`ri._minimum_score(rj.atoms, ...)`, :347-348)
+            rec[2 + k] = r._species_count(r.atoms, s)
+            rec[2 + 2 * S + k] = r.units.lambda_dbs.get(s, np.nan)
             if s in mu:
-                rec[2 + k] = r._species_count(r.atoms, s)
                 rec[2 + S + k] = mu[s]
-                rec[2 + 2 * S + k] = r.units.lambda_dbs[s]
-            else:
-                rec[2 + 2 * S + k] = 1.0
+                rec[2 + 3 * S + k] = 1.0
         return rec
 
     def _gather_records(self) -> np.ndarray:
         """The only collective: all_gather of the per-replica records (padded to equal shards)."""
         S = len(self.species)
-        width = 2 + 3 * S
+        width = 2 + 4 * S
         local = np.array([self._record(r) for r in self.replicas]).reshape(-1, width)
         if self.world_size == 1 or self._dist is None:
             return local
         import torch
-        per = max(shard_range(self.n_replicas, g, self.world_size)[1]
-                  - shard_range(self.n_replicas, g, self.world_size)[0] for g in range(self.world_size))
-        buf = torch.zeros(per, width, dtype=torch.float64, device=self.device)
+        t0 = time.perf_counter()
+        per = -(-self.n_replicas_total // self.world_size)
+        if self._gather_buf is None or self._gather_buf[0].shape != (per, width):
+            pin = str(self.device) != 'cpu'
+            self._gather_buf = (torch.zeros(per, width, dtype=torch.float64, pin_memory=pin),
+                                torch.zeros(per, width, dtype=torch.float64, device=self.device),
+                                torch.zeros(self.world_size * per, width, dtype=torch.float64, device=self.device),
+                                torch.zeros(self.world_size * per, width, dtype=torch.float64, pin_memory=pin))
+        h_in, d_in, d_out, h_out = self._gather_buf
+        h_in.zero_()
         if len(local):
-            buf[:len(local)] = torch.from_numpy(local).to(self.device)
-        out = [torch.empty_like(buf) for _ in range(self.world_size)]
-        self._dist.all_gather(out, buf, group=self.group)
+            h_in[:len(local)] = torch.from_numpy(local)
+        d_in.copy_(h_in, non_blocking=True)
+        self._dist.all_gather_into_tensor(d_out, d_in, group=self.group)
+        h_out.copy_(d_out, non_blocking=True)
+        if str(self.device) != 'cpu':
+            torch.cuda.current_stream().synchronize()
+        out = h_out.numpy().reshape(self.world_size, per, width)
         rows = []
         for g in range(self.world_size):
-            lo, hi = shard_range(self.n_replicas, g, self.world_size)
-            rows.append(out[g][:hi - lo].cpu().numpy())
+            lo, hi = shard_range(self.n_replicas_total, g, self.world_size)
+            rows.append(out[g, :hi - lo])
+        self.collective_seconds += time.perf_counter() - t0
         return np.concatenate(rows)
 
-    def _attempt_exchanges(self, step: int = 0) -> None:
+    def _attempt_exchanges(self) -> None:
+        if self.species is None:
+            self.species = self._species()
+        step = self._re_step
         offset = 0 if self.rng.get_uniform() < 0.5 else 1
         records = self._gather_records()
+        self.exchange_rounds += 1
         S = len(self.species)
-        for i in range(offset, self.n_replicas - 1, 2):
+        for i in range(offset, self.n_replicas_total - 1, 2):
             j = i + 1
-            self.exchange_attempts[i] += 1
-            self.exchange_attempts[j] += 1
+            self.global_attempts[i] += 1
+            self.global_attempts[j] += 1
             delta = swap_exponent(records[i], records[j], S)
             if not np.isfinite(delta):
-                logger.warning('swap %d<->%d: non-finite acceptance exponent (delta=%r); rejecting.',
-                               i, j, delta)
+                self.logger.warning('swap %d<->%d: non-finite acceptance exponent (delta=%r); rejecting. A NaN/inf '
+                                    'replica energy usually means a diverged relaxation.', i, j, delta)
                 accepted = False
             else:
                 p = 1.0 if delta >= 0.0 else float(np.exp(delta))
@@ -289,39 +244,44 @@ class ShardedReplicaExchange:
             self.swap_log.append((step, i, j, float(delta), bool(accepted)))
             if accepted:
                 self._swap_states(i, j)
-                self.exchange_successes[i] += 1
-                self.exchange_successes[j] += 1
+                self.global_successes[i] += 1
+                self.global_successes[j] += 1
+        # the inherited output / post-mortem code reads the local slice of the tallies
+        self.exchange_attempts = self.global_attempts[self.lo:self.hi]
+        self.exchange_successes = self.global_successes[self.lo:self.hi]
 
     # ------------------------------------------------------- state transport
     @staticmethod
-    def _pack(r):
+    def _pack(r) -> bytes:
         atoms = r.atoms
-        extra = sorted(k for k in atoms.arrays if k not in ('positions', 'numbers'))
-        n = len(atoms)
-        parts = [np.asarray(atoms.positions, dtype=np.float64).reshape(-1),
-                 np.asarray(atoms.numbers, dtype=np.float64)]
-        for k in extra:
-            parts.append(np.asarray(atoms.arrays[k], dtype=np.float64).reshape(-1))
-        head = np.array([n, r.E_old, r.n_atoms, len(extra)], dtype=np.float64)
-        return head, np.concatenate(parts) if n else np.zeros(0), extra
+        calc = getattr(atoms, 'calc', None)
+        atoms.calc = None                              # a calculator holds device handles: it stays with the slot
+        try:
+            return pickle.dumps((atoms, float(r.E_old), int(r.n_atoms)), protocol=pickle.HIGHEST_PROTOCOL)
+        finally:
+            atoms.calc = calc
 
-    @staticmethod
-    def _unpack(r, head, payload, extra_names, template_atoms):
-        n = int(head[0])
-        pos = payload[:3 * n].reshape(n, 3).copy()
-        num = payload[3 * n:4 * n].astype(int)
-        atoms = type(template_atoms)(numbers=num, positions=pos, cell=np.asarray(template_atoms.cell),
-                                     pbc=template_atoms.pbc)
-        cur = 4 * n
-        for k in extra_names:
-            old = template_atoms.arrays[k]
-            width = int(np.prod(old.shape[1:])) if old.ndim > 1 else 1
-            vals = payload[cur:cur + n * width].reshape((n,) + old.shape[1:]).astype(old.dtype)
-            atoms.arrays[k] = vals
-            cur += n * width
-        r.atoms = atoms
-        r.E_old = float(head[1])
-        r.n_atoms = int(head[2])
+    def _exchange_bytes(self, payload: bytes, peer: int) -> bytes:
+        """Send ``payload`` to ``peer`` and receive its payload (sizes first); the lower rank sends first."""
+        import torch
+        dist, dev = self._dist, self.device
+        first = self.rank < peer
+
+        def swap(t_send, t_recv):
+            ops = [dist.P2POp(dist.isend, t_send, peer, group=self.group),
+                   dist.P2POp(dist.irecv, t_recv, peer, group=self.group)]
+            if not first:
+                ops.reverse()
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+        n_mine = torch.tensor([len(payload)], dtype=torch.int64, device=dev)
+        n_peer = torch.zeros(1, dtype=torch.int64, device=dev)
+        swap(n_mine, n_peer)
+        t_pay = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+        r_pay = torch.empty(int(n_peer.item()), dtype=torch.uint8, device=dev)
+        swap(t_pay, r_pay)
+        return r_pay.cpu().numpy().tobytes()
 
     def _swap_states(self, i: int, j: int) -> None:
         oi, oj = self.owner(i), self.owner(j)
@@ -335,37 +295,12 @@ class ShardedReplicaExchange:
             return
         if self.rank not in (oi, oj):
             return
-        import torch
+        t0 = time.perf_counter()
         mine, peer = (i, oj) if self.rank == oi else (j, oi)
         r = self.local(mine)
-        head, payload, extra = self._pack(r)
-        dist = self._dist
-        t_head = torch.from_numpy(head).to(self.device)
-        r_head = torch.empty_like(t_head)
-        first = self.rank < peer
-        # fixed-size header first (sizes), then the payload; lower rank sends first
-        if first:
-            dist.send(t_head, peer, group=self.group); dist.recv(r_head, peer, group=self.group)
-        else:
-            dist.recv(r_head, peer, group=self.group); dist.send(t_head, peer, group=self.group)
-        n_peer = int(r_head[0].item())
-        if int(r_head[3].item()) != len(extra):
-            raise RuntimeError('replicas exchange configurations with different per-atom arrays')
-        widths = 4
-        for k in extra:
-            a = r.atoms.arrays[k]
-            widths += int(np.prod(a.shape[1:])) if a.ndim > 1 else 1
-        t_pay = torch.from_numpy(np.ascontiguousarray(payload)).to(self.device)
-        r_pay = torch.empty(n_peer * widths, dtype=torch.float64, device=self.device)
-        if first:
-            if t_pay.numel():
-                dist.send(t_pay, peer, group=self.group)
-            if r_pay.numel():
-                dist.recv(r_pay, peer, group=self.group)
-        else:
-            if r_pay.numel():
-                dist.recv(r_pay, peer, group=self.group)
-            if t_pay.numel():
-                dist.send(t_pay, peer, group=self.group)
-        self._unpack(r, r_head.cpu().numpy(), r_pay.cpu().numpy(), extra, r.atoms)
+        calc = getattr(r.atoms, 'calc', None)
+        atoms, e_old, n_atoms = pickle.loads(self._exchange_bytes(self._pack(r), peer))
+        atoms.calc = calc
+        r.atoms, r.E_old, r.n_atoms = atoms, e_old, n_atoms
+        self.transport_seconds += time.perf_counter() - t0
         r.calculate_cells_volume(r.atoms)

@@ -9,7 +9,10 @@ distance pass; here candidates are drawn in batches, tested in one launch (``mcp
 and the generators are then rewound and replayed up to the first accepted candidate, so a run seeded
 like the reference consumes exactly the draws the reference would.
 
-The distance test needs ``min_insert <= engine.cutoff`` (the cell list only sees that far).
+The distance test runs on a PRIVATE query engine of the move (same device as the ``engine`` it is
+given, cell list cut at ``min_insert``): uploading the proposal's configuration there leaves the resident
+bases of the calculator's engine -- the incremental ``get_potential_energy`` / ``get_potential_energies``
+path -- untouched.
 """
 from __future__ import annotations
 
@@ -59,15 +62,22 @@ def _restore_cell_rng(cell, state):
 class _B200InsertionBase:
     batch = 64
 
+    def _query_engine(self, engine):
+        """The move's own engine for ``min_dist2`` queries: a pure distance search, so any pair potential
+        with cutoff ``min_insert`` gives the right cell list (atoms farther away cannot fail the test)."""
+        from ..engine import Engine
+        if self.min_insert is None:
+            return None
+        if not self.min_insert > 0:
+            raise ValueError(f'min_insert must be positive, got {self.min_insert}')
+        q = Engine(getattr(engine, 'device', 0) if engine is not None else 0)
+        q.set_lj(1.0, 1.0, rc=float(self.min_insert) * (1.0 + 1e-9))
+        return q
+
     def _upload(self, atoms):
-        self.engine.upload([atoms.positions], [np.asarray(atoms.numbers, dtype=np.int32)],
+        self.engine.upload([atoms.positions], [np.ones(len(atoms), dtype=np.int32)],
                            np.asarray(atoms.cell, dtype=np.float64).reshape(1, 9),
                            np.asarray(atoms.pbc, dtype=bool).reshape(1, 3))
-
-    def _check_cutoff(self):
-        if self.min_insert is not None and self.min_insert > self.engine.cutoff * (1 + 1e-12):
-            raise ValueError(f'min_insert={self.min_insert} exceeds the engine cutoff '
-                             f'{self.engine.cutoff}: the cell list cannot see that far')
 
     def get_volume(self):
         return self.cell.get_volume()
@@ -77,12 +87,12 @@ class _B200InsertionBase:
 
 
 class B200InsertionMove(_B200InsertionBase):
-    def __init__(self, cell, species, seed, engine, min_insert=None, max_atoms=None):
-        self.cell, self.species, self.engine = cell, species, engine
+    def __init__(self, cell, species, seed, engine=None, min_insert=None, max_atoms=None):
+        self.cell, self.species = cell, species
         self.rng = _Rng(seed=seed)
         self.min_insert, self.max_atoms = min_insert, max_atoms
         self._min_insert_sq = min_insert ** 2 if min_insert is not None else None
-        self._check_cutoff()
+        self.engine = self._query_engine(engine)
 
     def do_trial_move(self, atoms):
         from ase import Atoms
@@ -134,9 +144,9 @@ class B200MoleculeInsertionMove(_B200InsertionBase):
     """Rigid-molecule insertion; the (atoms x fragment-atoms) distance matrix of the reference
     (``molecule_insertion_move.py:61-72``) becomes one min-distance query per fragment atom."""
 
-    def __init__(self, cell, molecule, name, seed, engine, min_insert=None, max_molecules=None,
+    def __init__(self, cell, molecule, name, seed, engine=None, min_insert=None, max_molecules=None,
                  count_molecules=None):
-        self.cell, self.name, self.engine = cell, name, engine
+        self.cell, self.name = cell, name
         self.species = [name]
         self.rng = _Rng(seed=seed)
         self.molecule = molecule.copy()
@@ -145,23 +155,20 @@ class B200MoleculeInsertionMove(_B200InsertionBase):
         self.min_insert, self.max_molecules = min_insert, max_molecules
         self._min_insert_sq = min_insert ** 2 if min_insert is not None else None
         self.last_exchange_count = None
-        # callable(atoms, template_symbols, cell) -> list of member index arrays; defaults to the
-        # composition match of mcpy.moves.molecule_utils.find_molecules without the spatial filter
+        # callable(atoms, template_symbols, cell) -> list of member index arrays; the default is the cached
+        # equivalent of find_molecules(atoms, template, cell) (molecule_insertion_move.py:44): composition match
+        # AND centre of mass exchangeable with the cell -- the count the deletion move uses too
         self._count = count_molecules
-        self._check_cutoff()
+        self._index = None
+        self.engine = self._query_engine(engine)
 
     def _n_molecules(self, atoms):
         if self._count is not None:
             return len(self._count(atoms, self._template_symbols, self.cell))
-        ids = atoms.arrays.get('molecule_id')
-        if ids is None:
-            return 0
-        symbols = np.asarray(atoms.get_chemical_symbols())
-        n = 0
-        for mid in np.unique(ids):
-            if mid >= 0 and sorted(symbols[ids == mid]) == self._template_symbols:
-                n += 1
-        return n
+        if self._index is None:
+            from .molecules import MoleculeIndex
+            self._index = MoleculeIndex(self._template_symbols)
+        return len(self._index.groups(atoms, self.cell))
 
     def do_trial_move(self, atoms):
         n_mol = self._n_molecules(atoms)

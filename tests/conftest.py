@@ -3,10 +3,11 @@
 * ``-m "not gpu"`` (CPU container): oracle vs golden vectors, host logic, C-ABI
   symbol checks.  ``-m gpu`` (B200 box): parity of the CUDA path against the
   oracle, always through the C ABI (ctypes).
-* The oracle (``oracle/``) and the test-only ``ase`` shim are put on ``sys.path``
-  here and nowhere else; the shim only when a real ``ase`` is not importable.
+* The oracle (``oracle/``), the unmodified reference (``baseline/_ref``, installed by
+  ``__graft_entry__.build()``; ``/root/reference`` as a fall-back in the build container) and,
+  only when a real ``ase`` is not importable, the ``ase`` stand-in (``baseline/ase_shim``) are
+  put on ``sys.path`` here (``baseline/refpath.py``).
 """
-import importlib.util
 import os
 import sys
 
@@ -15,8 +16,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-if importlib.util.find_spec('ase') is None:
-    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'ase_shim'))
+from baseline import refpath  # noqa: E402
+
+ASE_KIND, MCPY_ROOT = refpath.enable()
 
 
 def pytest_configure(config):

@@ -4,7 +4,7 @@
     python tests/golden/make_golden.py
 
 The reference needs ``ase`` (absent here, no network); the test-only stand-in under
-``oracle/ase_shim`` supplies ``Atoms`` etc.  Everything numeric that ends up in the fixtures
+``baseline/ase_shim`` supplies ``Atoms`` etc.  Everything numeric that ends up in the fixtures
 comes from the reference's own code paths (moves, cells, ``GrandCanonicalEnsemble``,
 numpy PCG64 / Python MT19937 streams, scipy cKDTree) and from the oracle energies.
 
@@ -29,8 +29,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'oracle', 'ase_shim'))
-sys.path.insert(0, '/root/reference')
+from baseline import refpath  # noqa: E402
+ASE_KIND, MCPY_ROOT = refpath.enable()
 
 from ase import Atoms  # noqa: E402
 from ase.cluster import Octahedron  # noqa: E402

@@ -1,78 +1,5 @@
-"""Test helpers: a minimal GCMC replica with the attributes the replica drivers touch."""
-from random import Random
-
+"""Test helpers: CPU stand-in calculators and a factory of UNMODIFIED reference GCMC replicas."""
 import numpy as np
-
-from mcpy_b200.ensembles.acceptance import Units, accept_trial
-
-
-class _Selector:
-    """One of insertion / deletion / displacement per trial, box cell, own RNG stream."""
-
-    def __init__(self, seed, L, max_disp=0.3, n_moves=1):
-        self.rng = Random(seed)
-        self.L, self.max_disp, self.n_moves = L, max_disp, n_moves
-        self.accepted = 0
-
-    def do_trial_move(self, atoms):
-        from ase import Atoms
-        u = self.rng.random()
-        n = len(atoms)
-        if u < 1 / 3:
-            p = [self.rng.random() * self.L for _ in range(3)]
-            atoms += Atoms('H', positions=[p])
-            return atoms, 1, 'H'
-        if u < 2 / 3:
-            if n <= 1:
-                return False, -1, 'H'
-            del atoms[self.rng.randrange(n)]
-            return atoms, -1, 'H'
-        if n == 0:
-            return False, 0, 'X'
-        i = self.rng.randrange(n)
-        atoms.positions[i] += [(2 * self.rng.random() - 1) * self.max_disp for _ in range(3)]
-        return atoms, 0, 'X'
-
-    def get_volume(self):
-        return self.L ** 3
-
-    def get_exchange_count(self):
-        return None
-
-    def acceptance_counter(self):
-        self.accepted += 1
-
-
-class MiniGCMC:
-    """The slice of ``GrandCanonicalEnsemble`` the batched / sharded drivers use."""
-
-    def __init__(self, atoms, L, temperature, mu, seed):
-        self.atoms = atoms
-        self.E_old = 0.0
-        self.n_atoms = len(atoms)
-        self._mu = dict(mu)
-        self.units = Units('LJ', temperature, {'H': 1.0})
-        self.move_selector = _Selector(seed + 1, L)
-        self._acc_rng = Random(seed + 2)
-        self._wrap_on_accept = True
-        self._step = 0
-        self.volume_refreshes = 0
-
-    def _acceptance_condition(self, dE, dN, volume, species, n_atoms):
-        return accept_trial(self.units, self._mu, dE, dN, volume, species, n_atoms,
-                            lambda: self._acc_rng.uniform(0.0, 1.0))
-
-    def _species_count(self, atoms, specie):
-        return atoms.get_chemical_symbols().count(specie)
-
-    def _minimum_score(self, atoms, energy):
-        score = energy
-        for s, mu in self._mu.items():
-            score -= mu * self._species_count(atoms, s)
-        return score
-
-    def calculate_cells_volume(self, atoms):
-        self.volume_refreshes += 1
 
 
 class OracleLJCalculator:
@@ -91,11 +18,28 @@ class OracleLJCalculator:
         return np.array([self.get_potential_energy(a) for a in atoms_list])
 
 
-def make_factory(L=7.0, n0=24, base_seed=100):
+def make_factory(calc, L=7.0, n0=24, base_seed=100, fix=(), n_moves=1, extra_mu=None):
+    """``gcmc_factory(T=.., rank=..)`` / ``(mu=.., rank=..)`` of the replica drivers: a fresh reference
+    ``GrandCanonicalEnsemble`` (own atoms, cell, moves, selector, seeds from ``rank``) in LJ units.
+    ``fix``: indices held by an ``ase.constraints.FixAtoms``; ``extra_mu``: ``{rank: mu dict}`` overrides
+    (ladders whose replicas carry different chemical-potential key sets)."""
     def factory(T=None, mu=None, rank=0):
         from ase import Atoms
+        from ase.constraints import FixAtoms
+        from mcpy.cell import Cell
+        from mcpy.ensembles import GrandCanonicalEnsemble
+        from mcpy.moves import DeletionMove, DisplacementMove, InsertionMove, MoveSelector
         rng = np.random.default_rng(base_seed + rank)
         atoms = Atoms(f'H{n0}', positions=rng.uniform(0.5, L - 0.5, size=(n0, 3)), cell=[L, L, L], pbc=True)
-        return MiniGCMC(atoms, L, T if T is not None else 2.0, mu if mu is not None else {'H': -2.5},
-                        seed=base_seed + 10 * rank)
+        if len(fix):
+            atoms.set_constraint(FixAtoms(indices=list(fix)))
+        atoms.info['origin'] = rank
+        cell = Cell(atoms, seed=300 + rank)
+        moves = [InsertionMove(cell, species=['H'], seed=11 + rank), DeletionMove(cell, species=['H'], seed=12 + rank),
+                 DisplacementMove(species=['H'], seed=13 + rank, max_displacement=0.3)]
+        ms = MoveSelector([1, 1, 1], moves, seed=14 + rank, n_moves=n_moves)
+        mu_r = (extra_mu or {}).get(rank, mu if mu is not None else {'H': -2.5})
+        return GrandCanonicalEnsemble(atoms=atoms, cells=[cell], units_type='LJ', calculator=calc,
+                                      mu=mu_r, species=['H'], temperature=T if T is not None else 2.0,
+                                      move_selector=ms, random_seed=40 + rank, traj_file=None, outfile=None)
     return factory

@@ -30,25 +30,32 @@ def test_swap_exponent_reduces_to_the_textbook_forms():
     assert swap_exponent(ri, rj, S) == pytest.approx(3.0 * (10 - 13) * np.log(1.7 / 1.2), rel=1e-13)
 
 
-def _run(rank, world, port, n_rep, steps, out):
+def _run(rank, world, port, n_rep, steps, out, kind='T'):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
-    import importlib.util
-    if importlib.util.find_spec('ase') is None:
-        sys.path.insert(0, os.path.join(ROOT, 'oracle', 'ase_shim'))
+    from baseline import refpath
+    refpath.enable()
     import torch.distributed as dist
     from helpers import OracleLJCalculator, make_factory
     from mcpy_b200.ensembles import ShardedReplicaExchange
     if world > 1:
         dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
-    temps = list(np.linspace(1.5, 3.0, n_rep))
-    re = ShardedReplicaExchange(make_factory(), OracleLJCalculator(), temperatures=temps,
-                                gcmc_steps=steps, exchange_interval=3, seed=31,
-                                rank=rank, world_size=world)
+    calc = OracleLJCalculator()
+    if kind == 'T':
+        ladder = dict(temperatures=list(np.linspace(1.5, 3.0, n_rep)))
+        factory = make_factory(calc, fix=(0, 3))
+    else:
+        # a mu ladder whose replicas do not all carry the same chemical-potential keys
+        ladder = dict(mus=[{'H': -3.0 + 0.3 * k} for k in range(n_rep)])
+        factory = make_factory(calc, fix=(1,), extra_mu={1: {'H': -2.7, 'He': -1.0}})
+    re = ShardedReplicaExchange(factory, calc, gcmc_steps=steps, exchange_interval=3, seed=31,
+                                rank=rank, world_size=world, **ladder)
     re.run()
-    state = {re.lo + k: (r.E_old, r.n_atoms, r.atoms.positions.copy(), r.volume_refreshes)
+    state = {re.lo + k: (r.E_old, r.n_atoms, r.atoms.positions.copy(), r.cells[0].get_volume(),
+                         [list(map(int, c.get_indices())) for c in r.atoms.constraints],
+                         dict(r.atoms.info), r._step)
              for k, r in enumerate(re.replicas)}
-    out.put((rank, re.swap_log, state))
+    out.put((rank, re.swap_log, state, (re.global_attempts, re.global_successes)))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -60,12 +67,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _launch(world, n_rep=5, steps=16):
+def _launch(world, n_rep=5, steps=16, kind='T'):
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_run, args=(r, world, port, n_rep, steps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_run, args=(r, world, port, n_rep, steps, q, kind)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in range(world)]
@@ -75,53 +82,42 @@ def _launch(world, n_rep=5, steps=16):
     return sorted(results, key=lambda t: t[0])
 
 
-def test_two_rank_gloo_run_equals_single_process_run():
-    single = _launch(1)
-    double = _launch(2)
+@pytest.mark.parametrize('kind', ['T', 'mu'])
+def test_two_rank_gloo_run_equals_single_process_run(kind):
+    """World size 2 over gloo == one process: same swap decisions, and after cross-rank swaps the same
+    energies, positions, free volumes, FixAtoms constraints and ``atoms.info`` in every slot."""
+    single = _launch(1, kind=kind)
+    double = _launch(2, kind=kind)
     log1 = single[0][1]
     assert len(log1) > 0 and any(a for *_, a in log1), 'no swap was attempted / accepted'
+    assert any(a and i == 2 for _, i, _, _, a in log1), 'no cross-rank swap (slots 2 <-> 3) was accepted'
     # every rank made the same decisions as the single-process run
-    for _, log, _ in double:
+    for _, log, _, tallies in double:
         assert log == log1
+        assert tallies == single[0][3]
     state1 = single[0][2]
     state2 = {}
-    for _, _, st in double:
+    for _, _, st, _ in double:
         state2.update(st)
     assert sorted(state2) == sorted(state1)
+    origins = set()
     for i in state1:
         assert state2[i][0] == state1[i][0] and state2[i][1] == state1[i][1]
         assert np.array_equal(state2[i][2], state1[i][2])
-        assert state2[i][3] == state1[i][3]          # free-volume refreshes after swaps too
+        assert state2[i][3:] == state1[i][3:]          # volume, constraints, info, step counter
+        origins.add(state1[i][5]['origin'] == i)
+    assert False in origins, 'no configuration changed slots'
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/mcpy'), reason='reference checkout not present')
 def test_single_rank_run_equals_reference_batched_replica_exchange():
     """Same factory, same seeds: the reference's BatchedReplicaExchange and this driver end in
     identical states after identical swap decisions (reference rows a5-a7 of SURVEY.md 8a)."""
-    sys.path.insert(0, '/root/reference')
-    sys.path.insert(0, os.path.join(ROOT, 'tests'))
-    from ase import Atoms
-    from helpers import OracleLJCalculator
-    from mcpy.cell import Cell
-    from mcpy.ensembles import BatchedReplicaExchange, GrandCanonicalEnsemble
-    from mcpy.moves import DeletionMove, DisplacementMove, InsertionMove, MoveSelector
+    from helpers import OracleLJCalculator, make_factory
+    from mcpy.ensembles import BatchedReplicaExchange
     from mcpy_b200.ensembles import ShardedReplicaExchange
 
-    L = 7.0
-
-    def factory(T=None, mu=None, rank=0):
-        rng = np.random.default_rng(200 + rank)
-        atoms = Atoms('H20', positions=rng.uniform(0.5, L - 0.5, size=(20, 3)), cell=[L, L, L], pbc=True)
-        cell = Cell(atoms, seed=300 + rank)
-        moves = [InsertionMove(cell, species=['H'], seed=11 + rank), DeletionMove(cell, species=['H'], seed=12 + rank),
-                 DisplacementMove(species=['H'], seed=13 + rank, max_displacement=0.3)]
-        ms = MoveSelector([1, 1, 1], moves, seed=14 + rank, n_moves=2)
-        return GrandCanonicalEnsemble(atoms=atoms, cells=[cell], units_type='LJ', calculator=calc,
-                                      mu=mu if mu is not None else {'H': -2.5}, species=['H'],
-                                      temperature=T if T is not None else 2.0, move_selector=ms,
-                                      random_seed=40 + rank, traj_file=None, outfile=None)
-
     calc = OracleLJCalculator()
+    factory = make_factory(calc, n0=20, base_seed=200, n_moves=2)
     for ladder in (dict(temperatures=[1.6, 2.0, 2.5, 3.1]),
                    dict(mus=[{'H': -3.0}, {'H': -2.6}, {'H': -2.2}])):
         ref = BatchedReplicaExchange(factory, calc, gcmc_steps=14, exchange_interval=3, seed=31,
