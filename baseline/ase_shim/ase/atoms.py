@@ -336,7 +336,11 @@ class Atoms:
     def get_forces(self, apply_constraint=True, md=False):
         if self.calc is None:
             raise RuntimeError('Atoms object has no calculator.')
-        return self.calc.get_forces(self)
+        forces = np.array(self.calc.get_forces(self), dtype=float)
+        if apply_constraint:
+            for c in self.constraints:
+                c.adjust_forces(self, forces)
+        return forces
 
     def __repr__(self):
         return (f'Atoms(symbols={self.get_chemical_formula()!r}, pbc={self._pbc.tolist()}, '

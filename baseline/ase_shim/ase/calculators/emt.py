@@ -1,17 +1,20 @@
-"""``EMT`` stand-in whose energy is the CPU oracle (oracle/emt.py)."""
+"""``EMT`` stand-in whose energy and forces are the CPU oracle (oracle/emt.py, oracle/cfast.py)."""
 import numpy as np
 
 from .calculator import Calculator, all_changes
 
 
 class EMT(Calculator):
-    implemented_properties = ['energy', 'free_energy']
+    implemented_properties = ['energy', 'free_energy', 'forces']
     default_parameters = {'asap_cutoff': False}
 
     def calculate(self, atoms=None, properties=None, system_changes=all_changes):
-        from oracle.emt import emt_energy
+        from oracle import cfast
+        from oracle.emt import emt_forces
         super().calculate(atoms, properties, system_changes)
-        e = emt_energy(self.atoms.positions, self.atoms.numbers,
-                       np.asarray(self.atoms.cell), self.atoms.pbc)
+        a = self.atoms
+        e = cfast.emt_energy(a.positions, a.numbers, np.asarray(a.cell), a.pbc)
         self.results['energy'] = e
         self.results['free_energy'] = e
+        if properties is not None and 'forces' in properties:
+            self.results['forces'] = emt_forces(a.positions, a.numbers, np.asarray(a.cell), a.pbc)

@@ -263,3 +263,35 @@ class B200RelaxCalculator:
             damping=self.damping)
         atoms.positions[...] = pos        # the optimiser writes the relaxed geometry back (base_calculator.py:19-21)
         return e
+
+
+class B200LBFGS:
+    """Drop-in for ``ase.optimize.LBFGS`` wherever mcpy takes an optimiser CLASS -- ``CanonicalEnsemble(optimizer=...)``
+    builds ``optimizer(atoms, logfile=None)`` and calls ``run(fmax=...)`` on every trial configuration
+    (``mcpy/ensembles/canonical_ensemble.py:115-123``).  ``atoms.calc`` must be a :class:`B200Calculator`; the
+    whole relaxation is ONE ``mcpyb_relax_lbfgs_host`` call (ASE's iteration without line search and ASE's
+    defaults, ``FixAtoms`` honoured), the relaxed positions are written back in place."""
+
+    def __init__(self, atoms, logfile=None, trajectory=None, maxstep=0.2, memory=100, damping=1.0, alpha=70.0,
+                 **kwargs):
+        self.atoms = atoms
+        self.maxstep, self.memory, self.damping, self.alpha = float(maxstep), int(memory), float(damping), float(alpha)
+        self.nsteps = 0
+        self.fmax = float('nan')
+
+    def run(self, fmax=0.05, steps=100_000_000):
+        atoms = self.atoms
+        engine = getattr(getattr(atoms, 'calc', None), 'engine', None)
+        if engine is None:
+            raise ValueError('B200LBFGS needs atoms.calc to be a B200Calculator')
+        if steps == 0 or len(atoms) == 0:
+            return True
+        e, pos, self.nsteps, self.fmax = engine.relax_lbfgs(
+            atoms.positions, atoms.numbers, np.asarray(atoms.cell, dtype=np.float64), atoms.pbc, fmax=fmax,
+            steps=steps, fixed=B200RelaxCalculator._fixed_indices(atoms), maxstep=self.maxstep, memory=self.memory,
+            alpha=self.alpha, damping=self.damping)
+        atoms.positions[...] = pos
+        return bool(self.fmax < fmax)
+
+    def get_number_of_steps(self):
+        return self.nsteps

@@ -1,9 +1,13 @@
 /* Plain-C restatement of the CPU oracle (TEST INFRASTRUCTURE -- NOT PRODUCT CODE).
  *
  * Same definitions as oracle/neighbors.py, oracle/lj.py, oracle/emt.py and
- * oracle/free_volume.py (which cite the reference files they follow), written as
- * O(N^2 * images) loops so the 2 000- and 10 000-atom cases of BASELINE.json
- * finish in seconds.  Compiled with -ffp-contract=off: the squared distance
+ * oracle/free_volume.py (which cite the reference files they follow): loops over
+ * every (i, j, image) in ascending order.  By default the j loop skips atoms whose
+ * bin (edge >= cutoff / 2) is more than two bins from i's bin in any periodic image -- such a j
+ * cannot pass the cutoff test, the visited (i, j, S) sequence and every sum stay
+ * bit-identical to the plain O(N^2 * images) loop (oracle_set_bruteforce(1) selects
+ * it; tests/test_oracle_lj.py compares the two), and the 64 x 2 000-atom and
+ * 10 000-atom cases of BASELINE.json finish in seconds instead of minutes.  Compiled with -ffp-contract=off: the squared distance
  * (dx*dx + dy*dy) + dz*dz must be evaluated without FMA to stay bit-identical to
  * numpy and to the CUDA kernels.  tests/test_oracle_c.py pins this file to the
  * numpy oracle.
@@ -96,10 +100,110 @@ static int* wrap_counts(const double* pos, int n, const geom_t* g) {
     return w;
 }
 
+/* ---- candidate pruning: bins of perpendicular thickness >= cutoff over the wrapped fractional coordinates ---- */
+static int g_bruteforce = 0;
+void oracle_set_bruteforce(int on) { g_bruteforce = on; }
+
+typedef struct {
+    int nb[3];
+    int* bin_start;   /* [nbins + 1] */
+    int* bin_atoms;   /* atoms sorted by bin, ascending index inside a bin */
+    int* bin_of;      /* [n][3] */
+    int* cand;        /* scratch: candidates of the current atom, ascending */
+    int ncand;
+    int n;
+    double* f;        /* wrapped fractional coordinates [n][3] */
+    double reach[3];  /* an image farther than this (fractional, per axis) cannot be within the cutoff */
+} bins_t;
+
+static int cmp_int(const void* a, const void* b) { return *(const int*)a - *(const int*)b; }
+
+static void bins_build(bins_t* b, const double* pos, int n, const geom_t* g, const int* w, double cutoff) {
+    b->n = n;
+    b->cand = (int*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int));
+    b->bin_of = (int*)malloc((size_t)(n > 0 ? n : 1) * 3 * sizeof(int));
+    double* f = (double*)malloc((size_t)(n > 0 ? n : 1) * 3 * sizeof(double));
+    double fmin[3] = {0, 0, 0}, fmax[3] = {1, 1, 1};
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d) {
+            double fd = pos[3 * i] * g->inv[d] + pos[3 * i + 1] * g->inv[3 + d] + pos[3 * i + 2] * g->inv[6 + d];
+            if (g->pbc[d]) fd -= (double)w[3 * i + d];
+            f[3 * i + d] = fd;
+        }
+    for (int d = 0; d < 3; ++d) {
+        if (!g->pbc[d] && n > 0) {
+            fmin[d] = fmax[d] = f[d];
+            for (int i = 1; i < n; ++i) {
+                if (f[3 * i + d] < fmin[d]) fmin[d] = f[3 * i + d];
+                if (f[3 * i + d] > fmax[d]) fmax[d] = f[3 * i + d];
+            }
+        }
+        /* bins of fractional width wd with wd * h >= cutoff / 2 * (1 + 1e-9) */
+        const double span = (fmax[d] - fmin[d]) * g->h[d];
+        int nb = (int)floor(span / (0.5 * cutoff * (1.0 + 1e-9)));   /* two bins per cutoff: visit +-2 */
+        if (nb < 1) nb = 1;
+        if (nb > 64) nb = 64;
+        b->nb[d] = nb;
+    }
+    const int nbins = b->nb[0] * b->nb[1] * b->nb[2];
+    b->bin_start = (int*)calloc((size_t)nbins + 1, sizeof(int));
+    b->bin_atoms = (int*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int));
+    for (int i = 0; i < n; ++i) {
+        for (int d = 0; d < 3; ++d) {
+            int k = (int)floor((f[3 * i + d] - fmin[d]) / (fmax[d] - fmin[d] > 0 ? (fmax[d] - fmin[d]) : 1.0) * b->nb[d]);
+            if (k < 0) k = 0;
+            if (k >= b->nb[d]) k = b->nb[d] - 1;
+            b->bin_of[3 * i + d] = k;
+        }
+        b->bin_start[(b->bin_of[3 * i] * b->nb[1] + b->bin_of[3 * i + 1]) * b->nb[2] + b->bin_of[3 * i + 2] + 1]++;
+    }
+    for (int k = 0; k < nbins; ++k) b->bin_start[k + 1] += b->bin_start[k];
+    int* cur = (int*)malloc((size_t)nbins * sizeof(int));
+    memcpy(cur, b->bin_start, (size_t)nbins * sizeof(int));
+    for (int i = 0; i < n; ++i)
+        b->bin_atoms[cur[(b->bin_of[3 * i] * b->nb[1] + b->bin_of[3 * i + 1]) * b->nb[2] + b->bin_of[3 * i + 2]]++] = i;
+    free(cur);
+    b->f = f;
+    /* |df_d| * h_d is the distance between the lattice planes through the two points: a lower bound of the
+     * pair distance.  1e-6 relative slack covers the rounding of f (|f| <= 512). */
+    for (int d = 0; d < 3; ++d) b->reach[d] = g_bruteforce ? 1e300 : cutoff * (1.0 + 1e-6) / g->h[d] + 1e-9;
+}
+
+/* ascending list of the atoms j that can have an image within the cutoff of atom i */
+static void bins_candidates(bins_t* b, const geom_t* g, int i) {
+    b->ncand = 0;
+    if (g_bruteforce) { for (int j = 0; j < b->n; ++j) b->cand[j] = j; b->ncand = b->n; return; }
+    int lo[3], cnt[3];
+    for (int d = 0; d < 3; ++d) {
+        if (b->nb[d] <= 5 && g->pbc[d]) { lo[d] = 0; cnt[d] = b->nb[d]; }          /* every bin once */
+        else if (g->pbc[d]) { lo[d] = b->bin_of[3 * i + d] - 2; cnt[d] = 5; }       /* wraps around */
+        else {
+            lo[d] = b->bin_of[3 * i + d] - 2; cnt[d] = 5;
+            if (lo[d] < 0) { cnt[d] += lo[d]; lo[d] = 0; }
+            if (lo[d] + cnt[d] > b->nb[d]) cnt[d] = b->nb[d] - lo[d];
+        }
+    }
+    for (int a = 0; a < cnt[0]; ++a) for (int bb = 0; bb < cnt[1]; ++bb) for (int c = 0; c < cnt[2]; ++c) {
+        const int k0 = ((lo[0] + a) % b->nb[0] + b->nb[0]) % b->nb[0], k1 = ((lo[1] + bb) % b->nb[1] + b->nb[1]) % b->nb[1],
+                  k2 = ((lo[2] + c) % b->nb[2] + b->nb[2]) % b->nb[2];
+        const int k = (k0 * b->nb[1] + k1) * b->nb[2] + k2;
+        for (int q = b->bin_start[k]; q < b->bin_start[k + 1]; ++q) b->cand[b->ncand++] = b->bin_atoms[q];
+    }
+    qsort(b->cand, (size_t)b->ncand, sizeof(int), cmp_int);
+}
+
+static void bins_free(bins_t* b) { free(b->bin_start); free(b->bin_atoms); free(b->bin_of); free(b->cand); free(b->f); }
+
 #define PAIR_LOOP_BEGIN \
-    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) \
-    for (int s0 = -g.nimg[0]; s0 <= g.nimg[0]; ++s0) for (int s1 = -g.nimg[1]; s1 <= g.nimg[1]; ++s1) \
+    bins_t bins; bins_build(&bins, pos, n, &g, w, c.rc); \
+    for (int i = 0; i < n; ++i) { bins_candidates(&bins, &g, i); \
+    for (int jj = 0; jj < bins.ncand; ++jj) { const int j = bins.cand[jj]; \
+    for (int s0 = -g.nimg[0]; s0 <= g.nimg[0]; ++s0) { \
+    if (fabs(bins.f[3 * j] + s0 - bins.f[3 * i]) > bins.reach[0]) continue; \
+    for (int s1 = -g.nimg[1]; s1 <= g.nimg[1]; ++s1) { \
+    if (fabs(bins.f[3 * j + 1] + s1 - bins.f[3 * i + 1]) > bins.reach[1]) continue; \
     for (int s2 = -g.nimg[2]; s2 <= g.nimg[2]; ++s2) { \
+        if (fabs(bins.f[3 * j + 2] + s2 - bins.f[3 * i + 2]) > bins.reach[2]) continue; \
         const int S0 = s0 + w[3 * i] - w[3 * j], S1 = s1 + w[3 * i + 1] - w[3 * j + 1], S2 = s2 + w[3 * i + 2] - w[3 * j + 2]; \
         if (i == j && S0 == 0 && S1 == 0 && S2 == 0) continue; \
         const double sx = ((double)S0 * g.cell[0] + (double)S1 * g.cell[3]) + (double)S2 * g.cell[6]; \
@@ -109,7 +213,7 @@ static int* wrap_counts(const double* pos, int n, const geom_t* g) {
                      dz = (pos[3 * j + 2] + sz) - pos[3 * i + 2]; \
         const double r2 = (dx * dx + dy * dy) + dz * dz; \
         if (!in_cut(&c, r2)) continue;
-#define PAIR_LOOP_END }
+#define PAIR_LOOP_END } } } } } bins_free(&bins);
 
 int64_t oracle_neighbor_pairs(const double* pos, int n, const double* cell, const uint8_t* pbc, double cutoff,
                               int mode, int64_t max_pairs, int32_t* oi, int32_t* oj, int32_t* oS, double* or2) {

@@ -1,7 +1,7 @@
 """ctypes face of the plain-C oracle ``oracle/c/oracle.c`` (TEST INFRASTRUCTURE).
 
 Same definitions as the numpy oracle, fast enough for the 2 000- and
-10 000-atom configurations.  ``tests/test_oracle_c.py`` pins it to the numpy
+10 000-atom configurations.  ``tests/test_oracle_lj.py`` / ``test_oracle_emt.py`` pin it to the numpy
 restatements, which in turn are pinned to the reference's golden values.
 """
 from __future__ import annotations
@@ -40,8 +40,14 @@ def _load():
                                           C.c_double, v, v, v]
         lib.oracle_fv_covered.argtypes = [v, C.c_int64, v, v, C.c_int64, v]
         lib.oracle_fv_covered.restype = C.c_int64
+        lib.oracle_set_bruteforce.argtypes = [C.c_int]
         _lib = lib
     return _lib
+
+
+def set_bruteforce(on):
+    """Plain O(N^2 * images) loops instead of the bin-pruned ones (same visiting order, same bits)."""
+    _load().oracle_set_bruteforce(1 if on else 0)
 
 
 def _prep(positions, cell, pbc):

@@ -2,15 +2,35 @@
 import numpy as np
 
 
+def de_tol(dE_ref, E_scale):
+    """Tolerance on a trial-move dE: 1e-10 relative to dE itself (north_star), plus the rounding of the ORACLE's
+    difference of two totals of size ``E_scale`` (each total is the fp64 rounding of an exact long-double sum:
+    <= 1.2e-16 |E| per total; 1e-13 leaves room for the numpy restatements)."""
+    return 1e-10 * max(1.0, abs(dE_ref)) + 1e-13 * abs(E_scale)
+
+
 class OracleLJCalculator:
     """CPU calculator with the batched contract (test stand-in for B200Calculator)."""
 
-    def __init__(self, rc=2.5):
-        self.rc = rc
+    def __init__(self, rc=2.5, sigma=1.0, epsilon=1.0):
+        self.rc, self.sigma, self.epsilon = rc, sigma, epsilon
 
     def get_potential_energy(self, atoms):
         from oracle import cfast
-        return cfast.lj_energy(atoms.positions, np.asarray(atoms.cell), atoms.pbc, 1.0, 1.0, self.rc)
+        return cfast.lj_energy(atoms.positions, np.asarray(atoms.cell), atoms.pbc, self.sigma, self.epsilon, self.rc)
+
+    def get_potential_energies(self, atoms_list, chunk_size=None):
+        if not atoms_list:
+            return np.empty(0)
+        return np.array([self.get_potential_energy(a) for a in atoms_list])
+
+
+class OracleEMTCalculator:
+    """The EMT oracle (plain C) behind the calculator interface."""
+
+    def get_potential_energy(self, atoms):
+        from oracle import cfast
+        return cfast.emt_energy(atoms.positions, atoms.numbers, np.asarray(atoms.cell), atoms.pbc)
 
     def get_potential_energies(self, atoms_list, chunk_size=None):
         if not atoms_list:

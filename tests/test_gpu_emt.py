@@ -2,7 +2,9 @@
 import numpy as np
 import pytest
 
+from helpers import de_tol
 from mcpy_b200.utils import synthetic
+from oracle import cfast
 from oracle import emt as oemt
 from oracle.neighbors import neighbor_pairs
 
@@ -77,13 +79,14 @@ def test_unsupported_species_raises(emt_engine):
         _energy(emt_engine, np.zeros((1, 3)), [26], np.zeros((3, 3)), [0, 0, 0])
 
 
-def _check_trials(engine, cfg, tb, tol_scale):
-    E0 = oemt.emt_energy(cfg['positions'], cfg['numbers'], cfg['cell'], cfg['pbc'])
+def _check_trials(engine, cfg, tb, tol_scale=None):
+    """dE of every trial against the difference of two oracle totals: 1e-10 of |dE| (helpers.de_tol)."""
+    E0 = cfast.emt_energy(cfg['positions'], cfg['numbers'], cfg['cell'], cfg['pbc'])
     dE = engine.trial_delta_e(tb['old_off'], tb['old_idx'], tb['new_off'], tb['new_pos'], tb['new_Z'])
     for t in range(len(dE)):
         p1, n1 = synthetic.apply_trial(cfg, tb, t)
-        ref = oemt.emt_energy(p1, n1, cfg['cell'], cfg['pbc']) - E0
-        assert abs(dE[t] - ref) <= RTOL * tol_scale, (t, dE[t], ref)
+        ref = cfast.emt_energy(p1, n1, cfg['cell'], cfg['pbc']) - E0
+        assert abs(dE[t] - ref) <= de_tol(ref, E0), (t, dE[t], ref)
     return dE
 
 
@@ -164,4 +167,4 @@ def test_s5_ten_thousand_atoms_cluster_build(emt_engine):
     for t in range(3):
         p1, n1 = synthetic.apply_trial(cfg, tb, t)
         r = cfast.emt_energy(p1, n1, cfg['cell'], cfg['pbc']) - ref
-        assert abs(dE[t] - r) <= RTOL * max(1.0, abs(ref)), (t, dE[t], r)
+        assert abs(dE[t] - r) <= de_tol(r, ref), (t, dE[t], r)

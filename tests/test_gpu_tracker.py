@@ -1,11 +1,18 @@
-"""GPU: the incremental drop-in path (mcpyb_tracked_energy_host) against the full path on a chain
-of GCMC-like configurations: displacements, insertions, deletions, accepted moves that accumulate,
-ULP-level perturbation of every coordinate (atoms.wrap()), box changes."""
+"""GPU: the incremental drop-in path (mcpyb_tracked_energy_host) against the ORACLE and against the engine's own
+full path on a chain of GCMC-like configurations: displacements, insertions, deletions, accepted moves that
+accumulate, ULP-level perturbation of every coordinate (atoms.wrap()), box changes."""
 import numpy as np
 import pytest
 
 from mcpy_b200 import Engine
 from mcpy_b200.utils import synthetic
+from oracle import cfast
+
+
+def _oracle_energy(potential, cfg, pos, num, cell, pbc):
+    if potential == 'lj':
+        return cfast.lj_energy(pos, cell, pbc, cfg.get('sigma', 1.0), cfg.get('epsilon', 1.0), cfg.get('rc', 3.0))
+    return cfast.emt_energy(pos, num, cell, pbc)
 
 pytestmark = pytest.mark.gpu
 
@@ -42,6 +49,8 @@ def test_tracked_chain_equals_full_evaluations(potential):
         paths[path] += 1
         e_f = full.potential_energy(tp, tn, cell, pbc)
         assert abs(e_t - e_f) <= 1e-10 * max(1.0, abs(e_f)), (it, kind, path, e_t, e_f)
+        e_o = _oracle_energy(potential, cfg, tp, tn, cell, pbc)            # the third leg: the CPU oracle
+        assert abs(e_t - e_o) <= 1e-10 * max(1.0, abs(e_o)), (it, kind, path, e_t, e_o)
         if rng.random() < 0.5:                         # accepted: the trial becomes the state ...
             pos, num = tp, tn
             if potential == 'lj':                      # ... and atoms.wrap() perturbs every coordinate
@@ -107,6 +116,9 @@ def test_tracked_batch_equals_full_evaluations(potential, zdt):
         e_t, pth = trk.tracked_energies(given, [tn[r] for r in sel], cells[sel], pbcs[sel])
         e_f = full.potential_energies([tp[r] for r in sel], [tn[r] for r in sel], cells[sel], pbcs[sel])
         assert np.all(np.abs(e_t - e_f) <= 1e-10 * np.maximum(1.0, np.abs(e_f))), (it, e_t - e_f)
+        e_o = np.array([_oracle_energy(potential, {'rc': 3.0}, tp[r], tn[r], cells[k].reshape(3, 3), pbcs[k])
+                        for r, k in zip(sel, sel)])
+        assert np.all(np.abs(e_t - e_o) <= 1e-10 * np.maximum(1.0, np.abs(e_o))), (it, e_t - e_o)
         for x in pth:
             paths[x] += 1
         for r in sel:                                       # accept about half of the moves

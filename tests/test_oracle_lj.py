@@ -72,3 +72,35 @@ def test_delta_e_is_difference_of_totals():
     new[7] += [0.2, -0.1, 0.15]
     d = lj.lj_delta_e(pos, new, cell, [1, 1, 1])
     assert d == lj.lj_energy(new, cell, [1, 1, 1]) - lj.lj_energy(pos, cell, [1, 1, 1])
+
+
+def test_c_oracle_bin_pruning_changes_no_bit():
+    """The plain-C oracle skips atoms whose bin cannot hold an image within the cutoff; the visited
+    (i, j, S) sequence must be the plain O(N^2 * images) loop's, so every result is bit-identical."""
+    from oracle import cfast
+    rng = np.random.default_rng(11)
+    tri = np.array([[11.0, 0.0, 0.0], [3.0, 9.5, 0.0], [-2.0, 1.5, 10.0]])
+    cases = [
+        (rng.random((400, 3)) @ (np.eye(3) * 12.0) * 1.3 - 2.0, np.eye(3) * 12.0, [1, 1, 1], 3.0),      # unwrapped atoms
+        (rng.random((300, 3)) @ tri, tri, [1, 1, 1], 2.5),                                             # triclinic
+        (rng.random((300, 3)) * [9.0, 9.0, 30.0], np.diag([9.0, 9.0, 40.0]), [1, 1, 0], 3.0),           # slab
+        (rng.normal(size=(250, 3)) * 6.0, np.zeros((3, 3)), [0, 0, 0], 3.0),                            # cluster
+        (rng.random((60, 3)) * 4.0, np.eye(3) * 4.0, [1, 1, 1], 3.0),                                   # box thinner than 2 rc
+    ]
+    for pos, cell, pbc, rc in cases:
+        num = rng.choice([29, 46, 8, 6], size=len(pos))
+        cfast.set_bruteforce(False)
+        fast = (cfast.lj_energy(pos, cell, pbc, 1.0, 1.0, rc, return_pairs=True),
+                cfast.emt_energy(pos, num, cell, pbc, return_details=True),
+                cfast.neighbor_pairs(pos, cell, pbc, rc, mode=1))
+        cfast.set_bruteforce(True)
+        try:
+            slow = (cfast.lj_energy(pos, cell, pbc, 1.0, 1.0, rc, return_pairs=True),
+                    cfast.emt_energy(pos, num, cell, pbc, return_details=True),
+                    cfast.neighbor_pairs(pos, cell, pbc, rc, mode=1))
+        finally:
+            cfast.set_bruteforce(False)
+        assert fast[0] == slow[0] and fast[0][1] > 0
+        assert fast[1][0] == slow[1][0] and np.array_equal(fast[1][1], slow[1][1]) and fast[1][2] == slow[1][2]
+        for a, b in zip(fast[2], slow[2]):
+            assert np.array_equal(a, b)
