@@ -71,3 +71,45 @@ def accept_trial(units, mu, potential_diff, delta_particles, volume, species, n_
     if delta_particles != 0 and p > 1:
         return True
     return bool(p > draw())
+
+
+def swap_exponent(rec_i, rec_j, n_species):
+    """ln(w'/w) of exchanging the configurations of slots i and j.
+
+    ``rec = [E, beta, N_1..N_S, mu_1..mu_S, Lambda_1..Lambda_S, has_1..has_S]`` (``has_s`` = slot
+    has a chemical potential for species s; a record without the ``has`` block means "all"; a
+    ``Lambda`` the replica's units do not define travels as NaN).
+    Same operation order as ``BatchedReplicaExchange._accept_swap`` / ``_de_broglie_cross_term``
+    (``batched_replica_exchange.py:339-353, 372-386``):
+    ``beta_i Phi_ii + beta_j Phi_jj - beta_i Phi_ji - beta_j Phi_ij`` with
+    ``Phi_Z^(k) = E_Z - sum_{s in mu_k} mu_k,s N_Z,s`` accumulated species by species, plus
+    ``3 sum_{s in mu_i} (N_X,s - N_Y,s) ln(Lambda_i,s / Lambda_j,s)`` when the betas differ.
+    """
+    S = n_species
+    Ei, bi, Ni, mui, Li = rec_i[0], rec_i[1], rec_i[2:2 + S], rec_i[2 + S:2 + 2 * S], rec_i[2 + 2 * S:2 + 3 * S]
+    Ej, bj, Nj, muj, Lj = rec_j[0], rec_j[1], rec_j[2:2 + S], rec_j[2 + S:2 + 2 * S], rec_j[2 + 2 * S:2 + 3 * S]
+    has_i = rec_i[2 + 3 * S:2 + 4 * S] if len(rec_i) >= 2 + 4 * S else np.ones(S)
+    has_j = rec_j[2 + 3 * S:2 + 4 * S] if len(rec_j) >= 2 + 4 * S else np.ones(S)
+
+    def phi(E, N, mu, has):
+        score = E
+        for s in range(S):
+            if has[s]:
+                score -= mu[s] * N[s]
+        return score
+
+    phi_ii, phi_jj = phi(Ei, Ni, mui, has_i), phi(Ej, Nj, muj, has_j)
+    phi_ji, phi_ij = phi(Ej, Nj, mui, has_i), phi(Ei, Ni, muj, has_j)
+    delta = bi * phi_ii + bj * phi_jj - bi * phi_ji - bj * phi_ij
+    if bi != bj:
+        term = 0.0
+        for s in range(S):
+            if not has_i[s]:
+                continue
+            dn = int(Ni[s]) - int(Nj[s])
+            if dn:
+                if np.isnan(Li[s]) or np.isnan(Lj[s]):      # the reference's lambda_dbs[specie] lookup fails here
+                    raise KeyError(f'a replica has no de Broglie wavelength for species #{s} of the ladder')
+                term += 3.0 * dn * np.log(Li[s] / Lj[s])
+        delta += term
+    return delta

@@ -1,0 +1,156 @@
+"""A shard of a replica ladder kept RESIDENT in HBM, for batched trial scoring between exchange steps.
+
+``ShardedReplicaExchange`` drives the reference's host-side replicas one trial per replica per call.
+This class is the device-resident form of the same ladder for the batched trial kernel (many proposals
+per replica per launch, ``Engine.trial_delta_e_dev``): the configurations of the local replicas live in
+one device array, the engine's cell lists are built from it in place, and an exchange attempt moves
+configurations between SLOTS without a host round trip of the atoms:
+
+* ``attempt_exchanges()`` gathers one record per replica ``[E, beta, N, mu, Lambda, has, n_atoms, cell, pbc]`` with the
+  ladder's only collective (``LadderComm.gather_records``), takes the even / odd pairing and the Metropolis
+  decisions from a generator seeded identically on every rank with the reference's exponent
+  (``swap_exponent`` = ``BatchedReplicaExchange._accept_swap``, ``batched_replica_exchange.py:320-370``),
+  swaps accepted local pairs inside the device array, ships accepted cross-rank pairs point to point over
+  NCCL (positions + numbers, device to device, one grouped call per round) and rebuilds the engine's cell
+  lists from the device array (``Engine.upload_dev``).  As in the reference, beta / mu stay with the slot,
+  E and the configuration travel together (``_swap_states``, ``:401-410``).
+
+One exchanged species (every atom of the configuration counts), one box per replica.
+"""
+from __future__ import annotations
+
+from random import Random
+
+import numpy as np
+
+from .ladder_comm import LadderComm
+from .acceptance import swap_exponent
+
+_WIDTH = 19                  # E, beta, N, mu, Lambda, has_mu, n_atoms, cell (9), pbc (3)
+
+
+class ResidentLadderShard:
+    def __init__(self, engine, configs, betas, mus, lambdas=None, seed=31, rank=None, world_size=None,
+                 group=None, device=None):
+        """``configs``: the LOCAL replicas, each ``(positions (n, 3), numbers (n,), cell (3, 3), pbc (3,))``;
+        ``betas`` / ``mus`` (/ ``lambdas``): the GLOBAL ladder, one value per slot."""
+        import torch
+        self.torch = torch
+        self.engine = engine
+        self.n_total = len(betas)
+        if len(mus) != self.n_total:
+            raise ValueError('betas and mus must list every slot of the ladder')
+        self.device = device if device is not None else f'cuda:{engine.device}'
+        self.comm = LadderComm(self.n_total, rank=rank, world_size=world_size, group=group, device=self.device)
+        self.lo, self.hi = self.comm.lo, self.comm.hi
+        if len(configs) != self.hi - self.lo:
+            raise ValueError(f'rank {self.comm.rank} owns slots [{self.lo}, {self.hi}) but got {len(configs)} configurations')
+        self.betas = np.asarray(betas, dtype=float)
+        self.mus = np.asarray(mus, dtype=float)
+        self.lambdas = np.ones(self.n_total) if lambdas is None else np.asarray(lambdas, dtype=float)
+        self.rng = Random(seed)                        # mcpy.utils.RandomNumberGenerator(seed).get_uniform()
+        self.n_of = [len(c[0]) for c in configs]
+        self.cells = np.stack([np.asarray(c[2], dtype=float).reshape(9) for c in configs]) if configs else np.zeros((0, 9))
+        self.pbcs = np.stack([np.asarray(c[3], dtype=bool).reshape(3) for c in configs]) if configs else np.zeros((0, 3), bool)
+        dev = self.device
+        cat = np.concatenate([np.asarray(c[0], dtype=np.float64).reshape(-1, 3) for c in configs]) if configs else np.zeros((0, 3))
+        num = np.concatenate([np.asarray(c[1], dtype=np.int32).reshape(-1) for c in configs]) if configs else np.zeros(0, np.int32)
+        self.d_pos = torch.from_numpy(np.ascontiguousarray(cat)).to(dev)
+        self.d_num = torch.from_numpy(np.ascontiguousarray(num)).to(dev)
+        if str(dev) != 'cpu':
+            # the engine builds its cell lists from tensors torch has just written: one stream for both
+            engine.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.E = np.zeros(len(configs))
+        self.swap_log = []
+        self.rounds = 0
+        self.upload(energies=True)
+
+    # ------------------------------------------------------------------ residency
+    def offsets(self):
+        return np.concatenate([[0], np.cumsum(self.n_of)]).astype(np.int64)
+
+    def upload(self, energies=False):
+        """(Re)build the engine's cell lists from the device array; optionally read the replica energies."""
+        self.engine.upload_dev(self.offsets(), self.d_pos.data_ptr(), self.d_num.data_ptr(), self.cells, self.pbcs)
+        if energies and len(self.n_of):
+            self.E = self.engine.energies().copy()
+
+    def slot_rows(self, k):
+        off = self.offsets()
+        return int(off[k]), int(off[k + 1])
+
+    # ------------------------------------------------------------------ exchange
+    def records(self):
+        rec = np.zeros((self.hi - self.lo, _WIDTH))
+        for k in range(self.hi - self.lo):
+            g = self.lo + k
+            rec[k, :7] = (self.E[k], self.betas[g], self.n_of[k], self.mus[g], self.lambdas[g], 1.0, self.n_of[k])
+            rec[k, 7:16] = self.cells[k]
+            rec[k, 16:19] = self.pbcs[k]
+        return rec
+
+    def attempt_exchanges(self):
+        """One exchange round; returns the number of accepted swaps (identical on every rank)."""
+        torch = self.torch
+        offset = 0 if self.rng.uniform(0.0, 1.0) < 0.5 else 1
+        rec = self.comm.gather_records(self.records())
+        self.rounds += 1
+        accepted_pairs = []
+        for i in range(offset, self.n_total - 1, 2):
+            j = i + 1
+            delta = swap_exponent(rec[i, :6], rec[j, :6], 1)
+            if not np.isfinite(delta):
+                ok = False
+            else:
+                p = 1.0 if delta >= 0.0 else float(np.exp(delta))
+                ok = self.rng.uniform(0.0, 1.0) < p
+            self.swap_log.append((self.rounds, i, j, float(delta), bool(ok)))
+            if ok:
+                accepted_pairs.append((i, j))
+        if not accepted_pairs:
+            return 0
+        me = self.comm.rank
+        sends, recvs, incoming = [], [], []
+        local_swaps = []
+        for i, j in accepted_pairs:
+            oi, oj = self.comm.owner(i), self.comm.owner(j)
+            if oi == me and oj == me:
+                local_swaps.append((i - self.lo, j - self.lo))
+            elif me in (oi, oj):
+                mine, theirs, peer = (i, j, oj) if me == oi else (j, i, oi)
+                k = mine - self.lo
+                a, b = self.slot_rows(k)
+                n_in = int(rec[theirs, 6])
+                r_pos = torch.empty((n_in, 3), dtype=torch.float64, device=self.device)
+                r_num = torch.empty(n_in, dtype=torch.int32, device=self.device)
+                sends += [(self.d_pos[a:b].contiguous(), peer), (self.d_num[a:b].contiguous(), peer)]
+                recvs += [(r_pos, peer), (r_num, peer)]
+                incoming.append((k, r_pos, r_num, rec[theirs]))
+        self.comm.exchange(sends, recvs)
+        # apply: the device array is re-assembled from its blocks in their new slots (one concatenation each
+        # for positions and numbers, whatever the number of swaps)
+        off = self.offsets()
+        blocks = [[self.d_pos[off[k]:off[k + 1]], self.d_num[off[k]:off[k + 1]]] for k in range(len(self.n_of))]
+        for a, b in local_swaps:
+            blocks[a], blocks[b] = blocks[b], blocks[a]
+            self.n_of[a], self.n_of[b] = self.n_of[b], self.n_of[a]
+            self.E[a], self.E[b] = self.E[b], self.E[a]
+            self.cells[[a, b]] = self.cells[[b, a]]
+            self.pbcs[[a, b]] = self.pbcs[[b, a]]
+        for k, r_pos, r_num, rec_in in incoming:
+            blocks[k] = [r_pos, r_num]
+            self.n_of[k] = len(r_pos)
+            self.E[k] = rec_in[0]
+            self.cells[k] = rec_in[7:16]
+            self.pbcs[k] = rec_in[16:19] != 0
+        if blocks:
+            self.d_pos = torch.cat([b[0] for b in blocks])
+            self.d_num = torch.cat([b[1] for b in blocks])
+        self.upload()
+        return len(accepted_pairs)
+
+    def positions_host(self):
+        """The local configurations back on the host (tests): list of ``(positions, numbers)``."""
+        off = self.offsets()
+        p, z = self.d_pos.cpu().numpy(), self.d_num.cpu().numpy()
+        return [(p[off[k]:off[k + 1]].copy(), z[off[k]:off[k + 1]].copy()) for k in range(len(self.n_of))]

@@ -29,7 +29,6 @@ from __future__ import annotations
 
 import logging
 import pickle
-import time
 from typing import Callable, Dict, List, Optional
 
 import numpy as np
@@ -40,51 +39,10 @@ except ImportError as exc:                                   # pragma: no cover
     raise ImportError('mcpy_b200.ensembles.ShardedReplicaExchange extends BatchedReplicaExchange of '
                       'farrisric/mcpy: the `mcpy` package (and its dependency `ase`) must be importable') from exc
 
-from ..utils.chunking import shard_range
+from .acceptance import swap_exponent
+from .ladder_comm import LadderComm
 
 logger = logging.getLogger(__name__)
-
-
-def swap_exponent(rec_i, rec_j, n_species):
-    """ln(w'/w) of exchanging the configurations of slots i and j.
-
-    ``rec = [E, beta, N_1..N_S, mu_1..mu_S, Lambda_1..Lambda_S, has_1..has_S]`` (``has_s`` = slot
-    has a chemical potential for species s; a record without the ``has`` block means "all"; a
-    ``Lambda`` the replica's units do not define travels as NaN).
-    Same operation order as ``BatchedReplicaExchange._accept_swap`` / ``_de_broglie_cross_term``
-    (``batched_replica_exchange.py:339-353, 372-386``):
-    ``beta_i Phi_ii + beta_j Phi_jj - beta_i Phi_ji - beta_j Phi_ij`` with
-    ``Phi_Z^(k) = E_Z - sum_{s in mu_k} mu_k,s N_Z,s`` accumulated species by species, plus
-    ``3 sum_{s in mu_i} (N_X,s - N_Y,s) ln(Lambda_i,s / Lambda_j,s)`` when the betas differ.
-    """
-    S = n_species
-    Ei, bi, Ni, mui, Li = rec_i[0], rec_i[1], rec_i[2:2 + S], rec_i[2 + S:2 + 2 * S], rec_i[2 + 2 * S:2 + 3 * S]
-    Ej, bj, Nj, muj, Lj = rec_j[0], rec_j[1], rec_j[2:2 + S], rec_j[2 + S:2 + 2 * S], rec_j[2 + 2 * S:2 + 3 * S]
-    has_i = rec_i[2 + 3 * S:2 + 4 * S] if len(rec_i) >= 2 + 4 * S else np.ones(S)
-    has_j = rec_j[2 + 3 * S:2 + 4 * S] if len(rec_j) >= 2 + 4 * S else np.ones(S)
-
-    def phi(E, N, mu, has):
-        score = E
-        for s in range(S):
-            if has[s]:
-                score -= mu[s] * N[s]
-        return score
-
-    phi_ii, phi_jj = phi(Ei, Ni, mui, has_i), phi(Ej, Nj, muj, has_j)
-    phi_ji, phi_ij = phi(Ej, Nj, mui, has_i), phi(Ei, Ni, muj, has_j)
-    delta = bi * phi_ii + bj * phi_jj - bi * phi_ji - bj * phi_ij
-    if bi != bj:
-        term = 0.0
-        for s in range(S):
-            if not has_i[s]:
-                continue
-            dn = int(Ni[s]) - int(Nj[s])
-            if dn:
-                if np.isnan(Li[s]) or np.isnan(Lj[s]):      # the reference's lambda_dbs[specie] lookup fails here
-                    raise KeyError(f'a replica has no de Broglie wavelength for species #{s} of the ladder')
-                term += 3.0 * dn * np.log(Li[s] / Lj[s])
-        delta += term
-    return delta
 
 
 class ShardedReplicaExchange(BatchedReplicaExchange):
@@ -98,24 +56,11 @@ class ShardedReplicaExchange(BatchedReplicaExchange):
             raise ValueError('Provide either temperatures or mus (one per replica).')
         if temperatures is not None and mus is not None:
             raise ValueError('Pass temperatures OR mus, not both.')
-        self._dist = None
-        if world_size is None:
-            try:
-                import torch.distributed as dist
-                if dist.is_available() and dist.is_initialized():
-                    self._dist = dist
-                    rank, world_size = dist.get_rank(group), dist.get_world_size(group)
-            except ImportError:
-                pass
-            if world_size is None:
-                rank, world_size = 0, 1
-        elif world_size > 1:
-            import torch.distributed as dist
-            self._dist = dist
-        self.rank, self.world_size, self.group, self.device = int(rank), int(world_size), group, device
         ladder = list(temperatures) if temperatures is not None else list(mus)
+        self.comm = LadderComm(len(ladder), rank=rank, world_size=world_size, group=group, device=device)
+        self.rank, self.world_size, self.group, self.device = self.comm.rank, self.comm.world_size, group, device
         self.n_replicas_total = len(ladder)
-        self.lo, self.hi = shard_range(self.n_replicas_total, self.rank, self.world_size)
+        self.lo, self.hi = self.comm.lo, self.comm.hi
         lo = self.lo
 
         def local_factory(rank=0, **kw):          # the reference numbers replicas 0..R-1 through `rank`
@@ -134,18 +79,19 @@ class ShardedReplicaExchange(BatchedReplicaExchange):
         self.global_successes = [0] * self.n_replicas_total
         self.swap_log = []                             # (step, i, j, delta, accepted), identical on every rank
         self.species = None
-        self.collective_seconds = 0.0                  # all_gather of the records (+ the host<->device hops around it)
-        self.transport_seconds = 0.0                   # point-to-point state transport of cross-rank swaps
         self.exchange_rounds = 0
-        self._gather_buf = None
+
+    @property
+    def collective_seconds(self):                      # all_gather of the records (+ the host<->device hops around it)
+        return self.comm.collective_seconds
+
+    @property
+    def transport_seconds(self):                       # point-to-point state transport of cross-rank swaps
+        return self.comm.transport_seconds
 
     # ------------------------------------------------------------------ helpers
     def owner(self, i: int) -> int:
-        for g in range(self.world_size):
-            lo, hi = shard_range(self.n_replicas_total, g, self.world_size)
-            if lo <= i < hi:
-                return g
-        raise IndexError(i)
+        return self.comm.owner(i)
 
     def local(self, i: int):
         return self.replicas[i - self.lo]
@@ -158,15 +104,12 @@ class ShardedReplicaExchange(BatchedReplicaExchange):
             for k in (getattr(r, '_mu', None) or {}):
                 if k not in keys:
                     keys.append(k)
-        if self._dist is not None and self.world_size > 1:
-            gathered = [None] * self.world_size
-            self._dist.all_gather_object(gathered, keys, group=self.group)
-            keys = []
-            for ks in gathered:
-                for k in ks:
-                    if k not in keys:
-                        keys.append(k)
-        return keys
+        merged: List[str] = []
+        for ks in self.comm.all_gather_object(keys):
+            for k in ks:
+                if k not in merged:
+                    merged.append(k)
+        return merged
 
     def _batched_gcmc_step(self) -> None:
         if self.replicas:                              # a rank may own no replica (R < world size)
@@ -189,37 +132,10 @@ class ShardedReplicaExchange(BatchedReplicaExchange):
         return rec
 
     def _gather_records(self) -> np.ndarray:
-        """The only collective: all_gather of the per-replica records (padded to equal shards)."""
-        S = len(self.species)
-        width = 2 + 4 * S
+        """The only collective: all_gather of the per-replica records (``LadderComm.gather_records``)."""
+        width = 2 + 4 * len(self.species)
         local = np.array([self._record(r) for r in self.replicas]).reshape(-1, width)
-        if self.world_size == 1 or self._dist is None:
-            return local
-        import torch
-        t0 = time.perf_counter()
-        per = -(-self.n_replicas_total // self.world_size)
-        if self._gather_buf is None or self._gather_buf[0].shape != (per, width):
-            pin = str(self.device) != 'cpu'
-            self._gather_buf = (torch.zeros(per, width, dtype=torch.float64, pin_memory=pin),
-                                torch.zeros(per, width, dtype=torch.float64, device=self.device),
-                                torch.zeros(self.world_size * per, width, dtype=torch.float64, device=self.device),
-                                torch.zeros(self.world_size * per, width, dtype=torch.float64, pin_memory=pin))
-        h_in, d_in, d_out, h_out = self._gather_buf
-        h_in.zero_()
-        if len(local):
-            h_in[:len(local)] = torch.from_numpy(local)
-        d_in.copy_(h_in, non_blocking=True)
-        self._dist.all_gather_into_tensor(d_out, d_in, group=self.group)
-        h_out.copy_(d_out, non_blocking=True)
-        if str(self.device) != 'cpu':
-            torch.cuda.current_stream().synchronize()
-        out = h_out.numpy().reshape(self.world_size, per, width)
-        rows = []
-        for g in range(self.world_size):
-            lo, hi = shard_range(self.n_replicas_total, g, self.world_size)
-            rows.append(out[g, :hi - lo])
-        self.collective_seconds += time.perf_counter() - t0
-        return np.concatenate(rows)
+        return self.comm.gather_records(local)
 
     def _attempt_exchanges(self) -> None:
         if self.species is None:
@@ -261,28 +177,6 @@ class ShardedReplicaExchange(BatchedReplicaExchange):
         finally:
             atoms.calc = calc
 
-    def _exchange_bytes(self, payload: bytes, peer: int) -> bytes:
-        """Send ``payload`` to ``peer`` and receive its payload (sizes first); the lower rank sends first."""
-        import torch
-        dist, dev = self._dist, self.device
-        first = self.rank < peer
-
-        def swap(t_send, t_recv):
-            ops = [dist.P2POp(dist.isend, t_send, peer, group=self.group),
-                   dist.P2POp(dist.irecv, t_recv, peer, group=self.group)]
-            if not first:
-                ops.reverse()
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-
-        n_mine = torch.tensor([len(payload)], dtype=torch.int64, device=dev)
-        n_peer = torch.zeros(1, dtype=torch.int64, device=dev)
-        swap(n_mine, n_peer)
-        t_pay = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
-        r_pay = torch.empty(int(n_peer.item()), dtype=torch.uint8, device=dev)
-        swap(t_pay, r_pay)
-        return r_pay.cpu().numpy().tobytes()
-
     def _swap_states(self, i: int, j: int) -> None:
         oi, oj = self.owner(i), self.owner(j)
         if oi == self.rank and oj == self.rank:
@@ -295,12 +189,10 @@ class ShardedReplicaExchange(BatchedReplicaExchange):
             return
         if self.rank not in (oi, oj):
             return
-        t0 = time.perf_counter()
         mine, peer = (i, oj) if self.rank == oi else (j, oi)
         r = self.local(mine)
         calc = getattr(r.atoms, 'calc', None)
-        atoms, e_old, n_atoms = pickle.loads(self._exchange_bytes(self._pack(r), peer))
+        atoms, e_old, n_atoms = pickle.loads(self.comm.exchange_bytes(self._pack(r), peer))
         atoms.calc = calc
         r.atoms, r.E_old, r.n_atoms = atoms, e_old, n_atoms
-        self.transport_seconds += time.perf_counter() - t0
         r.calculate_cells_volume(r.atoms)

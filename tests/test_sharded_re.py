@@ -133,3 +133,106 @@ def test_single_rank_run_equals_reference_batched_replica_exchange():
             assert a.E_old == b.E_old and a.n_atoms == b.n_atoms
             assert np.array_equal(a.atoms.positions, b.atoms.positions)
             assert a.cells[0].get_volume() == b.cells[0].get_volume()
+
+
+# ------------------------------------------------------------------ the device-resident form of the ladder
+class _HostEngine:
+    """Stands in for ``Engine`` on the CPU: ``upload_dev`` records what it is handed, energies from the oracle."""
+    device = 0
+
+    def __init__(self):
+        self.uploads = 0
+
+    def upload_dev(self, off, d_pos, d_num, cells, pbcs):
+        self.off, self.cells, self.pbcs = np.array(off), np.array(cells), np.array(pbcs)
+        self.uploads += 1
+
+    def bind(self, shard):
+        self.shard = shard
+
+    def energies(self):
+        from oracle import cfast
+        sh, off = self.shard, self.off
+        pos = sh.d_pos.numpy()
+        return np.array([cfast.lj_energy(pos[off[k]:off[k + 1]], self.cells[k].reshape(3, 3), self.pbcs[k], 1.0, 1.0, 2.5)
+                         for k in range(len(off) - 1)])
+
+
+def _resident_configs(n_rep):
+    out = []
+    for g in range(n_rep):
+        rng = np.random.default_rng(700 + g)
+        L = 6.0 + 0.1 * g                                   # boxes differ: they must travel with the configuration
+        n = 20 + (g % 3)                                    # ragged sizes
+        out.append((rng.uniform(0.3, L - 0.3, size=(n, 3)), np.full(n, 1 + g % 2, np.int32), np.eye(3) * L, np.ones(3, bool)))
+    return out
+
+
+def _run_resident(rank, world, port, n_rep, rounds, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from mcpy_b200.ensembles.resident_shard import ResidentLadderShard
+    if world > 1:
+        dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    from mcpy_b200.utils.chunking import shard_range
+    lo, hi = shard_range(n_rep, rank, world)
+    cfgs = _resident_configs(n_rep)
+    eng = _HostEngine()
+
+    class _Shard(ResidentLadderShard):
+        def upload(self, energies=False):
+            eng.bind(self)
+            super().upload(energies)
+    sh = _Shard(eng, cfgs[lo:hi], betas=np.full(n_rep, 0.5), mus=np.linspace(-3.0, -1.0, n_rep), seed=31,
+                rank=rank, world_size=world, device='cpu')
+    e0 = sh.E.copy()
+    for _ in range(rounds):
+        sh.attempt_exchanges()
+    state = {lo + k: (p, z, float(sh.E[k]), sh.cells[k].copy()) for k, (p, z) in enumerate(sh.positions_host())}
+    out.put((rank, sh.swap_log, state, e0, eng.uploads))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_resident_ladder_shard_two_ranks_equal_one():
+    """ResidentLadderShard: after a few exchange rounds every slot of the world-size-2 run holds the same
+    configuration, box and energy as the single-process run, decisions are identical on all ranks, and every
+    configuration still carries the energy it was uploaded with."""
+    import torch.multiprocessing as mp
+    n_rep, rounds = 7, 9
+    res = {}
+    for world in (1, 2):
+        ctx = mp.get_context('spawn')
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_run_resident, args=(r, world, port, n_rep, rounds, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        got = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        res[world] = got
+    log1 = res[1][0][1]
+    assert any(ok for *_, ok in log1) and any(not ok for *_, ok in log1)
+    assert any(ok and i == 3 for _, i, _, _, ok in log1), 'no cross-rank swap (slots 3 <-> 4)'
+    for _, log, *_ in res[2]:
+        assert log == log1
+    s1 = res[1][0][2]
+    s2 = {}
+    for _, _, st, *_ in res[2]:
+        s2.update(st)
+    assert sorted(s1) == sorted(s2) == list(range(n_rep))
+    e_initial = res[1][0][3]
+    cfgs = _resident_configs(n_rep)
+    moved = 0
+    for i in range(n_rep):
+        assert np.array_equal(s1[i][0], s2[i][0]) and np.array_equal(s1[i][1], s2[i][1])
+        assert s1[i][2] == s2[i][2] and np.array_equal(s1[i][3], s2[i][3])
+        src = [g for g in range(n_rep) if cfgs[g][0].shape == s1[i][0].shape and np.array_equal(cfgs[g][0], s1[i][0])]
+        assert len(src) == 1                                  # a permutation of the initial configurations ...
+        assert s1[i][2] == e_initial[src[0]]                  # ... each still with its own energy
+        assert np.array_equal(s1[i][3], cfgs[src[0]][2].reshape(9))
+        moved += src[0] != i
+    assert moved >= 2
