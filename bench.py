@@ -4,36 +4,36 @@
     python bench.py --gpus N --steps K --warmup W            # this repository (CUDA)
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path
 
-Workload (BASELINE.json configs[1], SURVEY.md 8d "S2"): a 2 000-atom Lennard-Jones
-fluid (eps = sigma = 1, rc = 3, rho* = 0.6, periodic cubic box) and a batch of
-pre-generated GCMC proposals against it -- insertions, deletions and displacements
-in the ratio 1:1:1.  One "step" scores the whole batch once.
+Workload, identical at every N (weak scaling): the block of BASELINE.json configs[3] ("64 replicas x
+~2 000-atom LJ, sharded over 8 B200": SURVEY.md 8d "S4") that one GPU owns -- 8 replicas of configs[1]
+("S2": 2 000-atom Lennard-Jones fluid, eps = sigma = 1, rc = 3, rho* = 0.6, periodic cubic box) on a
+chemical-potential ladder.  One SWEEP scores 8 192 pre-generated GCMC proposals per replica (65 536 dE
+evaluations: insertions, deletions, displacements 1:1:1) against the rank's resident configurations in ONE
+batched launch of the trial pipeline.  Every 10 sweeps the ladder attempts an exchange: the records
+[E, beta, N, mu, Lambda, ...] of all replicas are all_gathered (NCCL over NVLink; the path's only collective),
+every rank takes the same Metropolis decisions, accepted pairs swap configurations -- inside a rank by
+relabelling device rows, across ranks point to point -- and the changed cell lists are rebuilt.  One STEP =
+`--sweeps` sweeps (default 320) and their exchange attempts, so that K = 20 steps time more than half a second.
 
-  value      whole-job delta-E evaluations / s with the configuration and the
-             proposals already resident in HBM (the five launches of the trial
-             pipeline per step, CUDA events on the launching stream, L2 flushed
-             between steps).
-  e2e        the same metric through the plug-in with HOST buffers: every step
-             uploads the configuration (cell list rebuilt) and the proposals and reads
-             the delta-E array back (B200Calculator.set_configuration +
-             trial_delta_energies -> mcpyb_upload_host + mcpyb_trial_delta_e_host).
-  dropin     what an unmodified mcpy run gets today: one
-             calculator.get_potential_energy(atoms) per trial, sequential, host buffers
-             (the engine answers with its resident base + one single-launch delta).
-  stages_ms  device time of each launch of the pipeline (CUDA events between them).
-  roofline   the dominant kernel (the row sums) against the FP64 pipe: algorithmic flop
-             per launch / its own event-timed duration, over the DFMA rate measured in
-             this process (MEASURED_PEAKS.json has no FP64 figure).  Tensor cores are
-             not used: nothing on this path is a dense contraction.
+  value      whole-job dE evaluations / s over all ranks, configurations and proposals resident in HBM
+             (ResidentLadderShard + Engine.trial_delta_e_dev); K steps between two barriers, CUDA events on
+             the launching stream, max over ranks.  Inputs are larger than L2: 64 distinct proposal batches
+             (141 MB) and 80 MB of per-configuration stencil lists cycle through the 126 MB L2.
+  e2e        the same steps through the plug-in API with HOST buffers: every sweep uploads the 8
+             configurations from their ``Atoms`` (B200Calculator.set_configurations), the proposals from
+             page-locked numpy arrays, and reads the dE array back; every 10 sweeps the replicas -- unmodified
+             reference GrandCanonicalEnsemble objects -- go through ShardedReplicaExchange's exchange step
+             (host records, NCCL all_gather, pickled state transport).
+  driver     what an unmodified mcpy replica-exchange run gets: ShardedReplicaExchange.run() over the same
+             replicas, ONE trial per replica per batched get_potential_energies call, exchanges every 10 steps.
+  dropin     one calculator.get_potential_energy(atoms) per trial, sequential (a single GCMC chain).
+  roofline   the dominant kernel (the row sums of the trial pipeline) against the FP64 pipe: algorithmic flop
+             per launch / its event-timed duration over the DFMA rate measured in this process; further
+             kernels (cell-list build, EMT trial, free volume) under ``secondary.*.roofline``.
   cpu_baseline / --impl reference
              the reference's cost of one trial: one full-energy evaluation
-             (grand_canonical_ensemble.py:283-284) by the port of ASE's
-             LennardJones + NeighborList cost structure in oracle/lj.py, one process
-             per host core.  ASE itself (third-party, not vendored) is not installable
-             offline, hence kind = "port".
-
-With N > 1 (torchrun, one rank per GPU) every rank owns its own replica and its own
-proposal batch (weak scaling); there is no data-path collective.
+             (grand_canonical_ensemble.py:283-284) by ASE's LennardJones when a real ``ase`` is importable,
+             else by the port of its cost structure (oracle/lj.py::AseStyleLJ), one process per host core.
 """
 from __future__ import annotations
 
@@ -56,36 +56,105 @@ UNIT = 'dE evals/s'
 N_ATOMS = 2000
 RC = 3.0
 RHO = 0.6
+REPLICAS_PER_GPU = 8
+TRIALS_PER_REPLICA = 8192
+EXCHANGE_INTERVAL = 10
+MU_LADDER = (-3.0, -1.8)             # SURVEY 8d S4, over the whole ladder
+T_STAR = 2.0
 ALG_FLOP_PER_CANDIDATE = 17          # 3 sub + MIC + r2 + compare
 ALG_FLOP_PER_PAIR = 8                # extra work of an in-cutoff pair
 ALG_CANDIDATES_PER_SITE = 27 * RHO * RC ** 3      # 27-cell stencil at cell edge rc
 
 
-def workload_config(trials):
-    return {'workload': 'S2: 2000-atom LJ GCMC (eps=sigma=1, rc=3, rho*=0.6, cubic pbc), '
-                        f'{trials} proposals/step insert:delete:displace = 1:1:1',
-            'n_atoms': N_ATOMS, 'trials_per_step': trials, 'potential': 'ase.LennardJones(rc=3)',
-            'l2': 'flushed between timed steps (256 MiB write); working set itself is L2-resident'}
+def workload_config(args):
+    """One dictionary for both arms (the driver compares them)."""
+    trials = REPLICAS_PER_GPU * TRIALS_PER_REPLICA
+    return {'workload': f'S4 shard: {REPLICAS_PER_GPU} replicas per GPU x S2 (2000-atom LJ GCMC, eps=sigma=1, rc=3, '
+                        f'rho*=0.6, cubic pbc) on a mu ladder; sweep = {TRIALS_PER_REPLICA} proposals per replica '
+                        f'({trials} dE evals, insert:delete:displace = 1:1:1); step = {args.sweeps} sweeps + an '
+                        f'exchange attempt every {EXCHANGE_INTERVAL} sweeps',
+            'n_atoms': N_ATOMS, 'replicas_per_gpu': REPLICAS_PER_GPU, 'trials_per_sweep': trials,
+            'sweeps_per_step': args.sweeps, 'exchange_interval_sweeps': EXCHANGE_INTERVAL,
+            'potential': 'ase.LennardJones(rc=3)',
+            'parallelism': 'replica-sharded, 8 replicas per GPU; one all_gather of the replica records per '
+                           'exchange attempt, point-to-point transport of accepted cross-rank swaps',
+            'l2': f'inputs larger than L2: {args.batches} distinct proposal batches ({args.batches * 2.2:.0f} MB) and '
+                  f'80 MB of stencil lists cycle through the 126 MB L2',
+            'host_buffers': 'e2e: page-locked numpy arrays (mcpy_b200.pinned_copy); pageable arrays reported '
+                            'under e2e.pageable'}
+
+
+def local_configs(rank):
+    from mcpy_b200.utils import synthetic
+    return [synthetic.s2_lj(N_ATOMS, RC, RHO, seed=100 + rank * REPLICAS_PER_GPU + k) for k in range(REPLICAS_PER_GPU)]
+
+
+def proposal_batch(cfgs, seed):
+    """One sweep's proposals: TRIALS_PER_REPLICA per local replica, concatenated (``rep`` = replica of each trial)."""
+    from mcpy_b200.utils import synthetic
+    parts = [synthetic.trial_batch_periodic(c, TRIALS_PER_REPLICA, seed=seed * 64 + k) for k, c in enumerate(cfgs)]
+    old_off = np.concatenate([[0]] + [p['old_off'][1:] + sum(int(q['old_off'][-1]) for q in parts[:k])
+                                      for k, p in enumerate(parts)]).astype(np.int32)
+    new_off = np.concatenate([[0]] + [p['new_off'][1:] + sum(int(q['new_off'][-1]) for q in parts[:k])
+                                      for k, p in enumerate(parts)]).astype(np.int32)
+    return dict(rep=np.repeat(np.arange(len(cfgs), dtype=np.int32), TRIALS_PER_REPLICA),
+                old_off=old_off, new_off=new_off,
+                old_idx=np.concatenate([p['old_idx'] for p in parts]),
+                new_pos=np.concatenate([p['new_pos'] for p in parts]),
+                new_Z=np.concatenate([p['new_Z'] for p in parts]),
+                kind=np.concatenate([p['kind'] for p in parts]))
+
+
+def trial_config(cfgs, tb, t):
+    """(positions, numbers, cell, pbc) of the configuration after trial ``t`` of a batch."""
+    c = cfgs[int(tb['rep'][t])]
+    old = tb['old_idx'][tb['old_off'][t]:tb['old_off'][t + 1]]
+    ns, ne = tb['new_off'][t], tb['new_off'][t + 1]
+    keep = np.ones(len(c['positions']), bool)
+    keep[old] = False
+    return (np.concatenate([c['positions'][keep], tb['new_pos'][ns:ne]]),
+            np.concatenate([c['numbers'][keep], tb['new_Z'][ns:ne]]), c['cell'], c['pbc'])
 
 
 # --------------------------------------------------------------------------- CPU arm
-def _cpu_worker(args):
-    """One trial = one full-energy evaluation of the trial configuration."""
-    positions, cell, pbc = args
+def real_ase():
+    """The real ASE if one is importable (never the stand-in under baseline/ase_shim)."""
+    import importlib.util
+    spec = importlib.util.find_spec('ase')
+    if spec is None or 'ase_shim' in (spec.origin or ''):
+        return None
+    try:
+        import ase
+        from ase.calculators.lj import LennardJones  # noqa: F401
+        return ase
+    except Exception:
+        return None
+
+
+def _cpu_worker(task):
+    """One trial = one full-energy evaluation of the trial configuration, as compute_energy issues it."""
+    positions, numbers, cell, pbc, use_ase = task
+    if use_ase:
+        from ase import Atoms
+        from ase.calculators.lj import LennardJones
+        atoms = Atoms(numbers=numbers, positions=positions, cell=cell, pbc=pbc)
+        return LennardJones(sigma=1.0, epsilon=1.0, rc=RC).get_potential_energy(atoms)
     from oracle.lj import AseStyleLJ
     return AseStyleLJ(1.0, 1.0, RC).energy(positions, cell, pbc)
 
 
-def cpu_reference_rate(cfg, tb, n_sample, pool, cores):
-    from mcpy_b200.utils import synthetic
-    tasks = []
-    for t in range(n_sample):
-        p1, _ = synthetic.apply_trial(cfg, tb, t)
-        tasks.append((p1, cfg['cell'], cfg['pbc']))
+def cpu_reference_rate(cfgs, tb, n_sample, pool, cores, use_ase, first=0):
+    tasks = [trial_config(cfgs, tb, (first + t) % len(tb['rep'])) + (use_ase,) for t in range(n_sample)]
     t0 = time.perf_counter()
     pool.map(_cpu_worker, tasks, chunksize=max(1, n_sample // (cores * 2)))
     dt = time.perf_counter() - t0
     return n_sample / dt, dt
+
+
+def cpu_kind(use_ase):
+    return ('reference', 'ase.calculators.lj.LennardJones (real ASE)') if use_ase else \
+        ('port', 'oracle/lj.py::AseStyleLJ (port of ASE LennardJones + NeighborList: kd-tree neighbour-list '
+                 'rebuild + interpreted per-atom loop; ASE is not installable offline)')
 
 
 def run_reference(args):
@@ -93,28 +162,30 @@ def run_reference(args):
     if rank != 0:
         return 0
     import multiprocessing as mp
-    from mcpy_b200.utils import synthetic
-    cfg = synthetic.s2_lj(N_ATOMS, RC, RHO)
+    use_ase = real_ase() is not None
+    cfgs = local_configs(0)
     cores = os.cpu_count() or 1
     n_sample = 4 * cores
-    tb = synthetic.trial_batch(cfg, max(n_sample, 64), seed=7)
+    tb = proposal_batch(cfgs, seed=7)
     with mp.get_context('fork').Pool(cores) as pool:
-        for _ in range(args.warmup):
-            cpu_reference_rate(cfg, tb, min(cores, n_sample), pool, cores)
+        for w in range(args.warmup):
+            cpu_reference_rate(cfgs, tb, min(cores, n_sample), pool, cores, use_ase, first=17 * w)
         total_t, total_n = 0.0, 0
-        for _ in range(args.steps):
-            _, dt = cpu_reference_rate(cfg, tb, n_sample, pool, cores)
+        for k in range(args.steps):
+            # samples stride across the replicas of the shard
+            _, dt = cpu_reference_rate(cfgs, tb, n_sample, pool, cores, use_ase, first=k * 8209)
             total_t += dt
             total_n += n_sample
     value = total_n / total_t
-    sample = (f'{n_sample} of the batch proposals per step, each one full-energy evaluation '
-              f'(ASE-style neighbour-list rebuild + per-atom loop, numpy), {cores} processes')
+    kind, how = cpu_kind(use_ase)
+    sample = (f'{n_sample} proposals of the shard per step, each one full-energy evaluation of its 2000-atom trial '
+              f'configuration (the reference recomputes the total for every trial), {how}, {cores} processes')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_t / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': workload_config(args.trials),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'data': 'synthetic', 'config': workload_config(args),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -139,7 +210,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -177,13 +248,21 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def _profile_json(name):
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', name)))
+    except Exception:
+        return {}
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
+    from mcpy_b200 import pinned_copy, pinned_empty
     from mcpy_b200.calculators import B200Calculator
-    from mcpy_b200.utils import synthetic
+    from mcpy_b200.ensembles import ResidentLadderShard
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -200,154 +279,277 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce(x, op):
         if world == 1:
             return float(x)
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
+    max_over_ranks = lambda x: reduce(x, dist.ReduceOp.MAX) if world > 1 else float(x)   # noqa: E731
+    sum_over_ranks = lambda x: reduce(x, dist.ReduceOp.SUM) if world > 1 else float(x)   # noqa: E731
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    R = REPLICAS_PER_GPU
+    T = R * TRIALS_PER_REPLICA
+    SW, XI, NB, K, W = args.sweeps, EXCHANGE_INTERVAL, args.batches, args.steps, args.warmup
+    n_total = R * world
+    cfgs = local_configs(rank)
+    mus = np.linspace(MU_LADDER[0], MU_LADDER[1], n_total)
+    betas = np.full(n_total, 1.0 / T_STAR)
+    batches = [proposal_batch(cfgs, seed=1000 * rank + b) for b in range(NB)]
 
-    T = args.trials
-    cfg = synthetic.s2_lj(N_ATOMS, RC, RHO, seed=2 + rank)          # one replica per rank
-    tb = synthetic.trial_batch(cfg, T, seed=7 + 1000 * rank)
     calc = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=RC, device=local)
     eng = calc.engine
-    stream = torch.cuda.Stream(device=dev)          # a real (non-legacy) stream: events and the
+    stream = torch.cuda.Stream(device=dev)          # a real (non-legacy) stream: events, torch copies and the
     torch.cuda.set_stream(stream)                    # engine's launches share it
     eng.set_stream(stream.cuda_stream)
 
-    class _Cfg:                       # minimal ASE-shaped view for the plug-in calls
-        def __init__(self, c):
-            self.positions, self.numbers, self.cell, self.pbc = c['positions'], c['numbers'], c['cell'], c['pbc']
-    atoms = _Cfg(cfg)
-
-    # ---- resident inputs for the kernel-only number
-    calc.set_configuration(atoms)
-    d = {k: torch.from_numpy(np.ascontiguousarray(tb[k])).to(dev) for k in
-         ('old_off', 'old_idx', 'new_off', 'new_pos', 'new_Z')}
+    # ---- kernel-only: configurations and proposals resident in HBM
+    shard = ResidentLadderShard(eng, [(c['positions'], c['numbers'], c['cell'], c['pbc']) for c in cfgs],
+                                betas=betas, mus=mus, seed=31, rank=rank, world_size=world, device=f'cuda:{local}')
+    keys = ('rep', 'old_off', 'old_idx', 'new_off', 'new_pos', 'new_Z')
+    d_batches = [{k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev) for k in keys} for b in batches]
+    n_old = [int(b['old_off'][-1]) for b in batches]
+    n_new = [int(b['new_off'][-1]) for b in batches]
     d_dE = torch.empty(T, dtype=torch.float64, device=dev)
     d_pairs = torch.empty(T, dtype=torch.int32, device=dev)
-    n_old, n_new = int(tb['old_off'][-1]), int(tb['new_off'][-1])
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def launch(pairs_ptr=0):
-        eng.trial_delta_e_dev(T, 0, d['old_off'].data_ptr(), d['old_idx'].data_ptr(),
+    def sweep(b, pairs_ptr=0):
+        d = d_batches[b]
+        eng.trial_delta_e_dev(T, d['rep'].data_ptr(), d['old_off'].data_ptr(), d['old_idx'].data_ptr(),
                               d['new_off'].data_ptr(), d['new_pos'].data_ptr(), d['new_Z'].data_ptr(),
-                              n_old, n_new, d_dE.data_ptr(), pairs_ptr)
+                              n_old[b], n_new[b], d_dE.data_ptr(), pairs_ptr)
 
-    launch(d_pairs.data_ptr())
+    # sanity before anything is timed: against the CPU oracle on a few trials, and bit-reproducible
+    sweep(0, d_pairs.data_ptr())
     torch.cuda.synchronize()
-    pairs_per_step = int(d_pairs.sum().item())
+    pairs_per_sweep = int(d_pairs.sum().item())
     dE_ref = d_dE.clone()
+    if rank == 0:
+        from oracle import cfast
+        h = dE_ref.cpu().numpy()
+        for t in (0, T // 3 + 1, T - 1):
+            p1, _, cell, pbc = trial_config(cfgs, batches[0], t)
+            c0 = cfgs[int(batches[0]['rep'][t])]
+            e0 = cfast.lj_energy(c0['positions'], cell, pbc, 1.0, 1.0, RC)
+            ref = cfast.lj_energy(p1, cell, pbc, 1.0, 1.0, RC) - e0
+            assert abs(h[t] - ref) <= 1e-10 * max(1.0, abs(ref)) + 1e-13 * abs(e0), (t, h[t], ref)
+    sweep(0)
+    torch.cuda.synchronize()
+    assert torch.equal(d_dE, dE_ref), 'trial kernel is not deterministic'
 
-    for _ in range(args.warmup):
-        flush.zero_()
-        launch()
+    counter = [0]
+
+    def step():
+        for s in range(SW):
+            sweep(counter[0] % NB)
+            counter[0] += 1
+            if (s + 1) % XI == 0:
+                shard.attempt_exchanges()
+
+    for _ in range(W):
+        step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    comm = shard.comm
+    c0, t0c, g0, x0 = comm.collective_seconds, comm.transport_seconds, comm.gathers, comm.transports
+    rounds0, swaps0 = shard.rounds, sum(1 for *_, ok in shard.swap_log if ok)
     barrier()
     launches0 = eng.launch_count
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    for k in range(args.steps):
-        flush.zero_()                                 # evict the working set from L2
-        starts[k].record(stream)
-        launch()
-        ends[k].record(stream)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev[0].record(stream)
+    for k in range(K):
+        step()
+        ev[k + 1].record(stream)
     barrier()
     gpu_launches = eng.launch_count - launches0
-    # per-stage device times of the same step (separate, untimed pass: events between the launches)
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[K]))
+    value = world * T * SW * K / (total_ms * 1e-3)
+    ms_per_step = total_ms / K
+    rounds = shard.rounds - rounds0
+    exchange = {
+        'attempts': rounds, 'accepted_swaps': sum(1 for *_, ok in shard.swap_log if ok) - swaps0,
+        'collective_us_per_exchange': 1e6 * (comm.collective_seconds - c0) / max(1, comm.gathers - g0) if world > 1 else 0.0,
+        'transport_us_per_cross_rank_round': 1e6 * (comm.transport_seconds - t0c) / max(1, comm.transports - x0) if world > 1 else 0.0,
+        'cross_rank_transport_rounds': comm.transports - x0,
+    }
+    # an exchange attempt on its own (host wall clock incl. the rebuild of the cell lists), untimed by the metric
+    torch.cuda.synchronize()
+    tx = time.perf_counter()
+    for _ in range(8):
+        shard.attempt_exchanges()
+    torch.cuda.synchronize()
+    exchange['exchange_us_per_attempt'] = 1e6 * (time.perf_counter() - tx) / 8
+    exchange['share_of_step'] = exchange['exchange_us_per_attempt'] * (SW // XI) / (ms_per_step * 1e3)
+    exchange['collective_share_of_step'] = exchange['collective_us_per_exchange'] * (SW // XI) / (ms_per_step * 1e3)
+
+    # per-stage device times of a sweep (separate, untimed pass: events between the launches)
     eng.stage_timing(True)
-    for _ in range(max(3, args.steps // 2)):
-        flush.zero_()
-        launch()
+    for b in range(max(8, min(NB, 24))):
+        sweep(b % NB)
         stage_ms, stage_calls = eng.stage_timing(True)
     eng.stage_timing(False)
-    kernel_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    kernel_ms = max_over_ranks(kernel_ms)
-    assert torch.equal(d_dE, dE_ref), 'trial kernel is not deterministic'
-    value = world * T * args.steps / (kernel_ms * 1e-3)
-    ms_per_step = kernel_ms / args.steps
+    sweep(0)
+    torch.cuda.synchronize()
+    if shard.rounds == rounds0 + 8 and False:
+        pass
 
     # ---- end to end through the plug-in with host buffers
-    # the step's inputs and its result live in page-locked host arrays (mcpy_b200.pinned_copy): the engine
-    # hands them to the copy engine as they are; pageable numpy arrays would be staged first ('e2e_pageable')
-    from mcpy_b200 import pinned_copy, pinned_empty
-    trials_pageable = {k: np.ascontiguousarray(tb[k]) for k in ('old_off', 'old_idx', 'new_off', 'new_pos', 'new_Z')}
-    trials_host = {k: pinned_copy(v) for k, v in trials_pageable.items()}
+    from baseline import refpath
+    ase_kind, mcpy_root = refpath.enable()
+    NBH = min(NB, 8)
+    host_pageable = [{k: np.ascontiguousarray(batches[b][k]) for k in keys} for b in range(NBH)]
+    host_pinned = [{k: pinned_copy(v) for k, v in hb.items()} for hb in host_pageable]
     dE_host = pinned_empty(T, np.float64)
+    re = None
+    e2e_note = None
+    try:
+        from ase import Atoms
+        from mcpy.cell import Cell
+        from mcpy.ensembles import GrandCanonicalEnsemble
+        from mcpy.moves import DeletionMove, DisplacementMove, InsertionMove, MoveSelector
+        from mcpy_b200.ensembles import ShardedReplicaExchange
 
-    def e2e_step(tr=trials_host, out=dE_host):
-        calc.set_configuration(atoms)                                 # H2D config + cell list
-        return eng.trial_delta_e(tr['old_off'], tr['old_idx'], tr['new_off'],
-                                 tr['new_pos'], tr['new_Z'], out=out)            # H2D trials, D2H dE
+        def factory(T=None, mu=None, rank=0):
+            c = local_configs(rank // R)[rank % R]
+            atoms = Atoms(numbers=c['numbers'], positions=c['positions'].copy(), cell=c['cell'], pbc=c['pbc'])
+            cell = Cell(atoms, seed=500 + rank)
+            moves = [InsertionMove(cell, ['H'], 600 + rank), DeletionMove(cell, ['H'], 700 + rank),
+                     DisplacementMove(['H'], 800 + rank, max_displacement=0.3)]
+            ms = MoveSelector([1, 1, 1], moves, seed=900 + rank, n_moves=1)
+            return GrandCanonicalEnsemble(atoms=atoms, cells=[cell], units_type='LJ', calculator=calc, mu=mu,
+                                          species=['H'], temperature=T_STAR, move_selector=ms,
+                                          random_seed=1000 + rank, traj_file=None, outfile=None)
+        re = ShardedReplicaExchange(factory, calc, mus=[{'H': float(m)} for m in mus], gcmc_steps=0,
+                                    exchange_interval=XI, seed=31, rank=rank, world_size=world,
+                                    device=f'cuda:{local}', outfile=None, global_minimum_file=None)
+        re._rebatch_initial_energies()
+        replicas_atoms = lambda: [r.atoms for r in re.replicas]                      # noqa: E731
+    except ImportError as exc:                    # the reference is not installed: no host-side exchange step
+        e2e_note = f'exchange step skipped: {exc}'
 
-    for _ in range(args.warmup):
-        out = e2e_step()
-    assert np.array_equal(out, dE_ref.cpu().numpy())
+        class _A:
+            pass
+        fixed = []
+        for c in cfgs:
+            a = _A()
+            a.positions, a.numbers, a.cell, a.pbc = c['positions'], c['numbers'], c['cell'], c['pbc']
+            fixed.append(a)
+        replicas_atoms = lambda: fixed                                                # noqa: E731
+
+    def e2e_sweep(hb, out):
+        calc.set_configurations(replicas_atoms())                                     # H2D configurations + cell lists
+        return eng.trial_delta_e(hb['old_off'], hb['old_idx'], hb['new_off'], hb['new_pos'], hb['new_Z'],
+                                 rep=hb['rep'], out=out)                              # H2D proposals, D2H dE
+
+    e2e_counter = [0]
+
+    def e2e_step(bufs, out):
+        for s in range(SW):
+            e2e_sweep(bufs[e2e_counter[0] % NBH], out)
+            e2e_counter[0] += 1
+            if re is not None and (s + 1) % XI == 0:
+                re._attempt_exchanges()
+
+    out = e2e_sweep(host_pinned[0], dE_host)
+    assert np.array_equal(out, dE_ref.cpu().numpy()), 'host-buffer path disagrees with the device path'
+    for _ in range(min(W, 3)):
+        e2e_step(host_pinned, dE_host)
+    if re is not None:
+        rc0, rt0, rg0 = re.comm.collective_seconds, re.comm.transport_seconds, re.comm.gathers
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    for _ in range(K):
+        e2e_step(host_pinned, dE_host)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = world * T * args.steps / e2e_s
-    # the same call with ordinary (pageable) numpy arrays, for the record
-    for _ in range(args.warmup):
-        out = e2e_step(trials_pageable, None)
-    assert np.array_equal(out, dE_ref.cpu().numpy())
+    e2e_value = world * T * SW * K / e2e_s
+    e2e_exchange = None
+    if re is not None:
+        e2e_exchange = {'attempts': K * (SW // XI),
+                        'collective_us_per_exchange': 1e6 * (re.comm.collective_seconds - rc0) / max(1, re.comm.gathers - rg0),
+                        'transport_s_total': re.comm.transport_seconds - rt0}
+    # the same sweeps with ordinary (pageable) numpy arrays, a shorter sample
+    KP = max(2, K // 5)
+    e2e_step(host_pageable, None)
+    barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step(trials_pageable, None)
+    for _ in range(KP):
+        e2e_step(host_pageable, None)
     torch.cuda.synchronize()
     e2e_pageable_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    h2d = (N_ATOMS * (24 + 4) + 256) + sum(int(v.nbytes) for v in trials_host.values()) + 4 * T
-    d2h = 8 * T
+    h2d_sweep = R * (N_ATOMS * (24 + 4)) + 256 + sum(int(v.nbytes) for v in host_pinned[0].values())
+    d2h_sweep = 8 * T
 
-    # ---- drop-in chain: one get_potential_energy(atoms) per trial, sequential
-    n_chain = min(T, args.chain)
-    chain_cfgs = [synthetic.apply_trial(cfg, tb, t) for t in range(min(n_chain, 256))]
+    # ---- driver mode: the unmodified replica-exchange loop, one trial per replica per batched call
+    driver = None
+    if re is not None and not args.no_driver:
+        n_steps = args.driver_steps
+        for r in re.replicas:
+            r.initialize_run()
+        re._rebatch_initial_energies()
+        g0, c0d, t0d, s0 = re.comm.gathers, re.comm.collective_seconds, re.comm.transport_seconds, re.comm.transports
+        paths0 = list(calc.path_counts)
+        barrier()
+        t0 = time.perf_counter()
+        for st in range(n_steps):
+            re._batched_gcmc_step()
+            if st > 0 and st % XI == 0:
+                re._attempt_exchanges()
+            re._re_step += 1
+        torch.cuda.synchronize()
+        drv_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        for r in re.replicas:
+            r.finalize_run()
+        driver = {'value': world * R * n_steps / drv_s, 'unit': 'replica trial-move dE evals/s',
+                  'steps': n_steps, 'ms_per_batched_call': 1e3 * drv_s / n_steps,
+                  'collective_us_per_exchange': 1e6 * (re.comm.collective_seconds - c0d) / max(1, re.comm.gathers - g0),
+                  'transport_us_per_cross_rank_swap': 1e6 * (re.comm.transport_seconds - t0d) / max(1, re.comm.transports - s0),
+                  'exchange_attempts': re.comm.gathers - g0 if world > 1 else (n_steps - 1) // XI,
+                  'paths_full_incremental_identical': [a - b for a, b in zip(calc.path_counts, paths0)],
+                  'api': 'ShardedReplicaExchange (subclass of the unmodified BatchedReplicaExchange) over unmodified '
+                         'GrandCanonicalEnsemble replicas + B200Calculator.get_potential_energies; host time is the '
+                         "reference's own Python (snapshots, moves, acceptance, wrap)"}
 
-    class _A:
+    # ---- drop-in chain: one get_potential_energy(atoms) per trial, sequential (a single GCMC run)
+    n_chain = args.chain
+    chain_cfgs = [trial_config(cfgs[:1], {k: (v[:TRIALS_PER_REPLICA + 1] if k.endswith('off') else v) for k, v in batches[0].items()}, t)
+                  for t in range(min(n_chain, 256))]
+
+    class _A1:
         pass
-    a = _A()
-    a.cell, a.pbc = cfg['cell'], cfg['pbc']
-    for p1, z1 in chain_cfgs[:8]:
+    a = _A1()
+    a.cell, a.pbc = cfgs[0]['cell'], cfgs[0]['pbc']
+    calc.path_counts = [0, 0, 0]
+    for p1, z1, _, _ in chain_cfgs[:8]:
         a.positions, a.numbers = p1, z1
         calc.get_potential_energy(a)
     barrier()
     t0 = time.perf_counter()
     for i in range(n_chain):
-        a.positions, a.numbers = chain_cfgs[i % len(chain_cfgs)]
+        a.positions, a.numbers = chain_cfgs[i % len(chain_cfgs)][:2]
         calc.get_potential_energy(a)
     chain_s = max_over_ranks(time.perf_counter() - t0)
     dropin_value = world * n_chain / chain_s
 
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- secondary workloads of the same path (rank 0 only, untimed by the driver's metric):
-    # EMT energies / trial dE on S3 (Ag140 + O) and S5 (~10.8k-atom CuPd + CO), free volume on both
+    # ---- secondary workloads of the same path (rank 0 only, untimed by the driver's metric)
     extra = {}
     if rank == 0 and not args.no_extra:
         extra = secondary_workloads(local)
 
     # ---- roofline of the trial kernel (FP64 pipe)
-    sites = n_old + n_new
-    alg_flop = sites * ALG_CANDIDATES_PER_SITE * ALG_FLOP_PER_CANDIDATE + pairs_per_step * ALG_FLOP_PER_PAIR
+    sites = n_old[0] + n_new[0]
+    alg_flop = sites * ALG_CANDIDATES_PER_SITE * ALG_FLOP_PER_CANDIDATE + pairs_per_sweep * ALG_FLOP_PER_PAIR
     peak = eng.fp64_peak_tflops()
     rows_ms = stage_ms['row_sums']
     achieved = alg_flop / (rows_ms * 1e-3) / 1e12
-    pair_rate = sum_over_ranks(pairs_per_step) / (ms_per_step * 1e-3)
+    pair_rate = sum_over_ranks(pairs_per_sweep) * SW / (ms_per_step * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -357,39 +559,38 @@ def run_b200(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         import multiprocessing as mp
+        use_ase = real_ase() is not None
         cores = os.cpu_count() or 1
         n_sample = 4 * cores
         with mp.get_context('fork').Pool(cores) as pool:
-            cpu_reference_rate(cfg, tb, cores, pool, cores)          # warm the workers
-            rate, dt = cpu_reference_rate(cfg, tb, n_sample, pool, cores)
+            cpu_reference_rate(cfgs, batches[0], cores, pool, cores, use_ase)          # warm the workers
+            rate, dt = cpu_reference_rate(cfgs, batches[0], n_sample, pool, cores, use_ase, first=8209)
+        kind, how = cpu_kind(use_ase)
         cpu_baseline = {
-            'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': f'{n_sample} of the batch proposals, one full-energy evaluation each '
-                      f'(ASE-style neighbour-list rebuild + per-atom loop, numpy), {cores} processes, '
-                      f'{dt:.1f} s wall'}
+            'value': rate, 'unit': UNIT, 'cores': cores, 'kind': kind,
+            'sample': f'{n_sample} proposals of the shard, one full-energy evaluation each ({how}), '
+                      f'{cores} processes, {dt:.1f} s wall'}
 
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get('lj_trial_rows_block_kernel_dram_bytes_per_launch')
-        except Exception:
-            traffic = None
-
+    prof = _profile_json('traffic.json')
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K,
+        'warmup': W, 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': dict(workload_config(T), replicas_per_gpu=1,
-                       parallelism=f'replica-parallel x{world}, no data-path collective'),
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'api': 'B200Calculator.set_configuration + Engine.trial_delta_e '
-                       '(mcpyb_upload_host + mcpyb_trial_delta_e_host), host numpy arrays in page-locked memory '
-                       '(mcpy_b200.pinned_copy / pinned_empty)',
-                'ms_per_step': 1e3 * e2e_s / args.steps,
-                'pageable': {'value': world * T * args.steps / e2e_pageable_s,
-                             'ms_per_step': 1e3 * e2e_pageable_s / args.steps,
+        'config': workload_config(args),
+        'ms_per_step_median_rank0': float(np.median(step_ms)), 'ms_per_sweep': ms_per_step / SW,
+        'timed_region_s': total_ms * 1e-3,
+        'exchange': exchange,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_sweep * SW, 'd2h_bytes_per_step': d2h_sweep * SW,
+                'api': 'B200Calculator.set_configurations(list of Atoms) + Engine.trial_delta_e (mcpyb_upload_host + '
+                       'mcpyb_trial_delta_e_host) per sweep, proposals and results in page-locked numpy arrays '
+                       '(mcpy_b200.pinned_copy / pinned_empty); ShardedReplicaExchange._attempt_exchanges over the '
+                       'unmodified GrandCanonicalEnsemble replicas every 10 sweeps',
+                'ms_per_step': 1e3 * e2e_s / K, 'ms_per_sweep': 1e3 * e2e_s / (K * SW), 'timed_region_s': e2e_s,
+                'exchange': e2e_exchange, 'note': e2e_note,
+                'pageable': {'value': world * T * SW * KP / e2e_pageable_s,
+                             'ms_per_sweep': 1e3 * e2e_pageable_s / (KP * SW), 'steps': KP,
                              'note': 'same calls with ordinary numpy arrays: staged through pinned memory inside the engine'}},
+        'driver': driver,
         'dropin': {'value': dropin_value, 'unit': UNIT, 'calls': n_chain,
                    'api': 'calculator.get_potential_energy(atoms) per trial, sequential '
                           '(mcpyb_tracked_energy_host: resident base + one delta; the trial rides in the '
@@ -399,20 +600,23 @@ def run_b200(args):
                    'us_per_call': 1e6 * chain_s / n_chain},
         'stages_ms': {k: round(v, 5) for k, v in stage_ms.items()},
         'pair_interactions_per_s': pair_rate,
-        'pairs_per_step': pairs_per_step,
+        'pairs_per_sweep': pairs_per_sweep,
         'gpu_launches': int(gpu_launches),
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                     'frac': achieved / peak if peak else None, 'traffic': traffic,
-                     'kernel': 'lj_trial_rows_block_kernel<4,12>',
-                     'kernel_ms': rows_ms, 'kernel_share_of_step': rows_ms / sum(stage_ms.values()),
+                     'frac': achieved / peak if peak else None,
+                     'traffic': prof.get('lj_trial_rows_block_kernel_dram_bytes_per_launch'),
+                     'pipe_fp64_pct': prof.get('lj_trial_rows_block_kernel_pipe_fp64_pct'),
+                     'kernel': 'lj_trial_rows_block_kernel',
+                     'kernel_ms': rows_ms, 'kernel_share_of_sweep': rows_ms / sum(stage_ms.values()),
                      'algorithmic_flop_per_launch': alg_flop,
-                     'step_achieved': alg_flop / (ms_per_step * 1e-3) / 1e12,
+                     'step_achieved': alg_flop * SW / (ms_per_step * 1e-3) / 1e12,
                      'peak_source': 'measured here: DFMA microbenchmark (mcpyb_fp64_peak_tflops); '
                                     'MEASURED_PEAKS.json holds only HBM and bf16 figures',
-                     'note': 'HBM is not the bound: the 64 KB configuration is L1/L2 resident; algorithmic flop '
+                     'note': 'HBM is not the bound: each 64 KB configuration is L1/L2 resident; algorithmic flop '
                              'follow SURVEY 8d (27-cell stencil at cell edge rc: 437 candidates x 17 flop per site '
-                             '+ 8 per in-cutoff pair); the kernel itself visits ~200 candidates per site after '
-                             'pruning, see profiles/ for the FP64-pipe counters'},
+                             '+ 8 per in-cutoff pair); the kernel itself visits fewer candidates after pruning -- '
+                             'pipe_fp64_pct is the executed FP64-pipe utilisation of the committed ncu capture '
+                             '(profiles/)'},
         'clocks': clocks,
     }
     if cpu_baseline is not None:
@@ -506,20 +710,20 @@ def secondary_workloads(device):
             a.cell, a.pbc = base[k]['cell'], base[k]['pbc']
             reps.append(a)
         return reps
-    batches = [batch_of(t) for t in range(8)]
+    bts = [batch_of(t) for t in range(8)]
     res = {}
     for label, inc in (('full_recompute', False), ('resident_bases', True)):
         calc = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=RC, device=device, incremental=inc)
-        for bt in batches[:2]:
+        for bt in bts[:2]:
             calc.get_potential_energies(bt)
         t0 = time.perf_counter()
         for rep_ in range(3):
-            for bt in batches:
+            for bt in bts:
                 res[label + '_E'] = calc.get_potential_energies(bt)
-        res[label] = (time.perf_counter() - t0) / (3 * len(batches))
+        res[label] = (time.perf_counter() - t0) / (3 * len(bts))
         if inc:
             res['paths'] = list(calc.path_counts)
-            t_1 = _time(lambda: [calc.get_potential_energy(a) for a in batches[0][:8]], 3) / 8
+            t_1 = _time(lambda: [calc.get_potential_energy(a) for a in bts[0][:8]], 3) / 8
         calc.engine.close()
     scale = np.maximum(1.0, np.abs(res['full_recompute_E']))
     assert np.all(np.abs(res['resident_bases_E'] - res['full_recompute_E']) <= 1e-10 * scale)
@@ -553,20 +757,24 @@ def secondary_workloads(device):
     return out
 
 
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--trials', type=int, default=65536, help='proposals per step')
+    ap.add_argument('--sweeps', type=int, default=320, help='sweeps (batched launches of 65 536 proposals) per step')
+    ap.add_argument('--batches', type=int, default=64, help='distinct proposal batches cycled through (141 MB at 64)')
     ap.add_argument('--chain', type=int, default=2000, help='sequential drop-in calls to time')
+    ap.add_argument('--driver-steps', type=int, default=60, help='steps of the unmodified replica-exchange loop to time')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-driver', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary EMT / free-volume numbers')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3
+    if args.sweeps % EXCHANGE_INTERVAL:
+        args.sweeps += EXCHANGE_INTERVAL - args.sweeps % EXCHANGE_INTERVAL
     if args.impl == 'reference':
         return run_reference(args)
     return run_b200(args)

@@ -48,21 +48,11 @@ def test_insertion_moves_follow_the_reference_stream(lj_engine):
     """tests/golden/insertion_trace.npz was recorded from the UNMODIFIED InsertionMove /
     MoleculeInsertionMove; same seeds -> same inserted positions and the same generator states."""
     from ase import Atoms
-    from mcpy_b200.cell.b200_cells import _B200CellBase
+    from mcpy.cell import Cell
     from mcpy_b200.moves import B200InsertionMove, B200MoleculeInsertionMove
 
-    class BoxCell(_B200CellBase):                 # mcpy.cell.Cell: whole periodic box
-        def __init__(self, atoms, species_radii, seed):
-            self.dimensions = np.array(atoms.cell, dtype=float).reshape(3, 3)
-            self.species_radii = species_radii
-            self.volume = float(abs(np.linalg.det(self.dimensions)))
-            self._rng = np.random.default_rng(seed)
-
-        def get_random_point(self):
-            return self._rng.random(3) @ self.dimensions
-
-        def get_atoms_specie_inside_cell(self, atoms, species):
-            return np.where(np.isin(atoms.get_chemical_symbols(), species))[0]
+    def BoxCell(atoms, species_radii, seed):       # the reference's whole-box cell
+        return Cell(atoms, species_radii=species_radii, seed=seed)
 
     d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'insertion_trace.npz'))
     lj_engine.set_lj(1.0, 1.0, 3.0)
