@@ -7,18 +7,18 @@
 Workload, identical at every N (weak scaling): the block of BASELINE.json configs[3] ("64 replicas x
 ~2 000-atom LJ, sharded over 8 B200": SURVEY.md 8d "S4") that one GPU owns -- 8 replicas of configs[1]
 ("S2": 2 000-atom Lennard-Jones fluid, eps = sigma = 1, rc = 3, rho* = 0.6, periodic cubic box) on a
-chemical-potential ladder.  One SWEEP scores 8 192 pre-generated GCMC proposals per replica (65 536 dE
+chemical-potential ladder.  One SWEEP scores 65 536 pre-generated GCMC proposals per replica (524 288 dE
 evaluations: insertions, deletions, displacements 1:1:1) against the rank's resident configurations in ONE
 batched launch of the trial pipeline.  Every 10 sweeps the ladder attempts an exchange: the records
 [E, beta, N, mu, Lambda, ...] of all replicas are all_gathered (NCCL over NVLink; the path's only collective),
 every rank takes the same Metropolis decisions, accepted pairs swap configurations -- inside a rank by
 relabelling device rows, across ranks point to point -- and the changed cell lists are rebuilt.  One STEP =
-`--sweeps` sweeps (default 320) and their exchange attempts, so that K = 20 steps time more than half a second.
+`--sweeps` sweeps (default 80) and their exchange attempts, so that K = 20 steps time more than half a second.
 
   value      whole-job dE evaluations / s over all ranks, configurations and proposals resident in HBM
              (ResidentLadderShard + Engine.trial_delta_e_dev); K steps between two barriers, CUDA events on
-             the launching stream, max over ranks.  Inputs are larger than L2: 64 distinct proposal batches
-             (141 MB) and 80 MB of per-configuration stencil lists cycle through the 126 MB L2.
+             the launching stream, max over ranks.  Inputs are larger than L2: 16 distinct proposal batches
+             (18 MB each) and 35 MB of per-configuration stencil lists cycle through the 126 MB L2.
   e2e        the same steps through the plug-in API with HOST buffers: every sweep uploads the 8
              configurations from their ``Atoms`` (B200Calculator.set_configurations), the proposals from
              page-locked numpy arrays, and reads the dE array back; every 10 sweeps the replicas -- unmodified
@@ -57,7 +57,7 @@ N_ATOMS = 2000
 RC = 3.0
 RHO = 0.6
 REPLICAS_PER_GPU = 8
-TRIALS_PER_REPLICA = 8192
+TRIALS_PER_REPLICA = 65536
 EXCHANGE_INTERVAL = 10
 MU_LADDER = (-3.0, -1.8)             # SURVEY 8d S4, over the whole ladder
 T_STAR = 2.0
@@ -78,8 +78,9 @@ def workload_config(args):
             'potential': 'ase.LennardJones(rc=3)',
             'parallelism': 'replica-sharded, 8 replicas per GPU; one all_gather of the replica records per '
                            'exchange attempt, point-to-point transport of accepted cross-rank swaps',
-            'l2': f'inputs larger than L2: {args.batches} distinct proposal batches ({args.batches * 2.2:.0f} MB) and '
-                  f'80 MB of stencil lists cycle through the 126 MB L2',
+            'l2': f'inputs larger than L2: {args.batches} distinct proposal batches '
+                  f'({args.batches * 2.2 * TRIALS_PER_REPLICA / 8192:.0f} MB) and 35 MB of stencil lists cycle through the '
+                  f'126 MB L2',
             'host_buffers': 'e2e: page-locked numpy arrays (mcpy_b200.pinned_copy); pageable arrays reported '
                             'under e2e.pageable'}
 
@@ -398,7 +399,7 @@ def run_b200(args):
     # ---- end to end through the plug-in with host buffers
     from baseline import refpath
     ase_kind, mcpy_root = refpath.enable()
-    NBH = min(NB, 8)
+    NBH = min(NB, 4)
     host_pageable = [{k: np.ascontiguousarray(batches[b][k]) for k in keys} for b in range(NBH)]
     host_pinned = [{k: pinned_copy(v) for k, v in hb.items()} for hb in host_pageable]
     dE_host = pinned_empty(T, np.float64)
@@ -604,9 +605,9 @@ def run_b200(args):
         'gpu_launches': int(gpu_launches),
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': achieved / peak if peak else None,
-                     'traffic': prof.get('lj_trial_rows_block_kernel_dram_bytes_per_launch'),
-                     'pipe_fp64_pct': prof.get('lj_trial_rows_block_kernel_pipe_fp64_pct'),
-                     'kernel': 'lj_trial_rows_block_kernel',
+                     'traffic': prof.get('lj_trial_rows_warp_kernel_dram_bytes_per_launch'),
+                     'pipe_fp64_pct': prof.get('lj_trial_rows_warp_kernel_pipe_fp64_pct'),
+                     'kernel': 'lj_trial_rows_warp_kernel',
                      'kernel_ms': rows_ms, 'kernel_share_of_sweep': rows_ms / sum(stage_ms.values()),
                      'algorithmic_flop_per_launch': alg_flop,
                      'step_achieved': alg_flop * SW / (ms_per_step * 1e-3) / 1e12,
@@ -763,8 +764,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--sweeps', type=int, default=320, help='sweeps (batched launches of 65 536 proposals) per step')
-    ap.add_argument('--batches', type=int, default=64, help='distinct proposal batches cycled through (141 MB at 64)')
+    ap.add_argument('--sweeps', type=int, default=80, help='sweeps (batched launches of 8 x 65 536 proposals) per step')
+    ap.add_argument('--batches', type=int, default=16, help='distinct proposal batches cycled through (18 MB each)')
     ap.add_argument('--chain', type=int, default=2000, help='sequential drop-in calls to time')
     ap.add_argument('--driver-steps', type=int, default=60, help='steps of the unmodified replica-exchange loop to time')
     ap.add_argument('--no-cpu-baseline', action='store_true')

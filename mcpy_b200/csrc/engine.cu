@@ -22,6 +22,7 @@
 #include "lj_kernels.cuh"
 #include "site_kernels.cuh"
 #include "rows_block.cuh"
+#include "rows_warp.cuh"
 #include "emt_kernels.cuh"
 #include "free_volume.cuh"
 #include "pcg64.cuh"
@@ -188,8 +189,12 @@ struct mcpyb_engine {
     //   MCPYB_PDL=0        ordinary stream-ordered launches instead of programmatic dependent launch
     //   MCPYB_RB_SLICES=n  candidate-list slices per work item (1..8)
     //   MCPYB_EXPAND=0     no per-configuration stencil lists (every work item stages from the cell list)
+    //   MCPYB_ROWS=block   the CTA-per-cell row-sum kernel of round 1 instead of the warp-per-item one
     bool use_pdl = true;
     bool use_expand = true;
+    bool use_warp_rows = true;            // MCPYB_ROWS=block: the round-1 CTA-per-cell row-sum kernel (A/B runs only)
+    int rw_minb = RW_MIN_BLOCKS;          // MCPYB_RW_MINB=4|5|6: resident CTAs per SM the warp row-sum kernel is built for
+    int l2_persist_mb = 0;                // MCPYB_L2PERSIST=<MB>: keep the stencil lists in a persisting L2 window
     // stencil lists of the resident batch (rows_block.cuh): built when a SECOND trial batch is scored against
     // the same resident configuration -- one batch per upload (the end-to-end pattern) does not amortise them
     bool exp_valid = false;
@@ -275,6 +280,8 @@ struct mcpyb_engine {
     DevBuf<double4> tw_pos, tw_spos;
     DevBuf<int4> tw_meta;
     DevBuf<int2> tw_items;
+    DevBuf<int4> tw_items4;
+    DevBuf<unsigned long long> tw_chain;
     DevBuf<double> tw_E;
 
     // neighbour list scratch
@@ -549,6 +556,12 @@ int mcpyb_create(int device, mcpyb_engine** out) {
     { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) e->num_sms = sms; }
     if (const char* v = getenv("MCPYB_PDL")) e->use_pdl = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_EXPAND")) e->use_expand = atoi(v) != 0;
+    if (const char* v = getenv("MCPYB_ROWS")) e->use_warp_rows = strcmp(v, "block") != 0;
+    if (const char* v = getenv("MCPYB_RW_MINB")) { const int n = atoi(v); if (n >= 4 && n <= 6) e->rw_minb = n; }
+    if (const char* v = getenv("MCPYB_L2PERSIST")) {
+        e->l2_persist_mb = atoi(v);
+        if (e->l2_persist_mb > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)e->l2_persist_mb << 20);
+    }
     if (const char* v = getenv("MCPYB_RB_SLICES")) { const int n = atoi(v); if (n >= 1 && n <= 8) e->rb_slices = n; }
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete e;
@@ -1033,9 +1046,14 @@ static int prepare_rows_work(mcpyb_engine* e, int nsites, int n_old_total, int n
     const size_t ns = (size_t)(nsites > 0 ? nsites : 1), nbp = (size_t)w.nbins + 1;
     // every path cuts a cell's candidate list into the same slices, so a trial's bits do not depend on
     // the batch it arrives in
-    w.nplanes = e->rb_slices;
-    w.item_slices = e->rb_slices;            // one work item walks all slices of its cell (one header for both)
-    w.item_shift = RB_SITES_SHIFT;
+    if (e->use_warp_rows) {
+        // one folded row sum per site: the four interleaved classes of rows_warp.cuh
+        w.nplanes = 1; w.item_slices = 1; w.item_shift = RW_SITES_SHIFT;
+    } else {
+        w.nplanes = e->rb_slices;
+        w.item_slices = e->rb_slices;        // one work item walks all slices of its cell (one header for both)
+        w.item_shift = RB_SITES_SHIFT;
+    }
     const size_t nsp = ns * (size_t)w.nplanes;
     CK(e->tw_int.reserve(2 * ns + nsp + 4), "cudaMalloc trial work");
     CK(e->tw_E.reserve(nsp), "cudaMalloc trial work");
@@ -1061,7 +1079,8 @@ static int stencil_lists(mcpyb_engine* e, bool few_sites, StencilLists* xl) {
     memset(xl, 0, sizeof *xl);
     if (!e->use_expand || e->pot_kind != POT_LJ || !e->have_batch || e->total_atoms <= 0) return MCPYB_OK;
     if (few_sites && e->total_atoms > 20000) return MCPYB_OK;
-    if (!e->exp_valid && ++e->exp_batches < 2) return MCPYB_OK;
+    // the warp row-sum kernel reads nothing but the lists; the single-launch kernels wait for a second call
+    if (!e->exp_valid && ++e->exp_batches < 2 && (few_sites || !e->use_warp_rows)) return MCPYB_OK;
     const int nbins = e->R * e->max_cells;
     long long cap = (long long)e->total_atoms * 128;              // (2m+1)^3 = 125 cells see each atom at m = 2
     if (cap > (32LL << 20)) cap = 32LL << 20;                      // 1.3 GB; cells beyond it are staged on the fly
@@ -1074,9 +1093,26 @@ static int stencil_lists(mcpyb_engine* e, bool few_sites, StencilLists* xl) {
         CK(cudaMemsetAsync(e->exp_cursor.p, 0, sizeof(unsigned long long), e->stream), "memset stencil cursor");
         int blocks_x = (nbins + EX_WARPS - 1) / EX_WARPS;
         if (blocks_x > e->num_sms * 8) blocks_x = e->num_sms * 8;
-        expand_stencils_kernel<<<blocks_x, 32 * EX_WARPS, 0, e->stream>>>(e->view(), *xl, nbins, e->max_cells);
+        expand_stencils_kernel<<<blocks_x, 32 * EX_WARPS, 0, e->stream>>>(e->view(), *xl, nbins, e->max_cells, e->lj.rc);
         LAUNCH_CHECK("expand_stencils_kernel");
         e->exp_valid = true;
+        if (e->l2_persist_mb > 0) {
+            // the lists are read by every trial launch against this batch: ask L2 to keep them across the streaming
+            // proposal / result traffic
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            size_t span = (size_t)e->total_atoms * 128 * sizeof(double4);
+            int maxwin = 0;
+            cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
+            if (maxwin > 0 && span > (size_t)maxwin) span = (size_t)maxwin;
+            av.accessPolicyWindow.base_ptr = e->exp_q.p;
+            av.accessPolicyWindow.num_bytes = span;
+            const double set_aside = (double)((size_t)e->l2_persist_mb << 20);
+            av.accessPolicyWindow.hitRatio = (float)(set_aside >= (double)span ? 1.0 : set_aside / (double)span);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        }
     }
     return MCPYB_OK;
 }
@@ -1147,6 +1183,15 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     w.stamp = e->tw_stamp;
     const size_t max_items = (ns >> w.item_shift) + (ns < nbp ? ns : nbp) + 1;
     CK(e->tw_items.reserve(max_items), "cudaMalloc trial items");
+    if (e->use_warp_rows) {
+        CK(e->tw_items4.reserve(2 * max_items), "cudaMalloc trial items");
+        const size_t had = e->tw_chain.cap;
+        const size_t scan_ctas = (size_t)(e->R > 0 ? e->R : 1) * ((e->max_cells + RW_SCAN_THREADS) / RW_SCAN_THREADS);
+        CK(e->tw_chain.reserve(2 * scan_ctas), "cudaMalloc scan chain");
+        if (e->tw_chain.cap != had)          // stamp 0 = "not published"
+            CK(cudaMemsetAsync(e->tw_chain.p, 0, e->tw_chain.cap * sizeof(unsigned long long), e->stream), "memset scan chain");
+        w.items = e->tw_items4.p; w.chain = e->tw_chain.p;
+    }
     CK(e->tw_spos.reserve(ns), "cudaMalloc trial work");
     CK(e->tw_meta.reserve(ns), "cudaMalloc trial work");
     w.item_tab = e->tw_items.p; w.sorted_pos = e->tw_spos.p; w.sorted_meta = e->tw_meta.p;
@@ -1176,15 +1221,33 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
         { cudaLaunchConfig_t cfg = config((T + 255) / 256, 256, 0);
           CK(cudaLaunchKernelEx(&cfg, trial_sites_kernel, bv, tb, w), "launch trial_sites_kernel"); e->launches++; }
         mark();
-        { cudaLaunchConfig_t cfg = config(1, 1024, 0);
-          CK(cudaLaunchKernelEx(&cfg, trial_scan_kernel, w), "launch trial_scan_kernel"); e->launches++; }
+        if (e->use_warp_rows) {
+            // (max_cells + 1 bins per replica so that the end marker of a full grid has a thread)
+            const int cpr = (e->max_cells + RW_SCAN_THREADS) / RW_SCAN_THREADS;
+            cudaLaunchConfig_t cfg = config(e->R * cpr, RW_SCAN_THREADS, 0);
+            CK(cudaLaunchKernelEx(&cfg, trial_scan_items_kernel, bv, w, xl, cpr), "launch trial_scan_items_kernel"); e->launches++;
+        } else {
+            cudaLaunchConfig_t cfg = config(1, 1024, 0);
+            CK(cudaLaunchKernelEx(&cfg, trial_scan_kernel, w), "launch trial_scan_kernel"); e->launches++;
+        }
         mark();
         { cudaLaunchConfig_t cfg = config((nsites + 255) / 256, 256, 0);
           CK(cudaLaunchKernelEx(&cfg, trial_scatter_kernel, tb, w), "launch trial_scatter_kernel"); e->launches++; }
     }
     mark();
     const long long est = (long long)max_items * (w.nplanes / w.item_slices);
-    {
+    if (e->use_warp_rows) {
+        const long long want = ((long long)max_items + RW_WARPS - 1) / RW_WARPS;
+        const int grid = (int)(want < (long long)e->num_sms * e->rw_minb ? want : (long long)e->num_sms * e->rw_minb);
+        cudaLaunchConfig_t cfg = config(grid, 32 * RW_WARPS, 0);
+        if (e->rw_minb == 4)
+            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_warp_kernel<4>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_warp_kernel");
+        else if (e->rw_minb == 5)
+            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_warp_kernel<5>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_warp_kernel");
+        else
+            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_warp_kernel<6>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_warp_kernel");
+        e->launches++;
+    } else {
         const int rb = (int)(est < e->num_sms * RB_MIN_BLOCKS ? est : e->num_sms * RB_MIN_BLOCKS);
         cudaLaunchConfig_t cfg = config(rb, RB_THREADS, 0);
         CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_block_kernel<RB_UNROLL, RB_MIN_BLOCKS>, bv, tb, w, e->lj, xl),

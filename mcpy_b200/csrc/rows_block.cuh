@@ -185,6 +185,29 @@ __device__ __noinline__ void rb_generic_row(const GridDesc& g, const double4* __
     acc12 = a12; acc6 = a6; cnt = c;
 }
 
+// Pruning rule of the stencil lists: a candidate image farther than rc from the BOX of the home cell is farther
+// than rc from every site binned into that cell (sites of an edge cell that lie beyond the grid on a non-periodic
+// axis are on the far side of the cell from every atom, so the bound holds for them too).  Per axis the distance
+// to the cell's slab is (fractional distance) x (perpendicular height of the box); for a diagonal lattice the
+// three combine to the exact box distance, otherwise only their maximum is a bound.  A function of the
+// configuration alone: every kernel that walks a cell's stencil prunes it identically.
+__device__ __forceinline__ bool rb_keep_candidate(const GridDesc& g, int c0, int c1, int c2,
+                                                  double x, double y, double z, double reach) {
+    double f[3];
+    to_frac(g, x, y, z, f);
+    const int c[3] = {c0, c1, c2};
+    double e2 = 0.0, emax = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double flo = g.lo[d] + (double)c[d] / g.scale[d], fhi = g.lo[d] + (double)(c[d] + 1) / g.scale[d];
+        const double e = fmax(fmax(flo - f[d], f[d] - fhi), 0.0) * g.height[d];
+        e2 = fma(e, e, e2);
+        emax = fmax(emax, e);
+    }
+    return g.ortho ? (e2 <= reach * reach) : (emax <= reach);
+}
+__device__ __forceinline__ double rb_keep_reach(double rc) { return rc * 1.000001 + 1.0e-9; }
+
 // The stencil of every cell, written out once per resident configuration (expand_stencils_kernel): the
 // candidate records the row-sum kernel would otherwise re-derive for every work item of every launch
 // (piece table, a binary search and a gather per candidate, image shift) as one contiguous, ordered run
@@ -227,7 +250,7 @@ __device__ __forceinline__ void rp_stage_candidate(const GridDesc& g, const doub
 #define EX_WARPS 4
 // One warp per (replica, cell): piece table, then the whole stencil in list order.
 __global__ void __launch_bounds__(32 * EX_WARPS)
-expand_stencils_kernel(BatchView b, StencilLists x, int nbins, int bin_stride) {
+expand_stencils_kernel(BatchView b, StencilLists x, int nbins, int bin_stride, double rc) {
     __shared__ RbPieces pcs[EX_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     RbPieces& pc = pcs[wid];
@@ -251,14 +274,28 @@ expand_stencils_kernel(BatchView b, StencilLists x, int nbins, int bin_stride) {
             if (lane == 0) base = atomicAdd(x.cursor, (unsigned long long)total);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base + (unsigned long long)total <= (unsigned long long)x.cap) {
-                for (int gi = lane; gi < total; gi += 32) {
-                    double4 q;
-                    int2 info;
-                    rp_stage_candidate(g, spos, pc, npieces, gi, q, info);
-                    x.q[base + gi] = q;
-                    x.info[base + gi] = info;
+                // the run is reserved for the whole stencil and filled, in list order, with the candidates that
+                // can be within rc of a site of this cell (the unused tail is never read)
+                const double reach = rb_keep_reach(rc);
+                int kept = 0;
+                for (int g0 = 0; g0 < total; g0 += 32) {
+                    const int gi = g0 + lane;
+                    double4 q = make_double4(0.0, 0.0, 0.0, 0.0);
+                    int2 info = make_int2(0, 0);
+                    bool keep = false;
+                    if (gi < total) {
+                        rp_stage_candidate(g, spos, pc, npieces, gi, q, info);
+                        keep = rb_keep_candidate(g, c0, c1, c2, q.x, q.y, q.z, reach);
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        const unsigned long long at = base + kept + __popc(bal & ((1u << lane) - 1u));
+                        x.q[at] = q;
+                        x.info[at] = info;
+                    }
+                    kept += __popc(bal);
                 }
-                head = make_int2((int)base, total);
+                head = make_int2((int)base, kept);
             }
         }
         if (lane == 0) x.head[bin] = head;
@@ -566,10 +603,12 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
     const int nb = tb.new_off[t], ne = tb.new_off[t + 1];
     bool ok = !trial_invalid(b, tb, w, r, ob, oe, nb, ne);
     ok = ok && (is_old ? (s >= ob && s < oe) : (s - w.n_old >= nb && s - w.n_old < ne));
-    double acc12[8], acc6[8];
-    int cnt[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { acc12[q] = 0.0; acc6[q] = 0.0; cnt[q] = 0; }
+    // the row sum is the fold ((a0 + a1) + (a2 + a3)) of four class sums, class k = the candidates at positions
+    // = k (mod 4) of the cell's PRUNED stencil list, each accumulated in list order (rows_warp.cuh): thread k < 4
+    // carries class k across the chunks
+    double a12 = 0.0, a6 = 0.0;
+    int cc = 0, kpos = 0;                              // kpos: pruned-list position of the next kept candidate
+    bool generic = false;
     if (ok) {
         const GridDesc& g = b.grid[r];
         const int off = g.atom_off;
@@ -584,14 +623,17 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
         const int n0 = g.ncell[0], m0 = g.m[0];
         const int nrows = (2 * g.m[1] + 1) * (2 * g.m[2] + 1);
         const bool fast = (!g.pbc[0] || n0 >= 2 * m0 + 1) && 2 * nrows <= RB_MAXPIECES;
-        if (!fast) {
-            if (tid == 0) rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, acc12[0], acc6[0], cnt[0]);
+        // the cell's stencil: its per-configuration list when there is one (one coalesced read, no piece
+        // table, no search), else built here from the cell list and pruned by the same rule
+        const int cell_bin = r * w.bin_stride + (c[2] * g.ncell[1] + c[1]) * g.ncell[0] + c[0];
+        const int2 head = (fast && x.head) ? x.head[cell_bin] : make_int2(-1, 0);
+        const bool listed = head.x >= 0;
+        if (!fast || (x.head && !listed)) {
+            // thin box / oversized stencil / list buffer full: the batched kernel takes the exact per-lane
+            // traversal for such a cell, and so does this one
+            generic = true;
+            if (tid == 0) rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, a12, a6, cc);
         } else {
-            // the cell's stencil: its per-configuration list when there is one (one coalesced read, no piece
-            // table, no search), else built here from the cell list
-            const int cell_bin = r * w.bin_stride + (c[2] * g.ncell[1] + c[1]) * g.ncell[0] + c[0];
-            const int2 head = x.head ? x.head[cell_bin] : make_int2(-1, 0);
-            const bool listed = head.x >= 0;
             if (!listed) {
                 if (wid == 0) rb_build_pieces(sm.pc, g, cstart, c[0], c[1], c[2], lane);
                 __syncthreads();
@@ -599,7 +641,8 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
             const int total = listed ? head.y : sm.pc.total, npieces = 2 * nrows;
             const double4* xq = x.q + (listed ? head.x : 0);
             const int2* xi = x.info + (listed ? head.x : 0);
-            // per-site constants, as in lj_trial_rows_block_kernel
+            const double reach = rb_keep_reach(p.rc);
+            // per-site constants, as in lj_trial_rows_warp_kernel
             double qx = px, qy = py, qz = pz, band = 16.0;
             if (wsite != pack_wraps(0, 0, 0)) rb_wrap_site(g, p.rc, px, py, pz, wsite, qx, qy, qz, band);
             const double bw = p.rc2 * band * 2.220446049250313e-16;
@@ -610,50 +653,54 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
                     const int gi = cbase + i;
                     double4 q;
                     int2 info = make_int2(0, 0);
+                    bool keep = true;
                     if (listed) q = xq[gi];
-                    else rp_stage_candidate(g, spos, sm.pc, npieces, gi, q, info);
+                    else {
+                        rp_stage_candidate(g, spos, sm.pc, npieces, gi, q, info);
+                        keep = rb_keep_candidate(g, c[0], c[1], c[2], q.x, q.y, q.z, reach);
+                    }
                     const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
                     const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
                     const long long rb = __double_as_longlong(r2);
-                    bool in = rb < lo_bits;
-                    if (!in && rb <= hi_bits) in = rp_exact_r2(g, spos, listed ? xi[gi] : info, px, py, pz, wsite) <= p.rc2;
+                    bool in = keep && rb < lo_bits;
+                    if (keep && !in && rb <= hi_bits) in = rp_exact_r2(g, spos, listed ? xi[gi] : info, px, py, pz, wsite) <= p.rc2;
                     const int j = __double2loint(q.w);
                     for (int e = ob; e < oe; ++e) if (tb.old_idx[e] == j) in = false;
                     double c6 = 0.0;
                     if (in) { const double tt = p.sigma2 * fast_rcp(r2); c6 = tt * tt * tt; }
                     sm.c6[i] = c6;
-                    sm.hit[i] = in ? 1 : 0;
+                    sm.hit[i] = (in ? 1 : 0) | (keep ? 2 : 0);
                 }
                 __syncthreads();
-                // slice q of the list covers [total*q/nq, total*(q+1)/nq): thread q accumulates it in order
-                if (tid < nq && tid < 8) {
-                    const int cf = (int)(((long long)total * tid) / nq), cl = (int)(((long long)total * (tid + 1)) / nq);
-                    const int i0 = max(cf, cbase) - cbase, i1 = min(cl, cbase + n) - cbase;
-                    double a12 = 0.0, a6 = 0.0;
-                    int cc = 0;
-                    // carried across chunks through the registers of thread q (static indexing)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) if (q == tid) { a12 = acc12[q]; a6 = acc6[q]; cc = cnt[q]; }
-                    for (int i = i0; i < i1; ++i) {
-                        const double c6 = sm.c6[i];
-                        a12 = fma(c6, c6, a12);
-                        a6 += c6;
-                        cc += sm.hit[i];
+                if (tid < 4) {
+                    for (int i = 0; i < n; ++i) {
+                        const int h = sm.hit[i];
+                        if (!(h & 2)) continue;                  // pruned: holds no list position
+                        if ((kpos & 3) == tid) {
+                            const double c6 = sm.c6[i];
+                            a12 = fma(c6, c6, a12);
+                            a6 += c6;
+                            cc += h & 1;
+                        }
+                        ++kpos;
                     }
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) if (q == tid) { acc12[q] = a12; acc6[q] = a6; cnt[q] = cc; }
                 }
                 __syncthreads();
             }
         }
-        // thread q holds slice q (generic path: thread 0 holds everything in slice 0)
-        if (tid < nq && tid < 8) {
-            double a12 = 0.0, a6 = 0.0;
-            int cc = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) if (q == tid) { a12 = acc12[q]; a6 = acc6[q]; cc = cnt[q]; }
-            w.site_E[(size_t)s * nq + tid] = fma(p.eps4, a12 - a6, -p.e0 * (double)cc);
-            w.site_cnt[(size_t)s * nq + tid] = cc;
+        // fold the classes in the fixed order ((a0 + a1) + (a2 + a3))
+        if (!generic) {
+            if (tid < 4) { sm.part12[tid] = a12; sm.part6[tid] = a6; sm.partc[tid] = cc; }
+            __syncthreads();
+            if (tid == 0) {
+                a12 = (sm.part12[0] + sm.part12[1]) + (sm.part12[2] + sm.part12[3]);
+                a6 = (sm.part6[0] + sm.part6[1]) + (sm.part6[2] + sm.part6[3]);
+                cc = (sm.partc[0] + sm.partc[1]) + (sm.partc[2] + sm.partc[3]);
+            }
+        }
+        if (tid == 0) {
+            w.site_E[s] = fma(p.eps4, a12 - a6, -p.e0 * (double)cc);
+            w.site_cnt[s] = cc;
         }
     }
     // ---- the last CTA to arrive combines every trial

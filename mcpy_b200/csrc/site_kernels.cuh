@@ -413,6 +413,9 @@ struct TrialWork {
     unsigned long long* err_out;   // may be nullptr
     // CTA row-sum kernel (rows_block.cuh): its prologue reads these instead of chasing pointers
     int2* item_tab;        // [items] (bin, group of the bin's sites); nullptr: not wanted
+    // warp row-sum kernel (rows_warp.cuh)
+    int4* items;           // [2 * items] (bin, first site in bin order, sites, replica), (list first, list length, -, -)
+    unsigned long long* chain;   // [2 R] per-replica totals of the chained scan: (stamp << 36) | sites, | items
     double4* sorted_pos;   // [nsites] site_pos in bin order (.w = packed wraps)
     int4* sorted_meta;     // [nsites] (site id, first excluded atom or -1, old_off[t], old_off[t+1]) in bin order
 };

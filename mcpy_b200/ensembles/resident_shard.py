@@ -10,9 +10,11 @@ configurations between SLOTS without a host round trip of the atoms:
   ladder's only collective (``LadderComm.gather_records``), takes the even / odd pairing and the Metropolis
   decisions from a generator seeded identically on every rank with the reference's exponent
   (``swap_exponent`` = ``BatchedReplicaExchange._accept_swap``, ``batched_replica_exchange.py:320-370``),
-  swaps accepted local pairs inside the device array, ships accepted cross-rank pairs point to point over
-  NCCL (positions + numbers, device to device, one grouped call per round) and rebuilds the engine's cell
-  lists from the device array (``Engine.upload_dev``).  As in the reference, beta / mu stay with the slot,
+  swaps accepted local pairs inside the device array and rebuilds the engine's cell lists from the device
+  array (``Engine.upload_dev``).  The configurations of a rank's two BOUNDARY slots ride in the same
+  all_gather as the records (2 x 64 KB for 2 000 atoms; NVLink moves that in microseconds, a second
+  round of point-to-point calls costs more in launch latency than the bytes do), so an accepted cross-rank
+  swap finds its incoming configuration already on the device: one collective per exchange attempt.  As in the reference, beta / mu stay with the slot,
   E and the configuration travel together (``_swap_states``, ``:401-410``).
 
 One exchanged species (every atom of the configuration counts), one box per replica.
@@ -60,6 +62,9 @@ class ResidentLadderShard:
         if str(dev) != 'cpu':
             # the engine builds its cell lists from tensors torch has just written: one stream for both
             engine.set_stream(torch.cuda.current_stream().cuda_stream)
+        # capacity of a boundary block of the exchange buffer: the largest replica of the whole ladder
+        self.cap = max(max(self.comm.all_gather_object(max(self.n_of, default=0))), 1)
+        self._xbuf = None
         self.E = np.zeros(len(configs))
         self.swap_log = []
         self.rounds = 0
@@ -89,11 +94,52 @@ class ResidentLadderShard:
             rec[k, 16:19] = self.pbcs[k]
         return rec
 
+    def _gather(self):
+        """Records of every replica (host) and, for world > 1, the device buffer holding every rank's two boundary
+        configurations: ONE all_gather."""
+        rec = self.records()
+        comm = self.comm
+        if comm.world_size == 1 or comm._dist is None:
+            return rec, None
+        import time
+        torch = self.torch
+        t0 = time.perf_counter()
+        nloc, per, cap = self.hi - self.lo, comm.per, self.cap
+        blk = 4 * cap                                      # positions (3 cap) + numbers (cap), as float64
+        width = per * _WIDTH + 2 * blk
+        if self._xbuf is None or self._xbuf[0].shape[0] != width:
+            self._xbuf = (torch.zeros(width, dtype=torch.float64, device=self.device),
+                          torch.zeros(comm.world_size * width, dtype=torch.float64, device=self.device),
+                          torch.zeros(per * _WIDTH, dtype=torch.float64, pin_memory=comm.on_gpu),
+                          torch.zeros(comm.world_size, per * _WIDTH, dtype=torch.float64, pin_memory=comm.on_gpu))
+        d_in, d_out, h_in, h_out = self._xbuf
+        h_in.zero_()
+        if nloc:
+            h_in[:nloc * _WIDTH] = torch.from_numpy(rec.reshape(-1))
+        d_in[:per * _WIDTH].copy_(h_in, non_blocking=True)
+        if nloc:
+            for which, k in ((0, 0), (1, nloc - 1)):
+                a, b = self.slot_rows(k)
+                n = b - a
+                if n > cap:
+                    raise RuntimeError(f'replica with {n} atoms exceeds the exchange capacity {cap}')
+                base = per * _WIDTH + which * blk
+                d_in[base:base + 3 * n].copy_(self.d_pos[a:b].reshape(-1))
+                d_in[base + 3 * cap:base + 3 * cap + n].copy_(self.d_num[a:b])
+        comm._dist.all_gather_into_tensor(d_out, d_in, group=comm.group)
+        h_out.copy_(d_out.view(comm.world_size, width)[:, :per * _WIDTH], non_blocking=True)
+        comm._sync()
+        out = h_out.numpy().reshape(comm.world_size, per, _WIDTH)
+        rows = np.concatenate([out[g, :hi - lo] for g, (lo, hi) in enumerate(comm._bounds)])
+        comm.collective_seconds += time.perf_counter() - t0
+        comm.gathers += 1
+        return rows, d_out.view(comm.world_size, width)
+
     def attempt_exchanges(self):
         """One exchange round; returns the number of accepted swaps (identical on every rank)."""
         torch = self.torch
         offset = 0 if self.rng.uniform(0.0, 1.0) < 0.5 else 1
-        rec = self.comm.gather_records(self.records())
+        rec, gathered = self._gather()
         self.rounds += 1
         accepted_pairs = []
         for i in range(offset, self.n_total - 1, 2):
@@ -109,44 +155,43 @@ class ResidentLadderShard:
                 accepted_pairs.append((i, j))
         if not accepted_pairs:
             return 0
-        me = self.comm.rank
-        sends, recvs, incoming = [], [], []
-        local_swaps = []
-        for i, j in accepted_pairs:
-            oi, oj = self.comm.owner(i), self.comm.owner(j)
-            if oi == me and oj == me:
-                local_swaps.append((i - self.lo, j - self.lo))
-            elif me in (oi, oj):
-                mine, theirs, peer = (i, j, oj) if me == oi else (j, i, oi)
-                k = mine - self.lo
-                a, b = self.slot_rows(k)
-                n_in = int(rec[theirs, 6])
-                r_pos = torch.empty((n_in, 3), dtype=torch.float64, device=self.device)
-                r_num = torch.empty(n_in, dtype=torch.int32, device=self.device)
-                sends += [(self.d_pos[a:b].contiguous(), peer), (self.d_num[a:b].contiguous(), peer)]
-                recvs += [(r_pos, peer), (r_num, peer)]
-                incoming.append((k, r_pos, r_num, rec[theirs]))
-        self.comm.exchange(sends, recvs)
-        # apply: the device array is re-assembled from its blocks in their new slots (one concatenation each
-        # for positions and numbers, whatever the number of swaps)
+        me, comm = self.comm.rank, self.comm
         off = self.offsets()
         blocks = [[self.d_pos[off[k]:off[k + 1]], self.d_num[off[k]:off[k + 1]]] for k in range(len(self.n_of))]
-        for a, b in local_swaps:
-            blocks[a], blocks[b] = blocks[b], blocks[a]
-            self.n_of[a], self.n_of[b] = self.n_of[b], self.n_of[a]
-            self.E[a], self.E[b] = self.E[b], self.E[a]
-            self.cells[[a, b]] = self.cells[[b, a]]
-            self.pbcs[[a, b]] = self.pbcs[[b, a]]
-        for k, r_pos, r_num, rec_in in incoming:
-            blocks[k] = [r_pos, r_num]
-            self.n_of[k] = len(r_pos)
-            self.E[k] = rec_in[0]
-            self.cells[k] = rec_in[7:16]
-            self.pbcs[k] = rec_in[16:19] != 0
-        if blocks:
+        touched = False
+        for i, j in accepted_pairs:
+            oi, oj = comm.owner(i), comm.owner(j)
+            if oi == me and oj == me:
+                a, b = i - self.lo, j - self.lo
+                blocks[a], blocks[b] = blocks[b], blocks[a]
+                self.n_of[a], self.n_of[b] = self.n_of[b], self.n_of[a]
+                self.E[a], self.E[b] = self.E[b], self.E[a]
+                self.cells[[a, b]] = self.cells[[b, a]]
+                self.pbcs[[a, b]] = self.pbcs[[b, a]]
+                touched = True
+            elif me in (oi, oj):
+                # the partner's configuration is its rank's boundary block of the gathered buffer: slot i is the LAST
+                # slot of the lower rank, slot j the FIRST slot of the upper one
+                mine, theirs, peer, which = (i, j, oj, 0) if me == oi else (j, i, oi, 1)
+                k = mine - self.lo
+                n_in = int(rec[theirs, 6])
+                cap, per = self.cap, comm.per
+                base = per * _WIDTH + which * 4 * cap
+                row = gathered[peer]
+                blocks[k] = [row[base:base + 3 * n_in].reshape(n_in, 3),
+                             row[base + 3 * cap:base + 3 * cap + n_in].to(torch.int32)]
+                self.n_of[k] = n_in
+                self.E[k] = rec[theirs, 0]
+                self.cells[k] = rec[theirs, 7:16]
+                self.pbcs[k] = rec[theirs, 16:19] != 0
+                comm.transports += 1
+                touched = True
+        if touched:
+            # the device array is re-assembled from its blocks in their new slots (one concatenation each for positions
+            # and numbers, whatever the number of swaps), then the cell lists are rebuilt in place
             self.d_pos = torch.cat([b[0] for b in blocks])
             self.d_num = torch.cat([b[1] for b in blocks])
-        self.upload()
+            self.upload()
         return len(accepted_pairs)
 
     def positions_host(self):
