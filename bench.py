@@ -371,17 +371,23 @@ def run_b200(args):
     rounds = shard.rounds - rounds0
     exchange = {
         'attempts': rounds, 'accepted_swaps': sum(1 for *_, ok in shard.swap_log if ok) - swaps0,
-        'collective_us_per_exchange': 1e6 * (comm.collective_seconds - c0) / max(1, comm.gathers - g0) if world > 1 else 0.0,
-        'transport_us_per_cross_rank_round': 1e6 * (comm.transport_seconds - t0c) / max(1, comm.transports - x0) if world > 1 else 0.0,
-        'cross_rank_transport_rounds': comm.transports - x0,
+        'cross_rank_swaps': comm.transports - x0,
     }
-    # an exchange attempt on its own (host wall clock incl. the rebuild of the cell lists), untimed by the metric
-    torch.cuda.synchronize()
-    tx = time.perf_counter()
+    # an exchange attempt on its own, untimed by the metric: host wall clock from an idle stream to an idle stream
+    # (inside the timed loop the attempt's first synchronisation also drains the sweeps queued before it, so the
+    # tallies of the loop measure queueing, not the collective)
+    c1, g1 = comm.collective_seconds, comm.gathers
+    tx_total = 0.0
     for _ in range(8):
+        barrier()
+        tx = time.perf_counter()
         shard.attempt_exchanges()
-    torch.cuda.synchronize()
-    exchange['exchange_us_per_attempt'] = 1e6 * (time.perf_counter() - tx) / 8
+        torch.cuda.synchronize()
+        tx_total += time.perf_counter() - tx
+    exchange['exchange_us_per_attempt'] = 1e6 * max_over_ranks(tx_total) / 8
+    exchange['collective_us_per_exchange'] = 1e6 * (comm.collective_seconds - c1) / max(1, comm.gathers - g1) if world > 1 else 0.0
+    exchange['collective_note'] = ('one all_gather_into_tensor of the records and the two boundary configurations of every '
+                                   'rank (host -> device, NCCL, device -> host of the records), measured from an idle stream')
     exchange['share_of_step'] = exchange['exchange_us_per_attempt'] * (SW // XI) / (ms_per_step * 1e3)
     exchange['collective_share_of_step'] = exchange['collective_us_per_exchange'] * (SW // XI) / (ms_per_step * 1e3)
 
@@ -393,8 +399,6 @@ def run_b200(args):
     eng.stage_timing(False)
     sweep(0)
     torch.cuda.synchronize()
-    if shard.rounds == rounds0 + 8 and False:
-        pass
 
     # ---- end to end through the plug-in with host buffers
     from baseline import refpath
@@ -755,7 +759,127 @@ def secondary_workloads(device):
                        'energy_forces_us_per_python_call': 1e6 * t_call}
         eng.close()
     out['relax_then_energy'] = relax
+    out['kernel_rooflines'] = kernel_rooflines(device)
     return out
+
+
+def kernel_rooflines(device):
+    """The other kernels north_star names, each against the bound that applies, timed with CUDA events
+    on the engine's stream with their inputs resident in HBM; peaks: HBM copy bandwidth from MEASURED_PEAKS.json
+    (fallback: the profiling recipe's 6 551.7 GB/s), FP64 FMA rate measured in this process."""
+    import torch
+
+    from mcpy_b200 import Engine
+    from mcpy_b200.utils import synthetic
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+        hbm_src = 'MEASURED_PEAKS.json (burst: the kernel is timed alone)'
+    except Exception:
+        hbm, hbm_src = 6551.7, 'fallback of /opt/skills/guides/B200_PROFILING.md'
+    dev = torch.device('cuda', device)
+    stream = torch.cuda.Stream(device=dev)
+    res = {}
+
+    def gpu_ms(fn, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        times = []
+        for _ in range(reps):
+            a.record(stream)
+            fn()
+            b.record(stream)
+            b.synchronize()
+            times.append(a.elapsed_time(b))
+        return float(np.median(times))
+
+    with torch.cuda.stream(stream):
+        # K1: counting-sort cell list of a 64 x 2 000-atom replica batch (72 B / atom: SURVEY 8d)
+        eng = Engine(device)
+        eng.set_stream(stream.cuda_stream)
+        eng.set_lj(1.0, 1.0, RC)
+        cfgs = [synthetic.s2_lj(N_ATOMS, RC, RHO, seed=100 + k) for k in range(64)]
+        pos = torch.from_numpy(np.concatenate([c['positions'] for c in cfgs])).to(dev)
+        num = torch.from_numpy(np.concatenate([c['numbers'] for c in cfgs]).astype(np.int32)).to(dev)
+        off = np.arange(65, dtype=np.int64) * N_ATOMS
+        cells = np.stack([c['cell'].reshape(9) for c in cfgs])
+        pbcs = np.stack([c['pbc'] for c in cfgs])
+        ms = gpu_ms(lambda: eng.upload_dev(off, pos.data_ptr(), num.data_ptr(), cells, pbcs))
+        nbytes = 64 * N_ATOMS * 72
+        res['K1_build_cell_list_64x2000'] = {
+            'bound': 'hbm', 'achieved': nbytes / (ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+            'frac': nbytes / (ms * 1e-3) / 1e9 / hbm, 'kernel_ms': ms, 'algorithmic_bytes_per_launch': nbytes,
+            'peak_source': hbm_src,
+            'note': 'one CTA per replica (64 CTAs on 148 SMs): the launch is latency-bound at this size, 9 MB cannot '
+                    'fill HBM; timed as Engine.upload_dev (48-byte header H2D + the build launch)'}
+        # K2: total energies of the same batch (FP64 pipe; 17 flop per stencil candidate + 8 per in-cutoff pair)
+        d_E = torch.empty(64, dtype=torch.float64, device=dev)
+        ms = gpu_ms(lambda: eng.energies_dev(d_E.data_ptr()))
+        E, pairs = eng.energies(return_pairs=True)
+        peak64 = eng.fp64_peak_tflops()
+        flop = 64 * N_ATOMS * ALG_CANDIDATES_PER_SITE * ALG_FLOP_PER_CANDIDATE + 2 * int(pairs.sum()) * ALG_FLOP_PER_PAIR
+        res['K2_lj_energies_64x2000'] = {
+            'bound': 'fp64', 'achieved': flop / (ms * 1e-3) / 1e12, 'peak': peak64, 'unit': 'TFLOP/s',
+            'frac': flop / (ms * 1e-3) / 1e12 / peak64, 'kernel_ms': ms, 'algorithmic_flop_per_launch': flop,
+            'pairs': int(pairs.sum())}
+        eng.close()
+        # K4 / K5: EMT pair + embedding pass on the 10 825-atom CuPd + CO particle (FP64 + XU: 55 flop + 6
+        # transcendentals per in-cutoff pair, 15 flop + 3 per atom; the stencil walk 17 flop per candidate)
+        eng = Engine(device)
+        eng.set_stream(stream.cuda_stream)
+        eng.set_emt()
+        c5 = synthetic.s5_cupd_co()
+        n5 = len(c5['positions'])
+        p5 = torch.from_numpy(c5['positions']).to(dev)
+        z5 = torch.from_numpy(c5['numbers'].astype(np.int32)).to(dev)
+        eng.upload_dev(np.array([0, n5], dtype=np.int64), p5.data_ptr(), z5.data_ptr(), c5['cell'].reshape(1, 9),
+                       c5['pbc'].reshape(1, 3))
+        d_E1 = torch.empty(1, dtype=torch.float64, device=dev)
+        ms = gpu_ms(lambda: eng.energies_dev(d_E1.data_ptr()))
+        _, pairs5 = eng.energies(return_pairs=True)
+        npair = int(pairs5[0])
+        rho5 = n5 / (4.0 / 3.0 * np.pi * (c5['sphere_radius'] - 3.5) ** 3)
+        cand = 27 * rho5 * eng.cutoff ** 3
+        flop = n5 * cand * 17 + 2 * npair * (55 + 6 * 20) + n5 * (15 + 3 * 20)
+        res['K4_K5_emt_energy_S5'] = {
+            'bound': 'fp64', 'achieved': flop / (ms * 1e-3) / 1e12, 'peak': peak64, 'unit': 'TFLOP/s',
+            'frac': flop / (ms * 1e-3) / 1e12 / peak64, 'kernel_ms': ms, 'algorithmic_flop_per_launch': flop,
+            'pairs': npair,
+            'note': 'exp / log / sqrt counted at 20 FP64-pipe flop each (their polynomial bodies run on the FP64 pipe; '
+                    'only the seed comes from the XU): emt_pair_kernel + emt_embed_kernel + reduce'}
+        # K7: covered test with the sample points streamed from HBM (24 B per point), S5 geometry
+        P = 1_000_000
+        rng = np.random.default_rng(3)
+        pts = torch.from_numpy(synthetic.sphere_points(rng, P, c5['sphere_radius'])).to(dev)
+        rad = torch.from_numpy(c5['radii']).to(dev)
+        cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+
+        def fv():
+            cnt.zero_()
+            eng.free_volume_count_dev(pts.data_ptr(), P, p5.data_ptr(), rad.data_ptr(), n5, cnt.data_ptr())
+        ms = gpu_ms(fv)
+        nbytes = 24 * P
+        res['K7_free_volume_count_S5_1M_points_from_hbm'] = {
+            'bound': 'hbm', 'achieved': nbytes / (ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+            'frac': nbytes / (ms * 1e-3) / 1e9 / hbm, 'kernel_ms': ms, 'algorithmic_bytes_per_launch': nbytes,
+            'points_per_s': P / (ms * 1e-3), 'peak_source': hbm_src,
+            'note': 'fv_build (spheres binned) + fv_count per call; 24 MB of points against ~0.36 kflop of gather + '
+                    'compare work per point (SURVEY 8d): the kernel is bound by the L1/L2 gather of the sphere cells, '
+                    'not by streaming the points'}
+        # K7 + K8: the same count with the points regenerated from the PCG64 stream on the device (no HBM traffic:
+        # integer-ALU bound, 3 x 128-bit LCG steps per candidate point)
+        rng = np.random.default_rng(3)
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            eng.sphere_free_volume_pcg64(rng, P, c5['sphere_radius'], np.zeros(3), c5['positions'], c5['radii'])
+        dt = (time.perf_counter() - t0) / reps
+        res['K7_K8_free_volume_pcg64_S5_1M_points'] = {
+            'bound': 'int-alu', 'points_per_s': P / dt, 'pcg64_steps_per_s': 1.5 * 3 * P * 2 / dt, 'call_ms': 1e3 * dt,
+            'note': 'host call incl. sphere upload and count readback; candidates = 1.5 P per round, two rounds '
+                    '(count + evaluate) regenerate the stream instead of storing 24 MB of points'}
+        eng.close()
+    return res
 
 
 def main():

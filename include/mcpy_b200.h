@@ -256,6 +256,12 @@ int mcpyb_fp64_peak_tflops(mcpyb_engine* e, double* tflops_out);
 int mcpyb_stage_timing(mcpyb_engine* e, int enable, double* mean_ms_out5, int64_t* calls_out);
 /* Number of kernels this engine has launched since creation.                 */
 int64_t mcpyb_launch_count(const mcpyb_engine* e);
+/* The resident chain behind mcpyb_tracked_energy_host (LJ): instead of one launch per call -- the pattern of
+ * GrandCanonicalEnsemble.do_gcmc_step, mcpy/ensembles/grand_canonical_ensemble.py:244-308 -- a small grid stays
+ * resident while calls keep coming and takes each trial from a mailbox in page-locked host memory; it leaves after
+ * 1.5 ms without a request and before anything it reads is rebuilt.  enable = 0 / 1 switches it, -1 leaves it as it
+ * is.  launches_out / trials_out (may be NULL): grids launched and trials answered through the mailbox so far.    */
+int mcpyb_resident_chain(mcpyb_engine* e, int enable, int64_t* launches_out, int64_t* trials_out);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@
 #include "site_kernels.cuh"
 #include "rows_block.cuh"
 #include "rows_warp.cuh"
+#include "chain.cuh"
 #include "emt_kernels.cuh"
 #include "free_volume.cuh"
 #include "pcg64.cuh"
@@ -284,6 +285,15 @@ struct mcpyb_engine {
     DevBuf<unsigned long long> tw_chain;
     DevBuf<double> tw_E;
 
+    // resident chain (chain.cuh): mailbox in pinned host memory, private work arrays, its own stream
+    bool use_chain = true;                // MCPYB_CHAIN=0: one launch per call, as in round 1
+    cudaStream_t chain_stream = nullptr;
+    cudaEvent_t chain_ev = nullptr;
+    ChainMailbox* chain_mb = nullptr;
+    unsigned int chain_seq = 0;
+    bool chain_launched = false;          // a CTA has been launched and not been waited for since
+    long long chain_launches = 0, chain_trials = 0;
+
     // neighbour list scratch
     DevBuf<int> nl_i, nl_j, nl_S;
     DevBuf<double> nl_r2;
@@ -325,6 +335,18 @@ struct mcpyb_engine {
 #define LAUNCH_CHECK(what) do { e->launches++; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return e->cuda_fail(_e, what); } while (0)
 
 namespace {
+
+// The resident chain grid reads the batch arrays, the stencil lists and its private work arrays: it has to be gone
+// before any of them is rebuilt or freed.
+int chain_stop(mcpyb_engine* e) {
+    if (!e->chain_mb || !e->chain_launched) return MCPYB_OK;
+    e->chain_mb->stop = 1;
+    CK(cudaStreamSynchronize(e->chain_stream), "sync resident chain");
+    e->chain_mb->stop = 0;
+    e->chain_mb->alive = 0;
+    e->chain_launched = false;
+    return MCPYB_OK;
+}
 
 // Lattice bookkeeping done once per upload on the host (9 numbers per replica).
 int make_geom(mcpyb_engine* e, const double* cell, const uint8_t* pbc, CellGeom* g) {
@@ -426,6 +448,7 @@ int upload_common(mcpyb_engine* e, int R, const int64_t* atom_off, const double*
     const int* d_off = (const int*)d_header;
     const CellGeom* d_geom = (const CellGeom*)(d_header + off_bytes);
     (void)atom_off; (void)cells; (void)pbc;
+    { int rc = chain_stop(e); if (rc != MCPYB_OK) return rc; }
     if (e->max_n >= 4096) {
         // large configurations: one 8-CTA thread-block cluster per replica
         CK(e->bbox.reserve((size_t)R * 8 * 6), "cudaMalloc bbox");
@@ -557,6 +580,7 @@ int mcpyb_create(int device, mcpyb_engine** out) {
     if (const char* v = getenv("MCPYB_PDL")) e->use_pdl = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_EXPAND")) e->use_expand = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_ROWS")) e->use_warp_rows = strcmp(v, "block") != 0;
+    if (const char* v = getenv("MCPYB_CHAIN")) e->use_chain = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_RW_MINB")) { const int n = atoi(v); if (n >= 4 && n <= 6) e->rw_minb = n; }
     if (const char* v = getenv("MCPYB_L2PERSIST")) {
         e->l2_persist_mb = atoi(v);
@@ -576,7 +600,11 @@ int mcpyb_create(int device, mcpyb_engine** out) {
 void mcpyb_destroy(mcpyb_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    chain_stop(e);
     cudaStreamSynchronize(e->stream);
+    if (e->chain_mb) cudaFreeHost(e->chain_mb);
+    if (e->chain_ev) cudaEventDestroy(e->chain_ev);
+    if (e->chain_stream) cudaStreamDestroy(e->chain_stream);
     e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release(); e->stmp.release(); e->fpos.release();
     e->cid.release(); e->cell_start.release(); e->geom.release(); e->bbox.release();
     e->exp_q.release(); e->exp_info.release(); e->exp_head.release(); e->exp_cursor.release();
@@ -614,6 +642,16 @@ int mcpyb_synchronize(mcpyb_engine* e) {
 }
 
 int64_t mcpyb_launch_count(const mcpyb_engine* e) { return e ? e->launches : 0; }
+
+int mcpyb_resident_chain(mcpyb_engine* e, int enable, int64_t* launches_out, int64_t* trials_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (enable == 0) { int rc = chain_stop(e); if (rc != MCPYB_OK) return rc; e->use_chain = false; }
+    else if (enable > 0) e->use_chain = true;
+    if (launches_out) *launches_out = e->chain_launches;
+    if (trials_out) *trials_out = e->chain_trials;
+    return MCPYB_OK;
+}
 double mcpyb_cutoff(const mcpyb_engine* e) { return e ? e->rcut : 0.0; }
 
 int mcpyb_set_lj(mcpyb_engine* e, double epsilon, double sigma, double rc) {
@@ -621,11 +659,15 @@ int mcpyb_set_lj(mcpyb_engine* e, double epsilon, double sigma, double rc) {
     if (!(sigma > 0.0) || !isfinite(epsilon)) return e->fail(MCPYB_ERR_ARG, "sigma must be > 0 and epsilon finite");
     if (!(rc > 0.0)) rc = 3.0 * sigma;
     cudaSetDevice(e->device);
+    chain_stop(e);
     e->pot_kind = POT_LJ;
     // Trial batches put many sites in every cell, so fine cells (edge rc/2) pay: 343 instead of 844
     // candidates per site.  Total energies have one site per atom: coarse cells (edge rc) fill the
     // 32 lanes of a work item (31 atoms per cell at rho* = 0.6) where fine cells leave 29 idle.
-    e->subdiv_trials = 2; e->subdiv_energy = 1; e->subdiv = 2;
+    // cells of edge rc / 3: 135 pruned candidates per site instead of 185 at rc / 2 (row sums 218 -> 201 us for the
+    // bench's 8 x 65 536 proposals; MCPYB_SUBDIV=2 restores the coarser grid for A/B runs)
+    e->subdiv_trials = 3; e->subdiv_energy = 1; e->subdiv = 3;
+    if (const char* v = getenv("MCPYB_SUBDIV")) { const int n = atoi(v); if (n >= 1 && n <= 3) { e->subdiv_trials = n; e->subdiv = n; } }
     e->rcut = rc;
     e->lj.eps4 = 4.0 * epsilon;
     e->lj.sigma2 = sigma * sigma;
@@ -724,6 +766,8 @@ static int upload_host_impl(mcpyb_engine* e, int subdiv, int R, const int64_t* a
     if (total > 0 && !positions) return e->fail(MCPYB_ERR_ARG, "positions is NULL");
     if (total > 0 && !numbers && e->pot_kind == POT_EMT) return e->fail(MCPYB_ERR_ARG, "EMT needs atomic numbers");
     e->have_batch = false;
+    rc = chain_stop(e);
+    if (rc != MCPYB_OK) return rc;
     rc = reserve_batch(e, R > 0 ? R : 1, total, max_n);
     if (rc != MCPYB_OK) return rc;
     e->R = R; e->total_atoms = total; e->max_n = max_n;
@@ -769,6 +813,8 @@ int mcpyb_upload_dev(mcpyb_engine* e, int R, const int64_t* atom_off, const doub
     if (total > 0 && !d_positions) return e->fail(MCPYB_ERR_ARG, "positions is NULL");
     if (total > 0 && !d_numbers && e->pot_kind == POT_EMT) return e->fail(MCPYB_ERR_ARG, "EMT needs atomic numbers");
     e->have_batch = false;
+    rc = chain_stop(e);
+    if (rc != MCPYB_OK) return rc;
     rc = reserve_batch(e, R > 0 ? R : 1, total, max_n);
     if (rc != MCPYB_OK) return rc;
     e->R = R; e->total_atoms = total; e->max_n = max_n;
@@ -1082,7 +1128,8 @@ static int stencil_lists(mcpyb_engine* e, bool few_sites, StencilLists* xl) {
     // the warp row-sum kernel reads nothing but the lists; the single-launch kernels wait for a second call
     if (!e->exp_valid && ++e->exp_batches < 2 && (few_sites || !e->use_warp_rows)) return MCPYB_OK;
     const int nbins = e->R * e->max_cells;
-    long long cap = (long long)e->total_atoms * 128;              // (2m+1)^3 = 125 cells see each atom at m = 2
+    const long long m_st = 2 * (long long)e->subdiv + 1;
+    long long cap = (long long)e->total_atoms * (m_st * m_st * m_st + 3);   // (2m+1)^3 cells see each atom (125 at m = 2)
     if (cap > (32LL << 20)) cap = 32LL << 20;                      // 1.3 GB; cells beyond it are staged on the fly
     CK(e->exp_q.reserve((size_t)cap), "cudaMalloc stencil lists");
     CK(e->exp_info.reserve((size_t)cap), "cudaMalloc stencil lists");
@@ -1101,7 +1148,7 @@ static int stencil_lists(mcpyb_engine* e, bool few_sites, StencilLists* xl) {
             // proposal / result traffic
             cudaStreamAttrValue av;
             memset(&av, 0, sizeof av);
-            size_t span = (size_t)e->total_atoms * 128 * sizeof(double4);
+            size_t span = (size_t)cap * sizeof(double4);
             int maxwin = 0;
             cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
             if (maxwin > 0 && span > (size_t)maxwin) span = (size_t)maxwin;
@@ -1446,6 +1493,92 @@ static bool wait_flag(volatile unsigned int* flag, unsigned int seq) {
     }
 }
 
+// ---- resident chain -------------------------------------------------------------------
+// Post one trial against the resident base to the chain CTA and wait for its dE.  *answered stays false when the
+// CTA cannot serve it (then the caller takes the one-launch path).
+static int chain_launch(mcpyb_engine* e, const StencilLists& xs, unsigned int start_seq) {
+    if (!e->chain_stream) {
+        CK(cudaStreamCreateWithFlags(&e->chain_stream, cudaStreamNonBlocking), "cudaStreamCreate chain");
+        CK(cudaEventCreateWithFlags(&e->chain_ev, cudaEventDisableTiming), "cudaEventCreate chain");
+        CK(cudaHostAlloc((void**)&e->chain_mb, sizeof(ChainMailbox), cudaHostAllocDefault), "cudaHostAlloc mailbox");
+        memset(e->chain_mb, 0, sizeof(ChainMailbox));
+    }
+    // everything the CTA reads was produced on the engine's stream
+    CK(cudaEventRecord(e->chain_ev, e->stream), "record chain dependency");
+    CK(cudaStreamWaitEvent(e->chain_stream, e->chain_ev, 0), "chain waits for the base");
+    e->chain_mb->alive = 1;
+    e->chain_mb->stop = 0;
+    lj_chain_kernel<<<1, CHAIN_THREADS, 0, e->chain_stream>>>(e->view(), e->lj, xs, e->chain_mb, start_seq);
+    LAUNCH_CHECK("lj_chain_kernel");
+    e->chain_launched = true;
+    e->chain_launches++;
+    return MCPYB_OK;
+}
+
+static int chain_trial(mcpyb_engine* e, int n_old, const int32_t* old_idx, int n_new, const double* new_pos,
+                       double* dE_out, bool* answered) {
+    *answered = false;
+    if (n_old > CHAIN_MAX_OLD || n_old + n_new > CHAIN_MAX_SITES || e->R != 1) return MCPYB_OK;
+    StencilLists xs;
+    {
+        // the lists appear with the second call against a base: the CTA is only used from then on
+        int rc = stencil_lists(e, true, &xs);
+        if (rc != MCPYB_OK) return rc;
+        if (!xs.head) return MCPYB_OK;
+    }
+    if (!e->chain_mb) { int rc = chain_launch(e, xs, e->chain_seq); if (rc != MCPYB_OK) return rc; }
+    ChainMailbox* mb = e->chain_mb;
+    const unsigned int seq = ++e->chain_seq;
+    const int nsites = n_old + n_new, used = 1 + (nsites + 1) / 2;
+    mb->l0.n_old = n_old; mb->l0.n_new = n_new;
+    for (int k = 0; k < n_old; ++k) mb->l0.old_idx[k] = old_idx[k];
+    for (int s = 0; s < nsites; ++s) {
+        const double* src = s < n_old ? &e->trk_pos[3 * (size_t)old_idx[s]] : new_pos + 3 * (s - n_old);
+        double* dst = mb->lp[s >> 1].pos[s & 1];
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+    std::atomic_thread_fence(std::memory_order_release);     // payload before the sequence words (x86: store order)
+    ((volatile unsigned int*)&mb->l0.seq)[0] = seq;
+    for (int k = 0; k + 1 < used; ++k) ((volatile unsigned int*)&mb->lp[k].seq)[0] = seq;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if (!e->chain_launched || !mb->alive) {
+            // not resident (first call, idle timeout, stopped): launch it; it starts from the request before this one
+            if (e->chain_launched) { CK(cudaStreamSynchronize(e->chain_stream), "sync resident chain"); e->chain_launched = false; }
+            int rc = chain_launch(e, xs, seq - 1);
+            if (rc != MCPYB_OK) return rc;
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        for (unsigned it = 1;; ++it) {
+            const unsigned long long ss = mb->status_seq;
+            if ((unsigned int)(ss & 0xFFFFFFFFULL) == seq) {
+                std::atomic_thread_fence(std::memory_order_acquire);
+                if ((unsigned int)(ss >> 32) != CHAIN_ST_OK) return MCPYB_OK;        // not for the CTA: the caller launches
+                *dE_out = mb->dE;
+                *answered = true;
+                e->chain_trials++;
+                return MCPYB_OK;
+            }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            if ((it & 0x3FF) == 0) {
+                if (!mb->alive) break;                                   // the CTA left before it saw the request
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(20)) {
+                    cudaError_t st = cudaStreamQuery(e->chain_stream);
+                    if (st != cudaSuccess && st != cudaErrorNotReady) return e->cuda_fail(st, "resident chain");
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(500)) {
+                        chain_stop(e);
+                        return MCPYB_OK;                                 // give up on the CTA: the caller launches
+                    }
+                }
+            }
+        }
+    }
+    chain_stop(e);
+    return MCPYB_OK;
+}
+
 // ---- incremental drop-in path ------------------------------------------------------
 // calculator.get_potential_energy(atoms) is called once per trial move on a configuration that
 // differs from the previous ones by a handful of atoms (grand_canonical_ensemble.py:244-308).
@@ -1515,7 +1648,14 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
         double dE = 0.0;
         const bool keep = e->trk_valid;
         int rc;
-        if (e->pot_kind == POT_LJ && n_old <= TINY_MAX_MOVED && n_new <= TINY_MAX_MOVED) {
+        bool answered = false;
+        if (e->pot_kind == POT_LJ && e->use_chain && n_old + n_new >= 1) {
+            // the resident chain grid (chain.cuh): the trial goes into the pinned mailbox, no launch
+            rc = chain_trial(e, n_old, old_idx, n_new, new_pos, &dE, &answered);
+            if (rc != MCPYB_OK) return rc;
+        }
+        if (answered) {
+        } else if (e->pot_kind == POT_LJ && n_old <= TINY_MAX_MOVED && n_new <= TINY_MAX_MOVED) {
             // the trial rides in the kernel parameters, the result lands in pinned host memory:
             // one launch and one stream synchronisation per call
             TinyTrial tt;

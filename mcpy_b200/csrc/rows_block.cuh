@@ -591,9 +591,11 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
                                                     const TrialWork& w, const LJParams& p,
                                                     double* __restrict__ dE, int* __restrict__ npairs,
                                                     int* __restrict__ done_counter, const StencilLists& x,
-                                                    volatile unsigned int* done_flag = nullptr, unsigned int seq = 0) {
+                                                    volatile unsigned int* done_flag = nullptr, unsigned int seq = 0,
+                                                    int site = -1, int nctas = -1) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int s = blockIdx.x;                          // site: [0, n_old) old, then new
+    const int s = site >= 0 ? site : (int)blockIdx.x;  // site: [0, n_old) old, then new
+    const int ncta = nctas >= 0 ? nctas : (int)gridDim.x;
     const int nq = w.nplanes;
     // ---- owning trial (T is small: binary search over the offsets)
     const bool is_old = s < w.n_old;
@@ -706,7 +708,7 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
     // ---- the last CTA to arrive combines every trial
     __threadfence();
     __syncthreads();
-    if (tid == 0) sm.last = (atomicAdd(done_counter, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    if (tid == 0) sm.last = (atomicAdd(done_counter, 1) == ncta - 1) ? 1 : 0;
     __syncthreads();
     if (!sm.last) return;
     __threadfence();

@@ -32,7 +32,7 @@
 #include "rows_block.cuh"
 
 #define RW_WARPS 4
-#define RW_MIN_BLOCKS 5
+#define RW_MIN_BLOCKS 4
 #define RW_STAGES 4                  // 1 KB chunks of a cell's list in flight or in use per warp
 
 __device__ __forceinline__ void rw_cp_async16(void* smem, const void* gmem) {

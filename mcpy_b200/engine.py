@@ -79,6 +79,13 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.mcpyb_launch_count(self._h))
 
+    def resident_chain(self, enable=None):
+        """Switch the resident chain grid of the one-call-per-trial path (``mcpyb_resident_chain``) and return
+        ``(grids launched, trials answered through the mailbox)``."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.mcpyb_resident_chain(self._h, -1 if enable is None else int(bool(enable)), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     STAGES = ('trial_sites', 'trial_scan', 'trial_scatter', 'row_sums', 'combine')
 
     def stage_timing(self, enable=True):
@@ -400,6 +407,17 @@ class Engine:
         if return_mask:
             return int(counts[0]), int(counts[1]), mask.astype(bool)
         return int(counts[0]), int(counts[1])
+
+    def free_volume_count_dev(self, d_points: int, n_points: int, d_positions: int, d_radii: int, n_atoms: int,
+                              d_counts2: int, offset=None, shifts=None):
+        """Covered test with everything resident in HBM (device pointers); ``d_counts2``: two uint64 (free, covered),
+        zeroed by the caller.  No synchronisation."""
+        offset = as_f64(np.zeros(3) if offset is None else offset).reshape(3)
+        shifts = as_f64(np.zeros((1, 3)) if shifts is None else shifts).reshape(-1, 3)
+        v = C.c_void_p
+        self._check(self._lib.mcpyb_free_volume_count_dev(
+            self._h, v(d_points), int(n_points), v(d_positions), v(d_radii), int(n_atoms), ptr(offset), ptr(shifts),
+            len(shifts), v(d_counts2)))
 
     # -- free volume with device-regenerated PCG64 points -------------------------
     @staticmethod

@@ -186,3 +186,16 @@ def trial_batch_periodic(cfg, n_trials, seed=7, mix=(1, 1, 1)):
     new_Z = np.where(kinds == 0, insert_Z, cfg['numbers'][atom])[has_new].astype(np.int32)
     return dict(kind=kinds, old_off=old_off, old_idx=old_idx, new_off=new_off,
                 new_pos=np.ascontiguousarray(new_pos, dtype=np.float64), new_Z=new_Z)
+
+
+def sphere_points(rng, n, radius):
+    """``n`` uniform points in the ball by cube rejection (the sampling scheme of ``SphericalCell``; bench input)."""
+    out = np.empty((n, 3))
+    filled = 0
+    while filled < n:
+        pts = (rng.random((int(1.5 * n) + 1, 3)) - 0.5) * 2.0 * radius
+        keep = pts[np.einsum('ij,ij->i', pts, pts) <= radius * radius]
+        take = min(len(keep), n - filled)
+        out[filled:filled + take] = keep[:take]
+        filled += take
+    return out

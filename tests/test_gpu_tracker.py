@@ -132,3 +132,51 @@ def test_tracked_batch_equals_full_evaluations(potential, zdt):
                 cells[[i, j]] = cells[[j, i]]
     assert paths[1] > 150 and paths[0] >= R                 # mostly incremental, re-based at least once
     trk.close(); full.close()
+
+
+def test_resident_chain_answers_like_the_launch_path():
+    """The resident chain grid (mailbox in pinned memory, no launch per call) and the one-launch-per-call path give
+    the same bits for the same chain of configurations; the grid survives accepted moves that accumulate, leaves
+    when the chain pauses and comes back, and is replaced when the base is rebuilt."""
+    import time
+    cfg = synthetic.s2_lj()
+    cell, pbc = cfg['cell'], cfg['pbc']
+    rng = np.random.default_rng(5)
+    steps = []
+    pos, num = cfg['positions'].copy(), cfg['numbers'].copy()
+    for it in range(120):
+        tp, tn = pos.copy(), num.copy()
+        kind = it % 3
+        if kind == 0:
+            i = rng.integers(len(tp)); tp[i] += rng.uniform(-0.3, 0.3, 3)
+        elif kind == 1:
+            tp = np.concatenate([tp, [rng.random(3) @ cell]]); tn = np.concatenate([tn, [1]]).astype(np.int32)
+        else:
+            i = rng.integers(len(tp)); tp = np.delete(tp, i, axis=0); tn = np.delete(tn, i)
+        steps.append((tp, tn))
+        if rng.random() < 0.3:
+            pos, num = tp, tn
+    out = {}
+    for mode in (True, False):
+        eng = Engine(0)
+        eng.set_lj(1.0, 1.0, 3.0)
+        eng.resident_chain(mode)
+        res = []
+        for k, (tp, tn) in enumerate(steps):
+            if k in (40, 41):
+                time.sleep(0.01)                      # longer than the grid's idle timeout: it leaves and is relaunched
+            res.append(eng.tracked_energy(tp, tn, cell, pbc))
+        out[mode] = (np.array([r[0] for r in res]), [r[1] for r in res], eng.resident_chain())
+        eng.close()
+    e_on, p_on, (launches, trials) = out[True]
+    e_off, p_off, (l_off, t_off) = out[False]
+    assert p_on == p_off and p_on.count(1) > 90
+    assert np.array_equal(e_on, e_off)
+    # resident: most incremental calls went through the mailbox (not the first one after a re-base -- the stencil
+    # lists appear with the second -- nor differences of more than 12 sites), with far fewer launches than trials
+    assert trials >= 0.6 * p_on.count(1) and 3 <= launches < 20, (trials, launches, p_on.count(1))
+    assert (l_off, t_off) == (0, 0)
+    for k in (0, 17, 63, 119):
+        tp, tn = steps[k]
+        ref = cfast.lj_energy(tp, cell, pbc, 1.0, 1.0, 3.0)
+        assert abs(e_on[k] - ref) <= 1e-10 * max(1.0, abs(ref))
