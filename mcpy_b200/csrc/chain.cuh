@@ -25,6 +25,7 @@
 // CHAIN_ST_FALLBACK tells the host so).
 #pragma once
 #include "rows_block.cuh"
+#include "emt_kernels.cuh"
 
 #define CHAIN_THREADS 256
 #define CHAIN_WARPS (CHAIN_THREADS / 32)
@@ -37,11 +38,12 @@
 #define CHAIN_ST_OK 0u
 #define CHAIN_ST_FALLBACK 1u
 
-struct __align__(64) ChainLine0 { int n_old, n_new; int old_idx[CHAIN_MAX_OLD]; unsigned int pad[7]; unsigned int seq; };
+struct __align__(64) ChainLine0 { int n_old, n_new; int old_idx[CHAIN_MAX_OLD]; int new_Z[CHAIN_MAX_OLD]; unsigned int pad[1]; unsigned int seq; };
 struct __align__(64) ChainLineP { double pos[2][3]; unsigned int pad[3]; unsigned int seq; };
 
 struct __align__(64) ChainMailbox {
-    // request (host -> device): sites are the removed atoms' (base) positions first, then the added ones
+    // request (host -> device).  LJ: sites are the removed atoms' (base) positions first, then the added ones;
+    // EMT: the added atoms' positions only (the kernel body reads the removed ones from the resident batch)
     ChainLine0 l0;
     ChainLineP lp[CHAIN_LINES - 1];
     // control
@@ -227,6 +229,109 @@ lj_chain_kernel(BatchView b, LJParams p, StencilLists x, ChainMailbox* mb, unsig
             const unsigned long long ss = ((unsigned long long)(unsigned int)sm.status << 32) | (unsigned long long)seq;
             asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::
                          "l"(&mb->dE), "l"(__double_as_longlong(dE)), "l"(ss) : "memory");
+            __threadfence_system();
+        }
+        last = seq;
+        t_idle = chain_clock_ns();
+        __syncthreads();
+    }
+    if (tid == 0) {
+        __threadfence_system();
+        mb->alive = 0;
+        __threadfence_system();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same for EMT: the CTA runs the body of emt_trial_tiny_kernel (the whole CTA on one trial: moved atoms' rows,
+// every affected neighbour re-embedded once with its summed density change) on what the mailbox holds.
+// ---------------------------------------------------------------------------------------------------------
+struct EmtChainSmem {
+    unsigned int req[16 * CHAIN_LINES];
+    EmtTinyTrial tt;
+    double s_part[8];
+    int s_parti[8];
+    double dE;
+    int cmd;
+};
+
+__global__ void __launch_bounds__(256, 1)
+emt_chain_kernel(BatchView b, const EmtTable* __restrict__ tp, const int* __restrict__ z_to_slot,
+                 const double* __restrict__ sigma1, const double* __restrict__ e_atom, ChainMailbox* mb,
+                 unsigned int start_seq) {
+    __shared__ EmtChainSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned int last = start_seq;
+    const unsigned long long t_start = chain_clock_ns();
+    unsigned long long t_idle = t_start;
+    const volatile unsigned int* lines = (const volatile unsigned int*)&mb->l0;
+    for (;;) {
+        if (wid == 0) {
+            int cmd = -1;
+            while (cmd < 0) {
+                unsigned int wv[(16 * CHAIN_LINES + 31) / 32];
+#pragma unroll
+                for (int k = 0; k < (16 * CHAIN_LINES + 31) / 32; ++k)
+                    wv[k] = (32 * k + lane) < 16 * CHAIN_LINES ? lines[32 * k + lane] : 0u;
+                const unsigned int s0 = __shfl_sync(0xffffffffu, wv[0], 15);
+                bool fresh = s0 != last;
+                if (fresh) {
+                    int n_new = (int)__shfl_sync(0xffffffffu, wv[0], 1);
+                    n_new = max(0, min(n_new, CHAIN_MAX_OLD));
+                    const int used = 1 + (n_new + 1) / 2;
+#pragma unroll
+                    for (int k = 0; k < (16 * CHAIN_LINES + 31) / 32; ++k) {
+                        const unsigned int sa = __shfl_sync(0xffffffffu, wv[k], 15), sb = __shfl_sync(0xffffffffu, wv[k], 31);
+                        if (2 * k < used && sa != s0) fresh = false;
+                        if (2 * k + 1 < used && sb != s0) fresh = false;
+                    }
+                }
+                if (fresh) {
+#pragma unroll
+                    for (int k = 0; k < (16 * CHAIN_LINES + 31) / 32; ++k)
+                        if ((32 * k + lane) < 16 * CHAIN_LINES) sm.req[32 * k + lane] = wv[k];
+                    cmd = 0;
+                    break;
+                }
+                int leave = 0;
+                if (lane == 0) {
+                    const unsigned long long now = chain_clock_ns();
+                    leave = (mb->stop || now - t_idle > (unsigned long long)CHAIN_IDLE_US * 1000ULL ||
+                             now - t_start > (unsigned long long)CHAIN_LIFETIME_US * 1000ULL) ? 1 : 0;
+                }
+                leave = __shfl_sync(0xffffffffu, leave, 0);
+                if (leave) { cmd = 1; break; }
+                __nanosleep(64);
+            }
+            if (lane == 0) sm.cmd = cmd;
+        }
+        __syncthreads();
+        if (sm.cmd == 1) break;
+        const ChainLine0& l0 = *(const ChainLine0*)&sm.req[0];
+        const ChainLineP* lp = (const ChainLineP*)&sm.req[16];
+        const unsigned int seq = l0.seq;
+        const int n_old = l0.n_old, n_new = l0.n_new;
+        const bool serve = n_old >= 0 && n_new >= 0 && n_old <= CHAIN_MAX_OLD && n_new <= CHAIN_MAX_OLD && n_old + n_new >= 1;
+        if (serve) {
+            if (tid == 0) { sm.tt.old_off[0] = 0; sm.tt.old_off[1] = n_old; sm.tt.new_off[0] = 0; sm.tt.new_off[1] = n_new; }
+            if (tid < n_old) sm.tt.old_idx[tid] = l0.old_idx[tid];
+            if (tid < n_new) {
+                sm.tt.new_Z[tid] = l0.new_Z[tid];
+                const double* q = lp[tid >> 1].pos[tid & 1];
+                sm.tt.new_pos[3 * tid] = q[0]; sm.tt.new_pos[3 * tid + 1] = q[1]; sm.tt.new_pos[3 * tid + 2] = q[2];
+            }
+            __syncthreads();
+            TrialBatch tb;
+            tb.T = 1; tb.rep = nullptr; tb.old_off = sm.tt.old_off; tb.old_idx = sm.tt.old_idx;
+            tb.new_off = sm.tt.new_off; tb.new_pos = sm.tt.new_pos; tb.new_Z = sm.tt.new_Z;
+            emt_trial_delta_body<256>(b, tb, tp, z_to_slot, sigma1, e_atom, &sm.dE, nullptr, sm.s_part, sm.s_parti);
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const unsigned int status = serve ? CHAIN_ST_OK : CHAIN_ST_FALLBACK;
+            const unsigned long long ss = ((unsigned long long)status << 32) | (unsigned long long)seq;
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::
+                         "l"(&mb->dE), "l"(__double_as_longlong(serve ? sm.dE : 0.0)), "l"(ss) : "memory");
             __threadfence_system();
         }
         last = seq;

@@ -283,6 +283,7 @@ struct mcpyb_engine {
     DevBuf<int2> tw_items;
     DevBuf<int4> tw_items4;
     DevBuf<unsigned long long> tw_chain;
+    DevBuf<int> self_trials;              // rep | old_off | old_idx | new_off of the all-atoms trial batch (K2 via rows)
     DevBuf<double> tw_E;
 
     // resident chain (chain.cuh): mailbox in pinned host memory, private work arrays, its own stream
@@ -513,9 +514,31 @@ size_t header_bytes(int R) {
     return align_up(align_up((size_t)(R + 1) * sizeof(int), 16) + (size_t)R * sizeof(CellGeom), 64);
 }
 
+int launch_trials_fwd(mcpyb_engine* e, int T, const int32_t* d_rep, const int32_t* d_old_off, const int32_t* d_old_idx,
+                      const int32_t* d_new_off, int n_old_total, double* d_dE, int32_t* d_pairs);
+
 int launch_energies(mcpyb_engine* e) {
     if (!e->have_batch) return e->fail(MCPYB_ERR_STATE, "no resident batch (call mcpyb_upload_* first)");
+    if (e->pot_kind == POT_EMT) { int rc = chain_stop(e); if (rc != MCPYB_OK) return rc; }   // sigma1 / e_atom are rewritten
     const int total = e->total_atoms;
+    if (total >= 16384 && e->pot_kind == POT_LJ && e->use_warp_rows && e->use_expand && e->R > 0) {
+        // large LJ batches: every atom's row from the trial pipeline (rows_warp.cuh)
+        const size_t tp = (size_t)total + 1;
+        CK(e->self_trials.reserve(4 * tp), "cudaMalloc self trials");
+        CK(e->dE.reserve(tp), "cudaMalloc dE");
+        CK(e->tpairs.reserve(tp), "cudaMalloc trial pairs");
+        int* rep = e->self_trials.p; int* oo = rep + tp; int* oi = oo + tp; int* no = oi + tp;
+        self_trials_kernel<<<(total + 256) / 256, 256, 0, e->stream>>>(e->d_atom_off, e->R, total, rep, oo, oi, no);
+        LAUNCH_CHECK("self_trials_kernel");
+        int rc = launch_trials_fwd(e, total, rep, oo, oi, no, total, e->dE.p, e->tpairs.p);
+        if (rc != MCPYB_OK) return rc;
+        rows_to_atom_energy_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(total, e->dE.p, e->tpairs.p, e->e_atom.p, e->pair_count.p);
+        LAUNCH_CHECK("rows_to_atom_energy_kernel");
+        reduce_replica_kernel<<<e->R, e->max_n > 1024 ? 1024 : 256, 0, e->stream>>>(
+            e->e_atom.p, e->d_atom_off, e->E.p, e->pair_count.p, e->pairs_ptr(), e->grid.p, e->status_ptr(), nullptr, nullptr, 1);
+        LAUNCH_CHECK("reduce_replica_kernel");
+        return MCPYB_OK;
+    }
     if (total > 0) {
         const int warps_per_block = 8;
         int blocks = (total + warps_per_block - 1) / warps_per_block;
@@ -1130,7 +1153,9 @@ static int stencil_lists(mcpyb_engine* e, bool few_sites, StencilLists* xl) {
     const int nbins = e->R * e->max_cells;
     const long long m_st = 2 * (long long)e->subdiv + 1;
     long long cap = (long long)e->total_atoms * (m_st * m_st * m_st + 3);   // (2m+1)^3 cells see each atom (125 at m = 2)
-    if (cap > (32LL << 20)) cap = 32LL << 20;                      // 1.3 GB; cells beyond it are staged on the fly
+    // a cell's run is reserved for its whole stencil and filled with the pruned part; 40 B per record: 1.8 GB for a
+    // 64 x 2 000-atom batch, capped at 20 GB of the 180 GB (cells beyond the cap take the exact per-lane traversal)
+    if (cap > (512LL << 20)) cap = 512LL << 20;
     CK(e->exp_q.reserve((size_t)cap), "cudaMalloc stencil lists");
     CK(e->exp_info.reserve((size_t)cap), "cudaMalloc stencil lists");
     CK(e->exp_head.reserve((size_t)nbins), "cudaMalloc stencil lists");
@@ -1308,6 +1333,15 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     mark();
     return MCPYB_OK;
 }
+
+extern "C++" {
+namespace {
+int launch_trials_fwd(mcpyb_engine* e, int T, const int32_t* d_rep, const int32_t* d_old_off, const int32_t* d_old_idx,
+                      const int32_t* d_new_off, int n_old_total, double* d_dE, int32_t* d_pairs) {
+    return launch_trials(e, T, d_rep, d_old_off, d_old_idx, d_new_off, nullptr, nullptr, n_old_total, 0, d_dE, d_pairs);
+}
+}  // namespace
+}  // extern "C++"
 
 int mcpyb_trial_delta_e_dev(mcpyb_engine* e, int T, const int32_t* d_rep, const int32_t* d_old_off,
                             const int32_t* d_old_idx, const int32_t* d_new_off, const double* d_new_pos,
@@ -1508,32 +1542,47 @@ static int chain_launch(mcpyb_engine* e, const StencilLists& xs, unsigned int st
     CK(cudaStreamWaitEvent(e->chain_stream, e->chain_ev, 0), "chain waits for the base");
     e->chain_mb->alive = 1;
     e->chain_mb->stop = 0;
-    lj_chain_kernel<<<1, CHAIN_THREADS, 0, e->chain_stream>>>(e->view(), e->lj, xs, e->chain_mb, start_seq);
-    LAUNCH_CHECK("lj_chain_kernel");
+    if (e->pot_kind == POT_LJ) {
+        lj_chain_kernel<<<1, CHAIN_THREADS, 0, e->chain_stream>>>(e->view(), e->lj, xs, e->chain_mb, start_seq);
+        LAUNCH_CHECK("lj_chain_kernel");
+    } else {
+        emt_chain_kernel<<<1, 256, 0, e->chain_stream>>>(e->view(), e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p,
+                                                         e->chain_mb, start_seq);
+        LAUNCH_CHECK("emt_chain_kernel");
+    }
     e->chain_launched = true;
     e->chain_launches++;
     return MCPYB_OK;
 }
 
 static int chain_trial(mcpyb_engine* e, int n_old, const int32_t* old_idx, int n_new, const double* new_pos,
-                       double* dE_out, bool* answered) {
+                       const int32_t* new_Z, double* dE_out, bool* answered) {
     *answered = false;
-    if (n_old > CHAIN_MAX_OLD || n_old + n_new > CHAIN_MAX_SITES || e->R != 1) return MCPYB_OK;
+    const bool lj = e->pot_kind == POT_LJ;
+    if (n_old > CHAIN_MAX_OLD || e->R != 1) return MCPYB_OK;
+    if (lj ? (n_old + n_new > CHAIN_MAX_SITES) : (n_new > CHAIN_MAX_OLD)) return MCPYB_OK;
     StencilLists xs;
-    {
+    memset(&xs, 0, sizeof xs);
+    if (lj) {
         // the lists appear with the second call against a base: the CTA is only used from then on
         int rc = stencil_lists(e, true, &xs);
         if (rc != MCPYB_OK) return rc;
         if (!xs.head) return MCPYB_OK;
+    } else if (!e->emt_state_valid) {
+        int rc = launch_energies(e);               // sigma1 / e_atom of the resident base
+        if (rc != MCPYB_OK) return rc;
     }
     if (!e->chain_mb) { int rc = chain_launch(e, xs, e->chain_seq); if (rc != MCPYB_OK) return rc; }
     ChainMailbox* mb = e->chain_mb;
     const unsigned int seq = ++e->chain_seq;
-    const int nsites = n_old + n_new, used = 1 + (nsites + 1) / 2;
+    // LJ: positions of the removed atoms (from the host mirror of the base), then of the added ones; EMT: added only
+    const int nsites = lj ? n_old + n_new : n_new, used = 1 + (nsites + 1) / 2;
     mb->l0.n_old = n_old; mb->l0.n_new = n_new;
     for (int k = 0; k < n_old; ++k) mb->l0.old_idx[k] = old_idx[k];
+    for (int k = 0; k < n_new && k < CHAIN_MAX_OLD; ++k) mb->l0.new_Z[k] = new_Z ? new_Z[k] : 0;
     for (int s = 0; s < nsites; ++s) {
-        const double* src = s < n_old ? &e->trk_pos[3 * (size_t)old_idx[s]] : new_pos + 3 * (s - n_old);
+        const double* src = !lj ? new_pos + 3 * s
+                                : (s < n_old ? &e->trk_pos[3 * (size_t)old_idx[s]] : new_pos + 3 * (s - n_old));
         double* dst = mb->lp[s >> 1].pos[s & 1];
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
     }
@@ -1649,10 +1698,16 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
         const bool keep = e->trk_valid;
         int rc;
         bool answered = false;
-        if (e->pot_kind == POT_LJ && e->use_chain && n_old + n_new >= 1) {
-            // the resident chain grid (chain.cuh): the trial goes into the pinned mailbox, no launch
-            rc = chain_trial(e, n_old, old_idx, n_new, new_pos, &dE, &answered);
-            if (rc != MCPYB_OK) return rc;
+        if (e->use_chain && n_old + n_new >= 1) {
+            // the resident chain CTA (chain.cuh): the trial goes into the pinned mailbox, no launch
+            bool species_ok = true;
+            if (e->pot_kind == POT_EMT)
+                for (int k = 0; k < n_new; ++k)
+                    species_ok = species_ok && new_Z[k] >= 0 && new_Z[k] < 120 && e->z_to_slot_host[new_Z[k]] >= 0;
+            if (species_ok) {
+                rc = chain_trial(e, n_old, old_idx, n_new, new_pos, new_Z, &dE, &answered);
+                if (rc != MCPYB_OK) return rc;
+            }
         }
         if (answered) {
         } else if (e->pot_kind == POT_LJ && n_old <= TINY_MAX_MOVED && n_new <= TINY_MAX_MOVED) {

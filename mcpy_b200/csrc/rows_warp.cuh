@@ -331,3 +331,32 @@ lj_trial_rows_warp_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, S
         next_wi = __shfl_sync(0xffffffffu, claimed, 0);
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// K2 for large batches: the total energy of every resident configuration from the SAME row-sum pipeline --
+// every atom is the removed atom of one trial (its row is the sum over its neighbours), e_atom = row / 2.
+// A 64 x 2 000-atom batch takes the five launches of the pipeline (~0.1 ms) instead of 1.28 ms in the
+// lane-per-atom kernel with its fp32 screen and per-lane FIFOs (profiles/README.md, round 2).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+self_trials_kernel(const int* __restrict__ atom_off, int R, int total, int* __restrict__ rep,
+                   int* __restrict__ old_off, int* __restrict__ old_idx, int* __restrict__ new_off) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > total) return;
+    old_off[t] = t;
+    new_off[t] = 0;
+    if (t < total) {
+        const int r = find_replica(atom_off, R, t);
+        rep[t] = r;
+        old_idx[t] = t - atom_off[r];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rows_to_atom_energy_kernel(int total, const double* __restrict__ dE, const int* __restrict__ pairs,
+                           double* __restrict__ e_atom, int* __restrict__ pair_count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    e_atom[t] = -0.5 * dE[t];                     // dE of removing atom t = -(its row)
+    pair_count[t] = pairs[t];
+}

@@ -134,12 +134,14 @@ def test_tracked_batch_equals_full_evaluations(potential, zdt):
     trk.close(); full.close()
 
 
-def test_resident_chain_answers_like_the_launch_path():
-    """The resident chain grid (mailbox in pinned memory, no launch per call) and the one-launch-per-call path give
-    the same bits for the same chain of configurations; the grid survives accepted moves that accumulate, leaves
+@pytest.mark.parametrize('potential', ['lj', 'emt'])
+def test_resident_chain_answers_like_the_launch_path(potential):
+    """The resident chain CTA (mailbox in pinned memory, no launch per call) and the one-launch-per-call path give
+    the same bits for the same chain of configurations; the CTA survives accepted moves that accumulate, leaves
     when the chain pauses and comes back, and is replaced when the base is rebuilt."""
     import time
-    cfg = synthetic.s2_lj()
+    cfg = synthetic.s2_lj() if potential == 'lj' else synthetic.s3_ag_o()
+    new_Z = 1 if potential == 'lj' else 8
     cell, pbc = cfg['cell'], cfg['pbc']
     rng = np.random.default_rng(5)
     steps = []
@@ -150,7 +152,8 @@ def test_resident_chain_answers_like_the_launch_path():
         if kind == 0:
             i = rng.integers(len(tp)); tp[i] += rng.uniform(-0.3, 0.3, 3)
         elif kind == 1:
-            tp = np.concatenate([tp, [rng.random(3) @ cell]]); tn = np.concatenate([tn, [1]]).astype(np.int32)
+            p_new = rng.random(3) @ cell if potential == 'lj' else tp[rng.integers(len(tp))] + rng.uniform(-2.5, 2.5, 3)
+            tp = np.concatenate([tp, [p_new]]); tn = np.concatenate([tn, [new_Z]]).astype(np.int32)
         else:
             i = rng.integers(len(tp)); tp = np.delete(tp, i, axis=0); tn = np.delete(tn, i)
         steps.append((tp, tn))
@@ -159,7 +162,10 @@ def test_resident_chain_answers_like_the_launch_path():
     out = {}
     for mode in (True, False):
         eng = Engine(0)
-        eng.set_lj(1.0, 1.0, 3.0)
+        if potential == 'lj':
+            eng.set_lj(1.0, 1.0, 3.0)
+        else:
+            eng.set_emt()
         eng.resident_chain(mode)
         res = []
         for k, (tp, tn) in enumerate(steps):
@@ -178,5 +184,5 @@ def test_resident_chain_answers_like_the_launch_path():
     assert (l_off, t_off) == (0, 0)
     for k in (0, 17, 63, 119):
         tp, tn = steps[k]
-        ref = cfast.lj_energy(tp, cell, pbc, 1.0, 1.0, 3.0)
+        ref = _oracle_energy(potential, {'rc': 3.0}, tp, tn, cell, pbc)
         assert abs(e_on[k] - ref) <= 1e-10 * max(1.0, abs(ref))
