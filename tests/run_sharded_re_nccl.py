@@ -1,4 +1,4 @@
-"""Not a pytest file: the sharded replica-exchange driver on real GPUs over NCCL.
+"""The sharded replica-exchange driver on real GPUs over NCCL (launched by tests/test_gpu_nccl.py, or by hand):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29531 tests/run_sharded_re_nccl.py
@@ -19,9 +19,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
-import importlib.util
-if importlib.util.find_spec('ase') is None:
-    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'ase_shim'))
+from baseline import refpath
+refpath.enable()
 
 import torch
 import torch.distributed as dist
@@ -38,17 +37,17 @@ def main():
     n_rep, steps = 8, 24
     temps = list(np.linspace(1.5, 3.0, n_rep))
     calc = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=3.0, device=local)
-    re = ShardedReplicaExchange(make_factory(), calc, temperatures=temps, gcmc_steps=steps, exchange_interval=3,
-                                seed=31, rank=rank, world_size=world, device=f'cuda:{local}')
+    re = ShardedReplicaExchange(make_factory(calc, fix=(0, 3)), calc, temperatures=temps, gcmc_steps=steps,
+                                exchange_interval=3, seed=31, rank=rank, world_size=world, device=f'cuda:{local}')
     re.run()
     mine = {re.lo + k: (r.E_old, r.n_atoms, r.atoms.positions.copy()) for k, r in enumerate(re.replicas)}
     gathered = [None] * world
     dist.all_gather_object(gathered, (re.swap_log, mine))
     ok = True
     if rank == 0:
-        ref = ShardedReplicaExchange(make_factory(), B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=3.0, device=local),
-                                     temperatures=temps, gcmc_steps=steps, exchange_interval=3, seed=31,
-                                     rank=0, world_size=1)
+        calc1 = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=3.0, device=local)
+        ref = ShardedReplicaExchange(make_factory(calc1, fix=(0, 3)), calc1, temperatures=temps, gcmc_steps=steps,
+                                     exchange_interval=3, seed=31, rank=0, world_size=1)
         ref.run()
         merged = {}
         for log, st in gathered:
