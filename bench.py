@@ -760,7 +760,40 @@ def secondary_workloads(device):
         eng.close()
     out['relax_then_energy'] = relax
     out['kernel_rooflines'] = kernel_rooflines(device)
+    out['fp32_pair_math'] = fp32_mode(device)
     return out
+
+
+def fp32_mode(device):
+    """north_star's second precision for the batched LJ row sums (mcpyb_set_precision): the same sweep in fp64 and
+    with fp32 pair math + fp64 accumulation; error of dE relative to the fp64 mode and the row-sum stage time."""
+    from mcpy_b200 import Engine
+    cfgs = local_configs(0)
+    tb = proposal_batch(cfgs, seed=5)
+    res = {}
+    dE = {}
+    for prec in ('fp64', 'fp32'):
+        eng = Engine(device)
+        eng.set_lj(1.0, 1.0, RC)
+        eng.set_precision(prec)
+        eng.upload([c['positions'] for c in cfgs], [c['numbers'] for c in cfgs],
+                   np.stack([c['cell'].reshape(9) for c in cfgs]), np.stack([c['pbc'] for c in cfgs]))
+        call = lambda: eng.trial_delta_e(tb['old_off'], tb['old_idx'], tb['new_off'], tb['new_pos'], tb['new_Z'], rep=tb['rep'])  # noqa: E731
+        for _ in range(3):
+            dE[prec] = call()
+        eng.stage_timing(True)
+        for _ in range(6):
+            call()
+            st, _ = eng.stage_timing(True)
+        res[prec + '_row_sums_ms'] = st['row_sums']
+        eng.close()
+    rel = np.abs(dE['fp32'] - dE['fp64']) / np.maximum(1.0, np.abs(dE['fp64']))
+    res['max_rel_error_vs_fp64'] = float(rel.max())
+    res['tolerance'] = 1e-5
+    res['note'] = ('fp32 r2 / reciprocal / c6 from an fp64 distance vector, class sums added in fp32 per trip and accumulated '
+                   'in fp64; membership bit-exact.  On B200 the mode is SLOWER than fp64: the three f64->f32 conversions per '
+                   'candidate issue at a quarter of the DFMA rate, and the FP64 pipe is only 2x narrower than the FP32 one')
+    return res
 
 
 def kernel_rooflines(device):

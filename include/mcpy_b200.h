@@ -60,6 +60,12 @@ int mcpyb_set_lj(mcpyb_engine* e, double epsilon, double sigma, double rc);
  * (Reference call sites: tests/test_canonical_nvt.py:26,
  * docs/examples/gcmc_simulations.rst:31.)                                      */
 int mcpyb_set_emt(mcpyb_engine* e);
+/* Arithmetic of the batched LJ trial-move row sums (mcpyb_trial_delta_e_*, and the energies of large batches that
+ * run through the same pipeline).  0 (default): fp64 throughout -- energies and dE within 1e-10 relative of
+ * ase.calculators.lj.LennardJones.  1: fp32 pair math (r^2, reciprocal, c6 on the FP32 pipe from an fp64 distance
+ * vector; sums accumulated in fp64) -- within 1e-5 relative; membership r^2 <= rc^2 stays bit-exact (candidates
+ * within 1e-6 of the cutoff are decided and evaluated in fp64).  The one-call-per-trial paths stay fp64.        */
+int mcpyb_set_precision(mcpyb_engine* e, int fp32_pair_math);
 /* Neighbour cutoff in use: LJ rc, EMT rc_list.                               */
 double mcpyb_cutoff(const mcpyb_engine* e);
 /* Derived EMT constants for atomic number Z: out9 = E0,s0,V0,eta2,kappa,lambda,

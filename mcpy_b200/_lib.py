@@ -29,7 +29,7 @@ SYMBOLS = [
     'mcpyb_sphere_free_volume_pcg64', 'mcpyb_dome_free_volume_pcg64', 'mcpyb_box_free_volume_pcg64',
     'mcpyb_alloc_pinned', 'mcpyb_free_pinned',
     'mcpyb_min_dist2_host', 'mcpyb_pcg64_host_doubles', 'mcpyb_fp64_peak_tflops', 'mcpyb_stage_timing', 'mcpyb_launch_count',
-    'mcpyb_resident_chain',
+    'mcpyb_resident_chain', 'mcpyb_set_precision',
 ]
 
 _p = C.c_void_p
@@ -106,6 +106,7 @@ def load():
     lib.mcpyb_launch_count.argtypes = [_p]
     lib.mcpyb_launch_count.restype = C.c_int64
     lib.mcpyb_resident_chain.argtypes = [_p, C.c_int, _i64p, _i64p]
+    lib.mcpyb_set_precision.argtypes = [_p, C.c_int]
     _lib = lib
     return lib
 

@@ -54,7 +54,7 @@ class _B200Core:
 
     implemented_properties = ['energy', 'free_energy', 'forces']
 
-    def _init_engine(self, potential, epsilon, sigma, rc, device, chunk_size, incremental=True):
+    def _init_engine(self, potential, epsilon, sigma, rc, device, chunk_size, incremental=True, precision='fp64'):
         potential = str(potential).lower()
         if potential not in ('lj', 'lennardjones', 'emt'):
             raise ValueError(f"potential must be 'lj' or 'emt', got {potential!r}")
@@ -69,6 +69,11 @@ class _B200Core:
                                   'rc': self.engine.cutoff}
         else:
             self.engine.set_emt()
+        if precision != 'fp64':
+            if self.potential != 'lj':
+                raise ValueError("precision='fp32' is available for the LJ trial batches only")
+            self.engine.set_precision(precision)
+        self.precision = precision
         self.n_energy_calls = 0
         self.incremental = bool(incremental)
         self.path_counts = [0, 0, 0]          # full evaluations, incremental, identical-to-base
@@ -174,9 +179,9 @@ if _AseCalculator is not None:
         nolabel = True
 
         def __init__(self, potential='lj', epsilon=1.0, sigma=1.0, rc=None, device=0,
-                     chunk_size=None, incremental=True, **kwargs):
+                     chunk_size=None, incremental=True, precision='fp64', **kwargs):
             _AseCalculator.__init__(self, **kwargs)
-            self._init_engine(potential, epsilon, sigma, rc, device, chunk_size, incremental)
+            self._init_engine(potential, epsilon, sigma, rc, device, chunk_size, incremental, precision)
 
         def calculate(self, atoms=None, properties=('energy',), system_changes=_all_changes):
             _AseCalculator.calculate(self, atoms, properties, system_changes)
@@ -200,10 +205,10 @@ else:
         __doc__ = __doc__
 
         def __init__(self, potential='lj', epsilon=1.0, sigma=1.0, rc=None, device=0,
-                     chunk_size=None, incremental=True, **kwargs):
+                     chunk_size=None, incremental=True, precision='fp64', **kwargs):
             self.results = {}
             self.atoms = None
-            self._init_engine(potential, epsilon, sigma, rc, device, chunk_size, incremental)
+            self._init_engine(potential, epsilon, sigma, rc, device, chunk_size, incremental, precision)
 
         def calculate(self, atoms=None, properties=('energy',), system_changes=_all_changes):
             self.atoms = atoms

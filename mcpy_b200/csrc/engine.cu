@@ -196,6 +196,7 @@ struct mcpyb_engine {
     bool use_warp_rows = true;            // MCPYB_ROWS=block: the round-1 CTA-per-cell row-sum kernel (A/B runs only)
     int rw_minb = RW_MIN_BLOCKS;          // MCPYB_RW_MINB=4|5|6: resident CTAs per SM the warp row-sum kernel is built for
     int l2_persist_mb = 0;                // MCPYB_L2PERSIST=<MB>: keep the stencil lists in a persisting L2 window
+    bool fp32_pairs = false;              // mcpyb_set_precision: fp32 pair math in the batched LJ row sums
     // stencil lists of the resident batch (rows_block.cuh): built when a SECOND trial batch is scored against
     // the same resident configuration -- one batch per upload (the end-to-end pattern) does not amortise them
     bool exp_valid = false;
@@ -665,6 +666,12 @@ int mcpyb_synchronize(mcpyb_engine* e) {
 }
 
 int64_t mcpyb_launch_count(const mcpyb_engine* e) { return e ? e->launches : 0; }
+
+int mcpyb_set_precision(mcpyb_engine* e, int fp32_pair_math) {
+    if (!e) return MCPYB_ERR_ARG;
+    e->fp32_pairs = fp32_pair_math != 0;
+    return MCPYB_OK;
+}
 
 int mcpyb_resident_chain(mcpyb_engine* e, int enable, int64_t* launches_out, int64_t* trials_out) {
     if (!e) return MCPYB_ERR_ARG;
@@ -1310,14 +1317,17 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     const long long est = (long long)max_items * (w.nplanes / w.item_slices);
     if (e->use_warp_rows) {
         const long long want = ((long long)max_items + RW_WARPS - 1) / RW_WARPS;
-        const int grid = (int)(want < (long long)e->num_sms * e->rw_minb ? want : (long long)e->num_sms * e->rw_minb);
+        const int minb = e->fp32_pairs ? 4 : e->rw_minb;
+        const int grid = (int)(want < (long long)e->num_sms * minb ? want : (long long)e->num_sms * minb);
         cudaLaunchConfig_t cfg = config(grid, 32 * RW_WARPS, 0);
-        if (e->rw_minb == 4)
-            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_warp_kernel<4>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_warp_kernel");
+        if (e->fp32_pairs)
+            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_warp_kernel<4, true>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_warp_kernel");
+        else if (e->rw_minb == 4)
+            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_warp_kernel<4, false>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_warp_kernel");
         else if (e->rw_minb == 5)
-            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_warp_kernel<5>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_warp_kernel");
+            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_warp_kernel<5, false>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_warp_kernel");
         else
-            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_warp_kernel<6>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_warp_kernel");
+            CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_warp_kernel<6, false>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_warp_kernel");
         e->launches++;
     } else {
         const int rb = (int)(est < e->num_sms * RB_MIN_BLOCKS ? est : e->num_sms * RB_MIN_BLOCKS);

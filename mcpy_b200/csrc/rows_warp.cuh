@@ -143,7 +143,11 @@ trial_scan_items_kernel(BatchView b, TrialWork w, StencilLists x, int cpr) {
 // ascending inside each class) into its 4 / G accumulator pairs.  The tail of the last chunk is padded with records
 // that lie 1e150 away: misses, never ambiguous, not on any exclusion list.
 // ---------------------------------------------------------------------------------------------------------
-template <int G>
+// F32 = true: fp32 pair math (north_star's second precision).  The distance vector is still formed in fp64
+// (q - site: both are exact records) and rounded once; r2, the reciprocal and c6 run on the FP32 pipe; the class sums
+// of a trip are added up in fp32 and go into the fp64 accumulators once per trip.  Membership stays bit-exact: a
+// candidate whose fp32 r2 falls within 4e-7 of rc^2 is decided -- and evaluated -- by the fp64 path.
+template <int G, bool F32>
 __device__ __noinline__ void rw_candidate_loop(
         const double4* __restrict__ xq, const int2* __restrict__ xi, int len, int lane, int grp, double4 (*buf)[32],   // buf[RW_STAGES][32]
         double qx, double qy, double qz, int ksite, const double4* __restrict__ sorted_pos,
@@ -157,6 +161,9 @@ __device__ __noinline__ void rw_candidate_loop(
     int cnt = 0;
     const int lo_hi = (int)(lo_bits >> 32), hi_hi = (int)(hi_bits >> 32);
     const unsigned amb_width = (unsigned)(hi_hi - lo_hi);
+    // fp32 mode: the window around rc^2 inside which the fp64 arithmetic decides (fp32 rounding of d and r2: < 3e-7)
+    const float lo_f = __double2float_rd(rc2 * (1.0 - 1.0e-6)), hi_f = __double2float_ru(rc2 * (1.0 + 1.0e-6));
+    const float s2f = (float)sigma2;
     const double4 pad = make_double4(1.0e150, 1.0e150, 1.0e150, __longlong_as_double(-2LL));
     const int nchunks = (len + 31) >> 5;
     auto fetch = [&](int c) {                              // chunk c -> its ring slot (one commit group per call)
@@ -181,6 +188,37 @@ __device__ __noinline__ void rw_candidate_loop(
         const double4* cur = buf[c % RW_STAGES];
         const int here = min(32, len - (c << 5));
         for (int i = 0; i < here; i += 4 * G) {
+            if (F32) {
+                float r2f[4];
+                int jj[4];
+                bool amb = multi;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double4 q = cur[i + grp + G * u];
+                    const float fx = (float)(q.x - qx), fy = (float)(q.y - qy), fz = (float)(q.z - qz);
+                    r2f[u] = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
+                    amb = amb || (r2f[u] >= lo_f && r2f[u] <= hi_f);
+                    jj[u] = __double2loint(q.w);
+                }
+                if (!__any_sync(0xffffffffu, amb)) {
+                    float p12[NA], p6[NA];
+#pragma unroll
+                    for (int k = 0; k < NA; ++k) { p12[k] = 0.0f; p6[k] = 0.0f; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool hit = r2f[u] < lo_f && jj[u] != ex0 && jj[u] != ex1;
+                        const float t = s2f * __frcp_rn(r2f[u]);
+                        float c6 = t * t * t;
+                        c6 = hit ? c6 : 0.0f;
+                        p12[u % NA] = fmaf(c6, c6, p12[u % NA]);
+                        p6[u % NA] += c6;
+                        if (hit) ++cnt;
+                    }
+#pragma unroll
+                    for (int k = 0; k < NA; ++k) { a12[k] += (double)p12[k]; a6[k] += (double)p6[k]; }
+                    continue;
+                }
+            }
             double r2[4];
             int jj[4], rh[4];
             unsigned amb = multi ? 0u : 0xffffffffu;       // min over the trip of (hi(r2) - lo_hi), unsigned
@@ -193,7 +231,7 @@ __device__ __noinline__ void rw_candidate_loop(
                 amb = min(amb, (unsigned)(rh[u] - lo_hi));
                 jj[u] = __double2loint(q.w);
             }
-            if (__any_sync(0xffffffffu, amb <= amb_width)) {
+            if (F32 || __any_sync(0xffffffffu, amb <= amb_width)) {
                 // rare: some lane has a candidate within rounding of the cutoff (the oracle's arithmetic decides) or
                 // a move of more than two atoms (exclusion list)
                 double px = 0.0, py = 0.0, pz = 0.0;
@@ -255,7 +293,7 @@ __device__ __noinline__ void rw_candidate_loop(
     outc = cnt;
 }
 
-template <int MINB>
+template <int MINB, bool F32>
 __global__ void __launch_bounds__(32 * RW_WARPS, MINB)
 lj_trial_rows_warp_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, StencilLists x) {
     __shared__ double4 s_buf[RW_WARPS][RW_STAGES][32];
@@ -316,10 +354,10 @@ lj_trial_rows_warp_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, S
             const int2* xi = x.info + h1.x;
             const int ksite = active ? kbeg + sl : -1;
             if (gshift == 4)
-                rw_candidate_loop<2>(xq, xi, h1.y, lane, grp, s_buf[wid], qx, qy, qz, ksite, w.sorted_pos, lo_bits, hi_bits,
+                rw_candidate_loop<2, F32>(xq, xi, h1.y, lane, grp, s_buf[wid], qx, qy, qz, ksite, w.sorted_pos, lo_bits, hi_bits,
                                      ex0, ex1, multi, ob, oe, g, spos, tb, p.sigma2, p.rc2, acc12, acc6, cnt);
             else
-                rw_candidate_loop<4>(xq, xi, h1.y, lane, grp, s_buf[wid], qx, qy, qz, ksite, w.sorted_pos, lo_bits, hi_bits,
+                rw_candidate_loop<4, F32>(xq, xi, h1.y, lane, grp, s_buf[wid], qx, qy, qz, ksite, w.sorted_pos, lo_bits, hi_bits,
                                      ex0, ex1, multi, ob, oe, g, spos, tb, p.sigma2, p.rc2, acc12, acc6, cnt);
         }
         if (active && grp == 0) {

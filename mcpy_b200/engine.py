@@ -111,6 +111,14 @@ class Engine:
                                            -1.0 if rc is None else float(rc)))
         self.potential = 'lj'
 
+    def set_precision(self, precision='fp64'):
+        """'fp64' (default) or 'fp32': fp32 pair math with fp64 accumulation in the batched LJ row sums
+        (``mcpyb_set_precision``; 1e-5 relative instead of 1e-10)."""
+        if precision not in ('fp64', 'fp32'):
+            raise ValueError("precision must be 'fp64' or 'fp32'")
+        self._check(self._lib.mcpyb_set_precision(self._h, 1 if precision == 'fp32' else 0))
+        self.precision = precision
+
     def set_emt(self):
         self._check(self._lib.mcpyb_set_emt(self._h))
         self.potential = 'emt'

@@ -354,3 +354,36 @@ def test_full_size_batch_properties(lj_engine):
         d_ins = lj_engine.trial_delta_e(zero, np.zeros(0, np.int32), one, b.reshape(1, 3), np.ones(1, np.int32))[0]
         up(pos)
         assert abs(dE[t] - (d_del + d_ins)) <= RTOL * max(1.0, abs(d_del), abs(d_ins)), (t, dE[t], d_del, d_ins)
+
+
+@pytest.mark.parametrize('name,n_trials', [('s1_argon', 3000), ('s2_lj', 6000)])
+def test_fp32_pair_math_mode_within_1e5(name, n_trials):
+    """north_star's second precision: fp32 pair math (r2, reciprocal, c6 on the FP32 pipe, fp64 accumulation) in the
+    batched row sums.  dE within 1e-5 relative of the oracle (tolerance: 1e-5 max(1, |dE|)), the in-cutoff pair
+    counts -- membership is still decided bit-exactly -- identical to the fp64 mode's."""
+    from mcpy_b200 import Engine
+    cfg = getattr(synthetic, name)()
+    tb = synthetic.trial_batch(cfg, n_trials, seed=21)
+    args = (tb['old_off'], tb['old_idx'], tb['new_off'], tb['new_pos'], tb['new_Z'])
+    out = {}
+    for prec in ('fp64', 'fp32'):
+        eng = Engine(0)
+        eng.set_lj(cfg['epsilon'], cfg['sigma'], cfg['rc'])
+        eng.set_precision(prec)
+        eng.upload([cfg['positions']], [cfg['numbers']], cfg['cell'].reshape(1, 9), cfg['pbc'].reshape(1, 3))
+        out[prec] = eng.trial_delta_e(*args, return_pairs=True)
+        eng.close()
+    d64, p64 = out['fp64']
+    d32, p32 = out['fp32']
+    assert np.array_equal(p64, p32)
+    assert not np.array_equal(d64, d32)                                   # the mode really ran in another arithmetic
+    E0 = cfast.lj_energy(cfg['positions'], cfg['cell'], cfg['pbc'], cfg['sigma'], cfg['epsilon'], cfg['rc'])
+    worst = 0.0
+    for t in range(0, n_trials, n_trials // 60):
+        p1, _ = synthetic.apply_trial(cfg, tb, t)
+        ref = cfast.lj_energy(p1, cfg['cell'], cfg['pbc'], cfg['sigma'], cfg['epsilon'], cfg['rc']) - E0
+        worst = max(worst, abs(d32[t] - ref) / max(1.0, abs(ref)))
+        assert abs(d32[t] - ref) <= 1e-5 * max(1.0, abs(ref)) + 1e-13 * abs(E0), (t, d32[t], ref)
+    rel = np.abs(d32 - d64) / np.maximum(1.0, np.abs(d64))
+    assert rel.max() <= 1e-5, rel.max()
+    print(f'fp32 pair math on {name}: max |dE32 - dE64| / max(1, |dE|) = {rel.max():.2e}, vs oracle {worst:.2e}')
