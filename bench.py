@@ -880,6 +880,33 @@ def kernel_rooflines(device):
             'pairs': npair,
             'note': 'exp / log / sqrt counted at 20 FP64-pipe flop each (their polynomial bodies run on the FP64 pipe; '
                     'only the seed comes from the XU): emt_pair_kernel + emt_embed_kernel + reduce'}
+        # K6: EMT trial-move dE on the same particle, the trial batch resident in HBM (list-driven warp-per-trial
+        # kernel, emt_rows.cuh).  Work per trial, counted from the pair counter the kernel returns: every directed
+        # pair term is 2 exp + a shared cutoff exp (~55 flop + 3 x 20), every touched neighbour one re-embedding
+        # (log + 2 exp, ~15 flop + 3 x 20); the list walk is 9 flop per candidate.
+        res['K6_emt_trial_dE_S5'] = {}
+        for T in (8192, 65536):
+            tb = synthetic.trial_batch(c5, T, seed=11, insert_Z=8)
+            dt = {k: torch.from_numpy(np.ascontiguousarray(tb[k], dtype=np.int32)).to(dev) for k in ('old_off', 'old_idx', 'new_off', 'new_Z')}
+            dnp = torch.from_numpy(np.ascontiguousarray(tb['new_pos'], dtype=np.float64)).to(dev)
+            d_dE = torch.empty(T + 1, dtype=torch.float64, device=dev)
+            d_np = torch.empty(T, dtype=torch.int32, device=dev)
+            n_old, n_new = int(tb['old_off'][-1]), int(tb['new_off'][-1])
+
+            def tr():
+                eng.trial_delta_e_dev(T, 0, dt['old_off'].data_ptr(), dt['old_idx'].data_ptr(), dt['new_off'].data_ptr(),
+                                      dnp.data_ptr(), dt['new_Z'].data_ptr(), n_old, n_new, d_dE.data_ptr(), d_np.data_ptr())
+            ms = gpu_ms(tr)
+            terms = int(d_np.sum().item())
+            sites = n_old + n_new
+            flop = terms * (55 + 3 * 20) + sites * 54 * (15 + 3 * 20) + sites * 200 * 9
+            res['K6_emt_trial_dE_S5'][f'T{T}'] = {
+                'bound': 'fp64', 'achieved': flop / (ms * 1e-3) / 1e12, 'peak': peak64, 'unit': 'TFLOP/s',
+                'frac': flop / (ms * 1e-3) / 1e12 / peak64, 'kernel_ms': ms, 'dE_evals_per_s': T / (ms * 1e-3),
+                'pair_terms': terms, 'algorithmic_flop_per_launch': flop}
+        res['K6_emt_trial_dE_S5']['note'] = (
+            'memset + emt_trial_rows_kernel + emt_trial_redo_kernel per call; transcendentals at 20 FP64-pipe flop '
+            'each; the first-generation kernel (MCPYB_EMT_LISTS=0) is the A/B baseline in profiles/README.md')
         # K7: covered test with the sample points streamed from HBM (24 B per point), S5 geometry
         P = 1_000_000
         rng = np.random.default_rng(3)

@@ -90,14 +90,16 @@ emt_pair_kernel(BatchView b, const int* __restrict__ atom_off, int total_atoms,
     }
 }
 
-// K5: e_atom[a] += embedding(sigma1[a]); one thread per atom.
+// K5: e_emb[a] = embedding(sigma1[a]), e_atom[a] += e_emb[a]; one thread per atom.
 __global__ void __launch_bounds__(256)
 emt_embed_kernel(BatchView b, int total_atoms, const EmtTable* __restrict__ tp,
-                 const double* __restrict__ sigma1, double* __restrict__ e_atom) {
+                 const double* __restrict__ sigma1, double* __restrict__ e_atom, double* __restrict__ e_emb) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= total_atoms) return;
     const int sp = tag_species(tag_of(b.upos[a]));
-    e_atom[a] += emt_embed(*tp, sp, sigma1[a]);
+    const double v = emt_embed(*tp, sp, sigma1[a]);
+    e_emb[a] = v;
+    e_atom[a] += v;
 }
 
 // ---------------------------------------------------------------------------
@@ -191,7 +193,9 @@ __device__ __forceinline__ void emt_trial_delta_body(const BatchView& b, const T
                                                      const int* __restrict__ z_to_slot,
                                                      const double* __restrict__ sigma1,
                                                      const double* __restrict__ e_atom, double* __restrict__ dE,
-                                                     int* __restrict__ npairs, double* s_part, int* s_parti) {
+                                                     int* __restrict__ npairs, double* s_part, int* s_parti,
+                                                     const int* __restrict__ only = nullptr, int n_only = 0) {
+    // `only` != nullptr: just the trials only[0 .. n_only) (the ones the list-driven kernel handed back)
     const EmtTable& t = *tp;
     const double rcl = t.rc_list;
     const int gl = threadIdx.x % G;
@@ -200,7 +204,9 @@ __device__ __forceinline__ void emt_trial_delta_body(const BatchView& b, const T
     const int trows = G > 32 ? G / 32 : 1, trow0 = G > 32 ? (gl >> 5) : 0;
     const int group = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int ngroups = (gridDim.x * blockDim.x) / G;
-    for (int tr = group; tr < tb.T; tr += ngroups) {
+    const int ntr = only ? n_only : tb.T;
+    for (int kk = group; kk < ntr; kk += ngroups) {
+        const int tr = only ? only[kk] : kk;
         const int r = tb.rep ? tb.rep[tr] : 0;
         const GridDesc& g = b.grid[r];
         const int off = g.atom_off;

@@ -24,6 +24,7 @@
 #include "rows_block.cuh"
 #include "rows_warp.cuh"
 #include "chain.cuh"
+#include "emt_rows.cuh"
 #include "emt_kernels.cuh"
 #include "free_volume.cuh"
 #include "pcg64.cuh"
@@ -197,6 +198,8 @@ struct mcpyb_engine {
     int rw_minb = RW_MIN_BLOCKS;          // MCPYB_RW_MINB=4|5|6: resident CTAs per SM the warp row-sum kernel is built for
     int l2_persist_mb = 0;                // MCPYB_L2PERSIST=<MB>: keep the stencil lists in a persisting L2 window
     bool fp32_pairs = false;              // mcpyb_set_precision: fp32 pair math in the batched LJ row sums
+    int er_minb = 6;                      // MCPYB_ER_MINB: resident CTAs per SM the list-driven EMT trial kernel is compiled for
+    bool use_emt_lists = true;            // MCPYB_EMT_LISTS=0: the first-generation EMT trial kernel for every batch
     // stencil lists of the resident batch (rows_block.cuh): built when a SECOND trial batch is scored against
     // the same resident configuration -- one batch per upload (the end-to-end pattern) does not amortise them
     bool exp_valid = false;
@@ -227,7 +230,7 @@ struct mcpyb_engine {
     const int* d_atom_off = nullptr;      // points into stage_dev (header of the last upload)
     DevBuf<CellGeom> geom;
     DevBuf<double> bbox;                  // cluster build scratch
-    DevBuf<double> e_atom, sigma1, e_part, deds, forces;
+    DevBuf<double> e_atom, sigma1, e_emb, e_part, deds, forces;
     DevBuf<int> cnt_part;
     DevBuf<double> E;                     // one block: E[R] | pairs[R] (int64) | status[R] (int32)
     DevBuf<int> pair_count;
@@ -284,6 +287,7 @@ struct mcpyb_engine {
     DevBuf<int2> tw_items;
     DevBuf<int4> tw_items4;
     DevBuf<unsigned long long> tw_chain;
+    DevBuf<int> emt_redo;                 // [1 + T] trials handed back by the list-driven EMT trial kernel
     DevBuf<int> self_trials;              // rep | old_off | old_idx | new_off of the all-atoms trial batch (K2 via rows)
     DevBuf<double> tw_E;
 
@@ -437,6 +441,7 @@ int reserve_batch(mcpyb_engine* e, int R, int total, int max_n) {
     CK(e->cid.reserve(na), "cudaMalloc cid");
     CK(e->e_atom.reserve(na), "cudaMalloc e_atom");
     CK(e->sigma1.reserve(na), "cudaMalloc sigma1");
+    CK(e->e_emb.reserve(na), "cudaMalloc e_emb");
     CK(e->pair_count.reserve(na), "cudaMalloc pair_count");
     return MCPYB_OK;
 }
@@ -564,7 +569,7 @@ int launch_energies(mcpyb_engine* e) {
                 e->view(), e->d_atom_off, total, e->emt_dev.p, e->e_atom.p, e->sigma1.p, e->pair_count.p);
             LAUNCH_CHECK("emt_pair_kernel");
             const int eb = (total + 255) / 256;
-            emt_embed_kernel<<<eb, 256, 0, e->stream>>>(e->view(), total, e->emt_dev.p, e->sigma1.p, e->e_atom.p);
+            emt_embed_kernel<<<eb, 256, 0, e->stream>>>(e->view(), total, e->emt_dev.p, e->sigma1.p, e->e_atom.p, e->e_emb.p);
             LAUNCH_CHECK("emt_embed_kernel");
             e->emt_state_valid = true;
         }
@@ -605,6 +610,8 @@ int mcpyb_create(int device, mcpyb_engine** out) {
     if (const char* v = getenv("MCPYB_EXPAND")) e->use_expand = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_ROWS")) e->use_warp_rows = strcmp(v, "block") != 0;
     if (const char* v = getenv("MCPYB_CHAIN")) e->use_chain = atoi(v) != 0;
+    if (const char* v = getenv("MCPYB_EMT_LISTS")) e->use_emt_lists = atoi(v) != 0;
+    if (const char* v = getenv("MCPYB_ER_MINB")) e->er_minb = atoi(v);
     if (const char* v = getenv("MCPYB_RW_MINB")) { const int n = atoi(v); if (n >= 4 && n <= 6) e->rw_minb = n; }
     if (const char* v = getenv("MCPYB_L2PERSIST")) {
         e->l2_persist_mb = atoi(v);
@@ -632,7 +639,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     e->emt_dev.release(); e->z_to_slot.release(); e->grid.release(); e->upos.release(); e->spos.release(); e->stmp.release(); e->fpos.release();
     e->cid.release(); e->cell_start.release(); e->geom.release(); e->bbox.release();
     e->exp_q.release(); e->exp_info.release(); e->exp_head.release(); e->exp_cursor.release();
-    e->e_atom.release(); e->sigma1.release(); e->e_part.release(); e->deds.release(); e->forces.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
+    e->e_atom.release(); e->sigma1.release(); e->e_emb.release(); e->e_part.release(); e->deds.release(); e->forces.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
     e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release(); e->tw_spos.release(); e->tw_meta.release(); e->tw_items.release(); e->tw_a.release(); e->tw_err.release(); e->tw_hist.release();
@@ -1153,10 +1160,11 @@ static int prepare_rows_work(mcpyb_engine* e, int nsites, int n_old_total, int n
 // worth it for the configurations such a chain runs on, not for a 100 000-atom batch.
 static int stencil_lists(mcpyb_engine* e, bool few_sites, StencilLists* xl) {
     memset(xl, 0, sizeof *xl);
-    if (!e->use_expand || e->pot_kind != POT_LJ || !e->have_batch || e->total_atoms <= 0) return MCPYB_OK;
+    if (!e->use_expand || e->pot_kind == POT_NONE || !e->have_batch || e->total_atoms <= 0) return MCPYB_OK;
+    if (e->pot_kind == POT_EMT && few_sites) return MCPYB_OK;        // the EMT chain / single-launch kernels walk the cell list
     if (few_sites && e->total_atoms > 20000) return MCPYB_OK;
     // the warp row-sum kernel reads nothing but the lists; the single-launch kernels wait for a second call
-    if (!e->exp_valid && ++e->exp_batches < 2 && (few_sites || !e->use_warp_rows)) return MCPYB_OK;
+    if (!e->exp_valid && ++e->exp_batches < 2 && (few_sites || (!e->use_warp_rows && e->pot_kind == POT_LJ))) return MCPYB_OK;
     const int nbins = e->R * e->max_cells;
     const long long m_st = 2 * (long long)e->subdiv + 1;
     long long cap = (long long)e->total_atoms * (m_st * m_st * m_st + 3);   // (2m+1)^3 cells see each atom (125 at m = 2)
@@ -1172,7 +1180,7 @@ static int stencil_lists(mcpyb_engine* e, bool few_sites, StencilLists* xl) {
         CK(cudaMemsetAsync(e->exp_cursor.p, 0, sizeof(unsigned long long), e->stream), "memset stencil cursor");
         int blocks_x = (nbins + EX_WARPS - 1) / EX_WARPS;
         if (blocks_x > e->num_sms * 8) blocks_x = e->num_sms * 8;
-        expand_stencils_kernel<<<blocks_x, 32 * EX_WARPS, 0, e->stream>>>(e->view(), *xl, nbins, e->max_cells, e->lj.rc);
+        expand_stencils_kernel<<<blocks_x, 32 * EX_WARPS, 0, e->stream>>>(e->view(), *xl, nbins, e->max_cells, e->rcut);
         LAUNCH_CHECK("expand_stencils_kernel");
         e->exp_valid = true;
         if (e->l2_persist_mb > 0) {
@@ -1212,6 +1220,29 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
     }
     const int nsites = n_old_total + n_new_total;
     if (e->pot_kind == POT_EMT) {
+        StencilLists xe;
+        memset(&xe, 0, sizeof xe);
+        if (T >= 64 && e->use_emt_lists) {
+            int rc = stencil_lists(e, false, &xe);
+            if (rc != MCPYB_OK) return rc;
+        }
+        if (xe.head) {
+            // one warp per trial over the pruned per-cell lists, hits compacted (emt_rows.cuh); trials it cannot take
+            // (cells without a list) come back through emt_redo and run on the first-generation body
+            CK(e->emt_redo.reserve((size_t)T + 1), "cudaMalloc emt redo");
+            CK(cudaMemsetAsync(e->emt_redo.p, 0, sizeof(int), e->stream), "memset emt redo");
+            int gb = (T + ER_WARPS - 1) / ER_WARPS;
+            if (gb > e->num_sms * e->er_minb) gb = e->num_sms * e->er_minb;
+#define ER_LAUNCH(M) emt_trial_rows_kernel<M><<<gb, 32 * ER_WARPS, 0, e->stream>>>( \
+                e->view(), tb, e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p, e->e_emb.p, xe, e->max_cells, d_dE, d_pairs, e->emt_redo.p)
+            if (e->er_minb >= 8) ER_LAUNCH(8); else if (e->er_minb >= 6) ER_LAUNCH(6); else ER_LAUNCH(4);
+#undef ER_LAUNCH
+            LAUNCH_CHECK("emt_trial_rows_kernel");
+            emt_trial_redo_kernel<<<e->num_sms, 256, 0, e->stream>>>(
+                e->view(), tb, e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p, d_dE, d_pairs, e->emt_redo.p);
+            LAUNCH_CHECK("emt_trial_redo_kernel");
+            return MCPYB_OK;
+        }
         // one warp per trial, lanes over the candidates (see the note at the end of emt_kernels.cuh)
         emt_trial_delta_kernel<32><<<blocks, 256, 0, e->stream>>>(
             e->view(), tb, e->emt_dev.p, e->z_to_slot.p, e->sigma1.p, e->e_atom.p, d_dE, d_pairs);

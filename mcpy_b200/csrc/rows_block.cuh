@@ -243,7 +243,8 @@ __device__ __forceinline__ void rp_stage_candidate(const GridDesc& g, const doub
         shift_vec(g, sx - jx, sy - jy, sz - jz, ax, ay, az);
     }
     q.x = __dadd_rn(q.x, ax); q.y = __dadd_rn(q.y, ay); q.z = __dadd_rn(q.z, az);
-    q.w = __longlong_as_double((long long)tag_index(tag));       // low word = atom index
+    // low word = atom index | species slot << 24 (the slot is 0 for LJ, so the LJ loops read the index as it is)
+    q.w = __longlong_as_double((long long)tag_index(tag) | ((long long)tag_species(tag) << 24));
     info = make_int2(k, pS);
 }
 
