@@ -34,6 +34,29 @@ def find_nvcc() -> str:
     return nvcc
 
 
+def marshal_path() -> str:
+    import sysconfig
+    return os.path.join(HERE, '_marshal' + (sysconfig.get_config_var('EXT_SUFFIX') or '.so'))
+
+
+def build_marshal(force: bool = False) -> str:
+    """The CPython helper that walks an atoms list for the batched call (csrc/marshal.c; plain gcc, no CUDA)."""
+    import sysconfig
+    src, out = os.path.join(CSRC, 'marshal.c'), marshal_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cc = shutil.which('gcc') or shutil.which('cc')
+    if not cc:
+        raise RuntimeError('gcc not found: cannot build the marshalling helper')
+    import numpy
+    cmd = [cc, '-O2', '-shared', '-fPIC', '-Wall', '-I' + sysconfig.get_paths()['include'], '-I' + numpy.get_include(),
+           '-o', out, src]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError('gcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
+    return out
+
+
 def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -44,6 +67,7 @@ def is_stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the engine for sm_100a; returns the path of the shared library."""
+    build_marshal(force)
     if not force and not is_stale():
         return LIB
     cmd = [find_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \

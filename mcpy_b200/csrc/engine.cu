@@ -78,77 +78,90 @@ struct PinBuf {
 
 // A few helper threads for the large host-side passes of the batched calls (user arrays -> pinned staging
 // and back; the row-by-row comparison of 64 incoming configurations with their resident bases): one core
-// moves ~20 GB/s, which made such a pass the longest single item of a call.  Workers sleep on a condition
-// variable between calls.
+// moves ~20 GB/s, which made such a pass the longest single item of a call.  Workers poll for the next job for a
+// short while after each one, then sleep on a condition variable.
 class CopyPool {
 public:
-    explicit CopyPool(int nworkers) {
-        for (int i = 0; i < nworkers; ++i) threads_.emplace_back([this]() { loop(); });
+    explicit CopyPool(int nworkers, int spin_us) : n_(nworkers), spin_us_(spin_us) {
+        for (int k = 0; k < nworkers; ++k) threads_.emplace_back([this, k]() { loop(k); });
     }
     ~CopyPool() {
-        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        { std::lock_guard<std::mutex> lk(m_); stop_.store(true); gen_.fetch_add(1, std::memory_order_release); }
         cv_.notify_all();
         for (auto& t : threads_) t.join();
     }
+    int workers() const { return n_; }
     // memcpy(dst, src, n) split over the workers and the caller
     void copy(void* dst, const void* src, size_t n) {
         const size_t min_part = 128u << 10;
         int parts = (int)(n / min_part);
-        if (parts > (int)threads_.size() + 1) parts = (int)threads_.size() + 1;
+        if (parts > n_ + 1) parts = n_ + 1;
         if (parts <= 1) { memcpy(dst, src, n); return; }
-        const size_t each = ((n / parts) + 63) & ~(size_t)63;
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            for (int p = 1; p < parts; ++p) {
-                const size_t beg = each * p, len = (p == parts - 1) ? n - beg : each;
-                jobs_.push_back({(unsigned char*)dst + beg, (const unsigned char*)src + beg, len});
-            }
-            pending_.fetch_add(parts - 1);
-        }
-        cv_.notify_all();
-        memcpy(dst, src, each);
-        while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+        struct Ctx { unsigned char* dst; const unsigned char* src; size_t n, each; int parts; };
+        Ctx c{(unsigned char*)dst, (const unsigned char*)src, n, ((n / parts) + 63) & ~(size_t)63, parts};
+        parallel_for(parts, [](void* v, int p) {
+            Ctx& x = *(Ctx*)v;
+            const size_t beg = x.each * p;
+            if (beg < x.n) memcpy(x.dst + beg, x.src + beg, (p == x.parts - 1 || beg + x.each > x.n) ? x.n - beg : x.each);
+        }, &c);
     }
-    // fn(ctx, i) for i in [0, n), interleaved over the workers and the caller
+    // fn(ctx, i) for i in [0, n): index i always runs on the same thread (i mod parts; the caller takes part 0), so
+    // whatever a thread touched for index i in the last call is still in its cache
     void parallel_for(int n, void (*fn)(void*, int), void* ctx) {
-        int parts = (int)threads_.size() + 1;
+        int parts = n_ + 1;
         if (parts > n) parts = n;
         if (parts <= 1) { for (int i = 0; i < n; ++i) fn(ctx, i); return; }
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            for (int p = 1; p < parts; ++p) jobs_.push_back({nullptr, nullptr, 0, fn, ctx, p, parts, n});
-            pending_.fetch_add(parts - 1);
-        }
-        cv_.notify_all();
+        fn_ = fn; ctx_ = ctx; count_ = n; parts_ = parts;
+        pending_.store(n_, std::memory_order_relaxed);
+        bool wake;
+        { std::lock_guard<std::mutex> lk(m_); gen_.fetch_add(1, std::memory_order_release); wake = sleepers_ > 0; }
+        if (wake) cv_.notify_all();
         for (int i = 0; i < n; i += parts) fn(ctx, i);
-        while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
     }
 private:
-    struct Job {
-        unsigned char* dst; const unsigned char* src; size_t n;
-        void (*fn)(void*, int) = nullptr; void* ctx = nullptr; int first = 0, step = 1, count = 0;
-    };
-    void loop() {
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    // Every worker acknowledges every generation (pending_ counts all of them), so the job fields are never rewritten
+    // while a worker may still read them.  After a job a worker polls for the next one for spin_us_ before it goes to
+    // sleep on the condition variable: a Monte-Carlo loop calls every ~100 us, and a futex wake-up costs 10-20 us.
+    void loop(int k) {
+        unsigned long long seen = 0;
         for (;;) {
-            Job j;
-            {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [this]() { return stop_ || !jobs_.empty(); });
-                if (stop_ && jobs_.empty()) return;
-                j = jobs_.back();
-                jobs_.pop_back();
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned it = 1; gen_.load(std::memory_order_acquire) == seen; ++it) {
+                cpu_relax();
+                if ((it & 0xFF) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_)) {
+                    std::unique_lock<std::mutex> lk(m_);
+                    ++sleepers_;
+                    cv_.wait(lk, [&]() { return gen_.load(std::memory_order_acquire) != seen; });
+                    --sleepers_;
+                    break;
+                }
             }
-            if (j.fn) { for (int i = j.first; i < j.count; i += j.step) j.fn(j.ctx, i); }
-            else memcpy(j.dst, j.src, j.n);
+            if (stop_.load()) return;
+            seen = gen_.load(std::memory_order_acquire);
+            const int first = k + 1;
+            if (first < parts_) for (int i = first; i < count_; i += parts_) fn_(ctx_, i);
             pending_.fetch_sub(1, std::memory_order_release);
         }
     }
+    const int n_, spin_us_;
     std::vector<std::thread> threads_;
-    std::vector<Job> jobs_;
     std::mutex m_;
     std::condition_variable cv_;
+    std::atomic<unsigned long long> gen_{0};
     std::atomic<int> pending_{0};
-    bool stop_ = false;
+    std::atomic<bool> stop_{false};
+    int sleepers_ = 0;
+    void (*fn_)(void*, int) = nullptr;
+    void* ctx_ = nullptr;
+    int count_ = 0, parts_ = 1;
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -247,6 +260,9 @@ struct mcpyb_engine {
     uint8_t trk_pbc[3];
     double trk_E = 0.0;
     long long trk_full = 0, trk_incremental = 0;
+    bool trkb_timing = false;             // MCPYB_TRK_TIMING=1: host-side split of the batched tracked call, printed at destroy
+    double trkb_t_compare = 0.0, trkb_t_build = 0.0, trkb_t_trial = 0.0, trkb_t_stage = 0.0, trkb_t_launch = 0.0, trkb_t_wait = 0.0;
+    long long trkb_calls = 0;
     // ... and of a resident BATCH of bases (mcpyb_tracked_energies_host): slot r holds rows
     // [trkb_off[r], trkb_off[r+1]) of trkb_pos / trkb_Z
     bool trkb_valid = false;
@@ -612,6 +628,7 @@ int mcpyb_create(int device, mcpyb_engine** out) {
     if (const char* v = getenv("MCPYB_CHAIN")) e->use_chain = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_EMT_LISTS")) e->use_emt_lists = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_ER_MINB")) e->er_minb = atoi(v);
+    if (const char* v = getenv("MCPYB_TRK_TIMING")) e->trkb_timing = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_RW_MINB")) { const int n = atoi(v); if (n >= 4 && n <= 6) e->rw_minb = n; }
     if (const char* v = getenv("MCPYB_L2PERSIST")) {
         e->l2_persist_mb = atoi(v);
@@ -633,6 +650,10 @@ void mcpyb_destroy(mcpyb_engine* e) {
     cudaSetDevice(e->device);
     chain_stop(e);
     cudaStreamSynchronize(e->stream);
+    if (e->trkb_timing && e->trkb_calls)
+        fprintf(stderr, "[mcpyb] batched tracked calls %lld: compare %.1f us, build %.1f us, trial call %.1f us (stage + H2D %.1f, launch %.1f, wait %.1f) (means)\n", e->trkb_calls,
+                1e6 * e->trkb_t_compare / e->trkb_calls, 1e6 * e->trkb_t_build / e->trkb_calls, 1e6 * e->trkb_t_trial / e->trkb_calls,
+                1e6 * e->trkb_t_stage / e->trkb_calls, 1e6 * e->trkb_t_launch / e->trkb_calls, 1e6 * e->trkb_t_wait / e->trkb_calls);
     if (e->chain_mb) cudaFreeHost(e->chain_mb);
     if (e->chain_ev) cudaEventDestroy(e->chain_ev);
     if (e->chain_stream) cudaStreamDestroy(e->chain_stream);
@@ -774,8 +795,12 @@ int mcpyb_emt_species(const mcpyb_engine* e, int Z, double* out9) {
 static CopyPool* copy_pool_for(mcpyb_engine* e, size_t bytes) {
     if (bytes < (1u << 20)) return nullptr;
     if (!e->copy_pool) {
+        // helper threads: MCPYB_POOL_THREADS, else 7 of >= 16 cores, 3 of >= 8, 1 of >= 4
         const unsigned hw = std::thread::hardware_concurrency();
-        e->copy_pool = new CopyPool(hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
+        int nw = hw >= 16 ? 7 : (hw >= 8 ? 3 : (hw >= 4 ? 1 : 0)), spin = 150;
+        if (const char* v = getenv("MCPYB_POOL_THREADS")) { nw = atoi(v); if (nw < 0) nw = 0; if (nw > 63) nw = 63; }
+        if (const char* v = getenv("MCPYB_POOL_SPIN_US")) { spin = atoi(v); if (spin < 0) spin = 0; }
+        e->copy_pool = new CopyPool(nw, spin);
     }
     return e->copy_pool;
 }
@@ -1207,7 +1232,10 @@ static int stencil_lists(mcpyb_engine* e, bool few_sites, StencilLists* xl) {
 static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int32_t* d_old_off,
                          const int32_t* d_old_idx, const int32_t* d_new_off, const double* d_new_pos,
                          const int32_t* d_new_Z, int n_old_total, int n_new_total,
-                         double* d_dE, int32_t* d_pairs, unsigned long long* d_status = nullptr) {
+                         double* d_dE, int32_t* d_pairs, unsigned long long* d_status = nullptr,
+                         volatile unsigned int* d_flag = nullptr, unsigned int flag_seq = 0) {
+    // d_flag (single-launch LJ batches only): d_dE / d_pairs / d_status are pinned host memory, the kernel's last CTA
+    // writes flag_seq to *d_flag after them
     if (T == 0) return MCPYB_OK;
     TrialBatch tb;
     tb.T = T; tb.rep = d_rep; tb.old_off = d_old_off; tb.old_idx = d_old_idx;
@@ -1263,7 +1291,7 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
             int rc = stencil_lists(e, true, &xs);
             if (rc != MCPYB_OK) return rc;
             lj_trial_small_kernel<<<nsites, RS_THREADS, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs,
-                                                                         (int*)(e->tw_err.p + 2), xs);
+                                                                         (int*)(e->tw_err.p + 2), xs, d_flag, flag_seq);
             LAUNCH_CHECK("lj_trial_small_kernel");
         } else {
             lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
@@ -1398,6 +1426,8 @@ int mcpyb_trial_delta_e_dev(mcpyb_engine* e, int T, const int32_t* d_rep, const 
                          d_dE_out, d_pairs_out);
 }
 
+static bool wait_flag(volatile unsigned int* flag, unsigned int seq);
+
 int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const int32_t* old_off,
                              const int32_t* old_idx, const int32_t* new_off, const double* new_pos,
                              const int32_t* new_Z, double* dE_out, int32_t* pairs_out) {
@@ -1476,6 +1506,7 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
     const bool direct = !small && is_pinned_host(old_off) && is_pinned_host(new_off) && (!rep || is_pinned_host(rep)) &&
                         (!n_old || is_pinned_host(old_idx)) && (!n_new || is_pinned_host(new_pos)) &&
                         (!(n_new && new_Z && e->pot_kind == POT_EMT) || is_pinned_host(new_Z));
+    const auto tq0 = std::chrono::steady_clock::now();
     if (small) {
         if (rep) memcpy(h + o_rep, rep, (size_t)T * 4);
         memcpy(h + o_oo, old_off, (size_t)(T + 1) * 4);
@@ -1504,17 +1535,38 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
         CK(cudaEventRecord(e->copy_ev, cs), "cudaEventRecord (copy)");
         CK(cudaStreamWaitEvent(e->stream, e->copy_ev, 0), "cudaStreamWaitEvent (copy)");
     }
+    const size_t ob = (size_t)(T + 1) * sizeof(double), pb = (size_t)T * sizeof(int);
+    const size_t o_flag = align_up(ob + pb, 8);
+    CK(e->trial_out_pin.reserve(o_flag + 8), "cudaMallocHost trial out");
+    // A batch the single-launch LJ kernel takes: its last CTA writes dE, the pair counts and the status word straight
+    // into the pinned block and then a sequence word the host polls -- no D2H copies, no stream synchronisation
+    // (~12 us of a ~45 us call for the 64-replica batch of BatchedReplicaExchange).
+    const bool flagged = small && e->pot_kind == POT_LJ && n_old + n_new > 0 && n_old + n_new <= RS_MAX_SITES;
+    volatile unsigned int* h_flag = (volatile unsigned int*)(e->trial_out_pin.p + o_flag);
+    unsigned int seq = 0;
+    if (flagged) { seq = ++e->tiny_seq; *h_flag = seq - 1; }
+    const auto tq1 = std::chrono::steady_clock::now();
     int rc = launch_trials(e, T, rep ? (const int32_t*)(d + o_rep) : nullptr, (const int32_t*)(d + o_oo), (const int32_t*)(d + o_oi),
                            (const int32_t*)(d + o_no), (const double*)(d + o_np),
-                           (new_Z && e->pot_kind == POT_EMT) ? (const int32_t*)(d + o_nz) : nullptr, n_old, n_new, e->dE.p, e->tpairs.p,
-                           (unsigned long long*)(e->dE.p + T));
+                           (new_Z && e->pot_kind == POT_EMT) ? (const int32_t*)(d + o_nz) : nullptr, n_old, n_new,
+                           flagged ? (double*)e->trial_out_pin.p : e->dE.p,
+                           flagged ? (pairs_out ? (int32_t*)(e->trial_out_pin.p + ob) : nullptr) : e->tpairs.p,
+                           flagged ? (unsigned long long*)(e->trial_out_pin.p + (size_t)T * sizeof(double)) : (unsigned long long*)(e->dE.p + T),
+                           flagged ? h_flag : nullptr, seq);
     if (rc != MCPYB_OK) return rc;
-    const size_t ob = (size_t)(T + 1) * sizeof(double), pb = (size_t)T * sizeof(int);
-    CK(e->trial_out_pin.reserve(ob + pb), "cudaMallocHost trial out");
     // status word first, then dE in two halves: the host copies half 1 out while half 2 is in flight
     const size_t half = ((size_t)T / 2) * sizeof(double), full = (size_t)T * sizeof(double);
     const bool out_direct = !small && is_pinned_host(dE_out) && (!pairs_out || is_pinned_host(pairs_out));
-    if (small) {
+    const auto tq2 = std::chrono::steady_clock::now();
+    if (flagged) {
+        if (!wait_flag(h_flag, seq)) CK(cudaStreamSynchronize(e->stream), "sync trials");
+        if (e->trkb_timing) {
+            const auto tq3 = std::chrono::steady_clock::now();
+            e->trkb_t_stage += std::chrono::duration<double>(tq1 - tq0).count();
+            e->trkb_t_launch += std::chrono::duration<double>(tq2 - tq1).count();
+            e->trkb_t_wait += std::chrono::duration<double>(tq3 - tq2).count();
+        }
+    } else if (small) {
         CK(cudaMemcpyAsync(e->trial_out_pin.p, e->dE.p, ob, cudaMemcpyDeviceToHost, e->stream), "D2H dE");
         if (pairs_out) CK(cudaMemcpyAsync(e->trial_out_pin.p + ob, e->tpairs.p, pb, cudaMemcpyDeviceToHost, e->stream), "D2H pairs");
         CK(cudaStreamSynchronize(e->stream), "sync trials");
@@ -1909,6 +1961,8 @@ static int tracked_energies_core(mcpyb_engine* e, int R, const double* const* po
         bool ok = false;
     };
     std::vector<Own> own(incremental ? (size_t)R : 0);
+    const auto tk0 = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); };
     auto try_slot = [&](int r, int q, int32_t* old_idx, int* new_row, int& n_old, int& n_new) -> bool {
         if (q >= Rb) return false;
         const int n = (int)n_of[r];
@@ -1931,6 +1985,8 @@ static int tracked_energies_core(mcpyb_engine* e, int R, const double* const* po
         CopyPool* pool = copy_pool_for(e, touched);
         if (pool) pool->parallel_for(R, body, &ctx); else for (int r = 0; r < R; ++r) body(&ctx, r);
     }
+    const double t_cmp = since(tk0);
+    const auto tk1 = std::chrono::steady_clock::now();
     if (incremental) {
         int32_t old_idx_buf[kLimit];
         int new_row_buf[kLimit];
@@ -1962,6 +2018,8 @@ static int tracked_energies_core(mcpyb_engine* e, int R, const double* const* po
         const int T = (int)t_rep.size();
         std::vector<double> dE((size_t)(T > 0 ? T : 1), 0.0);
         bool finite = true;
+        const double t_build = since(tk1);
+        const auto tk2 = std::chrono::steady_clock::now();
         if (T > 0) {
             const bool keep = e->trkb_valid;
             int rc = mcpyb_trial_delta_e_host(e, T, t_rep.data(), t_old_off.data(), t_old_idx.data(), t_new_off.data(),
@@ -1976,6 +2034,7 @@ static int tracked_energies_core(mcpyb_engine* e, int R, const double* const* po
                 if (paths_out) paths_out[r] = trial_of[r] >= 0 ? 1 : 2;
             }
             e->trk_incremental += T;
+            if (e->trkb_timing) { e->trkb_t_compare += t_cmp; e->trkb_t_build += t_build; e->trkb_t_trial += since(tk2); e->trkb_calls++; }
             return MCPYB_OK;
         }
     }

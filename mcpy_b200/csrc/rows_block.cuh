@@ -576,7 +576,7 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, 
 // publishes the validation status: no histogram, scan, scatter or separate combine launch.
 // ---------------------------------------------------------------------------
 #define RS_THREADS 128
-#define RS_MAX_SITES 128           // batches up to this many sites take the single-launch kernel
+#define RS_MAX_SITES 1024          // batches up to this many sites take the single-launch kernel
 #define RS_CAND 1024              // candidates of one stencil held in shared memory per chunk
 
 struct RowsSmallSmem {
@@ -652,42 +652,60 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
             const long long lo_bits = __double_as_longlong(p.rc2 - bw), hi_bits = __double_as_longlong(p.rc2 + bw);
             for (int cbase = 0; cbase < total; cbase += RS_CAND) {
                 const int n = min(RS_CAND, total - cbase);
-                for (int i = tid; i < n; i += RS_THREADS) {
-                    const int gi = cbase + i;
-                    double4 q;
-                    int2 info = make_int2(0, 0);
-                    bool keep = true;
-                    if (listed) q = xq[gi];
-                    else {
-                        rp_stage_candidate(g, spos, sm.pc, npieces, gi, q, info);
-                        keep = rb_keep_candidate(g, c[0], c[1], c[2], q.x, q.y, q.z, reach);
-                    }
-                    const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
-                    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    const long long rb = __double_as_longlong(r2);
-                    bool in = keep && rb < lo_bits;
-                    if (keep && !in && rb <= hi_bits) in = rp_exact_r2(g, spos, listed ? xi[gi] : info, px, py, pz, wsite) <= p.rc2;
-                    const int j = __double2loint(q.w);
-                    for (int e = ob; e < oe; ++e) if (tb.old_idx[e] == j) in = false;
+                // c6 of the chunk's KEPT candidates, compacted in list order (a listed cell holds kept ones only)
+                int kept = 0;
+                for (int i0 = 0; i0 < n; i0 += RS_THREADS) {
+                    const int i = i0 + tid;
+                    bool keep = false, in = false;
                     double c6 = 0.0;
-                    if (in) { const double tt = p.sigma2 * fast_rcp(r2); c6 = tt * tt * tt; }
-                    sm.c6[i] = c6;
-                    sm.hit[i] = (in ? 1 : 0) | (keep ? 2 : 0);
-                }
-                __syncthreads();
-                if (tid < 4) {
-                    for (int i = 0; i < n; ++i) {
-                        const int h = sm.hit[i];
-                        if (!(h & 2)) continue;                  // pruned: holds no list position
-                        if ((kpos & 3) == tid) {
-                            const double c6 = sm.c6[i];
-                            a12 = fma(c6, c6, a12);
-                            a6 += c6;
-                            cc += h & 1;
+                    if (i < n) {
+                        const int gi = cbase + i;
+                        double4 q;
+                        int2 info = make_int2(0, 0);
+                        keep = true;
+                        if (listed) q = xq[gi];
+                        else {
+                            rp_stage_candidate(g, spos, sm.pc, npieces, gi, q, info);
+                            keep = rb_keep_candidate(g, c[0], c[1], c[2], q.x, q.y, q.z, reach);
                         }
-                        ++kpos;
+                        const double dx = q.x - qx, dy = q.y - qy, dz = q.z - qz;
+                        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                        const long long rb = __double_as_longlong(r2);
+                        in = keep && rb < lo_bits;
+                        if (keep && !in && rb <= hi_bits) in = rp_exact_r2(g, spos, listed ? xi[gi] : info, px, py, pz, wsite) <= p.rc2;
+                        const int j = __double2loint(q.w) & 0xFFFFFF;
+                        for (int e = ob; e < oe; ++e) if (tb.old_idx[e] == j) in = false;
+                        if (in) { const double tt = p.sigma2 * fast_rcp(r2); c6 = tt * tt * tt; }
+                    }
+                    if (listed) {
+                        if (i < n) { sm.c6[i] = c6; sm.hit[i] = in ? 1 : 0; }
+                    } else {
+                        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                        if (lane == 0) sm.partc[wid] = __popc(bal);
+                        __syncthreads();
+                        int before = 0, all = 0;
+                        for (int k = 0; k < RS_THREADS / 32; ++k) { const int v = sm.partc[k]; all += v; if (k < wid) before += v; }
+                        if (keep) {
+                            const int at = kept + before + __popc(bal & ((1u << lane) - 1u));
+                            sm.c6[at] = c6;
+                            sm.hit[at] = in ? 1 : 0;
+                        }
+                        kept += all;
+                        __syncthreads();
                     }
                 }
+                if (listed) kept = n;
+                __syncthreads();
+                // class k = the kept candidates at list positions = k (mod 4), each summed in list order
+                if (tid < 4) {
+                    for (int i = (tid - kpos) & 3; i < kept; i += 4) {
+                        const double c6 = sm.c6[i];
+                        a12 = fma(c6, c6, a12);
+                        a6 += c6;
+                        cc += sm.hit[i];
+                    }
+                }
+                kpos += kept;
                 __syncthreads();
             }
         }
@@ -739,9 +757,11 @@ __device__ __forceinline__ void lj_trial_small_body(RowsSmallSmem& sm, const Bat
 
 __global__ void __launch_bounds__(RS_THREADS)
 lj_trial_small_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p,
-                      double* __restrict__ dE, int* __restrict__ npairs, int* __restrict__ done_counter, StencilLists x) {
+                      double* __restrict__ dE, int* __restrict__ npairs, int* __restrict__ done_counter, StencilLists x,
+                      volatile unsigned int* done_flag, unsigned int seq) {
+    // done_flag != nullptr: dE / npairs / the status word are pinned host memory and the host polls done_flag
     __shared__ RowsSmallSmem sm;
-    lj_trial_small_body(sm, b, tb, w, p, dE, npairs, done_counter, x);
+    lj_trial_small_body(sm, b, tb, w, p, dE, npairs, done_counter, x, done_flag, seq);
 }
 
 // One trial whose description travels in the kernel's parameter space and whose result is written
