@@ -106,6 +106,10 @@ int mcpyb_potential_energies_host(mcpyb_engine* e, int R, const int64_t* atom_of
 int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const int32_t* numbers,
                               int n, const double* cell9, const uint8_t* pbc3,
                               double* energy_out, int* path_out);
+/* The same call with the atomic numbers as int64 (what ase.Atoms.numbers holds): the caller converts nothing. */
+int mcpyb_tracked_energy_z64_host(mcpyb_engine* e, const double* positions, const int64_t* numbers,
+                                  int n, const double* cell9, const uint8_t* pbc3,
+                                  double* energy_out, int* path_out);
 
 /* Forces of the resident batch, host array [sum N][3] (eV/A): ASE's results['forces'] of
  * LennardJones / EMT.  Replaces the forces the ASE calculators hand to the optimisers behind

@@ -21,7 +21,7 @@ SYMBOLS = [
     'mcpyb_create', 'mcpyb_destroy', 'mcpyb_last_error', 'mcpyb_version', 'mcpyb_set_stream',
     'mcpyb_synchronize', 'mcpyb_set_lj', 'mcpyb_set_emt', 'mcpyb_cutoff', 'mcpyb_emt_species',
     'mcpyb_upload_host', 'mcpyb_upload_dev', 'mcpyb_energies_host', 'mcpyb_energies_dev',
-    'mcpyb_potential_energies_host', 'mcpyb_tracked_energy_host', 'mcpyb_atom_energies_host',
+    'mcpyb_potential_energies_host', 'mcpyb_tracked_energy_host', 'mcpyb_tracked_energy_z64_host', 'mcpyb_atom_energies_host',
     'mcpyb_tracked_energies_host', 'mcpyb_tracked_energies_rows_host', 'mcpyb_forces_host', 'mcpyb_energy_forces_host', 'mcpyb_relax_lbfgs_host',
     'mcpyb_trial_delta_e_host', 'mcpyb_trial_delta_e_dev',
     'mcpyb_neighbor_pairs_host',
@@ -74,6 +74,7 @@ def load():
     lib.mcpyb_energies_dev.argtypes = [_p, _p]
     lib.mcpyb_potential_energies_host.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p, _p]
     lib.mcpyb_tracked_energy_host.argtypes = [_p, _p, _p, C.c_int, _p, _p, _p, _p]
+    lib.mcpyb_tracked_energy_z64_host.argtypes = [_p, _p, _p, C.c_int, _p, _p, _p, _p]
     lib.mcpyb_atom_energies_host.argtypes = [_p, _p, _p]
     lib.mcpyb_tracked_energies_host.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p, _p, _p]
     lib.mcpyb_tracked_energies_rows_host.argtypes = [_p, C.c_int, _p, _p, C.c_int, _p, _p, _p, _p, _p]

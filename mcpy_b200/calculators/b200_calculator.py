@@ -86,9 +86,14 @@ class _B200Core:
             if atoms is None:
                 raise ValueError('get_potential_energy() needs an Atoms object')
         self.n_energy_calls += 1
-        cell = np.asarray(atoms.cell, dtype=np.float64)
         if self.incremental:
             # one resident base + a delta per call; same numbers as the full path to rounding
+            res = self.engine.tracked_energy_atoms(atoms)
+            if res is not None:
+                self.path_counts[res[1]] += 1
+                return res[0]
+        cell = np.asarray(atoms.cell, dtype=np.float64)
+        if self.incremental:
             e, path = self.engine.tracked_energy(atoms.positions, atoms.numbers, cell, atoms.pbc)
             self.path_counts[path] += 1
             return e

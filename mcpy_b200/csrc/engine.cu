@@ -1730,8 +1730,10 @@ static int chain_trial(mcpyb_engine* e, int n_old, const int32_t* old_idx, int n
 // E_base + dE(base -> incoming) from the trial kernels.  There is no accept / reject inference and
 // no drift: every answer is one full evaluation plus ONE delta.  When the difference grows beyond a
 // few atoms (accepted moves accumulate) the incoming configuration becomes the new base.
-int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const int32_t* numbers, int n,
-                              const double* cell9, const uint8_t* pbc3, double* energy_out, int* path_out) {
+extern "C++" {
+template <class ZT>
+static int tracked_energy_core(mcpyb_engine* e, const double* positions, const ZT* numbers, int n,
+                               const double* cell9, const uint8_t* pbc3, double* energy_out, int* path_out) {
     if (!e) return MCPYB_ERR_ARG;
     cudaSetDevice(e->device);
     if (n < 0 || !cell9 || !pbc3 || !energy_out || (n > 0 && !positions)) return e->fail(MCPYB_ERR_ARG, "bad arguments");
@@ -1739,7 +1741,7 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
     if (e->pot_kind == POT_EMT && n > 0 && !numbers) return e->fail(MCPYB_ERR_ARG, "EMT needs atomic numbers");
     const double tol = 1e-10;
     const int kRebase = 16;                      // moved atoms (old + new) beyond which we re-base
-    auto zof = [&](int j) { return numbers ? numbers[j] : 0; };
+    auto zof = [&](int j) -> int32_t { return numbers ? (int32_t)numbers[j] : 0; };
     bool same_box = e->trk_valid && memcmp(e->trk_cell, cell9, sizeof e->trk_cell) == 0 &&
                     memcmp(e->trk_pbc, pbc3, 3) == 0 && e->have_batch && e->R == 1;
     int32_t old_idx[2 * MCPYB_MAX_MOVED];
@@ -1759,7 +1761,12 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
         const int kBlock = 64;
         auto same_block = [&](int i0, int j0) {
             if (memcmp(B + 3 * (size_t)i0, positions + 3 * (size_t)j0, (size_t)kBlock * 24) != 0) return false;
-            if (numbers) return memcmp(e->trk_Z.data() + i0, numbers + j0, (size_t)kBlock * 4) == 0;
+            if (numbers && sizeof(ZT) == sizeof(int32_t)) return memcmp(e->trk_Z.data() + i0, numbers + j0, (size_t)kBlock * 4) == 0;
+            if (numbers) {
+                int diff = 0;
+                for (int k = 0; k < kBlock; ++k) diff |= (long long)e->trk_Z[i0 + k] != (long long)numbers[j0 + k];
+                return diff == 0;
+            }
             for (int k = 0; k < kBlock; ++k) if (e->trk_Z[i0 + k] != 0) return false;
             return true;
         };
@@ -1870,7 +1877,13 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
     }
     // full evaluation; the incoming configuration becomes the base
     const int64_t off[2] = {0, n};
-    int rc = upload_host_impl(e, e->subdiv_trials, 1, off, positions, numbers, cell9, pbc3);
+    std::vector<int32_t> z32;
+    const int32_t* numbers32 = nullptr;
+    if (numbers) {
+        if (sizeof(ZT) == sizeof(int32_t)) numbers32 = (const int32_t*)numbers;
+        else { z32.resize((size_t)n); for (int j = 0; j < n; ++j) z32[j] = (int32_t)numbers[j]; numbers32 = z32.data(); }
+    }
+    int rc = upload_host_impl(e, e->subdiv_trials, 1, off, positions, numbers32, cell9, pbc3);
     if (rc != MCPYB_OK) return rc;
     double E = 0.0;
     rc = mcpyb_energies_host(e, &E, nullptr);
@@ -1886,6 +1899,18 @@ int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const in
     *energy_out = E;
     if (path_out) *path_out = 0;
     return MCPYB_OK;
+}
+}  // extern "C++"
+
+int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const int32_t* numbers, int n,
+                              const double* cell9, const uint8_t* pbc3, double* energy_out, int* path_out) {
+    return tracked_energy_core<int32_t>(e, positions, numbers, n, cell9, pbc3, energy_out, path_out);
+}
+
+// The same call with the atomic numbers as ase.Atoms keeps them (int64): no conversion pass on the caller's side.
+int mcpyb_tracked_energy_z64_host(mcpyb_engine* e, const double* positions, const int64_t* numbers, int n,
+                                  const double* cell9, const uint8_t* pbc3, double* energy_out, int* path_out) {
+    return tracked_energy_core<int64_t>(e, positions, numbers, n, cell9, pbc3, energy_out, path_out);
 }
 
 // Align an incoming configuration P with a base B: rows equal within 1e-10 A and of the same species

@@ -122,7 +122,83 @@ static PyObject* rows(PyObject* self, PyObject* args) {
     return PyLong_FromLong(bad ? -1 : (ztype == 8 ? 1 : 0));
 }
 
+/* One configuration: positions / numbers / cell / pbc of `a` read in place (0), or -1. */
+typedef struct { const double* pos; const void* num; int64_t n; int zwidth; double cell[9]; uint8_t pbc[3]; } OneConfig;
+
+static int read_one(PyObject* a, OneConfig* o) {
+    PyObject *p = NULL, *z = NULL, *c = NULL, *b = NULL;
+    int bad = 0;
+    PyObject* arrays = attr(a, s_arrays);
+    if (arrays && PyDict_CheckExact(arrays)) {
+        p = PyDict_GetItemWithError(arrays, s_positions);
+        z = PyDict_GetItemWithError(arrays, s_numbers);
+        Py_XINCREF(p); Py_XINCREF(z);
+        PyErr_Clear();
+        PyObject* co = attr(a, s_cellobj);
+        if (co) { c = attr(co, s_array); Py_DECREF(co); }
+        b = attr(a, s_pbc_priv);
+    }
+    Py_XDECREF(arrays);
+    if (!p) p = attr(a, s_positions);
+    if (!z) z = attr(a, s_numbers);
+    if (!c) {
+        c = attr(a, s_cell);
+        if (c && !PyArray_Check(c)) { PyObject* inner = attr(c, s_array); Py_DECREF(c); c = inner; }
+    }
+    if (!b) b = attr(a, s_pbc);
+    if (!plain(p, NPY_FLOAT64) || PyArray_NDIM((PyArrayObject*)p) != 2 || PyArray_DIM((PyArrayObject*)p, 1) != 3) bad = 1;
+    if (!bad) {
+        const npy_intp n = PyArray_DIM((PyArrayObject*)p, 0);
+        o->n = (int64_t)n;
+        o->pos = n ? (const double*)PyArray_DATA((PyArrayObject*)p) : NULL;
+        const int zt = z && PyArray_Check(z) ? PyArray_TYPE((PyArrayObject*)z) : -1;
+        const int w = (zt == NPY_INT64 || (zt == NPY_LONG && sizeof(long) == 8) || zt == NPY_LONGLONG) ? 8
+                    : (zt == NPY_INT32 || (zt == NPY_LONG && sizeof(long) == 4) || zt == NPY_INT) ? 4 : 0;
+        if (!w || !plain(z, zt) || PyArray_NDIM((PyArrayObject*)z) != 1 || PyArray_DIM((PyArrayObject*)z, 0) != n) bad = 1;
+        else { o->zwidth = w; o->num = n ? PyArray_DATA((PyArrayObject*)z) : NULL; }
+    }
+    if (!bad) {
+        if (!plain(c, NPY_FLOAT64) || PyArray_SIZE((PyArrayObject*)c) != 9) bad = 1;
+        else memcpy(o->cell, PyArray_DATA((PyArrayObject*)c), 72);
+    }
+    if (!bad) {
+        if (!b || !PyArray_Check(b) || PyArray_ITEMSIZE((PyArrayObject*)b) != 1 || PyArray_SIZE((PyArrayObject*)b) != 3 ||
+            !PyArray_IS_C_CONTIGUOUS((PyArrayObject*)b)) bad = 1;
+        else {
+            const uint8_t* s = (const uint8_t*)PyArray_DATA((PyArrayObject*)b);
+            o->pbc[0] = s[0] != 0; o->pbc[1] = s[1] != 0; o->pbc[2] = s[2] != 0;
+        }
+    }
+    /* the arrays stay alive through `a` (the caller holds it, and the GIL, until the engine call returns) */
+    Py_XDECREF(p); Py_XDECREF(z); Py_XDECREF(c); Py_XDECREF(b);
+    if (PyErr_Occurred()) PyErr_Clear();
+    return bad ? -1 : 0;
+}
+
+typedef int (*tracked_fn)(void*, const double*, const void*, int, const double*, const uint8_t*, double*, int*);
+
+/* tracked_energy(fn_i32, fn_i64, engine, atoms) -> (status, energy, path, n_atoms) or None (cannot read `atoms` in place).
+ * fn_i32 / fn_i64: addresses of mcpyb_tracked_energy_host / mcpyb_tracked_energy_z64_host (include/mcpy_b200.h),
+ * engine: the mcpyb_engine handle.  The drop-in call of a Monte-Carlo chain -- one per trial -- without the ~5 us
+ * of numpy / ctypes marshalling around a ~9 us engine call. */
+static PyObject* tracked_energy(PyObject* self, PyObject* args) {
+    PyObject *o32, *o64, *oh, *atoms;
+    if (!PyArg_ParseTuple(args, "OOOO", &o32, &o64, &oh, &atoms)) return NULL;
+    void* f32 = PyLong_AsVoidPtr(o32);
+    void* f64 = PyLong_AsVoidPtr(o64);
+    void* h = PyLong_AsVoidPtr(oh);
+    if (PyErr_Occurred()) return NULL;
+    if (!f32 || !f64 || !h) { PyErr_SetString(PyExc_ValueError, "marshal.tracked_energy: null function or engine"); return NULL; }
+    OneConfig c;
+    if (read_one(atoms, &c) != 0 || c.n > 0x7fffffff) Py_RETURN_NONE;
+    double e = 0.0;
+    int path = 0;
+    const int rc = ((tracked_fn)(c.zwidth == 8 ? f64 : f32))(h, c.pos, c.num, (int)c.n, c.cell, c.pbc, &e, &path);
+    return Py_BuildValue("(idiL)", rc, e, path, (long long)c.n);
+}
+
 static PyMethodDef methods[] = {
+    {"tracked_energy", tracked_energy, METH_VARARGS, "one tracked energy call on an Atoms-like object"},
     {"rows", rows, METH_VARARGS, "fill the per-configuration pointer tables of a batched engine call"},
     {NULL, NULL, 0, NULL}};
 

@@ -53,6 +53,7 @@ class Engine:
         self._e1_ptr = self._e1.ctypes.data
         self._path_ref = C.byref(self._path)
         self._tables = None                            # pointer / size tables of tracked_energies_atoms
+        self._tracked_fns = None                       # (fn int32, fn int64, handle) addresses for _marshal.tracked_energy
         self._table_ptrs = None
 
     # -- plumbing ------------------------------------------------------------
@@ -298,6 +299,26 @@ class Engine:
         self._R = 1
         self._ntot = n
         return float(self._e1[0])
+
+    def tracked_energy_atoms(self, atoms):
+        """``tracked_energy`` of an ``ase.Atoms``-like object with the attribute walk and the C call made by the
+        CPython helper (csrc/marshal.c); None when ``atoms`` cannot be read in place (the caller marshals with
+        numpy)."""
+        if _marshal is None:
+            return None
+        fns = self._tracked_fns
+        if fns is None:
+            cast = lambda f: C.cast(f, C.c_void_p).value                      # noqa: E731
+            fns = self._tracked_fns = (cast(self._lib.mcpyb_tracked_energy_host),
+                                       cast(self._lib.mcpyb_tracked_energy_z64_host), self._h.value)
+        res = _marshal.tracked_energy(fns[0], fns[1], fns[2], atoms)
+        if res is None:
+            return None
+        if res[0] != 0:
+            self._check(res[0])
+        self._R = 1
+        self._ntot = res[3]
+        return res[1], res[2]
 
     def tracked_energy(self, positions, numbers, cell, pbc):
         """Single configuration through the incremental path (base + one delta); returns
