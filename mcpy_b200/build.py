@@ -40,16 +40,16 @@ def marshal_path() -> str:
 
 
 def build_marshal(force: bool = False) -> str:
-    """The CPython helper that walks an atoms list for the batched call (csrc/marshal.c; plain gcc, no CUDA)."""
+    """The CPython helper that walks an atoms list for the batched call (csrc/marshal.cpp; plain gcc, no CUDA)."""
     import sysconfig
-    src, out = os.path.join(CSRC, 'marshal.c'), marshal_path()
+    src, out = os.path.join(CSRC, 'marshal.cpp'), marshal_path()
     if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
         return out
-    cc = shutil.which('gcc') or shutil.which('cc')
+    cc = shutil.which('g++') or shutil.which('c++')
     if not cc:
-        raise RuntimeError('gcc not found: cannot build the marshalling helper')
+        raise RuntimeError('g++ not found: cannot build the marshalling helper')
     import numpy
-    cmd = [cc, '-O2', '-shared', '-fPIC', '-Wall', '-I' + sysconfig.get_paths()['include'], '-I' + numpy.get_include(),
+    cmd = [cc, '-O2', '-std=c++17', '-shared', '-fPIC', '-Wall', '-I' + sysconfig.get_paths()['include'], '-I' + numpy.get_include(),
            '-o', out, src]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:

@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 from ._lib import EngineError, as_f64, as_i32, as_i64, as_u8, ptr
 
-try:                                      # host-side marshalling helper (csrc/marshal.c, built by mcpy_b200.build)
+try:                                      # host-side marshalling helper (csrc/marshal.cpp, built by mcpy_b200.build)
     from . import _marshal
 except ImportError:                       # not built: the numpy marshalling below does the same work, slower
     _marshal = None
@@ -224,7 +224,7 @@ class Engine:
 
     def tracked_energies_atoms(self, atoms_list):
         """``tracked_energies`` of a list of ``ase.Atoms``-like configurations, the walk over the list done by the
-        CPython helper (csrc/marshal.c: ~10 us for 64 configurations, against ~135 us from Python).  Returns None
+        CPython helper (csrc/marshal.cpp: ~10 us for 64 configurations, against ~135 us from Python).  Returns None
         when some configuration cannot be read in place (the caller then marshals with numpy)."""
         if _marshal is None:
             return None
@@ -302,7 +302,7 @@ class Engine:
 
     def tracked_energy_atoms(self, atoms):
         """``tracked_energy`` of an ``ase.Atoms``-like object with the attribute walk and the C call made by the
-        CPython helper (csrc/marshal.c); None when ``atoms`` cannot be read in place (the caller marshals with
+        CPython helper (csrc/marshal.cpp); None when ``atoms`` cannot be read in place (the caller marshals with
         numpy)."""
         if _marshal is None:
             return None

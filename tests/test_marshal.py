@@ -1,4 +1,4 @@
-"""The CPython marshalling helper (csrc/marshal.c) against the numpy marshalling it replaces (Engine._row_pointers):
+"""The CPython marshalling helper (csrc/marshal.cpp) against the numpy marshalling it replaces (Engine._row_pointers):
 same pointer / size tables, cells and pbcs for ase.Atoms-like and plain attribute objects, -1 for anything that
 cannot be read in place.  No GPU needed."""
 import numpy as np
