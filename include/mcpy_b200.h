@@ -86,6 +86,15 @@ int mcpyb_upload_host(mcpyb_engine* e, int R, const int64_t* atom_off,
 int mcpyb_upload_dev(mcpyb_engine* e, int R, const int64_t* atom_off,
                      const double* d_positions, const int32_t* d_numbers,
                      const double* cells, const uint8_t* pbc);
+/* nseg small copies between device-accessible buffers in ONE launch on the engine's stream (48 segments per launch):
+ * count[k] elements from src[k] to dst[k], kind[k] = 0: float64 -> float64, 1: int32 -> int32, 2: float64 -> int32,
+ * 3: int32 -> float64.  A ladder shard that keeps its replicas in HBM uses it twice per exchange round
+ * (BatchedReplicaExchange._attempt_exchanges / _swap_states, batched_replica_exchange.py:310-410): to pack its
+ * records (page-locked host memory, read in place) and boundary configurations into the all_gather buffer, and to
+ * move the replica blocks into their new slots afterwards -- a dozen framework copies otherwise, ~10 us of host
+ * time each.  Sources and destinations must not overlap.                                                        */
+int mcpyb_copy_segments_dev(mcpyb_engine* e, int nseg, const uint64_t* src, const uint64_t* dst,
+                            const int64_t* count, const uint8_t* kind);
 /* Energies of the resident batch -> host array [R] (synchronises).
  * pairs_out (may be NULL) receives the number of unordered in-cutoff pairs.   */
 int mcpyb_energies_host(mcpyb_engine* e, double* energies_out, int64_t* pairs_out);

@@ -29,7 +29,7 @@ SYMBOLS = [
     'mcpyb_sphere_free_volume_pcg64', 'mcpyb_dome_free_volume_pcg64', 'mcpyb_box_free_volume_pcg64',
     'mcpyb_alloc_pinned', 'mcpyb_free_pinned',
     'mcpyb_min_dist2_host', 'mcpyb_pcg64_host_doubles', 'mcpyb_fp64_peak_tflops', 'mcpyb_stage_timing', 'mcpyb_launch_count',
-    'mcpyb_resident_chain', 'mcpyb_set_precision',
+    'mcpyb_resident_chain', 'mcpyb_set_precision', 'mcpyb_copy_segments_dev',
 ]
 
 _p = C.c_void_p
@@ -70,6 +70,7 @@ def load():
     lib.mcpyb_emt_species.argtypes = [_p, C.c_int, _f64p]
     lib.mcpyb_upload_host.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p]
     lib.mcpyb_upload_dev.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p]
+    lib.mcpyb_copy_segments_dev.argtypes = [_p, C.c_int, _p, _p, _p, _p]
     lib.mcpyb_energies_host.argtypes = [_p, _p, _p]
     lib.mcpyb_energies_dev.argtypes = [_p, _p]
     lib.mcpyb_potential_energies_host.argtypes = [_p, C.c_int, _p, _p, _p, _p, _p, _p]

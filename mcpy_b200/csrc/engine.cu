@@ -892,6 +892,64 @@ int mcpyb_upload_dev(mcpyb_engine* e, int R, const int64_t* atom_off, const doub
     return upload_common(e, R, atom_off, cells, pbc, d_positions, d_numbers, e->stage_dev.p);
 }
 
+// ---- many small device copies in one launch ----------------------------------------------------
+#define SEG_MAX 48
+struct CopySegs {
+    const void* src[SEG_MAX];
+    void* dst[SEG_MAX];
+    int count[SEG_MAX];
+    unsigned char kind[SEG_MAX];          // 0: f64 -> f64, 1: i32 -> i32, 2: f64 -> i32, 3: i32 -> f64
+    int n;
+};
+
+__global__ void __launch_bounds__(256)
+copy_segments_kernel(const __grid_constant__ CopySegs sg) {
+    const int k = blockIdx.y;
+    const int n = sg.count[k], kind = sg.kind[k];
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
+    if (kind == 0) {
+        const double* s = (const double*)sg.src[k]; double* d = (double*)sg.dst[k];
+        for (int i = i0; i < n; i += step) d[i] = s[i];
+    } else if (kind == 1) {
+        const int* s = (const int*)sg.src[k]; int* d = (int*)sg.dst[k];
+        for (int i = i0; i < n; i += step) d[i] = s[i];
+    } else if (kind == 2) {
+        const double* s = (const double*)sg.src[k]; int* d = (int*)sg.dst[k];
+        for (int i = i0; i < n; i += step) d[i] = (int)s[i];
+    } else {
+        const int* s = (const int*)sg.src[k]; double* d = (double*)sg.dst[k];
+        for (int i = i0; i < n; i += step) d[i] = (double)s[i];
+    }
+}
+
+int mcpyb_copy_segments_dev(mcpyb_engine* e, int nseg, const uint64_t* src, const uint64_t* dst, const int64_t* count,
+                            const uint8_t* kind) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (nseg < 0 || (nseg > 0 && (!src || !dst || !count || !kind))) return e->fail(MCPYB_ERR_ARG, "bad arguments");
+    for (int s0 = 0; s0 < nseg; s0 += SEG_MAX) {
+        CopySegs sg;
+        memset(&sg, 0, sizeof sg);
+        sg.n = nseg - s0 < SEG_MAX ? nseg - s0 : SEG_MAX;
+        int64_t most = 0;
+        for (int k = 0; k < sg.n; ++k) {
+            const int64_t c = count[s0 + k];
+            if (c < 0 || c > 0x7fffffffLL || kind[s0 + k] > 3 || (c > 0 && (!src[s0 + k] || !dst[s0 + k])))
+                return e->fail(MCPYB_ERR_ARG, "segment %d: bad count / kind / address", s0 + k);
+            sg.src[k] = (const void*)(uintptr_t)src[s0 + k];
+            sg.dst[k] = (void*)(uintptr_t)dst[s0 + k];
+            sg.count[k] = (int)c; sg.kind[k] = kind[s0 + k];
+            if (c > most) most = c;
+        }
+        if (most == 0) continue;
+        int bx = (int)((most + 255) / 256);
+        if (bx > 64) bx = 64;
+        copy_segments_kernel<<<dim3(bx, sg.n), 256, 0, e->stream>>>(sg);
+        LAUNCH_CHECK("copy_segments_kernel");
+    }
+    return MCPYB_OK;
+}
+
 int mcpyb_energies_dev(mcpyb_engine* e, double* d_energies_out) {
     if (!e) return MCPYB_ERR_ARG;
     cudaSetDevice(e->device);

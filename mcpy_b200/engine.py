@@ -175,6 +175,14 @@ class Engine:
         self._R = R
         self._ntot = int(off[-1])
 
+    def copy_segments_dev(self, segments):
+        """``segments``: iterable of ``(src address, dst address, count, kind)`` with kind 0 f64->f64, 1 i32->i32,
+        2 f64->i32, 3 i32->f64; all of them in one launch on the engine's stream (``mcpyb_copy_segments_dev``)."""
+        seg = np.array(segments, dtype=np.uint64).reshape(-1, 4)
+        src, dst = np.ascontiguousarray(seg[:, 0]), np.ascontiguousarray(seg[:, 1])
+        cnt, kind = seg[:, 2].astype(np.int64), seg[:, 3].astype(np.uint8)
+        self._check(self._lib.mcpyb_copy_segments_dev(self._h, len(seg), ptr(src), ptr(dst), ptr(cnt), ptr(kind)))
+
     def energies(self, return_pairs=False):
         E = np.empty(self._R, dtype=np.float64)
         pairs = np.empty(self._R, dtype=np.int64) if return_pairs else None

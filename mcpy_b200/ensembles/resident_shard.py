@@ -31,6 +31,24 @@ from .acceptance import swap_exponent
 _WIDTH = 19                  # E, beta, N, mu, Lambda, has_mu, n_atoms, cell (9), pbc (3)
 
 
+def _pair_exponent(ri, rj):
+    """``swap_exponent(rec_i, rec_j, 1)`` for records ``[E, beta, N, mu, Lambda, has]`` held as Python floats."""
+    Ei, bi, Ni, mui, Li, hi = ri
+    Ej, bj, Nj, muj, Lj, hj = rj
+    phi_ii = Ei - mui * Ni if hi else Ei
+    phi_jj = Ej - muj * Nj if hj else Ej
+    phi_ji = Ej - mui * Nj if hi else Ej
+    phi_ij = Ei - muj * Ni if hj else Ei
+    delta = bi * phi_ii + bj * phi_jj - bi * phi_ji - bj * phi_ij
+    if bi != bj and hi:
+        dn = int(Ni) - int(Nj)
+        if dn:
+            if Li != Li or Lj != Lj:
+                raise KeyError('a replica has no de Broglie wavelength for the exchanged species')
+            delta += 0.0 + 3.0 * dn * np.log(Li / Lj)
+    return delta
+
+
 class ResidentLadderShard:
     def __init__(self, engine, configs, betas, mus, lambdas=None, seed=31, rank=None, world_size=None,
                  group=None, device=None):
@@ -65,6 +83,7 @@ class ResidentLadderShard:
         # capacity of a boundary block of the exchange buffer: the largest replica of the whole ladder
         self.cap = max(max(self.comm.all_gather_object(max(self.n_of, default=0))), 1)
         self._xbuf = None
+        self._xnp = None
         self.E = np.zeros(len(configs))
         self.swap_log = []
         self.rounds = 0
@@ -86,17 +105,25 @@ class ResidentLadderShard:
 
     # ------------------------------------------------------------------ exchange
     def records(self):
-        rec = np.zeros((self.hi - self.lo, _WIDTH))
-        for k in range(self.hi - self.lo):
-            g = self.lo + k
-            rec[k, :7] = (self.E[k], self.betas[g], self.n_of[k], self.mus[g], self.lambdas[g], 1.0, self.n_of[k])
-            rec[k, 7:16] = self.cells[k]
-            rec[k, 16:19] = self.pbcs[k]
+        nloc = self.hi - self.lo
+        rec = np.zeros((nloc, _WIDTH))
+        if nloc:
+            sl = slice(self.lo, self.hi)
+            rec[:, 0] = self.E
+            rec[:, 1] = self.betas[sl]
+            rec[:, 2] = self.n_of
+            rec[:, 3] = self.mus[sl]
+            rec[:, 4] = self.lambdas[sl]
+            rec[:, 5] = 1.0
+            rec[:, 6] = self.n_of
+            rec[:, 7:16] = self.cells
+            rec[:, 16:19] = self.pbcs
         return rec
 
     def _gather(self):
         """Records of every replica (host) and, for world > 1, the device buffer holding every rank's two boundary
-        configurations: ONE all_gather."""
+        configurations: ONE all_gather, packed by ONE launch (the records are read from page-locked memory where
+        they are; ``Engine.copy_segments_dev``)."""
         rec = self.records()
         comm = self.comm
         if comm.world_size == 1 or comm._dist is None:
@@ -112,24 +139,28 @@ class ResidentLadderShard:
                           torch.zeros(comm.world_size * width, dtype=torch.float64, device=self.device),
                           torch.zeros(per * _WIDTH, dtype=torch.float64, pin_memory=comm.on_gpu),
                           torch.zeros(comm.world_size, per * _WIDTH, dtype=torch.float64, pin_memory=comm.on_gpu))
+            self._xnp = (self._xbuf[2].numpy(), self._xbuf[3].numpy())
         d_in, d_out, h_in, h_out = self._xbuf
-        h_in.zero_()
+        np_in, np_out = self._xnp
+        np_in[:nloc * _WIDTH] = rec.reshape(-1)
+        np_in[nloc * _WIDTH:] = 0.0
+        din = d_in.data_ptr()
+        segs = [(h_in.data_ptr(), din, per * _WIDTH, 0)]
         if nloc:
-            h_in[:nloc * _WIDTH] = torch.from_numpy(rec.reshape(-1))
-        d_in[:per * _WIDTH].copy_(h_in, non_blocking=True)
-        if nloc:
+            p0, z0 = self.d_pos.data_ptr(), self.d_num.data_ptr()
+            off = self.offsets()
             for which, k in ((0, 0), (1, nloc - 1)):
-                a, b = self.slot_rows(k)
-                n = b - a
+                a, n = int(off[k]), int(off[k + 1] - off[k])
                 if n > cap:
                     raise RuntimeError(f'replica with {n} atoms exceeds the exchange capacity {cap}')
-                base = per * _WIDTH + which * blk
-                d_in[base:base + 3 * n].copy_(self.d_pos[a:b].reshape(-1))
-                d_in[base + 3 * cap:base + 3 * cap + n].copy_(self.d_num[a:b])
+                base = din + 8 * (per * _WIDTH + which * blk)
+                segs.append((p0 + 24 * a, base, 3 * n, 0))
+                segs.append((z0 + 4 * a, base + 8 * 3 * cap, n, 3))
+        self.engine.copy_segments_dev(segs)
         comm._dist.all_gather_into_tensor(d_out, d_in, group=comm.group)
         h_out.copy_(d_out.view(comm.world_size, width)[:, :per * _WIDTH], non_blocking=True)
         comm._sync()
-        out = h_out.numpy().reshape(comm.world_size, per, _WIDTH)
+        out = np_out.reshape(comm.world_size, per, _WIDTH)
         rows = np.concatenate([out[g, :hi - lo] for g, (lo, hi) in enumerate(comm._bounds)])
         comm.collective_seconds += time.perf_counter() - t0
         comm.gathers += 1
@@ -142,9 +173,13 @@ class ResidentLadderShard:
         rec, gathered = self._gather()
         self.rounds += 1
         accepted_pairs = []
+        # the six leading columns as Python floats: the same IEEE operations as swap_exponent on numpy scalars, in
+        # the same order, at a twentieth of the cost (every rank evaluates every pair of the ladder: 32 per round
+        # at 64 replicas)
+        cols = rec[:, :6].tolist()
         for i in range(offset, self.n_total - 1, 2):
             j = i + 1
-            delta = swap_exponent(rec[i, :6], rec[j, :6], 1)
+            delta = _pair_exponent(cols[i], cols[j])
             if not np.isfinite(delta):
                 ok = False
             else:
@@ -157,7 +192,10 @@ class ResidentLadderShard:
             return 0
         me, comm = self.comm.rank, self.comm
         off = self.offsets()
-        blocks = [[self.d_pos[off[k]:off[k + 1]], self.d_num[off[k]:off[k + 1]]] for k in range(len(self.n_of))]
+        # every slot's block as (address of its rows, address of its numbers, copy kind of the numbers, rows): blocks
+        # that change slot are re-pointed, then ONE launch writes the new device arrays (Engine.copy_segments_dev)
+        p0, z0 = self.d_pos.data_ptr(), self.d_num.data_ptr()
+        blocks = [[p0 + 24 * int(off[k]), z0 + 4 * int(off[k]), 1, int(off[k + 1] - off[k])] for k in range(len(self.n_of))]
         touched = False
         for i, j in accepted_pairs:
             oi, oj = comm.owner(i), comm.owner(j)
@@ -177,9 +215,8 @@ class ResidentLadderShard:
                 n_in = int(rec[theirs, 6])
                 cap, per = self.cap, comm.per
                 base = per * _WIDTH + which * 4 * cap
-                row = gathered[peer]
-                blocks[k] = [row[base:base + 3 * n_in].reshape(n_in, 3),
-                             row[base + 3 * cap:base + 3 * cap + n_in].to(torch.int32)]
+                row0 = gathered.data_ptr() + 8 * (peer * gathered.shape[1] + base)
+                blocks[k] = [row0, row0 + 8 * 3 * cap, 2, n_in]
                 self.n_of[k] = n_in
                 self.E[k] = rec[theirs, 0]
                 self.cells[k] = rec[theirs, 7:16]
@@ -187,10 +224,19 @@ class ResidentLadderShard:
                 comm.transports += 1
                 touched = True
         if touched:
-            # the device array is re-assembled from its blocks in their new slots (one concatenation each for positions
-            # and numbers, whatever the number of swaps), then the cell lists are rebuilt in place
-            self.d_pos = torch.cat([b[0] for b in blocks])
-            self.d_num = torch.cat([b[1] for b in blocks])
+            total = sum(b[3] for b in blocks)
+            new_pos = torch.empty((total, 3), dtype=torch.float64, device=self.device)
+            new_num = torch.empty(total, dtype=torch.int32, device=self.device)
+            segs, at = [], 0
+            dp, dz = new_pos.data_ptr(), new_num.data_ptr()
+            for src_p, src_z, kind, n in blocks:
+                if n:
+                    segs.append((src_p, dp + 24 * at, 3 * n, 0))
+                    segs.append((src_z, dz + 4 * at, n, kind))
+                at += n
+            self.engine.copy_segments_dev(segs)
+            self.d_pos, self.d_num = new_pos, new_num
+            # the cell lists are rebuilt in place from the new arrays
             self.upload()
         return len(accepted_pairs)
 

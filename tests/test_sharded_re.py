@@ -147,6 +147,17 @@ class _HostEngine:
         self.off, self.cells, self.pbcs = np.array(off), np.array(cells), np.array(pbcs)
         self.uploads += 1
 
+    def copy_segments_dev(self, segments):
+        """Engine.copy_segments_dev on host memory: the same moves, through the same addresses."""
+        import ctypes
+        ctype = {0: (ctypes.c_double, ctypes.c_double), 1: (ctypes.c_int32, ctypes.c_int32),
+                 2: (ctypes.c_double, ctypes.c_int32), 3: (ctypes.c_int32, ctypes.c_double)}
+        for src, dst, n, kind in segments:
+            if n:
+                ts, td = ctype[kind]
+                a = np.ctypeslib.as_array((ts * n).from_address(src))
+                np.ctypeslib.as_array((td * n).from_address(dst))[:] = a
+
     def bind(self, shard):
         self.shard = shard
 
