@@ -211,6 +211,11 @@ struct mcpyb_engine {
     int rw_minb = RW_MIN_BLOCKS;          // MCPYB_RW_MINB=4|5|6: resident CTAs per SM the warp row-sum kernel is built for
     int l2_persist_mb = 0;                // MCPYB_L2PERSIST=<MB>: keep the stencil lists in a persisting L2 window
     bool fp32_pairs = false;              // mcpyb_set_precision: fp32 pair math in the batched LJ row sums
+    bool use_direct = true;               // MCPYB_DIRECT=0: dense LJ batches keep the scan + scatter pipeline
+    int slot_cap_override = 0;            // MCPYB_SLOT_CAP: slots per bin of the direct placement (tests: force overflow)
+    bool hist_dirty = false;              // the trial histogram holds the counts of a direct-placement launch
+    double cells_est = 0.0;               // cells of the resident batch's grids, summed over replicas (periodic boxes)
+    DevBuf<int> tw_ovf;                   // [0] sites that found their bin full, [2] bin claim counter (direct placement)
     int er_minb = 6;                      // MCPYB_ER_MINB: resident CTAs per SM the list-driven EMT trial kernel is compiled for
     bool use_emt_lists = true;            // MCPYB_EMT_LISTS=0: the first-generation EMT trial kernel for every batch
     // stencil lists of the resident batch (rows_block.cuh): built when a SECOND trial batch is scored against
@@ -524,10 +529,28 @@ int fill_header(mcpyb_engine* e, int R, const int64_t* atom_off, const double* c
     int* off32 = (int*)hdr;
     for (int r = 0; r <= R; ++r) off32[r] = (int)atom_off[r];
     CellGeom* g = (CellGeom*)(hdr + align_up((size_t)(R + 1) * sizeof(int), 16));
+    double cells_est = 0.0;
     for (int r = 0; r < R; ++r) {
         int rc = make_geom(e, cells + 9 * r, pbc + 3 * r, g + r);
         if (rc != MCPYB_OK) return rc;
+        // the grid build_cell_list_kernel will choose for a periodic box (cell_list.cuh); an open direction spans the
+        // atoms' extent, which only the device knows: taken as the full height (more cells, smaller mean)
+        const double rc_safe = e->rcut * (1.0 + 1e-12);
+        double want[3], total = 1.0;
+        for (int d = 0; d < 3; ++d) {
+            double nc = floor(g[r].height[d] * (double)e->subdiv / rc_safe);
+            if (!(nc >= 1.0)) nc = 1.0;
+            if (nc > 1024.0) nc = 1024.0;
+            want[d] = nc; total *= nc;
+        }
+        if (total > (double)e->max_cells) {
+            const double f = cbrt((double)e->max_cells / total);
+            total = 1.0;
+            for (int d = 0; d < 3; ++d) total *= fmax(1.0, floor(want[d] * f));
+        }
+        cells_est += total < (double)e->max_cells ? total : (double)e->max_cells;
     }
+    e->cells_est = cells_est;
     e->atom_off_host.assign(off32, off32 + R + 1);
     return MCPYB_OK;
 }
@@ -629,6 +652,8 @@ int mcpyb_create(int device, mcpyb_engine** out) {
     if (const char* v = getenv("MCPYB_EMT_LISTS")) e->use_emt_lists = atoi(v) != 0;
     if (const char* v = getenv("MCPYB_ER_MINB")) e->er_minb = atoi(v);
     if (const char* v = getenv("MCPYB_TRK_TIMING")) e->trkb_timing = atoi(v) != 0;
+    if (const char* v = getenv("MCPYB_DIRECT")) e->use_direct = atoi(v) != 0;
+    if (const char* v = getenv("MCPYB_SLOT_CAP")) e->slot_cap_override = atoi(v);
     if (const char* v = getenv("MCPYB_RW_MINB")) { const int n = atoi(v); if (n >= 4 && n <= 6) e->rw_minb = n; }
     if (const char* v = getenv("MCPYB_L2PERSIST")) {
         e->l2_persist_mb = atoi(v);
@@ -663,7 +688,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     e->e_atom.release(); e->sigma1.release(); e->e_emb.release(); e->e_part.release(); e->deds.release(); e->forces.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
-    e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release(); e->tw_spos.release(); e->tw_meta.release(); e->tw_items.release(); e->tw_a.release(); e->tw_err.release(); e->tw_hist.release();
+    e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release(); e->tw_spos.release(); e->tw_meta.release(); e->tw_items.release(); e->tw_a.release(); e->tw_err.release(); e->tw_ovf.release(); e->tw_hist.release();
     e->nl_i.release(); e->nl_j.release(); e->nl_S.release(); e->nl_r2.release(); e->nl_cursor.release();
     e->fv_grid.release(); e->fv_spheres.release(); e->fv_cell_start.release(); e->fv_cursor.release();
     e->fv_cid.release(); e->fv_points.release(); e->fv_pos.release(); e->fv_radii.release(); e->fv_small.release();
@@ -1358,13 +1383,89 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
         }
         return MCPYB_OK;
     }
+    // dense batches: direct placement (site_kernels.cuh: trial_sites_direct_kernel) -- the rank a site draws from its
+    // bin's histogram is its slot, the row-sum warps claim bins: no scan, no scatter, no item table
+    int slot_cap = 0;
+    if (e->use_direct && e->use_warp_rows && !e->fp32_pairs && w.nbins > 0) {
+        // sites per occupied-grid cell: the grids are sized on the device, the host knows them for periodic boxes
+        // (make_geom) and otherwise falls back on the stride (an underestimate of the mean: more overflow, same bits)
+        const double cells = e->cells_est > 0.0 ? e->cells_est : (double)w.nbins;
+        const double mean = (double)nsites / cells;
+        if (mean >= 4.0 || e->slot_cap_override > 0) {
+            slot_cap = e->slot_cap_override > 0 ? e->slot_cap_override : 16 * (int)ceil((1.6 * mean + 24.0) / 16.0);
+            if ((double)w.nbins * slot_cap * 48.0 > 1.5e9) slot_cap = 0;
+        }
+    }
+    if (slot_cap > 0) {
+        // the histogram is zeroed here (the row-sum warps of several items read a bin's count, none of them may clear it)
+        CK(e->tw_hist.reserve(nbp * TRIAL_HIST_STRIDE), "cudaMalloc trial histogram");
+        CK(cudaMemsetAsync(e->tw_hist.p, 0, nbp * TRIAL_HIST_STRIDE * sizeof(int), e->stream), "memset histogram");
+        e->hist_dirty = true;
+        CK(e->tw_items.reserve((ns >> 4) + (ns < nbp ? ns : nbp) + 1), "cudaMalloc trial items");
+        w.item_tab = e->tw_items.p;
+        CK(e->tw_pos.reserve(ns), "cudaMalloc trial work");          // overflow records
+        CK(e->tw_a.reserve(ns), "cudaMalloc trial work");
+        CK(e->tw_spos.reserve((size_t)w.nbins * slot_cap), "cudaMalloc trial slots");
+        CK(e->tw_meta.reserve((size_t)w.nbins * slot_cap), "cudaMalloc trial slots");
+        if (!e->tw_ovf.p) {
+            // [0] overflow count, [1] work items, [2] claim counter of the row-sum warps: zero on entry, re-zeroed by the
+            // combine kernel
+            CK(e->tw_ovf.reserve(4), "cudaMalloc trial overflow");
+            CK(cudaMemsetAsync(e->tw_ovf.p, 0, 4 * sizeof(int), e->stream), "memset trial counters");
+        }
+        w.totals = e->tw_ovf.p + 1;
+        w.hist = e->tw_hist.p; w.site_pos = e->tw_pos.p; w.site_a = e->tw_a.p;
+        w.sorted_pos = e->tw_spos.p; w.sorted_meta = e->tw_meta.p;
+        w.slot_cap = slot_cap; w.ovf = e->tw_ovf.p;
+        auto mark = [&]() { if (e->stage_timing && e->stage_n < 6) cudaEventRecord(e->stage_ev[e->stage_n++], e->stream); };
+        const bool pdl = e->use_pdl && !e->stage_timing;
+        cudaLaunchAttribute pdl_attr[1];
+        pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+        auto config = [&](int grid, int block) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.stream = e->stream;
+            cfg.attrs = pdl_attr; cfg.numAttrs = pdl ? 1 : 0;
+            return cfg;
+        };
+        const BatchView bv = e->view();
+        StencilLists xl;
+        { int rc = stencil_lists(e, false, &xl); if (rc != MCPYB_OK) return rc; }
+        mark();
+        { cudaLaunchConfig_t cfg = config((T + 255) / 256, 256);
+          CK(cudaLaunchKernelEx(&cfg, trial_sites_direct_kernel, bv, tb, w), "launch trial_sites_direct_kernel"); e->launches++; }
+        mark(); mark(); mark();                                   // (no scan, no scatter)
+        {
+            const long long max_items = (long long)(ns >> 4) + (long long)(ns < nbp ? ns : nbp) + 1;
+            const long long want = (max_items + RW_WARPS - 1) / RW_WARPS;
+            const int grid = (int)(want < (long long)e->num_sms * e->rw_minb ? want : (long long)e->num_sms * e->rw_minb);
+            cudaLaunchConfig_t cfg = config(grid, 32 * RW_WARPS);
+            if (e->rw_minb == 4)
+                CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_direct_kernel<4>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_direct_kernel");
+            else if (e->rw_minb == 5)
+                CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_direct_kernel<5>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_direct_kernel");
+            else
+                CK(cudaLaunchKernelEx(&cfg, lj_trial_rows_direct_kernel<6>, bv, tb, w, e->lj, xl), "launch lj_trial_rows_direct_kernel");
+            e->launches++;
+        }
+        mark();
+        { cudaLaunchConfig_t cfg = config(e->num_sms * 2, 32 * RW_WARPS);
+          CK(cudaLaunchKernelEx(&cfg, lj_trial_overflow_kernel, bv, tb, w, e->lj, xl), "launch lj_trial_overflow_kernel"); e->launches++; }
+        { cudaLaunchConfig_t cfg = config((T + 127) / 128, 128);
+          CK(cudaLaunchKernelEx(&cfg, lj_trial_combine_kernel, bv, tb, w, e->lj, d_dE, d_pairs), "launch lj_trial_combine_kernel");
+          e->launches++; }
+        mark();
+        return MCPYB_OK;
+    }
     // batches: counting sort of the sites by cell, then one CTA per (cell, <= RB_SITES sites)
     CK(e->tw_bins.reserve(2 * nbp), "cudaMalloc trial bins");
     {
         const size_t had = e->tw_hist.cap;
         CK(e->tw_hist.reserve(nbp * TRIAL_HIST_STRIDE), "cudaMalloc trial histogram");
-        if (e->tw_hist.cap != had)           // fresh histogram: zero once, the scan kernel keeps it zero
-            CK(cudaMemsetAsync(e->tw_hist.p, 0, e->tw_hist.cap * sizeof(int), e->stream), "memset histogram");
+        if (e->tw_hist.cap != had || e->hist_dirty)      // fresh histogram, or one the direct placement left behind:
+            CK(cudaMemsetAsync(e->tw_hist.p, 0, e->tw_hist.cap * sizeof(int), e->stream), "memset histogram");   // zero once, the scan kernel keeps it zero
+        e->hist_dirty = false;
     }
     {
         const size_t had = e->tw_pos.cap;

@@ -293,6 +293,65 @@ __device__ __noinline__ void rw_candidate_loop(
     outc = cnt;
 }
 
+// One work item: sites [kbeg, kbeg + n) of sorted_pos / sorted_meta (n <= 16, all in one cell of replica r) against
+// the cell's list `head` (first record, length; first < 0: no list).
+template <bool F32>
+__device__ __forceinline__ void rw_item(const BatchView& b, const TrialBatch& tb, const TrialWork& w, const LJParams& p,
+                                        const StencilLists& x, double4 (*buf)[32], int lane,
+                                        const double4* __restrict__ rec_pos, const int4* __restrict__ rec_meta,
+                                        int kbeg, int n, int r, int2 head) {
+    const GridDesc& g = b.grid[r];
+    const double4* spos = b.spos + g.atom_off;
+    // lane groups: sites sl = 0 .. SP-1 in each of G = 32 / SP groups
+    const int gshift = n <= 8 ? 3 : 4;
+    const int sl = lane & ((1 << gshift) - 1), grp = lane >> gshift;
+    const bool active = sl < n;
+    int s = 0, ob = 0, oe = 0, ex0 = -1, wsite = pack_wraps(0, 0, 0);
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (active) {
+        const double4 me = rec_pos[(size_t)kbeg + sl];
+        const int4 mt = rec_meta[(size_t)kbeg + sl];
+        px = me.x; py = me.y; pz = me.z;
+        wsite = (int)__double_as_longlong(me.w);
+        s = mt.x; ex0 = mt.y; ob = mt.z; oe = mt.w;
+    }
+    double acc12 = 0.0, acc6 = 0.0;
+    int cnt = 0;
+    if (head.x < 0) {
+        // no list for this cell (thin box, oversized stencil, list buffer full): exact per-lane traversal
+        if (active && grp == 0) {
+            const int* cstart = b.cell_start + (size_t)r * b.cs_stride;
+            rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, acc12, acc6, cnt);
+        }
+    } else {
+        // the site wrapped into the primary cell and the band (ulps of rc^2) in which the fused r2 is re-checked
+        double qx = 3.0e150, qy = -3.0e150, qz = 3.0e150;    // idle lanes: r2 overflows, never inside
+        double band = 16.0;
+        if (active) {
+            qx = px; qy = py; qz = pz;
+            if (wsite != pack_wraps(0, 0, 0)) rb_wrap_site(g, p.rc, px, py, pz, wsite, qx, qy, qz, band);
+        }
+        const double bw = p.rc2 * band * 2.220446049250313e-16;
+        const long long lo_bits = __double_as_longlong(p.rc2 - bw), hi_bits = __double_as_longlong(p.rc2 + bw);
+        const bool multi = (oe - ob) > 2;
+        const int ex1 = (oe - ob) > 1 ? tb.old_idx[ob + 1] : -1;
+        const double4* xq = x.q + head.x;
+        const int2* xi = x.info + head.x;
+        const int ksite = active ? kbeg + sl : -1;
+        if (gshift == 4)
+            rw_candidate_loop<2, F32>(xq, xi, head.y, lane, grp, buf, qx, qy, qz, ksite, rec_pos, lo_bits, hi_bits,
+                                 ex0, ex1, multi, ob, oe, g, spos, tb, p.sigma2, p.rc2, acc12, acc6, cnt);
+        else
+            rw_candidate_loop<4, F32>(xq, xi, head.y, lane, grp, buf, qx, qy, qz, ksite, rec_pos, lo_bits, hi_bits,
+                                 ex0, ex1, multi, ob, oe, g, spos, tb, p.sigma2, p.rc2, acc12, acc6, cnt);
+    }
+    if (active && grp == 0) {
+        // row = 4 eps (sum c12 - sum c6) - e0 * pairs
+        w.site_E[s] = fma(p.eps4, acc12 - acc6, -p.e0 * (double)cnt);
+        w.site_cnt[s] = cnt;
+    }
+}
+
 template <int MINB, bool F32>
 __global__ void __launch_bounds__(32 * RW_WARPS, MINB)
 lj_trial_rows_warp_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, StencilLists x) {
@@ -314,59 +373,58 @@ lj_trial_rows_warp_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, S
         const int4 h0 = w.items[2 * wi], h1 = w.items[2 * wi + 1];
         int claimed = nwork;
         if (next_wi < nwork && lane == 0) claimed = nwarps + atomicAdd(&w.totals[1], 1);
-        const int kbeg = h0.y, n = h0.z, r = h0.w;
-        const GridDesc& g = b.grid[r];
-        const double4* spos = b.spos + g.atom_off;
-        // lane groups: sites sl = 0 .. SP-1 in each of G = 32 / SP groups
-        const int gshift = n <= 8 ? 3 : 4;
-        const int sl = lane & ((1 << gshift) - 1), grp = lane >> gshift;
-        const bool active = sl < n;
-        int s = 0, ob = 0, oe = 0, ex0 = -1, wsite = pack_wraps(0, 0, 0);
-        double px = 0.0, py = 0.0, pz = 0.0;
-        if (active) {
-            const double4 me = w.sorted_pos[kbeg + sl];
-            const int4 mt = w.sorted_meta[kbeg + sl];
-            px = me.x; py = me.y; pz = me.z;
-            wsite = (int)__double_as_longlong(me.w);
-            s = mt.x; ex0 = mt.y; ob = mt.z; oe = mt.w;
-        }
-        double acc12 = 0.0, acc6 = 0.0;
-        int cnt = 0;
-        if (h1.x < 0) {
-            // no list for this cell (thin box, oversized stencil, list buffer full): exact per-lane traversal
-            if (active && grp == 0) {
-                const int* cstart = b.cell_start + (size_t)r * b.cs_stride;
-                rb_generic_row(g, spos, cstart, p, px, py, pz, tb.old_idx, ob, oe, acc12, acc6, cnt);
-            }
-        } else {
-            // the site wrapped into the primary cell and the band (ulps of rc^2) in which the fused r2 is re-checked
-            double qx = 3.0e150, qy = -3.0e150, qz = 3.0e150;    // idle lanes: r2 overflows, never inside
-            double band = 16.0;
-            if (active) {
-                qx = px; qy = py; qz = pz;
-                if (wsite != pack_wraps(0, 0, 0)) rb_wrap_site(g, p.rc, px, py, pz, wsite, qx, qy, qz, band);
-            }
-            const double bw = p.rc2 * band * 2.220446049250313e-16;
-            const long long lo_bits = __double_as_longlong(p.rc2 - bw), hi_bits = __double_as_longlong(p.rc2 + bw);
-            const bool multi = (oe - ob) > 2;
-            const int ex1 = (oe - ob) > 1 ? tb.old_idx[ob + 1] : -1;
-            const double4* xq = x.q + h1.x;
-            const int2* xi = x.info + h1.x;
-            const int ksite = active ? kbeg + sl : -1;
-            if (gshift == 4)
-                rw_candidate_loop<2, F32>(xq, xi, h1.y, lane, grp, s_buf[wid], qx, qy, qz, ksite, w.sorted_pos, lo_bits, hi_bits,
-                                     ex0, ex1, multi, ob, oe, g, spos, tb, p.sigma2, p.rc2, acc12, acc6, cnt);
-            else
-                rw_candidate_loop<4, F32>(xq, xi, h1.y, lane, grp, s_buf[wid], qx, qy, qz, ksite, w.sorted_pos, lo_bits, hi_bits,
-                                     ex0, ex1, multi, ob, oe, g, spos, tb, p.sigma2, p.rc2, acc12, acc6, cnt);
-        }
-        if (active && grp == 0) {
-            // row = 4 eps (sum c12 - sum c6) - e0 * pairs
-            w.site_E[s] = fma(p.eps4, acc12 - acc6, -p.e0 * (double)cnt);
-            w.site_cnt[s] = cnt;
-        }
+        rw_item<F32>(b, tb, w, p, x, s_buf[wid], lane, w.sorted_pos, w.sorted_meta, h0.y, h0.z, h0.w, make_int2(h1.x, h1.y));
         wi = next_wi;
         next_wi = __shfl_sync(0xffffffffu, claimed, 0);
+    }
+}
+
+// Direct placement (TrialWork::slot_cap > 0): the work items are the (bin, group of 16 ranks) pairs the site kernel
+// announced; a group's sites are slots [16 g, min(16 g + 16, count)) of its bin, the count is the bin's histogram
+// word.  No scan, no scatter.
+template <int MINB>
+__global__ void __launch_bounds__(32 * RW_WARPS, MINB)
+lj_trial_rows_direct_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, StencilLists x) {
+    __shared__ double4 s_buf[RW_WARPS][RW_STAGES][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    pdl_wait();
+    pdl_trigger();
+    const int nwork = w.totals[0];
+    int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int next_wi = nwork;
+    if (wi < nwork) {
+        if (lane == 0) next_wi = nwarps + atomicAdd(&w.totals[1], 1);
+        next_wi = __shfl_sync(0xffffffffu, next_wi, 0);
+    }
+    while (wi < nwork) {
+        const int2 it = w.item_tab[wi];
+        int claimed = nwork;
+        if (next_wi < nwork && lane == 0) claimed = nwarps + atomicAdd(&w.totals[1], 1);
+        const int c = min(w.hist[(size_t)it.x * TRIAL_HIST_STRIDE], w.slot_cap);
+        const int2 head = x.head ? x.head[it.x] : make_int2(-1, 0);
+        const int first = it.y << RW_SITES_SHIFT;
+        rw_item<false>(b, tb, w, p, x, s_buf[wid], lane, w.sorted_pos, w.sorted_meta, it.x * w.slot_cap + first,
+                       min(1 << RW_SITES_SHIFT, c - first), it.x / w.bin_stride, head);
+        wi = next_wi;
+        next_wi = __shfl_sync(0xffffffffu, claimed, 0);
+    }
+}
+
+// Sites that found their bin's slots full (records in site_pos / site_a, the bin in the upper half of .w): one warp
+// per site through the same item code, so such a site's row carries the bits of every other listed row.
+__global__ void __launch_bounds__(32 * RW_WARPS)
+lj_trial_overflow_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, StencilLists x) {
+    __shared__ double4 s_buf[RW_WARPS][RW_STAGES][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    pdl_wait();
+    pdl_trigger();
+    const int n = w.ovf[0];
+    for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += nwarps) {
+        const int bin = (int)(__double_as_longlong(w.site_pos[k].w) >> 32);
+        const int2 head = x.head ? x.head[bin] : make_int2(-1, 0);
+        rw_item<false>(b, tb, w, p, x, s_buf[wid], lane, w.site_pos, w.site_a, k, 1, bin / w.bin_stride, head);
     }
 }
 

@@ -418,6 +418,12 @@ struct TrialWork {
     unsigned long long* chain;   // [2 R] per-replica totals of the chained scan: (stamp << 36) | sites, | items
     double4* sorted_pos;   // [nsites] site_pos in bin order (.w = packed wraps)
     int4* sorted_meta;     // [nsites] (site id, first excluded atom or -1, old_off[t], old_off[t+1]) in bin order
+    // direct placement (dense batches; trial_sites_direct_kernel): slot_cap > 0 means sorted_pos / sorted_meta hold
+    // slot_cap records per bin -- the site that drew rank k in the histogram of bin c sits at c * slot_cap + k -- and
+    // item_tab lists (bin, group of 16 ranks) in the order the groups were opened (totals[0] of them), so neither the
+    // scan nor the scatter runs; sites beyond a bin's capacity go to site_pos / site_a [0 .. ovf[0])
+    int slot_cap;
+    int* ovf;
 };
 
 __device__ __forceinline__ int owner_of(const int* __restrict__ off, int T, int k) {
@@ -484,6 +490,82 @@ __device__ __forceinline__ void trial_sites_body(const BatchView& b, const Trial
         const int bin = bin_of(x, y, z, wr);
         const int rank = atomicAdd(&w.hist[(size_t)bin * TRIAL_HIST_STRIDE], 1);
         record(s, bin, rank, x, y, z, wr);
+    }
+}
+
+// Direct placement: the rank a site draws from its bin's histogram IS its slot.  Record formats are those of
+// sorted_pos / sorted_meta; the bin rides in the upper half of .w (the row-sum kernel reads the lower one).
+// The two sites of an ordinary trial (one removed, one added atom) are handled side by side, so their gathers and
+// their atomics are in flight together.
+__device__ __forceinline__ void trial_place(const TrialWork& w, int s, int bin, int rank, double x, double y, double z,
+                                            const int wr[3], int ex0, int ob, int oe) {
+    const double4 rp = make_double4(x, y, z, __longlong_as_double((long long)(unsigned int)pack_wraps(wr[0], wr[1], wr[2]) |
+                                                                  ((long long)bin << 32)));
+    const int4 rm = make_int4(s, ex0, ob, oe);
+    if (rank < w.slot_cap) {
+        const size_t k = (size_t)bin * w.slot_cap + rank;
+        w.sorted_pos[k] = rp;
+        w.sorted_meta[k] = rm;
+        // the first site of every group of 16 announces the group as a work item of the row-sum kernel
+        if ((rank & ((1 << 4) - 1)) == 0) w.item_tab[atomicAdd(&w.totals[0], 1)] = make_int2(bin, rank >> 4);
+    } else {
+        const int k = atomicAdd(w.ovf, 1);
+        w.site_pos[k] = rp;
+        w.site_a[k] = rm;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+trial_sites_direct_kernel(BatchView b, TrialBatch tb, TrialWork w) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
+    if (t >= tb.T) return;
+    const int r = tb.rep ? tb.rep[t] : 0;
+    const int ob = tb.old_off[t], oe = tb.old_off[t + 1];
+    const int nb = tb.new_off[t], ne = tb.new_off[t + 1];
+    const int bad = trial_invalid(b, tb, w, r, ob, oe, nb, ne);
+    if (bad) {
+        atomicMin(w.err, ((unsigned long long)t << 8) | (unsigned long long)bad);
+        return;
+    }
+    const GridDesc& g = b.grid[r];
+    const int ex0 = oe > ob ? tb.old_idx[ob] : -1;
+    auto bin_of = [&](double x, double y, double z, int wr[3]) {
+        int c[3];
+        locate(g, x, y, z, c, wr);
+        return r * w.bin_stride + (c[2] * g.ncell[1] + c[1]) * g.ncell[0] + c[0];
+    };
+    const int ko = oe - ob, kn = ne - nb;
+    if (ko <= 1 && kn <= 1) {
+        double xo = 0.0, yo = 0.0, zo = 0.0, xn = 0.0, yn = 0.0, zn = 0.0;
+        if (ko) { const double4 q = b.upos[g.atom_off + ex0]; xo = q.x; yo = q.y; zo = q.z; }
+        if (kn) { xn = tb.new_pos[3 * nb]; yn = tb.new_pos[3 * nb + 1]; zn = tb.new_pos[3 * nb + 2]; }
+        int wo[3] = {0, 0, 0}, wn[3] = {0, 0, 0}, bo = 0, bn = 0, ro = 0, rn = 0;
+        if (ko) bo = bin_of(xo, yo, zo, wo);
+        if (kn) bn = bin_of(xn, yn, zn, wn);
+        if (ko) ro = atomicAdd(&w.hist[(size_t)bo * TRIAL_HIST_STRIDE], 1);
+        if (kn) rn = atomicAdd(&w.hist[(size_t)bn * TRIAL_HIST_STRIDE], 1);
+        if (ko) trial_place(w, ob, bo, ro, xo, yo, zo, wo, ex0, ob, oe);
+        if (kn) trial_place(w, w.n_old + nb, bn, rn, xn, yn, zn, wn, ex0, ob, oe);
+        return;
+    }
+    for (int i = ob; i < oe + kn; ++i) {
+        int s;
+        double x, y, z;
+        if (i < oe) {
+            s = i;
+            const double4 q = b.upos[g.atom_off + tb.old_idx[i]];
+            x = q.x; y = q.y; z = q.z;
+        } else {
+            const int k = nb + (i - oe);
+            s = w.n_old + k;
+            x = tb.new_pos[3 * k]; y = tb.new_pos[3 * k + 1]; z = tb.new_pos[3 * k + 2];
+        }
+        int wr[3];
+        const int bin = bin_of(x, y, z, wr);
+        const int rank = atomicAdd(&w.hist[(size_t)bin * TRIAL_HIST_STRIDE], 1);
+        trial_place(w, s, bin, rank, x, y, z, wr, ex0, ob, oe);
     }
 }
 
@@ -641,6 +723,15 @@ lj_trial_combine_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p,
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_wait();
     pdl_trigger();
+    if (w.slot_cap > 0 && t == 0) {
+        // direct placement has no scan kernel: the validation word is published, and the counters re-armed, here
+        const unsigned long long ev = *w.err;
+        if (w.err_out) *w.err_out = ev;
+        *w.err = ~0ULL;
+        w.totals[0] = 0;
+        w.totals[1] = 0;
+        w.ovf[0] = 0;
+    }
     if (t >= tb.T) return;
     combine_trial(b, tb, w, p, t, dE, npairs);
 }
