@@ -1377,8 +1377,8 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
                                                                          (int*)(e->tw_err.p + 2), xs, d_flag, flag_seq);
             LAUNCH_CHECK("lj_trial_small_kernel");
         } else {
-            lj_trial_combine_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
-            LAUNCH_CHECK("lj_trial_combine_kernel");
+            lj_trial_combine_all_kernel<<<(T + 127) / 128, 128, 0, e->stream>>>(e->view(), tb, w, e->lj, d_dE, d_pairs);
+            LAUNCH_CHECK("lj_trial_combine_all_kernel");
             if (d_status) CK(cudaMemsetAsync(d_status, 0xFF, sizeof(unsigned long long), e->stream), "memset status");
         }
         return MCPYB_OK;
@@ -1452,8 +1452,11 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
         mark();
         { cudaLaunchConfig_t cfg = config(e->num_sms * 2, 32 * RW_WARPS);
           CK(cudaLaunchKernelEx(&cfg, lj_trial_overflow_kernel, bv, tb, w, e->lj, xl), "launch lj_trial_overflow_kernel"); e->launches++; }
-        { cudaLaunchConfig_t cfg = config((T + 127) / 128, 128);
+        { cudaLaunchConfig_t cfg = config((T + 255) / 256, 256);
           CK(cudaLaunchKernelEx(&cfg, lj_trial_combine_kernel, bv, tb, w, e->lj, d_dE, d_pairs), "launch lj_trial_combine_kernel");
+          e->launches++; }
+        { cudaLaunchConfig_t cfg = config(e->num_sms * 4, 128);
+          CK(cudaLaunchKernelEx(&cfg, lj_trial_combine_rest_kernel, bv, tb, w, e->lj, d_dE, d_pairs), "launch lj_trial_combine_rest_kernel");
           e->launches++; }
         mark();
         return MCPYB_OK;
@@ -1555,8 +1558,11 @@ static int launch_trials(mcpyb_engine* e, int T, const int32_t* d_rep, const int
         e->launches++;
     }
     mark();
-    { cudaLaunchConfig_t cfg = config((T + 127) / 128, 128, 0);
+    { cudaLaunchConfig_t cfg = config((T + 255) / 256, 256, 0);
       CK(cudaLaunchKernelEx(&cfg, lj_trial_combine_kernel, bv, tb, w, e->lj, d_dE, d_pairs), "launch lj_trial_combine_kernel");
+      e->launches++; }
+    { cudaLaunchConfig_t cfg = config(e->num_sms * 4, 128, 0);
+      CK(cudaLaunchKernelEx(&cfg, lj_trial_combine_rest_kernel, bv, tb, w, e->lj, d_dE, d_pairs), "launch lj_trial_combine_rest_kernel");
       e->launches++; }
     mark();
     return MCPYB_OK;

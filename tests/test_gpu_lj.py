@@ -387,3 +387,52 @@ def test_fp32_pair_math_mode_within_1e5(name, n_trials):
     rel = np.abs(d32 - d64) / np.maximum(1.0, np.abs(d64))
     assert rel.max() <= 1e-5, rel.max()
     print(f'fp32 pair math on {name}: max |dE32 - dE64| / max(1, |dE|) = {rel.max():.2e}, vs oracle {worst:.2e}')
+
+
+def test_direct_placement_overflow_and_scan_pipelines_give_the_same_bits(monkeypatch):
+    """A dense batch takes the direct placement (site_kernels.cuh: the rank a site draws from its bin's histogram is
+    its slot, no scan, no scatter).  The same batch through (a) 8 slots per bin, which sends most sites through the
+    overflow kernel, (b) the scan + scatter pipeline and (c) a replica batch with ragged boxes must not move a bit,
+    and a sample is checked against the oracle."""
+    from mcpy_b200 import Engine
+    cfgs = [synthetic.s2_lj(2000, 3.0, rho, seed=40 + k) for k, rho in enumerate((0.6, 0.8442, 0.7))]
+    rng = np.random.default_rng(12)
+    parts = [synthetic.trial_batch(c, 12_000, seed=50 + k) for k, c in enumerate(cfgs)]
+    rep = np.concatenate([np.full(12_000, k, np.int32) for k in range(3)])
+    old_off = np.concatenate([[0], np.cumsum(np.concatenate([np.diff(p['old_off']) for p in parts]))]).astype(np.int32)
+    new_off = np.concatenate([[0], np.cumsum(np.concatenate([np.diff(p['new_off']) for p in parts]))]).astype(np.int32)
+    old_idx = np.concatenate([p['old_idx'] for p in parts])
+    new_pos = np.concatenate([p['new_pos'] for p in parts])
+    new_Z = np.concatenate([p['new_Z'] for p in parts])
+    perm = rng.permutation(len(rep))              # interleave the replicas' trials
+    def take(off, rows, order):
+        seg = [np.arange(off[t], off[t + 1]) for t in order]
+        idx = np.concatenate(seg).astype(int)
+        return np.concatenate([[0], np.cumsum([len(s) for s in seg])]).astype(np.int32), rows[idx]
+    oo, oi = take(old_off, old_idx, perm)
+    no, npos = take(new_off, new_pos, perm)
+    _, nz = take(new_off, new_Z, perm)
+    res = {}
+    for label, env in (('direct', {}), ('overflow', {'MCPYB_SLOT_CAP': '8'}), ('scan', {'MCPYB_DIRECT': '0'})):
+        for k in ('MCPYB_SLOT_CAP', 'MCPYB_DIRECT'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = Engine(0)
+        eng.set_lj(1.0, 1.0, 3.0)
+        eng.upload([c['positions'] for c in cfgs], [c['numbers'] for c in cfgs],
+                   np.stack([c['cell'].reshape(9) for c in cfgs]), np.stack([c['pbc'] for c in cfgs]))
+        res[label] = [eng.trial_delta_e(oo, oi, no, npos, nz, rep=rep[perm]).copy() for _ in range(2)]
+        eng.close()
+    base = res['direct'][0]
+    assert np.all(np.isfinite(base))
+    for label, runs in res.items():
+        for r in runs:
+            assert np.array_equal(r, base), label
+    for t in range(0, len(perm), len(perm) // 12):
+        k, tt = int(rep[perm[t]]), int(perm[t]) % 12_000
+        c = cfgs[k]
+        p1, _ = synthetic.apply_trial(c, parts[k], tt)
+        E0 = cfast.lj_energy(c['positions'], c['cell'], c['pbc'], 1.0, 1.0, 3.0)
+        ref = cfast.lj_energy(p1, c['cell'], c['pbc'], 1.0, 1.0, 3.0) - E0
+        assert abs(base[t] - ref) <= de_tol(ref, E0), (t, base[t], ref)
