@@ -282,6 +282,82 @@ int64_t mcpyb_launch_count(const mcpyb_engine* e);
  * is.  launches_out / trials_out (may be NULL): grids launched and trials answered through the mailbox so far.    */
 int mcpyb_resident_chain(mcpyb_engine* e, int enable, int64_t* launches_out, int64_t* trials_out);
 
+/* ---- device-resident GCMC chains ---------------------------------------------
+ * Whole Markov chains of GrandCanonicalEnsemble.do_gcmc_step (mcpy/ensembles/grand_canonical_ensemble.py:244-308)
+ * on the device, ONE CTA per chain, the chain's state (positions, atom order, cell lists, random-number states) held
+ * in the CTA's shared memory for the length of a launch: MoveSelector.do_trial_move (moves/move_selector.py:74-96),
+ * InsertionMove / DeletionMove / DisplacementMove.do_trial_move (insertion_move.py:30-74, deletion_move.py:19-47,
+ * displacement_move.py:51-84) over a periodic box Cell (cell/cell.py:34-41), the LJ trial dE, _acceptance_condition
+ * (:197-242), atoms.wrap() and _record_minimum (base_ensemble.py:142-150) on acceptance.  The five MT19937 streams
+ * (random.Random: selector, one per move, acceptance -- utils/random_number_generator.py:4-47) and the cells' PCG64
+ * streams are taken from and handed back to the caller, so a chain can alternate between the device and the
+ * reference's own host loop and the draw sequence, the accept / reject sequence and the configuration stay those of
+ * the host loop.  Scope: one atomic species, Lennard-Jones, orthorhombic box periodic along all three axes with
+ * rc < L/2, no constraints, no min_insert; anything else goes through the calculator path.                      */
+#define MCPYB_GCMC_MAX_MOVES 8
+#define MCPYB_GCMC_MT_WORDS 625      /* 624 state words + the position, as random.Random.getstate()[1] */
+typedef struct mcpyb_gcmc mcpyb_gcmc;
+enum { MCPYB_GCMC_INSERT = 0, MCPYB_GCMC_DELETE = 1, MCPYB_GCMC_DISPLACE = 2 };
+enum {                                   /* per-chain status after mcpyb_gcmc_run                               */
+    MCPYB_GCMC_DONE = 0,                 /* all requested trials done                                           */
+    MCPYB_GCMC_CELL_FULL = 1,            /* stopped between two trials: a cell list reached its capacity         */
+    MCPYB_GCMC_ATOMS_FULL = 2,           /* stopped between two trials: the atom storage is full                 */
+    MCPYB_GCMC_TRACE_FULL = 3,           /* stopped between two trials: the trace buffer is full                 */
+    MCPYB_GCMC_EMPTY_DISPLACE = 4        /* DisplacementMove on an empty configuration (the reference raises)    */
+};
+typedef struct mcpyb_gcmc_desc {
+    double box[3];                                   /* diagonal of atoms.cell                                   */
+    double beta, mu, lambda3;                        /* SetUnits.beta, mu[species], lambda_dbs[species] ** 3      */
+    double lj_epsilon, lj_sigma, lj_rc;
+    double move_cum_weight[MCPYB_GCMC_MAX_MOVES];    /* MoveSelector.rho                                         */
+    double move_volume[MCPYB_GCMC_MAX_MOVES];        /* move.get_volume() (insertion / deletion)                 */
+    double move_max_displacement[MCPYB_GCMC_MAX_MOVES];
+    int32_t move_kind[MCPYB_GCMC_MAX_MOVES];         /* MCPYB_GCMC_INSERT / _DELETE / _DISPLACE                  */
+    int32_t move_limit[MCPYB_GCMC_MAX_MOVES];        /* max_atoms (insertion) / min_atoms (deletion); -1 = none  */
+    int32_t move_pcg[MCPYB_GCMC_MAX_MOVES];          /* insertion: which PCG64 stream (cell) it draws from        */
+    int32_t n_move_types;
+    int32_t atom_capacity;                           /* storage, in atoms (<= 65535)                             */
+    int32_t cell_capacity;                           /* slots per cell of the chain's cell list; 0 = choose       */
+} mcpyb_gcmc_desc;
+typedef struct mcpyb_gcmc_scalars {                  /* read / written by get_state / set_state                  */
+    double energy;                                   /* E_old                                                    */
+    double best_score, best_energy;                  /* _best_score / _best_energy                               */
+    int64_t attempts[MCPYB_GCMC_MAX_MOVES];          /* since set_state: move_counter                            */
+    int64_t accepted[MCPYB_GCMC_MAX_MOVES];          /*                  move_acceptance                         */
+    int64_t failed[MCPYB_GCMC_MAX_MOVES];            /*                  move_failed_counter                     */
+    int64_t trials_done;                             /* since set_state                                          */
+    uint64_t pcg[MCPYB_GCMC_MAX_MOVES][4];           /* per stream: state hi, lo, inc hi, lo                     */
+    int32_t n_atoms;
+    int32_t best_n;                                  /* atoms of the best configuration; -1 = not improved        */
+    int32_t last_move;                               /* MoveSelector.to_use                                      */
+    int32_t status;
+} mcpyb_gcmc_scalars;
+typedef struct mcpyb_gcmc_trial {                    /* one record per trial when a trace is requested           */
+    double dE;                                       /* NaN for a failed proposal                                */
+    int32_t move;                                    /* index into the move list                                 */
+    int32_t flags;                                   /* bit 0 accepted, bit 1 failed proposal, bit 2 a draw was consumed */
+    int32_t n_atoms;                                 /* after the trial                                          */
+    int32_t index;                                   /* deleted / displaced atom index, insertion: N              */
+} mcpyb_gcmc_trial;
+/* n_chains chains, desc[c] each; trace_capacity > 0 keeps the last launch's trial records per chain.  */
+int mcpyb_gcmc_create(mcpyb_engine* e, int n_chains, const mcpyb_gcmc_desc* desc, int64_t trace_capacity,
+                      mcpyb_gcmc** out);
+void mcpyb_gcmc_destroy(mcpyb_gcmc* g);
+/* positions[n][3] in atom order; mt[(n_move_types + 2)][625]: selector, moves in list order, acceptance.  */
+int mcpyb_gcmc_set_state(mcpyb_gcmc* g, int chain, const double* positions, const mcpyb_gcmc_scalars* s,
+                         const uint32_t* mt);
+/* positions_out[atom_capacity][3], best_positions_out[atom_capacity][3] (may be NULL). */
+int mcpyb_gcmc_get_state(mcpyb_gcmc* g, int chain, double* positions_out, mcpyb_gcmc_scalars* s_out,
+                         uint32_t* mt_out, double* best_positions_out);
+/* Every chain advances by up to n_trials[c] trials in ONE launch (grid = chains) and the call returns when the
+ * launch has finished; a chain that stops early says why in its status and how far it got in trials_done.   */
+int mcpyb_gcmc_run(mcpyb_gcmc* g, const int64_t* n_trials, int32_t* status_out);
+int mcpyb_gcmc_get_trace(mcpyb_gcmc* g, int chain, mcpyb_gcmc_trial* out, int64_t capacity, int64_t* n_out);
+/* cell list geometry chosen for a chain: cells per axis, slots per cell, bytes of state, 1 if it lives in shared memory */
+int mcpyb_gcmc_info(mcpyb_gcmc* g, int chain, int32_t* out6);
+/* device time of the last mcpyb_gcmc_run launch (CUDA events on the engine's stream) */
+int mcpyb_gcmc_last_run_ms(mcpyb_gcmc* g, double* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,7 +30,36 @@ SYMBOLS = [
     'mcpyb_alloc_pinned', 'mcpyb_free_pinned',
     'mcpyb_min_dist2_host', 'mcpyb_pcg64_host_doubles', 'mcpyb_fp64_peak_tflops', 'mcpyb_stage_timing', 'mcpyb_launch_count',
     'mcpyb_resident_chain', 'mcpyb_set_precision', 'mcpyb_copy_segments_dev',
+    'mcpyb_gcmc_create', 'mcpyb_gcmc_destroy', 'mcpyb_gcmc_set_state', 'mcpyb_gcmc_get_state', 'mcpyb_gcmc_run',
+    'mcpyb_gcmc_get_trace', 'mcpyb_gcmc_info', 'mcpyb_gcmc_last_run_ms',
 ]
+
+GCMC_MAX_MOVES = 8          # MCPYB_GCMC_MAX_MOVES
+GCMC_MT_WORDS = 625         # MCPYB_GCMC_MT_WORDS
+
+
+class GcmcDesc(C.Structure):
+    """``mcpyb_gcmc_desc``."""
+    _fields_ = [('box', C.c_double * 3), ('beta', C.c_double), ('mu', C.c_double), ('lambda3', C.c_double),
+                ('lj_epsilon', C.c_double), ('lj_sigma', C.c_double), ('lj_rc', C.c_double),
+                ('move_cum_weight', C.c_double * GCMC_MAX_MOVES), ('move_volume', C.c_double * GCMC_MAX_MOVES),
+                ('move_max_displacement', C.c_double * GCMC_MAX_MOVES),
+                ('move_kind', C.c_int32 * GCMC_MAX_MOVES), ('move_limit', C.c_int32 * GCMC_MAX_MOVES),
+                ('move_pcg', C.c_int32 * GCMC_MAX_MOVES),
+                ('n_move_types', C.c_int32), ('atom_capacity', C.c_int32), ('cell_capacity', C.c_int32)]
+
+
+class GcmcScalars(C.Structure):
+    """``mcpyb_gcmc_scalars``."""
+    _fields_ = [('energy', C.c_double), ('best_score', C.c_double), ('best_energy', C.c_double),
+                ('attempts', C.c_int64 * GCMC_MAX_MOVES), ('accepted', C.c_int64 * GCMC_MAX_MOVES),
+                ('failed', C.c_int64 * GCMC_MAX_MOVES), ('trials_done', C.c_int64),
+                ('pcg', (C.c_uint64 * 4) * GCMC_MAX_MOVES),
+                ('n_atoms', C.c_int32), ('best_n', C.c_int32), ('last_move', C.c_int32), ('status', C.c_int32)]
+
+
+GCMC_TRIAL_DTYPE = np.dtype([('dE', np.float64), ('move', np.int32), ('flags', np.int32), ('n_atoms', np.int32),
+                             ('index', np.int32)])          # mcpyb_gcmc_trial
 
 _p = C.c_void_p
 _i64p = C.POINTER(C.c_int64)
@@ -109,6 +138,15 @@ def load():
     lib.mcpyb_launch_count.restype = C.c_int64
     lib.mcpyb_resident_chain.argtypes = [_p, C.c_int, _i64p, _i64p]
     lib.mcpyb_set_precision.argtypes = [_p, C.c_int]
+    lib.mcpyb_gcmc_create.argtypes = [_p, C.c_int, C.POINTER(GcmcDesc), C.c_int64, C.POINTER(_p)]
+    lib.mcpyb_gcmc_destroy.argtypes = [_p]
+    lib.mcpyb_gcmc_destroy.restype = None
+    lib.mcpyb_gcmc_set_state.argtypes = [_p, C.c_int, _p, C.POINTER(GcmcScalars), _p]
+    lib.mcpyb_gcmc_get_state.argtypes = [_p, C.c_int, _p, C.POINTER(GcmcScalars), _p, _p]
+    lib.mcpyb_gcmc_run.argtypes = [_p, _p, _p]
+    lib.mcpyb_gcmc_get_trace.argtypes = [_p, C.c_int, _p, C.c_int64, _i64p]
+    lib.mcpyb_gcmc_info.argtypes = [_p, C.c_int, _p]
+    lib.mcpyb_gcmc_last_run_ms.argtypes = [_p, _f64p]
     _lib = lib
     return lib
 

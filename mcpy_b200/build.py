@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmcpy_b200.so')
 SOURCES = ['engine.cu']
 HEADERS = ['common.cuh', 'cell_list.cuh', 'stencil.cuh', 'lj_kernels.cuh', 'emt_kernels.cuh',
-           'free_volume.cuh', 'pcg64.cuh', 'site_kernels.cuh', 'rows_block.cuh', 'rows_warp.cuh', 'chain.cuh', 'emt_rows.cuh', os.path.join('..', '..', 'include', 'mcpy_b200.h')]
+           'free_volume.cuh', 'pcg64.cuh', 'site_kernels.cuh', 'rows_block.cuh', 'rows_warp.cuh', 'chain.cuh', 'emt_rows.cuh', 'gcmc_chain.cuh', os.path.join('..', '..', 'include', 'mcpy_b200.h')]
 
 NVCC_FLAGS = [
     '-O3', '-std=c++17',

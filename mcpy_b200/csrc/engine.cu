@@ -2676,3 +2676,6 @@ int mcpyb_pcg64_host_doubles(const uint64_t* state_hi_lo, const uint64_t* inc_hi
 }
 
 }  // extern "C"
+
+// f2: device-resident GCMC chains (kernel + its C ABI); needs mcpyb_engine, CK and LAUNCH_CHECK from above
+#include "gcmc_chain.cuh"

@@ -1,0 +1,725 @@
+// f2 -- device-resident GCMC chains: the loop of GrandCanonicalEnsemble.do_gcmc_step
+// (mcpy/ensembles/grand_canonical_ensemble.py:244-308) without a host round trip per trial.
+//
+// ONE CTA runs one Markov chain.  For the length of a launch the chain's whole state lives in the CTA's shared memory
+// (2 000 atoms: 61 KB of positions, 23 KB of cell lists, 12 KB of Mersenne-Twister states, ... ~115 KB of the 227 KB):
+//   px, py, pz [slot]      positions by storage slot (a slot is stable for the life of an atom)
+//   order [index]          atom index -> slot: the reference's atom order (del atoms[i] shifts it, insertion appends);
+//                          order[n..] holds the free slots
+//   cell_cnt / cell_slots  cell list of edge >= rc/2 with a fixed number of slots per cell
+//   mt [stream][625]       MT19937 states of random.Random: MoveSelector.rng, each move's rng, rng_acceptance
+// Thread 0 is the Markov chain (draws, proposal, acceptance, commit); the CTA is its energy evaluator: a quad of
+// lanes per stencil cell of each site, candidates by minimum image, the LJ pair sum folded in a fixed order.
+//
+// What is restated, with the reference's draw order (the contract is an identical accept / reject sequence):
+//   MoveSelector.__get_index__ / do_trial_move           moves/move_selector.py:66-87
+//   InsertionMove.do_trial_move (no min_insert)          moves/insertion_move.py:30-74   + Cell.get_random_point cell.py:34-41
+//   DeletionMove.do_trial_move                           moves/deletion_move.py:19-47
+//   DisplacementMove.do_trial_move (n_steps = 1)         moves/displacement_move.py:51-84
+//   GrandCanonicalEnsemble._acceptance_condition         ensembles/grand_canonical_ensemble.py:197-242
+//   Atoms.wrap() on acceptance (:296-297)                ase.geometry.wrap_positions, diagonal cell
+//   BaseEnsemble._record_minimum                         ensembles/base_ensemble.py:142-150
+//   random.Random: random(), _randbelow(), choice()      CPython Lib/random.py, Modules/_randommodule.c (MT19937)
+#pragma once
+#include "common.cuh"
+#include "lj_kernels.cuh"
+#include "pcg64.cuh"
+#include "../../include/mcpy_b200.h"
+
+#define GC_THREADS 512
+#define GC_QUADS (GC_THREADS / 4)
+#define GC_NONE 0xFFFF
+#define GC_SERIAL_WRAP 6          // unstable lists up to this length are wrapped by thread 0 itself
+
+struct GcLayout {                 // byte offsets of the arrays inside a chain's state block
+    int px, py, pz, mt, order, cell_of, unstable, uflag, cell_cnt, cell_slots, bytes;
+};
+
+struct GcChain {                  // read-only description of one chain
+    mcpyb_gcmc_desc d;
+    double inv_box[3];
+    LJParams lj;
+    int ncell[3], span[3];
+    int ncells, ccap, acap, nmt;
+    GcLayout lay;
+    unsigned char* blob;          // the state block in global memory
+    double* best_pos;             // [acap][3], atom order
+    mcpyb_gcmc_trial* trace;
+    long long trace_cap;
+    int in_smem;
+};
+
+struct GcDyn {                    // read-write scalars of one chain
+    mcpyb_gcmc_scalars s;
+    long long trace_len;
+    int n_unstable;
+    int pad;
+};
+
+static inline int gc_align16(int x) { return (x + 15) & ~15; }
+static inline GcLayout gc_layout(int acap, int ncells, int ccap, int nmt) {
+    GcLayout l;
+    int o = 0;
+    l.px = o; o += gc_align16(8 * acap);
+    l.py = o; o += gc_align16(8 * acap);
+    l.pz = o; o += gc_align16(8 * acap);
+    l.mt = o; o += gc_align16(4 * MCPYB_GCMC_MT_WORDS * nmt);
+    l.order = o; o += gc_align16(2 * acap);
+    l.cell_of = o; o += gc_align16(2 * acap);
+    l.unstable = o; o += gc_align16(2 * acap);
+    l.uflag = o; o += gc_align16(acap);
+    l.cell_cnt = o; o += gc_align16(2 * ncells);
+    l.cell_slots = o; o += gc_align16(2 * ncells * ccap);
+    l.bytes = o;
+    return l;
+}
+
+// ---- MT19937 as CPython drives it --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gc_mt_next(uint32_t* s) {
+    uint32_t i = s[624];
+    if (i >= 624) {
+        // genrand_uint32's regeneration, in place: s[k + 1] is carried in a register, s[k + 397 - 624] is already new
+        // for k >= 227, and k = 623 pairs the old s[623] with the NEW s[0]
+        uint32_t cur = s[0];
+        for (int k = 0; k < 623; ++k) {
+            const int km = (k + 397 >= 624) ? k + 397 - 624 : k + 397;
+            const uint32_t nxt = s[k + 1];
+            const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+            s[k] = s[km] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            cur = nxt;
+        }
+        const uint32_t y = (cur & 0x80000000u) | (s[0] & 0x7fffffffu);
+        s[623] = s[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        i = 0;
+    }
+    uint32_t y = s[i];
+    s[624] = i + 1;
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+// random.random(): (a * 2^26 + b) / 2^53 with a = 27 bits, b = 26 bits (exact in fp64)
+__device__ __forceinline__ double gc_mt_random(uint32_t* s) {
+    const uint32_t a = gc_mt_next(s) >> 5, b = gc_mt_next(s) >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
+// Random._randbelow_with_getrandbits(n), n >= 1: k = n.bit_length(); r = getrandbits(k) until r < n
+__device__ __forceinline__ uint32_t gc_mt_randbelow(uint32_t* s, uint32_t n) {
+    const int k = 32 - __clz(n);
+    uint32_t r = gc_mt_next(s) >> (32 - k);
+    while (r >= n) r = gc_mt_next(s) >> (32 - k);
+    return r;
+}
+
+// ase.geometry.wrap_positions for a diagonal cell and a periodic axis (center 0.5, eps 1e-7), operation for operation:
+// fractional = x * (1/L) - shift, shift = -1e-7 (np.linalg.solve on a diagonal matrix multiplies by the reciprocal);
+// fractional %= 1.0 (numpy remainder); fractional += shift; x' = fractional * L.
+__device__ __forceinline__ double gc_wrap(double x, double inv, double L) {
+    const double f = __dadd_rn(__dmul_rn(x, inv), 1e-7);
+    double m = __dsub_rn(f, trunc(f));                 // fmod(f, 1.0), exact
+    if (m != 0.0) { if (m < 0.0) m = __dadd_rn(m, 1.0); } else m = 0.0;
+    return __dmul_rn(__dadd_rn(m, -1e-7), L);
+}
+
+__device__ __forceinline__ int gc_cell_coord(double x, double inv, int nc) {
+    double f = x * inv;
+    f -= floor(f);
+    int c = (int)(f * (double)nc);
+    return c < 0 ? 0 : (c >= nc ? nc - 1 : c);
+}
+
+struct GcTrial {                  // thread 0 -> CTA
+    double sx[2], sy[2], sz[2];   // site positions: [0] removed (sign -1) or inserted; [1] the new position of a displacement
+    double sign[2];
+    int home[2][3];
+    int nsites;
+    int excl;                     // slot left out of the sums (the moved / deleted atom), GC_NONE for an insertion
+    int done;
+    int par;                      // parallel commit work: bit 0 shift the order, bit 1 wrap the unstable list, bit 2 copy the best
+    int shift_from, shift_n;      // order[shift_from .. shift_n - 2] <- order[shift_from + 1 .. shift_n - 1]
+    int freed_slot;
+    int n;                        // atoms after the commit (for the best copy)
+    int n_unstable;
+};
+
+#define GC_PAR_SHIFT 1
+#define GC_PAR_WRAP 2
+#define GC_PAR_BEST 4
+
+__global__ void __launch_bounds__(GC_THREADS, 1)
+gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, const long long* __restrict__ n_trials) {
+    extern __shared__ __align__(16) unsigned char gc_smem[];
+    __shared__ GcTrial T;
+    __shared__ double s_part[GC_THREADS / 32];
+    __shared__ unsigned long long s_pcg[MCPYB_GCMC_MAX_MOVES][4];
+    __shared__ long long s_cnt[3][MCPYB_GCMC_MAX_MOVES];      // attempts, accepted, failed
+
+    const GcChain& C = chains[blockIdx.x];
+    GcDyn& D = dyn[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const GcLayout lay = C.lay;
+    unsigned char* base = C.in_smem ? gc_smem : C.blob;
+    if (C.in_smem) {
+        const uint4* src = reinterpret_cast<const uint4*>(C.blob);
+        uint4* dst = reinterpret_cast<uint4*>(gc_smem);
+        for (int i = tid; i < lay.bytes / 16; i += GC_THREADS) dst[i] = src[i];
+    }
+    double* px = reinterpret_cast<double*>(base + lay.px);
+    double* py = reinterpret_cast<double*>(base + lay.py);
+    double* pz = reinterpret_cast<double*>(base + lay.pz);
+    uint32_t* mt = reinterpret_cast<uint32_t*>(base + lay.mt);
+    unsigned short* order = reinterpret_cast<unsigned short*>(base + lay.order);
+    unsigned short* cell_of = reinterpret_cast<unsigned short*>(base + lay.cell_of);
+    unsigned short* unstable = reinterpret_cast<unsigned short*>(base + lay.unstable);
+    unsigned char* uflag = base + lay.uflag;
+    unsigned short* cell_cnt = reinterpret_cast<unsigned short*>(base + lay.cell_cnt);
+    unsigned short* cell_slots = reinterpret_cast<unsigned short*>(base + lay.cell_slots);
+
+    const double L0 = C.d.box[0], L1 = C.d.box[1], L2 = C.d.box[2];
+    const double i0 = C.inv_box[0], i1 = C.inv_box[1], i2 = C.inv_box[2];
+    const int nc0 = C.ncell[0], nc1 = C.ncell[1], nc2 = C.ncell[2];
+    const int sp0 = C.span[0], sp1 = C.span[1], sp2 = C.span[2];
+    const int ns = sp0 * sp1 * sp2;
+    const int ccap = C.ccap;
+    const LJParams lj = C.lj;
+    const int nm = C.d.n_move_types;
+
+    // thread 0's chain state
+    int n = 0, n_unst = 0, pending = 0, cur_move = 0, cur_kind = 0, cur_index = 0, have_rows = 0, drew = 0;
+    long long t_done = 0, t_goal = 0, trace_len = 0;
+    double E = 0.0, best_score = 0.0, best_E = 0.0;
+    int best_n = -1;
+    if (tid == 0) {
+        n = D.s.n_atoms; n_unst = D.n_unstable; E = D.s.energy; best_score = D.s.best_score; best_E = D.s.best_energy;
+        best_n = D.s.best_n; t_done = D.s.trials_done; t_goal = t_done + n_trials[blockIdx.x]; trace_len = 0;
+        for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k)
+            for (int j = 0; j < 4; ++j) s_pcg[k][j] = D.s.pcg[k][j];
+        for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k) { s_cnt[0][k] = D.s.attempts[k]; s_cnt[1][k] = D.s.accepted[k]; s_cnt[2][k] = D.s.failed[k]; }
+        T.done = 0; T.par = 0; T.nsites = 0;
+        D.s.status = MCPYB_GCMC_DONE;
+    }
+    __syncthreads();
+
+    while (true) {
+        if (tid == 0) {
+            // ---------------- the Markov chain proper (serial) ----------------
+            bool proposing = true;
+            if (T.par) { T.par = 0; }                       // the parallel commit of the last trial is done
+            else if (have_rows) {
+                have_rows = 0;
+                double dE = 0.0;
+                for (int w = 0; w < GC_THREADS / 32; ++w) dE += s_part[w];
+                // _acceptance_condition; n is the pre-move atom count (self.n_atoms)
+                bool acc;
+                drew = 0;
+                uint32_t* mt_acc = mt + (nm + 1) * MCPYB_GCMC_MT_WORDS;
+                if (cur_kind == MCPYB_GCMC_DISPLACE) {
+                    if (dE <= 0.0) acc = true;
+                    else { const double p = exp(__dmul_rn(-dE, C.d.beta)); drew = 1; acc = p > gc_mt_random(mt_acc); }
+                } else {
+                    double p;
+                    if (cur_kind == MCPYB_GCMC_INSERT) {
+                        const double db = C.d.move_volume[cur_move] / __dmul_rn((double)(n + 1), C.d.lambda3);
+                        p = __dmul_rn(db, exp(__dmul_rn(-C.d.beta, __dsub_rn(dE, C.d.mu))));
+                    } else {
+                        const double db = __dmul_rn(C.d.lambda3, (double)n) / C.d.move_volume[cur_move];
+                        p = __dmul_rn(db, exp(__dmul_rn(-C.d.beta, __dadd_rn(dE, C.d.mu))));
+                    }
+                    if (p > 1.0) acc = true;
+                    else { drew = 1; acc = p > gc_mt_random(mt_acc); }
+                }
+                int par = 0;
+                if (acc) {
+                    s_cnt[1][cur_move] += 1;
+                    int moved = GC_NONE;
+                    if (cur_kind == MCPYB_GCMC_INSERT) {
+                        const int slot = order[n];
+                        px[slot] = T.sx[0]; py[slot] = T.sy[0]; pz[slot] = T.sz[0];
+                        const int c = (T.home[0][0] * nc1 + T.home[0][1]) * nc2 + T.home[0][2];
+                        const int cnt = cell_cnt[c];
+                        cell_slots[c * ccap + cnt] = (unsigned short)slot;
+                        cell_cnt[c] = (unsigned short)(cnt + 1);
+                        cell_of[slot] = (unsigned short)c;
+                        if (cnt + 1 >= ccap) pending = MCPYB_GCMC_CELL_FULL;
+                        ++n;
+                        if (n >= C.acap) pending = MCPYB_GCMC_ATOMS_FULL;
+                        moved = slot;
+                    } else {
+                        const int slot = T.excl;
+                        const int c_old = cell_of[slot];
+                        const int c_new = cur_kind == MCPYB_GCMC_DISPLACE
+                                              ? (T.home[1][0] * nc1 + T.home[1][1]) * nc2 + T.home[1][2] : -1;
+                        if (c_new != c_old) {
+                            const int cnt = cell_cnt[c_old];
+                            unsigned short* lst = cell_slots + c_old * ccap;
+                            int k = 0;
+                            while (k < cnt && lst[k] != slot) ++k;
+                            lst[k] = lst[cnt - 1];
+                            cell_cnt[c_old] = (unsigned short)(cnt - 1);
+                            if (c_new >= 0) {
+                                const int cn = cell_cnt[c_new];
+                                cell_slots[c_new * ccap + cn] = (unsigned short)slot;
+                                cell_cnt[c_new] = (unsigned short)(cn + 1);
+                                cell_of[slot] = (unsigned short)c_new;
+                                if (cn + 1 >= ccap) pending = MCPYB_GCMC_CELL_FULL;
+                            }
+                        }
+                        if (cur_kind == MCPYB_GCMC_DISPLACE) {
+                            px[slot] = T.sx[1]; py[slot] = T.sy[1]; pz[slot] = T.sz[1];
+                            moved = slot;
+                        } else {
+                            // del atoms[i]: the order shifts down (in parallel), the slot joins the free ones
+                            par |= GC_PAR_SHIFT;
+                            T.shift_from = cur_index; T.shift_n = n; T.freed_slot = slot;
+                            --n;
+                            if (uflag[slot]) {
+                                uflag[slot] = 0;
+                                int k = 0;
+                                while (k < n_unst && unstable[k] != slot) ++k;
+                                if (k < n_unst) { unstable[k] = unstable[n_unst - 1]; --n_unst; }
+                            }
+                        }
+                    }
+                    if (moved != GC_NONE && !uflag[moved]) { uflag[moved] = 1; unstable[n_unst++] = (unsigned short)moved; }
+                    E += dE;
+                    // atoms.wrap(): only atoms whose last wrap still changed a bit can change again
+                    if (n_unst <= GC_SERIAL_WRAP) {
+                        int keep = 0;
+                        for (int k = 0; k < n_unst; ++k) {
+                            const int s = unstable[k];
+                            const double x = px[s], y = py[s], z = pz[s];
+                            const double xw = gc_wrap(x, i0, L0), yw = gc_wrap(y, i1, L1), zw = gc_wrap(z, i2, L2);
+                            if (xw != x || yw != y || zw != z) { px[s] = xw; py[s] = yw; pz[s] = zw; unstable[keep++] = (unsigned short)s; }
+                            else uflag[s] = 0;
+                        }
+                        n_unst = keep;
+                    } else {
+                        par |= GC_PAR_WRAP;
+                        T.n_unstable = n_unst;
+                    }
+                    // _record_minimum: score = E - mu * N
+                    const double score = __dsub_rn(E, __dmul_rn(C.d.mu, (double)n));
+                    if (score < best_score) { best_score = score; best_E = E; best_n = n; par |= GC_PAR_BEST; }
+                    T.n = n;
+                }
+                if (C.trace) {
+                    mcpyb_gcmc_trial r;
+                    r.dE = dE; r.move = cur_move; r.flags = (acc ? 1 : 0) | (drew ? 4 : 0); r.n_atoms = n; r.index = cur_index;
+                    C.trace[trace_len++] = r;
+                }
+                ++t_done;
+                if (par) { T.par = par; proposing = false; }
+            }
+            // ---------------- next proposal ----------------
+            while (proposing) {
+                if (pending) { D.s.status = pending; T.done = 1; break; }
+                if (t_done >= t_goal) { T.done = 1; break; }
+                if (C.trace && trace_len >= C.trace_cap) { D.s.status = MCPYB_GCMC_TRACE_FULL; T.done = 1; break; }
+                // MoveSelector.__get_index__: searchsorted(rho, u * rho_total, side='right'), clamped
+                const double v = __dmul_rn(gc_mt_random(mt), C.d.move_cum_weight[nm - 1]);
+                int mv = 0;
+                while (mv < nm && C.d.move_cum_weight[mv] <= v) ++mv;
+                if (mv >= nm) mv = nm - 1;
+                cur_move = mv; cur_kind = C.d.move_kind[mv];
+                uint32_t* mt_mv = mt + (1 + mv) * MCPYB_GCMC_MT_WORDS;
+                bool failed = false;
+                if (cur_kind == MCPYB_GCMC_DISPLACE && n == 0) { D.s.status = MCPYB_GCMC_EMPTY_DISPLACE; T.done = 1; break; }
+                s_cnt[0][mv] += 1;
+                if (cur_kind == MCPYB_GCMC_INSERT) {
+                    gc_mt_randbelow(mt_mv, 1u);                                   // rng.random.choice(self.species)
+                    cur_index = n;
+                    if (C.d.move_limit[mv] >= 0 && n >= C.d.move_limit[mv]) failed = true;
+                    else {
+                        unsigned long long* ps = s_pcg[C.d.move_pcg[mv]];
+                        u128 st = ((u128)ps[0] << 64) | ps[1];
+                        const u128 inc = ((u128)ps[2] << 64) | ps[3];
+                        const double u0 = pcg_next_double(st, inc), u1 = pcg_next_double(st, inc), u2 = pcg_next_double(st, inc);
+                        ps[0] = (unsigned long long)(st >> 64); ps[1] = (unsigned long long)st;
+                        T.sx[0] = __dmul_rn(u0, L0); T.sy[0] = __dmul_rn(u1, L1); T.sz[0] = __dmul_rn(u2, L2);
+                        T.sign[0] = 1.0; T.nsites = 1; T.excl = GC_NONE;
+                    }
+                } else if (cur_kind == MCPYB_GCMC_DELETE) {
+                    gc_mt_randbelow(mt_mv, 1u);
+                    cur_index = -1;
+                    if ((C.d.move_limit[mv] >= 0 && n <= C.d.move_limit[mv]) || n == 0) failed = true;
+                    else {
+                        cur_index = (int)gc_mt_randbelow(mt_mv, (uint32_t)n);     // rng.random.choice(indices_of_species)
+                        const int slot = order[cur_index];
+                        T.sx[0] = px[slot]; T.sy[0] = py[slot]; T.sz[0] = pz[slot];
+                        T.sign[0] = -1.0; T.nsites = 1; T.excl = slot;
+                    }
+                } else {
+                    cur_index = (int)gc_mt_randbelow(mt_mv, (uint32_t)n);         // rng.random.choice(to_move)
+                    const int slot = order[cur_index];
+                    double rx, ry, rz, rsq;
+                    do {
+                        rx = __dsub_rn(__dmul_rn(2.0, gc_mt_random(mt_mv)), 1.0);
+                        ry = __dsub_rn(__dmul_rn(2.0, gc_mt_random(mt_mv)), 1.0);
+                        rz = __dsub_rn(__dmul_rn(2.0, gc_mt_random(mt_mv)), 1.0);
+                        rsq = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                    } while (rsq > 1.0);
+                    const double md = C.d.move_max_displacement[mv];
+                    T.sx[0] = px[slot]; T.sy[0] = py[slot]; T.sz[0] = pz[slot];
+                    T.sx[1] = __dadd_rn(T.sx[0], __dmul_rn(rx, md));
+                    T.sy[1] = __dadd_rn(T.sy[0], __dmul_rn(ry, md));
+                    T.sz[1] = __dadd_rn(T.sz[0], __dmul_rn(rz, md));
+                    T.sign[0] = -1.0; T.sign[1] = 1.0; T.nsites = 2; T.excl = slot;
+                }
+                if (failed) {
+                    s_cnt[2][mv] += 1;
+                    if (C.trace) {
+                        mcpyb_gcmc_trial r;
+                        r.dE = __longlong_as_double(0x7ff8000000000000LL); r.move = mv; r.flags = 2; r.n_atoms = n; r.index = cur_index;
+                        C.trace[trace_len++] = r;
+                    }
+                    ++t_done;
+                    continue;
+                }
+                for (int s = 0; s < T.nsites; ++s) {
+                    T.home[s][0] = gc_cell_coord(T.sx[s], i0, nc0);
+                    T.home[s][1] = gc_cell_coord(T.sy[s], i1, nc1);
+                    T.home[s][2] = gc_cell_coord(T.sz[s], i2, nc2);
+                }
+                have_rows = 1;
+                break;
+            }
+        }
+        __syncthreads();
+        if (T.done) break;
+        if (T.par) {
+            const int par = T.par;
+            if (par & GC_PAR_SHIFT) {
+                const int from = T.shift_from, last = T.shift_n - 1;        // order[from .. last-1] <- order[from+1 .. last]
+                for (int b0 = from; b0 < last; b0 += GC_THREADS) {
+                    const int j = b0 + tid;
+                    unsigned short v = 0;
+                    if (j < last) v = order[j + 1];
+                    __syncthreads();
+                    if (j < last) order[j] = v;
+                    __syncthreads();
+                }
+                if (tid == 0) order[last] = (unsigned short)T.freed_slot;
+            }
+            if (par & GC_PAR_WRAP) {
+                const int nu = T.n_unstable;
+                for (int k = tid; k < nu; k += GC_THREADS) {
+                    const int s = unstable[k];
+                    const double x = px[s], y = py[s], z = pz[s];
+                    const double xw = gc_wrap(x, i0, L0), yw = gc_wrap(y, i1, L1), zw = gc_wrap(z, i2, L2);
+                    if (xw != x || yw != y || zw != z) { px[s] = xw; py[s] = yw; pz[s] = zw; }
+                    else { uflag[s] = 0; unstable[k] = GC_NONE; }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int keep = 0;
+                    for (int k = 0; k < nu; ++k) { const unsigned short s = unstable[k]; if (s != GC_NONE) unstable[keep++] = s; }
+                    n_unst = keep;
+                }
+            }
+            if (par & GC_PAR_BEST) {
+                __syncthreads();
+                const int nn = T.n;
+                for (int j = tid; j < nn; j += GC_THREADS) {
+                    const int s = order[j];
+                    C.best_pos[3 * j] = px[s]; C.best_pos[3 * j + 1] = py[s]; C.best_pos[3 * j + 2] = pz[s];
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---------------- row sums: a quad of lanes per (site, stencil cell) ----------------
+        {
+            double acc = 0.0;
+            const int ntasks = T.nsites * ns;
+            const int excl = T.excl;
+            for (int task = tid >> 2; task < ntasks; task += GC_QUADS) {
+                const int site = task >= ns ? 1 : 0;
+                int sc = task - site * ns;
+                const int a2 = sc % sp2; sc /= sp2;
+                const int a1 = sc % sp1;
+                const int a0 = sc / sp1;
+                int c0 = a0, c1 = a1, c2 = a2;
+                if (sp0 != nc0) { c0 = T.home[site][0] - 2 + a0; c0 += c0 < 0 ? nc0 : 0; c0 -= c0 >= nc0 ? nc0 : 0; }
+                if (sp1 != nc1) { c1 = T.home[site][1] - 2 + a1; c1 += c1 < 0 ? nc1 : 0; c1 -= c1 >= nc1 ? nc1 : 0; }
+                if (sp2 != nc2) { c2 = T.home[site][2] - 2 + a2; c2 += c2 < 0 ? nc2 : 0; c2 -= c2 >= nc2 ? nc2 : 0; }
+                const int cell = (c0 * nc1 + c1) * nc2 + c2;
+                const int cnt = cell_cnt[cell];
+                const double sx = T.sx[site], sy = T.sy[site], sz = T.sz[site], sg = T.sign[site];
+                for (int k = tid & 3; k < cnt; k += 4) {
+                    const int slot = cell_slots[cell * ccap + k];
+                    if (slot == excl) continue;
+                    const double x = px[slot], y = py[slot], z = pz[slot];
+                    // the image of the neighbour the reference's neighbour list pairs with the site: (pos_j + S * L) - pos_i
+                    const double S0 = -rint((x - sx) * i0), S1 = -rint((y - sy) * i1), S2 = -rint((z - sz) * i2);
+                    const double dx = __dsub_rn(__dadd_rn(x, __dmul_rn(S0, L0)), sx);
+                    const double dy = __dsub_rn(__dadd_rn(y, __dmul_rn(S1, L1)), sy);
+                    const double dz = __dsub_rn(__dadd_rn(z, __dmul_rn(S2, L2)), sz);
+                    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    if (r2 <= lj.rc2) acc += sg * lj_pair(lj, r2);
+                }
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) s_part[warp] = acc;
+        }
+        __syncthreads();
+    }
+
+    // ---------------- hand the state back ----------------
+    if (tid == 0) {
+        D.s.n_atoms = n; D.n_unstable = n_unst; D.s.energy = E; D.s.best_score = best_score; D.s.best_energy = best_E;
+        D.s.best_n = best_n; D.s.last_move = cur_move; D.s.trials_done = t_done; D.trace_len = trace_len;
+        for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k)
+            for (int j = 0; j < 4; ++j) D.s.pcg[k][j] = s_pcg[k][j];
+        for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k) { D.s.attempts[k] = s_cnt[0][k]; D.s.accepted[k] = s_cnt[1][k]; D.s.failed[k] = s_cnt[2][k]; }
+    }
+    __syncthreads();
+    if (C.in_smem) {
+        uint4* dst = reinterpret_cast<uint4*>(C.blob);
+        const uint4* src = reinterpret_cast<const uint4*>(gc_smem);
+        for (int i = tid; i < lay.bytes / 16; i += GC_THREADS) dst[i] = src[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side (C ABI: include/mcpy_b200.h, "device-resident GCMC chains")
+// ---------------------------------------------------------------------------------------------------------------
+struct mcpyb_gcmc {
+    mcpyb_engine* e = nullptr;
+    int n = 0;
+    std::vector<GcChain> chains;
+    std::vector<GcDyn> dyn;
+    GcChain* d_chains = nullptr;
+    GcDyn* d_dyn = nullptr;
+    long long* d_ntr = nullptr;
+    size_t smem = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    long long launches = 0;
+};
+
+namespace {
+
+int gc_cell_coord_host(double x, double inv, int nc) {
+    double f = x * inv;
+    f -= floor(f);
+    int c = (int)(f * (double)nc);
+    return c < 0 ? 0 : (c >= nc ? nc - 1 : c);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcpyb_gcmc_create(mcpyb_engine* e, int n_chains, const mcpyb_gcmc_desc* desc, int64_t trace_capacity, mcpyb_gcmc** out) {
+    if (!e || !out) return MCPYB_ERR_ARG;
+    *out = nullptr;
+    if (n_chains < 1 || !desc) return e->fail(MCPYB_ERR_ARG, "gcmc: need at least one chain");
+    cudaSetDevice(e->device);
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device), "query shared memory");
+    mcpyb_gcmc* g = new mcpyb_gcmc();
+    g->e = e; g->n = n_chains;
+    g->chains.resize(n_chains);
+    g->dyn.resize(n_chains);
+    memset(g->dyn.data(), 0, sizeof(GcDyn) * n_chains);
+    auto bail = [&](int code) { mcpyb_gcmc_destroy(g); return code; };
+    for (int c = 0; c < n_chains; ++c) {
+        GcChain& C = g->chains[c];
+        memset(&C, 0, sizeof C);
+        C.d = desc[c];
+        const mcpyb_gcmc_desc& d = C.d;
+        if (d.n_move_types < 1 || d.n_move_types > MCPYB_GCMC_MAX_MOVES) return bail(e->fail(MCPYB_ERR_ARG, "gcmc chain %d: 1..%d moves", c, MCPYB_GCMC_MAX_MOVES));
+        if (d.atom_capacity < 1 || d.atom_capacity > 65535) return bail(e->fail(MCPYB_ERR_ARG, "gcmc chain %d: atom_capacity must be 1..65535", c));
+        if (!(d.lj_sigma > 0.0) || !std::isfinite(d.lj_epsilon)) return bail(e->fail(MCPYB_ERR_ARG, "gcmc chain %d: sigma must be > 0 and epsilon finite", c));
+        const double rc = d.lj_rc > 0.0 ? d.lj_rc : 3.0 * d.lj_sigma;
+        for (int m = 0; m < d.n_move_types; ++m) {
+            if (d.move_kind[m] < 0 || d.move_kind[m] > 2) return bail(e->fail(MCPYB_ERR_ARG, "gcmc chain %d: unknown kind of move %d", c, m));
+            if (!(d.move_cum_weight[m] >= (m ? d.move_cum_weight[m - 1] : 0.0))) return bail(e->fail(MCPYB_ERR_ARG, "gcmc chain %d: cumulative move weights must not decrease", c));
+            if (d.move_kind[m] == MCPYB_GCMC_INSERT && (d.move_pcg[m] < 0 || d.move_pcg[m] >= MCPYB_GCMC_MAX_MOVES)) return bail(e->fail(MCPYB_ERR_ARG, "gcmc chain %d: move %d names no PCG64 stream", c, m));
+            if (d.move_kind[m] != MCPYB_GCMC_DISPLACE && !(d.move_volume[m] > 0.0)) return bail(e->fail(MCPYB_ERR_ARG, "gcmc chain %d: move %d needs a positive volume", c, m));
+        }
+        C.ncells = 1;
+        for (int k = 0; k < 3; ++k) {
+            if (!(d.box[k] > 2.0 * rc)) return bail(e->fail(MCPYB_ERR_ARG, "gcmc chain %d: box edge %d (%g) must exceed 2 rc (%g): the resident chain pairs an atom with ONE image of each neighbour", c, k, d.box[k], 2.0 * rc));
+            C.inv_box[k] = 1.0 / d.box[k];
+            int nc = (int)floor(d.box[k] / (0.5 * rc * (1.0 + 1e-6)));
+            if (nc > 40) nc = 40;
+            C.ncell[k] = nc;
+            C.span[k] = nc >= 5 ? 5 : nc;
+            C.ncells *= nc;
+        }
+        C.lj.eps4 = 4.0 * d.lj_epsilon; C.lj.sigma2 = d.lj_sigma * d.lj_sigma; C.lj.rc2 = rc * rc; C.lj.rc = rc;
+        C.lj.e0 = 4.0 * d.lj_epsilon * (pow(d.lj_sigma / rc, 12) - pow(d.lj_sigma / rc, 6));
+        C.acap = d.atom_capacity;
+        C.ccap = d.cell_capacity > 0 ? d.cell_capacity : 16;
+        if (C.ccap > 4096) return bail(e->fail(MCPYB_ERR_ARG, "gcmc chain %d: cell_capacity too large", c));
+        C.nmt = d.n_move_types + 2;
+        C.lay = gc_layout(C.acap, C.ncells, C.ccap, C.nmt);
+        C.in_smem = (size_t)C.lay.bytes + 4096 <= (size_t)optin;
+        if (C.in_smem && (size_t)C.lay.bytes > g->smem) g->smem = C.lay.bytes;
+        if (cudaMalloc(&C.blob, C.lay.bytes) != cudaSuccess) return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: cudaMalloc state"));
+        if (cudaMalloc(&C.best_pos, sizeof(double) * 3 * C.acap) != cudaSuccess) return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: cudaMalloc best"));
+        C.trace_cap = trace_capacity > 0 ? trace_capacity : 0;
+        if (C.trace_cap && cudaMalloc(&C.trace, sizeof(mcpyb_gcmc_trial) * C.trace_cap) != cudaSuccess) return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: cudaMalloc trace"));
+        g->dyn[c].s.best_n = -1;
+    }
+    if (cudaMalloc(&g->d_chains, sizeof(GcChain) * n_chains) != cudaSuccess || cudaMalloc(&g->d_dyn, sizeof(GcDyn) * n_chains) != cudaSuccess ||
+        cudaMalloc(&g->d_ntr, sizeof(long long) * n_chains) != cudaSuccess)
+        return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: cudaMalloc descriptors"));
+    if (cudaMemcpy(g->d_chains, g->chains.data(), sizeof(GcChain) * n_chains, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(g->d_dyn, g->dyn.data(), sizeof(GcDyn) * n_chains, cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: upload descriptors"));
+    if (g->smem && cudaFuncSetAttribute(gcmc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem) != cudaSuccess)
+        return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: shared memory opt-in of %zu bytes refused", g->smem));
+    cudaEventCreate(&g->ev0); cudaEventCreate(&g->ev1);
+    *out = g;
+    return MCPYB_OK;
+}
+
+void mcpyb_gcmc_destroy(mcpyb_gcmc* g) {
+    if (!g) return;
+    cudaSetDevice(g->e->device);
+    cudaStreamSynchronize(g->e->stream);
+    for (auto& C : g->chains) { if (C.blob) cudaFree(C.blob); if (C.best_pos) cudaFree(C.best_pos); if (C.trace) cudaFree(C.trace); }
+    if (g->d_chains) cudaFree(g->d_chains);
+    if (g->d_dyn) cudaFree(g->d_dyn);
+    if (g->d_ntr) cudaFree(g->d_ntr);
+    if (g->ev0) cudaEventDestroy(g->ev0);
+    if (g->ev1) cudaEventDestroy(g->ev1);
+    delete g;
+}
+
+int mcpyb_gcmc_set_state(mcpyb_gcmc* g, int chain, const double* positions, const mcpyb_gcmc_scalars* s, const uint32_t* mt) {
+    if (!g) return MCPYB_ERR_ARG;
+    mcpyb_engine* e = g->e;
+    if (chain < 0 || chain >= g->n || !s || !mt) return e->fail(MCPYB_ERR_ARG, "gcmc set_state: bad argument");
+    const GcChain& C = g->chains[chain];
+    const int n = s->n_atoms;
+    if (n < 0 || n >= C.acap) return e->fail(MCPYB_ERR_CAPACITY, "gcmc chain %d: %d atoms do not fit a capacity of %d (one slot stays free)", chain, n, C.acap);
+    if (n > 0 && !positions) return e->fail(MCPYB_ERR_ARG, "gcmc set_state: positions missing");
+    cudaSetDevice(e->device);
+    std::vector<unsigned char> blob(C.lay.bytes, 0);
+    double* px = reinterpret_cast<double*>(blob.data() + C.lay.px);
+    double* py = reinterpret_cast<double*>(blob.data() + C.lay.py);
+    double* pz = reinterpret_cast<double*>(blob.data() + C.lay.pz);
+    uint32_t* mts = reinterpret_cast<uint32_t*>(blob.data() + C.lay.mt);
+    unsigned short* order = reinterpret_cast<unsigned short*>(blob.data() + C.lay.order);
+    unsigned short* cell_of = reinterpret_cast<unsigned short*>(blob.data() + C.lay.cell_of);
+    unsigned short* unstable = reinterpret_cast<unsigned short*>(blob.data() + C.lay.unstable);
+    unsigned char* uflag = blob.data() + C.lay.uflag;
+    unsigned short* cell_cnt = reinterpret_cast<unsigned short*>(blob.data() + C.lay.cell_cnt);
+    unsigned short* cell_slots = reinterpret_cast<unsigned short*>(blob.data() + C.lay.cell_slots);
+    for (int i = 0; i < C.acap; ++i) order[i] = (unsigned short)i;
+    for (int i = 0; i < n; ++i) {
+        const double x = positions[3 * i], y = positions[3 * i + 1], z = positions[3 * i + 2];
+        if (!std::isfinite(x) || !std::isfinite(y) || !std::isfinite(z)) return e->fail(MCPYB_ERR_ARG, "gcmc chain %d: atom %d has a non-finite position", chain, i);
+        px[i] = x; py[i] = y; pz[i] = z;
+        const int c = (gc_cell_coord_host(x, C.inv_box[0], C.ncell[0]) * C.ncell[1] + gc_cell_coord_host(y, C.inv_box[1], C.ncell[1])) * C.ncell[2]
+                      + gc_cell_coord_host(z, C.inv_box[2], C.ncell[2]);
+        if (cell_cnt[c] + 1 >= C.ccap) return e->fail(MCPYB_ERR_CAPACITY, "gcmc chain %d: more than %d atoms in one cell of the chain's cell list", chain, C.ccap - 2);
+        cell_slots[c * C.ccap + cell_cnt[c]] = (unsigned short)i;
+        cell_cnt[c] += 1;
+        cell_of[i] = (unsigned short)c;
+        unstable[i] = (unsigned short)i;
+        uflag[i] = 1;
+    }
+    for (int k = 0; k < C.nmt; ++k) {
+        const uint32_t* src = mt + (size_t)k * MCPYB_GCMC_MT_WORDS;
+        if (src[624] > 624) return e->fail(MCPYB_ERR_ARG, "gcmc chain %d: Mersenne-Twister stream %d has position %u (> 624)", chain, k, src[624]);
+        memcpy(mts + (size_t)k * MCPYB_GCMC_MT_WORDS, src, sizeof(uint32_t) * MCPYB_GCMC_MT_WORDS);
+    }
+    GcDyn& D = g->dyn[chain];
+    D.s = *s;
+    D.s.status = MCPYB_GCMC_DONE;
+    D.trace_len = 0;
+    D.n_unstable = n;
+    CK(cudaMemcpyAsync(C.blob, blob.data(), C.lay.bytes, cudaMemcpyHostToDevice, e->stream), "gcmc upload state");
+    CK(cudaMemcpyAsync(g->d_dyn + chain, &D, sizeof(GcDyn), cudaMemcpyHostToDevice, e->stream), "gcmc upload scalars");
+    CK(cudaStreamSynchronize(e->stream), "gcmc set_state sync");
+    return MCPYB_OK;
+}
+
+int mcpyb_gcmc_get_state(mcpyb_gcmc* g, int chain, double* positions_out, mcpyb_gcmc_scalars* s_out, uint32_t* mt_out, double* best_positions_out) {
+    if (!g) return MCPYB_ERR_ARG;
+    mcpyb_engine* e = g->e;
+    if (chain < 0 || chain >= g->n) return e->fail(MCPYB_ERR_ARG, "gcmc get_state: no chain %d", chain);
+    const GcChain& C = g->chains[chain];
+    cudaSetDevice(e->device);
+    std::vector<unsigned char> blob(C.lay.bytes);
+    GcDyn& D = g->dyn[chain];
+    CK(cudaMemcpyAsync(blob.data(), C.blob, C.lay.bytes, cudaMemcpyDeviceToHost, e->stream), "gcmc download state");
+    CK(cudaMemcpyAsync(&D, g->d_dyn + chain, sizeof(GcDyn), cudaMemcpyDeviceToHost, e->stream), "gcmc download scalars");
+    CK(cudaStreamSynchronize(e->stream), "gcmc get_state sync");
+    if (s_out) *s_out = D.s;
+    const int n = D.s.n_atoms;
+    if (positions_out) {
+        const double* px = reinterpret_cast<const double*>(blob.data() + C.lay.px);
+        const double* py = reinterpret_cast<const double*>(blob.data() + C.lay.py);
+        const double* pz = reinterpret_cast<const double*>(blob.data() + C.lay.pz);
+        const unsigned short* order = reinterpret_cast<const unsigned short*>(blob.data() + C.lay.order);
+        for (int i = 0; i < n; ++i) {
+            const int s = order[i];
+            positions_out[3 * i] = px[s]; positions_out[3 * i + 1] = py[s]; positions_out[3 * i + 2] = pz[s];
+        }
+    }
+    if (mt_out) memcpy(mt_out, blob.data() + C.lay.mt, sizeof(uint32_t) * MCPYB_GCMC_MT_WORDS * C.nmt);
+    if (best_positions_out && D.s.best_n > 0) {
+        CK(cudaMemcpyAsync(best_positions_out, C.best_pos, sizeof(double) * 3 * D.s.best_n, cudaMemcpyDeviceToHost, e->stream), "gcmc download best");
+        CK(cudaStreamSynchronize(e->stream), "gcmc get_state sync");
+    }
+    return MCPYB_OK;
+}
+
+int mcpyb_gcmc_run(mcpyb_gcmc* g, const int64_t* n_trials, int32_t* status_out) {
+    if (!g) return MCPYB_ERR_ARG;
+    mcpyb_engine* e = g->e;
+    if (!n_trials) return e->fail(MCPYB_ERR_ARG, "gcmc run: n_trials missing");
+    for (int c = 0; c < g->n; ++c) if (n_trials[c] < 0) return e->fail(MCPYB_ERR_ARG, "gcmc run: negative trial count");
+    cudaSetDevice(e->device);
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t");
+    CK(cudaMemcpyAsync(g->d_ntr, n_trials, sizeof(long long) * g->n, cudaMemcpyHostToDevice, e->stream), "gcmc upload trial counts");
+    CK(cudaEventRecord(g->ev0, e->stream), "event");
+    gcmc_chain_kernel<<<g->n, GC_THREADS, g->smem, e->stream>>>(g->d_chains, g->d_dyn, g->d_ntr);
+    LAUNCH_CHECK("gcmc_chain_kernel");
+    CK(cudaEventRecord(g->ev1, e->stream), "event");
+    CK(cudaMemcpyAsync(g->dyn.data(), g->d_dyn, sizeof(GcDyn) * g->n, cudaMemcpyDeviceToHost, e->stream), "gcmc download scalars");
+    CK(cudaStreamSynchronize(e->stream), "gcmc run");
+    cudaEventElapsedTime(&g->last_ms, g->ev0, g->ev1);
+    g->launches++;
+    if (status_out) for (int c = 0; c < g->n; ++c) status_out[c] = g->dyn[c].s.status;
+    return MCPYB_OK;
+}
+
+int mcpyb_gcmc_get_trace(mcpyb_gcmc* g, int chain, mcpyb_gcmc_trial* out, int64_t capacity, int64_t* n_out) {
+    if (!g) return MCPYB_ERR_ARG;
+    mcpyb_engine* e = g->e;
+    if (chain < 0 || chain >= g->n || !n_out) return e->fail(MCPYB_ERR_ARG, "gcmc get_trace: bad argument");
+    const GcChain& C = g->chains[chain];
+    long long len = g->dyn[chain].trace_len;
+    if (len > capacity) len = capacity;
+    *n_out = len;
+    if (len > 0 && out) {
+        cudaSetDevice(e->device);
+        CK(cudaMemcpyAsync(out, C.trace, sizeof(mcpyb_gcmc_trial) * len, cudaMemcpyDeviceToHost, e->stream), "gcmc download trace");
+        CK(cudaStreamSynchronize(e->stream), "gcmc get_trace sync");
+    }
+    return MCPYB_OK;
+}
+
+int mcpyb_gcmc_info(mcpyb_gcmc* g, int chain, int32_t* out6) {
+    if (!g) return MCPYB_ERR_ARG;
+    if (chain < 0 || chain >= g->n || !out6) return g->e->fail(MCPYB_ERR_ARG, "gcmc info: bad argument");
+    const GcChain& C = g->chains[chain];
+    out6[0] = C.ncell[0]; out6[1] = C.ncell[1]; out6[2] = C.ncell[2]; out6[3] = C.ccap; out6[4] = C.lay.bytes; out6[5] = C.in_smem;
+    return MCPYB_OK;
+}
+
+int mcpyb_gcmc_last_run_ms(mcpyb_gcmc* g, double* ms_out) {
+    if (!g || !ms_out) return MCPYB_ERR_ARG;
+    *ms_out = (double)g->last_ms;
+    return MCPYB_OK;
+}
+
+}  // extern "C"

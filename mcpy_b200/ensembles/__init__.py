@@ -5,7 +5,8 @@ lazily, so that ``mcpy_b200.ensembles.acceptance`` stays usable where ``mcpy`` i
 from .acceptance import Units, acceptance_probability, accept_trial, swap_exponent  # noqa: F401
 
 _LAZY = {'ShardedReplicaExchange': 'sharded_replica_exchange',
-         'ResidentLadderShard': 'resident_shard', 'LadderComm': 'ladder_comm'}
+         'ResidentLadderShard': 'resident_shard', 'LadderComm': 'ladder_comm',
+         'ResidentGCMC': 'resident_gcmc'}
 
 
 def __getattr__(name):

@@ -1,0 +1,242 @@
+"""GPU: device-resident GCMC chains (row f2, ``csrc/gcmc_chain.cuh``) against the UNMODIFIED reference loop.
+
+Two copies of the same reference ``GrandCanonicalEnsemble`` (``baseline/_ref``), same seeds: one advanced by the
+reference's own ``do_gcmc_step`` (``grand_canonical_ensemble.py:244-308``) over the CPU oracle calculator, one handed
+to ``ResidentGCMC``.  Asserted: the same move, decision and particle number at EVERY trial, dE within
+``1e-10 max(1, |dE|) + 1e-13 |E|``, and afterwards the same configuration to the bit, the same five Mersenne-Twister
+states and PCG64 state (so the next host trial draws the same numbers), the same counters and the same running minimum.
+"""
+import numpy as np
+import pytest
+
+from helpers import OracleLJCalculator, de_tol
+from mcpy_b200.utils import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def box_gcmc(cfg, symbol, mu, seed=0, n_moves=3, weights=(1, 1, 1), max_atoms=None, min_atoms=None, temperature=None):
+    from ase import Atoms
+    from mcpy.cell import Cell
+    from mcpy.ensembles import GrandCanonicalEnsemble
+    from mcpy.moves import DeletionMove, DisplacementMove, InsertionMove, MoveSelector
+    atoms = Atoms(numbers=cfg['numbers'], positions=cfg['positions'].copy(), cell=cfg['cell'], pbc=cfg['pbc'])
+    calc = OracleLJCalculator(rc=cfg['rc'], sigma=cfg['sigma'], epsilon=cfg['epsilon'])
+    cell = Cell(atoms, seed=21 + seed)
+    moves = [InsertionMove(cell, [symbol], 31 + seed, max_atoms=max_atoms),
+             DeletionMove(cell, [symbol], 32 + seed, min_atoms=min_atoms),
+             DisplacementMove([symbol], 33 + seed, max_displacement=cfg['max_displacement'])]
+    ms = MoveSelector(list(weights), moves, seed=34 + seed, n_moves=n_moves)
+    return GrandCanonicalEnsemble(atoms=atoms, cells=[cell], units_type=cfg['units'], calculator=calc, mu={symbol: mu},
+                                  species=[symbol], temperature=temperature or cfg['temperature'], move_selector=ms,
+                                  random_seed=35 + seed, traj_file=None, outfile=None)
+
+
+def small_box(n=40, L=7.0, seed=5, rc=2.5):
+    pos = synthetic.jittered_lattice(n, L, seed)
+    return dict(positions=pos, numbers=np.ones(n, np.int32), cell=np.eye(3) * L, pbc=np.ones(3, bool), rc=rc, sigma=1.0,
+                epsilon=1.0, units='LJ', temperature=2.0, max_displacement=0.3)
+
+
+def host_trace(g):
+    """(move, dE, accepted, N after) of every scored trial + the failed proposals, in order, of the reference loop."""
+    trace = []
+    ms = g.move_selector
+    inner_acc = g._acceptance_condition
+    inner_trial = ms.do_trial_move
+
+    def trial(atoms):
+        res = inner_trial(atoms)
+        a = res[0] if isinstance(res, tuple) else res
+        if a is False or a is None:
+            trace.append([ms.to_use, float('nan'), False, True, len(g.atoms), float(g.E_old)])
+        return res
+
+    def acc(dE, dN, volume, species, n):
+        ok = inner_acc(dE, dN, volume, species, n)
+        trace.append([ms.to_use, float(dE), bool(ok), False, n + (dN if ok else 0), float(g.E_old)])
+        return ok
+    ms.do_trial_move = trial
+    g._acceptance_condition = acc
+    return trace
+
+
+def gen_states(g):
+    ms = g.move_selector
+    gens = [ms.rng.random] + [m.rng.random for m in ms.move_list] + [g.rng_acceptance.random]
+    return [r.getstate() for r in gens], [c._rng.bit_generator.state for c in g.cells]
+
+
+def assert_same_chain(g_ref, g_dev, exact_positions=True):
+    assert len(g_ref.atoms) == len(g_dev.atoms) == g_ref.n_atoms == g_dev.n_atoms
+    if exact_positions:
+        assert np.array_equal(g_ref.atoms.positions, g_dev.atoms.positions)
+    else:
+        assert np.allclose(g_ref.atoms.positions, g_dev.atoms.positions, rtol=0, atol=1e-9)
+    assert np.array_equal(g_ref.atoms.numbers, g_dev.atoms.numbers)
+    assert gen_states(g_ref) == gen_states(g_dev)
+    a, b = g_ref.move_selector, g_dev.move_selector
+    for name in ('move_counter', 'move_acceptance', 'move_failed_counter', 'move_counter_total',
+                 'move_acceptance_total', 'move_failed_counter_total'):
+        assert getattr(a, name) == getattr(b, name), name
+    assert a.to_use == b.to_use
+    assert abs(g_ref.E_old - g_dev.E_old) <= 1e-9 * max(1.0, abs(g_ref.E_old))
+
+
+def assert_same_trace(ref, dev):
+    assert len(ref) == len(dev), (len(ref), len(dev))
+    for k, (r, d) in enumerate(zip(ref, dev)):
+        failed = bool(d['flags'] & 2)
+        assert (r[0], r[2], r[3], r[4]) == (int(d['move']), bool(d['flags'] & 1), failed, int(d['n_atoms'])), \
+            f'trial {k}: reference {r} vs device {d}'
+        if not failed:
+            assert abs(r[1] - d['dE']) <= de_tol(r[1], r[5]), f'trial {k}: dE {r[1]!r} vs {d["dE"]!r}'
+
+
+def run_pair(make, steps, **kw):
+    from mcpy_b200.ensembles import ResidentGCMC
+    g_ref, g_dev = make(), make()
+    trace = host_trace(g_ref)
+    for _ in range(steps):
+        g_ref.do_gcmc_step()
+    n_trials = steps * g_dev.move_selector.n_moves
+    cfg = kw.pop('cfg')
+    rg = ResidentGCMC(g_dev, lj=(cfg['epsilon'], cfg['sigma'], cfg['rc']), trace=n_trials, **kw)
+    rg.run_trials(n_trials)
+    assert_same_trace(trace, rg.traces[0])
+    assert_same_chain(g_ref, g_dev)
+    return g_ref, g_dev, rg, trace
+
+
+def test_small_box_every_trial_and_the_state_handed_back():
+    cfg = small_box()
+    g_ref, g_dev, rg, trace = run_pair(lambda: box_gcmc(cfg, 'H', -2.5), 400, cfg=cfg)
+    accepted = sum(t[2] for t in trace)
+    kinds = {t[0] for t in trace if t[2]}
+    assert accepted > 100 and kinds == {0, 1, 2}, (accepted, kinds)          # all three moves were accepted
+    assert rg.info()['in_shared_memory']
+    # the running minimum
+    assert g_dev._best_score == pytest.approx(g_ref._best_score, rel=1e-10, abs=1e-10)
+    assert len(g_dev._best_atoms) == len(g_ref._best_atoms)
+    assert np.array_equal(g_dev._best_atoms.positions, g_ref._best_atoms.positions)
+
+
+def test_c1_argon():
+    cfg = synthetic.s1_argon()
+    run_pair(lambda: box_gcmc(cfg, 'Ar', -0.085), 50, cfg=cfg)
+
+
+def test_c2_lj_2000_attractive_and_repulsive():
+    for rc in (3.0, 2.0 ** (1.0 / 6.0)):
+        cfg = synthetic.s2_lj(rc=rc)
+        g_ref, g_dev, rg, trace = run_pair(lambda: box_gcmc(cfg, 'H', -1.0, n_moves=4), 40, cfg=cfg)
+        assert sum(t[2] for t in trace) > 10
+
+
+def test_device_and_host_blocks_alternate_on_one_chain():
+    """device block, the reference's own loop, device block == the reference's loop alone."""
+    from mcpy_b200.ensembles import ResidentGCMC
+    cfg = small_box(seed=9)
+    g_ref, g_dev = box_gcmc(cfg, 'H', -2.0, seed=3), box_gcmc(cfg, 'H', -2.0, seed=3)
+    for _ in range(90):
+        g_ref.do_gcmc_step()
+    rg = ResidentGCMC(g_dev, lj=(cfg['epsilon'], cfg['sigma'], cfg['rc']))
+    rg.run_trials(30 * 3)
+    for _ in range(30):
+        g_dev.do_gcmc_step()
+    rg.run_trials(30 * 3)
+    assert_same_chain(g_ref, g_dev)
+
+
+def test_many_chains_one_launch():
+    from mcpy_b200.ensembles import ResidentGCMC
+    cfg = small_box(seed=11)
+    mus = [-3.0, -2.5, -2.0, -1.5, -1.0, -0.5]
+    refs = [box_gcmc(cfg, 'H', mu, seed=10 * k) for k, mu in enumerate(mus)]
+    devs = [box_gcmc(cfg, 'H', mu, seed=10 * k) for k, mu in enumerate(mus)]
+    for g in refs:
+        for _ in range(60):
+            g.do_gcmc_step()
+    rg = ResidentGCMC(devs, lj=(cfg['epsilon'], cfg['sigma'], cfg['rc']))
+    rg.run_trials(180)
+    for a, b in zip(refs, devs):
+        assert_same_chain(a, b)
+    assert len({len(g.atoms) for g in devs}) > 1
+
+
+def test_growth_limits_and_an_emptied_box():
+    from mcpy_b200.ensembles import ResidentGCMC
+    # high mu: the box fills up, the chain stops at its capacities, is rebuilt larger and carries on
+    cfg = small_box(n=20, seed=13)
+    mk = lambda: box_gcmc(cfg, 'H', 4.0, seed=1, weights=(3, 1, 1), n_moves=5, max_atoms=150)  # noqa: E731
+    g_ref, g_dev = mk(), mk()
+    for _ in range(120):
+        g_ref.do_gcmc_step()
+    rg = ResidentGCMC(g_dev, lj=(cfg['epsilon'], cfg['sigma'], cfg['rc']), atom_capacity=32, cell_capacity=4)
+    rg.run_trials(600)
+    assert_same_chain(g_ref, g_dev)
+    assert len(g_dev.atoms) > 60
+    assert g_dev.move_selector.move_failed_counter_total[0] > 0 or len(g_dev.atoms) < 150
+    # very low mu: the box empties; deletions of an empty box fail, min_atoms holds; no displacement move in the list
+    from mcpy.cell import Cell
+    from mcpy.ensembles import GrandCanonicalEnsemble
+    from mcpy.moves import DeletionMove, InsertionMove, MoveSelector
+    from ase import Atoms
+
+    def emptied(min_atoms):
+        c = small_box(n=6, seed=17)
+        atoms = Atoms(numbers=c['numbers'], positions=c['positions'].copy(), cell=c['cell'], pbc=c['pbc'])
+        cell = Cell(atoms, seed=2)
+        ms = MoveSelector([1, 3], [InsertionMove(cell, ['H'], 3), DeletionMove(cell, ['H'], 4, min_atoms=min_atoms)],
+                          seed=5, n_moves=2)
+        return GrandCanonicalEnsemble(atoms=atoms, cells=[cell], units_type='LJ', calculator=OracleLJCalculator(rc=2.5),
+                                      mu={'H': -12.0}, species=['H'], temperature=1.0, move_selector=ms, random_seed=6,
+                                      traj_file=None, outfile=None)
+    for min_atoms in (None, 2):
+        g_ref, g_dev = emptied(min_atoms), emptied(min_atoms)
+        for _ in range(60):
+            g_ref.do_gcmc_step()
+        ResidentGCMC(g_dev, lj=(1.0, 1.0, 2.5)).run_trials(120)
+        assert_same_chain(g_ref, g_dev)
+        assert len(g_dev.atoms) == (0 if min_atoms is None else 2)
+        assert g_dev.move_selector.move_failed_counter_total[1] > 0
+
+
+def test_run_writes_the_same_files_as_the_reference(tmp_path):
+    """``ResidentGCMC.run(steps)`` against ``gcmc.run(steps)``: outfile rows and trajectory frames."""
+    from mcpy_b200.ensembles import ResidentGCMC
+    cfg = small_box(seed=19)
+
+    def make(tag):
+        g = box_gcmc(cfg, 'H', -2.0, seed=7)
+        g._outfile, g._traj_file = str(tmp_path / f'{tag}.out'), str(tmp_path / f'{tag}.xyz')
+        g._outfile_write_interval, g._trajectory_write_interval = 5, 10
+        return g
+    g_ref, g_dev = make('ref'), make('dev')
+    g_ref.run(40)
+    ResidentGCMC(g_dev, lj=(cfg['epsilon'], cfg['sigma'], cfg['rc'])).run(40)
+    assert_same_chain(g_ref, g_dev)
+    rows_ref = [ln.split()[:2] for ln in open(tmp_path / 'ref.out') if ln[:1].isdigit()]
+    rows_dev = [ln.split()[:2] for ln in open(tmp_path / 'dev.out') if ln[:1].isdigit()]
+    assert rows_ref == rows_dev and len(rows_ref) >= 9                       # step, N per row
+    xyz_ref = [ln for ln in open(tmp_path / 'ref.xyz') if not ln.startswith('energy=')]
+    xyz_dev = [ln for ln in open(tmp_path / 'dev.xyz') if not ln.startswith('energy=')]
+    assert xyz_ref == xyz_dev                                                # positions print to the last digit
+
+
+def test_out_of_scope_chains_are_refused():
+    from mcpy_b200.ensembles import ResidentGCMC
+    from mcpy_b200.ensembles.resident_gcmc import supports
+    cfg = small_box()
+    g = box_gcmc(cfg, 'H', -2.0)
+    assert supports(g, lj=(1.0, 1.0, 2.5)) is None
+    assert 'exceed 2 rc' in supports(g, lj=(1.0, 1.0, 3.6))
+    g.atoms.pbc = [True, True, False]
+    assert 'periodic' in supports(g, lj=(1.0, 1.0, 2.5))
+    g = box_gcmc(cfg, 'H', -2.0)
+    g.move_selector.move_list[0].min_insert = 0.5
+    with pytest.raises(ValueError, match='min_insert'):
+        ResidentGCMC(g, lj=(1.0, 1.0, 2.5))
+    g = box_gcmc(cfg, 'H', -2.0)
+    with pytest.raises(ValueError, match='Lennard-Jones parameters'):
+        ResidentGCMC(g)
