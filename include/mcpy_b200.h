@@ -352,9 +352,20 @@ int mcpyb_gcmc_get_state(mcpyb_gcmc* g, int chain, double* positions_out, mcpyb_
 /* Every chain advances by up to n_trials[c] trials in ONE launch (grid = chains) and the call returns when the
  * launch has finished; a chain that stops early says why in its status and how far it got in trials_done.   */
 int mcpyb_gcmc_run(mcpyb_gcmc* g, const int64_t* n_trials, int32_t* status_out);
+/* scalars of a chain as of the end of the last mcpyb_gcmc_run / set_state / swap (host copy, no device traffic) */
+int mcpyb_gcmc_get_scalars(mcpyb_gcmc* g, int chain, mcpyb_gcmc_scalars* s_out);
+/* BatchedReplicaExchange._swap_states (batched_replica_exchange.py:401-410) between two chains of one set, on the
+ * device: configuration, energy and particle number change slots; generators, counters, the running minimum,
+ * temperature and chemical potential stay.  MCPYB_ERR_CAPACITY when the chains' boxes or storage layouts differ. */
+int mcpyb_gcmc_swap_configurations(mcpyb_gcmc* g, int i, int j);
 int mcpyb_gcmc_get_trace(mcpyb_gcmc* g, int chain, mcpyb_gcmc_trial* out, int64_t capacity, int64_t* n_out);
 /* cell list geometry chosen for a chain: cells per axis, slots per cell, bytes of state, 1 if it lives in shared memory */
 int mcpyb_gcmc_info(mcpyb_gcmc* g, int chain, int32_t* out6);
+/* out4[0..2]: SM cycles of a chain's last launch -- thread 0's serial section (draws, proposal, acceptance, commit),
+ * the whole trial loop, loop trips: what the serial Markov chain costs next to the CTA-wide row sums.
+ * out4[3]: how often the chain's running energy was replaced by a full sum over its configuration (done at the end of a
+ * launch when accepted moves x 2^-53 x max |E| since the last full sum exceeds 1e-12 max(1, |E|)).  */
+int mcpyb_gcmc_cycles(mcpyb_gcmc* g, int chain, int64_t* out4);
 /* device time of the last mcpyb_gcmc_run launch (CUDA events on the engine's stream) */
 int mcpyb_gcmc_last_run_ms(mcpyb_gcmc* g, double* ms_out);
 

@@ -31,7 +31,8 @@ SYMBOLS = [
     'mcpyb_min_dist2_host', 'mcpyb_pcg64_host_doubles', 'mcpyb_fp64_peak_tflops', 'mcpyb_stage_timing', 'mcpyb_launch_count',
     'mcpyb_resident_chain', 'mcpyb_set_precision', 'mcpyb_copy_segments_dev',
     'mcpyb_gcmc_create', 'mcpyb_gcmc_destroy', 'mcpyb_gcmc_set_state', 'mcpyb_gcmc_get_state', 'mcpyb_gcmc_run',
-    'mcpyb_gcmc_get_trace', 'mcpyb_gcmc_info', 'mcpyb_gcmc_last_run_ms',
+    'mcpyb_gcmc_get_trace', 'mcpyb_gcmc_info', 'mcpyb_gcmc_last_run_ms', 'mcpyb_gcmc_get_scalars',
+    'mcpyb_gcmc_swap_configurations', 'mcpyb_gcmc_cycles',
 ]
 
 GCMC_MAX_MOVES = 8          # MCPYB_GCMC_MAX_MOVES
@@ -144,6 +145,9 @@ def load():
     lib.mcpyb_gcmc_set_state.argtypes = [_p, C.c_int, _p, C.POINTER(GcmcScalars), _p]
     lib.mcpyb_gcmc_get_state.argtypes = [_p, C.c_int, _p, C.POINTER(GcmcScalars), _p, _p]
     lib.mcpyb_gcmc_run.argtypes = [_p, _p, _p]
+    lib.mcpyb_gcmc_get_scalars.argtypes = [_p, C.c_int, C.POINTER(GcmcScalars)]
+    lib.mcpyb_gcmc_swap_configurations.argtypes = [_p, C.c_int, C.c_int]
+    lib.mcpyb_gcmc_cycles.argtypes = [_p, C.c_int, _i64p]
     lib.mcpyb_gcmc_get_trace.argtypes = [_p, C.c_int, _p, C.c_int64, _i64p]
     lib.mcpyb_gcmc_info.argtypes = [_p, C.c_int, _p]
     lib.mcpyb_gcmc_last_run_ms.argtypes = [_p, _f64p]

@@ -32,7 +32,7 @@
 #define GC_SERIAL_WRAP 6          // unstable lists up to this length are wrapped by thread 0 itself
 
 struct GcLayout {                 // byte offsets of the arrays inside a chain's state block
-    int px, py, pz, mt, order, cell_of, unstable, uflag, cell_cnt, cell_slots, bytes;
+    int px, py, pz, mt, mt2, order, cell_of, unstable, uflag, cell_cnt, cell_slots, bytes;
 };
 
 struct GcChain {                  // read-only description of one chain
@@ -52,6 +52,10 @@ struct GcChain {                  // read-only description of one chain
 struct GcDyn {                    // read-write scalars of one chain
     mcpyb_gcmc_scalars s;
     long long trace_len;
+    long long cyc_serial, cyc_total, rounds;    // of the last launch: thread 0's serial section, the whole loop, loop trips
+    long long acc_since_resync;                 // accepted moves added onto E since it was last summed from scratch
+    long long resyncs;
+    double e_scale;                             // max |E| since then: bounds the rounding carried by E
     int n_unstable;
     int pad;
 };
@@ -64,6 +68,7 @@ static inline GcLayout gc_layout(int acap, int ncells, int ccap, int nmt) {
     l.py = o; o += gc_align16(8 * acap);
     l.pz = o; o += gc_align16(8 * acap);
     l.mt = o; o += gc_align16(4 * MCPYB_GCMC_MT_WORDS * nmt);
+    l.mt2 = o; o += gc_align16(4 * 624 * nmt);           // scratch: the NEXT state of every stream, computed ahead
     l.order = o; o += gc_align16(2 * acap);
     l.cell_of = o; o += gc_align16(2 * acap);
     l.unstable = o; o += gc_align16(2 * acap);
@@ -75,42 +80,109 @@ static inline GcLayout gc_layout(int acap, int ncells, int ccap, int nmt) {
 }
 
 // ---- MT19937 as CPython drives it --------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t gc_mt_next(uint32_t* s) {
-    uint32_t i = s[624];
-    if (i >= 624) {
-        // genrand_uint32's regeneration, in place: s[k + 1] is carried in a register, s[k + 397 - 624] is already new
-        // for k >= 227, and k = 623 pairs the old s[623] with the NEW s[0]
-        uint32_t cur = s[0];
-        for (int k = 0; k < 623; ++k) {
-            const int km = (k + 397 >= 624) ? k + 397 - 624 : k + 397;
-            const uint32_t nxt = s[k + 1];
-            const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
-            s[k] = s[km] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            cur = nxt;
-        }
-        const uint32_t y = (cur & 0x80000000u) | (s[0] & 0x7fffffffu);
-        s[623] = s[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-        i = 0;
-    }
-    uint32_t y = s[i];
-    s[624] = i + 1;
+// A stream's state is 624 words + the position (random.Random.getstate()[1]).  During a launch the position lives
+// in s_mt_idx, the words in one of two buffers: the canonical one (lay.mt) or the scratch (lay.mt2).  The NEXT
+// state is a function of the current words alone, so the CTA computes it ahead, out of place, in three parallel
+// phases (gc_mt_refill); when thread 0 has used up a state it just flips the buffers.  Without a precomputed state
+// (two states used up within one trial) thread 0 regenerates in place, serially, as genrand_uint32 does.
+#define GC_MAX_STREAMS (MCPYB_GCMC_MAX_MOVES + 2)
+struct GcMt {
+    uint32_t* a;                  // lay.mt : [stream][625]
+    uint32_t* b;                  // lay.mt2: [stream][624]
+    int idx[GC_MAX_STREAMS];
+    unsigned char flip[GC_MAX_STREAMS];      // 1: the current state lives in b
+    unsigned char ready[GC_MAX_STREAMS];     // 1: the next state is complete in the other buffer
+};
+__device__ __forceinline__ uint32_t* gc_mt_cur(GcMt& M, int k) { return M.flip[k] ? M.b + k * 624 : M.a + k * MCPYB_GCMC_MT_WORDS; }
+__device__ __forceinline__ uint32_t* gc_mt_other(GcMt& M, int k) { return M.flip[k] ? M.a + k * MCPYB_GCMC_MT_WORDS : M.b + k * 624; }
+__device__ __forceinline__ uint32_t gc_mt_twist(uint32_t cur, uint32_t nxt) {
+    const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t gc_mt_temper(uint32_t y) {
     y ^= y >> 11;
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
     y ^= y >> 18;
     return y;
 }
-// random.random(): (a * 2^26 + b) / 2^53 with a = 27 bits, b = 26 bits (exact in fp64)
-__device__ __forceinline__ double gc_mt_random(uint32_t* s) {
-    const uint32_t a = gc_mt_next(s) >> 5, b = gc_mt_next(s) >> 6;
-    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+// all threads: next state of stream k, current buffer -> other buffer (new[j] = old[j+397] ^ twist(old[j], old[j+1]) for
+// j < 227, new[j] = new[j-227] ^ twist(old[j], old[j+1]) after that, the last word pairs old[623] with new[0])
+__device__ __forceinline__ void gc_mt_refill(GcMt& M, int k, int tid) {
+    const uint32_t* o = gc_mt_cur(M, k);
+    uint32_t* w = gc_mt_other(M, k);
+    if (tid < 227) w[tid] = o[tid + 397] ^ gc_mt_twist(o[tid], o[tid + 1]);
+    __syncthreads();
+    if (tid < 227) w[tid + 227] = w[tid] ^ gc_mt_twist(o[tid + 227], o[tid + 228]);
+    __syncthreads();
+    if (tid < 169) w[tid + 454] = w[tid + 227] ^ gc_mt_twist(o[tid + 454], o[tid + 455]);
+    if (tid == 169) w[623] = w[396] ^ gc_mt_twist(o[623], w[0]);
+    __syncthreads();
 }
-// Random._randbelow_with_getrandbits(n), n >= 1: k = n.bit_length(); r = getrandbits(k) until r < n
-__device__ __forceinline__ uint32_t gc_mt_randbelow(uint32_t* s, uint32_t n) {
-    const int k = 32 - __clz(n);
-    uint32_t r = gc_mt_next(s) >> (32 - k);
-    while (r >= n) r = gc_mt_next(s) >> (32 - k);
-    return r;
+// thread 0: the state of stream k is used up
+__device__ __noinline__ void gc_mt_advance(GcMt& M, int k) {
+    if (M.ready[k]) { M.flip[k] ^= 1; M.ready[k] = 0; M.idx[k] = 0; return; }
+    uint32_t* s = gc_mt_cur(M, k);
+    uint32_t cur = s[0];
+    for (int j = 0; j < 623; ++j) {
+        const int jm = (j + 397 >= 624) ? j + 397 - 624 : j + 397;
+        const uint32_t nxt = s[j + 1];
+        s[j] = s[jm] ^ gc_mt_twist(cur, nxt);
+        cur = nxt;
+    }
+    s[623] = s[396] ^ gc_mt_twist(cur, s[0]);
+    M.idx[k] = 0;
+}
+// K consecutive outputs of stream k; the common case loads and tempers them side by side
+template <int K>
+__device__ __forceinline__ void gc_mt_take(GcMt& M, int k, uint32_t (&out)[K]) {
+    int i = M.idx[k];
+    if (i + K <= 624) {
+        const uint32_t* s = gc_mt_cur(M, k) + i;
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = s[j];
+        M.idx[k] = i + K;
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = gc_mt_temper(out[j]);
+        return;
+    }
+    for (int j = 0; j < K; ++j) {
+        if (M.idx[k] >= 624) gc_mt_advance(M, k);
+        out[j] = gc_mt_temper(gc_mt_cur(M, k)[M.idx[k]]);
+        M.idx[k] += 1;
+    }
+}
+// random.random(): (a * 2^26 + b) / 2^53 with a = 27 bits, b = 26 bits (exact in fp64)
+__device__ __forceinline__ double gc_mt_double(uint32_t w0, uint32_t w1) {
+    return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double gc_mt_random(GcMt& M, int k) {
+    uint32_t w[2];
+    gc_mt_take<2>(M, k, w);
+    return gc_mt_double(w[0], w[1]);
+}
+// Random._randbelow_with_getrandbits(n), n >= 1: k = n.bit_length(); r = getrandbits(k) until r < n.  Four words are
+// looked at side by side; only those up to the accepted one are consumed.
+__device__ __forceinline__ uint32_t gc_mt_randbelow(GcMt& M, int k, uint32_t n) {
+    const int sh = __clz(n);                     // 32 - bit_length
+    while (true) {
+        const int i = M.idx[k];
+        if (i + 4 <= 624) {
+            const uint32_t* s = gc_mt_cur(M, k) + i;
+            const uint32_t r0 = gc_mt_temper(s[0]) >> sh, r1 = gc_mt_temper(s[1]) >> sh,
+                           r2 = gc_mt_temper(s[2]) >> sh, r3 = gc_mt_temper(s[3]) >> sh;
+            if (r0 < n) { M.idx[k] = i + 1; return r0; }
+            if (r1 < n) { M.idx[k] = i + 2; return r1; }
+            if (r2 < n) { M.idx[k] = i + 3; return r2; }
+            M.idx[k] = i + 4;
+            if (r3 < n) return r3;
+        } else {
+            uint32_t w[1];
+            gc_mt_take<1>(M, k, w);
+            const uint32_t r = w[0] >> sh;
+            if (r < n) return r;
+        }
+    }
 }
 
 // ase.geometry.wrap_positions for a diagonal cell and a periodic axis (center 0.5, eps 1e-7), operation for operation:
@@ -142,6 +214,8 @@ struct GcTrial {                  // thread 0 -> CTA
     int freed_slot;
     int n;                        // atoms after the commit (for the best copy)
     int n_unstable;
+    int refill;                   // bit k: the CTA computes the next state of Mersenne-Twister stream k in this round
+    int resync;
 };
 
 #define GC_PAR_SHIFT 1
@@ -155,6 +229,9 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
     __shared__ double s_part[GC_THREADS / 32];
     __shared__ unsigned long long s_pcg[MCPYB_GCMC_MAX_MOVES][4];
     __shared__ long long s_cnt[3][MCPYB_GCMC_MAX_MOVES];      // attempts, accepted, failed
+    __shared__ GcMt M;
+    __shared__ mcpyb_gcmc_desc s_d;                           // the chain's description, read by thread 0 all the time
+    __shared__ signed char s_st[125][4];                      // stencil cell -> offsets along the three axes
 
     const GcChain& C = chains[blockIdx.x];
     GcDyn& D = dyn[blockIdx.x];
@@ -170,6 +247,7 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
     double* py = reinterpret_cast<double*>(base + lay.py);
     double* pz = reinterpret_cast<double*>(base + lay.pz);
     uint32_t* mt = reinterpret_cast<uint32_t*>(base + lay.mt);
+    uint32_t* mt2 = reinterpret_cast<uint32_t*>(base + lay.mt2);
     unsigned short* order = reinterpret_cast<unsigned short*>(base + lay.order);
     unsigned short* cell_of = reinterpret_cast<unsigned short*>(base + lay.cell_of);
     unsigned short* unstable = reinterpret_cast<unsigned short*>(base + lay.unstable);
@@ -177,6 +255,8 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
     unsigned short* cell_cnt = reinterpret_cast<unsigned short*>(base + lay.cell_cnt);
     unsigned short* cell_slots = reinterpret_cast<unsigned short*>(base + lay.cell_slots);
 
+    for (int i = tid; i < (int)(sizeof(mcpyb_gcmc_desc) / 4); i += GC_THREADS)
+        reinterpret_cast<uint32_t*>(&s_d)[i] = reinterpret_cast<const uint32_t*>(&C.d)[i];
     const double L0 = C.d.box[0], L1 = C.d.box[1], L2 = C.d.box[2];
     const double i0 = C.inv_box[0], i1 = C.inv_box[1], i2 = C.inv_box[2];
     const int nc0 = C.ncell[0], nc1 = C.ncell[1], nc2 = C.ncell[2];
@@ -185,11 +265,18 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
     const int ccap = C.ccap;
     const LJParams lj = C.lj;
     const int nm = C.d.n_move_types;
+    for (int sc = tid; sc < ns; sc += GC_THREADS) {
+        s_st[sc][2] = (signed char)(sc % sp2);
+        s_st[sc][1] = (signed char)((sc / sp2) % sp1);
+        s_st[sc][0] = (signed char)(sc / (sp2 * sp1));
+    }
+    __syncthreads();                                        // the state block is in shared memory: thread 0 reads it below
 
     // thread 0's chain state
     int n = 0, n_unst = 0, pending = 0, cur_move = 0, cur_kind = 0, cur_index = 0, have_rows = 0, drew = 0;
     long long t_done = 0, t_goal = 0, trace_len = 0;
-    double E = 0.0, best_score = 0.0, best_E = 0.0;
+    double E = 0.0, best_score = 0.0, best_E = 0.0, e_scale = 0.0;
+    long long acc_since = 0, resyncs = 0;
     int best_n = -1;
     if (tid == 0) {
         n = D.s.n_atoms; n_unst = D.n_unstable; E = D.s.energy; best_score = D.s.best_score; best_E = D.s.best_energy;
@@ -197,15 +284,25 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
         for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k)
             for (int j = 0; j < 4; ++j) s_pcg[k][j] = D.s.pcg[k][j];
         for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k) { s_cnt[0][k] = D.s.attempts[k]; s_cnt[1][k] = D.s.accepted[k]; s_cnt[2][k] = D.s.failed[k]; }
-        T.done = 0; T.par = 0; T.nsites = 0;
+        T.done = 0; T.par = 0; T.nsites = 0; T.refill = 0; T.resync = 0;
         D.s.status = MCPYB_GCMC_DONE;
+        M.a = mt; M.b = mt2;
+        for (int k = 0; k < nm + 2; ++k) { M.idx[k] = (int)mt[k * MCPYB_GCMC_MT_WORDS + 624]; M.flip[k] = 0; M.ready[k] = 0; }
+        e_scale = fmax(D.e_scale, fabs(E)); acc_since = D.acc_since_resync; resyncs = D.resyncs;
     }
-    __syncthreads();
+    __syncthreads();                                        // (the state block, s_d and the stencil table are in place)
 
+    long long cyc_serial = 0, rounds = 0;
+    const long long cyc_begin = clock64();
     while (true) {
         if (tid == 0) {
+            const long long cyc_in = clock64();
             // ---------------- the Markov chain proper (serial) ----------------
             bool proposing = true;
+            if (T.refill) {                                 // the CTA completed these next states in the last parallel section
+                for (int k = 0; k < nm + 2; ++k) if (T.refill >> k & 1) M.ready[k] = 1;
+                T.refill = 0;
+            }
             if (T.par) { T.par = 0; }                       // the parallel commit of the last trial is done
             else if (have_rows) {
                 have_rows = 0;
@@ -214,21 +311,21 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                 // _acceptance_condition; n is the pre-move atom count (self.n_atoms)
                 bool acc;
                 drew = 0;
-                uint32_t* mt_acc = mt + (nm + 1) * MCPYB_GCMC_MT_WORDS;
+                const int mt_acc = nm + 1;
                 if (cur_kind == MCPYB_GCMC_DISPLACE) {
                     if (dE <= 0.0) acc = true;
-                    else { const double p = exp(__dmul_rn(-dE, C.d.beta)); drew = 1; acc = p > gc_mt_random(mt_acc); }
+                    else { const double p = exp(__dmul_rn(-dE, s_d.beta)); drew = 1; acc = p > gc_mt_random(M, mt_acc); }
                 } else {
                     double p;
                     if (cur_kind == MCPYB_GCMC_INSERT) {
-                        const double db = C.d.move_volume[cur_move] / __dmul_rn((double)(n + 1), C.d.lambda3);
-                        p = __dmul_rn(db, exp(__dmul_rn(-C.d.beta, __dsub_rn(dE, C.d.mu))));
+                        const double db = s_d.move_volume[cur_move] / __dmul_rn((double)(n + 1), s_d.lambda3);
+                        p = __dmul_rn(db, exp(__dmul_rn(-s_d.beta, __dsub_rn(dE, s_d.mu))));
                     } else {
-                        const double db = __dmul_rn(C.d.lambda3, (double)n) / C.d.move_volume[cur_move];
-                        p = __dmul_rn(db, exp(__dmul_rn(-C.d.beta, __dadd_rn(dE, C.d.mu))));
+                        const double db = __dmul_rn(s_d.lambda3, (double)n) / s_d.move_volume[cur_move];
+                        p = __dmul_rn(db, exp(__dmul_rn(-s_d.beta, __dadd_rn(dE, s_d.mu))));
                     }
                     if (p > 1.0) acc = true;
-                    else { drew = 1; acc = p > gc_mt_random(mt_acc); }
+                    else { drew = 1; acc = p > gc_mt_random(M, mt_acc); }
                 }
                 int par = 0;
                 if (acc) {
@@ -284,6 +381,7 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                     }
                     if (moved != GC_NONE && !uflag[moved]) { uflag[moved] = 1; unstable[n_unst++] = (unsigned short)moved; }
                     E += dE;
+                    e_scale = fmax(e_scale, fabs(E)); ++acc_since;
                     // atoms.wrap(): only atoms whose last wrap still changed a bit can change again
                     if (n_unst <= GC_SERIAL_WRAP) {
                         int keep = 0;
@@ -300,7 +398,7 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                         T.n_unstable = n_unst;
                     }
                     // _record_minimum: score = E - mu * N
-                    const double score = __dsub_rn(E, __dmul_rn(C.d.mu, (double)n));
+                    const double score = __dsub_rn(E, __dmul_rn(s_d.mu, (double)n));
                     if (score < best_score) { best_score = score; best_E = E; best_n = n; par |= GC_PAR_BEST; }
                     T.n = n;
                 }
@@ -318,21 +416,21 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                 if (t_done >= t_goal) { T.done = 1; break; }
                 if (C.trace && trace_len >= C.trace_cap) { D.s.status = MCPYB_GCMC_TRACE_FULL; T.done = 1; break; }
                 // MoveSelector.__get_index__: searchsorted(rho, u * rho_total, side='right'), clamped
-                const double v = __dmul_rn(gc_mt_random(mt), C.d.move_cum_weight[nm - 1]);
+                const double v = __dmul_rn(gc_mt_random(M, 0), s_d.move_cum_weight[nm - 1]);
                 int mv = 0;
-                while (mv < nm && C.d.move_cum_weight[mv] <= v) ++mv;
+                while (mv < nm && s_d.move_cum_weight[mv] <= v) ++mv;
                 if (mv >= nm) mv = nm - 1;
-                cur_move = mv; cur_kind = C.d.move_kind[mv];
-                uint32_t* mt_mv = mt + (1 + mv) * MCPYB_GCMC_MT_WORDS;
+                cur_move = mv; cur_kind = s_d.move_kind[mv];
+                const int mt_mv = 1 + mv;
                 bool failed = false;
                 if (cur_kind == MCPYB_GCMC_DISPLACE && n == 0) { D.s.status = MCPYB_GCMC_EMPTY_DISPLACE; T.done = 1; break; }
                 s_cnt[0][mv] += 1;
                 if (cur_kind == MCPYB_GCMC_INSERT) {
-                    gc_mt_randbelow(mt_mv, 1u);                                   // rng.random.choice(self.species)
+                    gc_mt_randbelow(M, mt_mv, 1u);                                   // rng.random.choice(self.species)
                     cur_index = n;
-                    if (C.d.move_limit[mv] >= 0 && n >= C.d.move_limit[mv]) failed = true;
+                    if (s_d.move_limit[mv] >= 0 && n >= s_d.move_limit[mv]) failed = true;
                     else {
-                        unsigned long long* ps = s_pcg[C.d.move_pcg[mv]];
+                        unsigned long long* ps = s_pcg[s_d.move_pcg[mv]];
                         u128 st = ((u128)ps[0] << 64) | ps[1];
                         const u128 inc = ((u128)ps[2] << 64) | ps[3];
                         const double u0 = pcg_next_double(st, inc), u1 = pcg_next_double(st, inc), u2 = pcg_next_double(st, inc);
@@ -341,26 +439,28 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                         T.sign[0] = 1.0; T.nsites = 1; T.excl = GC_NONE;
                     }
                 } else if (cur_kind == MCPYB_GCMC_DELETE) {
-                    gc_mt_randbelow(mt_mv, 1u);
+                    gc_mt_randbelow(M, mt_mv, 1u);
                     cur_index = -1;
-                    if ((C.d.move_limit[mv] >= 0 && n <= C.d.move_limit[mv]) || n == 0) failed = true;
+                    if ((s_d.move_limit[mv] >= 0 && n <= s_d.move_limit[mv]) || n == 0) failed = true;
                     else {
-                        cur_index = (int)gc_mt_randbelow(mt_mv, (uint32_t)n);     // rng.random.choice(indices_of_species)
+                        cur_index = (int)gc_mt_randbelow(M, mt_mv, (uint32_t)n);     // rng.random.choice(indices_of_species)
                         const int slot = order[cur_index];
                         T.sx[0] = px[slot]; T.sy[0] = py[slot]; T.sz[0] = pz[slot];
                         T.sign[0] = -1.0; T.nsites = 1; T.excl = slot;
                     }
                 } else {
-                    cur_index = (int)gc_mt_randbelow(mt_mv, (uint32_t)n);         // rng.random.choice(to_move)
+                    cur_index = (int)gc_mt_randbelow(M, mt_mv, (uint32_t)n);         // rng.random.choice(to_move)
                     const int slot = order[cur_index];
                     double rx, ry, rz, rsq;
                     do {
-                        rx = __dsub_rn(__dmul_rn(2.0, gc_mt_random(mt_mv)), 1.0);
-                        ry = __dsub_rn(__dmul_rn(2.0, gc_mt_random(mt_mv)), 1.0);
-                        rz = __dsub_rn(__dmul_rn(2.0, gc_mt_random(mt_mv)), 1.0);
+                        uint32_t w[6];
+                        gc_mt_take<6>(M, mt_mv, w);
+                        rx = __dsub_rn(__dmul_rn(2.0, gc_mt_double(w[0], w[1])), 1.0);
+                        ry = __dsub_rn(__dmul_rn(2.0, gc_mt_double(w[2], w[3])), 1.0);
+                        rz = __dsub_rn(__dmul_rn(2.0, gc_mt_double(w[4], w[5])), 1.0);
                         rsq = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
                     } while (rsq > 1.0);
-                    const double md = C.d.move_max_displacement[mv];
+                    const double md = s_d.move_max_displacement[mv];
                     T.sx[0] = px[slot]; T.sy[0] = py[slot]; T.sz[0] = pz[slot];
                     T.sx[1] = __dadd_rn(T.sx[0], __dmul_rn(rx, md));
                     T.sy[1] = __dadd_rn(T.sy[0], __dmul_rn(ry, md));
@@ -385,9 +485,20 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                 have_rows = 1;
                 break;
             }
+            if (!T.done) {
+                int need = 0;
+                for (int k = 0; k < nm + 2; ++k) if (!M.ready[k]) need |= 1 << k;
+                T.refill = need;
+            }
+            cyc_serial += clock64() - cyc_in;
+            ++rounds;
         }
         __syncthreads();
         if (T.done) break;
+        if (T.refill) {                                     // next Mersenne-Twister states, computed ahead by the whole CTA
+            const int need = T.refill;
+            for (int k = 0; k < nm + 2; ++k) if (need >> k & 1) gc_mt_refill(M, k, tid);
+        }
         if (T.par) {
             const int par = T.par;
             if (par & GC_PAR_SHIFT) {
@@ -436,10 +547,8 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
             const int excl = T.excl;
             for (int task = tid >> 2; task < ntasks; task += GC_QUADS) {
                 const int site = task >= ns ? 1 : 0;
-                int sc = task - site * ns;
-                const int a2 = sc % sp2; sc /= sp2;
-                const int a1 = sc % sp1;
-                const int a0 = sc / sp1;
+                const int sc = task - site * ns;
+                const int a0 = s_st[sc][0], a1 = s_st[sc][1], a2 = s_st[sc][2];
                 int c0 = a0, c1 = a1, c2 = a2;
                 if (sp0 != nc0) { c0 = T.home[site][0] - 2 + a0; c0 += c0 < 0 ? nc0 : 0; c0 -= c0 >= nc0 ? nc0 : 0; }
                 if (sp1 != nc1) { c1 = T.home[site][1] - 2 + a1; c1 += c1 < 0 ? nc1 : 0; c1 -= c1 >= nc1 ? nc1 : 0; }
@@ -466,10 +575,66 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
         __syncthreads();
     }
 
-    // ---------------- hand the state back ----------------
+    // ---------------- E summed from scratch when the running sum may carry too much rounding ----------------
+    // E = E_start + sum of accepted dE: every addition rounds at the size of E at that time, so a chain that came down
+    // from a large |E| (overlapping start, a hot rung) keeps an absolute error the reference's per-trial full energy
+    // does not have.  Bound: accepted moves x 2^-53 x max |E| since the last full sum.
     if (tid == 0) {
+        T.n = n;
+        T.resync = (double)acc_since * 1.2e-16 * e_scale > 1e-12 * fmax(1.0, fabs(E)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (T.resync) {
+        const int nn = T.n;
+        double acc = 0.0;
+        for (int i = tid; i < nn; i += GC_THREADS) {
+            const int slot = order[i];
+            const double sx = px[slot], sy = py[slot], sz = pz[slot];
+            int c = cell_of[slot];
+            const int h2 = c % nc2; c /= nc2;
+            const int h1 = c % nc1;
+            const int h0 = c / nc1;
+            for (int sc = 0; sc < ns; ++sc) {
+                int c0 = s_st[sc][0], c1 = s_st[sc][1], c2 = s_st[sc][2];
+                if (sp0 != nc0) { c0 += h0 - 2; c0 += c0 < 0 ? nc0 : 0; c0 -= c0 >= nc0 ? nc0 : 0; }
+                if (sp1 != nc1) { c1 += h1 - 2; c1 += c1 < 0 ? nc1 : 0; c1 -= c1 >= nc1 ? nc1 : 0; }
+                if (sp2 != nc2) { c2 += h2 - 2; c2 += c2 < 0 ? nc2 : 0; c2 -= c2 >= nc2 ? nc2 : 0; }
+                const int cell = (c0 * nc1 + c1) * nc2 + c2;
+                const int cnt = cell_cnt[cell];
+                for (int q = 0; q < cnt; ++q) {
+                    const int other = cell_slots[cell * ccap + q];
+                    if (other == slot) continue;
+                    const double x = px[other], y = py[other], z = pz[other];
+                    const double S0 = -rint((x - sx) * i0), S1 = -rint((y - sy) * i1), S2 = -rint((z - sz) * i2);
+                    const double dx = __dsub_rn(__dadd_rn(x, __dmul_rn(S0, L0)), sx);
+                    const double dy = __dsub_rn(__dadd_rn(y, __dmul_rn(S1, L1)), sy);
+                    const double dz = __dsub_rn(__dadd_rn(z, __dmul_rn(S2, L2)), sz);
+                    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    if (r2 <= lj.rc2) acc += lj_pair(lj, r2);
+                }
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s_part[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double e2 = 0.0;
+            for (int w = 0; w < GC_THREADS / 32; ++w) e2 += s_part[w];
+            E = 0.5 * e2;                                   // every pair was met from both ends
+            e_scale = fabs(E); acc_since = 0; ++resyncs;
+        }
+    }
+    // ---------------- hand the state back ----------------
+    // Mersenne-Twister streams whose current state sits in the scratch buffer go back to the canonical one
+    for (int k = 0; k < nm + 2; ++k) {
+        if (M.flip[k]) for (int i = tid; i < 624; i += GC_THREADS) mt[k * MCPYB_GCMC_MT_WORDS + i] = mt2[k * 624 + i];
+    }
+    if (tid < nm + 2) mt[tid * MCPYB_GCMC_MT_WORDS + 624] = (uint32_t)M.idx[tid];
+    if (tid == 0) {
+        D.e_scale = e_scale; D.acc_since_resync = acc_since; D.resyncs = resyncs;
         D.s.n_atoms = n; D.n_unstable = n_unst; D.s.energy = E; D.s.best_score = best_score; D.s.best_energy = best_E;
         D.s.best_n = best_n; D.s.last_move = cur_move; D.s.trials_done = t_done; D.trace_len = trace_len;
+        D.cyc_serial = cyc_serial; D.cyc_total = clock64() - cyc_begin; D.rounds = rounds;
         for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k)
             for (int j = 0; j < 4; ++j) D.s.pcg[k][j] = s_pcg[k][j];
         for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k) { D.s.attempts[k] = s_cnt[0][k]; D.s.accepted[k] = s_cnt[1][k]; D.s.failed[k] = s_cnt[2][k]; }
@@ -493,6 +658,8 @@ struct mcpyb_gcmc {
     GcChain* d_chains = nullptr;
     GcDyn* d_dyn = nullptr;
     long long* d_ntr = nullptr;
+    unsigned char* d_swap = nullptr;      // scratch of mcpyb_gcmc_swap_configurations
+    size_t swap_bytes = 0;
     size_t smem = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
@@ -586,6 +753,7 @@ void mcpyb_gcmc_destroy(mcpyb_gcmc* g) {
     if (g->d_chains) cudaFree(g->d_chains);
     if (g->d_dyn) cudaFree(g->d_dyn);
     if (g->d_ntr) cudaFree(g->d_ntr);
+    if (g->d_swap) cudaFree(g->d_swap);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     delete g;
@@ -635,6 +803,8 @@ int mcpyb_gcmc_set_state(mcpyb_gcmc* g, int chain, const double* positions, cons
     D.s.status = MCPYB_GCMC_DONE;
     D.trace_len = 0;
     D.n_unstable = n;
+    D.e_scale = fabs(s->energy);             // the caller's energy is a full sum
+    D.acc_since_resync = 0;
     CK(cudaMemcpyAsync(C.blob, blob.data(), C.lay.bytes, cudaMemcpyHostToDevice, e->stream), "gcmc upload state");
     CK(cudaMemcpyAsync(g->d_dyn + chain, &D, sizeof(GcDyn), cudaMemcpyHostToDevice, e->stream), "gcmc upload scalars");
     CK(cudaStreamSynchronize(e->stream), "gcmc set_state sync");
@@ -708,11 +878,66 @@ int mcpyb_gcmc_get_trace(mcpyb_gcmc* g, int chain, mcpyb_gcmc_trial* out, int64_
     return MCPYB_OK;
 }
 
+int mcpyb_gcmc_get_scalars(mcpyb_gcmc* g, int chain, mcpyb_gcmc_scalars* s_out) {
+    if (!g) return MCPYB_ERR_ARG;
+    if (chain < 0 || chain >= g->n || !s_out) return g->e->fail(MCPYB_ERR_ARG, "gcmc get_scalars: bad argument");
+    *s_out = g->dyn[chain].s;                 // the host copy: mcpyb_gcmc_run downloads every chain's scalars
+    return MCPYB_OK;
+}
+
+int mcpyb_gcmc_swap_configurations(mcpyb_gcmc* g, int i, int j) {
+    if (!g) return MCPYB_ERR_ARG;
+    mcpyb_engine* e = g->e;
+    if (i < 0 || j < 0 || i >= g->n || j >= g->n) return e->fail(MCPYB_ERR_ARG, "gcmc swap: no such chain");
+    if (i == j) return MCPYB_OK;
+    GcChain& A = g->chains[i];
+    GcChain& B = g->chains[j];
+    if (memcmp(&A.lay, &B.lay, sizeof(GcLayout)) != 0 || A.acap != B.acap || A.ccap != B.ccap || A.ncells != B.ncells ||
+        memcmp(A.ncell, B.ncell, sizeof A.ncell) != 0 || memcmp(A.d.box, B.d.box, sizeof A.d.box) != 0)
+        return e->fail(MCPYB_ERR_CAPACITY, "gcmc swap: chains %d and %d have different boxes or storage layouts", i, j);
+    cudaSetDevice(e->device);
+    const size_t mt_bytes = (size_t)gc_align16(4 * MCPYB_GCMC_MT_WORDS * A.nmt);
+    if (!g->d_swap || g->swap_bytes < mt_bytes) {
+        if (g->d_swap) cudaFree(g->d_swap);
+        g->d_swap = nullptr;
+        if (cudaMalloc(&g->d_swap, mt_bytes) != cudaSuccess) return e->fail(MCPYB_ERR_CUDA, "gcmc swap: cudaMalloc");
+        g->swap_bytes = mt_bytes;
+    }
+    // the state blocks change owner (the configuration, its atom order, cell lists and wrap bookkeeping go with them);
+    // the Mersenne-Twister streams stay with the slot, so they are swapped back
+    cudaStream_t st = e->stream;
+    CK(cudaMemcpyAsync(g->d_swap, A.blob + A.lay.mt, mt_bytes, cudaMemcpyDeviceToDevice, st), "gcmc swap");
+    CK(cudaMemcpyAsync(A.blob + A.lay.mt, B.blob + B.lay.mt, mt_bytes, cudaMemcpyDeviceToDevice, st), "gcmc swap");
+    CK(cudaMemcpyAsync(B.blob + B.lay.mt, g->d_swap, mt_bytes, cudaMemcpyDeviceToDevice, st), "gcmc swap");
+    std::swap(A.blob, B.blob);
+    GcDyn& DA = g->dyn[i];
+    GcDyn& DB = g->dyn[j];
+    std::swap(DA.s.energy, DB.s.energy);
+    std::swap(DA.s.n_atoms, DB.s.n_atoms);
+    std::swap(DA.n_unstable, DB.n_unstable);
+    std::swap(DA.e_scale, DB.e_scale);
+    std::swap(DA.acc_since_resync, DB.acc_since_resync);
+    CK(cudaMemcpyAsync(g->d_chains + i, &A, sizeof(GcChain), cudaMemcpyHostToDevice, st), "gcmc swap");
+    CK(cudaMemcpyAsync(g->d_chains + j, &B, sizeof(GcChain), cudaMemcpyHostToDevice, st), "gcmc swap");
+    CK(cudaMemcpyAsync(g->d_dyn + i, &DA, sizeof(GcDyn), cudaMemcpyHostToDevice, st), "gcmc swap");
+    CK(cudaMemcpyAsync(g->d_dyn + j, &DB, sizeof(GcDyn), cudaMemcpyHostToDevice, st), "gcmc swap");
+    CK(cudaStreamSynchronize(st), "gcmc swap");          // the sources are pageable host structs
+    return MCPYB_OK;
+}
+
 int mcpyb_gcmc_info(mcpyb_gcmc* g, int chain, int32_t* out6) {
     if (!g) return MCPYB_ERR_ARG;
     if (chain < 0 || chain >= g->n || !out6) return g->e->fail(MCPYB_ERR_ARG, "gcmc info: bad argument");
     const GcChain& C = g->chains[chain];
     out6[0] = C.ncell[0]; out6[1] = C.ncell[1]; out6[2] = C.ncell[2]; out6[3] = C.ccap; out6[4] = C.lay.bytes; out6[5] = C.in_smem;
+    return MCPYB_OK;
+}
+
+int mcpyb_gcmc_cycles(mcpyb_gcmc* g, int chain, int64_t* out3 /* [4] */) {
+    if (!g) return MCPYB_ERR_ARG;
+    if (chain < 0 || chain >= g->n || !out3) return g->e->fail(MCPYB_ERR_ARG, "gcmc cycles: bad argument");
+    out3[0] = g->dyn[chain].cyc_serial; out3[1] = g->dyn[chain].cyc_total; out3[2] = g->dyn[chain].rounds;
+    out3[3] = g->dyn[chain].resyncs;
     return MCPYB_OK;
 }
 

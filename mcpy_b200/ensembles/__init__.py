@@ -6,7 +6,7 @@ from .acceptance import Units, acceptance_probability, accept_trial, swap_expone
 
 _LAZY = {'ShardedReplicaExchange': 'sharded_replica_exchange',
          'ResidentLadderShard': 'resident_shard', 'LadderComm': 'ladder_comm',
-         'ResidentGCMC': 'resident_gcmc'}
+         'ResidentGCMC': 'resident_gcmc', 'ResidentReplicaExchange': 'resident_replica_exchange'}
 
 
 def __getattr__(name):

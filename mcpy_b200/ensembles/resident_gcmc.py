@@ -134,7 +134,13 @@ class ResidentGCMC:
         h = C.c_void_p()
         self.engine._check(self._lib.mcpyb_gcmc_create(self.engine._h, n, self._desc, self.trace_capacity, C.byref(h)))
         self._h = h
-        self._resident = False
+        from ase.data import atomic_numbers
+        self._Z = [atomic_numbers[sp] for sp in self._species]
+        self._host_fresh = [True] * n              # the ensemble objects hold the current state
+        self._device_fresh = [False] * n           # the chain holds the current state
+        self._counted = [[[0] * GCMC_MAX_MOVES for _ in range(3)] for _ in range(n)]   # device counters already added on the host
+        self._trials_seen = [0] * n
+        self._gauss = {}
         self.last_status = [0] * n
         self.trials_run = 0
 
@@ -183,10 +189,17 @@ class ResidentGCMC:
         d.cell_capacity = int(cell_capacity)
 
     # ------------------------------------------------------------------ host objects -> device
-    def push(self):
-        """Upload every ensemble's current state (configuration, generators, energy, best) to its chain."""
-        from random import Random  # noqa: F401  (the states handled here are random.Random.getstate() tuples)
-        for k, g in enumerate(self.ensembles):
+    def _gens(self, g):
+        ms = g.move_selector
+        return [ms.rng.random] + [mv.rng.random for mv in ms.move_list] + [g.rng_acceptance.random]
+
+    def push(self, chains=None):
+        """Upload the current state of the ensembles (configuration, generators, energy, best) to their chains."""
+        for k in (range(len(self.ensembles)) if chains is None else chains):
+            g = self.ensembles[k]
+            if not self._host_fresh[k]:
+                raise RuntimeError(f'ResidentGCMC: chain {k} was advanced on the device and not synchronised back; '
+                                   'call sync_host() before touching the ensemble on the host')
             atoms = g.atoms
             ms = g.move_selector
             s = GcmcScalars()
@@ -202,9 +215,8 @@ class ResidentGCMC:
                     raise ValueError("the Cell's generator must be numpy PCG64 with no buffered 32-bit half")
                 hi_lo, inc = Engine._pcg_words(cell._rng)
                 s.pcg[c][0], s.pcg[c][1], s.pcg[c][2], s.pcg[c][3] = int(hi_lo[0]), int(hi_lo[1]), int(inc[0]), int(inc[1])
-            gens = [ms.rng.random] + [mv.rng.random for mv in ms.move_list] + [g.rng_acceptance.random]
+            gens = self._gens(g)
             mt = np.empty((len(gens), GCMC_MT_WORDS), dtype=np.uint32)
-            self._gauss = getattr(self, '_gauss', {})
             for j, r in enumerate(gens):
                 version, words, gauss_next = r.getstate()
                 if version != 3 or len(words) != GCMC_MT_WORDS:
@@ -214,15 +226,52 @@ class ResidentGCMC:
             pos = np.ascontiguousarray(atoms.positions, dtype=np.float64)
             self.engine._check(self._lib.mcpyb_gcmc_set_state(self._h, k, pos.ctypes.data if len(pos) else None,
                                                               C.byref(s), mt.ctypes.data))
-        self._resident = True
+            self._device_fresh[k] = True
+            self._counted[k] = [[0] * GCMC_MAX_MOVES for _ in range(3)]
+            self._trials_seen[k] = 0
 
     # ------------------------------------------------------------------ device -> host objects
-    def pull(self):
-        """Write every chain's state back into its ensemble: atoms, ``E_old``, ``n_atoms``, the generator states,
-        the selector's counters and ``to_use``, the running minimum."""
+    def _apply_scalars(self, k):
+        """What the drivers read between blocks: ``E_old``, ``n_atoms`` (and an ``Atoms`` of that length), the
+        selector's counters and ``to_use``, the running-minimum scores.  Positions and generator states stay on the
+        device until :meth:`sync_host`; the host ``positions`` are NaN meanwhile."""
+        g = self.ensembles[k]
+        s = GcmcScalars()
+        self.engine._check(self._lib.mcpyb_gcmc_get_scalars(self._h, k, C.byref(s)))
+        n = int(s.n_atoms)
+        atoms = g.atoms
+        if self._host_fresh[k] or len(atoms) != n:
+            atoms.arrays = {'numbers': np.full(n, self._Z[k], dtype=atoms.arrays['numbers'].dtype),
+                            'positions': np.full((n, 3), np.nan)}
+        self._host_fresh[k] = False
+        g.n_atoms = n
+        g.E_old = float(s.energy)
+        ms = g.move_selector
+        ms.to_use = int(s.last_move)
+        seen = self._counted[k]
+        for m in range(self._desc[k].n_move_types):
+            for c, (src, interval, total) in enumerate(((s.attempts, ms.move_counter, ms.move_counter_total),
+                                                        (s.accepted, ms.move_acceptance, ms.move_acceptance_total),
+                                                        (s.failed, ms.move_failed_counter, ms.move_failed_counter_total))):
+                d = int(src[m]) - seen[c][m]
+                if d:
+                    interval[m] += d
+                    total[m] += d
+                    seen[c][m] += d
+        if s.best_n >= 0:                                              # improved since the upload
+            g._best_score = float(s.best_score)
+            g._best_energy = float(s.best_energy)
+        return s
+
+    def sync_host(self, chains=None):
+        """Bring the ensembles fully up to date with their chains: configuration, the five Mersenne-Twister states and
+        the cells' PCG64 states, the best configuration.  The ensembles own the state afterwards: whatever the host does
+        to them (a block of the reference's own loop, a swap) is uploaded again before the next device block."""
         from ase import Atoms
-        from ase.data import atomic_numbers
-        for k, g in enumerate(self.ensembles):
+        for k in (range(len(self.ensembles)) if chains is None else chains):
+            if self._host_fresh[k]:
+                continue
+            g = self.ensembles[k]
             d = self._desc[k]
             cap = d.atom_capacity
             nm = d.n_move_types
@@ -232,63 +281,73 @@ class ResidentGCMC:
             s = GcmcScalars()
             self.engine._check(self._lib.mcpyb_gcmc_get_state(self._h, k, pos.ctypes.data, C.byref(s), mt.ctypes.data,
                                                               best.ctypes.data))
+            self._apply_scalars(k)
             n = int(s.n_atoms)
-            Z = atomic_numbers[self._species[k]]
             atoms = g.atoms
             # same object, new arrays: what the reference's in-place moves leave behind
-            atoms.arrays = {'numbers': np.full(n, Z, dtype=atoms.arrays['numbers'].dtype),
+            atoms.arrays = {'numbers': np.full(n, self._Z[k], dtype=atoms.arrays['numbers'].dtype),
                             'positions': pos[:n].copy()}
-            g.n_atoms = n
-            g.E_old = float(s.energy)
-            ms = g.move_selector
-            ms.to_use = int(s.last_move)
-            for m in range(nm):
-                a, acc, f = int(s.attempts[m]), int(s.accepted[m]), int(s.failed[m])
-                ms.move_counter[m] += a
-                ms.move_counter_total[m] += a
-                ms.move_acceptance[m] += acc
-                ms.move_acceptance_total[m] += acc
-                ms.move_failed_counter[m] += f
-                ms.move_failed_counter_total[m] += f
-            gens = [ms.rng.random] + [mv.rng.random for mv in ms.move_list] + [g.rng_acceptance.random]
-            for j, r in enumerate(gens):
-                r.setstate((3, tuple(int(w) for w in mt[j]), self._gauss[(k, j)]))
+            for j, r in enumerate(self._gens(g)):
+                r.setstate((3, tuple(mt[j].tolist()), self._gauss[(k, j)]))
             for c, cell in enumerate(self._pcg_cells[k]):
                 st = cell._rng.bit_generator.state
                 st['state']['state'] = (int(s.pcg[c][0]) << 64) | int(s.pcg[c][1])
                 cell._rng.bit_generator.state = st
-            if s.best_n >= 0:                                          # improved during the block
-                g._best_score = float(s.best_score)
-                g._best_energy = float(s.best_energy)
+            if s.best_n >= 0:
                 bn = int(s.best_n)
-                g._best_atoms = Atoms(numbers=np.full(bn, Z), positions=best[:bn].copy(), cell=atoms.cell, pbc=atoms.pbc)
+                g._best_atoms = Atoms(numbers=np.full(bn, self._Z[k]), positions=best[:bn].copy(), cell=atoms.cell,
+                                      pbc=atoms.pbc)
             if self.resync_energy:
                 g.E_old = float(g.compute_energy(atoms))
-        # the counters were added to the host ones: the next push starts the device's from zero
-        self._resident = False
+            self._host_fresh[k] = True
+            self._device_fresh[k] = False          # the ensemble owns the state again (the host may change it)
+
+    pull = sync_host
+
+    def swap_configurations(self, i, j):
+        """``_swap_states`` of the replica drivers between chains ``i`` and ``j`` on the device (configuration, energy,
+        particle number); the caller swaps the ensembles' ``atoms`` / ``E_old`` / ``n_atoms``.  Chains that are not both
+        device-fresh, or whose storage differs, are synchronised and re-uploaded instead."""
+        if self._device_fresh[i] and self._device_fresh[j] and self._same_storage(i, j):
+            self.engine._check(self._lib.mcpyb_gcmc_swap_configurations(self._h, int(i), int(j)))
+            return True
+        self.sync_host([i, j])
+        return False
+
+    def _same_storage(self, i, j):
+        a, b = self._desc[i], self._desc[j]
+        return (a.atom_capacity == b.atom_capacity and list(a.box) == list(b.box) and a.lj_rc == b.lj_rc
+                and a.n_move_types == b.n_move_types and self.info(i) == self.info(j))
 
     # ------------------------------------------------------------------ running
-    def run_trials(self, n_trials):
+    def advance(self, n_trials, sync='full'):
         """Advance every chain by ``n_trials`` trials (an int, or one count per chain) in as few launches as the
-        capacities allow, and write the states back.  Returns the device time of the launches in milliseconds."""
+        capacities allow.  ``sync='full'`` writes the whole state back into the ensembles; ``sync='scalars'`` only what
+        the drivers read between blocks (:meth:`_apply_scalars`) and leaves the rest on the device for the next block.
+        Returns the device time of the launches in milliseconds."""
         n = len(self.ensembles)
         want = np.full(n, int(n_trials), dtype=np.int64) if np.isscalar(n_trials) else np.asarray(n_trials, dtype=np.int64).copy()
         if want.shape != (n,) or np.any(want < 0):
             raise ValueError('n_trials: one non-negative count per chain')
         status = np.zeros(n, dtype=np.int32)
         total_ms = 0.0
+        ms = C.c_double(0.0)
         self.traces = [np.empty(0, dtype=GCMC_TRIAL_DTYPE) for _ in range(n)] if self.trace_capacity else None
         for _ in range(64):
-            self.push()
+            stale = [k for k in range(n) if not self._device_fresh[k]]
+            if stale:
+                self.push(stale)
             self.engine._check(self._lib.mcpyb_gcmc_run(self._h, want.ctypes.data, status.ctypes.data))
-            ms = C.c_double(0.0)
             self._lib.mcpyb_gcmc_last_run_ms(self._h, C.byref(ms))
             total_ms += ms.value
-            done = self._trials_done()
+            done = np.empty(n, dtype=np.int64)
+            for k in range(n):
+                s = self._apply_scalars(k)
+                done[k] = int(s.trials_done) - self._trials_seen[k]
+                self._trials_seen[k] = int(s.trials_done)
             if self.trace_capacity:
                 for k in range(n):
                     self.traces[k] = np.concatenate([self.traces[k], self._get_trace(k)])
-            self.pull()
             want -= done
             self.trials_run += int(done.sum())
             self.last_status = status.tolist()
@@ -297,12 +356,20 @@ class ResidentGCMC:
             for k in np.nonzero(want > 0)[0]:
                 st = int(status[k])
                 if st == 4:
+                    self.sync_host()
                     raise ValueError('No atoms to displace.')                  # displacement_move.py:60
-                if st in (1, 2):
-                    self._grow(int(k), st)
+            need = {int(status[k]) for k in np.nonzero(want > 0)[0]} & {1, 2}
+            if need:
+                self._grow(need)
         else:
             raise RuntimeError(f'ResidentGCMC: chains keep stopping early ({[STATUS.get(s, s) for s in self.last_status]})')
+        if sync == 'full':
+            self.sync_host()
         return total_ms
+
+    def run_trials(self, n_trials):
+        """:meth:`advance` with the whole state written back."""
+        return self.advance(n_trials, sync='full')
 
     def run(self, steps):
         """``gcmc.run(steps)`` of every ensemble (``base_ensemble.py:257-264``) with the trials on the device: blocks of
@@ -313,12 +380,18 @@ class ResidentGCMC:
             done = 0
             while done < steps:
                 block = steps - done
+                need_positions = False
                 for g in self.ensembles:
                     for iv in (g._outfile_write_interval if g._outfile is not None else None,
                                g._trajectory_write_interval if g._traj_file is not None else None):
                         if iv:
                             block = min(block, iv - (g._step % iv))
-                self.run_trials([block * g.move_selector.n_moves for g in self.ensembles])
+                for g in self.ensembles:
+                    if g._traj_file is not None and (g._step + block) % g._trajectory_write_interval == 0:
+                        need_positions = True
+                last = done + block >= steps
+                self.advance([block * g.move_selector.n_moves for g in self.ensembles],
+                             sync='full' if (need_positions or last) else 'scalars')
                 done += block
                 for g in self.ensembles:
                     g._step += block
@@ -327,46 +400,48 @@ class ResidentGCMC:
                     if g._traj_file is not None and g._step % g._trajectory_write_interval == 0:
                         g.write_coordinates(g.atoms, g.E_old)
         finally:
+            self.sync_host()
             for g in self.ensembles:
                 g.finalize_run()
 
     # ------------------------------------------------------------------ helpers
-    def _trials_done(self):
-        out = np.zeros(len(self.ensembles), dtype=np.int64)
-        s = GcmcScalars()
-        for k in range(len(self.ensembles)):
-            self.engine._check(self._lib.mcpyb_gcmc_get_state(self._h, k, None, C.byref(s), None, None))
-            out[k] = s.trials_done
-        return out
-
     def _get_trace(self, k):
         buf = np.empty(self.trace_capacity, dtype=GCMC_TRIAL_DTYPE)
         n = C.c_int64(0)
         self.engine._check(self._lib.mcpyb_gcmc_get_trace(self._h, k, buf.ctypes.data, self.trace_capacity, C.byref(n)))
         return buf[:n.value].copy()
 
-    def _grow(self, k, status):
-        """A chain ran into a capacity: rebuild the chain set with more room for it."""
-        d = self._desc[k]
-        info = self.info(k)
-        if status == 2:
-            if d.atom_capacity >= 65535:
-                raise RuntimeError('ResidentGCMC: a chain outgrew 65 535 atoms')
-            d.atom_capacity = min(65535, 2 * d.atom_capacity)
-        else:
-            d.cell_capacity = 2 * info['cell_capacity']
+    def _grow(self, statuses):
+        """Chains ran into a capacity (1: a cell of the cell list, 2: the atom storage): rebuild the chain set with
+        more room -- for every chain alike, so that replica swaps keep finding identical storage."""
+        self.sync_host()
+        ccap = max(self.info(k)['cell_capacity'] for k in range(len(self.ensembles)))
+        for d in self._desc:
+            if 2 in statuses:
+                if d.atom_capacity >= 65535:
+                    raise RuntimeError('ResidentGCMC: a chain outgrew 65 535 atoms')
+                d.atom_capacity = min(65535, 2 * d.atom_capacity)
+            d.cell_capacity = 2 * ccap if 1 in statuses else ccap
         self._lib.mcpyb_gcmc_destroy(self._h)
         self._h = None
         h = C.c_void_p()
         self.engine._check(self._lib.mcpyb_gcmc_create(self.engine._h, len(self.ensembles), self._desc,
                                                        self.trace_capacity, C.byref(h)))
         self._h = h
+        self._device_fresh = [False] * len(self.ensembles)
+        self._trials_seen = [0] * len(self.ensembles)
 
     def info(self, k=0):
         out = (C.c_int32 * 6)()
         self.engine._check(self._lib.mcpyb_gcmc_info(self._h, k, out))
         return {'cells': (out[0], out[1], out[2]), 'cell_capacity': out[3], 'state_bytes': out[4],
                 'in_shared_memory': bool(out[5])}
+
+    def cycles(self, k=0):
+        """SM cycles of chain ``k``'s last launch: serial section of thread 0, whole loop, loop trips."""
+        out = (C.c_int64 * 4)()
+        self.engine._check(self._lib.mcpyb_gcmc_cycles(self._h, k, out))
+        return {'serial': out[0], 'total': out[1], 'rounds': out[2], 'energy_resyncs': out[3]}
 
     def close(self):
         if getattr(self, '_h', None):

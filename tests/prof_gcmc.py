@@ -58,7 +58,8 @@ def main():
                                        'trials_per_s': chains * trials / (1e-3 * ms),
                                        'wall_trials_per_s': chains * trials / wall,
                                        'accept_ratio': acc / (chains * (trials + 200)),
-                                       'mean_atoms': float(np.mean([len(g.atoms) for g in gs])), **rg.info()}
+                                       'mean_atoms': float(np.mean([len(g.atoms) for g in gs])), **rg.info(),
+                                       'cycles_last_launch': rg.cycles(0)}
             rg.close()
         # the reference's loop, one calculator call per trial
         g = make(cfg, symbol, mu, calc)

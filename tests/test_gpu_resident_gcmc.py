@@ -240,3 +240,36 @@ def test_out_of_scope_chains_are_refused():
     g = box_gcmc(cfg, 'H', -2.0)
     with pytest.raises(ValueError, match='Lennard-Jones parameters'):
         ResidentGCMC(g)
+
+
+@pytest.mark.parametrize('kind', ['T', 'mu'])
+def test_replica_exchange_with_resident_replicas_equals_the_reference_driver(kind, tmp_path):
+    """The reference's ``BatchedReplicaExchange`` over the CPU oracle against ``ResidentReplicaExchange`` (all replicas
+    advance in one launch per block, swaps of local replicas happen on the device): same swap decisions, same replicas."""
+    from helpers import make_factory
+    from mcpy.ensembles import BatchedReplicaExchange
+    from mcpy_b200.ensembles import ResidentReplicaExchange
+    calc = OracleLJCalculator()
+    factory = make_factory(calc, n0=24, base_seed=400, n_moves=3)
+    ladder = dict(temperatures=[1.5, 1.8, 2.2, 2.7, 3.3, 4.0]) if kind == 'T' else \
+        dict(mus=[{'H': m} for m in (-3.2, -2.9, -2.6, -2.3, -2.0, -1.7)])
+    ref = BatchedReplicaExchange(factory, calc, gcmc_steps=45, exchange_interval=4, seed=31, write_out_interval=10,
+                                 outfile=str(tmp_path / 'ref.out'), global_minimum_file=str(tmp_path / 'ref_min.xyz'),
+                                 **ladder)
+    ref.run()
+    mine = ResidentReplicaExchange(factory, calc, gcmc_steps=45, exchange_interval=4, seed=31, write_out_interval=10,
+                                   outfile=str(tmp_path / 'dev.out'), global_minimum_file=str(tmp_path / 'dev_min.xyz'),
+                                   rank=0, world_size=1, lj=(1.0, 1.0, 2.5), **ladder)
+    mine.run()
+    assert mine.exchange_attempts == ref.exchange_attempts
+    assert mine.exchange_successes == ref.exchange_successes
+    assert sum(mine.exchange_successes) > 2
+    assert mine.blocks < 45                                                  # several steps per launch
+    for a, b in zip(ref.replicas, mine.replicas):
+        assert_same_chain(a, b)
+        assert a._step == b._step
+    # the replica-exchange outfile: replica, step and atom counts of every row
+    rows = [[ln.split()[:4] for ln in open(tmp_path / f'{t}.out') if ln[:1].isdigit()] for t in ('ref', 'dev')]
+    assert rows[0] == rows[1] and len(rows[0]) >= 6 * 5
+    lines = [[ln for ln in open(tmp_path / f'{t}_min.xyz')][2:] for t in ('ref', 'dev')]
+    assert lines[0] == lines[1] and len(lines[0]) > 0                        # the global minimum, atom for atom
