@@ -520,6 +520,74 @@ def run_b200(args):
                          'GrandCanonicalEnsemble replicas + B200Calculator.get_potential_energies; host time is the '
                          "reference's own Python (snapshots, moves, acceptance, wrap)"}
 
+    # ---- resident mode: the same replica-exchange run with every replica's trials on the device (row f2)
+    resident = None
+    if re is not None and not args.no_resident:
+        try:
+            from mcpy_b200.ensembles import ResidentGCMC, ResidentReplicaExchange
+            n_res = args.resident_steps
+            rre = ResidentReplicaExchange(factory, calc, mus=[{'H': float(m)} for m in mus], gcmc_steps=10 ** 9,
+                                          exchange_interval=XI, write_out_interval=10 ** 9, seed=31, rank=rank,
+                                          world_size=world, device=f'cuda:{local}', outfile=None,
+                                          global_minimum_file=None, engine=eng)
+            for r in rre.replicas:
+                r.initialize_run()
+            rre._rebatch_initial_energies()
+
+            def resident_steps(n):
+                for _ in range(n):
+                    rre._batched_gcmc_step()
+                    if rre._re_step > 0 and rre._re_step % XI == 0:
+                        rre._attempt_exchanges()
+                    rre._re_step += 1
+            resident_steps(5 * XI)                                   # warm-up: first upload, first exchanges
+            g0r, c0r = rre.comm.gathers, rre.comm.collective_seconds
+            dev0, blocks0 = rre.device_ms, rre.blocks
+            acc0 = sum(sum(r.move_selector.move_acceptance_total) for r in rre.replicas)
+            swaps0 = sum(rre.global_successes)
+            barrier()
+            t0 = time.perf_counter()
+            resident_steps(n_res)
+            torch.cuda.synchronize()
+            res_s = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            launches_resident = rre.blocks - blocks0
+            rre.resident.sync_host()
+            # one chain alone: what a single GrandCanonicalEnsemble run gets (ResidentGCMC.run_trials)
+            one = ResidentGCMC([factory(mu={'H': float(mus[0])}, rank=rank * R)], engine=eng)
+            one.advance(500, sync='scalars')
+            t0 = time.perf_counter()
+            one_ms = one.advance(args.resident_chain_trials, sync='scalars')
+            one_wall = time.perf_counter() - t0
+            cyc = one.cycles(0)
+            one.sync_host()
+            one.close()
+            resident = {
+                'value': world * R * n_res / res_s, 'unit': 'replica trial-move dE evals/s (whole trials: proposal, dE, '
+                                                             'acceptance, commit)',
+                'steps': n_res, 'trials_per_replica': n_res, 'wall_s': res_s,
+                'device_ms': rre.device_ms - dev0, 'launches': launches_resident,
+                'us_per_trial_per_replica_device': 1e3 * (rre.device_ms - dev0) / n_res,
+                'host_share': 1.0 - 1e-3 * (rre.device_ms - dev0) / res_s,
+                'exchange_attempts': (rre.comm.gathers - g0r) if world > 1 else n_res // XI,
+                'accepted_swaps': sum(rre.global_successes) - swaps0,
+                'collective_us_per_exchange': 1e6 * (rre.comm.collective_seconds - c0r) / max(1, rre.comm.gathers - g0r),
+                'accepted_moves': sum(sum(r.move_selector.move_acceptance_total) for r in rre.replicas) - acc0,
+                'speedup_vs_driver': (world * R * n_res / res_s) / driver['value'] if driver else None,
+                'single_chain': {'trials': args.resident_chain_trials, 'device_trials_per_s': args.resident_chain_trials / (1e-3 * one_ms),
+                                 'wall_trials_per_s': args.resident_chain_trials / one_wall,
+                                 'device_us_per_trial': 1e3 * one_ms / args.resident_chain_trials,
+                                 'serial_share_of_cycles': cyc['serial'] / max(1, cyc['total']),
+                                 'speedup_vs_dropin_calls': None},
+                'api': 'ResidentReplicaExchange (subclass of the unmodified BatchedReplicaExchange): the unmodified '
+                       'GrandCanonicalEnsemble replicas hand their state to one CTA each (csrc/gcmc_chain.cuh: MT19937 / '
+                       'PCG64 draws, proposal, LJ dE, acceptance, wrap, commit on the device, bit-identical decisions), '
+                       'one launch per block of steps between two exchange attempts, swaps of local replicas on the '
+                       'device, records all_gathered as in the driver arm'}
+            rre.resident.close()
+        except Exception as exc:                                     # the arm must not take the headline down with it
+            resident = {'error': f'{type(exc).__name__}: {exc}'}
+
     # ---- drop-in chain: one get_potential_energy(atoms) per trial, sequential (a single GCMC run)
     n_chain = args.chain
     chain_cfgs = [trial_config(cfgs[:1], {k: (v[:TRIALS_PER_REPLICA + 1] if k.endswith('off') else v) for k, v in batches[0].items()}, t)
@@ -540,6 +608,8 @@ def run_b200(args):
         calc.get_potential_energy(a)
     chain_s = max_over_ranks(time.perf_counter() - t0)
     dropin_value = world * n_chain / chain_s
+    if resident and 'single_chain' in resident:
+        resident['single_chain']['speedup_vs_dropin_calls'] = resident['single_chain']['wall_trials_per_s'] / (n_chain / chain_s)
 
     clocks = sampler.stop() if rank == 0 else None
 
@@ -596,6 +666,7 @@ def run_b200(args):
                              'ms_per_sweep': 1e3 * e2e_pageable_s / (KP * SW), 'steps': KP,
                              'note': 'same calls with ordinary numpy arrays: staged through pinned memory inside the engine'}},
         'driver': driver,
+        'resident': resident,
         'dropin': {'value': dropin_value, 'unit': UNIT, 'calls': n_chain,
                    'api': 'calculator.get_potential_energy(atoms) per trial, sequential '
                           '(mcpyb_tracked_energy_host: resident base + one delta; the trial rides in the '
@@ -954,6 +1025,9 @@ def main():
     ap.add_argument('--driver-steps', type=int, default=60, help='steps of the unmodified replica-exchange loop to time')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-driver', action='store_true')
+    ap.add_argument('--resident-steps', type=int, default=4000, help='steps of the device-resident replica-exchange run to time')
+    ap.add_argument('--resident-chain-trials', type=int, default=50000, help='trials of the single device-resident chain')
+    ap.add_argument('--no-resident', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary EMT / free-volume numbers')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':

@@ -26,13 +26,15 @@
 #include "pcg64.cuh"
 #include "../../include/mcpy_b200.h"
 
-#define GC_THREADS 512
-#define GC_QUADS (GC_THREADS / 4)
+#define GC_ROW_THREADS 512            // warps 1..16: the energy evaluator
+#define GC_THREADS (GC_ROW_THREADS + 32)   // warp 0: the Markov chain (its lane 0), busy while the others sum rows
+#define GC_QUADS (GC_ROW_THREADS / 4)
 #define GC_NONE 0xFFFF
 #define GC_SERIAL_WRAP 6          // unstable lists up to this length are wrapped by thread 0 itself
 
-struct GcLayout {                 // byte offsets of the arrays inside a chain's state block
-    int px, py, pz, mt, mt2, order, cell_of, unstable, uflag, cell_cnt, cell_slots, bytes;
+struct GcLayout {                 // byte offsets of the arrays inside a chain's state image
+    // [0, mt): what belongs to the CONFIGURATION (moves with it in a replica swap); [mt, bytes): what belongs to the SLOT
+    int px, py, pz, order, cell_of, unstable, uflag, cell_cnt, cell_slots, mt, mt2, bytes;
 };
 
 struct GcChain {                  // read-only description of one chain
@@ -42,7 +44,8 @@ struct GcChain {                  // read-only description of one chain
     int ncell[3], span[3];
     int ncells, ccap, acap, nmt;
     GcLayout lay;
-    unsigned char* blob;          // the state block in global memory
+    unsigned char* blob;          // global memory: the configuration part of the state image, [0, lay.mt)
+    unsigned char* slot;          // global memory: the slot part, [lay.mt, lay.bytes)
     double* best_pos;             // [acap][3], atom order
     mcpyb_gcmc_trial* trace;
     long long trace_cap;
@@ -53,6 +56,8 @@ struct GcDyn {                    // read-write scalars of one chain
     mcpyb_gcmc_scalars s;
     long long trace_len;
     long long cyc_serial, cyc_total, rounds;    // of the last launch: thread 0's serial section, the whole loop, loop trips
+    long long cyc_pre;                          // ... and thread 0's look-ahead proposals (hidden behind the row sums)
+    long long cyc_rows, cyc_wait;               // the row sums (first row thread), thread 0 waiting for them
     long long acc_since_resync;                 // accepted moves added onto E since it was last summed from scratch
     long long resyncs;
     double e_scale;                             // max |E| since then: bounds the rounding carried by E
@@ -67,14 +72,14 @@ static inline GcLayout gc_layout(int acap, int ncells, int ccap, int nmt) {
     l.px = o; o += gc_align16(8 * acap);
     l.py = o; o += gc_align16(8 * acap);
     l.pz = o; o += gc_align16(8 * acap);
-    l.mt = o; o += gc_align16(4 * MCPYB_GCMC_MT_WORDS * nmt);
-    l.mt2 = o; o += gc_align16(4 * 624 * nmt);           // scratch: the NEXT state of every stream, computed ahead
     l.order = o; o += gc_align16(2 * acap);
     l.cell_of = o; o += gc_align16(2 * acap);
     l.unstable = o; o += gc_align16(2 * acap);
     l.uflag = o; o += gc_align16(acap);
     l.cell_cnt = o; o += gc_align16(2 * ncells);
     l.cell_slots = o; o += gc_align16(2 * ncells * ccap);
+    l.mt = o; o += gc_align16(4 * MCPYB_GCMC_MT_WORDS * nmt);
+    l.mt2 = o; o += gc_align16(4 * 624 * nmt);           // scratch: the NEXT state of every stream, computed ahead
     l.bytes = o;
     return l;
 }
@@ -89,12 +94,13 @@ static inline GcLayout gc_layout(int acap, int ncells, int ccap, int nmt) {
 struct GcMt {
     uint32_t* a;                  // lay.mt : [stream][625]
     uint32_t* b;                  // lay.mt2: [stream][624]
+    uint32_t* cur[GC_MAX_STREAMS];           // where the current state of a stream lives (a or b)
     int idx[GC_MAX_STREAMS];
-    unsigned char flip[GC_MAX_STREAMS];      // 1: the current state lives in b
-    unsigned char ready[GC_MAX_STREAMS];     // 1: the next state is complete in the other buffer
+    int flip_mask;                // bit k: the current state of stream k lives in b
+    int ready_mask;               // bit k: the next state of stream k is complete in the other buffer
 };
-__device__ __forceinline__ uint32_t* gc_mt_cur(GcMt& M, int k) { return M.flip[k] ? M.b + k * 624 : M.a + k * MCPYB_GCMC_MT_WORDS; }
-__device__ __forceinline__ uint32_t* gc_mt_other(GcMt& M, int k) { return M.flip[k] ? M.a + k * MCPYB_GCMC_MT_WORDS : M.b + k * 624; }
+__device__ __forceinline__ uint32_t* gc_mt_cur(GcMt& M, int k) { return M.cur[k]; }
+__device__ __forceinline__ uint32_t* gc_mt_other(GcMt& M, int k) { return (M.flip_mask >> k & 1) ? M.a + k * MCPYB_GCMC_MT_WORDS : M.b + k * 624; }
 __device__ __forceinline__ uint32_t gc_mt_twist(uint32_t cur, uint32_t nxt) {
     const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
     return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
@@ -121,7 +127,10 @@ __device__ __forceinline__ void gc_mt_refill(GcMt& M, int k, int tid) {
 }
 // thread 0: the state of stream k is used up
 __device__ __noinline__ void gc_mt_advance(GcMt& M, int k) {
-    if (M.ready[k]) { M.flip[k] ^= 1; M.ready[k] = 0; M.idx[k] = 0; return; }
+    if (M.ready_mask >> k & 1) {
+        M.cur[k] = gc_mt_other(M, k); M.flip_mask ^= 1 << k; M.ready_mask &= ~(1 << k); M.idx[k] = 0;
+        return;
+    }
     uint32_t* s = gc_mt_cur(M, k);
     uint32_t cur = s[0];
     for (int j = 0; j < 623; ++j) {
@@ -185,6 +194,25 @@ __device__ __forceinline__ uint32_t gc_mt_randbelow(GcMt& M, int k, uint32_t n) 
     }
 }
 
+// Looking ahead without consuming (the proposal prepared while the CTA sums the rows of the trial before it): the words
+// at offset `off` past the position of stream k, as long as the current state has them.
+__device__ __forceinline__ bool gc_peek_randbelow(GcMt& M, int k, int& off, uint32_t n, uint32_t& r) {
+    const int sh = __clz(n);
+    const uint32_t* s = gc_mt_cur(M, k) + M.idx[k];
+    const int avail = 624 - M.idx[k];
+    while (off < avail) {
+        const uint32_t v = gc_mt_temper(s[off]) >> sh;
+        ++off;
+        if (v < n) { r = v; return true; }
+    }
+    return false;
+}
+struct GcPre {                    // a proposal drawn ahead: valid as long as the generators have not moved and n == n_spec
+    int valid, mv, kind, n_spec, used_mv, index, has_point;
+    double a, b, c;               // displacement: the unit-ball vector; insertion: the point
+    unsigned long long st_hi, st_lo;         // insertion: the PCG64 state after the point
+};
+
 // ase.geometry.wrap_positions for a diagonal cell and a periodic axis (center 0.5, eps 1e-7), operation for operation:
 // fractional = x * (1/L) - shift, shift = -1e-7 (np.linalg.solve on a diagonal matrix multiplies by the reciprocal);
 // fractional %= 1.0 (numpy remainder); fractional += shift; x' = fractional * L.
@@ -238,16 +266,20 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const GcLayout lay = C.lay;
     unsigned char* base = C.in_smem ? gc_smem : C.blob;
+    unsigned char* sbase = C.in_smem ? gc_smem + lay.mt : C.slot;
     if (C.in_smem) {
         const uint4* src = reinterpret_cast<const uint4*>(C.blob);
         uint4* dst = reinterpret_cast<uint4*>(gc_smem);
-        for (int i = tid; i < lay.bytes / 16; i += GC_THREADS) dst[i] = src[i];
+        for (int i = tid; i < lay.mt / 16; i += GC_THREADS) dst[i] = src[i];
+        src = reinterpret_cast<const uint4*>(C.slot);
+        dst = reinterpret_cast<uint4*>(gc_smem + lay.mt);
+        for (int i = tid; i < (lay.bytes - lay.mt) / 16; i += GC_THREADS) dst[i] = src[i];
     }
     double* px = reinterpret_cast<double*>(base + lay.px);
     double* py = reinterpret_cast<double*>(base + lay.py);
     double* pz = reinterpret_cast<double*>(base + lay.pz);
-    uint32_t* mt = reinterpret_cast<uint32_t*>(base + lay.mt);
-    uint32_t* mt2 = reinterpret_cast<uint32_t*>(base + lay.mt2);
+    uint32_t* mt = reinterpret_cast<uint32_t*>(sbase);
+    uint32_t* mt2 = reinterpret_cast<uint32_t*>(sbase + (lay.mt2 - lay.mt));
     unsigned short* order = reinterpret_cast<unsigned short*>(base + lay.order);
     unsigned short* cell_of = reinterpret_cast<unsigned short*>(base + lay.cell_of);
     unsigned short* unstable = reinterpret_cast<unsigned short*>(base + lay.unstable);
@@ -278,6 +310,9 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
     double E = 0.0, best_score = 0.0, best_E = 0.0, e_scale = 0.0;
     long long acc_since = 0, resyncs = 0;
     int best_n = -1;
+    GcPre pre;
+    pre.valid = 0;
+    const int all_streams = (1 << (nm + 2)) - 1;
     if (tid == 0) {
         n = D.s.n_atoms; n_unst = D.n_unstable; E = D.s.energy; best_score = D.s.best_score; best_E = D.s.best_energy;
         best_n = D.s.best_n; t_done = D.s.trials_done; t_goal = t_done + n_trials[blockIdx.x]; trace_len = 0;
@@ -287,27 +322,25 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
         T.done = 0; T.par = 0; T.nsites = 0; T.refill = 0; T.resync = 0;
         D.s.status = MCPYB_GCMC_DONE;
         M.a = mt; M.b = mt2;
-        for (int k = 0; k < nm + 2; ++k) { M.idx[k] = (int)mt[k * MCPYB_GCMC_MT_WORDS + 624]; M.flip[k] = 0; M.ready[k] = 0; }
+        for (int k = 0; k < nm + 2; ++k) { M.idx[k] = (int)mt[k * MCPYB_GCMC_MT_WORDS + 624]; M.cur[k] = mt + k * MCPYB_GCMC_MT_WORDS; }
+        M.flip_mask = 0; M.ready_mask = 0;
         e_scale = fmax(D.e_scale, fabs(E)); acc_since = D.acc_since_resync; resyncs = D.resyncs;
     }
     __syncthreads();                                        // (the state block, s_d and the stencil table are in place)
 
-    long long cyc_serial = 0, rounds = 0;
+    long long cyc_serial = 0, rounds = 0, cyc_pre = 0, cyc_rows = 0, cyc_wait = 0;
     const long long cyc_begin = clock64();
     while (true) {
         if (tid == 0) {
             const long long cyc_in = clock64();
             // ---------------- the Markov chain proper (serial) ----------------
             bool proposing = true;
-            if (T.refill) {                                 // the CTA completed these next states in the last parallel section
-                for (int k = 0; k < nm + 2; ++k) if (T.refill >> k & 1) M.ready[k] = 1;
-                T.refill = 0;
-            }
+            if (T.refill) { M.ready_mask |= T.refill; T.refill = 0; }   // completed by the CTA in the last parallel section
             if (T.par) { T.par = 0; }                       // the parallel commit of the last trial is done
             else if (have_rows) {
                 have_rows = 0;
                 double dE = 0.0;
-                for (int w = 0; w < GC_THREADS / 32; ++w) dE += s_part[w];
+                for (int w = 0; w < GC_ROW_THREADS / 32; ++w) dE += s_part[w];
                 // _acceptance_condition; n is the pre-move atom count (self.n_atoms)
                 bool acc;
                 drew = 0;
@@ -415,31 +448,44 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                 if (pending) { D.s.status = pending; T.done = 1; break; }
                 if (t_done >= t_goal) { T.done = 1; break; }
                 if (C.trace && trace_len >= C.trace_cap) { D.s.status = MCPYB_GCMC_TRACE_FULL; T.done = 1; break; }
-                // MoveSelector.__get_index__: searchsorted(rho, u * rho_total, side='right'), clamped
-                const double v = __dmul_rn(gc_mt_random(M, 0), s_d.move_cum_weight[nm - 1]);
+                // a proposal drawn ahead during the last row sums stands for the draws below if nothing it assumed changed
+                const bool use = pre.valid && (pre.kind != MCPYB_GCMC_DISPLACE || pre.n_spec == n);
+                pre.valid = 0;
                 int mv = 0;
-                while (mv < nm && s_d.move_cum_weight[mv] <= v) ++mv;
-                if (mv >= nm) mv = nm - 1;
+                if (use) { mv = pre.mv; M.idx[0] += 2; }
+                else {
+                    // MoveSelector.__get_index__: searchsorted(rho, u * rho_total, side='right'), clamped
+                    const double v = __dmul_rn(gc_mt_random(M, 0), s_d.move_cum_weight[nm - 1]);
+                    while (mv < nm && s_d.move_cum_weight[mv] <= v) ++mv;
+                    if (mv >= nm) mv = nm - 1;
+                }
                 cur_move = mv; cur_kind = s_d.move_kind[mv];
                 const int mt_mv = 1 + mv;
                 bool failed = false;
                 if (cur_kind == MCPYB_GCMC_DISPLACE && n == 0) { D.s.status = MCPYB_GCMC_EMPTY_DISPLACE; T.done = 1; break; }
                 s_cnt[0][mv] += 1;
                 if (cur_kind == MCPYB_GCMC_INSERT) {
-                    gc_mt_randbelow(M, mt_mv, 1u);                                   // rng.random.choice(self.species)
+                    if (use) M.idx[mt_mv] += pre.used_mv;
+                    else gc_mt_randbelow(M, mt_mv, 1u);                              // rng.random.choice(self.species)
                     cur_index = n;
                     if (s_d.move_limit[mv] >= 0 && n >= s_d.move_limit[mv]) failed = true;
                     else {
                         unsigned long long* ps = s_pcg[s_d.move_pcg[mv]];
-                        u128 st = ((u128)ps[0] << 64) | ps[1];
-                        const u128 inc = ((u128)ps[2] << 64) | ps[3];
-                        const double u0 = pcg_next_double(st, inc), u1 = pcg_next_double(st, inc), u2 = pcg_next_double(st, inc);
-                        ps[0] = (unsigned long long)(st >> 64); ps[1] = (unsigned long long)st;
-                        T.sx[0] = __dmul_rn(u0, L0); T.sy[0] = __dmul_rn(u1, L1); T.sz[0] = __dmul_rn(u2, L2);
+                        if (use && pre.has_point) {
+                            ps[0] = pre.st_hi; ps[1] = pre.st_lo;
+                            T.sx[0] = pre.a; T.sy[0] = pre.b; T.sz[0] = pre.c;
+                        } else {
+                            u128 st = ((u128)ps[0] << 64) | ps[1];
+                            const u128 inc = ((u128)ps[2] << 64) | ps[3];
+                            const double u0 = pcg_next_double(st, inc), u1 = pcg_next_double(st, inc), u2 = pcg_next_double(st, inc);
+                            ps[0] = (unsigned long long)(st >> 64); ps[1] = (unsigned long long)st;
+                            T.sx[0] = __dmul_rn(u0, L0); T.sy[0] = __dmul_rn(u1, L1); T.sz[0] = __dmul_rn(u2, L2);
+                        }
                         T.sign[0] = 1.0; T.nsites = 1; T.excl = GC_NONE;
                     }
                 } else if (cur_kind == MCPYB_GCMC_DELETE) {
-                    gc_mt_randbelow(M, mt_mv, 1u);
+                    if (use) M.idx[mt_mv] += pre.used_mv;
+                    else gc_mt_randbelow(M, mt_mv, 1u);
                     cur_index = -1;
                     if ((s_d.move_limit[mv] >= 0 && n <= s_d.move_limit[mv]) || n == 0) failed = true;
                     else {
@@ -449,17 +495,20 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                         T.sign[0] = -1.0; T.nsites = 1; T.excl = slot;
                     }
                 } else {
-                    cur_index = (int)gc_mt_randbelow(M, mt_mv, (uint32_t)n);         // rng.random.choice(to_move)
-                    const int slot = order[cur_index];
                     double rx, ry, rz, rsq;
-                    do {
-                        uint32_t w[6];
-                        gc_mt_take<6>(M, mt_mv, w);
-                        rx = __dsub_rn(__dmul_rn(2.0, gc_mt_double(w[0], w[1])), 1.0);
-                        ry = __dsub_rn(__dmul_rn(2.0, gc_mt_double(w[2], w[3])), 1.0);
-                        rz = __dsub_rn(__dmul_rn(2.0, gc_mt_double(w[4], w[5])), 1.0);
-                        rsq = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-                    } while (rsq > 1.0);
+                    if (use) { M.idx[mt_mv] += pre.used_mv; cur_index = pre.index; rx = pre.a; ry = pre.b; rz = pre.c; }
+                    else {
+                        cur_index = (int)gc_mt_randbelow(M, mt_mv, (uint32_t)n);     // rng.random.choice(to_move)
+                        do {
+                            uint32_t w[6];
+                            gc_mt_take<6>(M, mt_mv, w);
+                            rx = __dsub_rn(__dmul_rn(2.0, gc_mt_double(w[0], w[1])), 1.0);
+                            ry = __dsub_rn(__dmul_rn(2.0, gc_mt_double(w[2], w[3])), 1.0);
+                            rz = __dsub_rn(__dmul_rn(2.0, gc_mt_double(w[4], w[5])), 1.0);
+                            rsq = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                        } while (rsq > 1.0);
+                    }
+                    const int slot = order[cur_index];
                     const double md = s_d.move_max_displacement[mv];
                     T.sx[0] = px[slot]; T.sy[0] = py[slot]; T.sz[0] = pz[slot];
                     T.sx[1] = __dadd_rn(T.sx[0], __dmul_rn(rx, md));
@@ -485,11 +534,7 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                 have_rows = 1;
                 break;
             }
-            if (!T.done) {
-                int need = 0;
-                for (int k = 0; k < nm + 2; ++k) if (!M.ready[k]) need |= 1 << k;
-                T.refill = need;
-            }
+            if (!T.done) T.refill = ~M.ready_mask & all_streams;
             cyc_serial += clock64() - cyc_in;
             ++rounds;
         }
@@ -541,11 +586,13 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
             continue;
         }
         // ---------------- row sums: a quad of lanes per (site, stencil cell) ----------------
-        {
+        if (tid >= 32) {
+            const long long cyc_in = clock64();
+            const int rt = tid - 32;
             double acc = 0.0;
             const int ntasks = T.nsites * ns;
             const int excl = T.excl;
-            for (int task = tid >> 2; task < ntasks; task += GC_QUADS) {
+            for (int task = rt >> 2; task < ntasks; task += GC_QUADS) {
                 const int site = task >= ns ? 1 : 0;
                 const int sc = task - site * ns;
                 const int a0 = s_st[sc][0], a1 = s_st[sc][1], a2 = s_st[sc][2];
@@ -556,7 +603,7 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                 const int cell = (c0 * nc1 + c1) * nc2 + c2;
                 const int cnt = cell_cnt[cell];
                 const double sx = T.sx[site], sy = T.sy[site], sz = T.sz[site], sg = T.sign[site];
-                for (int k = tid & 3; k < cnt; k += 4) {
+                for (int k = rt & 3; k < cnt; k += 4) {
                     const int slot = cell_slots[cell * ccap + k];
                     if (slot == excl) continue;
                     const double x = px[slot], y = py[slot], z = pz[slot];
@@ -570,9 +617,60 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                 }
             }
             acc = warp_sum(acc);
-            if (lane == 0) s_part[warp] = acc;
+            if (lane == 0) s_part[warp - 1] = acc;
+            cyc_rows += clock64() - cyc_in;
+        } else if (tid == 0) {
+            // ---------------- meanwhile: the draws of the NEXT proposal, looked at without consuming them ----------------
+            // MoveSelector.rng, the move's rng and the cell's PCG64 are not touched by the acceptance test (its own stream),
+            // so what the next proposal draws is known now -- except that an index is drawn below n, which the running
+            // trial may change.  Drawn for the current n; used only if n is still that (or not needed) when it is its turn.
+            const long long cyc_in = clock64();
+            pre.valid = 0;
+            const uint32_t* s0 = gc_mt_cur(M, 0) + M.idx[0];
+            if (t_done + 1 < t_goal && !pending && M.idx[0] + 2 <= 624) {
+                const double v = __dmul_rn(gc_mt_double(gc_mt_temper(s0[0]), gc_mt_temper(s0[1])), s_d.move_cum_weight[nm - 1]);
+                int mv = 0;
+                while (mv < nm && s_d.move_cum_weight[mv] <= v) ++mv;
+                if (mv >= nm) mv = nm - 1;
+                const int kind = s_d.move_kind[mv], k = 1 + mv;
+                pre.mv = mv; pre.kind = kind; pre.n_spec = n; pre.has_point = 0;
+                int off = 0;
+                uint32_t r = 0;
+                if (kind != MCPYB_GCMC_DISPLACE) {
+                    if (gc_peek_randbelow(M, k, off, 1u, r)) {           // rng.random.choice(self.species)
+                        pre.used_mv = off;
+                        pre.valid = 1;
+                        if (kind == MCPYB_GCMC_INSERT && s_d.move_limit[mv] < 0) {
+                            const unsigned long long* ps = s_pcg[s_d.move_pcg[mv]];
+                            u128 st = ((u128)ps[0] << 64) | ps[1];
+                            const u128 inc = ((u128)ps[2] << 64) | ps[3];
+                            const double u0 = pcg_next_double(st, inc), u1 = pcg_next_double(st, inc), u2 = pcg_next_double(st, inc);
+                            pre.st_hi = (unsigned long long)(st >> 64); pre.st_lo = (unsigned long long)st;
+                            pre.a = __dmul_rn(u0, L0); pre.b = __dmul_rn(u1, L1); pre.c = __dmul_rn(u2, L2);
+                            pre.has_point = 1;
+                        }
+                    }
+                } else if (n > 0 && gc_peek_randbelow(M, k, off, (uint32_t)n, r)) {   // rng.random.choice(to_move)
+                    pre.index = (int)r;
+                    const uint32_t* s = gc_mt_cur(M, k) + M.idx[k];
+                    const int avail = 624 - M.idx[k];
+                    while (off + 6 <= avail) {
+                        const double rx = __dsub_rn(__dmul_rn(2.0, gc_mt_double(gc_mt_temper(s[off]), gc_mt_temper(s[off + 1]))), 1.0);
+                        const double ry = __dsub_rn(__dmul_rn(2.0, gc_mt_double(gc_mt_temper(s[off + 2]), gc_mt_temper(s[off + 3]))), 1.0);
+                        const double rz = __dsub_rn(__dmul_rn(2.0, gc_mt_double(gc_mt_temper(s[off + 4]), gc_mt_temper(s[off + 5]))), 1.0);
+                        off += 6;
+                        const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                        if (!(rsq > 1.0)) { pre.a = rx; pre.b = ry; pre.c = rz; pre.used_mv = off; pre.valid = 1; break; }
+                    }
+                }
+            }
+            cyc_pre += clock64() - cyc_in;
         }
-        __syncthreads();
+        {
+            const long long cyc_in = clock64();
+            __syncthreads();
+            cyc_wait += clock64() - cyc_in;
+        }
     }
 
     // ---------------- E summed from scratch when the running sum may carry too much rounding ----------------
@@ -627,14 +725,15 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
     // ---------------- hand the state back ----------------
     // Mersenne-Twister streams whose current state sits in the scratch buffer go back to the canonical one
     for (int k = 0; k < nm + 2; ++k) {
-        if (M.flip[k]) for (int i = tid; i < 624; i += GC_THREADS) mt[k * MCPYB_GCMC_MT_WORDS + i] = mt2[k * 624 + i];
+        if (M.flip_mask >> k & 1) for (int i = tid; i < 624; i += GC_THREADS) mt[k * MCPYB_GCMC_MT_WORDS + i] = mt2[k * 624 + i];
     }
     if (tid < nm + 2) mt[tid * MCPYB_GCMC_MT_WORDS + 624] = (uint32_t)M.idx[tid];
+    if (tid == 32) D.cyc_rows = cyc_rows;
     if (tid == 0) {
         D.e_scale = e_scale; D.acc_since_resync = acc_since; D.resyncs = resyncs;
         D.s.n_atoms = n; D.n_unstable = n_unst; D.s.energy = E; D.s.best_score = best_score; D.s.best_energy = best_E;
         D.s.best_n = best_n; D.s.last_move = cur_move; D.s.trials_done = t_done; D.trace_len = trace_len;
-        D.cyc_serial = cyc_serial; D.cyc_total = clock64() - cyc_begin; D.rounds = rounds;
+        D.cyc_serial = cyc_serial; D.cyc_total = clock64() - cyc_begin; D.rounds = rounds; D.cyc_pre = cyc_pre; D.cyc_wait = cyc_wait;
         for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k)
             for (int j = 0; j < 4; ++j) D.s.pcg[k][j] = s_pcg[k][j];
         for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k) { D.s.attempts[k] = s_cnt[0][k]; D.s.accepted[k] = s_cnt[1][k]; D.s.failed[k] = s_cnt[2][k]; }
@@ -643,7 +742,10 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
     if (C.in_smem) {
         uint4* dst = reinterpret_cast<uint4*>(C.blob);
         const uint4* src = reinterpret_cast<const uint4*>(gc_smem);
-        for (int i = tid; i < lay.bytes / 16; i += GC_THREADS) dst[i] = src[i];
+        for (int i = tid; i < lay.mt / 16; i += GC_THREADS) dst[i] = src[i];
+        dst = reinterpret_cast<uint4*>(C.slot);
+        src = reinterpret_cast<const uint4*>(gc_smem + lay.mt);
+        for (int i = tid; i < (lay.bytes - lay.mt) / 16; i += GC_THREADS) dst[i] = src[i];
     }
 }
 
@@ -658,8 +760,7 @@ struct mcpyb_gcmc {
     GcChain* d_chains = nullptr;
     GcDyn* d_dyn = nullptr;
     long long* d_ntr = nullptr;
-    unsigned char* d_swap = nullptr;      // scratch of mcpyb_gcmc_swap_configurations
-    size_t swap_bytes = 0;
+    bool dirty = false;                   // host copies of chains / dyn are ahead of the device's (a swap)
     size_t smem = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
@@ -726,7 +827,8 @@ int mcpyb_gcmc_create(mcpyb_engine* e, int n_chains, const mcpyb_gcmc_desc* desc
         C.lay = gc_layout(C.acap, C.ncells, C.ccap, C.nmt);
         C.in_smem = (size_t)C.lay.bytes + 4096 <= (size_t)optin;
         if (C.in_smem && (size_t)C.lay.bytes > g->smem) g->smem = C.lay.bytes;
-        if (cudaMalloc(&C.blob, C.lay.bytes) != cudaSuccess) return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: cudaMalloc state"));
+        if (cudaMalloc(&C.blob, C.lay.mt) != cudaSuccess || cudaMalloc(&C.slot, C.lay.bytes - C.lay.mt) != cudaSuccess)
+            return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: cudaMalloc state"));
         if (cudaMalloc(&C.best_pos, sizeof(double) * 3 * C.acap) != cudaSuccess) return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: cudaMalloc best"));
         C.trace_cap = trace_capacity > 0 ? trace_capacity : 0;
         if (C.trace_cap && cudaMalloc(&C.trace, sizeof(mcpyb_gcmc_trial) * C.trace_cap) != cudaSuccess) return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: cudaMalloc trace"));
@@ -749,11 +851,10 @@ void mcpyb_gcmc_destroy(mcpyb_gcmc* g) {
     if (!g) return;
     cudaSetDevice(g->e->device);
     cudaStreamSynchronize(g->e->stream);
-    for (auto& C : g->chains) { if (C.blob) cudaFree(C.blob); if (C.best_pos) cudaFree(C.best_pos); if (C.trace) cudaFree(C.trace); }
+    for (auto& C : g->chains) { if (C.blob) cudaFree(C.blob); if (C.slot) cudaFree(C.slot); if (C.best_pos) cudaFree(C.best_pos); if (C.trace) cudaFree(C.trace); }
     if (g->d_chains) cudaFree(g->d_chains);
     if (g->d_dyn) cudaFree(g->d_dyn);
     if (g->d_ntr) cudaFree(g->d_ntr);
-    if (g->d_swap) cudaFree(g->d_swap);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     delete g;
@@ -805,7 +906,13 @@ int mcpyb_gcmc_set_state(mcpyb_gcmc* g, int chain, const double* positions, cons
     D.n_unstable = n;
     D.e_scale = fabs(s->energy);             // the caller's energy is a full sum
     D.acc_since_resync = 0;
-    CK(cudaMemcpyAsync(C.blob, blob.data(), C.lay.bytes, cudaMemcpyHostToDevice, e->stream), "gcmc upload state");
+    if (g->dirty) {                          // swapped chains first: the descriptors below must not be overwritten later
+        CK(cudaMemcpyAsync(g->d_chains, g->chains.data(), sizeof(GcChain) * g->n, cudaMemcpyHostToDevice, e->stream), "gcmc upload descriptors");
+        CK(cudaMemcpyAsync(g->d_dyn, g->dyn.data(), sizeof(GcDyn) * g->n, cudaMemcpyHostToDevice, e->stream), "gcmc upload scalars");
+        g->dirty = false;
+    }
+    CK(cudaMemcpyAsync(C.blob, blob.data(), C.lay.mt, cudaMemcpyHostToDevice, e->stream), "gcmc upload state");
+    CK(cudaMemcpyAsync(C.slot, blob.data() + C.lay.mt, C.lay.bytes - C.lay.mt, cudaMemcpyHostToDevice, e->stream), "gcmc upload state");
     CK(cudaMemcpyAsync(g->d_dyn + chain, &D, sizeof(GcDyn), cudaMemcpyHostToDevice, e->stream), "gcmc upload scalars");
     CK(cudaStreamSynchronize(e->stream), "gcmc set_state sync");
     return MCPYB_OK;
@@ -819,8 +926,9 @@ int mcpyb_gcmc_get_state(mcpyb_gcmc* g, int chain, double* positions_out, mcpyb_
     cudaSetDevice(e->device);
     std::vector<unsigned char> blob(C.lay.bytes);
     GcDyn& D = g->dyn[chain];
-    CK(cudaMemcpyAsync(blob.data(), C.blob, C.lay.bytes, cudaMemcpyDeviceToHost, e->stream), "gcmc download state");
-    CK(cudaMemcpyAsync(&D, g->d_dyn + chain, sizeof(GcDyn), cudaMemcpyDeviceToHost, e->stream), "gcmc download scalars");
+    CK(cudaMemcpyAsync(blob.data(), C.blob, C.lay.mt, cudaMemcpyDeviceToHost, e->stream), "gcmc download state");
+    CK(cudaMemcpyAsync(blob.data() + C.lay.mt, C.slot, C.lay.bytes - C.lay.mt, cudaMemcpyDeviceToHost, e->stream), "gcmc download state");
+    if (!g->dirty) CK(cudaMemcpyAsync(&D, g->d_dyn + chain, sizeof(GcDyn), cudaMemcpyDeviceToHost, e->stream), "gcmc download scalars");
     CK(cudaStreamSynchronize(e->stream), "gcmc get_state sync");
     if (s_out) *s_out = D.s;
     const int n = D.s.n_atoms;
@@ -849,6 +957,11 @@ int mcpyb_gcmc_run(mcpyb_gcmc* g, const int64_t* n_trials, int32_t* status_out) 
     for (int c = 0; c < g->n; ++c) if (n_trials[c] < 0) return e->fail(MCPYB_ERR_ARG, "gcmc run: negative trial count");
     cudaSetDevice(e->device);
     static_assert(sizeof(long long) == sizeof(int64_t), "int64_t");
+    if (g->dirty) {
+        CK(cudaMemcpyAsync(g->d_chains, g->chains.data(), sizeof(GcChain) * g->n, cudaMemcpyHostToDevice, e->stream), "gcmc upload descriptors");
+        CK(cudaMemcpyAsync(g->d_dyn, g->dyn.data(), sizeof(GcDyn) * g->n, cudaMemcpyHostToDevice, e->stream), "gcmc upload scalars");
+        g->dirty = false;
+    }
     CK(cudaMemcpyAsync(g->d_ntr, n_trials, sizeof(long long) * g->n, cudaMemcpyHostToDevice, e->stream), "gcmc upload trial counts");
     CK(cudaEventRecord(g->ev0, e->stream), "event");
     gcmc_chain_kernel<<<g->n, GC_THREADS, g->smem, e->stream>>>(g->d_chains, g->d_dyn, g->d_ntr);
@@ -895,20 +1008,9 @@ int mcpyb_gcmc_swap_configurations(mcpyb_gcmc* g, int i, int j) {
     if (memcmp(&A.lay, &B.lay, sizeof(GcLayout)) != 0 || A.acap != B.acap || A.ccap != B.ccap || A.ncells != B.ncells ||
         memcmp(A.ncell, B.ncell, sizeof A.ncell) != 0 || memcmp(A.d.box, B.d.box, sizeof A.d.box) != 0)
         return e->fail(MCPYB_ERR_CAPACITY, "gcmc swap: chains %d and %d have different boxes or storage layouts", i, j);
-    cudaSetDevice(e->device);
-    const size_t mt_bytes = (size_t)gc_align16(4 * MCPYB_GCMC_MT_WORDS * A.nmt);
-    if (!g->d_swap || g->swap_bytes < mt_bytes) {
-        if (g->d_swap) cudaFree(g->d_swap);
-        g->d_swap = nullptr;
-        if (cudaMalloc(&g->d_swap, mt_bytes) != cudaSuccess) return e->fail(MCPYB_ERR_CUDA, "gcmc swap: cudaMalloc");
-        g->swap_bytes = mt_bytes;
-    }
-    // the state blocks change owner (the configuration, its atom order, cell lists and wrap bookkeeping go with them);
-    // the Mersenne-Twister streams stay with the slot, so they are swapped back
-    cudaStream_t st = e->stream;
-    CK(cudaMemcpyAsync(g->d_swap, A.blob + A.lay.mt, mt_bytes, cudaMemcpyDeviceToDevice, st), "gcmc swap");
-    CK(cudaMemcpyAsync(A.blob + A.lay.mt, B.blob + B.lay.mt, mt_bytes, cudaMemcpyDeviceToDevice, st), "gcmc swap");
-    CK(cudaMemcpyAsync(B.blob + B.lay.mt, g->d_swap, mt_bytes, cudaMemcpyDeviceToDevice, st), "gcmc swap");
+    // the configuration part of the state changes owner (positions, atom order, cell lists, wrap bookkeeping) together
+    // with the energy and the particle number; the slot part (the Mersenne-Twister streams) stays.  Host copies only:
+    // the next mcpyb_gcmc_run / set_state uploads the descriptors and scalars of all chains in two copies.
     std::swap(A.blob, B.blob);
     GcDyn& DA = g->dyn[i];
     GcDyn& DB = g->dyn[j];
@@ -917,11 +1019,7 @@ int mcpyb_gcmc_swap_configurations(mcpyb_gcmc* g, int i, int j) {
     std::swap(DA.n_unstable, DB.n_unstable);
     std::swap(DA.e_scale, DB.e_scale);
     std::swap(DA.acc_since_resync, DB.acc_since_resync);
-    CK(cudaMemcpyAsync(g->d_chains + i, &A, sizeof(GcChain), cudaMemcpyHostToDevice, st), "gcmc swap");
-    CK(cudaMemcpyAsync(g->d_chains + j, &B, sizeof(GcChain), cudaMemcpyHostToDevice, st), "gcmc swap");
-    CK(cudaMemcpyAsync(g->d_dyn + i, &DA, sizeof(GcDyn), cudaMemcpyHostToDevice, st), "gcmc swap");
-    CK(cudaMemcpyAsync(g->d_dyn + j, &DB, sizeof(GcDyn), cudaMemcpyHostToDevice, st), "gcmc swap");
-    CK(cudaStreamSynchronize(st), "gcmc swap");          // the sources are pageable host structs
+    g->dirty = true;
     return MCPYB_OK;
 }
 
@@ -933,11 +1031,12 @@ int mcpyb_gcmc_info(mcpyb_gcmc* g, int chain, int32_t* out6) {
     return MCPYB_OK;
 }
 
-int mcpyb_gcmc_cycles(mcpyb_gcmc* g, int chain, int64_t* out3 /* [4] */) {
+int mcpyb_gcmc_cycles(mcpyb_gcmc* g, int chain, int64_t* out3 /* [7] */) {
     if (!g) return MCPYB_ERR_ARG;
     if (chain < 0 || chain >= g->n || !out3) return g->e->fail(MCPYB_ERR_ARG, "gcmc cycles: bad argument");
     out3[0] = g->dyn[chain].cyc_serial; out3[1] = g->dyn[chain].cyc_total; out3[2] = g->dyn[chain].rounds;
-    out3[3] = g->dyn[chain].resyncs;
+    out3[3] = g->dyn[chain].resyncs; out3[4] = g->dyn[chain].cyc_pre;
+    out3[5] = g->dyn[chain].cyc_rows; out3[6] = g->dyn[chain].cyc_wait;
     return MCPYB_OK;
 }
 

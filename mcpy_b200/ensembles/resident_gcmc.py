@@ -439,9 +439,10 @@ class ResidentGCMC:
 
     def cycles(self, k=0):
         """SM cycles of chain ``k``'s last launch: serial section of thread 0, whole loop, loop trips."""
-        out = (C.c_int64 * 4)()
+        out = (C.c_int64 * 7)()
         self.engine._check(self._lib.mcpyb_gcmc_cycles(self._h, k, out))
-        return {'serial': out[0], 'total': out[1], 'rounds': out[2], 'energy_resyncs': out[3]}
+        return {'serial': out[0], 'total': out[1], 'rounds': out[2], 'energy_resyncs': out[3], 'look_ahead': out[4],
+                'row_sums': out[5], 'wait_for_rows': out[6]}
 
     def close(self):
         if getattr(self, '_h', None):

@@ -44,10 +44,11 @@ class ResidentReplicaExchange(ShardedReplicaExchange):
         step ``self._re_step``; after its step ``s`` it attempts exchanges when ``s > 0 and s % exchange_interval == 0``
         and writes a row when ``s % write_out_interval == 0`` (``batched_replica_exchange.py:153-160``)."""
         step = self._re_step
+        files = [r for r in self.replicas if r._outfile is not None or r._traj_file is not None]
         b = 1
         while True:
             s = step + b - 1
-            frames = [self._file_due(r, r._step + b) for r in self.replicas]
+            frames = [self._file_due(r, r._step + b) for r in files]
             last = s >= self.gcmc_steps - 1
             if last or (s > 0 and s % self.exchange_interval == 0) or s % self.write_out_interval == 0 \
                     or any(o or t for o, t in frames):
@@ -66,11 +67,12 @@ class ResidentReplicaExchange(ShardedReplicaExchange):
         self._ahead -= 1
         for r in self.replicas:                        # the tail of the reference's step (:226-231)
             r._step += 1
-            out_due, traj_due = self._file_due(r, r._step)
-            if out_due:
-                r.write_outfile()
-            if traj_due:
-                r.write_coordinates(r.atoms, r.E_old)
+            if r._outfile is not None or r._traj_file is not None:
+                out_due, traj_due = self._file_due(r, r._step)
+                if out_due:
+                    r.write_outfile()
+                if traj_due:
+                    r.write_coordinates(r.atoms, r.E_old)
 
     # ------------------------------------------------------------------ swaps
     def _swap_states(self, i: int, j: int) -> None:

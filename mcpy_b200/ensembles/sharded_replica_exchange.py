@@ -124,12 +124,24 @@ class ShardedReplicaExchange(BatchedReplicaExchange):
         for k, s in enumerate(self.species):
             # counted for EVERY species of the ladder: the cross terms score this configuration with the
             # neighbour's chemical potentials (`ri._minimum_score(rj.atoms, ...)`, :347-348)
-            rec[2 + k] = r._species_count(r.atoms, s)
+            rec[2 + k] = self._count(r, s)
             rec[2 + 2 * S + k] = r.units.lambda_dbs.get(s, np.nan)
             if s in mu:
                 rec[2 + S + k] = mu[s]
                 rec[2 + 3 * S + k] = 1.0
         return rec
+
+    @staticmethod
+    def _count(r, s) -> int:
+        """``r._species_count(r.atoms, s)`` (``grand_canonical_ensemble.py:176-186``); an atomic species is counted on
+        the atomic numbers instead of a list of 2 000 chemical symbols."""
+        if s in r.units.molecules:
+            return r._species_count(r.atoms, s)
+        try:
+            from ase.data import atomic_numbers
+            return int(np.count_nonzero(r.atoms.numbers == atomic_numbers[s]))
+        except (ImportError, KeyError):
+            return r._species_count(r.atoms, s)
 
     def _gather_records(self) -> np.ndarray:
         """The only collective: all_gather of the per-replica records (``LadderComm.gather_records``)."""

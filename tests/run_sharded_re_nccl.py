@@ -27,7 +27,7 @@ import torch.distributed as dist
 
 from helpers import make_factory
 from mcpy_b200.calculators import B200Calculator
-from mcpy_b200.ensembles import ShardedReplicaExchange
+from mcpy_b200.ensembles import ResidentReplicaExchange, ShardedReplicaExchange
 
 
 def main():
@@ -37,8 +37,17 @@ def main():
     n_rep, steps = 8, 24
     temps = list(np.linspace(1.5, 3.0, n_rep))
     calc = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=3.0, device=local)
-    re = ShardedReplicaExchange(make_factory(calc, fix=(0, 3)), calc, temperatures=temps, gcmc_steps=steps,
-                                exchange_interval=3, seed=31, rank=rank, world_size=world, device=f'cuda:{local}')
+    resident = 'resident' in sys.argv[1:]
+    if resident:
+        # the replicas' trials on the device (a CTA each), swaps of local replicas there too; the boundary replica of an
+        # accepted cross-rank swap comes back to the host and travels as in the sharded driver (no FixAtoms: out of the
+        # resident chains' scope)
+        steps = 40
+        re = ResidentReplicaExchange(make_factory(calc, n_moves=3), calc, temperatures=temps, gcmc_steps=steps,
+                                     exchange_interval=3, seed=31, rank=rank, world_size=world, device=f'cuda:{local}')
+    else:
+        re = ShardedReplicaExchange(make_factory(calc, fix=(0, 3)), calc, temperatures=temps, gcmc_steps=steps,
+                                    exchange_interval=3, seed=31, rank=rank, world_size=world, device=f'cuda:{local}')
     re.run()
     mine = {re.lo + k: (r.E_old, r.n_atoms, r.atoms.positions.copy()) for k, r in enumerate(re.replicas)}
     gathered = [None] * world
@@ -46,8 +55,8 @@ def main():
     ok = True
     if rank == 0:
         calc1 = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=3.0, device=local)
-        ref = ShardedReplicaExchange(make_factory(calc1, fix=(0, 3)), calc1, temperatures=temps, gcmc_steps=steps,
-                                     exchange_interval=3, seed=31, rank=0, world_size=1)
+        ref = ShardedReplicaExchange(make_factory(calc1, n_moves=3) if resident else make_factory(calc1, fix=(0, 3)), calc1,
+                                     temperatures=temps, gcmc_steps=steps, exchange_interval=3, seed=31, rank=0, world_size=1)
         ref.run()
         merged = {}
         for log, st in gathered:
@@ -59,9 +68,12 @@ def main():
         accepted = sum(1 for *_, a in ref.swap_log if a)
         for i, r in enumerate(ref.replicas):
             e, n, p = merged[i]
-            ok = ok and n == r.n_atoms and abs(e - r.E_old) <= 1e-10 * max(1.0, abs(r.E_old)) \
+            ok = ok and n == r.n_atoms and abs(e - r.E_old) <= (1e-9 if resident else 1e-10) * max(1.0, abs(r.E_old)) \
                 and np.array_equal(p, r.atoms.positions)
-        print(f'sharded RE over NCCL: world={world} replicas={n_rep} swaps attempted={len(ref.swap_log)} '
+        cross = sum(1 for _, i, j, _, a in ref.swap_log if a and i == n_rep // world - 1)
+        if resident:
+            ok = ok and cross > 0 and re.blocks < steps
+        print(f'{"resident" if resident else "sharded"} RE over NCCL: world={world} cross_rank_swaps={cross}  replicas={n_rep} swaps attempted={len(ref.swap_log)} '
               f'accepted={accepted} identical_to_single_process={ok}')
     dist.barrier()
     dist.destroy_process_group()

@@ -41,6 +41,16 @@ def test_sharded_replica_exchange_over_nccl_equals_single_process():
 
 
 @pytest.mark.skipif(not _two_gpus(), reason='needs two GPUs')
+def test_resident_replica_exchange_over_nccl_equals_single_process_host_driver():
+    """ResidentReplicaExchange on two ranks (every replica's trials on its GPU, a CTA each; local swaps on the device,
+    the boundary swap shipped over NCCL) against the host-driven single-process run over B200Calculator: same swap
+    decisions, particle numbers and positions, energies to 1e-9."""
+    proc = _torchrun('run_sharded_re_nccl.py', 'resident')
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    assert 'identical_to_single_process=True' in proc.stdout
+
+
+@pytest.mark.skipif(not _two_gpus(), reason='needs two GPUs')
 def test_resident_ladder_shard_over_nccl_equals_single_process():
     """ResidentLadderShard: configurations resident in HBM, ONE all_gather per exchange attempt carrying records and
     boundary configurations; after the exchange rounds every slot holds the configuration, box and energy the
