@@ -535,9 +535,10 @@ def run_b200(args):
             rre._rebatch_initial_energies()
 
             def resident_steps(n):
+                xi = rre.exchange_interval
                 for _ in range(n):
                     rre._batched_gcmc_step()
-                    if rre._re_step > 0 and rre._re_step % XI == 0:
+                    if rre._re_step > 0 and rre._re_step % xi == 0:
                         rre._attempt_exchanges()
                     rre._re_step += 1
             resident_steps(5 * XI)                                   # warm-up: first upload, first exchanges
@@ -552,6 +553,19 @@ def run_b200(args):
             res_s = max_over_ranks(time.perf_counter() - t0)
             barrier()
             launches_resident = rre.blocks - blocks0
+            dev_res = rre.device_ms - dev0
+            # the same run with an exchange attempt every 100 steps: blocks of 100 trials per launch
+            rre.exchange_interval = 10 * XI
+            rre._re_step = 0
+            resident_steps(20 * XI)
+            dev1 = rre.device_ms
+            barrier()
+            t0 = time.perf_counter()
+            resident_steps(n_res)
+            torch.cuda.synchronize()
+            res100_s = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            dev100 = rre.device_ms - dev1
             rre.resident.sync_host()
             # one chain alone: what a single GrandCanonicalEnsemble run gets (ResidentGCMC.run_trials)
             one = ResidentGCMC([factory(mu={'H': float(mus[0])}, rank=rank * R)], engine=eng)
@@ -566,9 +580,12 @@ def run_b200(args):
                 'value': world * R * n_res / res_s, 'unit': 'replica trial-move dE evals/s (whole trials: proposal, dE, '
                                                              'acceptance, commit)',
                 'steps': n_res, 'trials_per_replica': n_res, 'wall_s': res_s,
-                'device_ms': rre.device_ms - dev0, 'launches': launches_resident,
-                'us_per_trial_per_replica_device': 1e3 * (rre.device_ms - dev0) / n_res,
-                'host_share': 1.0 - 1e-3 * (rre.device_ms - dev0) / res_s,
+                'device_ms': dev_res, 'launches': launches_resident,
+                'us_per_trial_per_replica_device': 1e3 * dev_res / n_res,
+                'host_share': 1.0 - 1e-3 * dev_res / res_s,
+                'exchange_every_100_steps': {'value': world * R * n_res / res100_s, 'wall_s': res100_s, 'device_ms': dev100,
+                                             'us_per_trial_per_replica_device': 1e3 * dev100 / n_res,
+                                             'host_share': 1.0 - 1e-3 * dev100 / res100_s},
                 'exchange_attempts': (rre.comm.gathers - g0r) if world > 1 else n_res // XI,
                 'accepted_swaps': sum(rre.global_successes) - swaps0,
                 'collective_us_per_exchange': 1e6 * (rre.comm.collective_seconds - c0r) / max(1, rre.comm.gathers - g0r),

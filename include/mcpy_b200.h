@@ -361,13 +361,15 @@ int mcpyb_gcmc_swap_configurations(mcpyb_gcmc* g, int i, int j);
 int mcpyb_gcmc_get_trace(mcpyb_gcmc* g, int chain, mcpyb_gcmc_trial* out, int64_t capacity, int64_t* n_out);
 /* cell list geometry chosen for a chain: cells per axis, slots per cell, bytes of state, 1 if it lives in shared memory */
 int mcpyb_gcmc_info(mcpyb_gcmc* g, int chain, int32_t* out6);
-/* out7[0..2]: SM cycles of a chain's last launch -- thread 0's serial section (acceptance, commit, the part of the
+/* out8[0..2]: SM cycles of a chain's last launch -- thread 0's serial section (acceptance, commit, the part of the
  * next proposal that was not drawn ahead), the whole trial loop, loop trips: what the serial Markov chain costs next to
- * the CTA-wide row sums.  out7[4]: cycles thread 0 spent drawing the next proposal ahead, behind the row sums.
- * out7[3]: how often the chain's running energy was replaced by a full sum over its configuration (done at the end of a
+ * the CTA-wide row sums.  out8[4]: cycles thread 0 spent drawing the next proposal ahead, behind the row sums.
+ * out8[3]: how often the chain's running energy was replaced by a full sum over its configuration (done at the end of a
  * launch when accepted moves x 2^-53 x max |E| since the last full sum exceeds 1e-12 max(1, |E|)).
- * out7[5]: cycles of the row sums (first evaluator thread); out7[6]: cycles thread 0 waited for them.  */
-int mcpyb_gcmc_cycles(mcpyb_gcmc* g, int chain, int64_t* out7);
+ * out8[5]: cycles of the row sums (first evaluator thread); out8[6]: thread 0 from the end of its look-ahead to its next
+ * serial section (waiting for the row sums + the barrier); out8[7]: from the end of a serial section to the look-ahead
+ * (the barrier that releases the evaluator).  */
+int mcpyb_gcmc_cycles(mcpyb_gcmc* g, int chain, int64_t* out8);
 /* device time of the last mcpyb_gcmc_run launch (CUDA events on the engine's stream) */
 int mcpyb_gcmc_last_run_ms(mcpyb_gcmc* g, double* ms_out);
 

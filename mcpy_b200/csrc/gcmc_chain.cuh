@@ -57,7 +57,8 @@ struct GcDyn {                    // read-write scalars of one chain
     long long trace_len;
     long long cyc_serial, cyc_total, rounds;    // of the last launch: thread 0's serial section, the whole loop, loop trips
     long long cyc_pre;                          // ... and thread 0's look-ahead proposals (hidden behind the row sums)
-    long long cyc_rows, cyc_wait;               // the row sums (first row thread), thread 0 waiting for them
+    long long cyc_rows, cyc_wait;               // the row sums (first row thread); thread 0: end of look-ahead -> next serial section
+    long long cyc_gap1;                         // thread 0: end of serial section -> start of look-ahead
     long long acc_since_resync;                 // accepted moves added onto E since it was last summed from scratch
     long long resyncs;
     double e_scale;                             // max |E| since then: bounds the rounding carried by E
@@ -320,6 +321,7 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
             for (int j = 0; j < 4; ++j) s_pcg[k][j] = D.s.pcg[k][j];
         for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k) { s_cnt[0][k] = D.s.attempts[k]; s_cnt[1][k] = D.s.accepted[k]; s_cnt[2][k] = D.s.failed[k]; }
         T.done = 0; T.par = 0; T.nsites = 0; T.refill = 0; T.resync = 0;
+        for (int a = 0; a < 2; ++a) { T.sx[a] = T.sy[a] = T.sz[a] = 0.0; T.sign[a] = 0.0; T.home[a][0] = T.home[a][1] = T.home[a][2] = 0; }
         D.s.status = MCPYB_GCMC_DONE;
         M.a = mt; M.b = mt2;
         for (int k = 0; k < nm + 2; ++k) { M.idx[k] = (int)mt[k * MCPYB_GCMC_MT_WORDS + 624]; M.cur[k] = mt + k * MCPYB_GCMC_MT_WORDS; }
@@ -328,11 +330,12 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
     }
     __syncthreads();                                        // (the state block, s_d and the stencil table are in place)
 
-    long long cyc_serial = 0, rounds = 0, cyc_pre = 0, cyc_rows = 0, cyc_wait = 0;
+    long long cyc_serial = 0, rounds = 0, cyc_pre = 0, cyc_rows = 0, cyc_wait = 0, cyc_gap1 = 0, mark_serial_end = 0, mark_pre_end = 0;
     const long long cyc_begin = clock64();
     while (true) {
         if (tid == 0) {
             const long long cyc_in = clock64();
+            if (mark_pre_end) { cyc_wait += cyc_in - mark_pre_end; mark_pre_end = 0; }
             // ---------------- the Markov chain proper (serial) ----------------
             bool proposing = true;
             if (T.refill) { M.ready_mask |= T.refill; T.refill = 0; }   // completed by the CTA in the last parallel section
@@ -535,7 +538,8 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                 break;
             }
             if (!T.done) T.refill = ~M.ready_mask & all_streams;
-            cyc_serial += clock64() - cyc_in;
+            mark_serial_end = clock64();
+            cyc_serial += mark_serial_end - cyc_in;
             ++rounds;
         }
         __syncthreads();
@@ -625,6 +629,7 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
             // so what the next proposal draws is known now -- except that an index is drawn below n, which the running
             // trial may change.  Drawn for the current n; used only if n is still that (or not needed) when it is its turn.
             const long long cyc_in = clock64();
+            cyc_gap1 += cyc_in - mark_serial_end;
             pre.valid = 0;
             const uint32_t* s0 = gc_mt_cur(M, 0) + M.idx[0];
             if (t_done + 1 < t_goal && !pending && M.idx[0] + 2 <= 624) {
@@ -664,13 +669,10 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                     }
                 }
             }
-            cyc_pre += clock64() - cyc_in;
+            mark_pre_end = clock64();
+            cyc_pre += mark_pre_end - cyc_in;
         }
-        {
-            const long long cyc_in = clock64();
-            __syncthreads();
-            cyc_wait += clock64() - cyc_in;
-        }
+        __syncthreads();
     }
 
     // ---------------- E summed from scratch when the running sum may carry too much rounding ----------------
@@ -733,7 +735,7 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
         D.e_scale = e_scale; D.acc_since_resync = acc_since; D.resyncs = resyncs;
         D.s.n_atoms = n; D.n_unstable = n_unst; D.s.energy = E; D.s.best_score = best_score; D.s.best_energy = best_E;
         D.s.best_n = best_n; D.s.last_move = cur_move; D.s.trials_done = t_done; D.trace_len = trace_len;
-        D.cyc_serial = cyc_serial; D.cyc_total = clock64() - cyc_begin; D.rounds = rounds; D.cyc_pre = cyc_pre; D.cyc_wait = cyc_wait;
+        D.cyc_serial = cyc_serial; D.cyc_total = clock64() - cyc_begin; D.rounds = rounds; D.cyc_pre = cyc_pre; D.cyc_wait = cyc_wait; D.cyc_gap1 = cyc_gap1;
         for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k)
             for (int j = 0; j < 4; ++j) D.s.pcg[k][j] = s_pcg[k][j];
         for (int k = 0; k < MCPYB_GCMC_MAX_MOVES; ++k) { D.s.attempts[k] = s_cnt[0][k]; D.s.accepted[k] = s_cnt[1][k]; D.s.failed[k] = s_cnt[2][k]; }
@@ -1031,12 +1033,12 @@ int mcpyb_gcmc_info(mcpyb_gcmc* g, int chain, int32_t* out6) {
     return MCPYB_OK;
 }
 
-int mcpyb_gcmc_cycles(mcpyb_gcmc* g, int chain, int64_t* out3 /* [7] */) {
+int mcpyb_gcmc_cycles(mcpyb_gcmc* g, int chain, int64_t* out3 /* [8] */) {
     if (!g) return MCPYB_ERR_ARG;
     if (chain < 0 || chain >= g->n || !out3) return g->e->fail(MCPYB_ERR_ARG, "gcmc cycles: bad argument");
     out3[0] = g->dyn[chain].cyc_serial; out3[1] = g->dyn[chain].cyc_total; out3[2] = g->dyn[chain].rounds;
     out3[3] = g->dyn[chain].resyncs; out3[4] = g->dyn[chain].cyc_pre;
-    out3[5] = g->dyn[chain].cyc_rows; out3[6] = g->dyn[chain].cyc_wait;
+    out3[5] = g->dyn[chain].cyc_rows; out3[6] = g->dyn[chain].cyc_wait; out3[7] = g->dyn[chain].cyc_gap1;
     return MCPYB_OK;
 }
 

@@ -141,6 +141,9 @@ class ResidentGCMC:
         self._counted = [[[0] * GCMC_MAX_MOVES for _ in range(3)] for _ in range(n)]   # device counters already added on the host
         self._trials_seen = [0] * n
         self._gauss = {}
+        self._scalars = GcmcScalars()              # scratch of _apply_scalars
+        self._scalars_ref = C.byref(self._scalars)
+        self._storage_sig = None
         self.last_status = [0] * n
         self.trials_run = 0
 
@@ -231,13 +234,14 @@ class ResidentGCMC:
             self._trials_seen[k] = 0
 
     # ------------------------------------------------------------------ device -> host objects
-    def _apply_scalars(self, k):
+    def _apply_scalars(self, k, counters=True):
         """What the drivers read between blocks: ``E_old``, ``n_atoms`` (and an ``Atoms`` of that length), the
         selector's counters and ``to_use``, the running-minimum scores.  Positions and generator states stay on the
-        device until :meth:`sync_host`; the host ``positions`` are NaN meanwhile."""
+        device until :meth:`sync_host`; the host ``positions`` are NaN meanwhile.  ``counters=False`` leaves the
+        selector's counters for later (the device's are cumulative since the upload, so nothing is lost)."""
         g = self.ensembles[k]
-        s = GcmcScalars()
-        self.engine._check(self._lib.mcpyb_gcmc_get_scalars(self._h, k, C.byref(s)))
+        s = self._scalars
+        self.engine._check(self._lib.mcpyb_gcmc_get_scalars(self._h, k, self._scalars_ref))
         n = int(s.n_atoms)
         atoms = g.atoms
         if self._host_fresh[k] or len(atoms) != n:
@@ -245,7 +249,12 @@ class ResidentGCMC:
                             'positions': np.full((n, 3), np.nan)}
         self._host_fresh[k] = False
         g.n_atoms = n
-        g.E_old = float(s.energy)
+        g.E_old = s.energy
+        if s.best_n >= 0:                                              # improved since the upload
+            g._best_score = s.best_score
+            g._best_energy = s.best_energy
+        if not counters:
+            return s
         ms = g.move_selector
         ms.to_use = int(s.last_move)
         seen = self._counted[k]
@@ -258,9 +267,6 @@ class ResidentGCMC:
                     interval[m] += d
                     total[m] += d
                     seen[c][m] += d
-        if s.best_n >= 0:                                              # improved since the upload
-            g._best_score = float(s.best_score)
-            g._best_energy = float(s.best_energy)
         return s
 
     def sync_host(self, chains=None):
@@ -315,12 +321,14 @@ class ResidentGCMC:
         return False
 
     def _same_storage(self, i, j):
-        a, b = self._desc[i], self._desc[j]
-        return (a.atom_capacity == b.atom_capacity and list(a.box) == list(b.box) and a.lj_rc == b.lj_rc
-                and a.n_move_types == b.n_move_types and self.info(i) == self.info(j))
+        sig = self._storage_sig
+        if sig is None:                                                # per chain: what must agree for a pointer swap
+            sig = self._storage_sig = [(d.atom_capacity, tuple(d.box), d.lj_rc, d.n_move_types, tuple(sorted(self.info(k).items())))
+                                       for k, d in enumerate(self._desc)]
+        return sig[i] == sig[j]
 
     # ------------------------------------------------------------------ running
-    def advance(self, n_trials, sync='full'):
+    def advance(self, n_trials, sync='full', counters=True):
         """Advance every chain by ``n_trials`` trials (an int, or one count per chain) in as few launches as the
         capacities allow.  ``sync='full'`` writes the whole state back into the ensembles; ``sync='scalars'`` only what
         the drivers read between blocks (:meth:`_apply_scalars`) and leaves the rest on the device for the next block.
@@ -342,7 +350,7 @@ class ResidentGCMC:
             total_ms += ms.value
             done = np.empty(n, dtype=np.int64)
             for k in range(n):
-                s = self._apply_scalars(k)
+                s = self._apply_scalars(k, counters)
                 done[k] = int(s.trials_done) - self._trials_seen[k]
                 self._trials_seen[k] = int(s.trials_done)
             if self.trace_capacity:
@@ -430,6 +438,7 @@ class ResidentGCMC:
         self._h = h
         self._device_fresh = [False] * len(self.ensembles)
         self._trials_seen = [0] * len(self.ensembles)
+        self._storage_sig = None
 
     def info(self, k=0):
         out = (C.c_int32 * 6)()
@@ -439,10 +448,10 @@ class ResidentGCMC:
 
     def cycles(self, k=0):
         """SM cycles of chain ``k``'s last launch: serial section of thread 0, whole loop, loop trips."""
-        out = (C.c_int64 * 7)()
+        out = (C.c_int64 * 8)()
         self.engine._check(self._lib.mcpyb_gcmc_cycles(self._h, k, out))
         return {'serial': out[0], 'total': out[1], 'rounds': out[2], 'energy_resyncs': out[3], 'look_ahead': out[4],
-                'row_sums': out[5], 'wait_for_rows': out[6]}
+                'row_sums': out[5], 'look_ahead_to_serial': out[6], 'serial_to_look_ahead': out[7]}
 
     def close(self):
         if getattr(self, '_h', None):

@@ -29,6 +29,8 @@ class ResidentReplicaExchange(ShardedReplicaExchange):
                 engine = getattr(self.calculator, 'engine', None)
             self.resident = ResidentGCMC(self.replicas, engine=engine, lj=lj, atom_capacity=atom_capacity,
                                          cell_capacity=cell_capacity)
+        import numpy as np
+        self._trials_per_step = np.array([r.move_selector.n_moves for r in self.replicas], dtype=np.int64)
         self._ahead = 0                    # steps the device is ahead of the run loop's step counter
         self.device_ms = 0.0               # device time of the chain launches
         self.blocks = 0
@@ -60,8 +62,10 @@ class ResidentReplicaExchange(ShardedReplicaExchange):
             return
         if self._ahead == 0:
             b, full = self._block()
-            self.device_ms += self.resident.advance([b * r.move_selector.n_moves for r in self.replicas],
-                                                    sync='full' if full else 'scalars')
+            # the selector's counters are only read by a replica's own outfile rows (and after the run)
+            counters = full or any(r._outfile is not None for r in self.replicas)
+            self.device_ms += self.resident.advance(self._trials_per_step * b if b > 1 else self._trials_per_step,
+                                                    sync='full' if full else 'scalars', counters=counters)
             self._ahead = b
             self.blocks += 1
         self._ahead -= 1
