@@ -544,6 +544,7 @@ def run_b200(args):
             resident_steps(5 * XI)                                   # warm-up: first upload, first exchanges
             g0r, c0r = rre.comm.gathers, rre.comm.collective_seconds
             dev0, blocks0 = rre.device_ms, rre.blocks
+            rre.resident.sync_host()                                 # (the selector's counters come back with a full sync)
             acc0 = sum(sum(r.move_selector.move_acceptance_total) for r in rre.replicas)
             swaps0 = sum(rre.global_successes)
             barrier()
@@ -554,6 +555,10 @@ def run_b200(args):
             barrier()
             launches_resident = rre.blocks - blocks0
             dev_res = rre.device_ms - dev0
+            swaps_res = sum(rre.global_successes) - swaps0
+            rre.resident.sync_host()
+            moves_res = sum(sum(r.move_selector.move_acceptance_total) for r in rre.replicas) - acc0
+            gathers_res, coll_res = rre.comm.gathers - g0r, rre.comm.collective_seconds - c0r
             # the same run with an exchange attempt every 100 steps: blocks of 100 trials per launch
             rre.exchange_interval = 10 * XI
             rre._re_step = 0
@@ -586,10 +591,10 @@ def run_b200(args):
                 'exchange_every_100_steps': {'value': world * R * n_res / res100_s, 'wall_s': res100_s, 'device_ms': dev100,
                                              'us_per_trial_per_replica_device': 1e3 * dev100 / n_res,
                                              'host_share': 1.0 - 1e-3 * dev100 / res100_s},
-                'exchange_attempts': (rre.comm.gathers - g0r) if world > 1 else n_res // XI,
-                'accepted_swaps': sum(rre.global_successes) - swaps0,
-                'collective_us_per_exchange': 1e6 * (rre.comm.collective_seconds - c0r) / max(1, rre.comm.gathers - g0r),
-                'accepted_moves': sum(sum(r.move_selector.move_acceptance_total) for r in rre.replicas) - acc0,
+                'exchange_attempts': gathers_res if world > 1 else n_res // XI,
+                'accepted_swaps': swaps_res,
+                'collective_us_per_exchange': 1e6 * coll_res / max(1, gathers_res),
+                'accepted_moves': moves_res,
                 'speedup_vs_driver': (world * R * n_res / res_s) / driver['value'] if driver else None,
                 'single_chain': {'trials': args.resident_chain_trials, 'device_trials_per_s': args.resident_chain_trials / (1e-3 * one_ms),
                                  'wall_trials_per_s': args.resident_chain_trials / one_wall,
