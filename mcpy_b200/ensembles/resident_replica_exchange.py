@@ -21,14 +21,16 @@ from .sharded_replica_exchange import ShardedReplicaExchange
 
 
 class ResidentReplicaExchange(ShardedReplicaExchange):
+    chains_class = ResidentGCMC            # what advances the local replicas (the CPU tests put a host stand-in here)
+
     def __init__(self, *args, lj=None, engine=None, atom_capacity=None, cell_capacity=0, **kw):
         super().__init__(*args, **kw)
         self.resident = None
         if self.replicas:
             if engine is None:
                 engine = getattr(self.calculator, 'engine', None)
-            self.resident = ResidentGCMC(self.replicas, engine=engine, lj=lj, atom_capacity=atom_capacity,
-                                         cell_capacity=cell_capacity)
+            self.resident = self.chains_class(self.replicas, engine=engine, lj=lj, atom_capacity=atom_capacity,
+                                              cell_capacity=cell_capacity)
         import numpy as np
         self._trials_per_step = np.array([r.move_selector.n_moves for r in self.replicas], dtype=np.int64)
         self._ahead = 0                    # steps the device is ahead of the run loop's step counter
