@@ -111,7 +111,12 @@ int mcpyb_potential_energies_host(mcpyb_engine* e, int R, const int64_t* atom_of
  * returns E_base + dE(base -> incoming); it re-bases (full evaluation) when more than a few atoms
  * differ or the box changes.  Same result as mcpyb_potential_energies_host to rounding (one full
  * evaluation plus one delta, no drift).  *path_out (may be NULL): 0 full, 1 incremental,
- * 2 identical to the base.  Any mcpyb_upload_* call resets the tracker.                        */
+ * 2 identical to the base.  Any mcpyb_upload_* call resets the tracker.
+ * Alignment bound: a row of the incoming configuration whose three coordinates are within 1e-10 A of a
+ * base row of the same species counts as that row unchanged, and the answer is the energy with the BASE's
+ * coordinates for it: an error of at most |F_i| x 1.7e-10 A per such row (~1e-10 eV for forces of order
+ * 1 eV/A; ASE's own wrap() moves atoms by ulps, far below this).  A displacement smaller than 1e-10 A is
+ * therefore scored as no move; the trial-move kernels (mcpyb_trial_delta_e_*) have no such threshold.   */
 int mcpyb_tracked_energy_host(mcpyb_engine* e, const double* positions, const int32_t* numbers,
                               int n, const double* cell9, const uint8_t* pbc3,
                               double* energy_out, int* path_out);
@@ -358,6 +363,13 @@ int mcpyb_gcmc_get_scalars(mcpyb_gcmc* g, int chain, mcpyb_gcmc_scalars* s_out);
  * device: configuration, energy and particle number change slots; generators, counters, the running minimum,
  * temperature and chemical potential stay.  MCPYB_ERR_CAPACITY when the chains' boxes or storage layouts differ. */
 int mcpyb_gcmc_swap_configurations(mcpyb_gcmc* g, int i, int j);
+/* A swap across two processes without the host (ReplicaExchange's sendrecv of atoms, replica_exchange.py:188-192):
+ * the device address and size of a chain's configuration block (positions by slot, atom order, cell lists, wrap
+ * bookkeeping -- position-independent, so a peer with the same storage layout can take it byte for byte over NCCL) and
+ * the five scalars that go with it {energy, atoms, unsettled atoms, max |E| since the last full sum, accepted moves since
+ * then}; set_config_scalars installs the scalars that came with a received block.  Valid between two launches.  */
+int mcpyb_gcmc_config_ptr(mcpyb_gcmc* g, int chain, void** dev_ptr, int64_t* bytes, double* scalars5);
+int mcpyb_gcmc_set_config_scalars(mcpyb_gcmc* g, int chain, const double* scalars5);
 int mcpyb_gcmc_get_trace(mcpyb_gcmc* g, int chain, mcpyb_gcmc_trial* out, int64_t capacity, int64_t* n_out);
 /* cell list geometry chosen for a chain: cells per axis, slots per cell, bytes of state, 1 if it lives in shared memory */
 int mcpyb_gcmc_info(mcpyb_gcmc* g, int chain, int32_t* out6);

@@ -1025,6 +1025,34 @@ int mcpyb_gcmc_swap_configurations(mcpyb_gcmc* g, int i, int j) {
     return MCPYB_OK;
 }
 
+int mcpyb_gcmc_config_ptr(mcpyb_gcmc* g, int chain, void** dev_ptr, int64_t* bytes, double* scalars5) {
+    if (!g) return MCPYB_ERR_ARG;
+    if (chain < 0 || chain >= g->n || !dev_ptr || !bytes) return g->e->fail(MCPYB_ERR_ARG, "gcmc config_ptr: bad argument");
+    const GcChain& C = g->chains[chain];
+    *dev_ptr = C.blob;
+    *bytes = C.lay.mt;
+    if (scalars5) {
+        const GcDyn& D = g->dyn[chain];
+        scalars5[0] = D.s.energy; scalars5[1] = (double)D.s.n_atoms; scalars5[2] = (double)D.n_unstable;
+        scalars5[3] = D.e_scale; scalars5[4] = (double)D.acc_since_resync;
+    }
+    return MCPYB_OK;
+}
+
+int mcpyb_gcmc_set_config_scalars(mcpyb_gcmc* g, int chain, const double* scalars5) {
+    if (!g) return MCPYB_ERR_ARG;
+    mcpyb_engine* e = g->e;
+    if (chain < 0 || chain >= g->n || !scalars5) return e->fail(MCPYB_ERR_ARG, "gcmc set_config_scalars: bad argument");
+    const GcChain& C = g->chains[chain];
+    const int n = (int)scalars5[1], nu = (int)scalars5[2];
+    if (n < 0 || n >= C.acap || nu < 0 || nu > n) return e->fail(MCPYB_ERR_ARG, "gcmc set_config_scalars: %d atoms (%d unsettled) do not fit chain %d", n, nu, chain);
+    GcDyn& D = g->dyn[chain];
+    D.s.energy = scalars5[0]; D.s.n_atoms = n; D.n_unstable = nu;
+    D.e_scale = scalars5[3]; D.acc_since_resync = (long long)scalars5[4];
+    g->dirty = true;
+    return MCPYB_OK;
+}
+
 int mcpyb_gcmc_info(mcpyb_gcmc* g, int chain, int32_t* out6) {
     if (!g) return MCPYB_ERR_ARG;
     if (chain < 0 || chain >= g->n || !out6) return g->e->fail(MCPYB_ERR_ARG, "gcmc info: bad argument");

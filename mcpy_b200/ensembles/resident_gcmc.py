@@ -144,6 +144,7 @@ class ResidentGCMC:
         self._scalars = GcmcScalars()              # scratch of _apply_scalars
         self._scalars_ref = C.byref(self._scalars)
         self._storage_sig = None
+        self._recv_block = None
         self.last_status = [0] * n
         self.trials_run = 0
 
@@ -319,6 +320,60 @@ class ResidentGCMC:
             return True
         self.sync_host([i, j])
         return False
+
+    # ------------------------------------------------------------------ swaps across two processes, device to device
+    class _DeviceBytes:
+        """``__cuda_array_interface__`` over a device address (what ``torch.as_tensor`` needs to wrap it)."""
+
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {'shape': (int(nbytes),), 'typestr': '|u1', 'data': (int(ptr), False),
+                                             'version': 2, 'strides': None}
+
+    def config_block(self, k):
+        """(device address, bytes, the five scalars that go with it) of chain ``k``'s configuration block."""
+        ptr, nbytes = C.c_void_p(), C.c_int64(0)
+        sc = (C.c_double * 5)()
+        self.engine._check(self._lib.mcpyb_gcmc_config_ptr(self._h, int(k), C.byref(ptr), C.byref(nbytes), sc))
+        return ptr.value, nbytes.value, list(sc)
+
+    def remote_swap(self, k, comm, peer):
+        """Swap chain ``k``'s configuration with a chain of rank ``peer`` (which calls this too) without passing
+        through the host: a 12-number header each way (can this side do it, storage layout, the scalars of the
+        configuration), then the configuration blocks themselves, device to device over ``comm`` (NCCL).  Returns
+        False -- on BOTH sides, both see both headers -- when either side cannot (its chain is not device-fresh, its
+        ``Atoms`` carries ``info`` the block does not hold, the layouts differ): the caller then ships the ``Atoms``."""
+        import torch
+        g = self.ensembles[k]
+        dev = torch.device(comm.device)
+        able = bool(self._device_fresh[k]) and not g.atoms.info
+        ptr, nbytes, sc = self.config_block(k)
+        d = self._desc[k]
+        info = self.info(k)
+        mine = torch.tensor([1.0 if able else 0.0, float(nbytes), float(d.atom_capacity), float(info['cell_capacity']),
+                             float(d.box[0]), float(d.box[1]), float(d.box[2])] + sc, dtype=torch.float64, device=dev)
+        theirs = torch.zeros_like(mine)
+        comm.exchange([(mine, peer)], [(theirs, peer)])
+        mine_h, theirs_h = mine.cpu().numpy(), theirs.cpu().numpy()
+        if not (mine_h[0] == 1.0 and theirs_h[0] == 1.0 and np.array_equal(mine_h[1:7], theirs_h[1:7])):
+            comm.transports -= 1
+            return False
+        block = torch.as_tensor(self._DeviceBytes(ptr, nbytes), device=dev)
+        if self._recv_block is None or self._recv_block.numel() != nbytes:
+            self._recv_block = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        comm.exchange([(block, peer)], [(self._recv_block, peer)])
+        comm.transports -= 1                                   # one state transport, two grouped calls
+        block.copy_(self._recv_block)
+        torch.cuda.current_stream(dev).synchronize()
+        got = (C.c_double * 5)(*theirs_h[7:12].tolist())
+        self.engine._check(self._lib.mcpyb_gcmc_set_config_scalars(self._h, int(k), got))
+        # the ensemble: what ShardedReplicaExchange._swap_states sets from the peer's payload
+        n = int(theirs_h[8])
+        atoms = g.atoms
+        atoms.arrays = {'numbers': np.full(n, self._Z[k], dtype=atoms.arrays['numbers'].dtype),
+                        'positions': np.full((n, 3), np.nan)}
+        g.E_old, g.n_atoms = float(theirs_h[7]), n
+        self._host_fresh[k] = False
+        return True
 
     def _same_storage(self, i, j):
         sig = self._storage_sig

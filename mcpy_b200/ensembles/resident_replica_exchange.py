@@ -9,7 +9,9 @@ the next step at which the host looks at them: an exchange attempt, a row of the
 replica's own outfile row or trajectory frame, the end of the run.  Between two such steps only ``E_old``,
 ``n_atoms`` and the selector's counters come back; positions and generator states stay on the device, and an accepted
 swap of two local replicas exchanges their configurations there (``mcpyb_gcmc_swap_configurations``).  A swap across
-two ranks brings the one boundary replica back to the host and ships it as ``ShardedReplicaExchange`` does.
+two ranks sends the boundary replica's configuration block device to device over NCCL (``ResidentGCMC.remote_swap``)
+when both sides hold the same storage layout; otherwise the replica comes back to the host and travels as a whole
+``Atoms`` as in ``ShardedReplicaExchange``.
 
 Each replica draws, accepts and rejects exactly as under the reference driver (``tests/test_gpu_resident_gcmc.py``
 runs the two side by side).  The replicas must be in ``ResidentGCMC``'s scope (``resident_gcmc.supports``).
@@ -35,6 +37,7 @@ class ResidentReplicaExchange(ShardedReplicaExchange):
         self._trials_per_step = np.array([r.move_selector.n_moves for r in self.replicas], dtype=np.int64)
         self._ahead = 0                    # steps the device is ahead of the run loop's step counter
         self.device_ms = 0.0               # device time of the chain launches
+        self.device_swaps = 0              # cross-rank swaps that went device to device
         self.blocks = 0
 
     # ------------------------------------------------------------------ blocks of steps
@@ -87,8 +90,15 @@ class ResidentReplicaExchange(ShardedReplicaExchange):
             if oi == self.rank and oj == self.rank:
                 self.resident.swap_configurations(i - self.lo, j - self.lo)
             elif self.rank in (oi, oj):
+                mine, peer = (i, oj) if self.rank == oi else (j, oi)
+                if self.comm.on_gpu and hasattr(self.resident, 'remote_swap') and \
+                        self.resident.remote_swap(mine - self.lo, self.comm, peer):
+                    self.device_swaps += 1
+                    r = self.local(mine)
+                    r.calculate_cells_volume(r.atoms)
+                    return
                 # the boundary replica travels as a whole Atoms: bring it back first; it is uploaded again afterwards
-                self.resident.sync_host([(i if self.rank == oi else j) - self.lo])
+                self.resident.sync_host([mine - self.lo])
         super()._swap_states(i, j)
 
     def run(self) -> None:

@@ -38,7 +38,7 @@ class OracleEMTCalculator:
         return np.array([self.get_potential_energy(a) for a in atoms_list])
 
 
-def make_factory(calc, L=7.0, n0=24, base_seed=100, fix=(), n_moves=1, extra_mu=None):
+def make_factory(calc, L=7.0, n0=24, base_seed=100, fix=(), n_moves=1, extra_mu=None, origin=True):
     """``gcmc_factory(T=.., rank=..)`` / ``(mu=.., rank=..)`` of the replica drivers: a fresh reference
     ``GrandCanonicalEnsemble`` (own atoms, cell, moves, selector, seeds from ``rank``) in LJ units.
     ``fix``: indices held by an ``ase.constraints.FixAtoms``; ``extra_mu``: ``{rank: mu dict}`` overrides
@@ -53,7 +53,8 @@ def make_factory(calc, L=7.0, n0=24, base_seed=100, fix=(), n_moves=1, extra_mu=
         atoms = Atoms(f'H{n0}', positions=rng.uniform(0.5, L - 0.5, size=(n0, 3)), cell=[L, L, L], pbc=True)
         if len(fix):
             atoms.set_constraint(FixAtoms(indices=list(fix)))
-        atoms.info['origin'] = rank
+        if origin:
+            atoms.info['origin'] = rank
         cell = Cell(atoms, seed=300 + rank)
         moves = [InsertionMove(cell, species=['H'], seed=11 + rank), DeletionMove(cell, species=['H'], seed=12 + rank),
                  DisplacementMove(species=['H'], seed=13 + rank, max_displacement=0.3)]

@@ -38,12 +38,13 @@ def main():
     temps = list(np.linspace(1.5, 3.0, n_rep))
     calc = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=3.0, device=local)
     resident = 'resident' in sys.argv[1:]
+    origin = 'device-swaps' not in sys.argv[1:]      # Atoms.info travels with the whole Atoms only: forces the host path
     if resident:
         # the replicas' trials on the device (a CTA each), swaps of local replicas there too; the boundary replica of an
         # accepted cross-rank swap comes back to the host and travels as in the sharded driver (no FixAtoms: out of the
         # resident chains' scope)
         steps = 40
-        re = ResidentReplicaExchange(make_factory(calc, n_moves=3), calc, temperatures=temps, gcmc_steps=steps,
+        re = ResidentReplicaExchange(make_factory(calc, n_moves=3, origin=origin), calc, temperatures=temps, gcmc_steps=steps,
                                      exchange_interval=3, seed=31, rank=rank, world_size=world, device=f'cuda:{local}')
     else:
         re = ShardedReplicaExchange(make_factory(calc, fix=(0, 3)), calc, temperatures=temps, gcmc_steps=steps,
@@ -52,10 +53,12 @@ def main():
     mine = {re.lo + k: (r.E_old, r.n_atoms, r.atoms.positions.copy()) for k, r in enumerate(re.replicas)}
     gathered = [None] * world
     dist.all_gather_object(gathered, (re.swap_log, mine))
+    dev_swaps = [None] * world
+    dist.all_gather_object(dev_swaps, getattr(re, 'device_swaps', 0))
     ok = True
     if rank == 0:
         calc1 = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=3.0, device=local)
-        ref = ShardedReplicaExchange(make_factory(calc1, n_moves=3) if resident else make_factory(calc1, fix=(0, 3)), calc1,
+        ref = ShardedReplicaExchange(make_factory(calc1, n_moves=3, origin=origin) if resident else make_factory(calc1, fix=(0, 3)), calc1,
                                      temperatures=temps, gcmc_steps=steps, exchange_interval=3, seed=31, rank=0, world_size=1)
         ref.run()
         merged = {}
@@ -73,7 +76,9 @@ def main():
         cross = sum(1 for _, i, j, _, a in ref.swap_log if a and i == n_rep // world - 1)
         if resident:
             ok = ok and cross > 0 and re.blocks < steps
-        print(f'{"resident" if resident else "sharded"} RE over NCCL: world={world} cross_rank_swaps={cross}  replicas={n_rep} swaps attempted={len(ref.swap_log)} '
+            # every accepted boundary swap went device to device on both ranks, or none did (Atoms.info present)
+            ok = ok and dev_swaps == ([0] * world if origin else [cross] * world)
+        print(f'{"resident" if resident else "sharded"} RE over NCCL: world={world} cross_rank_swaps={cross} device_to_device={dev_swaps}  replicas={n_rep} swaps attempted={len(ref.swap_log)} '
               f'accepted={accepted} identical_to_single_process={ok}')
     dist.barrier()
     dist.destroy_process_group()

@@ -51,6 +51,15 @@ def test_resident_replica_exchange_over_nccl_equals_single_process_host_driver()
 
 
 @pytest.mark.skipif(not _two_gpus(), reason='needs two GPUs')
+def test_resident_replica_exchange_swaps_device_to_device_across_ranks():
+    """Same run with nothing attached to the Atoms that the configuration block does not hold: every accepted boundary
+    swap sends the block GPU to GPU over NCCL (``ResidentGCMC.remote_swap``), no host round trip; same final state."""
+    proc = _torchrun('run_sharded_re_nccl.py', 'resident', 'device-swaps')
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    assert 'identical_to_single_process=True' in proc.stdout
+
+
+@pytest.mark.skipif(not _two_gpus(), reason='needs two GPUs')
 def test_resident_ladder_shard_over_nccl_equals_single_process():
     """ResidentLadderShard: configurations resident in HBM, ONE all_gather per exchange attempt carrying records and
     boundary configurations; after the exchange rounds every slot holds the configuration, box and energy the
