@@ -64,7 +64,8 @@ def host_trace(g):
 def gen_states(g):
     ms = g.move_selector
     gens = [ms.rng.random] + [m.rng.random for m in ms.move_list] + [g.rng_acceptance.random]
-    return [r.getstate() for r in gens], [c._rng.bit_generator.state for c in g.cells]
+    cells = [m.cell for m in ms.move_list if hasattr(m.cell, '_rng')]      # the cells the moves draw their points from
+    return [r.getstate() for r in gens], [c._rng.bit_generator.state for c in cells]
 
 
 def assert_same_chain(g_ref, g_dev, exact_positions=True):
@@ -273,3 +274,42 @@ def test_replica_exchange_with_resident_replicas_equals_the_reference_driver(kin
     assert rows[0] == rows[1] and len(rows[0]) >= 6 * 5
     lines = [[ln for ln in open(tmp_path / f'{t}_min.xyz')][2:] for t in ('ref', 'dev')]
     assert lines[0] == lines[1] and len(lines[0]) > 0                        # the global minimum, atom for atom
+
+
+def test_reference_lammps_parity_benchmark_stage1_series():
+    """The reference's own LJ GCMC benchmark (``benchmark/lammps_gcmc_parity.py:205-221,331-345``: L = 9, rc = 3, T* = 2,
+    20 randomly placed atoms, insertion / deletion(min_atoms=1) / displacement 1:1:1, one trial per step, the Cell built
+    from a separate empty Atoms): its per-step series N_i and E_i, from the device chain's per-trial trace."""
+    from ase import Atoms
+    from mcpy.cell import Cell
+    from mcpy.ensembles import GrandCanonicalEnsemble
+    from mcpy.moves import DeletionMove, DisplacementMove, InsertionMove, MoveSelector
+    from mcpy_b200.ensembles import ResidentGCMC
+    L, RC, T, steps = 9.0, 3.0, 2.0, 3000
+
+    def make(mu):
+        pos = np.random.default_rng(25).uniform(0.9, L - 0.9, size=(20, 3))
+        atoms = Atoms('H20', positions=pos, cell=[L, L, L], pbc=True)
+        cell = Cell(Atoms(cell=[L, L, L], pbc=True), seed=7)       # (the benchmark leaves it unseeded)
+        moves = [InsertionMove(cell, species=['H'], seed=21), DeletionMove(cell, species=['H'], seed=22, min_atoms=1),
+                 DisplacementMove(species=['H'], seed=23, max_displacement=0.3)]
+        ms = MoveSelector([1, 1, 1], moves, seed=25, n_moves=1)
+        return GrandCanonicalEnsemble(atoms=atoms, cells=[Cell(atoms)], units_type='LJ',
+                                      calculator=OracleLJCalculator(rc=RC), mu={'H': mu}, species=['H'], temperature=T,
+                                      move_selector=ms, random_seed=24, traj_file=None, outfile=None)
+    for mu in (-3.0, -1.0):
+        g_ref, g_dev = make(mu), make(mu)
+        n_series, e_series = np.empty(steps), np.empty(steps)
+        for i in range(steps):                                       # run_mcpy of the benchmark
+            g_ref.do_gcmc_step()
+            n_series[i], e_series[i] = len(g_ref.atoms), g_ref.E_old
+        E0 = g_dev.E_old
+        rg = ResidentGCMC(g_dev, lj=(1.0, 1.0, RC), trace=steps)
+        rg.run_trials(steps)
+        tr = rg.traces[0]
+        assert np.array_equal(tr['n_atoms'], n_series)
+        e_dev = E0 + np.cumsum(np.where(tr['flags'] & 1, tr['dE'], 0.0))
+        scale = np.maximum.accumulate(np.maximum(np.abs(e_series), abs(E0)))      # the running sum rounds at the largest |E| so far
+        assert np.all(np.abs(e_dev - e_series) <= 1e-10 * np.maximum(1.0, np.abs(e_series)) + 1e-13 * scale)
+        assert_same_chain(g_ref, g_dev)
+        assert n_series.max() > 25 and n_series.min() >= 1
