@@ -702,9 +702,12 @@ def run_b200(args):
         'gpu_launches': int(gpu_launches),
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': achieved / peak if peak else None,
-                     'traffic': prof.get('lj_trial_rows_warp_kernel_dram_bytes_per_launch'),
-                     'pipe_fp64_pct': prof.get('lj_trial_rows_warp_kernel_pipe_fp64_pct'),
-                     'kernel': 'lj_trial_rows_warp_kernel',
+                     'traffic': prof.get('lj_trial_rows_direct_kernel_dram_bytes_per_launch',
+                                         prof.get('lj_trial_rows_warp_kernel_dram_bytes_per_launch')),
+                     'pipe_fp64_pct': prof.get('lj_trial_rows_direct_kernel_pipe_fp64_pct',
+                                               prof.get('lj_trial_rows_warp_kernel_pipe_fp64_pct')),
+                     'kernel': 'lj_trial_rows_direct_kernel<4> (the warp-per-item row sums of rows_warp.cuh, work items '
+                               'announced by trial_sites_direct_kernel)',
                      'kernel_ms': rows_ms, 'kernel_share_of_sweep': rows_ms / sum(stage_ms.values()),
                      'algorithmic_flop_per_launch': alg_flop,
                      'step_achieved': alg_flop * SW / (ms_per_step * 1e-3) / 1e12,
