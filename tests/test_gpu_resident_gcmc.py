@@ -313,3 +313,12 @@ def test_reference_lammps_parity_benchmark_stage1_series():
         assert np.all(np.abs(e_dev - e_series) <= 1e-10 * np.maximum(1.0, np.abs(e_series)) + 1e-13 * scale)
         assert_same_chain(g_ref, g_dev)
         assert n_series.max() > 25 and n_series.min() >= 1
+
+
+def test_state_in_global_memory_when_it_does_not_fit_shared_memory():
+    """A chain whose storage (here: room for 20 000 atoms) exceeds the 227 KB of shared memory runs from global memory
+    with the same code: same trials, same state."""
+    cfg = small_box(seed=23)
+    g_ref, g_dev, rg, trace = run_pair(lambda: box_gcmc(cfg, 'H', -2.2, seed=4), 150, cfg=cfg, atom_capacity=20000)
+    assert not rg.info()['in_shared_memory'] and rg.info()['state_bytes'] > 227 * 1024
+    assert sum(t[2] for t in trace) > 50
