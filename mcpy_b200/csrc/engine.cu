@@ -1655,6 +1655,14 @@ int mcpyb_trial_delta_e_host(mcpyb_engine* e, int T, const int32_t* rep, const i
         CK(cudaEventCreateWithFlags(&e->copy_ev, cudaEventDisableTiming), "cudaEventCreate (copy)");
     }
     cudaStream_t cs = small ? e->stream : e->copy_stream;
+    // A batch that goes to the row-sum pipeline against a freshly uploaded configuration needs the per-configuration
+    // stencil lists first (expand_stencils_kernel: ~150 us for 8 x 2 000 atoms).  They depend on the configurations
+    // only: launched here, on the compute stream, they are built while the copy stream brings the proposals in.
+    if (!small && e->pot_kind == POT_LJ && e->use_warp_rows && n_old + n_new > RS_MAX_SITES) {
+        StencilLists ahead;
+        const int rc_lists = stencil_lists(e, false, &ahead);
+        if (rc_lists != MCPYB_OK) return rc_lists;
+    }
     // stage piece by piece: the H2D copy of one piece runs while the host copies the next one
     auto stage = [&](size_t off, const void* src, size_t nbytes) -> cudaError_t {
         const size_t piece = 512u << 10;
