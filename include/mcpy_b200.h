@@ -359,6 +359,9 @@ int mcpyb_gcmc_get_state(mcpyb_gcmc* g, int chain, double* positions_out, mcpyb_
 int mcpyb_gcmc_run(mcpyb_gcmc* g, const int64_t* n_trials, int32_t* status_out);
 /* scalars of a chain as of the end of the last mcpyb_gcmc_run / set_state / swap (host copy, no device traffic) */
 int mcpyb_gcmc_get_scalars(mcpyb_gcmc* g, int chain, mcpyb_gcmc_scalars* s_out);
+/* the same for all chains at once, only what a replica driver reads between two blocks: E_old, the particle number, trials
+ * done since set_state (arrays of n_chains entries) and {best score, best energy} (2 n_chains) */
+int mcpyb_gcmc_get_block_scalars(mcpyb_gcmc* g, double* energy, int32_t* n_atoms, int64_t* trials_done, double* best2);
 /* BatchedReplicaExchange._swap_states (batched_replica_exchange.py:401-410) between two chains of one set, on the
  * device: configuration, energy and particle number change slots; generators, counters, the running minimum,
  * temperature and chemical potential stay.  MCPYB_ERR_CAPACITY when the chains' boxes or storage layouts differ. */

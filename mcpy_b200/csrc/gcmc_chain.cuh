@@ -1025,6 +1025,17 @@ int mcpyb_gcmc_swap_configurations(mcpyb_gcmc* g, int i, int j) {
     return MCPYB_OK;
 }
 
+int mcpyb_gcmc_get_block_scalars(mcpyb_gcmc* g, double* energy, int32_t* n_atoms, int64_t* trials_done, double* best2) {
+    if (!g) return MCPYB_ERR_ARG;
+    if (!energy || !n_atoms || !trials_done || !best2) return g->e->fail(MCPYB_ERR_ARG, "gcmc get_block_scalars: bad argument");
+    for (int c = 0; c < g->n; ++c) {
+        const mcpyb_gcmc_scalars& s = g->dyn[c].s;
+        energy[c] = s.energy; n_atoms[c] = s.n_atoms; trials_done[c] = s.trials_done;
+        best2[2 * c] = s.best_score; best2[2 * c + 1] = s.best_energy;
+    }
+    return MCPYB_OK;
+}
+
 int mcpyb_gcmc_config_ptr(mcpyb_gcmc* g, int chain, void** dev_ptr, int64_t* bytes, double* scalars5) {
     if (!g) return MCPYB_ERR_ARG;
     if (chain < 0 || chain >= g->n || !dev_ptr || !bytes) return g->e->fail(MCPYB_ERR_ARG, "gcmc config_ptr: bad argument");

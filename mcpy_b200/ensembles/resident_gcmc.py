@@ -145,6 +145,7 @@ class ResidentGCMC:
         self._scalars_ref = C.byref(self._scalars)
         self._storage_sig = None
         self._recv_block = None
+        self._blk = None
         self.last_status = [0] * n
         self.trials_run = 0
 
@@ -269,6 +270,34 @@ class ResidentGCMC:
                     total[m] += d
                     seen[c][m] += d
         return s
+
+    def _apply_block_scalars(self):
+        """:meth:`_apply_scalars` without the counters, for all chains from ONE call: ``E_old``, ``n_atoms``, the
+        running-minimum scores of chains that improved.  Returns the trials each chain did in the last launch."""
+        b = self._blk
+        if b is None:
+            n = len(self.ensembles)
+            b = self._blk = (np.empty(n), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int64), np.empty(2 * n))
+            self._blk_ptrs = tuple(a.ctypes.data for a in b)
+        self.engine._check(self._lib.mcpyb_gcmc_get_block_scalars(self._h, *self._blk_ptrs))
+        energy, n_atoms, trials, best = b[0].tolist(), b[1].tolist(), b[2].tolist(), b[3].tolist()
+        seen = self._trials_seen
+        done = np.empty(len(energy), dtype=np.int64)
+        fresh = self._host_fresh
+        for k, g in enumerate(self.ensembles):
+            n = n_atoms[k]
+            if fresh[k] or g.n_atoms != n or len(g.atoms) != n:
+                atoms = g.atoms
+                atoms.arrays = {'numbers': np.full(n, self._Z[k], dtype=atoms.arrays['numbers'].dtype),
+                                'positions': np.full((n, 3), np.nan)}
+                fresh[k] = False
+                g.n_atoms = n
+            g.E_old = energy[k]
+            if best[2 * k] < g._best_score:                            # improved on the device (never worse than the host's)
+                g._best_score, g._best_energy = best[2 * k], best[2 * k + 1]
+            done[k] = trials[k] - seen[k]
+            seen[k] = trials[k]
+        return done
 
     def sync_host(self, chains=None):
         """Bring the ensembles fully up to date with their chains: configuration, the five Mersenne-Twister states and
@@ -403,11 +432,14 @@ class ResidentGCMC:
             self.engine._check(self._lib.mcpyb_gcmc_run(self._h, want.ctypes.data, status.ctypes.data))
             self._lib.mcpyb_gcmc_last_run_ms(self._h, C.byref(ms))
             total_ms += ms.value
-            done = np.empty(n, dtype=np.int64)
-            for k in range(n):
-                s = self._apply_scalars(k, counters)
-                done[k] = int(s.trials_done) - self._trials_seen[k]
-                self._trials_seen[k] = int(s.trials_done)
+            if counters:
+                done = np.empty(n, dtype=np.int64)
+                for k in range(n):
+                    s = self._apply_scalars(k, True)
+                    done[k] = int(s.trials_done) - self._trials_seen[k]
+                    self._trials_seen[k] = int(s.trials_done)
+            else:
+                done = self._apply_block_scalars()
             if self.trace_capacity:
                 for k in range(n):
                     self.traces[k] = np.concatenate([self.traces[k], self._get_trace(k)])

@@ -38,6 +38,7 @@ class ResidentReplicaExchange(ShardedReplicaExchange):
         self._ahead = 0                    # steps the device is ahead of the run loop's step counter
         self.device_ms = 0.0               # device time of the chain launches
         self.device_swaps = 0              # cross-rank swaps that went device to device
+        self._rec_static = None            # the slot-bound columns of the exchange records
         self.blocks = 0
 
     # ------------------------------------------------------------------ blocks of steps
@@ -82,6 +83,21 @@ class ResidentReplicaExchange(ShardedReplicaExchange):
                     r.write_outfile()
                 if traj_due:
                     r.write_coordinates(r.atoms, r.E_old)
+
+    # ------------------------------------------------------------------ records
+    def _gather_records(self):
+        """The records of ``ShardedReplicaExchange._record`` without a Python pass over every replica's atoms: in the
+        resident chains' scope a replica holds atoms of its one species only, so N_s is ``n_atoms``; beta, mu and Lambda
+        belong to the slot and are read once."""
+        import numpy as np
+        if self.resident is None or len(self.species) != 1 or not hasattr(self.resident, 'remote_swap'):
+            return super()._gather_records()
+        if self._rec_static is None:
+            self._rec_static = np.array([self._record(r) for r in self.replicas]).reshape(-1, 6)
+        rec = self._rec_static.copy()
+        rec[:, 0] = [r.E_old for r in self.replicas]
+        rec[:, 2] = [r.n_atoms for r in self.replicas]
+        return self.comm.gather_records(rec)
 
     # ------------------------------------------------------------------ swaps
     def _swap_states(self, i: int, j: int) -> None:
