@@ -322,3 +322,42 @@ def test_state_in_global_memory_when_it_does_not_fit_shared_memory():
     g_ref, g_dev, rg, trace = run_pair(lambda: box_gcmc(cfg, 'H', -2.2, seed=4), 150, cfg=cfg, atom_capacity=20000)
     assert not rg.info()['in_shared_memory'] and rg.info()['state_bytes'] > 227 * 1024
     assert sum(t[2] for t in trace) > 50
+
+
+@pytest.mark.parametrize('box', [(7.0, 9.0, 12.5), (5.5, 6.4, 5.2), (16.0, 5.3, 8.1)])
+def test_anisotropic_boxes_two_insertion_cells_fractional_weights_unwrapped_start(box):
+    """Boxes whose axes fall on different sides of the five-cell stencil (fewer than five cells along an axis: every
+    cell of that axis is a neighbour), two insertion moves drawing from two cells' PCG64 streams, non-integer move
+    weights, deletion and insertion limits, and a start with atoms one or two boxes outside the cell."""
+    from ase import Atoms
+    from mcpy.cell import Cell
+    from mcpy.ensembles import GrandCanonicalEnsemble
+    from mcpy.moves import DeletionMove, DisplacementMove, InsertionMove, MoveSelector
+    from mcpy_b200.ensembles import ResidentGCMC
+    rc = 2.5
+
+    def make():
+        rng = np.random.default_rng(77)
+        n = 30
+        pos = rng.uniform(0.0, 1.0, (n, 3)) * np.array(box)
+        pos[::5] += np.array(box) * rng.integers(-2, 3, (len(pos[::5]), 3))        # unwrapped images
+        atoms = Atoms(numbers=np.ones(n, int), positions=pos, cell=np.diag(box), pbc=True)
+        cell_a, cell_b = Cell(atoms, seed=5), Cell(atoms, seed=6)
+        moves = [InsertionMove(cell_a, ['H'], 41, max_atoms=60), InsertionMove(cell_b, ['H'], 42),
+                 DeletionMove(cell_a, ['H'], 43, min_atoms=8), DisplacementMove(['H'], 44, max_displacement=1.7)]
+        ms = MoveSelector([0.7, 0.45, 1.3, 2.05], moves, seed=45, n_moves=4)
+        return GrandCanonicalEnsemble(atoms=atoms, cells=[cell_a, cell_b], units_type='LJ',
+                                      calculator=OracleLJCalculator(rc=rc), mu={'H': -1.2}, species=['H'], temperature=1.7,
+                                      move_selector=ms, random_seed=46, traj_file=None, outfile=None)
+    g_ref, g_dev = make(), make()
+    trace = host_trace(g_ref)
+    steps = 150
+    for _ in range(steps):
+        g_ref.do_gcmc_step()
+    rg = ResidentGCMC(g_dev, lj=(1.0, 1.0, rc), trace=4 * steps)
+    rg.run_trials(4 * steps)
+    assert_same_trace(trace, rg.traces[0])
+    assert_same_chain(g_ref, g_dev)
+    assert {t[0] for t in trace if t[2]} == {0, 1, 2, 3}
+    cells = rg.info()['cells']
+    assert min(cells) < 5 or max(cells) >= 5
