@@ -550,3 +550,41 @@ class ResidentGCMC:
             self.close()
         except Exception:
             pass
+
+
+def install():
+    """Route ``GrandCanonicalEnsemble.run(steps)`` through the device-resident chains whenever it can be: afterwards an
+    UNMODIFIED mcpy script whose ensemble has a ``B200Calculator('lj')`` and is in scope (:func:`supports`) runs its
+    trials on the device -- same draws, decisions, files -- and every other ensemble runs the reference's loop as before.
+    Returns the original method (pass it to :func:`uninstall`).  This is the three-line change a maintainer would make in
+    ``BaseEnsemble.run`` (``mcpy/ensembles/base_ensemble.py:257-264``), done from outside (INTEGRATION.md)."""
+    from mcpy.ensembles.grand_canonical_ensemble import GrandCanonicalEnsemble
+    original = GrandCanonicalEnsemble.run
+    if getattr(original, '_b200_resident', False):
+        return original._b200_original
+
+    def run(self, steps):
+        calc = getattr(self, '_calculator', None)
+        if getattr(calc, 'lj_parameters', None) is not None and getattr(calc, 'engine', None) is not None \
+                and type(self) is GrandCanonicalEnsemble and supports(self) is None:
+            chains = ResidentGCMC(self, engine=calc.engine)
+            try:
+                return chains.run(steps)
+            finally:
+                chains.close()
+        return original(self, steps)
+    run._b200_resident = True
+    run._b200_original = original
+    GrandCanonicalEnsemble.run = run
+    return original
+
+
+def uninstall(original=None):
+    """Undo :func:`install`."""
+    from mcpy.ensembles.grand_canonical_ensemble import GrandCanonicalEnsemble
+    current = GrandCanonicalEnsemble.__dict__.get('run')
+    if current is not None and getattr(current, '_b200_resident', False):
+        if 'run' in GrandCanonicalEnsemble.__dict__:
+            del GrandCanonicalEnsemble.run               # BaseEnsemble.run is inherited again
+        if original is not None and original is not getattr(GrandCanonicalEnsemble, 'run'):
+            GrandCanonicalEnsemble.run = original

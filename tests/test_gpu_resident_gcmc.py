@@ -361,3 +361,42 @@ def test_anisotropic_boxes_two_insertion_cells_fractional_weights_unwrapped_star
     assert {t[0] for t in trace if t[2]} == {0, 1, 2, 3}
     cells = rg.info()['cells']
     assert min(cells) < 5 or max(cells) >= 5
+
+
+def test_install_routes_an_unmodified_run_call_through_the_device(tmp_path):
+    """``resident_gcmc.install()``: ``gcmc.run(steps)`` of an unmodified script with a ``B200Calculator('lj')`` runs on
+    the device (one launch per block between file writes instead of one calculator call per trial), an out-of-scope
+    ensemble keeps the reference's loop, and both leave the state and files the reference's loop over the oracle leaves."""
+    from mcpy.ensembles import GrandCanonicalEnsemble
+    from mcpy_b200.calculators import B200Calculator
+    from mcpy_b200.ensembles import resident_gcmc
+    cfg = small_box(seed=29)
+    calc = B200Calculator('lj', epsilon=cfg['epsilon'], sigma=cfg['sigma'], rc=cfg['rc'])
+
+    def make(tag, calculator=None, min_insert=None):
+        g = box_gcmc(cfg, 'H', -2.1, seed=8)
+        if calculator is not None:
+            g._calculator = calculator
+            g.E_old = g.compute_energy(g.atoms)
+        g.move_selector.move_list[0].min_insert = min_insert
+        g._outfile, g._traj_file = str(tmp_path / f'{tag}.out'), str(tmp_path / f'{tag}.xyz')
+        g._outfile_write_interval, g._trajectory_write_interval = 10, 20
+        return g
+    g_ref = make('ref')
+    g_ref.run(60)                                                   # the reference's loop over the CPU oracle
+    original = resident_gcmc.install()
+    try:
+        assert GrandCanonicalEnsemble.run is not original
+        g_dev = make('dev', calc)
+        calls0 = calc.n_energy_calls
+        g_dev.run(60)
+        assert calc.n_energy_calls == calls0                        # not one calculator call: the chain ran on the device
+        assert_same_chain(g_ref, g_dev)
+        xyz = [[ln for ln in open(tmp_path / f'{t}.xyz') if not ln.startswith('energy=')] for t in ('ref', 'dev')]
+        assert xyz[0] == xyz[1] and len(xyz[0]) > 100
+        g_out = make('out', calc, min_insert=0.3)                   # out of scope: the reference's own loop, per-trial calls
+        g_out.run(5)
+        assert calc.n_energy_calls >= calls0 + 5
+    finally:
+        resident_gcmc.uninstall(original)
+    assert 'run' not in GrandCanonicalEnsemble.__dict__ or GrandCanonicalEnsemble.run is original
