@@ -313,6 +313,8 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
     int best_n = -1;
     GcPre pre;
     pre.valid = 0;
+    double acc_db = 1.0, acc_u = 0.0;
+    bool acc_u_ok = false;
     const int all_streams = (1 << (nm + 2)) - 1;
     if (tid == 0) {
         n = D.s.n_atoms; n_unst = D.n_unstable; E = D.s.energy; best_score = D.s.best_score; best_E = D.s.best_energy;
@@ -348,20 +350,21 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                 bool acc;
                 drew = 0;
                 const int mt_acc = nm + 1;
+                // rng_acceptance.get_uniform(): the two words looked at behind the row sums, consumed here
+                auto draw = [&]() {
+                    drew = 1;
+                    if (acc_u_ok) { M.idx[mt_acc] += 2; return acc_u; }
+                    return gc_mt_random(M, mt_acc);
+                };
                 if (cur_kind == MCPYB_GCMC_DISPLACE) {
                     if (dE <= 0.0) acc = true;
-                    else { const double p = exp(__dmul_rn(-dE, s_d.beta)); drew = 1; acc = p > gc_mt_random(M, mt_acc); }
+                    else { const double p = exp(__dmul_rn(-dE, s_d.beta)); acc = p > draw(); }
                 } else {
                     double p;
-                    if (cur_kind == MCPYB_GCMC_INSERT) {
-                        const double db = s_d.move_volume[cur_move] / __dmul_rn((double)(n + 1), s_d.lambda3);
-                        p = __dmul_rn(db, exp(__dmul_rn(-s_d.beta, __dsub_rn(dE, s_d.mu))));
-                    } else {
-                        const double db = __dmul_rn(s_d.lambda3, (double)n) / s_d.move_volume[cur_move];
-                        p = __dmul_rn(db, exp(__dmul_rn(-s_d.beta, __dadd_rn(dE, s_d.mu))));
-                    }
+                    if (cur_kind == MCPYB_GCMC_INSERT) p = __dmul_rn(acc_db, exp(__dmul_rn(-s_d.beta, __dsub_rn(dE, s_d.mu))));
+                    else p = __dmul_rn(acc_db, exp(__dmul_rn(-s_d.beta, __dadd_rn(dE, s_d.mu))));
                     if (p > 1.0) acc = true;
-                    else { drew = 1; acc = p > gc_mt_random(M, mt_acc); }
+                    else acc = p > draw();
                 }
                 int par = 0;
                 if (acc) {
@@ -543,13 +546,14 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
             ++rounds;
         }
         __syncthreads();
-        if (T.done) break;
-        if (T.refill) {                                     // next Mersenne-Twister states, computed ahead by the whole CTA
-            const int need = T.refill;
+        const int ctl_done = T.done, ctl_refill = T.refill, ctl_par = T.par;     // three loads in flight together
+        if (ctl_done) break;
+        if (ctl_refill) {                                   // next Mersenne-Twister states, computed ahead by the whole CTA
+            const int need = ctl_refill;
             for (int k = 0; k < nm + 2; ++k) if (need >> k & 1) gc_mt_refill(M, k, tid);
         }
-        if (T.par) {
-            const int par = T.par;
+        if (ctl_par) {
+            const int par = ctl_par;
             if (par & GC_PAR_SHIFT) {
                 const int from = T.shift_from, last = T.shift_n - 1;        // order[from .. last-1] <- order[from+1 .. last]
                 for (int b0 = from; b0 < last; b0 += GC_THREADS) {
@@ -630,6 +634,15 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
             // trial may change.  Drawn for the current n; used only if n is still that (or not needed) when it is its turn.
             const long long cyc_in = clock64();
             cyc_gap1 += cyc_in - mark_serial_end;
+            // what the acceptance test of the running trial needs besides dE: the de Broglie factor (a division) and the
+            // next uniform of the acceptance stream (looked at, consumed only if the test draws)
+            if (cur_kind == MCPYB_GCMC_INSERT) acc_db = s_d.move_volume[cur_move] / __dmul_rn((double)(n + 1), s_d.lambda3);
+            else if (cur_kind == MCPYB_GCMC_DELETE) acc_db = __dmul_rn(s_d.lambda3, (double)n) / s_d.move_volume[cur_move];
+            acc_u_ok = M.idx[nm + 1] + 2 <= 624;
+            if (acc_u_ok) {
+                const uint32_t* sa = gc_mt_cur(M, nm + 1) + M.idx[nm + 1];
+                acc_u = gc_mt_double(gc_mt_temper(sa[0]), gc_mt_temper(sa[1]));
+            }
             pre.valid = 0;
             const uint32_t* s0 = gc_mt_cur(M, 0) + M.idx[0];
             if (t_done + 1 < t_goal && !pending && M.idx[0] + 2 <= 624) {
