@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmcpy_b200.so')
+# MCPYB_LIBRARY: another build of the SAME engine (the bounds-checking variant of `python -m mcpy_b200.build --bounds`)
+LIB_PATH = os.environ.get('MCPYB_LIBRARY') or os.path.join(_HERE, 'libmcpy_b200.so')
 
 # Every symbol include/mcpy_b200.h declares (tests check the library exports all of them).
 SYMBOLS = [

@@ -65,9 +65,20 @@ def is_stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the engine for sm_100a; returns the path of the shared library."""
+LIB_BOUNDS = os.path.join(HERE, 'libmcpy_b200_bounds.so')
+
+
+def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> str:
+    """Compile the engine for sm_100a; returns the path of the shared library.  ``bounds=True`` builds the checking
+    variant (``-DMCPYB_BOUNDS``: device-side asserts on the hand-computed indices, csrc/common.cuh) next to the
+    product library; ``MCPYB_LIBRARY=<path>`` makes ``mcpy_b200`` load it."""
     build_marshal(force)
+    if bounds:
+        cmd = [find_nvcc()] + NVCC_FLAGS + ['-DMCPYB_BOUNDS=1', '-o', LIB_BOUNDS] + [os.path.join(CSRC, s) for s in SOURCES]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout + proc.stderr)
+        return LIB_BOUNDS
     if not force and not is_stale():
         return LIB
     cmd = [find_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
@@ -81,4 +92,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, bounds='--bounds' in sys.argv))

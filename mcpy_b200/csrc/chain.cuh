@@ -154,6 +154,7 @@ lj_chain_kernel(BatchView b, LJParams p, StencilLists x, ChainMailbox* mb, unsig
                 const int cell_bin = (c[2] * g.ncell[1] + c[1]) * g.ncell[0] + c[0];
                 const int2 head = x.head[cell_bin];
                 if (head.x < 0) { if (lane == 0) sm.status = (int)CHAIN_ST_FALLBACK; continue; }
+                MCPYB_CHECK(head.y >= 0 && (long long)head.x + head.y <= x.cap);
                 const double4* xq = x.q + head.x;
                 const int2* xi = x.info + head.x;
                 double qx = px, qy = py, qz = pz, band = 16.0;

@@ -13,6 +13,16 @@
 //   bits 32..61  three 10-bit periodic wrap counts, biased by 512
 // so one 32-byte load delivers everything the pair loop needs.
 #pragma once
+// Bounds checks of the hand-computed indices (shared-memory staging slots, stencil-list runs, site slots, chain state):
+// compiled in by `python -m mcpy_b200.build --bounds` (-DMCPYB_BOUNDS -> libmcpy_b200_bounds.so, selected with
+// MCPYB_LIBRARY=...), absent from the product build.  A failing check stops the kernel with cudaErrorAssert and prints
+// file:line; the GPU test-suite is run under this build as a stand-in for compute-sanitizer (closed on the pool).
+#ifdef MCPYB_BOUNDS
+#include <cassert>
+#define MCPYB_CHECK(cond) assert(cond)
+#else
+#define MCPYB_CHECK(cond) ((void)0)
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 

@@ -165,6 +165,7 @@ emt_trial_rows_kernel(BatchView b, TrialBatch tb, const EmtTable* __restrict__ t
                 const int wsite = pack_wraps(wr[0], wr[1], wr[2]);
                 const int2 head = x.head[bin_base + (c[2] * g.ncell[1] + c[1]) * g.ncell[0] + c[0]];
                 if (head.x < 0) { listed = false; break; }
+                MCPYB_CHECK(head.y >= 0 && (long long)head.x + head.y <= x.cap);
                 const double4* xq = x.q + head.x;
                 const int2* xi = x.info + head.x;
                 // the list is written in the frame of the primary cell: a site stored outside it is shifted in, and

@@ -147,6 +147,7 @@ __device__ __noinline__ void gc_mt_advance(GcMt& M, int k) {
 template <int K>
 __device__ __forceinline__ void gc_mt_take(GcMt& M, int k, uint32_t (&out)[K]) {
     int i = M.idx[k];
+    MCPYB_CHECK(k >= 0 && k < GC_MAX_STREAMS && i >= 0 && i <= 624);
     if (i + K <= 624) {
         const uint32_t* s = gc_mt_cur(M, k) + i;
 #pragma unroll
@@ -371,10 +372,14 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                     s_cnt[1][cur_move] += 1;
                     int moved = GC_NONE;
                     if (cur_kind == MCPYB_GCMC_INSERT) {
+                        MCPYB_CHECK(n >= 0 && n < C.acap);
                         const int slot = order[n];
+                        MCPYB_CHECK(slot < C.acap);
                         px[slot] = T.sx[0]; py[slot] = T.sy[0]; pz[slot] = T.sz[0];
                         const int c = (T.home[0][0] * nc1 + T.home[0][1]) * nc2 + T.home[0][2];
+                        MCPYB_CHECK(c >= 0 && c < C.ncells);
                         const int cnt = cell_cnt[c];
+                        MCPYB_CHECK(cnt < ccap);
                         cell_slots[c * ccap + cnt] = (unsigned short)slot;
                         cell_cnt[c] = (unsigned short)(cnt + 1);
                         cell_of[slot] = (unsigned short)c;
@@ -392,10 +397,12 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                             unsigned short* lst = cell_slots + c_old * ccap;
                             int k = 0;
                             while (k < cnt && lst[k] != slot) ++k;
+                            MCPYB_CHECK(cnt > 0 && k < cnt);             // the atom was in the cell it is filed under
                             lst[k] = lst[cnt - 1];
                             cell_cnt[c_old] = (unsigned short)(cnt - 1);
                             if (c_new >= 0) {
                                 const int cn = cell_cnt[c_new];
+                                MCPYB_CHECK(c_new < C.ncells && cn < ccap);
                                 cell_slots[c_new * ccap + cn] = (unsigned short)slot;
                                 cell_cnt[c_new] = (unsigned short)(cn + 1);
                                 cell_of[slot] = (unsigned short)c_new;
@@ -419,6 +426,7 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                         }
                     }
                     if (moved != GC_NONE && !uflag[moved]) { uflag[moved] = 1; unstable[n_unst++] = (unsigned short)moved; }
+                    MCPYB_CHECK(n_unst >= 0 && n_unst <= C.acap && n >= 0 && n < C.acap + 1);
                     E += dE;
                     e_scale = fmax(e_scale, fabs(E)); ++acc_since;
                     // atoms.wrap(): only atoms whose last wrap still changed a bit can change again
@@ -609,10 +617,13 @@ gcmc_chain_kernel(const GcChain* __restrict__ chains, GcDyn* __restrict__ dyn, c
                 if (sp1 != nc1) { c1 = T.home[site][1] - 2 + a1; c1 += c1 < 0 ? nc1 : 0; c1 -= c1 >= nc1 ? nc1 : 0; }
                 if (sp2 != nc2) { c2 = T.home[site][2] - 2 + a2; c2 += c2 < 0 ? nc2 : 0; c2 -= c2 >= nc2 ? nc2 : 0; }
                 const int cell = (c0 * nc1 + c1) * nc2 + c2;
+                MCPYB_CHECK(sc >= 0 && sc < ns && cell >= 0 && cell < C.ncells);
                 const int cnt = cell_cnt[cell];
+                MCPYB_CHECK(cnt >= 0 && cnt <= ccap);
                 const double sx = T.sx[site], sy = T.sy[site], sz = T.sz[site], sg = T.sign[site];
                 for (int k = rt & 3; k < cnt; k += 4) {
                     const int slot = cell_slots[cell * ccap + k];
+                    MCPYB_CHECK(slot < C.acap);
                     if (slot == excl) continue;
                     const double x = px[slot], y = py[slot], z = pz[slot];
                     // the image of the neighbour the reference's neighbour list pairs with the site: (pos_j + S * L) - pos_i

@@ -291,6 +291,7 @@ expand_stencils_kernel(BatchView b, StencilLists x, int nbins, int bin_stride, d
                     const unsigned bal = __ballot_sync(0xffffffffu, keep);
                     if (keep) {
                         const unsigned long long at = base + kept + __popc(bal & ((1u << lane) - 1u));
+                        MCPYB_CHECK(at < (unsigned long long)x.cap);
                         x.q[at] = q;
                         x.info[at] = info;
                     }
@@ -490,6 +491,7 @@ lj_trial_rows_block_kernel(BatchView b, TrialBatch tb, TrialWork w, LJParams p, 
                         }
                         if (keep) {
                             const int slot = nst + before + __popc(bal & ((1u << lane) - 1u));
+                            MCPYB_CHECK(slot >= 0 && slot < RB_CAND);
                             sm.candd[slot] = q;
                             sm.cinfo[slot] = info;
                         }

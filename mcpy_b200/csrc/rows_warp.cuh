@@ -335,9 +335,11 @@ __device__ __forceinline__ void rw_item(const BatchView& b, const TrialBatch& tb
         const long long lo_bits = __double_as_longlong(p.rc2 - bw), hi_bits = __double_as_longlong(p.rc2 + bw);
         const bool multi = (oe - ob) > 2;
         const int ex1 = (oe - ob) > 1 ? tb.old_idx[ob + 1] : -1;
+        MCPYB_CHECK(head.x >= 0 && head.y >= 0 && (long long)head.x + head.y <= x.cap);
         const double4* xq = x.q + head.x;
         const int2* xi = x.info + head.x;
         const int ksite = active ? kbeg + sl : -1;
+        MCPYB_CHECK(ksite < (w.slot_cap > 0 ? w.nbins * w.slot_cap : w.nsites));
         if (gshift == 4)
             rw_candidate_loop<2, F32>(xq, xi, head.y, lane, grp, buf, qx, qy, qz, ksite, rec_pos, lo_bits, hi_bits,
                                  ex0, ex1, multi, ob, oe, g, spos, tb, p.sigma2, p.rc2, acc12, acc6, cnt);

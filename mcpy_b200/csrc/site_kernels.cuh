@@ -502,6 +502,7 @@ __device__ __forceinline__ void trial_place(const TrialWork& w, int s, int bin, 
     const double4 rp = make_double4(x, y, z, __longlong_as_double((long long)(unsigned int)pack_wraps(wr[0], wr[1], wr[2]) |
                                                                   ((long long)bin << 32)));
     const int4 rm = make_int4(s, ex0, ob, oe);
+    MCPYB_CHECK(bin >= 0 && bin < w.nbins && rank >= 0);
     if (rank < w.slot_cap) {
         const size_t k = (size_t)bin * w.slot_cap + rank;
         w.sorted_pos[k] = rp;
@@ -659,7 +660,9 @@ __device__ __forceinline__ void trial_scatter_body(const TrialWork& w, int s) {
     const long long wbits = __double_as_longlong(ps.w);
     if ((int)((unsigned long long)wbits >> 38) != w.stamp) return;   // not written by this launch (rejected trial)
     const int count = (int)(wbits >> 32) & 63;
+    MCPYB_CHECK(a.x >= 0 && a.x < w.nbins);
     const int k = w.bin_count[a.x] + a.y;
+    MCPYB_CHECK(k >= 0 && k < w.nsites);
     w.sorted[k] = s;
     if (w.sorted_pos) {
         w.sorted_pos[k] = make_double4(ps.x, ps.y, ps.z, __longlong_as_double(wbits & 0xFFFFFFFFLL));
