@@ -217,9 +217,12 @@ def test_run_writes_the_same_files_as_the_reference(tmp_path):
     g_ref.run(40)
     ResidentGCMC(g_dev, lj=(cfg['epsilon'], cfg['sigma'], cfg['rc'])).run(40)
     assert_same_chain(g_ref, g_dev)
-    rows_ref = [ln.split()[:2] for ln in open(tmp_path / 'ref.out') if ln[:1].isdigit()]
-    rows_dev = [ln.split()[:2] for ln in open(tmp_path / 'dev.out') if ln[:1].isdigit()]
-    assert rows_ref == rows_dev and len(rows_ref) >= 9                       # step, N per row
+    rows_ref = [ln.split() for ln in open(tmp_path / 'ref.out') if ln[:1].isdigit()]
+    rows_dev = [ln.split() for ln in open(tmp_path / 'dev.out') if ln[:1].isdigit()]
+    assert len(rows_ref) == len(rows_dev) >= 9
+    for a, b in zip(rows_ref, rows_dev):
+        assert a[:2] == b[:2] and a[3:] == b[3:], (a, b)                     # step, N, acceptance ratios of the interval
+        assert abs(float(a[2]) - float(b[2])) <= 2e-6 * max(1.0, abs(float(a[2])))
     xyz_ref = [ln for ln in open(tmp_path / 'ref.xyz') if not ln.startswith('energy=')]
     xyz_dev = [ln for ln in open(tmp_path / 'dev.xyz') if not ln.startswith('energy=')]
     assert xyz_ref == xyz_dev                                                # positions print to the last digit
