@@ -340,6 +340,23 @@ class ResidentGCMC:
 
     pull = sync_host
 
+    def sync_positions(self, chains=None):
+        """Only what a trajectory frame needs: the configurations (and the scalars / counters) of the chains, which stay
+        the owners of the state -- generator states and the best configuration are left on the device, nothing is
+        uploaded again before the next block."""
+        for k in (range(len(self.ensembles)) if chains is None else chains):
+            if self._host_fresh[k]:
+                continue
+            g = self.ensembles[k]
+            pos = np.empty((self._desc[k].atom_capacity, 3), dtype=np.float64)
+            s = GcmcScalars()
+            self.engine._check(self._lib.mcpyb_gcmc_get_state(self._h, k, pos.ctypes.data, C.byref(s), None, None))
+            self._apply_scalars(k)
+            n = int(s.n_atoms)
+            atoms = g.atoms
+            atoms.arrays = {'numbers': np.full(n, self._Z[k], dtype=atoms.arrays['numbers'].dtype),
+                            'positions': pos[:n].copy()}
+
     def swap_configurations(self, i, j):
         """``_swap_states`` of the replica drivers between chains ``i`` and ``j`` on the device (configuration, energy,
         particle number); the caller swaps the ensembles' ``atoms`` / ``E_old`` / ``n_atoms``.  Chains that are not both
@@ -485,8 +502,10 @@ class ResidentGCMC:
                     if g._traj_file is not None and (g._step + block) % g._trajectory_write_interval == 0:
                         need_positions = True
                 last = done + block >= steps
-                self.advance([block * g.move_selector.n_moves for g in self.ensembles],
-                             sync='full' if (need_positions or last) else 'scalars')
+                self.advance([block * g.move_selector.n_moves for g in self.ensembles], sync='full' if last else 'scalars')
+                if need_positions and not last:
+                    self.sync_positions([k for k, g in enumerate(self.ensembles) if g._traj_file is not None and
+                                         (g._step + block) % g._trajectory_write_interval == 0])
                 done += block
                 for g in self.ensembles:
                     g._step += block

@@ -67,11 +67,18 @@ class ResidentReplicaExchange(ShardedReplicaExchange):
         if not self.replicas:                          # a rank may own no replica (R < world size)
             return
         if self._ahead == 0:
-            b, full = self._block()
+            b, frames = self._block()
+            last = self._re_step + b - 1 >= self.gcmc_steps - 1
             # the selector's counters are only read by a replica's own outfile rows (and after the run)
-            counters = full or any(r._outfile is not None for r in self.replicas)
+            counters = last or any(r._outfile is not None for r in self.replicas)
             self.device_ms += self.resident.advance(self._trials_per_step * b if b > 1 else self._trials_per_step,
-                                                    sync='full' if full else 'scalars', counters=counters)
+                                                    sync='full' if last else 'scalars', counters=counters)
+            if frames and not last:                    # a trajectory frame is due: positions only, the chains keep the state
+                due = [k for k, r in enumerate(self.replicas) if self._file_due(r, r._step + b)[1]]
+                if hasattr(self.resident, 'sync_positions'):
+                    self.resident.sync_positions(due)
+                else:
+                    self.resident.sync_host(due)
             self._ahead = b
             self.blocks += 1
         self._ahead -= 1

@@ -403,3 +403,25 @@ def test_install_routes_an_unmodified_run_call_through_the_device(tmp_path):
     finally:
         resident_gcmc.uninstall(original)
     assert 'run' not in GrandCanonicalEnsemble.__dict__ or GrandCanonicalEnsemble.run is original
+
+
+def test_run_with_the_reference_defaults_a_row_and_a_frame_every_step(tmp_path):
+    """``outfile_write_interval = trajectory_write_interval = 1`` (the reference's defaults): one launch per step, the
+    positions of every step come back for the frame while generators and the rest stay on the device; same files."""
+    from mcpy_b200.ensembles import ResidentGCMC
+    cfg = small_box(seed=31)
+
+    def make(tag):
+        g = box_gcmc(cfg, 'H', -1.8, seed=9)
+        g._outfile, g._traj_file = str(tmp_path / f'{tag}.out'), str(tmp_path / f'{tag}.xyz')
+        g._outfile_write_interval, g._trajectory_write_interval = 1, 1
+        return g
+    g_ref, g_dev = make('ref'), make('dev')
+    g_ref.run(35)
+    rg = ResidentGCMC(g_dev, lj=(cfg['epsilon'], cfg['sigma'], cfg['rc']))
+    rg.run(35)
+    assert_same_chain(g_ref, g_dev)
+    frames = [[ln for ln in open(tmp_path / f'{t}.xyz') if not ln.startswith('energy=')] for t in ('ref', 'dev')]
+    assert frames[0] == frames[1] and sum(1 for ln in frames[0] if ln.strip().isdigit()) == 37      # step 0 .. 35 + final
+    rows = [[ln.split()[:2] + ln.split()[3:] for ln in open(tmp_path / f'{t}.out') if ln[:1].isdigit()] for t in ('ref', 'dev')]
+    assert rows[0] == rows[1] and len(rows[0]) >= 36

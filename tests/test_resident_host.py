@@ -13,6 +13,7 @@ class HostChains:
     def __init__(self, ensembles, engine=None, lj=None, atom_capacity=None, cell_capacity=0):
         self.ensembles = list(ensembles)
         self.blocks = []
+        self.frames = []
         self.swaps = 0
 
     def advance(self, n_trials, sync='full', counters=True):
@@ -30,6 +31,9 @@ class HostChains:
 
     def sync_host(self, chains=None):
         pass
+
+    def sync_positions(self, chains=None):
+        self.frames.append((len(self.blocks) - 1, list(chains)))
 
     def close(self):
         pass
@@ -107,6 +111,6 @@ def test_block_planning_files_and_swaps_equal_the_reference_driver(kind, tmp_pat
     looks = sorted({s for s in range(38) if (s > 0 and s % 5 == 0) or s % 12 == 0 or (s + 1) % 7 == 0 or (s + 1) % 11 == 0} | {37})
     sizes = np.diff([-1] + looks).tolist()
     assert [b[0][0] // 2 for b in mine.resident.blocks] == sizes
-    # positions are needed where a frame is written and at the end; scalars suffice elsewhere
-    full = [s for s in looks if (s + 1) % 11 == 0 or s == 37]
-    assert [looks[k] for k, b in enumerate(mine.resident.blocks) if b[1] == 'full'] == full
+    # everything comes back at the end; where replica 1 writes a frame only its positions do; scalars suffice elsewhere
+    assert [looks[k] for k, b in enumerate(mine.resident.blocks) if b[1] == 'full'] == [37]
+    assert [(looks[k], chains) for k, chains in mine.resident.frames] == [(s, [1]) for s in looks if (s + 1) % 11 == 0 and s != 37]
