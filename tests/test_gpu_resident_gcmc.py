@@ -425,3 +425,26 @@ def test_run_with_the_reference_defaults_a_row_and_a_frame_every_step(tmp_path):
     assert frames[0] == frames[1] and sum(1 for ln in frames[0] if ln.strip().isdigit()) == 37      # step 0 .. 35 + final
     rows = [[ln.split()[:2] + ln.split()[3:] for ln in open(tmp_path / f'{t}.out') if ln[:1].isdigit()] for t in ('ref', 'dev')]
     assert rows[0] == rows[1] and len(rows[0]) >= 36
+
+
+def test_long_run_in_one_launch_equals_many_launches_with_full_hand_backs():
+    """120 000 trials of a 500-atom argon chain in ONE launch against the same trials in 120 launches with the whole state
+    handed back to the ensemble and uploaded again in between (generator states through ``setstate`` / ``getstate``,
+    configuration, cell lists rebuilt): the same chain to the bit, and its energy is the oracle's for the final
+    configuration (the running sum is re-summed on the device when its rounding bound says so)."""
+    from oracle import cfast
+    from mcpy_b200.ensembles import ResidentGCMC
+    cfg = synthetic.s1_argon()
+    lj = (cfg['epsilon'], cfg['sigma'], cfg['rc'])
+    a, b = box_gcmc(cfg, 'Ar', -0.085, seed=12), box_gcmc(cfg, 'Ar', -0.085, seed=12)
+    ra, rb = ResidentGCMC(a, lj=lj), ResidentGCMC(b, lj=lj)
+    ra.run_trials(120_000)
+    for _ in range(120):
+        rb.run_trials(1000)
+    assert len(a.atoms) == len(b.atoms) and np.array_equal(a.atoms.positions, b.atoms.positions)
+    assert gen_states(a) == gen_states(b)
+    assert a.move_selector.move_acceptance_total == b.move_selector.move_acceptance_total
+    assert sum(a.move_selector.move_acceptance_total) > 5000
+    e = cfast.lj_energy(a.atoms.positions, np.asarray(a.atoms.cell), a.atoms.pbc, cfg['sigma'], cfg['epsilon'], cfg['rc'])
+    for g in (a, b):
+        assert abs(g.E_old - e) <= 1e-10 * max(1.0, abs(e)), (g.E_old, e)
