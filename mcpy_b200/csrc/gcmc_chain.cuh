@@ -787,6 +787,8 @@ struct mcpyb_gcmc {
     GcDyn* d_dyn = nullptr;
     long long* d_ntr = nullptr;
     bool dirty = false;                   // host copies of chains / dyn are ahead of the device's (a swap)
+    long long* h_ntr = nullptr;           // page-locked staging of the trial counts and of the scalars coming back:
+    GcDyn* h_dyn = nullptr;               // true asynchronous copies, one synchronisation per run
     size_t smem = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
@@ -869,6 +871,8 @@ int mcpyb_gcmc_create(mcpyb_engine* e, int n_chains, const mcpyb_gcmc_desc* desc
     if (g->smem && cudaFuncSetAttribute(gcmc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem) != cudaSuccess)
         return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: shared memory opt-in of %zu bytes refused", g->smem));
     cudaEventCreate(&g->ev0); cudaEventCreate(&g->ev1);
+    if (cudaMallocHost(&g->h_ntr, sizeof(long long) * n_chains) != cudaSuccess || cudaMallocHost(&g->h_dyn, sizeof(GcDyn) * n_chains) != cudaSuccess)
+        return bail(e->fail(MCPYB_ERR_CUDA, "gcmc: cudaMallocHost"));
     *out = g;
     return MCPYB_OK;
 }
@@ -881,6 +885,8 @@ void mcpyb_gcmc_destroy(mcpyb_gcmc* g) {
     if (g->d_chains) cudaFree(g->d_chains);
     if (g->d_dyn) cudaFree(g->d_dyn);
     if (g->d_ntr) cudaFree(g->d_ntr);
+    if (g->h_ntr) cudaFreeHost(g->h_ntr);
+    if (g->h_dyn) cudaFreeHost(g->h_dyn);
     if (g->ev0) cudaEventDestroy(g->ev0);
     if (g->ev1) cudaEventDestroy(g->ev1);
     delete g;
@@ -988,13 +994,15 @@ int mcpyb_gcmc_run(mcpyb_gcmc* g, const int64_t* n_trials, int32_t* status_out) 
         CK(cudaMemcpyAsync(g->d_dyn, g->dyn.data(), sizeof(GcDyn) * g->n, cudaMemcpyHostToDevice, e->stream), "gcmc upload scalars");
         g->dirty = false;
     }
-    CK(cudaMemcpyAsync(g->d_ntr, n_trials, sizeof(long long) * g->n, cudaMemcpyHostToDevice, e->stream), "gcmc upload trial counts");
+    memcpy(g->h_ntr, n_trials, sizeof(long long) * g->n);
+    CK(cudaMemcpyAsync(g->d_ntr, g->h_ntr, sizeof(long long) * g->n, cudaMemcpyHostToDevice, e->stream), "gcmc upload trial counts");
     CK(cudaEventRecord(g->ev0, e->stream), "event");
     gcmc_chain_kernel<<<g->n, GC_THREADS, g->smem, e->stream>>>(g->d_chains, g->d_dyn, g->d_ntr);
     LAUNCH_CHECK("gcmc_chain_kernel");
     CK(cudaEventRecord(g->ev1, e->stream), "event");
-    CK(cudaMemcpyAsync(g->dyn.data(), g->d_dyn, sizeof(GcDyn) * g->n, cudaMemcpyDeviceToHost, e->stream), "gcmc download scalars");
+    CK(cudaMemcpyAsync(g->h_dyn, g->d_dyn, sizeof(GcDyn) * g->n, cudaMemcpyDeviceToHost, e->stream), "gcmc download scalars");
     CK(cudaStreamSynchronize(e->stream), "gcmc run");
+    memcpy(g->dyn.data(), g->h_dyn, sizeof(GcDyn) * g->n);
     cudaEventElapsedTime(&g->last_ms, g->ev0, g->ev1);
     g->launches++;
     if (status_out) for (int c = 0; c < g->n; ++c) status_out[c] = g->dyn[c].s.status;
