@@ -1,15 +1,24 @@
 // f2 -- device-resident GCMC chains: the loop of GrandCanonicalEnsemble.do_gcmc_step
 // (mcpy/ensembles/grand_canonical_ensemble.py:244-308) without a host round trip per trial.
 //
-// ONE CTA runs one Markov chain.  For the length of a launch the chain's whole state lives in the CTA's shared memory
-// (2 000 atoms: 61 KB of positions, 23 KB of cell lists, 12 KB of Mersenne-Twister states, ... ~115 KB of the 227 KB):
-//   px, py, pz [slot]      positions by storage slot (a slot is stable for the life of an atom)
-//   order [index]          atom index -> slot: the reference's atom order (del atoms[i] shifts it, insertion appends);
-//                          order[n..] holds the free slots
-//   cell_cnt / cell_slots  cell list of edge >= rc/2 with a fixed number of slots per cell
-//   mt [stream][625]       MT19937 states of random.Random: MoveSelector.rng, each move's rng, rng_acceptance
-// Thread 0 is the Markov chain (draws, proposal, acceptance, commit); the CTA is its energy evaluator: a quad of
-// lanes per stencil cell of each site, candidates by minimum image, the LJ pair sum folded in a fixed order.
+// ONE CTA (17 warps) runs one Markov chain.  For the length of a launch the chain's whole state image lives in the CTA's
+// shared memory (2 000 atoms with room for 4 000: 96 KB of positions, 24 KB of order / cell-of / unsettled lists, 23 KB
+// of cell lists, 25 KB of Mersenne-Twister states: 174 KB of the 227 KB; larger chains run from global memory):
+//   configuration part (moves with the configuration in a replica swap)
+//     px, py, pz [slot]      positions by storage slot (a slot is stable for the life of an atom)
+//     order [index]          atom index -> slot: the reference's atom order (del atoms[i] shifts it, insertion appends);
+//                            order[n..] holds the free slots
+//     cell_of, unstable, uflag   cell of a slot; the atoms whose last wrap() still changed them
+//     cell_cnt / cell_slots  cell list of edge >= rc/2 with a fixed number of slots per cell
+//   slot part (stays with the replica slot)
+//     mt  [stream][625]      MT19937 states of random.Random: MoveSelector.rng, each move's rng, rng_acceptance
+//     mt2 [stream][624]      the NEXT state of each stream, computed ahead by the whole CTA (gc_mt_refill)
+// Lane 0 of warp 0 is the Markov chain: the serial section (acceptance of trial t, commit, proposal t+1) and, while the
+// other 16 warps sum the rows of a trial, the look-ahead (the draws of the next proposal, the de Broglie factor and the
+// acceptance uniform of the running trial -- looked at, never consumed before their turn).  Warps 1..16 are the energy
+// evaluator: a quad of lanes per (site, stencil cell), candidates by minimum image, the LJ pair sum folded in a fixed
+// order.  O(N) commit work (order shift after a deletion, many-atom wrap, best-configuration copy) and the full energy
+// re-sum at the end of a launch are done by the whole CTA.
 //
 // What is restated, with the reference's draw order (the contract is an identical accept / reject sequence):
 //   MoveSelector.__get_index__ / do_trial_move           moves/move_selector.py:66-87
