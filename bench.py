@@ -625,6 +625,24 @@ def run_b200(args):
             cyc = one.cycles(0)
             one.sync_host()
             one.close()
+            # BASELINE config 1 as a sweep: one chain per SM, each at its own chemical potential, ONE launch per block
+            sweep = None
+            if rank == 0 and not args.no_extra:
+                n_ch = 148
+                sweep_mus = np.linspace(MU_LADDER[0], MU_LADDER[1], n_ch)
+                many = ResidentGCMC([factory(mu={'H': float(m)}, rank=k % R) for k, m in enumerate(sweep_mus)], engine=eng)
+                many.advance(300, sync='scalars', counters=False)
+                t0 = time.perf_counter()
+                many_ms = many.advance(args.resident_sweep_trials, sync='scalars', counters=False)
+                many_wall = time.perf_counter() - t0
+                many.sync_host()
+                sweep = {'chains': n_ch, 'trials_per_chain': args.resident_sweep_trials,
+                         'device_trials_per_s': n_ch * args.resident_sweep_trials / (1e-3 * many_ms),
+                         'wall_trials_per_s': n_ch * args.resident_sweep_trials / many_wall,
+                         'mean_atoms': float(np.mean([len(g.atoms) for g in many.ensembles])),
+                         'note': 'density-vs-mu sweep of the 2 000-atom LJ box (BASELINE configs[1]): 148 independent '
+                                 'GrandCanonicalEnsemble chains, a CTA (an SM) each'}
+                many.close()
             resident = {
                 'value': world * R * n_res / res_s, 'unit': 'replica trial-move dE evals/s (whole trials: proposal, dE, '
                                                              'acceptance, commit)',
@@ -645,6 +663,7 @@ def run_b200(args):
                                  'device_us_per_trial': 1e3 * one_ms / args.resident_chain_trials,
                                  'serial_share_of_cycles': cyc['serial'] / max(1, cyc['total']),
                                  'speedup_vs_dropin_calls': None},
+                'mu_sweep': sweep,
                 'api': 'ResidentReplicaExchange (subclass of the unmodified BatchedReplicaExchange): the unmodified '
                        'GrandCanonicalEnsemble replicas hand their state to one CTA each (csrc/gcmc_chain.cuh: MT19937 / '
                        'PCG64 draws, proposal, LJ dE, acceptance, wrap, commit on the device, bit-identical decisions), '
@@ -1097,6 +1116,7 @@ def main():
     ap.add_argument('--no-driver', action='store_true')
     ap.add_argument('--resident-steps', type=int, default=4000, help='steps of the device-resident replica-exchange run to time')
     ap.add_argument('--resident-chain-trials', type=int, default=50000, help='trials of the single device-resident chain')
+    ap.add_argument('--resident-sweep-trials', type=int, default=5000, help='trials per chain of the 148-chain mu sweep')
     ap.add_argument('--no-resident', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary EMT / free-volume numbers')
     args = ap.parse_args()
