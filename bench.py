@@ -774,6 +774,11 @@ def run_b200(args):
                                'announced by trial_sites_direct_kernel)',
                      'kernel_ms': rows_ms, 'kernel_share_of_sweep': rows_ms / sum(stage_ms.values()),
                      'algorithmic_flop_per_launch': alg_flop,
+                     'algorithmic_bytes_per_launch': int(sites * 48 + sites * 2 * 12 + R * N_ATOMS * 32),
+                     'traffic_note': 'site records in (48 B) + two partial sums per site out (12 B each) + the configurations; '
+                                     'the ncu figure (cold caches, serialised launches) adds the 35 MB of per-configuration '
+                                     'stencil lists, which stay in the 126 MB L2 between the launches of a live run; either '
+                                     'way DRAM runs at < 10 % of its peak under this FP64-bound kernel',
                      'step_achieved': alg_flop * SW / (ms_per_step * 1e-3) / 1e12,
                      'peak_source': 'measured here: DFMA microbenchmark (mcpyb_fp64_peak_tflops); '
                                     'MEASURED_PEAKS.json holds only HBM and bf16 figures',
