@@ -303,7 +303,6 @@ class ResidentGCMC:
         """Bring the ensembles fully up to date with their chains: configuration, the five Mersenne-Twister states and
         the cells' PCG64 states, the best configuration.  The ensembles own the state afterwards: whatever the host does
         to them (a block of the reference's own loop, a swap) is uploaded again before the next device block."""
-        from ase import Atoms
         for k in (range(len(self.ensembles)) if chains is None else chains):
             if self._host_fresh[k]:
                 continue
@@ -331,8 +330,10 @@ class ResidentGCMC:
                 cell._rng.bit_generator.state = st
             if s.best_n >= 0:
                 bn = int(s.best_n)
-                g._best_atoms = Atoms(numbers=np.full(bn, self._Z[k]), positions=best[:bn].copy(), cell=atoms.cell,
-                                      pbc=atoms.pbc)
+                ba = atoms.copy()                                      # cell, pbc, info ... as `atoms.copy()` in _record_minimum
+                ba.arrays = {'numbers': np.full(bn, self._Z[k], dtype=atoms.arrays['numbers'].dtype),
+                             'positions': best[:bn].copy()}
+                g._best_atoms = ba
             if self.resync_energy:
                 g.E_old = float(g.compute_energy(atoms))
             self._host_fresh[k] = True
