@@ -256,6 +256,14 @@ int mcpyb_box_free_volume_pcg64(mcpyb_engine* e, const uint64_t* state_hi_lo,
                                 const double* offset3, const double* shifts, int nshift,
                                 int64_t* counts_out);
 
+/* K10: `species AND inside` of SphericalCell.get_atoms_specie_inside_cell (mcpy/cell/spherical_cell.py:65-80) and of
+ * DomeCell's (mcpy/cell/dome_cell.py: the same with `z >= bottom_z`): mask_out[i] = numbers[i] in species_Z and
+ * |positions[i] - center|^2 <= radius_squared (numpy's arithmetic of einsum('ij,ij->i'): (dx^2 + dz^2) + dy^2, unfused)
+ * and, with clip_z, positions[i][2] >= bottom_z.  Host arrays in, one byte per atom out; the caller's np.where keeps
+ * the reference's index order.                                                                                   */
+int mcpyb_region_mask_host(mcpyb_engine* e, const double* positions, const int32_t* numbers, int n, const double* center3,
+                           double radius_squared, int clip_z, double bottom_z, const int32_t* species_Z, int n_species,
+                           uint8_t* mask_out);
 /* ---- min_insert test: replaces the distance loop of InsertionMove.do_trial_move
  *      (mcpy/moves/insertion_move.py:54-62) and MoleculeInsertionMove
  *      (molecule_insertion_move.py:61-72).  For each of C candidate points: the smallest

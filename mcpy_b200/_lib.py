@@ -34,7 +34,7 @@ SYMBOLS = [
     'mcpyb_gcmc_create', 'mcpyb_gcmc_destroy', 'mcpyb_gcmc_set_state', 'mcpyb_gcmc_get_state', 'mcpyb_gcmc_run',
     'mcpyb_gcmc_get_trace', 'mcpyb_gcmc_info', 'mcpyb_gcmc_last_run_ms', 'mcpyb_gcmc_get_scalars',
     'mcpyb_gcmc_swap_configurations', 'mcpyb_gcmc_cycles', 'mcpyb_gcmc_config_ptr', 'mcpyb_gcmc_set_config_scalars',
-    'mcpyb_gcmc_get_block_scalars',
+    'mcpyb_gcmc_get_block_scalars', 'mcpyb_region_mask_host',
 ]
 
 GCMC_MAX_MOVES = 8          # MCPYB_GCMC_MAX_MOVES
@@ -153,6 +153,7 @@ def load():
     lib.mcpyb_gcmc_config_ptr.argtypes = [_p, C.c_int, C.POINTER(_p), _i64p, _f64p]
     lib.mcpyb_gcmc_set_config_scalars.argtypes = [_p, C.c_int, _f64p]
     lib.mcpyb_gcmc_get_block_scalars.argtypes = [_p, _p, _p, _p, _p]
+    lib.mcpyb_region_mask_host.argtypes = [_p, _p, _p, C.c_int, _p, C.c_double, C.c_int, C.c_double, _p, C.c_int, _p]
     lib.mcpyb_gcmc_get_trace.argtypes = [_p, C.c_int, _p, C.c_int64, _i64p]
     lib.mcpyb_gcmc_info.argtypes = [_p, C.c_int, _p]
     lib.mcpyb_gcmc_last_run_ms.argtypes = [_p, _f64p]

@@ -59,9 +59,27 @@ class _B200CellMixin:
         return radii
 
     def _species_mask(self, atoms, specie):
+        return np.isin(np.asarray(atoms.numbers), self._species_numbers(specie))
+
+    @staticmethod
+    def _species_numbers(specie):
         from ase.data import atomic_numbers
         names = [specie] if isinstance(specie, str) else list(specie)
-        return np.isin(np.asarray(atoms.numbers), [atomic_numbers[s] for s in names if s in atomic_numbers])
+        return [atomic_numbers[s] for s in names if s in atomic_numbers]
+
+    # K10: from this many atoms on the `species AND inside` mask of the sphere / dome cells is taken on the device
+    # (below it numpy's O(N) pass is cheaper than a launch and two copies); same bits either way
+    mask_on_device_from = 4096
+
+    def _inside_sphere(self, atoms, specie, bottom_z=None):
+        if len(atoms) >= self.mask_on_device_from:
+            return np.where(self.engine.region_mask(atoms.positions, atoms.numbers, self.center, self.radius,
+                                                    self._species_numbers(specie), bottom_z=bottom_z))[0]
+        d = atoms.positions - self.center
+        mask = self._species_mask(atoms, specie) & (np.einsum('ij,ij->i', d, d) <= self.radius ** 2)
+        if bottom_z is not None:
+            mask &= atoms.positions[:, 2] >= bottom_z
+        return np.where(mask)[0]
 
 
 class B200SphericalCell(_B200CellMixin, SphericalCell):
@@ -75,8 +93,7 @@ class B200SphericalCell(_B200CellMixin, SphericalCell):
     def get_atoms_specie_inside_cell(self, atoms, specie):
         if len(atoms) == 0:
             return np.empty(0, dtype=int)
-        d = atoms.positions - self.center
-        return np.where(self._species_mask(atoms, specie) & (np.einsum('ij,ij->i', d, d) <= self.radius ** 2))[0]
+        return self._inside_sphere(atoms, specie)
 
     def calculate_volume(self, atoms):
         if len(atoms) == 0:
@@ -107,9 +124,7 @@ class B200DomeCell(_B200CellMixin, DomeCell):
     def get_atoms_specie_inside_cell(self, atoms, specie):
         if len(atoms) == 0:
             return np.empty(0, dtype=int)
-        d = atoms.positions - self.center
-        mask = self._species_mask(atoms, specie) & (np.einsum('ij,ij->i', d, d) <= self.radius ** 2)
-        return np.where(mask & (atoms.positions[:, 2] >= self.bottom_z))[0]
+        return self._inside_sphere(atoms, specie, bottom_z=self.bottom_z)
 
     def calculate_volume(self, atoms):
         n_atoms = len(atoms)

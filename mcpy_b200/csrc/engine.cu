@@ -293,6 +293,8 @@ struct mcpyb_engine {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev = nullptr;
     DevBuf<unsigned char> trial_dev;
+    DevBuf<unsigned char> mask_dev;          // K10 region mask: positions | numbers | species | mask, one block
+    PinBuf mask_pin;
     PinBuf trial_pin, trial_out_pin;
     DevBuf<double> dE;
     DevBuf<int> tpairs;
@@ -687,6 +689,7 @@ void mcpyb_destroy(mcpyb_engine* e) {
     e->exp_q.release(); e->exp_info.release(); e->exp_head.release(); e->exp_cursor.release();
     e->e_atom.release(); e->sigma1.release(); e->e_emb.release(); e->e_part.release(); e->deds.release(); e->forces.release(); e->cnt_part.release(); e->E.release(); e->pair_count.release();
     e->stage_dev.release(); e->stage_pin.release(); e->out_pin.release();
+    e->mask_dev.release(); e->mask_pin.release();
     e->trial_dev.release(); e->trial_pin.release(); e->trial_out_pin.release(); e->dE.release(); e->tpairs.release();
     e->tw_int.release(); e->tw_bins.release(); e->tw_pos.release(); e->tw_E.release(); e->tw_spos.release(); e->tw_meta.release(); e->tw_items.release(); e->tw_a.release(); e->tw_err.release(); e->tw_ovf.release(); e->tw_hist.release();
     e->nl_i.release(); e->nl_j.release(); e->nl_S.release(); e->nl_r2.release(); e->nl_cursor.release();
@@ -2671,6 +2674,53 @@ int mcpyb_min_dist2_host(mcpyb_engine* e, int rep, const double* points, int64_t
     CK(cudaMemcpyAsync(out_d2, d_out.p, (size_t)C * 8, cudaMemcpyDeviceToHost, e->stream), "D2H min d2");
     CK(cudaStreamSynchronize(e->stream), "sync min d2");
     d_pts.release(); d_out.release(); d_mask.release();
+    return MCPYB_OK;
+}
+
+// K10: `species AND inside` of SphericalCell / DomeCell.get_atoms_specie_inside_cell
+// (spherical_cell.py:65-80, dome_cell.py).  The inside test is numpy's, operation for operation:
+// diff = positions - center; einsum('ij,ij->i', diff, diff) sums (dx^2 + dz^2) + dy^2 (its unrolled pair + tail order,
+// no fused multiply-add); `<= radius ** 2`; DomeCell adds `z >= bottom_z`.
+__global__ void __launch_bounds__(256)
+region_mask_kernel(const double* __restrict__ pos, const int* __restrict__ Z, int n, double cx, double cy, double cz,
+                   double R2, int clip_z, double bottom_z, const int* __restrict__ species, int n_species,
+                   unsigned char* __restrict__ mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int z = Z[i];
+    bool wanted = false;
+    for (int k = 0; k < n_species; ++k) wanted |= species[k] == z;
+    const double x = pos[3 * i], y = pos[3 * i + 1], zz = pos[3 * i + 2];
+    const double dx = __dsub_rn(x, cx), dy = __dsub_rn(y, cy), dz = __dsub_rn(zz, cz);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz)), __dmul_rn(dy, dy));
+    mask[i] = (wanted && d2 <= R2 && (!clip_z || zz >= bottom_z)) ? 1 : 0;
+}
+
+int mcpyb_region_mask_host(mcpyb_engine* e, const double* positions, const int32_t* numbers, int n, const double* center3,
+                           double radius_squared, int clip_z, double bottom_z, const int32_t* species_Z, int n_species,
+                           uint8_t* mask_out) {
+    if (!e) return MCPYB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (n < 0 || n_species < 0 || n_species > 64 || !center3 || (n > 0 && (!positions || !numbers || !mask_out)) ||
+        (n_species > 0 && !species_Z))
+        return e->fail(MCPYB_ERR_ARG, "bad region-mask arguments");
+    if (n == 0) return MCPYB_OK;
+    // one device block and one page-locked block, kept with the engine: [positions 24 n | numbers 4 n | species | mask n]
+    const size_t o_Z = (size_t)24 * n, o_sp = o_Z + (size_t)4 * n, o_mask = o_sp + 4 * 64, bytes = o_mask + (size_t)n;
+    CK(e->mask_dev.reserve(bytes), "cudaMalloc region mask");
+    CK(e->mask_pin.reserve(bytes), "cudaMallocHost region mask");
+    unsigned char* h = e->mask_pin.p;
+    unsigned char* d = e->mask_dev.p;
+    memcpy(h, positions, (size_t)24 * n);
+    memcpy(h + o_Z, numbers, (size_t)4 * n);
+    if (n_species) memcpy(h + o_sp, species_Z, (size_t)4 * n_species);
+    CK(cudaMemcpyAsync(d, h, o_mask, cudaMemcpyHostToDevice, e->stream), "H2D region mask");
+    region_mask_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>((const double*)d, (const int*)(d + o_Z), n, center3[0], center3[1], center3[2],
+                                                                radius_squared, clip_z, bottom_z, (const int*)(d + o_sp), n_species, d + o_mask);
+    LAUNCH_CHECK("region_mask_kernel");
+    CK(cudaMemcpyAsync(h + o_mask, d + o_mask, (size_t)n, cudaMemcpyDeviceToHost, e->stream), "D2H mask");
+    CK(cudaStreamSynchronize(e->stream), "sync region mask");
+    memcpy(mask_out, h + o_mask, (size_t)n);
     return MCPYB_OK;
 }
 

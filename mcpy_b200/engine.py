@@ -545,6 +545,18 @@ class Engine:
         return int(counts[0]), int(counts[1])
 
     # -- min_insert distance test ---------------------------------------------------
+    def region_mask(self, positions, numbers, center, radius, species_Z, bottom_z=None) -> np.ndarray:
+        """K10: bool mask ``numbers in species_Z and |positions - center|^2 <= radius ** 2`` (and ``z >= bottom_z``):
+        the inside test of ``SphericalCell`` / ``DomeCell.get_atoms_specie_inside_cell`` with numpy's bits."""
+        pos, num = as_f64(positions).reshape(-1, 3), as_i32(numbers)
+        sp = as_i32(np.asarray(species_Z, dtype=np.int32).reshape(-1))
+        c = as_f64(np.asarray(center, dtype=np.float64).reshape(3))
+        out = np.empty(len(num), dtype=np.uint8)
+        self._check(self._lib.mcpyb_region_mask_host(self._h, ptr(pos), ptr(num), len(num), ptr(c), float(radius) ** 2,
+                                                     int(bottom_z is not None), float(bottom_z or 0.0), ptr(sp), len(sp),
+                                                     ptr(out)))
+        return out.view(np.bool_)
+
     def min_dist2(self, points, rep=0, mask=None) -> np.ndarray:
         """Smallest squared image distance from each point to the (masked) atoms of the
         resident replica ``rep`` within the cutoff; ``inf`` where no atom is that close."""

@@ -210,3 +210,52 @@ def test_dome_cell_matches_oracle_in_both_point_modes(fv_engine):
         trial += Atoms('O', positions=[p])
         trial += Atoms('O', positions=[below])
         assert list(cell.get_atoms_specie_inside_cell(trial, ['O'])) == [len(atoms)]
+
+
+def test_region_mask_kernel_equals_the_reference_cells_bit_for_bit():
+    """K10: ``species AND inside`` of the unmodified ``SphericalCell`` / ``DomeCell.get_atoms_specie_inside_cell`` against
+    the device mask, atoms placed on the sphere's surface to the ulp, below / on / above the dome's floor, three species."""
+    from ase import Atoms
+    from mcpy.cell import DomeCell, SphericalCell
+    from mcpy_b200.cell import B200DomeCell, B200SphericalCell
+    rng = np.random.default_rng(11)
+    n = 12000
+    core = Atoms('Ag40', positions=rng.uniform(8.0, 14.0, (40, 3)), cell=[40.0, 40.0, 40.0], pbc=False)
+    radii = {'Ag': 1.4, 'O': 0.7, 'C': 0.8}
+    ref = SphericalCell(core.copy(), 3.0, radii, mc_sample_points=10, seed=1)      # (construction translates its atoms in place)
+    mine = B200SphericalCell(core.copy(), 3.0, radii, mc_sample_points=10, seed=1)
+    assert ref.radius == mine.radius and np.array_equal(ref.center, mine.center)
+    c, R = np.asarray(ref.center, dtype=float), float(ref.radius)
+    pos = c + rng.uniform(-1.3 * R, 1.3 * R, (n, 3))
+    u = rng.standard_normal((3000, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    pos[:3000] = c + u * R                                            # on the surface, to rounding
+    for k in range(1, 4):                                             # ... and a few ulps to either side
+        pos[3000 * 0 + 500 * k:3000 * 0 + 500 * k + 250] = c + u[500 * k:500 * k + 250] * np.nextafter(R, np.inf)
+        pos[500 * k + 250:500 * k + 500] = c + u[500 * k + 250:500 * k + 500] * np.nextafter(R, 0.0)
+    numbers = rng.choice([47, 8, 6, 1], size=n)
+    atoms = Atoms(numbers=numbers, positions=pos, cell=[40.0, 40.0, 40.0], pbc=False)
+    assert len(atoms) >= mine.mask_on_device_from
+    for specie in ('O', ['O', 'C'], ['Ag', 'O', 'C'], 'Xx', []):
+        a, b = ref.get_atoms_specie_inside_cell(atoms, specie), mine.get_atoms_specie_inside_cell(atoms, specie)
+        assert a.dtype.kind == b.dtype.kind == 'i' and np.array_equal(a, b), specie
+    assert 2000 < len(ref.get_atoms_specie_inside_cell(atoms, ['Ag', 'O', 'C', 'H'])) < n
+    # the numpy path of the same class (small systems) gives the same indices as the device path
+    small = mine.mask_on_device_from
+    try:
+        type(mine).mask_on_device_from = 10 ** 9
+        assert np.array_equal(mine.get_atoms_specie_inside_cell(atoms, ['O', 'C']), ref.get_atoms_specie_inside_cell(atoms, ['O', 'C']))
+    finally:
+        type(mine).mask_on_device_from = small
+    dref = DomeCell(core.copy(), 'Ag', 10.5, 3.0, radii, mc_sample_points=10, seed=1)
+    dmine = B200DomeCell(core.copy(), 'Ag', 10.5, 3.0, radii, mc_sample_points=10, seed=1)
+    assert np.array_equal(dref.center, dmine.center) and dref.radius == dmine.radius
+    cd, Rd = np.asarray(dref.center, dtype=float), float(dref.radius)
+    pos2 = cd + rng.uniform(-1.2 * Rd, 1.2 * Rd, (n, 3))
+    pos2[:2000] = cd + u[:2000] * Rd                                  # on the ball's surface
+    pos2[4000:4400, 2] = dref.bottom_z                                # on the floor
+    pos2[4400:4800, 2] = np.nextafter(dref.bottom_z, -np.inf)         # one ulp below it
+    atoms2 = Atoms(numbers=numbers, positions=pos2, cell=[40.0, 40.0, 40.0], pbc=False)
+    assert 500 < len(dref.get_atoms_specie_inside_cell(atoms2, ['Ag', 'O', 'C', 'H'])) < n
+    for specie in ('O', ['Ag', 'O', 'C']):
+        assert np.array_equal(dref.get_atoms_specie_inside_cell(atoms2, specie), dmine.get_atoms_specie_inside_cell(atoms2, specie))
