@@ -103,8 +103,14 @@ class ResidentGCMC:
     ``lj``: ``(epsilon, sigma, rc)`` when the ensembles' calculator is not a ``B200Calculator('lj')``.
     ``atom_capacity``: atoms a chain may grow to (default: twice the current count, at least 256).
     ``trace``: keep one record per trial of the last :meth:`run_trials` (``mcpyb_gcmc_trial``), at most this many.
-    ``resync_energy``: after a block, replace the accumulated ``E_old`` by a full energy of the final configuration
-    through the ensemble's own calculator (one call per chain and block).
+    ``resync_energy``: at every full hand-back, replace the running ``E_old`` by a full energy of the configuration
+    through the ensemble's own calculator (the kernel already re-sums it on the device when its rounding bound asks).
+
+    :meth:`run_trials` / :meth:`advance` ``(n, sync='full')`` advance every chain and write the whole state back;
+    ``advance(n, sync='scalars')`` brings back only ``E_old``, ``n_atoms``, counters and minimum scores and leaves the chains
+    the owners of the state (host ``positions`` are NaN until :meth:`sync_host`, or :meth:`sync_positions` for a frame);
+    :meth:`run` is ``gcmc.run(steps)`` with one launch per block between file writes; :func:`install` routes
+    ``GrandCanonicalEnsemble.run`` here without a change to the calling script.
     """
 
     def __init__(self, ensembles, engine: Engine | None = None, lj=None, atom_capacity=None, cell_capacity=0,
