@@ -481,6 +481,9 @@ def run_b200(args):
     # (ctypes releases the GIL during the C-ABI calls).  Exchange attempts stay on the main thread between groups.
     e2e_db = None
     try:
+        if world > 1:
+            # informational arm with collectives inside: kept to the single-GPU run, where no rank can be left waiting
+            raise RuntimeError('measured at one GPU only')
         from concurrent.futures import ThreadPoolExecutor
         calc_b = B200Calculator('lj', epsilon=1.0, sigma=1.0, rc=RC, device=local)
         calcs = (calc, calc_b)
